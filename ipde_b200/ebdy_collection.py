@@ -1,0 +1,253 @@
+"""
+EmbeddedBoundaryCollection: several EmbeddedBoundary objects over one periodic
+background grid.
+
+API mirror of ipde/ebdy_collection.py:230-829: `register_grid` (:351-526),
+`generate_grid` (:279-339), `ready_bump` / `demean_function` (:796-810),
+`divide_pnai` / `v2l` / `v2r` (:541-563), `interpolate_grid_to_interface`
+(:578-614), `interpolate_radial_to_grid1` (:619-620), `grid_integral` /
+`volume_integral` (:814-829) and the attribute set the solvers and example
+scripts read (phys, ext, grid_step, in_annulus, phys_not_in_annulus, grid_phys,
+grid_pna, grid_pnai, radial_pts, grid_and_radial_pts, all_bvx/y, all_ivx/y,
+interfaces_x/y_transf, kx, ky, ikx, iky, lap, splitter, rsplitter, bumpy ...).
+
+Registration is setup work and stays in NumPy.  The per-solve members
+(interpolate_grid_to_interface, interpolate_radial_to_grid1, demean_function)
+are executed by the CUDA library (ipde_b200/device.py).
+"""
+import numpy as np
+from .geometry import PointSet, Grid
+from .near import points_inside_curve
+from .embedded_boundary import EmbeddedBoundary, LoadEmbeddedBoundary
+from .embedded_function import EmbeddedFunction, BoundaryFunction
+from .utilities import affine_transformation
+
+
+def LoadEmbeddedBoundaryCollection(d):
+    ebdy_list = [LoadEmbeddedBoundary(e) for e in d['ebdy_list']]
+    ebdyc = EmbeddedBoundaryCollection(ebdy_list)
+    if d['grid'] is not None:
+        ebdyc.register_grid(Grid(**d['grid']), danger_zone_distance=d['ddd'])
+    if d['bumpy'] is not None:
+        ebdyc.bumpy = d['bumpy']
+        ebdyc.bumpy_readied = True
+    return ebdyc
+
+
+class EmbeddedBoundaryCollection(object):
+    def __init__(self, ebdy_list):
+        self.ebdys = ebdy_list
+        self.N = len(self.ebdys)
+        self.registered_partitions = []
+        self.bumpy_readied = False
+        self.bump_location = None
+        self._device = None
+
+    def __iter__(self):
+        return (ebdy for ebdy in self.ebdys)
+    def __len__(self):
+        return len(self.ebdys)
+    def __getitem__(self, ind):
+        return self.ebdys[ind]
+
+    def save(self):
+        ebdy_list = [ebdy.save() for ebdy in self.ebdys]
+        if hasattr(self, 'grid'):
+            g = self.grid
+            grid = {'x_bounds': g.x_bounds, 'y_bounds': g.y_bounds, 'Nx': g.Nx, 'Ny': g.Ny,
+                    'mask': g.mask, 'x_endpoints': g.x_endpoints, 'y_endpoints': g.y_endpoints}
+            ddd = self.danger_zone_distance
+        else:
+            grid, ddd = None, None
+        return {'ebdy_list': ebdy_list, 'grid': grid,
+                'bumpy': self.bumpy if hasattr(self, 'bumpy') else None, 'ddd': ddd}
+
+    def generate_grid(self, h=None, Ns=None, force_square=False, danger_zone_distance=None):
+        """Auto-generate the background grid around the first (interior) boundary (:279-339)."""
+        iebdy = self[0]
+        if not iebdy.interior:
+            raise Exception('Generate grid may only be used if the first boundary is interior.')
+        ibdy = iebdy.bdy
+        cheat_space = iebdy.radial_width
+        xmin = ibdy.x.min() - cheat_space
+        ymin = ibdy.y.min() - cheat_space
+        xmax = ibdy.x.max() + 2*cheat_space
+        ymax = ibdy.y.max() + 2*cheat_space
+        self.bump_location = [ibdy.x.max() + cheat_space, ibdy.y.max() + cheat_space]
+        xran, yran = xmax - xmin, ymax - ymin
+        if h is None:
+            h = iebdy.radial_width/iebdy.M
+        if Ns is None:
+            Nx = 2*int(0.5*np.ceil(xran/h))
+            Ny = 2*int(0.5*np.ceil(yran/h))
+        else:
+            Nx, Ny = Ns
+            if xmin + Nx*h < xmin + xran:
+                raise Exception('Provided value of Nx is too small')
+            if ymin + Ny*h < ymin + yran:
+                raise Exception('Provided value of Ny is too small')
+        if force_square:
+            Nx = Ny = max(Nx, Ny)
+        grid = Grid([xmin, xmin + Nx*h], Nx, [ymin, ymin + Ny*h], Ny,
+                    x_endpoints=[True, False], y_endpoints=[True, False])
+        assert np.abs(grid.xh - h) < 1e-15, 'Gridspacing not what was requested'
+        assert np.abs(grid.yh - h) < 1e-15, 'Gridspacing not what was requested'
+        self.register_grid(grid, danger_zone_distance=danger_zone_distance)
+        self.bumpy_readied = False
+        return grid
+
+    def register_grid(self, grid, danger_zone_distance=None, verbose=False):
+        self.grid = grid
+        self.danger_zone_distance = danger_zone_distance
+        self._device = None
+        for ei, ebdy in enumerate(self):
+            if verbose:
+                print('Registering ebdy #', ei + 1, 'of', self.N)
+            ebdy.register_grid(grid, index=ei + 1,
+                               danger_zone_distance=danger_zone_distance, verbose=verbose)
+        # physical region: inside the interior boundary, outside every exterior one
+        phys = np.ones(grid.shape, dtype=bool)
+        for ebdy in self:
+            inside = points_inside_curve(ebdy.bdy, grid.xv, grid.yv, ebdy.near_curve_result)
+            phys = np.logical_and(phys, inside if ebdy.interior else np.logical_not(inside))
+        self.phys = phys
+        self.ext = np.logical_not(phys)
+        self.phys_inds = np.zeros(grid.shape, dtype=int)
+        self.phys_n = int(np.sum(phys))
+        self.phys_inds[phys] = np.arange(self.phys_n)
+
+        kxv = np.fft.fftfreq(grid.Nx, grid.xh/(2*np.pi))
+        kyv = np.fft.fftfreq(grid.Ny, grid.yh/(2*np.pi))
+        self.kx = kxv[:, None]
+        self.ky = kyv
+        self.ikx = 1j*self.kx
+        self.iky = 1j*self.ky
+        self.lap = -self.kx*self.kx - self.ky*self.ky
+
+        iax = np.concatenate([ebdy.grid_ia_xind for ebdy in self])
+        iay = np.concatenate([ebdy.grid_ia_yind for ebdy in self])
+        ia = np.zeros(grid.shape, dtype=bool)
+        ia[iax, iay] = True
+        self.in_annulus = ia
+        self.phys_not_in_annulus = np.logical_and(phys, np.logical_not(ia))
+        for ebdy in self:
+            ebdy.register_ia_inds(self.phys_inds)
+
+        self.grid_step = phys.astype(float)
+        for ebdy in self:
+            self.grid_step[ebdy.grid_ia_xind, ebdy.grid_ia_yind] *= ebdy.grid_to_radial_step
+
+        xg, yg = grid.xg, grid.yg
+        grid_phys_x, grid_phys_y = xg[phys], yg[phys]
+        self.grid_phys = PointSet(grid_phys_x, grid_phys_y)
+        self.radial_x = np.concatenate([ebdy.radial_x.ravel() for ebdy in self])
+        self.radial_y = np.concatenate([ebdy.radial_y.ravel() for ebdy in self])
+        self.radial_pts = PointSet(self.radial_x, self.radial_y)
+        self.grid_and_radial_pts = PointSet(np.concatenate([grid_phys_x, self.radial_x]),
+                                            np.concatenate([grid_phys_y, self.radial_y]))
+        grid_pna_x = xg[self.phys_not_in_annulus]
+        grid_pna_y = yg[self.phys_not_in_annulus]
+        self.grid_pna = PointSet(grid_pna_x, grid_pna_y)
+        self.grid_pna_num = self.grid_pna.N
+        self.pnar = PointSet(np.concatenate([grid_pna_x, self.radial_x]),
+                             np.concatenate([grid_pna_y, self.radial_y]))
+        self.all_bvx = np.concatenate([ebdy.bdy.x for ebdy in self])
+        self.all_bvy = np.concatenate([ebdy.bdy.y for ebdy in self])
+        self.all_bv = PointSet(self.all_bvx, self.all_bvy)
+        self.all_ivx = np.concatenate([ebdy.interface.x for ebdy in self])
+        self.all_ivy = np.concatenate([ebdy.interface.y for ebdy in self])
+        self.all_iv = PointSet(self.all_ivx, self.all_ivy)
+        self.exterior_x = xg[self.ext]
+        self.exterior_y = yg[self.ext]
+        self.exterior_targ = PointSet(self.exterior_x, self.exterior_y)
+        self.grid_pnai = PointSet(np.concatenate([grid_pna_x, self.all_ivx]),
+                                  np.concatenate([grid_pna_y, self.all_ivy]))
+
+        self.bdy_Ns = [ebdy.bdy.N for ebdy in self]
+        self.cumsum_bdy_Ns = np.cumsum(self.bdy_Ns)
+        self.splitter = self.cumsum_bdy_Ns[:-1]
+        self.radial_Ns = [ebdy.bdy.N*ebdy.M for ebdy in self]
+        self.cumsum_radial_Ns = np.cumsum(self.radial_Ns)
+        self.rsplitter = self.cumsum_radial_Ns[:-1]
+        self.interfaces_x_transf = np.concatenate([ebdy.interface_x_transf for ebdy in self])
+        self.interfaces_y_transf = np.concatenate([ebdy.interface_y_transf for ebdy in self])
+        self.grid_dof = self.grid_phys.N
+        self.radial_dof_list = [int(np.prod(ebdy.radial_shape)) for ebdy in self]
+        self.radial_dof = int(np.sum(self.radial_dof_list))
+        self.dof = self.grid_dof + self.radial_dof
+
+    ############################################################################
+    def divide_grid_and_radial(self, v):
+        g, w = np.split(v, [self.grid_phys.N])
+        return g, self.v2r(w)
+    def divide_pnai(self, v):
+        g, w = np.split(v, [self.grid_pna.N])
+        return g, self.v2l(w)
+    def v2l(self, v):
+        return np.split(v, self.splitter)
+    def v2l2(self, v):
+        return np.split(v, self.splitter*2)
+    def v2l_vector(self, v):
+        return np.split(v, self.splitter, axis=1)
+    def v2r(self, v):
+        return [L.reshape(ebdy.radial_x.shape) for L, ebdy in zip(np.split(v, self.rsplitter), self.ebdys)]
+
+    ############################################################################
+    @property
+    def device(self):
+        """Device-resident copy of the registered geometry (built on first use)."""
+        if self._device is None:
+            from .device import DeviceCollection
+            self._device = DeviceCollection(self)
+        return self._device
+
+    def interpolate_radial_to_boundary(self, f):
+        out = BoundaryFunction(self)
+        out.load_data([ebdy.interpolate_radial_to_boundary(fr) for ebdy, fr in zip(self.ebdys, f)])
+        return out
+
+    def interpolate_grid_to_interface(self, f, order=3, cutoff=None):
+        """
+        Interpolate a grid function to all interface points (:578-614): order 1..7 =
+        periodic piecewise polynomial, np.inf = trigonometric (type-2 NUFFT).  Runs
+        on the device.
+        """
+        if type(f) == EmbeddedFunction:
+            f = f.get_grid_value()
+        if cutoff is None:
+            cutoff = order == np.inf
+        fc = f*self.grid_step if cutoff else f
+        return self.device.interpolate_grid_to_interface(fc, order)
+
+    def interpolate_radial_to_grid1(self, fr_list, f=None):
+        return [ebdy.interpolate_radial_to_grid1(fr, f) for ebdy, fr in zip(self.ebdys, fr_list)]
+    def update_radial_to_grid1(self, f):
+        _ = self.interpolate_radial_to_grid1(f.get_radial_value_list(), f['grid'])
+
+    ############################################################################
+    def ready_bump(self, bump, bump_loc=None, bump_width=None):
+        if bump_width is None:
+            bump_width = self[0].radial_width
+        if bump_loc is None:
+            if self.bump_location is None:
+                raise Exception('if ebdyc has no bump_location, need to give bump_loc')
+            bump_loc = self.bump_location
+        grr = np.hypot(self.grid.xg - bump_loc[0], self.grid.yg - bump_loc[1])
+        bumpy = bump(affine_transformation(grr, 0, bump_width, 0, 1))
+        self.bumpy = bumpy/self.grid_integral(bumpy)
+        self.bumpy_readied = True
+        self._device = None
+
+    def demean_function(self, f):
+        return f - self.grid_integral(f)*self.bumpy
+
+    def grid_integral(self, f):
+        return np.sum(f)*self.grid.xh*self.grid.yh
+
+    def volume_integral(self, f):
+        if f.ebdyc() is not self:
+            raise Exception('EmbeddedFunction must be defined over this EmbeddedBoundaryCollection.')
+        integral = self.grid_integral(f.get_smoothed_grid_value())
+        for fr, ebdy in zip(f, self):
+            integral += ebdy.radial_integral(fr)
+        return integral
