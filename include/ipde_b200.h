@@ -1,0 +1,140 @@
+/*
+ * libipde_b200 -- C ABI of the B200-native (sm_100a, FP64) kernels behind ipde's
+ * inhomogeneous-solve hot path.
+ *
+ * The reference (dbstein/ipde) is pure Python; it has no FFI for this path.  The seams at
+ * which native code sits in the reference -- and which these entry points replace -- are
+ * cited per function as `reference file:line`.  Callers: the Python solver classes in
+ * ipde_b200/solvers (ctypes, see ipde_b200/_lib.py); INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, nonzero on error; ipde_last_error() gives the text;
+ *   - all array pointers are DEVICE pointers owned by the caller unless marked `host`;
+ *   - complex data is interleaved (re, im) doubles; sizes are int64_t; `stream` is a cudaStream_t;
+ *   - plans are opaque handles created/destroyed by the library; a plan is not thread-safe,
+ *     different plans may be used from different threads;
+ *   - grids are (nx, ny) row-major with x the slow index (numpy meshgrid indexing='ij').
+ */
+#ifndef IPDE_B200_H
+#define IPDE_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IPDE_KIND_POISSON 0
+#define IPDE_KIND_MODHELM 1
+#define IPDE_KIND_STOKES 2
+
+const char* ipde_last_error(void);
+int ipde_version(void);
+int ipde_device_sm_count(void);
+
+/* ---- 1-D FFT (batched, contiguous lines).  Replaces numpy.fft.fft / ifft, ipde/utilities.py:5-12. */
+int ipde_fft_plan_create(int n, void** plan);
+int ipde_fft_plan_destroy(void* plan);
+int ipde_fft_next_size(int n);                 /* smallest even 2^a 3^b 5^c >= n */
+int ipde_fft_size_supported(int n);
+int ipde_fft_c2c(void* plan, const double* in, double* out, int64_t batch, int sign, double scale, void* stream);
+/* out = FFT(m * IFFT(in)), rows of length n: ipde/utilities.py:123-124 (ffourier_multiply) */
+int ipde_fft_mul_fft(void* plan, const double* in, double* out, const double* m, int64_t batch, void* stream);
+
+/* ---- periodic background grid ------------------------------------------------------------------ */
+int ipde_grid_plan_create(int nx, int ny, double xh, double yh, void** plan);
+int ipde_grid_plan_destroy(void* plan);
+/* row layout of a half spectrum: frequency index k1 + n1*k2 is stored at row n2*k1 + k2 (n2 == 1: natural) */
+int ipde_grid_plan_layout(void* plan, int* n1, int* n2);
+/* fc = zeros(nx,ny); fc[phys_lin[i]] = f_compact[i]*step_compact[i]
+ * EmbeddedFunction.get_components / get_smoothed_grid_value, ipde/embedded_function.py:135-138,184-194 */
+int ipde_grid_scatter_cutoff(void* plan, const double* f_compact, const int64_t* phys_lin,
+                             const double* step_compact, int64_t n_phys, double* fc, void* stream);
+/* f -= (h^2 sum f) * bumpy : ebdyc.demean_function, ipde/ebdy_collection.py:808-816 */
+int ipde_grid_demean(void* plan, double* f, const double* bumpy, void* stream);
+/* real (nx,ny) <-> half spectrum (nx, ny/2+1): numpy.fft.fft2 / ifft2(.).real of a real field */
+int ipde_grid_fft2_r2c(void* plan, const double* real_in, double* spec, void* stream);
+int ipde_grid_fft2_c2r(void* plan, const double* spec_in, double* spec_work, double* real_out, void* stream);
+/* spec *= 1/(k^2 + kx^2 + ky^2) (MODHELM) or 1/(-kx^2-ky^2), zero mode -> 0 (POISSON)
+ * ipde/solvers/multi_boundary/modified_helmholtz.py:43-46, poisson.py:34-38 */
+int ipde_grid_scalar_multiply(void* plan, double* spec, int kind, double k, void* stream);
+/* the whole `_grid_solve`: (demean) -> fft2 -> multiplier -> ifft2.real ; uch is kept for the
+ * spectral interface interpolation.  modified_helmholtz.py:40-42, poisson.py:30-33 */
+int ipde_grid_solve_scalar(void* plan, int kind, double k, double* fc, const double* bumpy, double* uch,
+                           double* spec_work, double* uc, void* stream);
+/* Stokes `_grid_solve`, ipde/solvers/multi_boundary/stokes.py:34-45: specs of u, v, p are returned too */
+int ipde_grid_solve_stokes(void* plan, double* fuc, double* fvc, const double* bumpy, double* uh, double* vh,
+                           double* ph, double* spec_work, double* uc, double* vc, double* pc, void* stream);
+/* 4th-order centred differences, zero in the 2-cell border: ipde/derivatives.py:3-23 */
+int ipde_grid_fd4(void* plan, const double* f, double* fx, double* fy, void* stream);
+/* periodic cubic interpolation to points: fast_interp.interp2d(k=3) at ipde/ebdy_collection.py:594-603 */
+int ipde_grid_interp_cubic(void* plan, const double* f, double x0, double y0, const double* px, const double* py,
+                           int64_t npts, double* out, void* stream);
+/* out[i] = uc[lin[i]] ; out[pos[i]] += v[i] ; out[pos[i]] = v[i]
+ * uc[pna] += gu, radial overwrite, uc*=phys, EmbeddedFunction.load_data: multi_boundary/scalar.py:107-116 */
+int ipde_grid_gather(const double* uc, const int64_t* lin, int64_t n, double* out, void* stream);
+int ipde_index_add(double* out, const int64_t* pos, const double* v, int64_t n, void* stream);
+int ipde_index_set(double* out, const int64_t* pos, const double* v, int64_t n, void* stream);
+
+/* ---- type-2 nonuniform FFT: periodic_interp2d / finufft.nufft2d2(eps=1e-14), scalar.py:80-88,
+ *      ebdy_collection.py:604-614.  px_host/py_host: deconvolution factors (host arrays). */
+int ipde_nufft2_plan_create(int nx, int ny, double xh, double yh, int fx, int fy, int w, double beta,
+                            const double* px_host, const double* py_host, void** plan);
+int ipde_nufft2_plan_destroy(void* plan);
+/* out_j = Re (1/(nx ny)) sum_k spec[k] (i kx)^dx (i ky)^dy e^{i k.x_j}; (cn1, cn2) = row layout of spec */
+int ipde_nufft2_apply(void* plan, const double* spec, int cn1, int cn2, int dx, int dy, const double* x,
+                      const double* y, int64_t npts, double* out, void* stream);
+
+/* ---- radial block -> points: ebdy.interpolate_radial_to_points, ipde/embedded_boundary.py:419-443 */
+int ipde_nufft1_plan_create(int n, int fn, int w, double beta, const double* dec_host, void** plan);
+int ipde_nufft1_plan_destroy(void* plan);
+int ipde_radial_to_points(void* plan, const double* cmat, int M, const double* fr, double* coef_work,
+                          const double* theta, const double* t, int64_t npts, double* out,
+                          const int64_t* out_pos, void* stream);
+
+/* ---- annular solver: AnnularModifiedHelmholtzSolver / AnnularPoissonSolver,
+ *      ipde/annular/modified_helmholtz.py:90-203, ipde/annular/poisson.py:3-21.  All setup arrays host. */
+int ipde_annular_plan_create(int n, int M, double k, const double* D01, const double* D12, const double* R01,
+                             const double* R12, const double* R02, const double* ibc, const double* obc,
+                             const double* ks, const double* psi1, const double* ipsi1, const double* ipsi2,
+                             const double* kinv_mode_minor, void** plan);
+int ipde_annular_plan_destroy(void* plan);
+int ipde_annular_apply(void* plan, const double* in, double* out, void* stream);     /* _apply,  :172-186 */
+int ipde_annular_precond(void* plan, const double* in, double* out, void* stream);   /* _optim_preconditioner, :157-159 */
+/* solve(RAG, f, ig, og, tol, restart, maxiter): :187-203.  f_sign = -1 for Poisson. iters/relres: host */
+int ipde_annular_solve(void* plan, const double* f, const double* ig, const double* og, double f_sign,
+                       double tol, int restart, int maxiter, double* u_out, int* iters, double* relres,
+                       void* stream);
+
+/* ---- layer potentials from point sources: pybie2d *_Layer_Apply / pyfmmlib2d.SFMM,
+ *      ipde/solvers/internals/poisson.py:34-35, modified_helmholtz.py:37, stokes.py:26-35 */
+int ipde_set_k0_table(const double* cheb_host, int ncheb);
+int ipde_eval_k0(const double* x, double* out, int64_t n, void* stream);
+int ipde_layer_apply_scalar(int kind, double k, const double* sx, const double* sy, const double* q,
+                            int64_t nsrc, const double* tx, const double* ty, int64_t ntrg, double* out,
+                            int accumulate, void* stream);
+int ipde_layer_apply_stokes(const double* sx, const double* sy, const double* fx, const double* fy,
+                            int64_t nsrc, const double* tx, const double* ty, int64_t ntrg, double* out_uvp,
+                            int accumulate, void* stream);
+
+/* ---- dense / sparse helpers ----------------------------------------------------------------- */
+int ipde_dense_gemv(const double* A, const double* x, double* y, int64_t m, int64_t n, void* stream);
+int ipde_lu_solve(const double* LU, const int* perm, const double* b, double* x, int M, void* stream);
+/* ipde/sparse_matvec.py:17-40 (zSpMV_viaMKL) and :43-108 (dSpMV_viaMKL) */
+int ipde_csr_spmv_d(const int* indptr, const int* indices, const double* data, const double* x, double* y,
+                    int64_t nrows, void* stream);
+int ipde_csr_spmv_z(const int* indptr, const int* indices, const double* data, const double* x, double* y,
+                    int64_t nrows, void* stream);
+int ipde_vec_axpby(double a, const double* x, double b, const double* y, double* out, int64_t n, void* stream);
+int ipde_vec_mul(const double* x, const double* y, double* out, int64_t n, void* stream);
+/* (1 x M) row . (M, n) block: get_boundary_values etc., ipde/solvers/internals/scalar.py:48-67 */
+int ipde_rowvec_apply(const double* row, const double* fr, double* out, int M, int64_t n, void* stream);
+/* interface jumps of ScalarHelper.__call__, ipde/solvers/internals/scalar.py:73-85: tau = [slp | dlp] */
+int ipde_scalar_jumps(const double* bv, const double* bx, const double* by, const double* nx, const double* ny,
+                      const double* ur, const double* in_est, int M, int64_t n, double sign, double* tau,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,213 @@
+// extern "C" surface of libipde_b200.so (declared in include/ipde_b200.h).
+#include "../../include/ipde_b200.h"
+#include "annular.cuh"
+#include "dense.cuh"
+#include "fft.cuh"
+#include "grid.cuh"
+#include "layer.cuh"
+#include "nufft.cuh"
+#include "radial.cuh"
+#include <cstdarg>
+#include <mutex>
+
+static thread_local char g_err[1024] = "";
+
+void ipde_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+#define ST(s) ((cudaStream_t)(s))
+#define CP(p) (reinterpret_cast<const cplx*>(p))
+#define MP(p) (reinterpret_cast<cplx*>(p))
+
+extern "C" {
+
+const char* ipde_last_error(void) { return g_err; }
+int ipde_version(void) { return 100; }
+int ipde_device_sm_count(void) { return ipde_num_sms(); }
+
+// ---- FFT
+int ipde_fft_plan_create(int n, void** plan) {
+    FftPlan* p = nullptr;
+    int rc = fft_plan_create(n, &p);
+    *plan = p;
+    return rc;
+}
+int ipde_fft_plan_destroy(void* plan) { fft_plan_destroy((FftPlan*)plan); return IPDE_OK; }
+int ipde_fft_next_size(int n) { return fft_next_size(n); }
+int ipde_fft_size_supported(int n) { return fft_size_supported(n) ? 1 : 0; }
+int ipde_fft_c2c(void* plan, const double* in, double* out, int64_t batch, int sign, double scale, void* stream) {
+    FftPlan* p = (FftPlan*)plan;
+    return fft_rows(p, CP(in), MP(out), batch, p->d.n, p->d.n, sign, scale, ST(stream));
+}
+int ipde_fft_mul_fft(void* plan, const double* in, double* out, const double* m, int64_t batch, void* stream) {
+    return fft_mul_fft_rows((FftPlan*)plan, CP(in), MP(out), m, batch, ST(stream));
+}
+
+// ---- grid
+int ipde_grid_plan_create(int nx, int ny, double xh, double yh, void** plan) {
+    GridPlan* g = nullptr;
+    int rc = grid_plan_create(nx, ny, xh, yh, &g);
+    *plan = g;
+    return rc;
+}
+int ipde_grid_plan_destroy(void* plan) { grid_plan_destroy((GridPlan*)plan); return IPDE_OK; }
+int ipde_grid_plan_layout(void* plan, int* n1, int* n2) {
+    GridPlan* g = (GridPlan*)plan;
+    *n1 = g->n1; *n2 = g->n2;
+    return IPDE_OK;
+}
+int ipde_grid_scatter_cutoff(void* plan, const double* f_compact, const int64_t* phys_lin, const double* step_compact,
+                             int64_t n_phys, double* fc, void* stream) {
+    return grid_scatter_cutoff((GridPlan*)plan, f_compact, phys_lin, step_compact, n_phys, fc, ST(stream));
+}
+int ipde_grid_demean(void* plan, double* f, const double* bumpy, void* stream) {
+    return grid_demean((GridPlan*)plan, f, bumpy, ST(stream));
+}
+int ipde_grid_fft2_r2c(void* plan, const double* real_in, double* spec, void* stream) {
+    return grid_fft2_forward((GridPlan*)plan, real_in, MP(spec), ST(stream));
+}
+int ipde_grid_fft2_c2r(void* plan, const double* spec_in, double* spec_work, double* real_out, void* stream) {
+    return grid_fft2_inverse((GridPlan*)plan, CP(spec_in), MP(spec_work), real_out, ST(stream));
+}
+int ipde_grid_scalar_multiply(void* plan, double* spec, int kind, double k, void* stream) {
+    return grid_scalar_multiply((GridPlan*)plan, MP(spec), kind, k, ST(stream));
+}
+int ipde_grid_solve_scalar(void* plan, int kind, double k, double* fc, const double* bumpy, double* uch, double* spec_work,
+                           double* uc, void* stream) {
+    GridPlan* g = (GridPlan*)plan;
+    int rc = IPDE_OK;
+    if (kind == IPDE_KIND_POISSON) {
+        ARG_CHECK(bumpy != nullptr, "Poisson grid solve needs the bump array (ebdyc.ready_bump)");
+        rc = grid_demean(g, fc, bumpy, ST(stream));
+        if (rc) return rc;
+    }
+    rc = grid_fft2_forward(g, fc, MP(uch), ST(stream));
+    if (rc) return rc;
+    rc = grid_scalar_multiply(g, MP(uch), kind, k, ST(stream));
+    if (rc) return rc;
+    return grid_fft2_inverse(g, CP(uch), MP(spec_work), uc, ST(stream));
+}
+int ipde_grid_solve_stokes(void* plan, double* fuc, double* fvc, const double* bumpy, double* uh, double* vh, double* ph,
+                           double* spec_work, double* uc, double* vc, double* pc, void* stream) {
+    GridPlan* g = (GridPlan*)plan;
+    ARG_CHECK(bumpy != nullptr, "Stokes grid solve needs the bump array (ebdyc.ready_bump)");
+    int rc = grid_demean(g, fuc, bumpy, ST(stream));
+    if (!rc) rc = grid_demean(g, fvc, bumpy, ST(stream));
+    if (!rc) rc = grid_fft2_forward(g, fuc, MP(uh), ST(stream));
+    if (!rc) rc = grid_fft2_forward(g, fvc, MP(vh), ST(stream));
+    if (!rc) rc = grid_stokes_multiply(g, MP(uh), MP(vh), MP(ph), ST(stream));
+    if (!rc) rc = grid_fft2_inverse(g, CP(uh), MP(spec_work), uc, ST(stream));
+    if (!rc) rc = grid_fft2_inverse(g, CP(vh), MP(spec_work), vc, ST(stream));
+    if (!rc) rc = grid_fft2_inverse(g, CP(ph), MP(spec_work), pc, ST(stream));
+    return rc;
+}
+int ipde_grid_fd4(void* plan, const double* f, double* fx, double* fy, void* stream) {
+    return grid_fd4((GridPlan*)plan, f, fx, fy, ST(stream));
+}
+int ipde_grid_interp_cubic(void* plan, const double* f, double x0, double y0, const double* px, const double* py,
+                           int64_t npts, double* out, void* stream) {
+    return grid_interp_cubic((GridPlan*)plan, f, x0, y0, px, py, npts, out, ST(stream));
+}
+int ipde_grid_gather(const double* uc, const int64_t* lin, int64_t n, double* out, void* stream) {
+    return grid_gather(uc, lin, n, out, ST(stream));
+}
+int ipde_index_add(double* out, const int64_t* pos, const double* v, int64_t n, void* stream) {
+    return grid_index_add(out, pos, v, n, ST(stream));
+}
+int ipde_index_set(double* out, const int64_t* pos, const double* v, int64_t n, void* stream) {
+    return grid_index_set(out, pos, v, n, ST(stream));
+}
+
+// ---- NUFFT
+int ipde_nufft2_plan_create(int nx, int ny, double xh, double yh, int fx, int fy, int w, double beta,
+                            const double* px_host, const double* py_host, void** plan) {
+    Nufft2Plan* p = nullptr;
+    int rc = nufft2_plan_create(nx, ny, xh, yh, fx, fy, w, beta, px_host, py_host, &p);
+    *plan = p;
+    return rc;
+}
+int ipde_nufft2_plan_destroy(void* plan) { nufft2_plan_destroy((Nufft2Plan*)plan); return IPDE_OK; }
+int ipde_nufft2_apply(void* plan, const double* spec, int cn1, int cn2, int dx, int dy, const double* x, const double* y,
+                      int64_t npts, double* out, void* stream) {
+    return nufft2_apply((Nufft2Plan*)plan, CP(spec), cn1, cn2, dx, dy, x, y, npts, out, ST(stream));
+}
+int ipde_nufft1_plan_create(int n, int fn, int w, double beta, const double* dec_host, void** plan) {
+    Nufft1Plan* p = nullptr;
+    int rc = nufft1_plan_create(n, fn, w, beta, dec_host, &p);
+    *plan = p;
+    return rc;
+}
+int ipde_nufft1_plan_destroy(void* plan) { nufft1_plan_destroy((Nufft1Plan*)plan); return IPDE_OK; }
+int ipde_radial_to_points(void* plan, const double* cmat, int M, const double* fr, double* coef_work, const double* theta,
+                          const double* t, int64_t npts, double* out, const int64_t* out_pos, void* stream) {
+    return radial_to_points((Nufft1Plan*)plan, cmat, M, fr, coef_work, theta, t, npts, out, out_pos, ST(stream));
+}
+
+// ---- annular
+int ipde_annular_plan_create(int n, int M, double k, const double* D01, const double* D12, const double* R01,
+                             const double* R12, const double* R02, const double* ibc, const double* obc, const double* ks,
+                             const double* psi1, const double* ipsi1, const double* ipsi2, const double* kinv_mode_minor,
+                             void** plan) {
+    AnnularPlan* p = nullptr;
+    int rc = annular_plan_create(n, M, k, D01, D12, R01, R12, R02, ibc, obc, ks, psi1, ipsi1, ipsi2, kinv_mode_minor, &p);
+    *plan = p;
+    return rc;
+}
+int ipde_annular_plan_destroy(void* plan) { annular_plan_destroy((AnnularPlan*)plan); return IPDE_OK; }
+int ipde_annular_apply(void* plan, const double* in, double* out, void* stream) {
+    return annular_apply((AnnularPlan*)plan, CP(in), MP(out), ST(stream));
+}
+int ipde_annular_precond(void* plan, const double* in, double* out, void* stream) {
+    return annular_precond((AnnularPlan*)plan, CP(in), MP(out), ST(stream));
+}
+int ipde_annular_solve(void* plan, const double* f, const double* ig, const double* og, double f_sign, double tol,
+                       int restart, int maxiter, double* u_out, int* iters, double* relres, void* stream) {
+    return annular_solve((AnnularPlan*)plan, f, ig, og, f_sign, tol, restart, maxiter, u_out, iters, relres, ST(stream));
+}
+
+// ---- layer potentials
+int ipde_set_k0_table(const double* cheb_host, int ncheb) { return layer_set_k0_table(cheb_host, ncheb); }
+int ipde_eval_k0(const double* x, double* out, int64_t n, void* stream) { return layer_eval_k0(x, out, n, ST(stream)); }
+int ipde_layer_apply_scalar(int kind, double k, const double* sx, const double* sy, const double* q, int64_t nsrc,
+                            const double* tx, const double* ty, int64_t ntrg, double* out, int accumulate, void* stream) {
+    return layer_apply_scalar(kind, k, sx, sy, q, nsrc, tx, ty, ntrg, out, accumulate, ST(stream));
+}
+int ipde_layer_apply_stokes(const double* sx, const double* sy, const double* fx, const double* fy, int64_t nsrc,
+                            const double* tx, const double* ty, int64_t ntrg, double* out_uvp, int accumulate, void* stream) {
+    return layer_apply_stokes(sx, sy, fx, fy, nsrc, tx, ty, ntrg, out_uvp, accumulate, ST(stream));
+}
+
+// ---- dense / sparse
+int ipde_dense_gemv(const double* A, const double* x, double* y, int64_t m, int64_t n, void* stream) {
+    return dense_gemv(A, x, y, m, n, ST(stream));
+}
+int ipde_lu_solve(const double* LU, const int* perm, const double* b, double* x, int M, void* stream) {
+    return dense_lu_solve(LU, perm, b, x, M, ST(stream));
+}
+int ipde_csr_spmv_d(const int* indptr, const int* indices, const double* data, const double* x, double* y, int64_t nrows,
+                    void* stream) {
+    return csr_spmv_d(indptr, indices, data, x, y, nrows, ST(stream));
+}
+int ipde_csr_spmv_z(const int* indptr, const int* indices, const double* data, const double* x, double* y, int64_t nrows,
+                    void* stream) {
+    return csr_spmv_z(indptr, indices, CP(data), CP(x), MP(y), nrows, ST(stream));
+}
+int ipde_vec_axpby(double a, const double* x, double b, const double* y, double* out, int64_t n, void* stream) {
+    return vec_axpby(a, x, b, y, out, n, ST(stream));
+}
+int ipde_vec_mul(const double* x, const double* y, double* out, int64_t n, void* stream) {
+    return vec_mul(x, y, out, n, ST(stream));
+}
+int ipde_rowvec_apply(const double* row, const double* fr, double* out, int M, int64_t n, void* stream) {
+    return rowvec_apply(row, fr, out, M, n, ST(stream));
+}
+int ipde_scalar_jumps(const double* bv, const double* bx, const double* by, const double* nx, const double* ny,
+                      const double* ur, const double* in_est, int M, int64_t n, double sign, double* tau, void* stream) {
+    return scalar_jumps(bv, bx, by, nx, ny, ur, in_est, M, n, sign, tau, ST(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,263 @@
+// Dense and sparse linear-algebra kernels used per solve:
+//   * row-major GEMV (QFS boundary->check operators; reference: qfs package, applied at
+//     ipde/solvers/internals/scalar.py:87-88)
+//   * LU substitution with the factors of the check<-source matrix (two-step QFS apply and u2s,
+//     internals/scalar.py:106), blocked, one cooperative kernel per triangular factor
+//   * CSR SpMV, warp per row (reference ipde/sparse_matvec.py:17-113, MKL mkl_cspblas_{z,d}csrgemv)
+//   * small fused vector helpers for the per-boundary glue of ScalarHelper.__call__ (internals/scalar.py:73-85)
+#include "dense.cuh"
+#include <cooperative_groups.h>
+#include <algorithm>
+namespace cg = cooperative_groups;
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_gemv(const double* __restrict__ A, const double* __restrict__ x, double* __restrict__ y, int64_t m,
+                       int64_t n, int64_t lda) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < m; r += nwarps) {
+        const double* a = A + r * lda;
+        double acc0 = 0.0, acc1 = 0.0;
+        int64_t c = lane;
+        for (; c + 32 < n; c += 64) {
+            acc0 = fma(a[c], x[c], acc0);
+            acc1 = fma(a[c + 32], x[c + 32], acc1);
+        }
+        if (c < n) acc0 = fma(a[c], x[c], acc0);
+        double acc = acc0 + acc1;
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) y[r] = acc;
+    }
+}
+
+int dense_gemv(const double* A, const double* x, double* y, int64_t m, int64_t n, cudaStream_t st) {
+    if (m <= 0) return IPDE_OK;
+    const int threads = 256;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(m * 32, threads), (int64_t)ipde_num_sms() * 8));
+    k_gemv<<<blocks, threads, 0, st>>>(A, x, y, m, n, n);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Blocked triangular solves.  LU is row-major (M x M): unit-lower L below the diagonal, U on and above.
+#define TRI_B 64
+#define TRI_THREADS 256
+
+// x <- L^{-1} x   (forward), every CTA solves the diagonal block redundantly, then updates its share of rows
+__global__ void __launch_bounds__(TRI_THREADS) k_trsv_lower_unit(const double* __restrict__ LU, double* __restrict__ x, int M) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double D[TRI_B][TRI_B + 1];
+    __shared__ double y[TRI_B];
+    const int lane = threadIdx.x & 31;
+    const int warp_in_block = threadIdx.x >> 5;
+    const int warps_per_block = blockDim.x >> 5;
+    const int64_t gwarp = (int64_t)blockIdx.x * warps_per_block + warp_in_block;
+    const int64_t nwarps = (int64_t)gridDim.x * warps_per_block;
+    for (int j0 = 0; j0 < M; j0 += TRI_B) {
+        const int bs = min(TRI_B, M - j0);
+        for (int t = threadIdx.x; t < bs * bs; t += blockDim.x) {
+            const int r = t / bs, c = t % bs;
+            D[r][c] = LU[(int64_t)(j0 + r) * M + j0 + c];
+        }
+        if (threadIdx.x < bs) y[threadIdx.x] = x[j0 + threadIdx.x];
+        __syncthreads();
+        for (int i = 0; i < bs - 1; ++i) {
+            const double yi = y[i];
+            const int r = i + 1 + threadIdx.x;
+            if (r < bs) y[r] -= D[r][i] * yi;
+            __syncthreads();
+        }
+        // update the remaining rows
+        const int r0 = j0 + bs;
+        for (int64_t r = r0 + gwarp; r < M; r += nwarps) {
+            const double* a = LU + r * M + j0;
+            double acc = 0.0;
+            for (int c = lane; c < bs; c += 32) acc = fma(a[c], y[c], acc);
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) x[r] -= acc;
+        }
+        grid.sync();
+        // every CTA has read the unsolved block by now: publish the solved one
+        if (blockIdx.x == 0 && threadIdx.x < bs) x[j0 + threadIdx.x] = y[threadIdx.x];
+    }
+}
+
+// x <- U^{-1} x   (backward)
+__global__ void __launch_bounds__(TRI_THREADS) k_trsv_upper(const double* __restrict__ LU, double* __restrict__ x, int M) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double D[TRI_B][TRI_B + 1];
+    __shared__ double y[TRI_B];
+    const int lane = threadIdx.x & 31;
+    const int warp_in_block = threadIdx.x >> 5;
+    const int warps_per_block = blockDim.x >> 5;
+    const int64_t gwarp = (int64_t)blockIdx.x * warps_per_block + warp_in_block;
+    const int64_t nwarps = (int64_t)gridDim.x * warps_per_block;
+    const int nblk = (M + TRI_B - 1) / TRI_B;
+    for (int jb = nblk - 1; jb >= 0; --jb) {
+        const int j0 = jb * TRI_B;
+        const int bs = min(TRI_B, M - j0);
+        for (int t = threadIdx.x; t < bs * bs; t += blockDim.x) {
+            const int r = t / bs, c = t % bs;
+            D[r][c] = LU[(int64_t)(j0 + r) * M + j0 + c];
+        }
+        if (threadIdx.x < bs) y[threadIdx.x] = x[j0 + threadIdx.x];
+        __syncthreads();
+        for (int i = bs - 1; i >= 0; --i) {
+            if (threadIdx.x == 0) y[i] /= D[i][i];
+            __syncthreads();
+            const double yi = y[i];
+            if ((int)threadIdx.x < i) y[threadIdx.x] -= D[threadIdx.x][i] * yi;
+            __syncthreads();
+        }
+        for (int64_t r = gwarp; r < j0; r += nwarps) {
+            const double* a = LU + r * M + j0;
+            double acc = 0.0;
+            for (int c = lane; c < bs; c += 32) acc = fma(a[c], y[c], acc);
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) x[r] -= acc;
+        }
+        grid.sync();
+        if (blockIdx.x == 0 && threadIdx.x < bs) x[j0 + threadIdx.x] = y[threadIdx.x];
+    }
+}
+
+__global__ void k_permute(const double* __restrict__ b, const int* __restrict__ perm, double* __restrict__ x, int M) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) x[i] = b[perm[i]];
+}
+
+static int coop_grid(const void* kernel) {
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TRI_THREADS, 0);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 2) per_sm = 2;
+    return per_sm * ipde_num_sms();
+}
+
+int dense_lu_solve(const double* LU, const int* perm, const double* b, double* x, int M, cudaStream_t st) {
+    if (M <= 0) return IPDE_OK;
+    k_permute<<<(M + 255) / 256, 256, 0, st>>>(b, perm, x, M);
+    KERNEL_CHECK();
+    void* args[] = {(void*)&LU, (void*)&x, (void*)&M};
+    int g1 = std::min(coop_grid((const void*)k_trsv_lower_unit), std::max(1, (M + TRI_B - 1) / TRI_B * 2));
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_trsv_lower_unit, dim3(g1), dim3(TRI_THREADS), args, 0, st));
+    int g2 = std::min(coop_grid((const void*)k_trsv_upper), std::max(1, (M + TRI_B - 1) / TRI_B * 2));
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_trsv_upper, dim3(g2), dim3(TRI_THREADS), args, 0, st));
+    return IPDE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// CSR SpMV, one warp per row
+template <typename T>
+__device__ __forceinline__ T zero_of();
+template <> __device__ __forceinline__ double zero_of<double>() { return 0.0; }
+template <> __device__ __forceinline__ cplx zero_of<cplx>() { return make_double2(0.0, 0.0); }
+__device__ __forceinline__ double madd(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ cplx madd(cplx a, cplx b, cplx c) { return cadd(c, cmul(a, b)); }
+__device__ __forceinline__ double wsum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ cplx wsum(cplx v) {
+    for (int o = 16; o > 0; o >>= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    }
+    return v;
+}
+
+template <typename T>
+__global__ void k_csr_spmv(const int* __restrict__ indptr, const int* __restrict__ indices, const T* __restrict__ data,
+                           const T* __restrict__ x, T* __restrict__ y, int64_t nrows) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < nrows; r += nwarps) {
+        const int a = indptr[r], b = indptr[r + 1];
+        T acc = zero_of<T>();
+        for (int e = a + lane; e < b; e += 32) acc = madd(data[e], x[indices[e]], acc);
+        acc = wsum(acc);
+        if (lane == 0) y[r] = acc;
+    }
+}
+
+int csr_spmv_d(const int* indptr, const int* indices, const double* data, const double* x, double* y, int64_t nrows,
+               cudaStream_t st) {
+    if (nrows <= 0) return IPDE_OK;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(nrows * 32, 256), (int64_t)ipde_num_sms() * 8));
+    k_csr_spmv<double><<<blocks, 256, 0, st>>>(indptr, indices, data, x, y, nrows);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+int csr_spmv_z(const int* indptr, const int* indices, const cplx* data, const cplx* x, cplx* y, int64_t nrows,
+               cudaStream_t st) {
+    if (nrows <= 0) return IPDE_OK;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(nrows * 32, 256), (int64_t)ipde_num_sms() * 8));
+    k_csr_spmv<cplx><<<blocks, 256, 0, st>>>(indptr, indices, data, x, y, nrows);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// small vector helpers
+__global__ void k_axpby(double a, const double* __restrict__ x, double b, const double* __restrict__ y, double* __restrict__ out,
+                        int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = a * x[i] + (y ? b * y[i] : 0.0);
+}
+__global__ void k_mul(const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ out, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = x[i] * y[i];
+}
+static inline int vblocks(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 256), 2048)); }
+
+int vec_axpby(double a, const double* x, double b, const double* y, double* out, int64_t n, cudaStream_t st) {
+    if (n <= 0) return IPDE_OK;
+    k_axpby<<<vblocks(n), 256, 0, st>>>(a, x, b, y, out, n);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+int vec_mul(const double* x, const double* y, double* out, int64_t n, cudaStream_t st) {
+    if (n <= 0) return IPDE_OK;
+    k_mul<<<vblocks(n), 256, 0, st>>>(x, y, out, n);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+
+// out[i] = sum_r row[r] * fr[r*n + i]     (1 x M Chebyshev row applied to an (M, n) radial block)
+__global__ void k_rowvec(const double* __restrict__ row, const double* __restrict__ fr, double* __restrict__ out, int M, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int r = 0; r < M; ++r) acc = fma(row[r], fr[(int64_t)r * n + i], acc);
+        out[i] = acc;
+    }
+}
+int rowvec_apply(const double* row, const double* fr, double* out, int M, int64_t n, cudaStream_t st) {
+    if (n <= 0) return IPDE_OK;
+    k_rowvec<<<vblocks(n), 256, 0, st>>>(row, fr, out, M, n);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+
+// ScalarHelper.__call__ glue (internals/scalar.py:73-85):
+//   tau[0:n] = sign*(in_est . ur - (bx nx + by ny)) ; tau[n:2n] = sign*bv
+__global__ void k_scalar_jumps(const double* __restrict__ bv, const double* __restrict__ bx, const double* __restrict__ by,
+                               const double* __restrict__ nx, const double* __restrict__ ny, const double* __restrict__ ur,
+                               const double* __restrict__ in_est, int M, int64_t n, double sign, double* __restrict__ tau) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double urn = 0.0;
+        for (int r = 0; r < M; ++r) urn = fma(in_est[r], ur[(int64_t)r * n + i], urn);
+        const double ucn = bx[i] * nx[i] + by[i] * ny[i];
+        tau[i] = sign * (urn - ucn);
+        tau[n + i] = sign * bv[i];
+    }
+}
+int scalar_jumps(const double* bv, const double* bx, const double* by, const double* nx, const double* ny, const double* ur,
+                 const double* in_est, int M, int64_t n, double sign, double* tau, cudaStream_t st) {
+    if (n <= 0) return IPDE_OK;
+    k_scalar_jumps<<<vblocks(n), 256, 0, st>>>(bv, bx, by, nx, ny, ur, in_est, M, n, sign, tau);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}

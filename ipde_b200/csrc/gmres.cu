@@ -1,0 +1,230 @@
+#include "gmres.cuh"
+#include <algorithm>
+#include <complex>
+
+typedef std::complex<double> hc;
+
+static const int DOT_THREADS = 256;
+
+__device__ __forceinline__ cplx block_reduce_cplx(cplx v, cplx* sh) {
+    for (int o = 16; o > 0; o >>= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    }
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    cplx r = make_double2(0.0, 0.0);
+    if (threadIdx.x < 32) {
+        r = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : make_double2(0.0, 0.0);
+        for (int o = 16; o > 0; o >>= 1) {
+            r.x += __shfl_xor_sync(0xffffffffu, r.x, o);
+            r.y += __shfl_xor_sync(0xffffffffu, r.y, o);
+        }
+    }
+    __syncthreads();
+    return r;
+}
+
+// partial[i*gridDim.x + b] = sum over this block's elements of conj(V_i[e]) * w[e]
+__global__ void k_multi_dot(const cplx* __restrict__ V, int nvec, const cplx* __restrict__ w, int64_t len,
+                            cplx* __restrict__ partial) {
+    __shared__ cplx sh[32];
+    for (int i = 0; i < nvec; ++i) {
+        const cplx* v = V + (int64_t)i * len;
+        cplx acc = make_double2(0.0, 0.0);
+        for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < len; e += (int64_t)gridDim.x * blockDim.x) {
+            const cplx a = v[e], b = w[e];
+            acc.x += a.x * b.x + a.y * b.y;
+            acc.y += a.x * b.y - a.y * b.x;
+        }
+        cplx r = block_reduce_cplx(acc, sh);
+        if (threadIdx.x == 0) partial[(int64_t)i * gridDim.x + blockIdx.x] = r;
+    }
+}
+
+__global__ void k_reduce_dots(const cplx* __restrict__ partial, int nvec, int nblocks, cplx* __restrict__ h) {
+    __shared__ cplx sh[32];
+    const int i = blockIdx.x;
+    cplx acc = make_double2(0.0, 0.0);
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) acc = cadd(acc, partial[(int64_t)i * nblocks + b]);
+    cplx r = block_reduce_cplx(acc, sh);
+    if (threadIdx.x == 0) h[i] = r;
+}
+
+__global__ void k_sub_combination(cplx* __restrict__ w, const cplx* __restrict__ V, int nvec, const cplx* __restrict__ h,
+                                  int64_t len) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < len; e += (int64_t)gridDim.x * blockDim.x) {
+        cplx acc = w[e];
+        for (int i = 0; i < nvec; ++i) acc = csub(acc, cmul(h[i], V[(int64_t)i * len + e]));
+        w[e] = acc;
+    }
+}
+
+__global__ void k_add_combination(cplx* __restrict__ y, const cplx* __restrict__ V, int nvec, const cplx* __restrict__ c,
+                                  int64_t len) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < len; e += (int64_t)gridDim.x * blockDim.x) {
+        cplx acc = y[e];
+        for (int i = 0; i < nvec; ++i) acc = cadd(acc, cmul(c[i], V[(int64_t)i * len + e]));
+        y[e] = acc;
+    }
+}
+
+// out = in / sqrt(Re normsq[0])
+__global__ void k_normalize(const cplx* __restrict__ in, cplx* __restrict__ out, const cplx* __restrict__ normsq, int64_t len) {
+    const double s = rsqrt(normsq[0].x);
+    const double inv = (normsq[0].x > 0.0) ? s : 0.0;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < len; e += (int64_t)gridDim.x * blockDim.x)
+        out[e] = cscale(in[e], inv);
+}
+
+__global__ void k_residual(const cplx* __restrict__ b, const cplx* __restrict__ ax, cplx* __restrict__ r, int64_t len) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < len; e += (int64_t)gridDim.x * blockDim.x)
+        r[e] = csub(b[e], ax[e]);
+}
+
+int gmres_workspace_ensure(GmresWorkspace* ws, int64_t len, int restart) {
+    if (ws->len >= len && ws->restart >= restart) return IPDE_OK;
+    gmres_workspace_free(ws);
+    ws->nblocks = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(len, DOT_THREADS * 4), (int64_t)ipde_num_sms() * 2));
+    CUDA_TRY(cudaMalloc(&ws->V, sizeof(cplx) * (size_t)(restart + 1) * len));
+    CUDA_TRY(cudaMalloc(&ws->w, sizeof(cplx) * (size_t)len));
+    CUDA_TRY(cudaMalloc(&ws->z, sizeof(cplx) * (size_t)len));
+    CUDA_TRY(cudaMalloc(&ws->y, sizeof(cplx) * (size_t)len));
+    CUDA_TRY(cudaMalloc(&ws->hbuf, sizeof(cplx) * (size_t)(3 * (restart + 2))));
+    CUDA_TRY(cudaMalloc(&ws->partial, sizeof(cplx) * (size_t)(restart + 2) * ws->nblocks));
+    CUDA_TRY(cudaMallocHost(&ws->host, sizeof(cplx) * (size_t)(3 * (restart + 2))));
+    ws->len = len;
+    ws->restart = restart;
+    return IPDE_OK;
+}
+
+void gmres_workspace_free(GmresWorkspace* ws) {
+    cudaFree(ws->V); cudaFree(ws->w); cudaFree(ws->z); cudaFree(ws->y); cudaFree(ws->hbuf); cudaFree(ws->partial);
+    if (ws->host) cudaFreeHost(ws->host);
+    *ws = GmresWorkspace();
+}
+
+static int dots(GmresWorkspace* ws, const cplx* V, int nvec, const cplx* w, int64_t len, cplx* h, cudaStream_t st) {
+    k_multi_dot<<<ws->nblocks, DOT_THREADS, 0, st>>>(V, nvec, w, len, reinterpret_cast<cplx*>(ws->partial));
+    KERNEL_CHECK();
+    k_reduce_dots<<<nvec, 128, 0, st>>>(reinterpret_cast<cplx*>(ws->partial), nvec, ws->nblocks, h);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+
+static inline int ew_blocks(int64_t len) {
+    return (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(len, 256), (int64_t)ipde_num_sms() * 8));
+}
+
+int gmres_solve(LinearOperator* op, GmresWorkspace* ws, const cplx* b, cplx* x, int64_t len, double tol, int restart,
+                int maxiter, int* iters, double* relres, cudaStream_t st) {
+    if (restart < 1) restart = 20;
+    if (restart > len) restart = (int)len;
+    if (maxiter < 1) maxiter = 1;
+    int rc = gmres_workspace_ensure(ws, len, restart);
+    if (rc) return rc;
+    const int R1 = ws->restart + 2;          // stride of the three small device vectors
+    cplx* d_h = ws->hbuf;
+    cplx* d_h2 = ws->hbuf + R1;
+    cplx* d_n = ws->hbuf + 2 * R1;
+    cplx* hst = ws->host;
+    cplx* V = ws->V;
+    const int eb = ew_blocks(len);
+    int total_its = 0;
+    *relres = 0.0;
+    *iters = 0;
+
+    // ||b||
+    rc = dots(ws, b, 1, b, len, d_n, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(hst, d_n, sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const double bnorm = sqrt(hst[0].x);
+    CUDA_TRY(cudaMemsetAsync(ws->y, 0, sizeof(cplx) * (size_t)len, st));
+    if (bnorm == 0.0) {
+        CUDA_TRY(cudaMemsetAsync(x, 0, sizeof(cplx) * (size_t)len, st));
+        return IPDE_OK;
+    }
+
+    std::vector<hc> H((size_t)(restart + 1) * restart), cs(restart), sn(restart), g(restart + 1);
+    bool converged = false;
+    for (int cycle = 0; cycle < maxiter && !converged; ++cycle) {
+        // r = b - A M y   (first cycle: y = 0)
+        if (cycle == 0) {
+            CUDA_TRY(cudaMemcpyAsync(ws->w, b, sizeof(cplx) * (size_t)len, cudaMemcpyDeviceToDevice, st));
+        } else {
+            rc = op->precond(ws->y, ws->z, st); if (rc) return rc;
+            rc = op->apply(ws->z, ws->w, st); if (rc) return rc;
+            k_residual<<<eb, 256, 0, st>>>(b, ws->w, ws->w, len);
+            KERNEL_CHECK();
+        }
+        rc = dots(ws, ws->w, 1, ws->w, len, d_n, st); if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(hst, d_n, sizeof(cplx), cudaMemcpyDeviceToHost, st));
+        k_normalize<<<eb, 256, 0, st>>>(ws->w, V, d_n, len);
+        KERNEL_CHECK();
+        CUDA_TRY(cudaStreamSynchronize(st));
+        const double beta = sqrt(hst[0].x);
+        if (beta <= tol * bnorm) { *relres = beta / bnorm; converged = true; break; }
+        std::fill(H.begin(), H.end(), hc(0.0));
+        std::fill(g.begin(), g.end(), hc(0.0));
+        g[0] = beta;
+        int kdone = 0;
+        for (int j = 0; j < restart; ++j) {
+            cplx* vj = V + (int64_t)j * len;
+            rc = op->precond(vj, ws->z, st); if (rc) return rc;
+            rc = op->apply(ws->z, ws->w, st); if (rc) return rc;
+            // classical Gram-Schmidt, twice
+            rc = dots(ws, V, j + 1, ws->w, len, d_h, st); if (rc) return rc;
+            k_sub_combination<<<eb, 256, 0, st>>>(ws->w, V, j + 1, d_h, len);
+            KERNEL_CHECK();
+            rc = dots(ws, V, j + 1, ws->w, len, d_h2, st); if (rc) return rc;
+            k_sub_combination<<<eb, 256, 0, st>>>(ws->w, V, j + 1, d_h2, len);
+            KERNEL_CHECK();
+            rc = dots(ws, ws->w, 1, ws->w, len, d_n, st); if (rc) return rc;
+            k_normalize<<<eb, 256, 0, st>>>(ws->w, V + (int64_t)(j + 1) * len, d_n, len);
+            KERNEL_CHECK();
+            CUDA_TRY(cudaMemcpyAsync(hst, ws->hbuf, sizeof(cplx) * (size_t)(2 * R1 + 1), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            const double hn = sqrt(hst[2 * R1].x);
+            for (int i = 0; i <= j; ++i)
+                H[(size_t)i * restart + j] = hc(hst[i].x + hst[R1 + i].x, hst[i].y + hst[R1 + i].y);
+            H[(size_t)(j + 1) * restart + j] = hn;
+            for (int i = 0; i < j; ++i) {
+                hc a = H[(size_t)i * restart + j], bb = H[(size_t)(i + 1) * restart + j];
+                H[(size_t)i * restart + j] = cs[i] * a + sn[i] * bb;
+                H[(size_t)(i + 1) * restart + j] = -std::conj(sn[i]) * a + cs[i] * bb;
+            }
+            hc a = H[(size_t)j * restart + j], bb = H[(size_t)(j + 1) * restart + j];
+            const double den = sqrt(std::norm(a) + std::norm(bb));
+            if (std::abs(a) != 0.0) {
+                cs[j] = std::abs(a) / den;
+                sn[j] = (a / std::abs(a)) * std::conj(bb) / den;
+            } else {
+                cs[j] = 0.0; sn[j] = 1.0;
+            }
+            H[(size_t)j * restart + j] = cs[j] * a + sn[j] * bb;
+            H[(size_t)(j + 1) * restart + j] = 0.0;
+            g[j + 1] = -std::conj(sn[j]) * g[j];
+            g[j] = cs[j] * g[j];
+            kdone = j + 1;
+            ++total_its;
+            const double rel = std::abs(g[j + 1]) / bnorm;
+            *relres = rel;
+            if (rel <= tol || hn == 0.0) { converged = true; break; }
+        }
+        // back substitution for the small triangular system, then y += V^T yk
+        std::vector<hc> yk(kdone);
+        for (int i = kdone - 1; i >= 0; --i) {
+            hc s = g[i];
+            for (int l = i + 1; l < kdone; ++l) s -= H[(size_t)i * restart + l] * yk[l];
+            yk[i] = s / H[(size_t)i * restart + i];
+        }
+        for (int i = 0; i < kdone; ++i) hst[i] = make_double2(yk[i].real(), yk[i].imag());
+        CUDA_TRY(cudaMemcpyAsync(d_h, hst, sizeof(cplx) * (size_t)kdone, cudaMemcpyHostToDevice, st));
+        k_add_combination<<<eb, 256, 0, st>>>(ws->y, V, kdone, d_h, len);
+        KERNEL_CHECK();
+        CUDA_TRY(cudaStreamSynchronize(st));   // hst is reused next cycle
+    }
+    *iters = total_its;
+    return op->precond(ws->y, x, st);
+}

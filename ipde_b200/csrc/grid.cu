@@ -1,0 +1,353 @@
+// Periodic background-grid kernels: compact->grid scatter with cutoff, demean, 2-D real FFT,
+// spectral multipliers (Poisson / modified Helmholtz / Stokes), finite differences, finalize.
+//
+// Replaces, on the device:
+//   EmbeddedFunction.get_components / get_smoothed_grid_value   ipde/embedded_function.py:135-138,184-194
+//   ebdyc.demean_function / grid_integral                       ipde/ebdy_collection.py:808-816
+//   ModifiedHelmholtzSolver._grid_solve                         ipde/solvers/multi_boundary/modified_helmholtz.py:40-46
+//   PoissonSolver._grid_solve                                   ipde/solvers/multi_boundary/poisson.py:30-38
+//   StokesSolver._grid_solve                                    ipde/solvers/multi_boundary/stokes.py:34-50
+//   derivatives.fd_x_4 / fd_y_4                                 ipde/derivatives.py:3-23
+//   uc[pna] += gu ; uc *= phys ; EmbeddedFunction.load_data     ipde/solvers/multi_boundary/scalar.py:107-116
+#include "grid.cuh"
+#include <algorithm>
+
+static const double TWO_PI = 6.283185307179586476925286766559;
+
+// ------------------------------------------------------------------------------------------
+int grid_plan_create(int nx, int ny, double xh, double yh, GridPlan** out) {
+    ARG_CHECK(nx >= 4 && ny >= 4 && ny % 2 == 0, "grid sizes must be >= 4 and ny even");
+    GridPlan* g = new GridPlan();
+    g->nx = nx; g->ny = ny; g->xh = xh; g->yh = yh;
+    g->pitch = ny / 2 + 1;
+    int rc = fft_plan_create(ny / 2, &g->row);
+    if (rc) { delete g; return rc; }
+    // columns: one pass if at least 4 adjacent columns fit next to each other in shared memory,
+    // otherwise a four-step split nx = n1*n2
+    if ((int64_t)nx * 4 <= IPDE_FFT_SMEM_MAX) {
+        g->n1 = nx; g->n2 = 1;
+        rc = fft_plan_create(nx, &g->colA);
+        if (rc) { grid_plan_destroy(g); return rc; }
+    } else {
+        int best = 1;
+        for (int d = 1; (int64_t)d * d <= nx; ++d)
+            if (nx % d == 0 && fft_size_supported(d) && fft_size_supported(nx / d)) best = d;
+        g->n2 = best; g->n1 = nx / best;
+        if (best == 1 || (int64_t)g->n1 * 4 > IPDE_FFT_SMEM_MAX) {
+            // no usable split: long-line global path
+            g->n1 = nx; g->n2 = 1;
+            rc = fft_plan_create(nx, &g->colA);
+            if (rc) { grid_plan_destroy(g); return rc; }
+        } else {
+            rc = fft_plan_create(g->n1, &g->colA);
+            if (!rc) rc = fft_plan_create(g->n2, &g->colB);
+            if (rc) { grid_plan_destroy(g); return rc; }
+            std::vector<cplx> tw(nx);
+            const long double tp = 6.283185307179586476925286766559005768L;
+            for (int j = 0; j < nx; ++j) {
+                long double a = -tp * (long double)j / (long double)nx;
+                tw[j] = make_double2((double)cosl(a), (double)sinl(a));
+            }
+            CUDA_TRY(cudaMalloc(&g->tw_big, sizeof(cplx) * (size_t)nx));
+            CUDA_TRY(cudaMemcpy(g->tw_big, tw.data(), sizeof(cplx) * (size_t)nx, cudaMemcpyHostToDevice));
+        }
+    }
+    *out = g;
+    return IPDE_OK;
+}
+
+void grid_plan_destroy(GridPlan* g) {
+    if (!g) return;
+    fft_plan_destroy(g->row);
+    fft_plan_destroy(g->colA);
+    fft_plan_destroy(g->colB);
+    cudaFree(g->tw_big);
+    cudaFree(g->reduce_buf);
+    delete g;
+}
+
+// forward column transform of the half spectrum (in place or out of place)
+int grid_cols_forward(GridPlan* g, const cplx* in, cplx* out, cudaStream_t st) {
+    const int64_t P = g->pitch;
+    if (g->n2 == 1) return fft_cols(g->colA, in, out, P, P, 1, 0, -1, 1.0, 0, nullptr, 0, st);
+    // x = n2*a + b.  A: FFT over a for every b (+ twiddle), B: FFT over b for every k1.
+    int rc = fft_cols(g->colA, in, out, (int64_t)g->n2 * P, P, g->n2, P, -1, 1.0, 1, g->tw_big, g->nx, st);
+    if (rc) return rc;
+    return fft_cols(g->colB, out, out, P, P, g->n1, (int64_t)g->n2 * P, -1, 1.0, 0, nullptr, 0, st);
+}
+
+int grid_cols_inverse(GridPlan* g, const cplx* in, cplx* out, cudaStream_t st) {
+    const int64_t P = g->pitch;
+    if (g->n2 == 1) return fft_cols(g->colA, in, out, P, P, 1, 0, +1, 1.0, 0, nullptr, 0, st);
+    int rc = fft_cols(g->colB, in, out, P, P, g->n1, (int64_t)g->n2 * P, +1, 1.0, 0, nullptr, 0, st);
+    if (rc) return rc;
+    return fft_cols(g->colA, out, out, (int64_t)g->n2 * P, P, g->n2, P, +1, 1.0, 2, g->tw_big, g->nx, st);
+}
+
+int grid_fft2_forward(GridPlan* g, const double* real_in, cplx* spec, cudaStream_t st) {
+    int rc = fft_r2c_rows(g->row, real_in, spec, g->nx, g->ny, g->pitch, st);
+    if (rc) return rc;
+    return grid_cols_forward(g, spec, spec, st);
+}
+
+int grid_fft2_inverse(GridPlan* g, const cplx* spec_in, cplx* spec_work, double* real_out, cudaStream_t st) {
+    int rc = grid_cols_inverse(g, spec_in, spec_work, st);
+    if (rc) return rc;
+    return fft_c2r_rows(g->row, spec_work, real_out, g->nx, g->pitch, g->ny, 1.0 / ((double)g->nx * (double)g->ny) * 2.0, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// compact physical vector -> zero-filled grid, times the cutoff
+__global__ void k_scatter_cutoff(double* __restrict__ fc, const double* __restrict__ f, const int64_t* __restrict__ lin,
+                                 const double* __restrict__ step, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        fc[lin[i]] = f[i] * step[i];
+}
+
+static inline int grid_blocks(int64_t n, int threads) {
+    return (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, threads), (int64_t)ipde_num_sms() * 8));
+}
+
+int grid_scatter_cutoff(GridPlan* g, const double* f_compact, const int64_t* phys_lin, const double* step_compact,
+                        int64_t n_phys, double* fc, cudaStream_t st) {
+    CUDA_TRY(cudaMemsetAsync(fc, 0, sizeof(double) * (size_t)g->nx * g->ny, st));
+    if (n_phys > 0) {
+        k_scatter_cutoff<<<grid_blocks(n_phys, 256), 256, 0, st>>>(fc, f_compact, phys_lin, step_compact, n_phys);
+        KERNEL_CHECK();
+    }
+    return IPDE_OK;
+}
+
+// sum reduction (deterministic two-stage) and demean
+__global__ void k_partial_sum(const double* __restrict__ x, int64_t n, double* __restrict__ partial) {
+    __shared__ double sh[32];
+    double acc = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc += x[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) partial[blockIdx.x] = v;
+    }
+}
+__global__ void k_final_sum(double* __restrict__ partial, int nparts) {
+    __shared__ double sh[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) acc += partial[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) partial[nparts] = v;
+    }
+}
+__global__ void k_demean(double* __restrict__ f, const double* __restrict__ bumpy, int64_t n, const double* __restrict__ total,
+                         double weight) {
+    const double m = total[0] * weight;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        f[i] -= m * bumpy[i];
+}
+
+int grid_demean(GridPlan* g, double* f, const double* bumpy, cudaStream_t st) {
+    const int64_t n = (int64_t)g->nx * g->ny;
+    const int parts = ipde_num_sms() * 4;
+    if (!g->reduce_buf) CUDA_TRY(cudaMalloc(&g->reduce_buf, sizeof(double) * (parts + 1)));
+    k_partial_sum<<<parts, 256, 0, st>>>(f, n, g->reduce_buf);
+    KERNEL_CHECK();
+    k_final_sum<<<1, 256, 0, st>>>(g->reduce_buf, parts);
+    KERNEL_CHECK();
+    k_demean<<<grid_blocks(n, 256), 256, 0, st>>>(f, bumpy, n, g->reduce_buf + parts, g->xh * g->yh);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// spectral multipliers on the half spectrum; rows may be in four-step order
+__device__ __forceinline__ int freq_of_row(int pos, int n1, int n2) {
+    if (n2 == 1) return pos;
+    const int k1 = pos / n2, k2 = pos % n2;
+    return k1 + n1 * k2;
+}
+__device__ __forceinline__ double wavenumber(int i, int n, double h) {
+    const int s = (i < (n + 1) / 2) ? i : i - n;     // numpy.fft.fftfreq ordering
+    return TWO_PI * (double)s / ((double)n * h);
+}
+
+__global__ void k_scalar_multiply(cplx* __restrict__ spec, int nx, int ny, int64_t pitch, int n1, int n2, double xh,
+                                  double yh, int kind, double k2const) {
+    const int64_t total = (int64_t)nx * pitch;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int pos = (int)(t / pitch), j = (int)(t % pitch);
+        const int i = freq_of_row(pos, n1, n2);
+        const double kx = wavenumber(i, nx, xh), ky = wavenumber(j, ny, yh);
+        double m;
+        if (kind == IPDE_KIND_POISSON) {
+            const double lap = -(kx * kx + ky * ky);
+            m = (i == 0 && j == 0) ? 0.0 : 1.0 / lap;
+        } else {
+            m = 1.0 / (k2const + kx * kx + ky * ky);
+        }
+        spec[t] = cscale(spec[t], m);
+    }
+}
+
+int grid_scalar_multiply(GridPlan* g, cplx* spec, int kind, double k, cudaStream_t st) {
+    const int64_t total = (int64_t)g->nx * g->pitch;
+    k_scalar_multiply<<<grid_blocks(total, 256), 256, 0, st>>>(spec, g->nx, g->ny, g->pitch, g->n1, g->n2, g->xh, g->yh,
+                                                               kind, k * k);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// 4th-order centred differences, zero in the 2-cell border (reference derivatives.py:3-23)
+__global__ void k_fd4(const double* __restrict__ f, double* __restrict__ fx, double* __restrict__ fy, int nx, int ny,
+                      double iahx, double iahy) {
+    const int64_t total = (int64_t)nx * ny;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(t / ny), j = (int)(t % ny);
+        double dx = 0.0, dy = 0.0;
+        if (i >= 2 && i < nx - 2)
+            dx = -(f[t + 2 * (int64_t)ny] - 8.0 * f[t + ny] + 8.0 * f[t - ny] - f[t - 2 * (int64_t)ny]) * iahx;
+        if (j >= 2 && j < ny - 2) dy = -(f[t + 2] - 8.0 * f[t + 1] + 8.0 * f[t - 1] - f[t - 2]) * iahy;
+        if (fx) fx[t] = dx;
+        if (fy) fy[t] = dy;
+    }
+}
+
+int grid_fd4(GridPlan* g, const double* f, double* fx, double* fy, cudaStream_t st) {
+    const int64_t total = (int64_t)g->nx * g->ny;
+    k_fd4<<<grid_blocks(total, 256), 256, 0, st>>>(f, fx, fy, g->nx, g->ny, 1.0 / (12.0 * g->xh), 1.0 / (12.0 * g->yh));
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+
+// periodic tensor-product cubic Lagrange interpolation (fast_interp.interp2d(k=3, p=[True,True]))
+__global__ void k_interp_cubic(const double* __restrict__ f, int nx, int ny, double x0, double y0, double xh, double yh,
+                               const double* __restrict__ px, const double* __restrict__ py, int64_t npts,
+                               double* __restrict__ out) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npts; p += (int64_t)gridDim.x * blockDim.x) {
+        const double sx = (px[p] - x0) / xh, sy = (py[p] - y0) / yh;
+        const int ix = (int)floor(sx) - 1, iy = (int)floor(sy) - 1;
+        const double ux = sx - ix, uy = sy - iy;
+        double wx[4], wy[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            double wa = 1.0, wb = 1.0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (a != b) {
+                    wa *= (ux - b) / (double)(a - b);
+                    wb *= (uy - b) / (double)(a - b);
+                }
+            wx[a] = wa; wy[a] = wb;
+        }
+        double acc = 0.0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int ii = ((ix + a) % nx + nx) % nx;
+            double row = 0.0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int jj = ((iy + b) % ny + ny) % ny;
+                row += f[(int64_t)ii * ny + jj] * wy[b];
+            }
+            acc += row * wx[a];
+        }
+        out[p] = acc;
+    }
+}
+
+int grid_interp_cubic(GridPlan* g, const double* f, double x0, double y0, const double* px, const double* py,
+                      int64_t npts, double* out, cudaStream_t st) {
+    if (npts <= 0) return IPDE_OK;
+    k_interp_cubic<<<grid_blocks(npts, 128), 128, 0, st>>>(f, g->nx, g->ny, x0, y0, g->xh, g->yh, px, py, npts, out);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// finalize: compact[g] = uc[phys_lin[g]] ; compact[pna_pos[i]] += gu[i] ; compact[ia_pos[i]] = radial value
+__global__ void k_gather(const double* __restrict__ uc, const int64_t* __restrict__ lin, int64_t n, double* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = uc[lin[i]];
+}
+__global__ void k_index_add(double* __restrict__ out, const int64_t* __restrict__ pos, const double* __restrict__ v, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[pos[i]] += v[i];
+}
+__global__ void k_index_set(double* __restrict__ out, const int64_t* __restrict__ pos, const double* __restrict__ v, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[pos[i]] = v[i];
+}
+
+int grid_gather(const double* uc, const int64_t* lin, int64_t n, double* out, cudaStream_t st) {
+    if (n <= 0) return IPDE_OK;
+    k_gather<<<grid_blocks(n, 256), 256, 0, st>>>(uc, lin, n, out);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+int grid_index_add(double* out, const int64_t* pos, const double* v, int64_t n, cudaStream_t st) {
+    if (n <= 0) return IPDE_OK;
+    k_index_add<<<grid_blocks(n, 256), 256, 0, st>>>(out, pos, v, n);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+int grid_index_set(double* out, const int64_t* pos, const double* v, int64_t n, cudaStream_t st) {
+    if (n <= 0) return IPDE_OK;
+    k_index_set<<<grid_blocks(n, 256), 256, 0, st>>>(out, pos, v, n);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Stokes multiplier (mu = 1), reference ipde/solvers/multi_boundary/stokes.py:34-50:
+//   ph = ilap (ikx fuh + iky fvh) ; uh = ilap (ikx ph - fuh) ; vh = ilap (iky ph - fvh)
+// followed there by ifft2(.).real.  Taking the real part symmetrises the spectrum; away from the Nyquist
+// row/column that changes nothing, on them it averages the expression over the two signs of the Nyquist
+// wavenumber ("Nyquist modes").
+struct Uvp { cplx u, v, p; };
+__device__ __forceinline__ Uvp stokes_symbol(double kx, double ky, cplx fu, cplx fv, bool zero_mode) {
+    Uvp r;
+    const double lap = -(kx * kx + ky * ky);
+    const double il = zero_mode ? 0.0 : 1.0 / lap;
+    // ikx*fu + iky*fv
+    cplx d = make_double2(-(kx * fu.y + ky * fv.y), kx * fu.x + ky * fv.x);
+    r.p = cscale(d, il);
+    cplx ikxp = make_double2(-kx * r.p.y, kx * r.p.x);
+    cplx ikyp = make_double2(-ky * r.p.y, ky * r.p.x);
+    r.u = cscale(csub(ikxp, fu), il);
+    r.v = cscale(csub(ikyp, fv), il);
+    return r;
+}
+
+__global__ void k_stokes_multiply(cplx* __restrict__ uh, cplx* __restrict__ vh, cplx* __restrict__ ph, int nx, int ny,
+                                  int64_t pitch, int n1, int n2, double xh, double yh) {
+    const int64_t total = (int64_t)nx * pitch;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int pos = (int)(t / pitch), j = (int)(t % pitch);
+        const int i = freq_of_row(pos, n1, n2);
+        const double kx = wavenumber(i, nx, xh), ky = wavenumber(j, ny, yh);
+        const bool xn = (nx % 2 == 0 && i == nx / 2), yn = (j == ny / 2);
+        const cplx fu = uh[t], fv = vh[t];
+        Uvp a = stokes_symbol(kx, ky, fu, fv, i == 0 && j == 0);
+        if (xn || yn) {
+            Uvp b = stokes_symbol(xn ? -kx : kx, yn ? -ky : ky, fu, fv, false);
+            a.u = cscale(cadd(a.u, b.u), 0.5);
+            a.v = cscale(cadd(a.v, b.v), 0.5);
+            a.p = cscale(cadd(a.p, b.p), 0.5);
+        }
+        uh[t] = a.u; vh[t] = a.v; ph[t] = a.p;
+    }
+}
+
+int grid_stokes_multiply(GridPlan* g, cplx* uh, cplx* vh, cplx* ph, cudaStream_t st) {
+    const int64_t total = (int64_t)g->nx * g->pitch;
+    k_stokes_multiply<<<grid_blocks(total, 256), 256, 0, st>>>(uh, vh, ph, g->nx, g->ny, g->pitch, g->n1, g->n2, g->xh, g->yh);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}

@@ -1,0 +1,39 @@
+#pragma once
+#include "fft.cuh"
+
+#define IPDE_KIND_POISSON 0
+#define IPDE_KIND_MODHELM 1
+#define IPDE_KIND_STOKES 2
+
+// Half-spectrum layout of a real (nx, ny) grid function: complex (nx, ny/2+1), row pitch ny/2+1.
+// When the column transform is split (n2 > 1) the rows of a spectrum are in four-step order:
+// frequency index k1 + n1*k2 is stored at row n2*k1 + k2.
+struct GridPlan {
+    int nx, ny;
+    double xh, yh;
+    int64_t pitch;
+    int n1, n2;
+    FftPlan* row = nullptr;    // length ny/2 (packed real rows)
+    FftPlan* colA = nullptr;   // length n1
+    FftPlan* colB = nullptr;   // length n2 (four-step only)
+    cplx* tw_big = nullptr;    // exp(-2 pi i j / nx)
+    double* reduce_buf = nullptr;
+};
+
+int grid_plan_create(int nx, int ny, double xh, double yh, GridPlan** out);
+void grid_plan_destroy(GridPlan* g);
+int grid_cols_forward(GridPlan* g, const cplx* in, cplx* out, cudaStream_t st);
+int grid_cols_inverse(GridPlan* g, const cplx* in, cplx* out, cudaStream_t st);
+int grid_fft2_forward(GridPlan* g, const double* real_in, cplx* spec, cudaStream_t st);
+int grid_fft2_inverse(GridPlan* g, const cplx* spec_in, cplx* spec_work, double* real_out, cudaStream_t st);
+int grid_scatter_cutoff(GridPlan* g, const double* f_compact, const int64_t* phys_lin, const double* step_compact,
+                        int64_t n_phys, double* fc, cudaStream_t st);
+int grid_demean(GridPlan* g, double* f, const double* bumpy, cudaStream_t st);
+int grid_scalar_multiply(GridPlan* g, cplx* spec, int kind, double k, cudaStream_t st);
+int grid_fd4(GridPlan* g, const double* f, double* fx, double* fy, cudaStream_t st);
+int grid_interp_cubic(GridPlan* g, const double* f, double x0, double y0, const double* px, const double* py,
+                      int64_t npts, double* out, cudaStream_t st);
+int grid_gather(const double* uc, const int64_t* lin, int64_t n, double* out, cudaStream_t st);
+int grid_index_add(double* out, const int64_t* pos, const double* v, int64_t n, cudaStream_t st);
+int grid_index_set(double* out, const int64_t* pos, const double* v, int64_t n, cudaStream_t st);
+int grid_stokes_multiply(GridPlan* g, cplx* uh, cplx* vh, cplx* ph, cudaStream_t st);

@@ -1,0 +1,234 @@
+// Direct (all-pairs) evaluation of sums of free-space Green's functions, FP64:
+//     u(x_t) = sum_s G(|x_t - y_s|) q_s
+// G = -log r / (2 pi)            (Laplace;   reference grid_evaluators/laplace_grid_evaluator.py:8-12)
+// G = K0(k r) / (2 pi)           (modified Helmholtz; modified_helmholtz_grid_evaluator.py:8-9)
+// Stokes: stokeslet velocity (1/4pi)(-log r I + r r^T / r^2) f and pressure (1/2pi) r.f / r^2
+//                                (solvers/internals/stokes_save.py:29-38; pyfmmlib2d.SFMM call at internals/stokes.py:29-34)
+// Stands in for pybie2d's *_Layer_Apply(backend='fly') / SFMM as called from
+// ipde/solvers/internals/scalar.py:101,113, multi_boundary/scalar.py:67 and modified_helmholtz.py:63.
+// q_s already includes the source quadrature weight.
+//
+// CUDA's math library has no double-precision K0, so it is evaluated here: power series for x <= 2,
+// exp(-x)/sqrt(x) times a Chebyshev series in 4/x - 1 beyond (coefficients fitted on the host against
+// scipy.special.k0e and uploaded with ipde_set_k0_table).
+#include "layer.cuh"
+#include <algorithm>
+
+#define K0_MAX_CHEB 40
+__constant__ double c_k0_cheb[K0_MAX_CHEB];
+__constant__ int c_k0_ncheb;
+__constant__ double c_k0_a[16];   // 1/(m!)^2
+__constant__ double c_k0_b[16];   // H_m/(m!)^2
+static bool g_k0_ready = false;
+
+int layer_set_k0_table(const double* cheb, int ncheb) {
+    ARG_CHECK(ncheb >= 2 && ncheb <= K0_MAX_CHEB, "bad Chebyshev table length");
+    CUDA_TRY(cudaMemcpyToSymbol(c_k0_cheb, cheb, sizeof(double) * ncheb));
+    CUDA_TRY(cudaMemcpyToSymbol(c_k0_ncheb, &ncheb, sizeof(int)));
+    double a[16], b[16];
+    double fact = 1.0, H = 0.0;
+    for (int m = 0; m < 16; ++m) {
+        if (m > 0) { fact *= m; H += 1.0 / m; }
+        a[m] = 1.0 / (fact * fact);
+        b[m] = H / (fact * fact);
+    }
+    CUDA_TRY(cudaMemcpyToSymbol(c_k0_a, a, sizeof(a)));
+    CUDA_TRY(cudaMemcpyToSymbol(c_k0_b, b, sizeof(b)));
+    g_k0_ready = true;
+    return IPDE_OK;
+}
+
+// K0(x) for x > 0, given x and x^2
+__device__ __forceinline__ double bessel_k0(double x, double x2) {
+    if (x <= 2.0) {
+        const double y = 0.25 * x2;
+        double i0 = c_k0_a[15], s = c_k0_b[15];
+#pragma unroll
+        for (int m = 14; m >= 0; --m) {
+            i0 = fma(i0, y, c_k0_a[m]);
+            s = fma(s, y, c_k0_b[m]);
+        }
+        const double EULER = 0.57721566490153286061;
+        return -(0.5 * log(y) + EULER) * i0 + s;
+    }
+    const double t = 4.0 / x - 1.0, t2 = 2.0 * t;
+    const int nc = c_k0_ncheb;
+    double b0 = 0.0, b1 = 0.0;
+    for (int m = nc - 1; m >= 1; --m) {
+        const double tmp = fma(t2, b0, c_k0_cheb[m]) - b1;
+        b1 = b0;
+        b0 = tmp;
+    }
+    const double p = fma(t, b0, c_k0_cheb[0]) - b1;
+    return exp(-x) * rsqrt(x) * p;
+}
+
+__global__ void k_eval_k0(const double* __restrict__ x, double* __restrict__ out, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = bessel_k0(x[i], x[i] * x[i]);
+}
+
+int layer_eval_k0(const double* x, double* out, int64_t n, cudaStream_t st) {
+    ARG_CHECK(g_k0_ready, "K0 table not set");
+    k_eval_k0<<<(int)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 256), 4096)), 256, 0, st>>>(x, out, n);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+
+#define LAYER_TILE 256
+#define LAYER_THREADS 128
+
+// kind 0: Laplace, 1: modified Helmholtz.  partial[chunk*ntrg + t]
+template <int KIND>
+__global__ void k_layer_scalar(const double* __restrict__ sx, const double* __restrict__ sy, const double* __restrict__ q,
+                               int64_t nsrc, const double* __restrict__ tx, const double* __restrict__ ty, int64_t ntrg,
+                               double kk, int64_t chunk_len, double* __restrict__ partial) {
+    __shared__ double shx[LAYER_TILE], shy[LAYER_TILE], shq[LAYER_TILE];
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t s0 = blockIdx.y * chunk_len;
+    const int64_t s1 = min(nsrc, s0 + chunk_len);
+    const bool live = t < ntrg;
+    const double x = live ? tx[t] : 0.0, y = live ? ty[t] : 0.0;
+    double acc = 0.0;
+    for (int64_t base = s0; base < s1; base += LAYER_TILE) {
+        const int cnt = (int)min((int64_t)LAYER_TILE, s1 - base);
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+            shx[i] = sx[base + i]; shy[i] = sy[base + i]; shq[i] = q[base + i];
+        }
+        __syncthreads();
+        if (live) {
+#pragma unroll 4
+            for (int i = 0; i < cnt; ++i) {
+                const double dx = x - shx[i], dy = y - shy[i];
+                const double r2 = dx * dx + dy * dy;
+                if (KIND == 0) {
+                    acc -= log(r2) * shq[i];
+                } else {
+                    const double xr = kk * sqrt(r2);
+                    acc += bessel_k0(xr, kk * kk * r2) * shq[i];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (live) {
+        const double scale = (KIND == 0) ? 0.07957747154594767280 /* 1/(4 pi) */ : 0.15915494309189533577 /* 1/(2 pi) */;
+        partial[(int64_t)blockIdx.y * ntrg + t] = acc * scale;
+    }
+}
+
+// Stokes: forces (fx, fy) already weighted; outputs u, v, p
+__global__ void k_layer_stokes(const double* __restrict__ sx, const double* __restrict__ sy, const double* __restrict__ fx,
+                               const double* __restrict__ fy, int64_t nsrc, const double* __restrict__ tx,
+                               const double* __restrict__ ty, int64_t ntrg, int64_t chunk_len, double* __restrict__ partial) {
+    __shared__ double shx[LAYER_TILE], shy[LAYER_TILE], shfx[LAYER_TILE], shfy[LAYER_TILE];
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t s0 = blockIdx.y * chunk_len;
+    const int64_t s1 = min(nsrc, s0 + chunk_len);
+    const bool live = t < ntrg;
+    const double x = live ? tx[t] : 0.0, y = live ? ty[t] : 0.0;
+    double au = 0.0, av = 0.0, ap = 0.0;
+    for (int64_t base = s0; base < s1; base += LAYER_TILE) {
+        const int cnt = (int)min((int64_t)LAYER_TILE, s1 - base);
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+            shx[i] = sx[base + i]; shy[i] = sy[base + i]; shfx[i] = fx[base + i]; shfy[i] = fy[base + i];
+        }
+        __syncthreads();
+        if (live) {
+#pragma unroll 4
+            for (int i = 0; i < cnt; ++i) {
+                const double dx = x - shx[i], dy = y - shy[i];
+                const double r2 = dx * dx + dy * dy;
+                const double ir2 = 1.0 / r2;
+                const double L = -0.5 * log(r2);
+                const double rf = (dx * shfx[i] + dy * shfy[i]) * ir2;
+                au += L * shfx[i] + rf * dx;
+                av += L * shfy[i] + rf * dy;
+                ap += rf;
+            }
+        }
+        __syncthreads();
+    }
+    if (live) {
+        const double c4 = 0.07957747154594767280, c2 = 0.15915494309189533577;
+        double* base = partial + (int64_t)blockIdx.y * 3 * ntrg;
+        base[t] = au * c4;
+        base[ntrg + t] = av * c4;
+        base[2 * ntrg + t] = ap * c2;
+    }
+}
+
+__global__ void k_layer_reduce(const double* __restrict__ partial, int nchunks, int64_t n, double* __restrict__ out,
+                               int accumulate) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double acc = accumulate ? out[i] : 0.0;
+        for (int c = 0; c < nchunks; ++c) acc += partial[(int64_t)c * n + i];
+        out[i] = acc;
+    }
+}
+
+static double* g_partial = nullptr;
+static size_t g_partial_cap = 0;
+
+static int ensure_partial(size_t n) {
+    if (g_partial_cap >= n) return IPDE_OK;
+    cudaFree(g_partial);
+    g_partial = nullptr; g_partial_cap = 0;
+    CUDA_TRY(cudaMalloc(&g_partial, sizeof(double) * n));
+    g_partial_cap = n;
+    return IPDE_OK;
+}
+
+static void choose_chunks(int64_t nsrc, int64_t ntrg, int* nchunks, int64_t* chunk_len) {
+    const int64_t tblocks = cdiv(ntrg, LAYER_THREADS);
+    const int64_t want = (int64_t)ipde_num_sms() * 4;
+    int64_t c = 1;
+    if (tblocks < want) c = std::min<int64_t>(cdiv(want, tblocks), cdiv(nsrc, LAYER_TILE));
+    if (c < 1) c = 1;
+    if (c > 4096) c = 4096;
+    int64_t len = cdiv(cdiv(nsrc, c), LAYER_TILE) * LAYER_TILE;
+    *nchunks = (int)cdiv(nsrc, len);
+    *chunk_len = len;
+}
+
+int layer_apply_scalar(int kind, double k, const double* sx, const double* sy, const double* q, int64_t nsrc,
+                       const double* tx, const double* ty, int64_t ntrg, double* out, int accumulate, cudaStream_t st) {
+    if (ntrg <= 0) return IPDE_OK;
+    if (nsrc <= 0) {
+        if (!accumulate) CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * ntrg, st));
+        return IPDE_OK;
+    }
+    if (kind == 1) ARG_CHECK(g_k0_ready, "K0 table not set (call ipde_set_k0_table)");
+    int nchunks; int64_t chunk_len;
+    choose_chunks(nsrc, ntrg, &nchunks, &chunk_len);
+    int rc = ensure_partial((size_t)nchunks * ntrg);
+    if (rc) return rc;
+    dim3 grid((unsigned)cdiv(ntrg, LAYER_THREADS), (unsigned)nchunks);
+    if (kind == 0)
+        k_layer_scalar<0><<<grid, LAYER_THREADS, 0, st>>>(sx, sy, q, nsrc, tx, ty, ntrg, k, chunk_len, g_partial);
+    else
+        k_layer_scalar<1><<<grid, LAYER_THREADS, 0, st>>>(sx, sy, q, nsrc, tx, ty, ntrg, k, chunk_len, g_partial);
+    KERNEL_CHECK();
+    k_layer_reduce<<<(int)std::max<int64_t>(1, std::min<int64_t>(cdiv(ntrg, 256), 2048)), 256, 0, st>>>(g_partial, nchunks, ntrg, out, accumulate);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+
+int layer_apply_stokes(const double* sx, const double* sy, const double* fx, const double* fy, int64_t nsrc,
+                       const double* tx, const double* ty, int64_t ntrg, double* out_uvp, int accumulate, cudaStream_t st) {
+    if (ntrg <= 0) return IPDE_OK;
+    if (nsrc <= 0) {
+        if (!accumulate) CUDA_TRY(cudaMemsetAsync(out_uvp, 0, sizeof(double) * 3 * ntrg, st));
+        return IPDE_OK;
+    }
+    int nchunks; int64_t chunk_len;
+    choose_chunks(nsrc, ntrg, &nchunks, &chunk_len);
+    int rc = ensure_partial((size_t)nchunks * 3 * ntrg);
+    if (rc) return rc;
+    dim3 grid((unsigned)cdiv(ntrg, LAYER_THREADS), (unsigned)nchunks);
+    k_layer_stokes<<<grid, LAYER_THREADS, 0, st>>>(sx, sy, fx, fy, nsrc, tx, ty, ntrg, chunk_len, g_partial);
+    KERNEL_CHECK();
+    k_layer_reduce<<<(int)std::max<int64_t>(1, std::min<int64_t>(cdiv(3 * ntrg, 256), 2048)), 256, 0, st>>>(g_partial, nchunks, 3 * ntrg, out_uvp, accumulate);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}

@@ -1,0 +1,195 @@
+// Type-2 nonuniform FFT (uniform spectrum -> values at nonuniform points) in FP64 to ~1e-14:
+// deconvolved zero-padded spectrum -> sigma-oversampled inverse FFT (our own Stockham) -> "exponential
+// of semicircle" kernel interpolation, one warp per target.
+//
+// Replaces near_finder.nufft_interp2d.periodic_interp2d / finufft.nufft2d2(isign=+1, eps=1e-14,
+// modeord=1) at ipde/solvers/multi_boundary/scalar.py:80-88 and ipde/ebdy_collection.py:604-614:
+//      v_j = Re (1/(nx ny)) sum_k fh[k] (i kx)^dx (i ky)^dy exp(+i (k1 x_j + k2 y_j))
+// The unpaired Nyquist modes (k = -n/2 in numpy order) are handled so that the real part of the
+// reference's complex sum is reproduced exactly ("Nyquist modes").
+#include "nufft.cuh"
+#include <algorithm>
+
+static const double TWO_PI = 6.283185307179586476925286766559;
+
+int nufft2_plan_create(int nx, int ny, double xh, double yh, int fx, int fy, int w, double beta, const double* px_host,
+                       const double* py_host, Nufft2Plan** out) {
+    ARG_CHECK(w >= 2 && w <= 32, "kernel width must be in [2, 32]");
+    ARG_CHECK(fx >= nx + w && fy >= ny + w, "fine grid too small");
+    Nufft2Plan* p = new Nufft2Plan();
+    p->nx = nx; p->ny = ny; p->fx = fx; p->fy = fy; p->w = w; p->beta = beta;
+    p->xh = xh; p->yh = yh;
+    // fine grid spacing only matters through the wavenumbers, which the pad kernel takes from the coarse grid
+    int rc = grid_plan_create(fx, fy, 1.0, 1.0, &p->fine);
+    if (rc) { delete p; return rc; }
+    CUDA_TRY(cudaMalloc(&p->px, sizeof(double) * nx));
+    CUDA_TRY(cudaMalloc(&p->py, sizeof(double) * (ny / 2 + 1)));
+    CUDA_TRY(cudaMemcpy(p->px, px_host, sizeof(double) * nx, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(p->py, py_host, sizeof(double) * (ny / 2 + 1), cudaMemcpyHostToDevice));
+    const size_t nspec = (size_t)fx * (fy / 2 + 1);
+    CUDA_TRY(cudaMalloc(&p->fine_spec, sizeof(cplx) * nspec));
+    CUDA_TRY(cudaMalloc(&p->fine_real, sizeof(double) * (size_t)fx * fy));
+    *out = p;
+    return IPDE_OK;
+}
+
+void nufft2_plan_destroy(Nufft2Plan* p) {
+    if (!p) return;
+    grid_plan_destroy(p->fine);
+    cudaFree(p->px); cudaFree(p->py); cudaFree(p->fine_spec); cudaFree(p->fine_real);
+    delete p;
+}
+
+__device__ __forceinline__ int row_of_freq(int i, int n1, int n2) {
+    if (n2 == 1) return i;
+    return n2 * (i % n1) + i / n1;
+}
+__device__ __forceinline__ int freq_of_row2(int pos, int n1, int n2) {
+    if (n2 == 1) return pos;
+    return pos / n2 + n1 * (pos % n2);
+}
+
+// Build the padded, deconvolved fine half-spectrum from a coarse half-spectrum.
+__global__ void k_nufft_pad(const cplx* __restrict__ spec, int nx, int ny, int64_t cpitch, int cn1, int cn2,
+                            cplx* __restrict__ fine, int fx, int fy, int64_t fpitch, int fn1, int fn2,
+                            const double* __restrict__ px, const double* __restrict__ py, double xh, double yh, int dxp,
+                            int dyp, double scale) {
+    const int64_t total = (int64_t)fx * fpitch;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int pos = (int)(t / fpitch), j = (int)(t % fpitch);
+        const int I = freq_of_row2(pos, fn1, fn2);
+        const int sI = (I < (fx + 1) / 2) ? I : I - fx;      // signed fine row frequency
+        cplx v = make_double2(0.0, 0.0);
+        const int hx = nx / 2, hy = ny / 2;
+        const bool x_in = (2 * abs(sI) < nx) || (nx % 2 == 0 && abs(sI) == hx);
+        if (x_in && j <= hy) {
+            const bool x_nyq = (nx % 2 == 0 && abs(sI) == hx);
+            const bool y_nyq = (j == hy);
+            double wgt = 1.0;
+            if (x_nyq) wgt *= 0.5;
+            if (y_nyq) wgt *= 0.5;
+            if (x_nyq && y_nyq) wgt = (sI > 0) ? 0.5 : 0.0;   // exp(-i(nx/2 x + ny/2 y)) pairs only with (+,+)
+            const int ci = (sI >= 0) ? sI : sI + nx;          // coarse frequency index (nx/2 for both +-nx/2)
+            cplx a = spec[(int64_t)row_of_freq(ci, cn1, cn2) * cpitch + j];
+            const double kx = TWO_PI * (double)sI / ((double)nx * xh);
+            const double ky = TWO_PI * (double)j / ((double)ny * yh);
+            a = cscale(a, wgt * scale * px[ci] * py[j]);
+            if (dxp) a = cscale(cmuli(a), kx);
+            if (dyp) a = cscale(cmuli(a), ky);
+            v = a;
+        }
+        fine[t] = v;
+    }
+}
+
+// One warp per target; lanes split the w*w stencil.
+__global__ void k_nufft_interp(const double* __restrict__ fine, int fx, int fy, const double* __restrict__ x,
+                               const double* __restrict__ y, int64_t npts, int w, double beta, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const double half = 0.5 * w;
+    for (int64_t p = warp; p < npts; p += nwarps) {
+        const double X = x[p] * ((double)fx / TWO_PI), Y = y[p] * ((double)fy / TWO_PI);
+        const int i0 = (int)ceil(X - half), j0 = (int)ceil(Y - half);
+        double acc = 0.0;
+        const int npt = w * w;
+        for (int s = lane; s < npt; s += 32) {
+            const int a = s / w, b = s % w;
+            const double zx = ((double)(i0 + a) - X) / half, zy = ((double)(j0 + b) - Y) / half;
+            const double ax = 1.0 - zx * zx, ay = 1.0 - zy * zy;
+            if (ax >= 0.0 && ay >= 0.0) {
+                const double k = exp(beta * (sqrt(ax) - 1.0) + beta * (sqrt(ay) - 1.0));
+                int ii = (i0 + a) % fx; if (ii < 0) ii += fx;
+                int jj = (j0 + b) % fy; if (jj < 0) jj += fy;
+                acc += k * fine[(int64_t)ii * fy + jj];
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) out[p] = acc;
+    }
+}
+
+int nufft2_apply(Nufft2Plan* p, const cplx* spec, int cn1, int cn2, int dxp, int dyp, const double* x, const double* y,
+                 int64_t npts, double* out, cudaStream_t st) {
+    GridPlan* f = p->fine;
+    const int64_t total = (int64_t)p->fx * f->pitch;
+    const int blocks = (int)std::min<int64_t>(cdiv(total, 256), (int64_t)ipde_num_sms() * 8);
+    const double scale = ((double)p->fx * (double)p->fy) / ((double)p->nx * (double)p->ny);
+    k_nufft_pad<<<blocks, 256, 0, st>>>(spec, p->nx, p->ny, p->ny / 2 + 1, cn1, cn2, p->fine_spec, p->fx, p->fy, f->pitch,
+                                        f->n1, f->n2, p->px, p->py, p->xh, p->yh, dxp, dyp, scale);
+    KERNEL_CHECK();
+    int rc = grid_fft2_inverse(f, p->fine_spec, p->fine_spec, p->fine_real, st);
+    if (rc) return rc;
+    if (npts > 0) {
+        const int b2 = (int)std::min<int64_t>(cdiv(npts * 32, 256), (int64_t)ipde_num_sms() * 16);
+        k_nufft_interp<<<b2, 256, 0, st>>>(p->fine_real, p->fx, p->fy, x, y, npts, p->w, p->beta, out);
+        KERNEL_CHECK();
+    }
+    return IPDE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// 1-D variant used for radial -> points: rows of a (nrows, n) spectrum, targets carry a row-independent t.
+int nufft1_plan_create(int n, int fn, int w, double beta, const double* p_host, Nufft1Plan** out) {
+    ARG_CHECK(w >= 2 && w <= 32, "kernel width must be in [2, 32]");
+    Nufft1Plan* p = new Nufft1Plan();
+    p->n = n; p->fn = fn; p->w = w; p->beta = beta;
+    int rc = fft_plan_create(n, &p->coarse);
+    if (!rc) rc = fft_plan_create(fn, &p->fine);
+    if (rc) { nufft1_plan_destroy(p); return rc; }
+    CUDA_TRY(cudaMalloc(&p->dec, sizeof(double) * n));
+    CUDA_TRY(cudaMemcpy(p->dec, p_host, sizeof(double) * n, cudaMemcpyHostToDevice));
+    *out = p;
+    return IPDE_OK;
+}
+
+void nufft1_plan_destroy(Nufft1Plan* p) {
+    if (!p) return;
+    fft_plan_destroy(p->coarse);
+    fft_plan_destroy(p->fine);
+    cudaFree(p->dec); cudaFree(p->buf_c); cudaFree(p->buf_f);
+    delete p;
+}
+
+__global__ void k_real_to_cplx(const double* __restrict__ in, cplx* __restrict__ out, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = make_double2(in[i], 0.0);
+}
+
+// pad a (rows, n) spectrum to (rows, fn) with deconvolution, Nyquist split
+__global__ void k_nufft1_pad(const cplx* __restrict__ spec, cplx* __restrict__ fine, int rows, int n, int fn,
+                             const double* __restrict__ dec, double scale) {
+    const int64_t total = (int64_t)rows * fn;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(t / fn), I = (int)(t % fn);
+        const int sI = (I < (fn + 1) / 2) ? I : I - fn;
+        cplx v = make_double2(0.0, 0.0);
+        const bool nyq = (n % 2 == 0 && abs(sI) == n / 2);
+        if (2 * abs(sI) < n || nyq) {
+            const int ci = (sI >= 0) ? sI : sI + n;
+            v = cscale(spec[(int64_t)r * n + ci], (nyq ? 0.5 : 1.0) * scale * dec[ci]);
+        }
+        fine[t] = v;
+    }
+}
+
+int nufft1_upsample_rows(Nufft1Plan* p, const double* rows_real, int nrows, cudaStream_t st) {
+    const size_t need_c = (size_t)nrows * p->n, need_f = (size_t)nrows * p->fn;
+    if (p->cap_rows < nrows) {
+        cudaFree(p->buf_c); cudaFree(p->buf_f);
+        p->buf_c = nullptr; p->buf_f = nullptr; p->cap_rows = 0;
+        CUDA_TRY(cudaMalloc(&p->buf_c, sizeof(cplx) * need_c));
+        CUDA_TRY(cudaMalloc(&p->buf_f, sizeof(cplx) * need_f));
+        p->cap_rows = nrows;
+    }
+    const int b1 = (int)std::min<int64_t>(cdiv((int64_t)need_c, 256), (int64_t)ipde_num_sms() * 8);
+    k_real_to_cplx<<<b1, 256, 0, st>>>(rows_real, p->buf_c, (int64_t)need_c);
+    KERNEL_CHECK();
+    int rc = fft_rows(p->coarse, p->buf_c, p->buf_c, nrows, p->n, p->n, -1, 1.0, st);
+    if (rc) return rc;
+    const int b2 = (int)std::min<int64_t>(cdiv((int64_t)need_f, 256), (int64_t)ipde_num_sms() * 8);
+    k_nufft1_pad<<<b2, 256, 0, st>>>(p->buf_c, p->buf_f, nrows, p->n, p->fn, p->dec, 1.0 / p->n);
+    KERNEL_CHECK();
+    return fft_rows(p->fine, p->buf_f, p->buf_f, nrows, p->fn, p->fn, +1, 1.0, st);
+}

@@ -1,0 +1,377 @@
+"""
+Device plumbing: torch CUDA tensors as buffers, thin Python objects around the library's
+opaque plans, and the device-resident copy of a registered EmbeddedBoundaryCollection.
+
+PyTorch is used for allocation, host<->device copies and streams only; every computation
+goes through libipde_b200.so (ipde_b200/_lib.py).  No CPU fallback exists: constructing any
+of these without a CUDA device raises.
+"""
+import numpy as np
+import scipy.special
+import torch
+
+from ._lib import lib, IpdeError
+
+F64 = torch.float64
+C128 = torch.complex128
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise IpdeError('ipde_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def to_dev(a, dtype=None):
+    dev = require_cuda()
+    a = np.ascontiguousarray(a)
+    t = torch.from_numpy(a)
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(dev)
+
+
+def empty(shape, dtype=F64):
+    return torch.empty(shape, dtype=dtype, device=require_cuda())
+
+
+def zeros(shape, dtype=F64):
+    return torch.zeros(shape, dtype=dtype, device=require_cuda())
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def hptr(a):
+    """pointer of a host numpy array (kept alive by the caller)"""
+    return a.ctypes.data
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ----------------------------------------------------------------------------------------
+# "exponential of semicircle" kernel (Barnett, Magland, af Klinteberg 2019) for the type-2 NUFFT
+def es_kernel_width(eps=1e-14):
+    return 16 if eps <= 1e-13 else max(4, int(np.ceil(-np.log10(eps/10.0))) + 1)
+
+
+def es_deconvolution(w, beta, n, fn):
+    """
+    factors dec[k], k in FFT order over n coarse modes, such that
+    sum_l b_l phi(x - x_l) reproduces exp(i k x) when b = ifft(dec * delta_k) on the fn-point fine grid
+    """
+    z, wq = np.polynomial.legendre.leggauss(256)
+    phi = np.exp(beta*(np.sqrt(1.0 - z*z) - 1.0))
+    s = np.abs(np.fft.fftfreq(n, 1.0/n))
+    xi = np.pi*w*s/fn
+    I = (np.cos(np.outer(xi, z))*phi).dot(wq)
+    return 2.0/(w*I)
+
+
+_k0_table_set = False
+
+
+def ensure_k0_table():
+    """Chebyshev fit of sqrt(x) e^x K0(x) in t = 4/x - 1 on x >= 2, uploaded once (layer.cu)."""
+    global _k0_table_set
+    if _k0_table_set:
+        return
+    nc = 36
+    t, _ = np.polynomial.chebyshev.chebgauss(4*nc)
+    x = 4.0/(t + 1.0)
+    g = np.sqrt(x)*scipy.special.k0e(x)
+    c = np.polynomial.chebyshev.chebfit(t, g, nc - 1)
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    lib().ipde_set_k0_table(hptr(c), nc)
+    _k0_table_set = True
+
+
+# ----------------------------------------------------------------------------------------
+class FFT1D(object):
+    def __init__(self, n):
+        require_cuda()
+        import ctypes
+        self.n = n
+        h = ctypes.c_void_p()
+        lib().ipde_fft_plan_create(n, ctypes.byref(h))
+        self.h = h
+
+    def __del__(self):
+        try:
+            lib().ipde_fft_plan_destroy(self.h)
+        except Exception:
+            pass
+
+    def c2c(self, x, sign=-1, scale=1.0, out=None):
+        """x: complex128 (..., n) contiguous device tensor"""
+        if out is None:
+            out = torch.empty_like(x)
+        batch = x.numel()//self.n
+        lib().ipde_fft_c2c(self.h, ptr(x), ptr(out), batch, sign, scale, stream())
+        return out
+
+    def mul_fft(self, x, m, out=None):
+        if out is None:
+            out = torch.empty_like(x)
+        lib().ipde_fft_mul_fft(self.h, ptr(x), ptr(out), ptr(m), x.numel()//self.n, stream())
+        return out
+
+
+class GridPlan(object):
+    """Periodic (nx, ny) grid: 2-D real FFT pair, spectral multipliers, differences, interpolation."""
+    def __init__(self, nx, ny, xh, yh):
+        require_cuda()
+        import ctypes
+        self.nx, self.ny, self.xh, self.yh = nx, ny, xh, yh
+        self.pitch = ny//2 + 1
+        h = ctypes.c_void_p()
+        lib().ipde_grid_plan_create(nx, ny, float(xh), float(yh), ctypes.byref(h))
+        self.h = h
+        n1, n2 = ctypes.c_int(), ctypes.c_int()
+        lib().ipde_grid_plan_layout(h, ctypes.byref(n1), ctypes.byref(n2))
+        self.n1, self.n2 = n1.value, n2.value
+
+    def __del__(self):
+        try:
+            lib().ipde_grid_plan_destroy(self.h)
+        except Exception:
+            pass
+
+    def row_of_freq(self):
+        """row position of every frequency index (identity unless the column FFT is split)"""
+        i = np.arange(self.nx)
+        if self.n2 == 1:
+            return i
+        return self.n2*(i % self.n1) + i//self.n1
+
+    def new_spec(self):
+        return empty((self.nx, self.pitch), C128)
+
+    def new_real(self):
+        return empty((self.nx, self.ny), F64)
+
+    def fft2(self, f, spec=None):
+        if spec is None:
+            spec = self.new_spec()
+        lib().ipde_grid_fft2_r2c(self.h, ptr(f), ptr(spec), stream())
+        return spec
+
+    def ifft2(self, spec, work=None, out=None):
+        if work is None:
+            work = self.new_spec()
+        if out is None:
+            out = self.new_real()
+        lib().ipde_grid_fft2_c2r(self.h, ptr(spec), ptr(work), ptr(out), stream())
+        return out
+
+    def spec_to_numpy_full(self, spec):
+        """half spectrum (device, plan row order) -> full (nx, ny) complex numpy array in FFT order (tests)"""
+        s = spec.cpu().numpy()[self.row_of_freq()]
+        full = np.empty((self.nx, self.ny), dtype=complex)
+        full[:, :self.pitch] = s
+        j = np.arange(self.pitch, self.ny)
+        i = (-np.arange(self.nx)) % self.nx
+        full[:, self.pitch:] = np.conj(s[i][:, self.ny - j])
+        return full
+
+
+class Nufft2(object):
+    """Type-2 NUFFT from a GridPlan half spectrum to fixed nonuniform points (angles in [0, 2 pi))."""
+    def __init__(self, grid, x, y, eps=1e-14, sigma=2.0):
+        import ctypes
+        self.grid = grid
+        self.w = es_kernel_width(eps)
+        self.beta = 2.30*self.w
+        self.fx = lib().ipde_fft_next_size(int(np.ceil(sigma*grid.nx)))
+        self.fy = lib().ipde_fft_next_size(int(np.ceil(sigma*grid.ny)))
+        px = np.ascontiguousarray(es_deconvolution(self.w, self.beta, grid.nx, self.fx))
+        py = np.ascontiguousarray(es_deconvolution(self.w, self.beta, grid.ny, self.fy)[:grid.ny//2 + 1])
+        h = ctypes.c_void_p()
+        lib().ipde_nufft2_plan_create(grid.nx, grid.ny, float(grid.xh), float(grid.yh), self.fx, self.fy, self.w,
+                                      self.beta, hptr(px), hptr(py), ctypes.byref(h))
+        self.h = h
+        self.x = to_dev(np.mod(x, 2*np.pi))
+        self.y = to_dev(np.mod(y, 2*np.pi))
+        self.npts = int(self.x.numel())
+
+    def __del__(self):
+        try:
+            lib().ipde_nufft2_plan_destroy(self.h)
+        except Exception:
+            pass
+
+    def __call__(self, spec, dx=0, dy=0, out=None):
+        if out is None:
+            out = empty((self.npts,))
+        lib().ipde_nufft2_apply(self.h, ptr(spec), self.grid.n1, self.grid.n2, dx, dy, ptr(self.x), ptr(self.y),
+                                self.npts, ptr(out), stream())
+        return out
+
+
+class RadialInterpolator(object):
+    """(M, n) radial block -> values at points (theta, t): embedded_boundary.py:419-434 on the device."""
+    def __init__(self, M, n, eps=1e-14, sigma=2.0):
+        import ctypes
+        self.M, self.n = M, n
+        self.w = es_kernel_width(eps)
+        self.beta = 2.30*self.w
+        self.fn = lib().ipde_fft_next_size(int(np.ceil(sigma*n)))
+        dec = np.ascontiguousarray(es_deconvolution(self.w, self.beta, n, self.fn))
+        h = ctypes.c_void_p()
+        lib().ipde_nufft1_plan_create(n, self.fn, self.w, self.beta, hptr(dec), ctypes.byref(h))
+        self.h = h
+        # DCT matrix: a_m = (2/M) sum_i f_i cos(m theta_i), a_0 halved; theta_i = (i + 1/2) pi / M
+        th = (np.arange(M) + 0.5)*np.pi/M
+        C = (2.0/M)*np.cos(np.outer(np.arange(M), th))
+        C[0] *= 0.5
+        self.cmat = to_dev(C)
+        self.coef = empty((M, n))
+
+    def __del__(self):
+        try:
+            lib().ipde_nufft1_plan_destroy(self.h)
+        except Exception:
+            pass
+
+    def __call__(self, fr, theta, t, out=None, out_pos=None):
+        npts = int(theta.numel())
+        if out is None:
+            out = empty((npts,))
+        lib().ipde_radial_to_points(self.h, ptr(self.cmat), self.M, ptr(fr), ptr(self.coef), ptr(theta), ptr(t),
+                                    npts, ptr(out), ptr(out_pos), stream())
+        return out
+
+
+def radial_to_points(fr, transf_r, t):
+    """host convenience used by EmbeddedBoundary.interpolate_radial_to_points"""
+    M, n = fr.shape
+    R = RadialInterpolator(M, n)
+    out = R(to_dev(fr), to_dev(transf_r), to_dev(np.mod(t, 2*np.pi)))
+    return out.cpu().numpy()
+
+
+class DenseLU(object):
+    """LU factors (host scipy.linalg.lu_factor output) kept on the device for two-step solves."""
+    def __init__(self, lu_piv):
+        lu, piv = lu_piv
+        M = lu.shape[0]
+        perm = np.arange(M)
+        for i, p in enumerate(piv):
+            perm[i], perm[p] = perm[p], perm[i]
+        self.M = M
+        self.lu = to_dev(np.ascontiguousarray(lu))
+        self.perm = to_dev(perm.astype(np.int32))
+
+    def solve(self, b, out=None):
+        if out is None:
+            out = empty((self.M,))
+        lib().ipde_lu_solve(ptr(self.lu), ptr(self.perm), ptr(b), ptr(out), self.M, stream())
+        return out
+
+
+def gemv(A, x, out=None):
+    m, n = A.shape
+    if out is None:
+        out = empty((m,))
+    lib().ipde_dense_gemv(ptr(A), ptr(x), ptr(out), m, n, stream())
+    return out
+
+
+def layer_apply_scalar(kind, k, sx, sy, q, tx, ty, out=None, accumulate=False):
+    """kind: 0 Laplace, 1 modified Helmholtz; q already weighted"""
+    if kind == 1:
+        ensure_k0_table()
+    nt = int(tx.numel())
+    if out is None:
+        out = empty((nt,))
+    lib().ipde_layer_apply_scalar(kind, float(k), ptr(sx), ptr(sy), ptr(q), int(sx.numel()), ptr(tx), ptr(ty), nt,
+                                  ptr(out), 1 if accumulate else 0, stream())
+    return out
+
+
+def layer_apply_stokes(sx, sy, fx, fy, tx, ty, out=None, accumulate=False):
+    nt = int(tx.numel())
+    if out is None:
+        out = empty((3, nt))
+    lib().ipde_layer_apply_stokes(ptr(sx), ptr(sy), ptr(fx), ptr(fy), int(sx.numel()), ptr(tx), ptr(ty), nt,
+                                  ptr(out), 1 if accumulate else 0, stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+class DeviceCollection(object):
+    """
+    Device-resident copy of what the per-solve path reads from a registered
+    EmbeddedBoundaryCollection (ipde/ebdy_collection.py:351-526): the compact<->grid index
+    lists, the cutoff, interface and radial point sets, per-boundary annulus coordinates.
+    """
+    def __init__(self, ebdyc):
+        require_cuda()
+        g = ebdyc.grid
+        self.nx, self.ny = g.Nx, g.Ny
+        self.grid = GridPlan(g.Nx, g.Ny, g.xh, g.yh)
+        phys = ebdyc.phys
+        lin = np.flatnonzero(phys.ravel())
+        self.n_phys = lin.size
+        self.phys_lin = to_dev(lin.astype(np.int64))
+        self.step_compact = to_dev(ebdyc.grid_step[phys])
+        # positions (in the compact physical vector) of the phys-not-in-annulus points
+        self.pna_pos = to_dev(ebdyc.phys_inds[ebdyc.phys_not_in_annulus].astype(np.int64))
+        self.n_pna = int(self.pna_pos.numel())
+        self.pnai_x = to_dev(ebdyc.grid_pnai.x)
+        self.pnai_y = to_dev(ebdyc.grid_pnai.y)
+        self.n_pnai = ebdyc.grid_pnai.N
+        self.iv_x = to_dev(ebdyc.all_ivx)
+        self.iv_y = to_dev(ebdyc.all_ivy)
+        self.n_iv = ebdyc.all_ivx.size
+        self.bumpy = to_dev(ebdyc.bumpy) if getattr(ebdyc, 'bumpy_readied', False) else None
+        self.x0, self.y0 = float(g.xv[0]), float(g.yv[0])
+        self._nufft = None
+        self._ebdyc_transf = (ebdyc.interfaces_x_transf, ebdyc.interfaces_y_transf)
+        self.radial_offsets = np.concatenate([[0], np.cumsum(ebdyc.radial_dof_list)]) + self.n_phys
+        self.bdy_offsets = np.concatenate([[0], np.cumsum(ebdyc.bdy_Ns)])
+        self.ebdys = [DeviceBoundary(e) for e in ebdyc]
+        # work buffers for the grid solve
+        self.fc = self.grid.new_real()
+        self.uc = self.grid.new_real()
+        self.uch = self.grid.new_spec()
+        self.spec_work = self.grid.new_spec()
+
+    @property
+    def nufft(self):
+        if self._nufft is None:
+            self._nufft = Nufft2(self.grid, self._ebdyc_transf[0], self._ebdyc_transf[1])
+        return self._nufft
+
+    def interpolate_grid_to_interface(self, f_host, order):
+        """host-array convenience behind ebdyc.interpolate_grid_to_interface (:578-614)"""
+        f = to_dev(np.asarray(f_host, dtype=float))
+        if order == np.inf:
+            spec = self.grid.fft2(f)
+            return self.nufft(spec).cpu().numpy()
+        if order != 3:
+            raise IpdeError('device polynomial interpolation implements order 3 (solver_type="fourth") only')
+        out = empty((self.n_iv,))
+        lib().ipde_grid_interp_cubic(self.grid.h, ptr(f), self.x0, self.y0, ptr(self.iv_x), ptr(self.iv_y),
+                                     self.n_iv, ptr(out), stream())
+        return out.cpu().numpy()
+
+
+class DeviceBoundary(object):
+    def __init__(self, ebdy):
+        self.M, self.n = ebdy.M, ebdy.bdy.N
+        self.interior = ebdy.interior
+        self.ia_theta = to_dev(ebdy.grid_ia_r_transf)
+        self.ia_t = to_dev(np.mod(ebdy.grid_ia_t, 2*np.pi))
+        self.ia_pos = to_dev(np.asarray(ebdy.ia_inds, dtype=np.int64))
+        self.n_ia = int(self.ia_pos.numel())
+        self.radial_x = to_dev(ebdy.radial_x.ravel())
+        self.radial_y = to_dev(ebdy.radial_y.ravel())
+        self.interface_x = to_dev(ebdy.interface.x)
+        self.interface_y = to_dev(ebdy.interface.y)
+        self.interface_nx = to_dev(ebdy.interface.normal_x)
+        self.interface_ny = to_dev(ebdy.interface.normal_y)
+        self.radial_interp = RadialInterpolator(self.M, self.n)

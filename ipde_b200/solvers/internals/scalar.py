@@ -1,0 +1,140 @@
+"""
+Per-boundary helper of the scalar solvers (device implementation).
+
+API mirror of ipde/solvers/internals/scalar.py:5-116 (`ScalarHelper`): annular solve with zero
+boundary data, interface jumps -> QFS effective sources (`sigma_g` for the grid side, `sigma_r`
+for the annulus side), and `correct()` which adds the annulus-side layer potential to the radial
+solution.  State (`ur`, `sigma_r`, `sigma_g`) lives on the device between `__call__` and `correct`.
+"""
+import numpy as np
+import torch
+from ..._lib import lib
+from ...annular import ApproximateAnnularGeometry, RealAnnularGeometry
+from ...device import (to_dev, empty, ptr, stream, DenseLU, gemv, layer_apply_scalar)
+
+
+class DeviceQFS(object):
+    """Device copy of the dense operators of an ipde_b200.qfs.QFS object (two-step apply)."""
+    def __init__(self, qfs):
+        self.qfs = qfs
+        self.M, self.N = qfs.M, qfs.N
+        self.C = to_dev(qfs.C)
+        self.E = DenseLU(qfs.E_lu)
+        self.Eb = DenseLU(qfs.Eb_lu)
+        self.U = to_dev(np.ascontiguousarray(qfs.U_MN))
+        self.sx = to_dev(qfs.source.x)
+        self.sy = to_dev(qfs.source.y)
+        self.sw = to_dev(qfs.source.weights)
+        self.nsrc = qfs.source.N
+        self._v = empty((self.C.shape[0],))
+
+    def __call__(self, tau):
+        gemv(self.C, tau, out=self._v)
+        return self.E.solve(self._v)
+
+    def u2s(self, ub):
+        gemv(self.U, ub, out=self._v)
+        return self.Eb.solve(self._v)
+
+
+class ScalarHelper(object):
+    kernel_kind = None       # 0 Laplace, 1 modified Helmholtz (csrc/layer.cu)
+    k = 0.0
+
+    def __init__(self, ebdy, helper=None, grid_backend='pybie2d'):
+        self.ebdy = ebdy
+        self.grid_backend = grid_backend
+        self.interior = ebdy.interior
+        if helper is None:
+            self.AAG = ApproximateAnnularGeometry(ebdy.bdy.N, ebdy.M, ebdy.radial_width, ebdy.approximate_radius)
+            self._define_annular_solver()
+        else:
+            self.annular_solver = helper.annular_solver if hasattr(helper, 'annular_solver') else helper
+            self.AAG = self.annular_solver.AAG
+        self._set_boundary_estimators()
+        self._get_RAG()
+        self._get_qfs()
+        self._define_layer_apply()
+        self._to_device()
+
+    def _define_annular_solver(self):
+        raise NotImplementedError
+    def _get_qfs(self):
+        raise NotImplementedError
+
+    def _get_RAG(self):
+        bb = self.ebdy.bdy if self.interior else self.ebdy.interface
+        self.RAG = RealAnnularGeometry(bb.speed, bb.curvature, self.annular_solver.AAG)
+
+    def _set_boundary_estimators(self):
+        CO = self.annular_solver.AAG.CO
+        if self.interior:
+            self._bv_estimator, self._bn_estimator = CO.obc_dirichlet[0], CO.obc_neumann[0]
+            self._iv_estimator, self._in_estimator = CO.ibc_dirichlet[0], CO.ibc_neumann[0]
+        else:
+            self._bv_estimator, self._bn_estimator = CO.ibc_dirichlet[0], CO.ibc_neumann[0]
+            self._iv_estimator, self._in_estimator = CO.obc_dirichlet[0], CO.obc_neumann[0]
+
+    def _to_device(self):
+        e = self.ebdy
+        self.d_in_estimator = to_dev(self._in_estimator)
+        self.d_qfs_g = DeviceQFS(self.interface_qfs_g)
+        self.d_qfs_r = DeviceQFS(self.interface_qfs_r)
+        self.d_inx = to_dev(e.interface.normal_x)
+        self.d_iny = to_dev(e.interface.normal_y)
+        self.d_ix = to_dev(e.interface.x)
+        self.d_iy = to_dev(e.interface.y)
+        self.d_rx = to_dev(e.radial_x.ravel())
+        self.d_ry = to_dev(e.radial_y.ravel())
+        n = e.bdy.N
+        self._tau = empty((2*n,))
+        self._w = empty((n,))
+
+    # ---- small (1 x M) . (M, n) products; host arrays in, host arrays out (drop-in use)
+    def get_boundary_values(self, ur):
+        return self._bv_estimator.dot(ur)
+    def get_boundary_normal_derivatives(self, ur):
+        return self._bn_estimator.dot(ur)
+    def get_interface_values(self, ur):
+        return self._iv_estimator.dot(ur)
+    def get_interface_normal_derivatives(self, ur):
+        return self._in_estimator.dot(ur)
+
+    def _define_layer_apply(self):
+        kind, k = self.kernel_kind, self.k
+        def Layer_Apply(src, trg, ch):
+            """u(trg) = sum G(trg - src) ch*src.weights, host arrays (reference Layer_Apply signature)"""
+            q = to_dev(np.asarray(ch, dtype=float)*src.weights)
+            out = layer_apply_scalar(kind, k, to_dev(src.x), to_dev(src.y), q, to_dev(trg.x), to_dev(trg.y))
+            return out.cpu().numpy()
+        self.Layer_Apply = Layer_Apply
+
+    # ---- per-solve, device tensors in and out
+    def __call__(self, fr, bv, bx, by, **kwargs):
+        e = self.ebdy
+        n, M = e.bdy.N, e.M
+        ur = self.annular_solver.solve(self.RAG, fr, None, None, **kwargs)
+        self.iterations_last_call = self.annular_solver.iterations_last_call
+        sign = 1.0 if self.interior else -1.0
+        lib().ipde_scalar_jumps(ptr(bv), ptr(bx), ptr(by), ptr(self.d_inx), ptr(self.d_iny), ptr(ur),
+                                ptr(self.d_in_estimator), M, n, sign, ptr(self._tau), stream())
+        self.sigma_g = self.d_qfs_g(self._tau)
+        self.sigma_r = self.d_qfs_r(self._tau)
+        self.ur = ur
+        return self.sigma_g
+
+    def correct(self, ub):
+        g, r = self.d_qfs_g, self.d_qfs_r
+        n = self.ebdy.bdy.N
+        # field of our own grid-side sources on our own interface
+        q = empty((g.nsrc,))
+        lib().ipde_vec_mul(ptr(self.sigma_g), ptr(g.sw), ptr(q), g.nsrc, stream())
+        layer_apply_scalar(self.kernel_kind, self.k, g.sx, g.sy, q, self.d_ix, self.d_iy, out=self._w)
+        lib().ipde_vec_axpby(1.0, ptr(ub), -1.0, ptr(self._w), ptr(self._w), n, stream())
+        sigma_r_adj = r.u2s(self._w)
+        qr = empty((r.nsrc,))
+        lib().ipde_vec_axpby(1.0, ptr(sigma_r_adj), 1.0, ptr(self.sigma_r), ptr(qr), r.nsrc, stream())
+        lib().ipde_vec_mul(ptr(qr), ptr(r.sw), ptr(qr), r.nsrc, stream())
+        layer_apply_scalar(self.kernel_kind, self.k, r.sx, r.sy, qr, self.d_rx, self.d_ry,
+                           out=self.ur.view(-1), accumulate=True)
+        return self.ur

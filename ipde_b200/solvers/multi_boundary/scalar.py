@@ -1,0 +1,134 @@
+"""
+ScalarSolver: the inhomogeneous scalar solve over an EmbeddedBoundaryCollection, on the device.
+
+API mirror of ipde/solvers/multi_boundary/scalar.py:7-120.  `__call__(f, **kwargs)` takes an
+EmbeddedFunction (host), returns an EmbeddedFunction (host); kwargs (tol, restart, maxiter,
+verbose) go to the annular GMRES.  Between the one host->device copy of `f` and the one
+device->host copy of the result everything runs in libipde_b200.so:
+
+  scatter + cutoff -> (demean) -> 2-D FFT -> multiplier -> inverse FFT            scalar.py:76-78
+  interface values of u, u_x, u_y: type-2 NUFFT of [uh, ikx uh, iky uh]            scalar.py:80-88
+        ('fourth': cubic interpolation of uc and its 4th-order differences          scalar.py:89-95)
+  per boundary: annular solve, jumps, QFS sources                                 scalar.py:100-101
+  all grid-side sources -> (phys, not in annulus) + interface points               scalar.py:104-105,63-71
+  uc[pna] += gu ; helper.correct ; radial -> grid ; mask ; pack                    scalar.py:107-116
+"""
+import numpy as np
+import torch
+from ..._lib import lib
+from ...device import to_dev, empty, ptr, stream, layer_apply_scalar
+from ...embedded_function import EmbeddedFunction, BoundaryFunction
+from ...geometry import BoundaryCollection
+
+
+class ScalarSolver(object):
+    kernel_kind = None
+    grid_kind = None
+    k = 0.0
+
+    def __init__(self, ebdyc, solver_type, helpers, grid_backend):
+        self.ebdyc = ebdyc
+        self.solver_type = solver_type
+        self.grid_backend = grid_backend
+        if helpers is None:
+            helpers = [None]*self.ebdyc.N
+        self.helpers = [self._get_helper(ebdy, helper) for ebdy, helper in zip(self.ebdyc, helpers)]
+        self.grid = self.ebdyc.grid
+        self.kx, self.ky = self.ebdyc.kx, self.ebdyc.ky
+        self.ikx, self.iky = self.ebdyc.ikx, self.ebdyc.iky
+        self.lap = -self.kx*self.kx - self.ky*self.ky
+        self.interpolation_order = 3 if self.solver_type == 'fourth' else np.inf
+        self.grid_step = self.ebdyc.grid_step
+        self._define_layer_apply()
+        self._collect_grid_sources()
+        self._define_grid_evaluator()
+        self.dev = self.ebdyc.device
+        self.iteration_counts = None
+
+    def _collect_grid_sources(self):
+        self.grid_sources = BoundaryCollection()
+        for helper in self.helpers:
+            self.grid_sources.add(helper.interface_qfs_g.source, 'i' if helper.interior else 'e')
+        self.grid_sources.amass_information()
+        self.d_gsx = to_dev(self.grid_sources.x)
+        self.d_gsy = to_dev(self.grid_sources.y)
+        self.d_gsw = to_dev(self.grid_sources.weights)
+        self.source_offsets = np.concatenate([[0], np.cumsum(self.grid_sources.Ns)])
+
+    def _get_helper(self, ebdy, helper):
+        raise NotImplementedError
+
+    def _define_grid_evaluator(self):
+        if self.grid_backend not in (None, 'pybie2d', 'fmm2d', 'flexmm'):
+            raise Exception('grid_backend not recognized')
+        # every string backend of the reference is a sum over all sources; here: the direct device sum
+        self.split_grid_evaluation = False
+
+    def _define_layer_apply(self):
+        self.Layer_Apply = self.helpers[0].Layer_Apply
+
+    def get_boundary_values(self, u):
+        bv = BoundaryFunction(self.ebdyc)
+        bv.load_data([helper.get_boundary_values(ur) for ur, helper in zip(u, self.helpers)])
+        return bv
+
+    def get_boundary_normal_derivatives(self, u):
+        bv = BoundaryFunction(self.ebdyc)
+        bv.load_data([helper.get_boundary_normal_derivatives(ur) for ur, helper in zip(u, self.helpers)])
+        return bv
+
+    # ------------------------------------------------------------------------------------
+    def solve_device(self, f_dev, **kwargs):
+        """f_dev: flat device vector [phys grid | radial blocks] -> flat device vector, same layout."""
+        D = self.dev
+        L = lib()
+        st = stream()
+        if self.grid_kind == 0 and D.bumpy is None:
+            raise Exception('Poisson solver requires ebdyc.ready_bump(...) before solving.')
+        L.ipde_grid_scatter_cutoff(D.grid.h, ptr(f_dev), ptr(D.phys_lin), ptr(D.step_compact), D.n_phys,
+                                   ptr(D.fc), st)
+        L.ipde_grid_solve_scalar(D.grid.h, self.grid_kind, float(self.k), ptr(D.fc), ptr(D.bumpy), ptr(D.uch),
+                                 ptr(D.spec_work), ptr(D.uc), st)
+        # interface values and gradient of the grid solution
+        if self.interpolation_order == np.inf:
+            nu = D.nufft
+            bvs, bxs, bys = nu(D.uch, 0, 0), nu(D.uch, 1, 0), nu(D.uch, 0, 1)
+        else:
+            ucx, ucy = D.grid.new_real(), D.grid.new_real()
+            L.ipde_grid_fd4(D.grid.h, ptr(D.uc), ptr(ucx), ptr(ucy), st)
+            bvs, bxs, bys = empty((D.n_iv,)), empty((D.n_iv,)), empty((D.n_iv,))
+            for src, dst in ((D.uc, bvs), (ucx, bxs), (ucy, bys)):
+                L.ipde_grid_interp_cubic(D.grid.h, ptr(src), D.x0, D.y0, ptr(D.iv_x), ptr(D.iv_y), D.n_iv,
+                                         ptr(dst), st)
+        self._interface_values = (bvs, bxs, bys)
+        # per-boundary annular solves and effective sources
+        sigmag = empty((self.grid_sources.N,))
+        for b, helper in enumerate(self.helpers):
+            r0, r1 = D.radial_offsets[b], D.radial_offsets[b + 1]
+            o0, o1 = D.bdy_offsets[b], D.bdy_offsets[b + 1]
+            fr = f_dev[r0:r1].view(helper.ebdy.M, helper.ebdy.bdy.N)
+            sg = helper(fr, bvs[o0:o1], bxs[o0:o1], bys[o0:o1], **kwargs)
+            s0, s1 = self.source_offsets[b], self.source_offsets[b + 1]
+            L.ipde_vec_mul(ptr(sg), ptr(self.d_gsw[s0:s1]), ptr(sigmag[s0:s1]), int(s1 - s0), st)
+        self.iteration_counts = [helper.iterations_last_call for helper in self.helpers]
+        # all grid-side sources -> (phys, not in annulus) U (interface points)
+        out = layer_apply_scalar(self.kernel_kind, self.k, self.d_gsx, self.d_gsy, sigmag, D.pnai_x, D.pnai_y)
+        # pack the result: grid part
+        res = empty((self.ebdyc.dof,))
+        L.ipde_grid_gather(ptr(D.uc), ptr(D.phys_lin), D.n_phys, ptr(res), st)
+        L.ipde_index_add(ptr(res), ptr(D.pna_pos), ptr(out), D.n_pna, st)
+        # radial part
+        for b, helper in enumerate(self.helpers):
+            o0, o1 = D.bdy_offsets[b], D.bdy_offsets[b + 1]
+            ur = helper.correct(out[D.n_pna + o0:D.n_pna + o1])
+            db = D.ebdys[b]
+            db.radial_interp(ur, db.ia_theta, db.ia_t, out=res, out_pos=db.ia_pos)
+            r0, r1 = D.radial_offsets[b], D.radial_offsets[b + 1]
+            res[r0:r1].copy_(ur.view(-1))
+        return res
+
+    def __call__(self, f, **kwargs):
+        """f must be of type EmbeddedFunction"""
+        f_dev = to_dev(np.asarray(f, dtype=float))
+        res = self.solve_device(f_dev, **kwargs)
+        return EmbeddedFunction(self.ebdyc, linear_data=res.cpu().numpy())

@@ -1,0 +1,48 @@
+"""Shared small problem setups for the parity tests (seeded / deterministic geometry)."""
+import numpy as np
+from ipde_b200.geometry import GSB, Grid, star, squished_circle
+from ipde_b200.embedded_boundary import EmbeddedBoundary
+from ipde_b200.ebdy_collection import EmbeddedBoundaryCollection
+from ipde_b200.embedded_function import EmbeddedFunction
+from ipde_b200.slepian import SlepianMollifier
+
+
+def single_star(nb=200, M=8, a=0.1, f=5, ng=None, bump=False, slepian_r=None):
+    """examples/interior_modified_helmholtz.py geometry: star in [-1.2, 1.2]^2"""
+    bdy = GSB(c=star(nb, a=a, f=f))
+    bh = bdy.dt*bdy.speed.min()
+    if ng is None:
+        ng = 2*int(0.5*2.4//bh)
+    grid = Grid([-1.2, 1.2], ng, [-1.2, 1.2], ng)
+    MOL = SlepianMollifier(2*M if slepian_r is None else slepian_r)
+    ebdy = EmbeddedBoundary(bdy, True, M, bh, heaviside=MOL.step)
+    ebdyc = EmbeddedBoundaryCollection([ebdy])
+    ebdyc.register_grid(grid)
+    if bump:
+        ebdyc.ready_bump(MOL.bump, (1.2 - ebdy.radial_width, 1.2 - ebdy.radial_width), ebdy.radial_width)
+    return ebdyc
+
+
+def three_bodies(nb=100, M=8, bump=False):
+    """scaled-down examples/multi_modified_helmholtz.py: interior star + two exterior bodies"""
+    bdy1 = GSB(c=star(4*nb, r=1.0, a=0.05, f=7))
+    bdy2 = GSB(c=squished_circle(nb, x=-0.4, y=-0.25, r=0.25, b=0.6, rot=-np.pi/4))
+    bdy3 = GSB(c=star(nb, x=0.35, y=0.2, r=0.22, a=0.1, f=3))
+    bdys = [bdy1, bdy2, bdy3]
+    bh = min(b.dt*b.speed.min() for b in bdys)
+    MOL = SlepianMollifier(2*M)
+    ebdys = [EmbeddedBoundary(b, b is bdy1, M, bh, heaviside=MOL.step) for b in bdys]
+    ebdyc = EmbeddedBoundaryCollection(ebdys)
+    ebdyc.generate_grid(force_square=True)
+    if bump:
+        ebdyc.ready_bump(MOL.bump)
+    return ebdyc
+
+
+def manufactured(ebdyc, helmholtz_k, kk=8*np.pi/3):
+    sol = lambda x, y: np.exp(np.sin(kk*x))*np.sin(kk*y)
+    lap = lambda x, y: kk**2*np.exp(np.sin(kk*x))*np.sin(kk*y)*(np.cos(kk*x)**2 - np.sin(kk*x) - 1.0)
+    force = lambda x, y: helmholtz_k**2*sol(x, y) - lap(x, y)
+    f = EmbeddedFunction(ebdyc, function=force if helmholtz_k != 0 else lap)
+    ua = EmbeddedFunction(ebdyc, function=sol)
+    return f, ua, sol

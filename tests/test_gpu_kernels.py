@@ -1,0 +1,275 @@
+"""GPU: every kernel of libipde_b200.so against NumPy/SciPy or the oracle (through the C ABI)."""
+import os
+import numpy as np
+import pytest
+import scipy.linalg
+import scipy.sparse
+import scipy.special
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return np.abs(a - b).max()/max(np.abs(b).max(), 1e-300)
+
+
+@pytest.fixture(scope='module')
+def D():
+    import torch
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    import ipde_b200.device as dev
+    return dev
+
+
+@pytest.mark.parametrize('n', [8, 60, 64, 96, 100, 1000, 1024, 1430, 4096, 7168, 8192, 30030])
+def test_fft_c2c(D, n):
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((3, n)) + 1j*rng.standard_normal((3, n))
+    p = D.FFT1D(n)
+    xd = D.to_dev(x)
+    y = p.c2c(xd, -1).cpu().numpy()
+    assert rel(y, np.fft.fft(x)) < 1e-14*np.log2(n)
+    z = p.c2c(D.to_dev(y), +1, 1.0/n).cpu().numpy()
+    assert rel(z, x) < 1e-14*np.log2(n)
+    # in place
+    p.c2c(xd, -1, out=xd)
+    assert rel(xd.cpu().numpy(), np.fft.fft(x)) < 1e-14*np.log2(n)
+
+
+@pytest.mark.parametrize('n', [96, 1024, 9000])
+def test_fft_mul_fft(D, n):
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((5, n)) + 1j*rng.standard_normal((5, n))
+    m = rng.standard_normal((5, n))
+    p = D.FFT1D(n)
+    y = p.mul_fft(D.to_dev(x), D.to_dev(m)).cpu().numpy()
+    assert rel(y, np.fft.fft(m*np.fft.ifft(x))) < 1e-13
+
+
+@pytest.mark.parametrize('shape', [(64, 64), (96, 80), (100, 36), (2048, 128), (128, 2048), (4096, 64), (6000, 20)])
+def test_grid_fft2(D, shape):
+    nx, ny = shape
+    rng = np.random.default_rng(nx + ny)
+    f = rng.standard_normal(shape)
+    g = D.GridPlan(nx, ny, 0.1, 0.1)
+    spec = g.fft2(D.to_dev(f))
+    full = g.spec_to_numpy_full(spec)
+    assert rel(full, np.fft.fft2(f)) < 3e-14
+    back = g.ifft2(spec).cpu().numpy()
+    assert rel(back, f) < 3e-14
+
+
+@pytest.mark.parametrize('kind,k', [(1, 2.5), (0, 0.0)])
+@pytest.mark.parametrize('shape', [(96, 80), (2048, 64)])
+def test_grid_solve_scalar(D, kind, k, shape):
+    from ipde_b200._lib import lib
+    nx, ny = shape
+    xh, yh = 2.4/nx, 2.0/ny
+    rng = np.random.default_rng(7)
+    f = rng.standard_normal(shape)
+    bumpy = np.abs(rng.standard_normal(shape))
+    bumpy /= bumpy.sum()*xh*yh
+    g = D.GridPlan(nx, ny, xh, yh)
+    fc, uch, work, uc = D.to_dev(f), g.new_spec(), g.new_spec(), g.new_real()
+    lib().ipde_grid_solve_scalar(g.h, kind, k, D.ptr(fc), D.ptr(D.to_dev(bumpy)), D.ptr(uch), D.ptr(work), D.ptr(uc), D.stream())
+    kx = np.fft.fftfreq(nx, xh/(2*np.pi))[:, None]
+    ky = np.fft.fftfreq(ny, yh/(2*np.pi))
+    lap = -kx*kx - ky*ky
+    if kind == 0:
+        ff = f - f.sum()*xh*yh*bumpy
+        lap[0, 0] = np.inf
+        ref_h = np.fft.fft2(ff)/lap
+    else:
+        ref_h = np.fft.fft2(f)/(k*k - lap)
+    ref = np.fft.ifft2(ref_h).real
+    assert rel(uc.cpu().numpy(), ref) < 1e-12
+    assert rel(g.spec_to_numpy_full(uch), ref_h) < 1e-12
+
+
+@pytest.mark.parametrize('shape', [(48, 40), (2048, 32)])
+def test_nufft2_against_direct_sum(D, shape):
+    from oracle.solvers import nudft2d_type2
+    nx, ny = shape
+    xh, yh = 2.4/nx, 3.0/ny
+    rng = np.random.default_rng(3)
+    f = rng.standard_normal(shape)
+    g = D.GridPlan(nx, ny, xh, yh)
+    spec = g.fft2(D.to_dev(f))
+    x = rng.uniform(0, 2*np.pi, 37)
+    y = rng.uniform(0, 2*np.pi, 37)
+    x[0], y[0] = 0.0, 0.0
+    x[1], y[1] = 2*np.pi*(1 - 1e-12), 1e-9
+    nu = D.Nufft2(g, x, y)
+    fh = np.fft.fft2(f)
+    kx = np.fft.fftfreq(nx, xh/(2*np.pi))[:, None]
+    ky = np.fft.fftfreq(ny, yh/(2*np.pi))
+    ref = nudft2d_type2(np.stack([fh, 1j*kx*fh, 1j*ky*fh]), x, y).real
+    scale = [np.abs(f).max(), np.abs(kx).max()*np.abs(f).max(), np.abs(ky).max()*np.abs(f).max()]
+    for i, (dx, dy) in enumerate([(0, 0), (1, 0), (0, 1)]):
+        v = nu(spec, dx, dy).cpu().numpy()
+        assert np.abs(v - ref[i]).max()/scale[i] < 2e-13, (dx, dy)
+
+
+@pytest.mark.parametrize('M,n', [(8, 40), (16, 300), (20, 1000)])
+def test_radial_to_points(D, M, n):
+    from oracle.solvers import interpolate_radial_to_points
+    rng = np.random.default_rng(M*n)
+    fr = rng.standard_normal((M, n))
+    th, t = rng.uniform(0, np.pi, 211), rng.uniform(0, 2*np.pi, 211)
+    th[0], t[0] = 0.0, 0.0
+    th[1] = np.pi
+    R = D.RadialInterpolator(M, n)
+    v = R(D.to_dev(fr), D.to_dev(th), D.to_dev(t)).cpu().numpy()
+    ref = interpolate_radial_to_points(fr, th, t)
+    assert np.abs(v - ref).max() < 2e-13*max(1.0, np.abs(ref).max())
+
+
+def test_k0(D):
+    from ipde_b200._lib import lib
+    D.ensure_k0_table()
+    x = np.concatenate([np.geomspace(1e-8, 2.0, 2000), np.linspace(2.0, 60.0, 4000), [100.0, 300.0, 700.0]])
+    out = D.empty((x.size,))
+    lib().ipde_eval_k0(D.ptr(D.to_dev(x)), D.ptr(out), x.size, D.stream())
+    ref = scipy.special.k0(x)
+    ok = ref > 0
+    assert np.abs(out.cpu().numpy()[ok]/ref[ok] - 1).max() < 1e-14
+
+
+@pytest.mark.parametrize('kind,k', [(0, 0.0), (1, 3.0)])
+@pytest.mark.parametrize('ns,nt', [(50, 7), (700, 3000), (5000, 129)])
+def test_layer_apply_scalar(D, kind, k, ns, nt):
+    from oracle.solvers import layer_apply
+    rng = np.random.default_rng(ns + nt)
+    sx, sy, q = rng.uniform(-1, 1, ns), rng.uniform(-1, 1, ns), rng.standard_normal(ns)
+    tx, ty = rng.uniform(-1, 1, nt) + 2.5, rng.uniform(-1, 1, nt)
+    out = D.layer_apply_scalar(kind, k, D.to_dev(sx), D.to_dev(sy), D.to_dev(q), D.to_dev(tx), D.to_dev(ty))
+    ref = layer_apply('laplace' if kind == 0 else 'mh', k, sx, sy, q, tx, ty)
+    assert rel(out.cpu().numpy(), ref) < 1e-13
+    out2 = D.layer_apply_scalar(kind, k, D.to_dev(sx), D.to_dev(sy), D.to_dev(q), D.to_dev(tx), D.to_dev(ty), out=out, accumulate=True)
+    assert rel(out2.cpu().numpy(), 2*ref) < 1e-13
+
+
+def test_layer_apply_stokes(D):
+    rng = np.random.default_rng(5)
+    ns, nt = 300, 500
+    sx, sy = rng.uniform(-1, 1, ns), rng.uniform(-1, 1, ns)
+    fx, fy = rng.standard_normal(ns), rng.standard_normal(ns)
+    tx, ty = rng.uniform(-1, 1, nt) + 2.5, rng.uniform(-1, 1, nt)
+    out = D.layer_apply_stokes(*[D.to_dev(a) for a in (sx, sy, fx, fy, tx, ty)]).cpu().numpy()
+    dx, dy = tx[:, None] - sx, ty[:, None] - sy
+    r2 = dx*dx + dy*dy
+    L = -0.5*np.log(r2)
+    rf = (dx*fx + dy*fy)/r2
+    u = ((L*fx + rf*dx).sum(1))/(4*np.pi)
+    v = ((L*fy + rf*dy).sum(1))/(4*np.pi)
+    p = rf.sum(1)/(2*np.pi)
+    assert rel(out[0], u) < 1e-13 and rel(out[1], v) < 1e-13 and rel(out[2], p) < 1e-13
+
+
+@pytest.mark.parametrize('M', [5, 64, 200, 1000])
+def test_gemv_and_lu_solve(D, M):
+    rng = np.random.default_rng(M)
+    A = rng.standard_normal((M, M)) + M*np.eye(M)*0.1
+    x = rng.standard_normal(M)
+    y = D.gemv(D.to_dev(A), D.to_dev(x)).cpu().numpy()
+    assert rel(y, A.dot(x)) < 1e-13
+    B = rng.standard_normal((M, 2*M + 3))
+    z = rng.standard_normal(2*M + 3)
+    assert rel(D.gemv(D.to_dev(B), D.to_dev(z)).cpu().numpy(), B.dot(z)) < 1e-13
+    lu = scipy.linalg.lu_factor(A)
+    sol = D.DenseLU(lu).solve(D.to_dev(y)).cpu().numpy()
+    ref = scipy.linalg.lu_solve(lu, y)
+    assert rel(sol, ref) < 1e-11
+    assert rel(A.dot(sol), y) < 1e-12
+
+
+def test_lu_solve_ill_conditioned_is_backward_stable(D):
+    # smooth-kernel matrix like the QFS check<-source map: tiny singular values, benign right-hand sides
+    n = 400
+    t = 2*np.pi*np.arange(n)/n
+    src = 1.3*np.exp(1j*t)
+    chk = 1.0*np.exp(1j*t)
+    E = -np.log(np.abs(chk[:, None] - src[None, :]))/(2*np.pi)*(2*np.pi*1.3/n)
+    rhs = np.exp(np.cos(t))*np.sin(2*t)
+    lu = scipy.linalg.lu_factor(E)
+    sol = D.DenseLU(lu).solve(D.to_dev(rhs)).cpu().numpy()
+    assert np.abs(E.dot(sol) - rhs).max() < 1e-11*max(1.0, np.abs(sol).max())
+
+
+def test_csr_spmv(D):
+    from ipde_b200._lib import lib
+    rng = np.random.default_rng(11)
+    blocks = [rng.standard_normal((6, 6)) for _ in range(50)]
+    A = scipy.sparse.block_diag(blocks, 'csr')
+    x = rng.standard_normal(A.shape[1])
+    y = D.empty((A.shape[0],))
+    ip, ix = D.to_dev(A.indptr.astype(np.int32)), D.to_dev(A.indices.astype(np.int32))
+    lib().ipde_csr_spmv_d(D.ptr(ip), D.ptr(ix), D.ptr(D.to_dev(A.data)), D.ptr(D.to_dev(x)), D.ptr(y), A.shape[0], D.stream())
+    assert rel(y.cpu().numpy(), A.dot(x)) < 1e-14
+    Az = A.astype(complex)*(1 + 0.5j)
+    xz = x + 1j*rng.standard_normal(x.size)
+    import torch
+    yz = torch.empty(A.shape[0], dtype=torch.complex128, device='cuda')
+    lib().ipde_csr_spmv_z(D.ptr(ip), D.ptr(ix), D.ptr(D.to_dev(Az.data)), D.ptr(D.to_dev(xz)), D.ptr(yz), A.shape[0], D.stream())
+    assert rel(yz.cpu().numpy(), Az.dot(xz)) < 1e-14
+
+
+def test_fd4_and_cubic_interp(D):
+    from ipde_b200._lib import lib
+    from oracle.solvers import fd_x_4, fd_y_4, lagrange_interp2d_periodic
+    rng = np.random.default_rng(2)
+    nx, ny, xh, yh = 40, 36, 0.1, 0.12
+    f = rng.standard_normal((nx, ny))
+    g = D.GridPlan(nx, ny, xh, yh)
+    fx, fy = g.new_real(), g.new_real()
+    lib().ipde_grid_fd4(g.h, D.ptr(D.to_dev(f)), D.ptr(fx), D.ptr(fy), D.stream())
+    assert rel(fx.cpu().numpy(), fd_x_4(f, xh)) < 1e-14
+    assert rel(fy.cpu().numpy(), fd_y_4(f, yh)) < 1e-14
+    px, py = rng.uniform(-1, 3, 100), rng.uniform(-1, 3, 100)
+    out = D.empty((100,))
+    lib().ipde_grid_interp_cubic(g.h, D.ptr(D.to_dev(f)), -1.0, -1.0, D.ptr(D.to_dev(px)), D.ptr(D.to_dev(py)), 100, D.ptr(out), D.stream())
+    ref = lagrange_interp2d_periodic(f, -1.0, -1.0, xh, yh, px, py, 3)
+    assert rel(out.cpu().numpy(), ref) < 1e-13
+
+
+def test_annular_against_reference_golden(D, golden_dir):
+    from ipde_b200.annular import (ApproximateAnnularGeometry, RealAnnularGeometry,
+                                   AnnularModifiedHelmholtzSolver, AnnularPoissonSolver)
+    g = np.load(os.path.join(golden_dir, 'annular_scalar.npz'))
+    n = int(g['n'])
+    AAG = ApproximateAnnularGeometry(n, int(g['M']), float(g['width']), float(g['approx_r']))
+    RAG = RealAnnularGeometry(g['speed'], g['curvature'], AAG)
+    S = AnnularModifiedHelmholtzSolver(AAG, float(g['mh_k']))
+    S.RAG = RAG
+    v = g['mh_apply_in']
+    assert rel(S._apply(v), g['mh_apply_out']) < 1e-13
+    assert rel(S._optim_preconditioner(v), g['mh_prec_out']) < 1e-11
+    u = S.solve(RAG, g['mh_f'], g['mh_ig'], g['mh_og'], tol=1e-14, maxiter=10, restart=50)
+    assert np.abs(u - g['mh_u']).max() < 1e-12
+    assert S.iterations_last_call < 40
+    u0 = S.solve(RAG, g['mh_f'], None, None, tol=1e-14, maxiter=10, restart=50)
+    assert np.abs(u0 - g['mh_u_zero_bc']).max() < 1e-12
+    P = AnnularPoissonSolver(AAG)
+    up = P.solve(RAG, g['po_f'], g['mh_ig'], g['mh_og'], tol=1e-14, maxiter=10, restart=50)
+    assert np.abs(up - g['po_u']).max() < 1e-12
+
+
+def test_annular_restart_and_iteration_parity_with_oracle(D):
+    from ipde_b200 import annular as A
+    from oracle import annular as O
+    n, M, width = 200, 12, 0.12
+    t = np.linspace(0, 2*np.pi, n, endpoint=False)
+    c = (1 + 0.2*np.cos(3*t))*np.exp(1j*t)
+    from ipde_b200.geometry import GSB
+    b = GSB(c=c)
+    rng = np.random.default_rng(0)
+    f = rng.standard_normal((M, n))
+    kw = dict(tol=1e-12, restart=8, maxiter=30)
+    Ao = O.ApproximateAnnularGeometry(n, M, width, 1.0)
+    So = O.AnnularModifiedHelmholtzSolver(Ao, 4.0)
+    uo = So.solve(O.RealAnnularGeometry(b.speed, b.curvature, Ao), f, np.zeros(n), np.zeros(n), **kw)
+    Ad = A.ApproximateAnnularGeometry(n, M, width, 1.0)
+    Sd = A.AnnularModifiedHelmholtzSolver(Ad, 4.0)
+    ud = Sd.solve(A.RealAnnularGeometry(b.speed, b.curvature, Ad), f, None, None, **kw)
+    assert rel(ud, uo) < 1e-10
+    assert abs(Sd.iterations_last_call - So.iterations_last_call) <= 2

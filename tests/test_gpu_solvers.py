@@ -1,0 +1,85 @@
+"""GPU: end-to-end parity of the solver classes against the CPU oracle on identical inputs."""
+import numpy as np
+import pytest
+from problems import single_star, three_bodies, manufactured
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-11     # BASELINE.json north_star: 1e-11 relative L2 / L-inf in FP64
+
+
+def rel_errors(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    linf = np.abs(a - b).max()/np.abs(b).max()
+    l2 = np.linalg.norm(a - b)/np.linalg.norm(b)
+    return linf, l2
+
+
+def oracle_for(solver, kind, k, solver_type):
+    from oracle.solvers import OracleScalarSolver
+    pairs = [(h.interface_qfs_g, h.interface_qfs_r) for h in solver.helpers]
+    return OracleScalarSolver(solver.ebdyc, kind, k, solver_type, pairs)
+
+
+@pytest.mark.parametrize('solver_type', ['spectral', 'fourth'])
+def test_modified_helmholtz_single_boundary(solver_type):
+    from ipde_b200.solvers.multi_boundary.modified_helmholtz import ModifiedHelmholtzSolver
+    ebdyc = single_star(nb=200, M=8)
+    f, ua, _ = manufactured(ebdyc, 2.0)
+    solver = ModifiedHelmholtzSolver(ebdyc, 2.0, solver_type=solver_type)
+    ue = solver(f, tol=1e-13, restart=40, maxiter=5)
+    O = oracle_for(solver, 'modified_helmholtz', 2.0, solver_type)
+    uo = O(f, tol=1e-13, restart=40, maxiter=5)
+    linf, l2 = rel_errors(ue, uo)
+    assert linf < TOL and l2 < TOL, (linf, l2)
+    assert abs(solver.iteration_counts[0] - O.iteration_counts[0]) <= 2
+    # drop-in surface
+    assert ue.shape == f.shape and ue[0].shape == (8, 200)
+    bv = solver.get_boundary_values(ue)
+    assert bv.shape == (200,)
+
+
+def test_poisson_single_boundary():
+    from ipde_b200.solvers.multi_boundary.poisson import PoissonSolver
+    ebdyc = single_star(nb=200, M=8, bump=True)
+    f, ua, _ = manufactured(ebdyc, 0.0)
+    solver = PoissonSolver(ebdyc)
+    ue = solver(f, tol=1e-13, restart=40, maxiter=5)
+    uo = oracle_for(solver, 'poisson', 0.0, 'spectral')(f, tol=1e-13, restart=40, maxiter=5)
+    linf, l2 = rel_errors(ue, uo)
+    assert linf < TOL and l2 < TOL, (linf, l2)
+
+
+def test_modified_helmholtz_three_boundaries():
+    from ipde_b200.solvers.multi_boundary.modified_helmholtz import ModifiedHelmholtzSolver
+    ebdyc = three_bodies(nb=100, M=8)
+    f, ua, _ = manufactured(ebdyc, 5.0, kk=10*np.pi/7)
+    solver = ModifiedHelmholtzSolver(ebdyc, 5.0)
+    ue = solver(f, tol=1e-13, restart=60, maxiter=5)
+    uo = oracle_for(solver, 'modified_helmholtz', 5.0, 'spectral')(f, tol=1e-13, restart=60, maxiter=5)
+    linf, l2 = rel_errors(ue, uo)
+    assert linf < TOL and l2 < TOL, (linf, l2)
+    # linearity of the whole path (size-independent property)
+    ue2 = solver(2.5*f, tol=1e-13, restart=60, maxiter=5)
+    linf, l2 = rel_errors(ue2, 2.5*np.asarray(ue))
+    assert linf < 1e-10
+
+
+def test_converges_to_manufactured_solution():
+    """interior MH + homogeneous Dirichlet correction by MFS lands on the reference's convergence curve"""
+    from ipde_b200.solvers.multi_boundary.modified_helmholtz import ModifiedHelmholtzSolver
+    from ipde_b200.qfs import Modified_Helmholtz_QFS
+    import ipde_b200.device as D
+    ebdyc = single_star(nb=600, M=16)
+    f, ua, sol = manufactured(ebdyc, 2.0)
+    solver = ModifiedHelmholtzSolver(ebdyc, 2.0)
+    ue = solver(f, tol=1e-14, restart=50, maxiter=5)
+    bdy = ebdyc[0].bdy
+    qb = Modified_Helmholtz_QFS(bdy, True, True, True, 2.0, tol=1e-13)
+    sig = qb.u2s(sol(bdy.x, bdy.y) - solver.get_boundary_values(ue)[0])
+    pts = ebdyc.grid_and_radial_pts
+    corr = D.layer_apply_scalar(1, 2.0, D.to_dev(qb.source.x), D.to_dev(qb.source.y), D.to_dev(sig*qb.source.weights),
+                                D.to_dev(pts.x), D.to_dev(pts.y)).cpu().numpy()
+    err = np.abs(np.asarray(ue) + corr - np.asarray(ua)).max()
+    # reference table errs16 at nb=600: 1.33e-9 (examples/interior_modified_helmholtz_using_multi.py:26)
+    assert err < 2e-9, err

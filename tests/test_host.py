@@ -1,0 +1,97 @@
+"""CPU: host-side setup code (geometry, cutoffs, QFS) and the C-ABI surface."""
+import os
+import re
+import numpy as np
+import pytest
+from ipde_b200.geometry import GSB, star, fourier_resample
+from ipde_b200.slepian import SlepianMollifier
+from ipde_b200 import qfs as Q
+from problems import single_star, three_bodies
+
+
+def test_slepian_matches_reference_tables(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'slepian_golden.npz'))
+    x = g['x']
+    for r in [4, 8, 16, 24, 30, 32, 40, 60]:
+        S = SlepianMollifier(r)
+        assert np.abs(S.step(x) - g['step_%d' % r]).max() < 2e-14
+        assert np.abs(S.bump(x) - g['bump_%d' % r]).max() < 2e-14
+
+
+def test_gsb_circle():
+    b = GSB(c=1.5*np.exp(1j*np.linspace(0, 2*np.pi, 64, endpoint=False)))
+    assert np.abs(b.curvature - 1/1.5).max() < 1e-13
+    assert np.abs(b.normal_x - np.cos(b.t)).max() < 1e-13
+    assert abs(b.perimeter - 3*np.pi) < 1e-12
+
+
+def test_fourier_resample_roundtrip():
+    t = np.linspace(0, 2*np.pi, 32, endpoint=False)
+    f = np.exp(np.sin(t)) + 0.1*np.cos(16*t)
+    up = fourier_resample(f, 96)
+    assert np.abs(up[::3] - f).max() < 1e-13
+    assert np.abs(fourier_resample(up, 32) - f).max() < 1e-13
+
+
+def test_local_coordinates_identity():
+    ebdyc = single_star(nb=200, M=8)
+    e = ebdyc[0]
+    bdy = e.bdy
+    k = np.fft.fftfreq(bdy.N, 1.0/bdy.N)
+    ch = np.fft.fft(bdy.c)
+    E = np.exp(1j*np.outer(e.grid_ia_t, k))
+    X = E.dot(ch)/bdy.N
+    Xp = E.dot(ch*1j*k)/bdy.N
+    nrm = -1j*Xp/np.abs(Xp)
+    z = X + e.grid_ia_r*nrm
+    assert np.abs(z - (e.grid_ia_x + 1j*e.grid_ia_y)).max() < 1e-12
+    assert e.grid_ia_r.max() <= 0 and e.grid_ia_r.min() >= -e.radial_width
+
+
+def test_collection_bookkeeping():
+    ebdyc = three_bodies(nb=60, M=6)
+    assert ebdyc.phys.sum() == ebdyc.grid_phys.N
+    assert ebdyc.grid_pna.N + sum(len(e.grid_ia_xind) for e in ebdyc) == ebdyc.grid_phys.N
+    assert ebdyc.grid_step.max() <= 1.0 + 1e-14
+    # every annulus point is physical
+    for e in ebdyc:
+        assert ebdyc.phys[e.grid_ia_xind, e.grid_ia_yind].all()
+
+
+@pytest.mark.parametrize('interior', [True, False])
+def test_qfs_green_identity_modified_helmholtz(interior):
+    import scipy.special as ss
+    k = 3.0
+    bdy = GSB(c=star(300, a=0.15, f=5))
+    tt = np.linspace(0, 2*np.pi, 333, endpoint=False)
+    q = Q.Modified_Helmholtz_QFS(bdy, interior, True, True, k, tol=1e-13)
+    if interior:
+        u = lambda x, y: np.exp(k*(0.6*x + 0.8*y))/10
+        un = k*u(bdy.x, bdy.y)*(0.6*bdy.normal_x + 0.8*bdy.normal_y)
+        sig = q([un, -u(bdy.x, bdy.y)])
+        z = (1 + 0.15*np.cos(5*tt))*np.exp(1j*tt)*0.995
+        ex = u(z.real, z.imag)
+    else:
+        x0, y0 = 0.1, 0.2
+        r = np.hypot(bdy.x - x0, bdy.y - y0)
+        ue = ss.k0(k*r)/(2*np.pi)
+        uen = -k*ss.k1(k*r)/(2*np.pi)*((bdy.x - x0)*bdy.normal_x + (bdy.y - y0)*bdy.normal_y)/r
+        sig = q([-uen, ue])
+        z = (1 + 0.15*np.cos(5*tt))*np.exp(1j*tt)*1.005
+        ex = ss.k0(k*np.hypot(z.real - x0, z.imag - y0))/(2*np.pi)
+    val = Q.layer_apply_matrix_free(q.kernel, q.source, z.real, z.imag, sig)
+    assert np.abs(val - ex).max() < 5e-12
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from ipde_b200._lib import lib, parse_header, LIB_PATH
+    protos = parse_header()
+    assert len(protos) >= 45
+    L = lib()         # raises if a declared symbol is missing from the .so
+    assert L.ipde_version() >= 100
+    import subprocess
+    out = subprocess.run(['nm', '-D', '--defined-only', LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r' T (ipde_\w+)', out))
+    assert set(protos) <= exported
+    # nothing torch-typed in the ABI
+    assert 'torch' not in open(os.path.join(os.path.dirname(LIB_PATH), '..', 'include', 'ipde_b200.h')).read()

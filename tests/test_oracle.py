@@ -1,0 +1,80 @@
+"""CPU: the oracle against golden vectors produced by the reference's own code (oracle/make_golden.py)."""
+import os
+import numpy as np
+from oracle.annular import (ApproximateAnnularGeometry, RealAnnularGeometry,
+                            AnnularModifiedHelmholtzSolver, AnnularPoissonSolver)
+from oracle import solvers as osol
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_chebyshev_operators_match_reference(golden_dir):
+    g = _load(golden_dir, 'annular_scalar.npz')
+    AAG = ApproximateAnnularGeometry(int(g['n']), int(g['M']), float(g['width']), float(g['approx_r']))
+    for name in ['D00', 'D01', 'D12', 'R01', 'R12', 'R02', 'P10', 'VI1', 'ibc_dirichlet', 'obc_dirichlet',
+                 'ibc_neumann', 'obc_neumann']:
+        assert np.abs(getattr(AAG.CO, name) - g['CO_' + name]).max() < 1e-12, name
+    assert np.abs(AAG.rv0 - g['rv0']).max() < 1e-15
+    RAG = RealAnnularGeometry(g['speed'], g['curvature'], AAG)
+    assert np.abs(RAG.psi1 - g['psi1']).max() < 1e-14
+
+
+def test_annular_mh_apply_precond_solve_match_reference(golden_dir):
+    g = _load(golden_dir, 'annular_scalar.npz')
+    n = int(g['n'])
+    AAG = ApproximateAnnularGeometry(n, int(g['M']), float(g['width']), float(g['approx_r']))
+    RAG = RealAnnularGeometry(g['speed'], g['curvature'], AAG)
+    S = AnnularModifiedHelmholtzSolver(AAG, float(g['mh_k']))
+    S.RAG = RAG
+    v = g['mh_apply_in']
+    ref = g['mh_apply_out']
+    assert np.abs(S._apply(v) - ref).max() <= 1e-13*np.abs(ref).max()
+    refp = g['mh_prec_out']
+    assert np.abs(S._preconditioner(v) - refp).max() <= 1e-11*np.abs(refp).max()
+    u = S.solve(RAG, g['mh_f'], g['mh_ig'], g['mh_og'], tol=1e-14, maxiter=10, restart=50)
+    assert np.abs(u - g['mh_u']).max() < 1e-13
+    u0 = S.solve(RAG, g['mh_f'], np.zeros(n), np.zeros(n), tol=1e-14, maxiter=10, restart=50)
+    assert np.abs(u0 - g['mh_u_zero_bc']).max() < 1e-13
+
+
+def test_annular_poisson_matches_reference(golden_dir):
+    g = _load(golden_dir, 'annular_scalar.npz')
+    AAG = ApproximateAnnularGeometry(int(g['n']), int(g['M']), float(g['width']), float(g['approx_r']))
+    RAG = RealAnnularGeometry(g['speed'], g['curvature'], AAG)
+    P = AnnularPoissonSolver(AAG)
+    up = P.solve(RAG, g['po_f'], g['mh_ig'], g['mh_og'], tol=1e-14, maxiter=10, restart=50)
+    assert np.abs(up - g['po_u']).max() < 1e-13
+
+
+def test_fd_derivatives_match_reference(golden_dir):
+    g = _load(golden_dir, 'misc_golden.npz')
+    assert np.abs(osol.fd_x_4(g['f'], float(g['h'])) - g['fdx']).max() < 1e-13
+    assert np.abs(osol.fd_y_4(g['f'], float(g['h'])) - g['fdy']).max() < 1e-13
+
+
+def test_nudft_is_inverse_dft_on_grid():
+    rng = np.random.default_rng(0)
+    f = rng.standard_normal((12, 10))
+    fh = np.fft.fft2(f)
+    x = 2*np.pi*np.arange(12)/12
+    y = 2*np.pi*np.arange(10)/10
+    X, Y = np.meshgrid(x, y, indexing='ij')
+    v = osol.nudft2d_type2(fh, X.ravel(), Y.ravel())[0]
+    assert np.abs(v.real - f.ravel()).max() < 1e-13
+
+
+def test_radial_interpolation_reproduces_nodes():
+    rng = np.random.default_rng(1)
+    M, n = 8, 16
+    # smooth function of (theta, t)
+    th = (np.arange(M) + 0.5)*np.pi/M
+    t = 2*np.pi*np.arange(n)/n
+    fr = np.cos(2*th)[:, None]*np.sin(3*t)[None, :] + 0.3*np.cos(th)[:, None]
+    T, TT = np.meshgrid(th, t, indexing='ij')
+    v = osol.interpolate_radial_to_points(fr, T.ravel(), TT.ravel())
+    assert np.abs(v - fr.ravel()).max() < 1e-13
+    tq, tt = rng.uniform(0, np.pi, 20), rng.uniform(0, 2*np.pi, 20)
+    v = osol.interpolate_radial_to_points(fr, tq, tt)
+    assert np.abs(v - (np.cos(2*tq)*np.sin(3*tt) + 0.3*np.cos(tq))).max() < 1e-13
