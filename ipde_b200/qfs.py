@@ -14,17 +14,19 @@ fundamental solutions", Adv. Comput. Math. 2022), in its desingularised form:
   * the layer potential S[tau_s] + D[tau_d] is evaluated on the check curve by the
     periodic trapezoid rule on a rho_f-times upsampled boundary (spectrally accurate at
     that distance), and the source strengths solve  E sigma = C tau  with E the
-    check<-source matrix.  The solve is applied in two steps (C tau, then LU
-    substitution): E is exponentially ill-conditioned and a pre-multiplied E^-1 C
-    loses all accuracy, while the two-step form is backward stable.
+    check<-source matrix.  E is exponentially ill-conditioned, so a pre-multiplied
+    E^-1 C loses all accuracy; the solve is kept factored, E = U S V^T (truncated SVD):
+    sigma = V (S^+ ((U^T C) tau)) -- two well-conditioned mat-vecs and a diagonal scaling,
+    which is backward stable, gives the minimum-norm strengths, and is insensitive to
+    summation order (what makes CPU-oracle / GPU parity at 1e-11 possible).
   * `u2s(ub)`: strengths whose potential equals `ub` on the boundary nodes
     (collocation on the boundary itself, upsampled to M points).
 
 What the per-solve path needs from an instance -- `source` (a curve object with x, y,
 weights), `__call__([slp, dlp]) -> sigma`, `u2s(ub) -> sigma` -- matches the reference's
-usage.  The dense operators (`C`, LU of `E`, LU of `Eb`) are exposed as arrays so that the
-CUDA library applies them on the device; the NumPy `__call__` below is the setup-time /
-oracle-side statement of the same arithmetic.
+usage.  The dense operators (`A = U^T C`, `Sinv`, `V` and their u2s counterparts) are exposed as
+arrays so that the CUDA library applies them on the device; the NumPy `__call__` below is the
+setup-time / oracle-side statement of the same arithmetic.
 
 Kernel normalisations follow the reference's in-tree pins: Laplace -log r/(2 pi)
 (grid_evaluators/laplace_grid_evaluator.py:8-12), modified Helmholtz K0(kr)/(2 pi)
@@ -133,6 +135,7 @@ class QFS(object):
         self.alpha_c = a_c if alpha_c is None else alpha_c
         self.rho = (r if rho is None else rho)*source_upsample_factor
         self.rho_f = r_f if rho_f is None else rho_f
+        self.svd_cut = min(1e-11, max(1e-14, tol))
         self._build()
 
     def _build(self):
@@ -142,21 +145,24 @@ class QFS(object):
         h = bdy.max_h
         M = 2*int(np.ceil(self.rho*N/2.0))
         self.N, self.M = N, M
-        bM = GSB(c=fourier_resample(bdy.c, M))
         # evaluation side: inside -> check curve inward (-n), sources outward (+n)
         sgn = 1.0 if self.interior else -1.0
+        # keep the source curve regular: the offset curve x + d n has speed |x'|(1 + kappa d), which must
+        # stay well away from zero; pay for a closer source curve with more source points
+        worst = np.max(-sgn*bdy.curvature)
+        if worst > 0.0 and self.alpha_s*h*worst > 0.4:
+            self.alpha_s = 0.4/(worst*h)
+            L = np.log(1.0/max(self.tol, 1e-15))
+            self.rho = max(self.rho, min(8.0, 1.0 + L/(TWO_PI*(self.alpha_s + self.alpha_c))))
+            M = 2*int(np.ceil(self.rho*N/2.0))
+            self.M = M
+        bM = GSB(c=fourier_resample(bdy.c, M))
         self.source = GSB(c=offset_curve(bM, sgn*self.alpha_s*h))
         self.check = GSB(c=offset_curve(bM, -sgn*self.alpha_c*h))
         src, chk = self.source, self.check
         w_s = np.tile(src.weights, nc)
-        # check <- source
-        E = ker.slp(chk.x, chk.y, src.x, src.y)*w_s[None, :]
-        self.E_lu = scipy.linalg.lu_factor(E)
-        # boundary(M nodes) <- source, for u2s
-        Eb = ker.slp(bM.x, bM.y, src.x, src.y)*w_s[None, :]
-        self.Eb_lu = scipy.linalg.lu_factor(Eb)
         UM = fourier_resample_matrix(N, M)
-        self.U_MN = UM if nc == 1 else scipy.linalg.block_diag(*([UM]*nc))
+        U_MN = UM if nc == 1 else scipy.linalg.block_diag(*([UM]*nc))
         # check <- boundary densities through the upsampled trapezoid rule
         Nf = self.rho_f*N
         bF = GSB(c=fourier_resample(bdy.c, Nf))
@@ -169,7 +175,20 @@ class QFS(object):
         if self.has_dlp:
             K = ker.dlp(chk.x, chk.y, bF.x, bF.y, bF.normal_x, bF.normal_y)*np.tile(w_f, nc)[None, :]
             blocks.append(self._times_upsample(K, UF, nc))
-        self.C = np.ascontiguousarray(np.hstack(blocks))      # (nc*M) x (nlayers*nc*N)
+        C = np.hstack(blocks)                                  # (nc*M) x (nlayers*nc*N)
+        # check <- source and boundary(M nodes) <- source, each as a truncated SVD  E = U S V^T
+        E = ker.slp(chk.x, chk.y, src.x, src.y)*w_s[None, :]
+        self.A, self.Sinv, self.V = self._factor(E, C)
+        Eb = ker.slp(bM.x, bM.y, src.x, src.y)*w_s[None, :]
+        self.Ab, self.Sinv_b, self.Vb = self._factor(Eb, U_MN)
+
+    def _factor(self, E, rhs_op):
+        """E = U S V^T  ->  (U^T rhs_op, 1/S with tiny singular values dropped, V), all C-contiguous."""
+        U, S, Vt = _svd(E)
+        keep = S > self.svd_cut*S[0]
+        Sinv = np.where(keep, 1.0/np.where(keep, S, 1.0), 0.0)
+        return (np.ascontiguousarray(U.T.dot(rhs_op)), np.ascontiguousarray(Sinv),
+                np.ascontiguousarray(Vt.T))
 
     @staticmethod
     def _times_upsample(K, UF, nc):
@@ -178,10 +197,23 @@ class QFS(object):
 
     def __call__(self, tau_list):
         tau = np.concatenate([np.asarray(t, dtype=float).ravel() for t in tau_list])
-        return scipy.linalg.lu_solve(self.E_lu, self.C.dot(tau))
+        return self.V.dot(self.Sinv*self.A.dot(tau))
 
     def u2s(self, ub):
-        return scipy.linalg.lu_solve(self.Eb_lu, self.U_MN.dot(np.asarray(ub, dtype=float).ravel()))
+        return self.Vb.dot(self.Sinv_b*self.Ab.dot(np.asarray(ub, dtype=float).ravel()))
+
+
+def _svd(E):
+    """SVD on the host; large systems go through torch on the GPU when one is present (setup only)."""
+    if E.shape[0] > 2500:
+        try:
+            import torch
+            if torch.cuda.is_available():
+                U, S, Vh = torch.linalg.svd(torch.from_numpy(E).cuda())
+                return U.cpu().numpy(), S.cpu().numpy(), Vh.cpu().numpy()
+        except Exception:
+            pass
+    return scipy.linalg.svd(E)
 
 
 class Laplace_QFS(QFS):

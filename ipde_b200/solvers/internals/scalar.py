@@ -10,31 +10,33 @@ import numpy as np
 import torch
 from ..._lib import lib
 from ...annular import ApproximateAnnularGeometry, RealAnnularGeometry
-from ...device import (to_dev, empty, ptr, stream, DenseLU, gemv, layer_apply_scalar)
+from ...device import (to_dev, empty, ptr, stream, gemv, layer_apply_scalar)
 
 
 class DeviceQFS(object):
-    """Device copy of the dense operators of an ipde_b200.qfs.QFS object (two-step apply)."""
+    """Device copy of the factored operators of an ipde_b200.qfs.QFS object."""
     def __init__(self, qfs):
         self.qfs = qfs
         self.M, self.N = qfs.M, qfs.N
-        self.C = to_dev(qfs.C)
-        self.E = DenseLU(qfs.E_lu)
-        self.Eb = DenseLU(qfs.Eb_lu)
-        self.U = to_dev(np.ascontiguousarray(qfs.U_MN))
+        self.A, self.Sinv, self.V = to_dev(qfs.A), to_dev(qfs.Sinv), to_dev(qfs.V)
+        self.Ab, self.Sinv_b, self.Vb = to_dev(qfs.Ab), to_dev(qfs.Sinv_b), to_dev(qfs.Vb)
         self.sx = to_dev(qfs.source.x)
         self.sy = to_dev(qfs.source.y)
         self.sw = to_dev(qfs.source.weights)
         self.nsrc = qfs.source.N
-        self._v = empty((self.C.shape[0],))
+        self._w = empty((self.A.shape[0],))
+
+    def _two_step(self, A, Sinv, V, x):
+        n = self._w.numel()
+        gemv(A, x, out=self._w)
+        lib().ipde_vec_mul(ptr(self._w), ptr(Sinv), ptr(self._w), n, stream())
+        return gemv(V, self._w)
 
     def __call__(self, tau):
-        gemv(self.C, tau, out=self._v)
-        return self.E.solve(self._v)
+        return self._two_step(self.A, self.Sinv, self.V, tau)
 
     def u2s(self, ub):
-        gemv(self.U, ub, out=self._v)
-        return self.Eb.solve(self._v)
+        return self._two_step(self.Ab, self.Sinv_b, self.Vb, ub)
 
 
 class ScalarHelper(object):

@@ -70,8 +70,8 @@ def test_grid_solve_scalar(D, kind, k, shape):
     bumpy = np.abs(rng.standard_normal(shape))
     bumpy /= bumpy.sum()*xh*yh
     g = D.GridPlan(nx, ny, xh, yh)
-    fc, uch, work, uc = D.to_dev(f), g.new_spec(), g.new_spec(), g.new_real()
-    lib().ipde_grid_solve_scalar(g.h, kind, k, D.ptr(fc), D.ptr(D.to_dev(bumpy)), D.ptr(uch), D.ptr(work), D.ptr(uc), D.stream())
+    fc, uch, work, uc, bd = D.to_dev(f), g.new_spec(), g.new_spec(), g.new_real(), D.to_dev(bumpy)
+    lib().ipde_grid_solve_scalar(g.h, kind, k, D.ptr(fc), D.ptr(bd), D.ptr(uch), D.ptr(work), D.ptr(uc), D.stream())
     kx = np.fft.fftfreq(nx, xh/(2*np.pi))[:, None]
     ky = np.fft.fftfreq(ny, yh/(2*np.pi))
     lap = -kx*kx - ky*ky
@@ -129,7 +129,8 @@ def test_k0(D):
     D.ensure_k0_table()
     x = np.concatenate([np.geomspace(1e-8, 2.0, 2000), np.linspace(2.0, 60.0, 4000), [100.0, 300.0, 700.0]])
     out = D.empty((x.size,))
-    lib().ipde_eval_k0(D.ptr(D.to_dev(x)), D.ptr(out), x.size, D.stream())
+    xd = D.to_dev(x)
+    lib().ipde_eval_k0(D.ptr(xd), D.ptr(out), x.size, D.stream())
     ref = scipy.special.k0(x)
     ok = ref > 0
     assert np.abs(out.cpu().numpy()[ok]/ref[ok] - 1).max() < 1e-14
@@ -204,13 +205,15 @@ def test_csr_spmv(D):
     x = rng.standard_normal(A.shape[1])
     y = D.empty((A.shape[0],))
     ip, ix = D.to_dev(A.indptr.astype(np.int32)), D.to_dev(A.indices.astype(np.int32))
-    lib().ipde_csr_spmv_d(D.ptr(ip), D.ptr(ix), D.ptr(D.to_dev(A.data)), D.ptr(D.to_dev(x)), D.ptr(y), A.shape[0], D.stream())
+    dd, xd = D.to_dev(A.data), D.to_dev(x)      # keep the device buffers alive across the call
+    lib().ipde_csr_spmv_d(D.ptr(ip), D.ptr(ix), D.ptr(dd), D.ptr(xd), D.ptr(y), A.shape[0], D.stream())
     assert rel(y.cpu().numpy(), A.dot(x)) < 1e-14
     Az = A.astype(complex)*(1 + 0.5j)
     xz = x + 1j*rng.standard_normal(x.size)
     import torch
     yz = torch.empty(A.shape[0], dtype=torch.complex128, device='cuda')
-    lib().ipde_csr_spmv_z(D.ptr(ip), D.ptr(ix), D.ptr(D.to_dev(Az.data)), D.ptr(D.to_dev(xz)), D.ptr(yz), A.shape[0], D.stream())
+    dz, xzd = D.to_dev(Az.data), D.to_dev(xz)
+    lib().ipde_csr_spmv_z(D.ptr(ip), D.ptr(ix), D.ptr(dz), D.ptr(xzd), D.ptr(yz), A.shape[0], D.stream())
     assert rel(yz.cpu().numpy(), Az.dot(xz)) < 1e-14
 
 
@@ -222,12 +225,14 @@ def test_fd4_and_cubic_interp(D):
     f = rng.standard_normal((nx, ny))
     g = D.GridPlan(nx, ny, xh, yh)
     fx, fy = g.new_real(), g.new_real()
-    lib().ipde_grid_fd4(g.h, D.ptr(D.to_dev(f)), D.ptr(fx), D.ptr(fy), D.stream())
+    fd = D.to_dev(f)
+    lib().ipde_grid_fd4(g.h, D.ptr(fd), D.ptr(fx), D.ptr(fy), D.stream())
     assert rel(fx.cpu().numpy(), fd_x_4(f, xh)) < 1e-14
     assert rel(fy.cpu().numpy(), fd_y_4(f, yh)) < 1e-14
     px, py = rng.uniform(-1, 3, 100), rng.uniform(-1, 3, 100)
     out = D.empty((100,))
-    lib().ipde_grid_interp_cubic(g.h, D.ptr(D.to_dev(f)), -1.0, -1.0, D.ptr(D.to_dev(px)), D.ptr(D.to_dev(py)), 100, D.ptr(out), D.stream())
+    pxd, pyd = D.to_dev(px), D.to_dev(py)
+    lib().ipde_grid_interp_cubic(g.h, D.ptr(fd), -1.0, -1.0, D.ptr(pxd), D.ptr(pyd), 100, D.ptr(out), D.stream())
     ref = lagrange_interp2d_periodic(f, -1.0, -1.0, xh, yh, px, py, 3)
     assert rel(out.cpu().numpy(), ref) < 1e-13
 

@@ -24,7 +24,7 @@ def oracle_for(solver, kind, k, solver_type):
 @pytest.mark.parametrize('solver_type', ['spectral', 'fourth'])
 def test_modified_helmholtz_single_boundary(solver_type):
     from ipde_b200.solvers.multi_boundary.modified_helmholtz import ModifiedHelmholtzSolver
-    ebdyc = single_star(nb=200, M=8)
+    ebdyc = single_star(nb=300, M=8)
     f, ua, _ = manufactured(ebdyc, 2.0)
     solver = ModifiedHelmholtzSolver(ebdyc, 2.0, solver_type=solver_type)
     ue = solver(f, tol=1e-13, restart=40, maxiter=5)
@@ -34,14 +34,14 @@ def test_modified_helmholtz_single_boundary(solver_type):
     assert linf < TOL and l2 < TOL, (linf, l2)
     assert abs(solver.iteration_counts[0] - O.iteration_counts[0]) <= 2
     # drop-in surface
-    assert ue.shape == f.shape and ue[0].shape == (8, 200)
+    assert ue.shape == f.shape and ue[0].shape == (8, 300)
     bv = solver.get_boundary_values(ue)
-    assert bv.shape == (200,)
+    assert bv.shape == (300,)
 
 
 def test_poisson_single_boundary():
     from ipde_b200.solvers.multi_boundary.poisson import PoissonSolver
-    ebdyc = single_star(nb=200, M=8, bump=True)
+    ebdyc = single_star(nb=300, M=8, bump=True)
     f, ua, _ = manufactured(ebdyc, 0.0)
     solver = PoissonSolver(ebdyc)
     ue = solver(f, tol=1e-13, restart=40, maxiter=5)
@@ -70,7 +70,7 @@ def test_converges_to_manufactured_solution():
     from ipde_b200.solvers.multi_boundary.modified_helmholtz import ModifiedHelmholtzSolver
     from ipde_b200.qfs import Modified_Helmholtz_QFS
     import ipde_b200.device as D
-    ebdyc = single_star(nb=600, M=16)
+    ebdyc = single_star(nb=600, M=16, ng=256)
     f, ua, sol = manufactured(ebdyc, 2.0)
     solver = ModifiedHelmholtzSolver(ebdyc, 2.0)
     ue = solver(f, tol=1e-14, restart=50, maxiter=5)
