@@ -31,6 +31,7 @@ extern "C" {
 const char* ipde_last_error(void);
 int ipde_version(void);
 int ipde_device_sm_count(void);
+int64_t ipde_launch_count(void);   /* kernels launched by this library since load */
 
 /* ---- 1-D FFT (batched, contiguous lines).  Replaces numpy.fft.fft / ifft, ipde/utilities.py:5-12. */
 int ipde_fft_plan_create(int n, void** plan);
@@ -108,8 +109,10 @@ int ipde_annular_solve(void* plan, const double* f, const double* ig, const doub
 
 /* ---- layer potentials from point sources: pybie2d *_Layer_Apply / pyfmmlib2d.SFMM,
  *      ipde/solvers/internals/poisson.py:34-35, modified_helmholtz.py:37, stokes.py:26-35 */
-int ipde_set_k0_table(const double* cheb_host, int ncheb);
+/* Chebyshev tables (host) of sqrt(x) e^x K0(x), sqrt(x) e^x K1(x) in t = 4/x - 1 for x >= 2 */
+int ipde_set_k0_table(const double* cheb0_host, const double* cheb1_host, int ncheb);
 int ipde_eval_k0(const double* x, double* out, int64_t n, void* stream);
+int ipde_eval_k1(const double* x, double* out, int64_t n, void* stream);
 int ipde_layer_apply_scalar(int kind, double k, const double* sx, const double* sy, const double* q,
                             int64_t nsrc, const double* tx, const double* ty, int64_t ntrg, double* out,
                             int accumulate, void* stream);

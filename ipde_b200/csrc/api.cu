@@ -19,6 +19,10 @@ void ipde_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+void ipde_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 #define ST(s) ((cudaStream_t)(s))
 #define CP(p) (reinterpret_cast<const cplx*>(p))
 #define MP(p) (reinterpret_cast<cplx*>(p))
@@ -28,6 +32,7 @@ extern "C" {
 const char* ipde_last_error(void) { return g_err; }
 int ipde_version(void) { return 100; }
 int ipde_device_sm_count(void) { return ipde_num_sms(); }
+int64_t ipde_launch_count(void) { return (int64_t)g_launches.load(); }
 
 // ---- FFT
 int ipde_fft_plan_create(int n, void** plan) {
@@ -170,8 +175,9 @@ int ipde_annular_solve(void* plan, const double* f, const double* ig, const doub
 }
 
 // ---- layer potentials
-int ipde_set_k0_table(const double* cheb_host, int ncheb) { return layer_set_k0_table(cheb_host, ncheb); }
-int ipde_eval_k0(const double* x, double* out, int64_t n, void* stream) { return layer_eval_k0(x, out, n, ST(stream)); }
+int ipde_set_k0_table(const double* cheb0_host, const double* cheb1_host, int ncheb) { return layer_set_k0_table(cheb0_host, cheb1_host, ncheb); }
+int ipde_eval_k0(const double* x, double* out, int64_t n, void* stream) { return layer_eval_k0(x, out, n, 0, ST(stream)); }
+int ipde_eval_k1(const double* x, double* out, int64_t n, void* stream) { return layer_eval_k0(x, out, n, 1, ST(stream)); }
 int ipde_layer_apply_scalar(int kind, double k, const double* sx, const double* sy, const double* q, int64_t nsrc,
                             const double* tx, const double* ty, int64_t ntrg, double* out, int accumulate, void* stream) {
     return layer_apply_scalar(kind, k, sx, sy, q, nsrc, tx, ty, ntrg, out, accumulate, ST(stream));

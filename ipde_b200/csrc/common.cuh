@@ -14,6 +14,7 @@
 #define IPDE_ERR_UNSUPPORTED 3
 
 void ipde_set_error(const char* fmt, ...);
+void ipde_count_launch();   // every kernel launch of this library is counted (bench.py: gpu_launches)
 
 #define CUDA_TRY(expr)                                                              \
     do {                                                                            \
@@ -25,7 +26,11 @@ void ipde_set_error(const char* fmt, ...);
         }                                                                           \
     } while (0)
 
-#define KERNEL_CHECK() CUDA_TRY(cudaGetLastError())
+#define KERNEL_CHECK()                  \
+    do {                                \
+        ipde_count_launch();            \
+        CUDA_TRY(cudaGetLastError());   \
+    } while (0)
 
 #define ARG_CHECK(cond, msg)                                                        \
     do {                                                                            \

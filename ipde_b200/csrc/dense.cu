@@ -143,8 +143,10 @@ int dense_lu_solve(const double* LU, const int* perm, const double* b, double* x
     void* args[] = {(void*)&LU, (void*)&x, (void*)&M};
     int g1 = std::min(coop_grid((const void*)k_trsv_lower_unit), std::max(1, (M + TRI_B - 1) / TRI_B * 2));
     CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_trsv_lower_unit, dim3(g1), dim3(TRI_THREADS), args, 0, st));
+    ipde_count_launch();
     int g2 = std::min(coop_grid((const void*)k_trsv_upper), std::max(1, (M + TRI_B - 1) / TRI_B * 2));
     CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_trsv_upper, dim3(g2), dim3(TRI_THREADS), args, 0, st));
+    ipde_count_launch();
     return IPDE_OK;
 }
 

@@ -14,53 +14,43 @@
 #include "layer.cuh"
 #include <algorithm>
 
-#define K0_MAX_CHEB 40
+#include "bessel.cuh"
 __constant__ double c_k0_cheb[K0_MAX_CHEB];
+__constant__ double c_k1_cheb[K0_MAX_CHEB];
 __constant__ int c_k0_ncheb;
-__constant__ double c_k0_a[16];   // 1/(m!)^2
-__constant__ double c_k0_b[16];   // H_m/(m!)^2
+__constant__ double c_k0_a[16];
+__constant__ double c_k0_b[16];
+__constant__ double c_k1_a[16];
+__constant__ double c_k1_b[16];
 static bool g_k0_ready = false;
+bool bessel_tables_ready() { return g_k0_ready; }
 
-int layer_set_k0_table(const double* cheb, int ncheb) {
+int layer_set_k0_table(const double* cheb, const double* cheb1, int ncheb) {
     ARG_CHECK(ncheb >= 2 && ncheb <= K0_MAX_CHEB, "bad Chebyshev table length");
     CUDA_TRY(cudaMemcpyToSymbol(c_k0_cheb, cheb, sizeof(double) * ncheb));
+    CUDA_TRY(cudaMemcpyToSymbol(c_k1_cheb, cheb1, sizeof(double) * ncheb));
     CUDA_TRY(cudaMemcpyToSymbol(c_k0_ncheb, &ncheb, sizeof(int)));
-    double a[16], b[16];
+    double a[16], b[16], a1[16], b1[16];
     double fact = 1.0, H = 0.0;
     for (int m = 0; m < 16; ++m) {
         if (m > 0) { fact *= m; H += 1.0 / m; }
         a[m] = 1.0 / (fact * fact);
         b[m] = H / (fact * fact);
+        const double f1 = fact * fact * (m + 1);            // m! (m+1)!
+        a1[m] = 1.0 / f1;
+        b1[m] = (H + H + 1.0 / (m + 1)) / (2.0 * f1);
     }
     CUDA_TRY(cudaMemcpyToSymbol(c_k0_a, a, sizeof(a)));
     CUDA_TRY(cudaMemcpyToSymbol(c_k0_b, b, sizeof(b)));
+    CUDA_TRY(cudaMemcpyToSymbol(c_k1_a, a1, sizeof(a1)));
+    CUDA_TRY(cudaMemcpyToSymbol(c_k1_b, b1, sizeof(b1)));
     g_k0_ready = true;
     return IPDE_OK;
 }
 
-// K0(x) for x > 0, given x and x^2
-__device__ __forceinline__ double bessel_k0(double x, double x2) {
-    if (x <= 2.0) {
-        const double y = 0.25 * x2;
-        double i0 = c_k0_a[15], s = c_k0_b[15];
-#pragma unroll
-        for (int m = 14; m >= 0; --m) {
-            i0 = fma(i0, y, c_k0_a[m]);
-            s = fma(s, y, c_k0_b[m]);
-        }
-        const double EULER = 0.57721566490153286061;
-        return -(0.5 * log(y) + EULER) * i0 + s;
-    }
-    const double t = 4.0 / x - 1.0, t2 = 2.0 * t;
-    const int nc = c_k0_ncheb;
-    double b0 = 0.0, b1 = 0.0;
-    for (int m = nc - 1; m >= 1; --m) {
-        const double tmp = fma(t2, b0, c_k0_cheb[m]) - b1;
-        b1 = b0;
-        b0 = tmp;
-    }
-    const double p = fma(t, b0, c_k0_cheb[0]) - b1;
-    return exp(-x) * rsqrt(x) * p;
+__global__ void k_eval_k1(const double* __restrict__ x, double* __restrict__ out, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = bessel_k1(x[i], x[i] * x[i]);
 }
 
 __global__ void k_eval_k0(const double* __restrict__ x, double* __restrict__ out, int64_t n) {
@@ -68,9 +58,11 @@ __global__ void k_eval_k0(const double* __restrict__ x, double* __restrict__ out
         out[i] = bessel_k0(x[i], x[i] * x[i]);
 }
 
-int layer_eval_k0(const double* x, double* out, int64_t n, cudaStream_t st) {
+int layer_eval_k0(const double* x, double* out, int64_t n, int order, cudaStream_t st) {
     ARG_CHECK(g_k0_ready, "K0 table not set");
-    k_eval_k0<<<(int)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 256), 4096)), 256, 0, st>>>(x, out, n);
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 256), 4096));
+    if (order == 0) k_eval_k0<<<blocks, 256, 0, st>>>(x, out, n);
+    else k_eval_k1<<<blocks, 256, 0, st>>>(x, out, n);
     KERNEL_CHECK();
     return IPDE_OK;
 }

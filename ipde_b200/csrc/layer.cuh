@@ -1,8 +1,8 @@
 #pragma once
 #include "common.cuh"
 
-int layer_set_k0_table(const double* cheb, int ncheb);
-int layer_eval_k0(const double* x, double* out, int64_t n, cudaStream_t st);
+int layer_set_k0_table(const double* cheb0, const double* cheb1, int ncheb);
+int layer_eval_k0(const double* x, double* out, int64_t n, int order, cudaStream_t st);
 // kind 0 Laplace, 1 modified Helmholtz (parameter k); q = charge * weight
 int layer_apply_scalar(int kind, double k, const double* sx, const double* sy, const double* q, int64_t nsrc,
                        const double* tx, const double* ty, int64_t ntrg, double* out, int accumulate, cudaStream_t st);

@@ -75,18 +75,39 @@ _k0_table_set = False
 
 
 def ensure_k0_table():
-    """Chebyshev fit of sqrt(x) e^x K0(x) in t = 4/x - 1 on x >= 2, uploaded once (layer.cu)."""
+    """Chebyshev fits of sqrt(x) e^x K0(x) and sqrt(x) e^x K1(x) in t = 4/x - 1 on x >= 2, uploaded once
+    (csrc/bessel.cuh)."""
     global _k0_table_set
     if _k0_table_set:
         return
     nc = 36
     t, _ = np.polynomial.chebyshev.chebgauss(4*nc)
     x = 4.0/(t + 1.0)
-    g = np.sqrt(x)*scipy.special.k0e(x)
-    c = np.polynomial.chebyshev.chebfit(t, g, nc - 1)
-    c = np.ascontiguousarray(c, dtype=np.float64)
-    lib().ipde_set_k0_table(hptr(c), nc)
+    c0 = np.polynomial.chebyshev.chebfit(t, np.sqrt(x)*scipy.special.k0e(x), nc - 1)
+    c1 = np.polynomial.chebyshev.chebfit(t, np.sqrt(x)*scipy.special.k1e(x), nc - 1)
+    c0 = np.ascontiguousarray(c0, dtype=np.float64)
+    c1 = np.ascontiguousarray(c1, dtype=np.float64)
+    lib().ipde_set_k0_table(hptr(c0), hptr(c1), nc)
     _k0_table_set = True
+
+
+class StageTimer(object):
+    """CUDA-event stage timer: mark(name) closes the stage `name`; results() -> {name: total ms}."""
+    def __init__(self):
+        self.events = []
+
+    def mark(self, name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(torch.cuda.current_stream())
+        self.events.append((name, e))
+
+    def results(self):
+        torch.cuda.synchronize()
+        out = {}
+        for (_, a), (name, b) in zip(self.events[:-1], self.events[1:]):
+            if name != 'start':
+                out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
 
 
 # ----------------------------------------------------------------------------------------

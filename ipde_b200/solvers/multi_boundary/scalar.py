@@ -44,6 +44,7 @@ class ScalarSolver(object):
         self._define_grid_evaluator()
         self.dev = self.ebdyc.device
         self.iteration_counts = None
+        self.timer = None          # set to a device.StageTimer to get per-stage CUDA-event times
 
     def _collect_grid_sources(self):
         self.grid_sources = BoundaryCollection()
@@ -83,12 +84,16 @@ class ScalarSolver(object):
         D = self.dev
         L = lib()
         st = stream()
+        T = self.timer
+        mark = T.mark if T is not None else (lambda name: None)
+        mark('start')
         if self.grid_kind == 0 and D.bumpy is None:
             raise Exception('Poisson solver requires ebdyc.ready_bump(...) before solving.')
         L.ipde_grid_scatter_cutoff(D.grid.h, ptr(f_dev), ptr(D.phys_lin), ptr(D.step_compact), D.n_phys,
                                    ptr(D.fc), st)
         L.ipde_grid_solve_scalar(D.grid.h, self.grid_kind, float(self.k), ptr(D.fc), ptr(D.bumpy), ptr(D.uch),
                                  ptr(D.spec_work), ptr(D.uc), st)
+        mark('grid_solve')
         # interface values and gradient of the grid solution
         if self.interpolation_order == np.inf:
             nu = D.nufft
@@ -101,6 +106,7 @@ class ScalarSolver(object):
                 L.ipde_grid_interp_cubic(D.grid.h, ptr(src), D.x0, D.y0, ptr(D.iv_x), ptr(D.iv_y), D.n_iv,
                                          ptr(dst), st)
         self._interface_values = (bvs, bxs, bys)
+        mark('interface_interp')
         # per-boundary annular solves and effective sources
         sigmag = empty((self.grid_sources.N,))
         for b, helper in enumerate(self.helpers):
@@ -111,20 +117,25 @@ class ScalarSolver(object):
             s0, s1 = self.source_offsets[b], self.source_offsets[b + 1]
             L.ipde_vec_mul(ptr(sg), ptr(self.d_gsw[s0:s1]), ptr(sigmag[s0:s1]), int(s1 - s0), st)
         self.iteration_counts = [helper.iterations_last_call for helper in self.helpers]
+        mark('annular_and_qfs')
         # all grid-side sources -> (phys, not in annulus) U (interface points)
         out = layer_apply_scalar(self.kernel_kind, self.k, self.d_gsx, self.d_gsy, sigmag, D.pnai_x, D.pnai_y)
+        mark('sources_to_grid')
         # pack the result: grid part
         res = empty((self.ebdyc.dof,))
         L.ipde_grid_gather(ptr(D.uc), ptr(D.phys_lin), D.n_phys, ptr(res), st)
         L.ipde_index_add(ptr(res), ptr(D.pna_pos), ptr(out), D.n_pna, st)
+        mark('pack_grid')
         # radial part
         for b, helper in enumerate(self.helpers):
             o0, o1 = D.bdy_offsets[b], D.bdy_offsets[b + 1]
             ur = helper.correct(out[D.n_pna + o0:D.n_pna + o1])
+            mark('correct')
             db = D.ebdys[b]
             db.radial_interp(ur, db.ia_theta, db.ia_t, out=res, out_pos=db.ia_pos)
             r0, r1 = D.radial_offsets[b], D.radial_offsets[b + 1]
             res[r0:r1].copy_(ur.view(-1))
+            mark('radial_to_grid')
         return res
 
     def __call__(self, f, **kwargs):
