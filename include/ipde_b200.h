@@ -120,6 +120,27 @@ int ipde_layer_apply_stokes(const double* sx, const double* sy, const double* fx
                             int64_t nsrc, const double* tx, const double* ty, int64_t ntrg, double* out_uvp,
                             int accumulate, void* stream);
 
+/* ---- spectral-Ewald free-space evaluator: the same sums as ipde_layer_apply_scalar in O(S sw^2 + P^2 log P).
+ *      Replaces Layer_Apply / Grid_Evaluator at ipde/solvers/multi_boundary/scalar.py:63-71,
+ *      ipde/solvers/internals/scalar.py:95-116 and ipde/grid_evaluators/scalar_grid_evaluator.py:188-231,299-307.
+ *      Host-side preprocessing (parameters, tables, tiles): ipde_b200/ewald.py.  The FFT box has (px, py) nodes
+ *      x0 + i h, y0 + j h; tab*, tile_* are host arrays, sx/sy/targets device arrays (all copied). */
+int ipde_ewald_plan_create(int kind, double kappa, double xi, double h, double rc, int m, double x0, double y0, int px,
+                           int py, double L, double c0, double c1, int64_t nsrc, const double* sx, const double* sy,
+                           int nint, int ndeg, int nlog, const double* tabS_host, const double* tabA_host, int ntiles,
+                           const int* tile_ix_host, const int* tile_iy_host, const int* tile_ptr_host,
+                           const int* tile_src_host, const int* tile_map_host, void** plan);
+int ipde_ewald_plan_destroy(void* plan);
+/* on-grid targets: node lin[i] of the box, local-sum slot loc[i] (tile*256 + offset, or -1), added to grid_out[out_pos[i]] */
+int ipde_ewald_set_grid_targets(void* plan, int64_t n, const int64_t* lin, const int64_t* loc, const int64_t* out_pos);
+int ipde_ewald_set_point_targets(void* plan, int64_t n, const double* tx, const double* ty);
+/* q: weighted charges (nsrc).  grid_out[out_pos] += u (if grid targets set and grid_out != NULL);
+ * point_out = u or += u at the point targets */
+int ipde_ewald_apply(void* plan, const double* q, double* grid_out, double* point_out, int accumulate_points, void* stream);
+
+/* tests: device pointer/length of a work array: 0 spread S_w, 1 last inverse transform, 2 local sums */
+int ipde_ewald_debug_buffer(void* plan, int which, double** ptr, int64_t* n);
+
 /* ---- dense / sparse helpers ----------------------------------------------------------------- */
 int ipde_dense_gemv(const double* A, const double* x, double* y, int64_t m, int64_t n, void* stream);
 int ipde_lu_solve(const double* LU, const int* perm, const double* b, double* x, int M, void* stream);

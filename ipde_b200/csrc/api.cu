@@ -2,6 +2,7 @@
 #include "../../include/ipde_b200.h"
 #include "annular.cuh"
 #include "dense.cuh"
+#include "ewald.cuh"
 #include "fft.cuh"
 #include "grid.cuh"
 #include "layer.cuh"
@@ -172,6 +173,34 @@ int ipde_annular_precond(void* plan, const double* in, double* out, void* stream
 int ipde_annular_solve(void* plan, const double* f, const double* ig, const double* og, double f_sign, double tol,
                        int restart, int maxiter, double* u_out, int* iters, double* relres, void* stream) {
     return annular_solve((AnnularPlan*)plan, f, ig, og, f_sign, tol, restart, maxiter, u_out, iters, relres, ST(stream));
+}
+
+// ---- spectral-Ewald free-space evaluator
+int ipde_ewald_plan_create(int kind, double kappa, double xi, double h, double rc, int m, double x0, double y0, int px,
+                           int py, double L, double c0, double c1, int64_t nsrc, const double* sx, const double* sy,
+                           int nint, int ndeg, int nlog, const double* tabS_host, const double* tabA_host, int ntiles,
+                           const int* tile_ix_host, const int* tile_iy_host, const int* tile_ptr_host,
+                           const int* tile_src_host, const int* tile_map_host, void** plan) {
+    EwaldPlan* p = nullptr;
+    int rc_ = ewald_plan_create(kind, kappa, xi, h, rc, m, x0, y0, px, py, L, c0, c1, nsrc, sx, sy, nint, ndeg, nlog,
+                                tabS_host, tabA_host, ntiles, tile_ix_host, tile_iy_host, tile_ptr_host, tile_src_host,
+                                tile_map_host, &p);
+    *plan = p;
+    return rc_;
+}
+int ipde_ewald_plan_destroy(void* plan) { ewald_plan_destroy((EwaldPlan*)plan); return IPDE_OK; }
+int ipde_ewald_set_grid_targets(void* plan, int64_t n, const int64_t* lin, const int64_t* loc, const int64_t* out_pos) {
+    return ewald_set_grid_targets((EwaldPlan*)plan, n, lin, loc, out_pos);
+}
+int ipde_ewald_set_point_targets(void* plan, int64_t n, const double* tx, const double* ty) {
+    return ewald_set_point_targets((EwaldPlan*)plan, n, tx, ty);
+}
+int ipde_ewald_apply(void* plan, const double* q, double* grid_out, double* point_out, int accumulate_points, void* stream) {
+    return ewald_apply((EwaldPlan*)plan, q, grid_out, point_out, accumulate_points, ST(stream));
+}
+
+int ipde_ewald_debug_buffer(void* plan, int which, double** ptr, int64_t* n) {
+    return ewald_debug_buffer((EwaldPlan*)plan, which, ptr, n);
 }
 
 // ---- layer potentials

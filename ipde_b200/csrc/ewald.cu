@@ -1,0 +1,351 @@
+// Spectral-Ewald free-space evaluator:  u(x_t) = sum_s G(|x_t - y_s|) q_s  for G = -log r/(2 pi) or
+// K0(kappa r)/(2 pi), from O(1e4..1e5) sources on curves to (a) nodes of the uniform grid and (b) off-grid
+// points, in FP64 to ~1e-14, in O(S sw^2 + P^2 log P) instead of O(S T).
+//
+// Replaces the reference's Layer_Apply / Grid_Evaluator calls on the per-solve path:
+//   ScalarSolver.evaluate_to_grid_pnai           ipde/solvers/multi_boundary/scalar.py:63-71
+//   ScalarHelper.correct (sources -> radial pts) ipde/solvers/internals/scalar.py:95-116
+//   ScalarGridBackend.ewald_local_freespace, ScalarFreespaceGridEvaluator.__call__
+//                                                ipde/grid_evaluators/scalar_grid_evaluator.py:188-231,299-307
+// Mathematics and host-side preprocessing: ipde_b200/ewald.py.  Stages of one application:
+//   1. k_ewald_tiles     one CTA per 16x16 tile of nodes that has a source within rc: every thread owns a node and
+//                        loops over the tile's source list (staged through shared memory): Gaussian spread S_w and
+//                        the local sum of G_loc; no atomics, results are deterministic.
+//   2. 2-D real FFT of S_w (our Stockham FFT, grid.cu), multiplication by the truncated kernel, inverse FFT(s).
+//   3. k_ewald_grid_out  out[pos] += U[node] + local[node] for the on-grid targets.
+//   4. k_ewald_points    one warp per off-grid target: Gaussian-window gather of H (31 x 31 nodes, rows coalesced)
+//                        plus the local sum over the sources of the target's tile.
+#include "ewald.cuh"
+#include <algorithm>
+
+static const double TWO_PI = 6.283185307179586476925286766559;
+#define EW_TILE 16
+#define EW_CHUNK 128
+#define EW_MAX_TAB (64 * 16)
+
+struct EwaldPlan {
+    int kind = 0;
+    double kappa = 0, xi = 0, h = 0, rc2 = 0, rw2 = 0, x0 = 0, y0 = 0;
+    int px = 0, py = 0, m = 0;
+    GridPlan* fft = nullptr;
+    int64_t nsrc = 0;
+    double *sx = nullptr, *sy = nullptr;
+    int nint = 0, ndeg = 0, nlog = 0;
+    double *tabS = nullptr, *tabA = nullptr;
+    int ntiles = 0, ntx = 0, nty = 0;
+    int *tile_ix = nullptr, *tile_iy = nullptr, *tile_ptr = nullptr, *tile_src = nullptr, *tile_map = nullptr;
+    double *multH = nullptr, *multU = nullptr;
+    double *Sw = nullptr, *R = nullptr, *Lc = nullptr;
+    cplx *spec = nullptr, *specw = nullptr;
+    int64_t n_og = 0;
+    int64_t *og_lin = nullptr, *og_out = nullptr, *og_loc = nullptr;
+    int64_t n_pt = 0;
+    double *ptx = nullptr, *pty = nullptr;
+};
+
+struct EwaldTab {
+    const double* S;
+    const double* A;
+    int nint, ndeg, nlog;
+    double inv_dz;
+};
+
+// G_loc(r), z = r^2 < rc^2, from the piecewise Chebyshev tables (shared memory copies)
+__device__ __forceinline__ double ewald_gloc(double z, const double* __restrict__ sS, const double* __restrict__ sA,
+                                             int nint, int ndeg, int nlog, double inv_dz) {
+    const double u = z * inv_dz;
+    int i = (int)u;
+    if (i > nint - 1) i = nint - 1;
+    const double t = 2.0 * (u - (double)i) - 1.0, t2 = 2.0 * t;
+    const double* c = sS + i * ndeg;
+    double b0 = 0.0, b1 = 0.0;
+    for (int k = ndeg - 1; k >= 1; --k) {
+        const double tmp = fma(t2, b0, c[k]) - b1;
+        b1 = b0; b0 = tmp;
+    }
+    double s = fma(t, b0, c[0]) - b1;
+    if (i < nlog) {
+        const double* a = sA + i * ndeg;
+        b0 = 0.0; b1 = 0.0;
+        for (int k = ndeg - 1; k >= 1; --k) {
+            const double tmp = fma(t2, b0, a[k]) - b1;
+            b1 = b0; b0 = tmp;
+        }
+        s -= (fma(t, b0, a[0]) - b1) * log(z);
+    }
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EW_TILE* EW_TILE)
+k_ewald_tiles(const int* __restrict__ tile_ix, const int* __restrict__ tile_iy, const int* __restrict__ tile_ptr,
+              const int* __restrict__ tile_src, const double* __restrict__ sx, const double* __restrict__ sy,
+              const double* __restrict__ q, EwaldTab T, double x0, double y0, double h, double rc2, double rw2,
+              double two_xi2, double norm, int px, int py, double* __restrict__ Sw, double* __restrict__ Lc,
+              int want_local) {
+    __shared__ double shx[EW_CHUNK], shy[EW_CHUNK], shq[EW_CHUNK];
+    __shared__ double sS[EW_MAX_TAB], sA[EW_MAX_TAB];
+    const int tid = threadIdx.y * EW_TILE + threadIdx.x;
+    const int ntab = T.nint * T.ndeg;
+    for (int i = tid; i < ntab; i += EW_TILE * EW_TILE) { sS[i] = T.S[i]; sA[i] = (i < T.nlog * T.ndeg) ? T.A[i] : 0.0; }
+    const int t = blockIdx.x;
+    const int ix = tile_ix[t] * EW_TILE + threadIdx.y;
+    const int iy = tile_iy[t] * EW_TILE + threadIdx.x;
+    const double x = x0 + ix * h, y = y0 + iy * h;
+    const int s0 = tile_ptr[t], s1 = tile_ptr[t + 1];
+    double spread = 0.0, loc = 0.0;
+    for (int base = s0; base < s1; base += EW_CHUNK) {
+        const int cnt = min(EW_CHUNK, s1 - base);
+        __syncthreads();
+        if (tid < cnt) {
+            const int s = tile_src[base + tid];
+            shx[tid] = sx[s]; shy[tid] = sy[s]; shq[tid] = q[s];
+        }
+        __syncthreads();
+        for (int i = 0; i < cnt; ++i) {
+            const double dx = x - shx[i], dy = y - shy[i];
+            const double d2 = dx * dx + dy * dy;
+            if (d2 < rw2) spread = fma(shq[i], exp(-two_xi2 * d2), spread);
+            if (want_local && d2 < rc2 && d2 > 0.0)
+                loc = fma(shq[i], ewald_gloc(d2, sS, sA, T.nint, T.ndeg, T.nlog, T.inv_dz), loc);
+        }
+    }
+    if (ix < px && iy < py) Sw[(int64_t)ix * py + iy] = spread * norm;
+    if (want_local) Lc[(int64_t)t * (EW_TILE * EW_TILE) + tid] = loc;
+}
+
+// multiplier tables on the half spectrum (plan row order)
+__device__ __forceinline__ int ew_freq_of_row(int pos, int n1, int n2) {
+    if (n2 == 1) return pos;
+    return pos / n2 + n1 * (pos % n2);
+}
+__global__ void k_ewald_mult(double* __restrict__ multH, double* __restrict__ multU, int px, int py, int64_t pitch, int n1,
+                             int n2, double h, int kind, double kappa, double L, double c0, double c1, double inv8xi2) {
+    const int64_t total = (int64_t)px * pitch;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int pos = (int)(t / pitch), j = (int)(t % pitch);
+        const int i = ew_freq_of_row(pos, n1, n2);
+        const int si = (i < (px + 1) / 2) ? i : i - px;
+        const double kx = TWO_PI * (double)si / ((double)px * h), ky = TWO_PI * (double)j / ((double)py * h);
+        const double k2 = kx * kx + ky * ky, k = sqrt(k2);
+        double g;
+        if (kind == 0) {
+            if (si == 0 && j == 0) g = c1;
+            else g = (1.0 - j0(L * k)) / k2 - c0 * j1(L * k) / k;
+        } else {
+            g = (1.0 + c0 * k * j1(L * k) - c1 * j0(L * k)) / (k2 + kappa * kappa);
+        }
+        multH[t] = g;
+        multU[t] = g * exp(-k2 * inv8xi2);
+    }
+}
+
+__global__ void k_ewald_apply_mult(const cplx* __restrict__ spec, const double* __restrict__ mult, cplx* __restrict__ out,
+                                   int64_t total) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x)
+        out[t] = cscale(spec[t], mult[t]);
+}
+
+__global__ void k_ewald_grid_out(const double* __restrict__ U, const double* __restrict__ Lc, const int64_t* __restrict__ lin,
+                                 const int64_t* __restrict__ loc, const int64_t* __restrict__ pos, int64_t n,
+                                 double* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = U[lin[i]];
+        const int64_t l = loc[i];
+        if (l >= 0) v += Lc[l];
+        out[pos[i]] += v;
+    }
+}
+
+// one warp per off-grid target
+__global__ void k_ewald_points(const double* __restrict__ H, const double* __restrict__ tx, const double* __restrict__ ty,
+                               int64_t npts, const int* __restrict__ tile_map, int ntx, int nty,
+                               const int* __restrict__ tile_ptr, const int* __restrict__ tile_src,
+                               const double* __restrict__ sx, const double* __restrict__ sy, const double* __restrict__ q,
+                               EwaldTab T, double x0, double y0, double h, double rc2, double two_xi2, double wnorm, int m,
+                               int px, int py, double* __restrict__ out, int accumulate) {
+    __shared__ double sS[EW_MAX_TAB], sA[EW_MAX_TAB];
+    const int ntab = T.nint * T.ndeg;
+    for (int i = threadIdx.x; i < ntab; i += blockDim.x) { sS[i] = T.S[i]; sA[i] = (i < T.nlog * T.ndeg) ? T.A[i] : 0.0; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int W = 2 * m + 1;      // <= 32 (checked at plan creation)
+    for (int64_t p = warp; p < npts; p += nwarps) {
+        const double x = tx[p], y = ty[p];
+        const double X = (x - x0) / h, Y = (y - y0) / h;
+        const int i0 = (int)ceil(X - m), j0 = (int)ceil(Y - m);
+        // lane b: column weight wy_b and (same index) row weight wx_b
+        double wy = 0.0, wx = 0.0;
+        if (lane < W) {
+            const double ddx = ((double)(i0 + lane) - X) * h, ddy = ((double)(j0 + lane) - Y) * h;
+            wx = exp(-two_xi2 * ddx * ddx);
+            wy = exp(-two_xi2 * ddy * ddy);
+        }
+        double acc = 0.0;
+        const bool in_cols = (lane < W) && (j0 + lane >= 0) && (j0 + lane < py);
+        for (int a = 0; a < W; ++a) {
+            const double wa = __shfl_sync(0xffffffffu, wx, a);
+            const int ii = i0 + a;
+            if (in_cols && ii >= 0 && ii < px) acc = fma(wa, H[(int64_t)ii * py + j0 + lane], acc);
+        }
+        acc *= wy * wnorm;
+        // local part: sources of the tile containing the target
+        const int fxi = (int)floor(X), fyi = (int)floor(Y);
+        const int tix = fxi / EW_TILE, tiy = fyi / EW_TILE;
+        if (fxi >= 0 && tix < ntx && fyi >= 0 && tiy < nty) {
+            const int t = tile_map[tix * nty + tiy];
+            if (t >= 0) {
+                const int s0 = tile_ptr[t], s1 = tile_ptr[t + 1];
+                for (int s = s0 + lane; s < s1; s += 32) {
+                    const int k = tile_src[s];
+                    const double dx = x - sx[k], dy = y - sy[k];
+                    const double d2 = dx * dx + dy * dy;
+                    if (d2 < rc2 && d2 > 0.0) acc = fma(q[k], ewald_gloc(d2, sS, sA, T.nint, T.ndeg, T.nlog, T.inv_dz), acc);
+                }
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) out[p] = accumulate ? out[p] + acc : acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+template <typename Tp>
+static int upload_arr(Tp** dst, const Tp* src, size_t count, cudaMemcpyKind kind) {
+    *dst = nullptr;
+    if (count == 0) return IPDE_OK;
+    CUDA_TRY(cudaMalloc(dst, sizeof(Tp) * count));
+    CUDA_TRY(cudaMemcpy(*dst, src, sizeof(Tp) * count, kind));
+    return IPDE_OK;
+}
+
+int ewald_plan_create(int kind, double kappa, double xi, double h, double rc, int m, double x0, double y0, int px, int py,
+                      double L, double c0, double c1, int64_t nsrc, const double* sx_dev, const double* sy_dev, int nint,
+                      int ndeg, int nlog, const double* tabS_host, const double* tabA_host, int ntiles,
+                      const int* tile_ix_host, const int* tile_iy_host, const int* tile_ptr_host,
+                      const int* tile_src_host, const int* tile_map_host, EwaldPlan** out) {
+    ARG_CHECK(kind == 0 || kind == 1, "kind must be 0 (Laplace) or 1 (modified Helmholtz)");
+    ARG_CHECK(2 * m + 1 <= 32, "window wider than a warp");
+    ARG_CHECK(nint * ndeg <= EW_MAX_TAB && nlog <= nint, "local-kernel table too large");
+    ARG_CHECK(px % 2 == 0 && py % 2 == 0, "FFT box sizes must be even");
+    EwaldPlan* p = new EwaldPlan();
+    p->kind = kind; p->kappa = kappa; p->xi = xi; p->h = h; p->rc2 = rc * rc; p->m = m;
+    p->rw2 = (m * h) * (m * h);
+    p->x0 = x0; p->y0 = y0; p->px = px; p->py = py;
+    p->nsrc = nsrc; p->nint = nint; p->ndeg = ndeg; p->nlog = nlog;
+    p->ntiles = ntiles;
+    p->ntx = (px + EW_TILE - 1) / EW_TILE; p->nty = (py + EW_TILE - 1) / EW_TILE;
+    int rc_ = grid_plan_create(px, py, h, h, &p->fft);
+    if (rc_) { delete p; return rc_; }
+#define EW_UP(call) rc_ = (call); if (rc_) { ewald_plan_destroy(p); return rc_; }
+    EW_UP(upload_arr(&p->sx, sx_dev, (size_t)nsrc, cudaMemcpyDeviceToDevice))
+    EW_UP(upload_arr(&p->sy, sy_dev, (size_t)nsrc, cudaMemcpyDeviceToDevice))
+    EW_UP(upload_arr(&p->tabS, tabS_host, (size_t)nint * ndeg, cudaMemcpyHostToDevice))
+    EW_UP(upload_arr(&p->tabA, tabA_host, (size_t)nint * ndeg, cudaMemcpyHostToDevice))
+    EW_UP(upload_arr(&p->tile_ix, tile_ix_host, (size_t)ntiles, cudaMemcpyHostToDevice))
+    EW_UP(upload_arr(&p->tile_iy, tile_iy_host, (size_t)ntiles, cudaMemcpyHostToDevice))
+    EW_UP(upload_arr(&p->tile_ptr, tile_ptr_host, (size_t)ntiles + 1, cudaMemcpyHostToDevice))
+    EW_UP(upload_arr(&p->tile_src, tile_src_host, (size_t)tile_ptr_host[ntiles], cudaMemcpyHostToDevice))
+    EW_UP(upload_arr(&p->tile_map, tile_map_host, (size_t)p->ntx * p->nty, cudaMemcpyHostToDevice))
+#undef EW_UP
+    const size_t nreal = (size_t)px * py, nspec = (size_t)px * (py / 2 + 1);
+    CUDA_TRY(cudaMalloc(&p->Sw, sizeof(double) * nreal));
+    CUDA_TRY(cudaMemset(p->Sw, 0, sizeof(double) * nreal));
+    CUDA_TRY(cudaMalloc(&p->R, sizeof(double) * nreal));
+    CUDA_TRY(cudaMalloc(&p->Lc, sizeof(double) * (size_t)std::max(1, ntiles) * EW_TILE * EW_TILE));
+    CUDA_TRY(cudaMalloc(&p->spec, sizeof(cplx) * nspec));
+    CUDA_TRY(cudaMalloc(&p->specw, sizeof(cplx) * nspec));
+    CUDA_TRY(cudaMalloc(&p->multH, sizeof(double) * nspec));
+    CUDA_TRY(cudaMalloc(&p->multU, sizeof(double) * nspec));
+    const int blocks = (int)std::min<int64_t>(cdiv((int64_t)nspec, 256), (int64_t)ipde_num_sms() * 8);
+    k_ewald_mult<<<blocks, 256>>>(p->multH, p->multU, px, py, py / 2 + 1, p->fft->n1, p->fft->n2, h, kind, kappa, L, c0, c1,
+                                  1.0 / (8.0 * xi * xi));
+    KERNEL_CHECK();
+    CUDA_TRY(cudaDeviceSynchronize());
+    *out = p;
+    return IPDE_OK;
+}
+
+void ewald_plan_destroy(EwaldPlan* p) {
+    if (!p) return;
+    grid_plan_destroy(p->fft);
+    cudaFree(p->sx); cudaFree(p->sy); cudaFree(p->tabS); cudaFree(p->tabA);
+    cudaFree(p->tile_ix); cudaFree(p->tile_iy); cudaFree(p->tile_ptr); cudaFree(p->tile_src); cudaFree(p->tile_map);
+    cudaFree(p->multH); cudaFree(p->multU); cudaFree(p->Sw); cudaFree(p->R); cudaFree(p->Lc);
+    cudaFree(p->spec); cudaFree(p->specw);
+    cudaFree(p->og_lin); cudaFree(p->og_out); cudaFree(p->og_loc); cudaFree(p->ptx); cudaFree(p->pty);
+    delete p;
+}
+
+int ewald_set_grid_targets(EwaldPlan* p, int64_t n, const int64_t* lin_dev, const int64_t* loc_dev, const int64_t* out_pos_dev) {
+    cudaFree(p->og_lin); cudaFree(p->og_out); cudaFree(p->og_loc);
+    p->og_lin = p->og_out = p->og_loc = nullptr;
+    p->n_og = n;
+    int rc = upload_arr(&p->og_lin, lin_dev, (size_t)n, cudaMemcpyDeviceToDevice);
+    if (!rc) rc = upload_arr(&p->og_loc, loc_dev, (size_t)n, cudaMemcpyDeviceToDevice);
+    if (!rc) rc = upload_arr(&p->og_out, out_pos_dev, (size_t)n, cudaMemcpyDeviceToDevice);
+    return rc;
+}
+
+int ewald_set_point_targets(EwaldPlan* p, int64_t n, const double* tx_dev, const double* ty_dev) {
+    cudaFree(p->ptx); cudaFree(p->pty);
+    p->ptx = p->pty = nullptr;
+    p->n_pt = n;
+    int rc = upload_arr(&p->ptx, tx_dev, (size_t)n, cudaMemcpyDeviceToDevice);
+    if (!rc) rc = upload_arr(&p->pty, ty_dev, (size_t)n, cudaMemcpyDeviceToDevice);
+    return rc;
+}
+
+int ewald_apply(EwaldPlan* p, const double* q, double* grid_out, double* point_out, int accumulate_points, cudaStream_t st) {
+    const bool want_grid = (p->n_og > 0 && grid_out != nullptr);
+    const bool want_pts = (p->n_pt > 0 && point_out != nullptr);
+    if (!want_grid && !want_pts) return IPDE_OK;
+    EwaldTab T;
+    T.S = p->tabS; T.A = p->tabA; T.nint = p->nint; T.ndeg = p->ndeg; T.nlog = p->nlog;
+    T.inv_dz = (double)p->nint / p->rc2;
+    const double two_xi2 = 2.0 * p->xi * p->xi;
+    const double ck = (p->kind == 1) ? exp(-p->kappa * p->kappa / (4.0 * p->xi * p->xi)) : 1.0;
+    const double wnorm = two_xi2 / 3.14159265358979323846;      // (2 xi^2 / pi)
+    if (p->ntiles > 0) {
+        k_ewald_tiles<<<p->ntiles, dim3(EW_TILE, EW_TILE), 0, st>>>(p->tile_ix, p->tile_iy, p->tile_ptr, p->tile_src, p->sx,
+                                                                   p->sy, q, T, p->x0, p->y0, p->h, p->rc2, p->rw2, two_xi2,
+                                                                   ck * wnorm, p->px, p->py, p->Sw, p->Lc, want_grid ? 1 : 0);
+        KERNEL_CHECK();
+    }
+    int rc = grid_fft2_forward(p->fft, p->Sw, p->spec, st);
+    if (rc) return rc;
+    const int64_t nspec = (int64_t)p->px * (p->py / 2 + 1);
+    const int mb = (int)std::min<int64_t>(cdiv(nspec, 256), (int64_t)ipde_num_sms() * 8);
+    if (want_grid) {
+        k_ewald_apply_mult<<<mb, 256, 0, st>>>(p->spec, p->multU, p->specw, nspec);
+        KERNEL_CHECK();
+        rc = grid_fft2_inverse(p->fft, p->specw, p->specw, p->R, st);
+        if (rc) return rc;
+        const int gb = (int)std::min<int64_t>(cdiv(p->n_og, 256), (int64_t)ipde_num_sms() * 8);
+        k_ewald_grid_out<<<gb, 256, 0, st>>>(p->R, p->Lc, p->og_lin, p->og_loc, p->og_out, p->n_og, grid_out);
+        KERNEL_CHECK();
+    }
+    if (want_pts) {
+        k_ewald_apply_mult<<<mb, 256, 0, st>>>(p->spec, p->multH, p->specw, nspec);
+        KERNEL_CHECK();
+        rc = grid_fft2_inverse(p->fft, p->specw, p->specw, p->R, st);
+        if (rc) return rc;
+        const int pb = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(p->n_pt * 32, 256), (int64_t)ipde_num_sms() * 16));
+        k_ewald_points<<<pb, 256, 0, st>>>(p->R, p->ptx, p->pty, p->n_pt, p->tile_map, p->ntx, p->nty, p->tile_ptr,
+                                           p->tile_src, p->sx, p->sy, q, T, p->x0, p->y0, p->h, p->rc2, two_xi2,
+                                           wnorm * p->h * p->h, p->m, p->px, p->py, point_out, accumulate_points);
+        KERNEL_CHECK();
+    }
+    return IPDE_OK;
+}
+
+// test/debug access to the work arrays: 0 S_w (px*py), 1 last inverse transform (px*py), 2 local sums (ntiles*256)
+int ewald_debug_buffer(EwaldPlan* p, int which, double** ptr, int64_t* n) {
+    if (which == 0) { *ptr = p->Sw; *n = (int64_t)p->px * p->py; }
+    else if (which == 1) { *ptr = p->R; *n = (int64_t)p->px * p->py; }
+    else if (which == 2) { *ptr = p->Lc; *n = (int64_t)p->ntiles * EW_TILE * EW_TILE; }
+    else { ipde_set_error("ewald_debug_buffer: unknown buffer %d", which); return IPDE_ERR_ARG; }
+    return IPDE_OK;
+}

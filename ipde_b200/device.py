@@ -396,3 +396,84 @@ class DeviceBoundary(object):
         self.interface_nx = to_dev(ebdy.interface.normal_x)
         self.interface_ny = to_dev(ebdy.interface.normal_y)
         self.radial_interp = RadialInterpolator(self.M, self.n)
+
+
+# ----------------------------------------------------------------------------------------
+class FreeSpaceEvaluator(object):
+    """
+    Spectral-Ewald evaluation of  u(x) = sum_s G(|x - y_s|) q_s  (csrc/ewald.cu, ipde_b200/ewald.py) from fixed
+    sources to fixed targets: nodes of the background grid (`grid_nodes`: (ix, iy) index arrays, results are
+    *added* to out[grid_out_pos]) and/or off-grid points (`points`: x, y arrays).
+      kind 0: G = -log r / (2 pi);  kind 1: G = K0(kappa r) / (2 pi)
+      grid: object with xv[0], yv[0], xh (== yh) -- FFT-box nodes are aligned with the background grid
+    """
+    def __init__(self, kind, kappa, grid_x0, grid_y0, h, sx, sy, grid_nodes=None, grid_out_pos=None, points=None):
+        import ctypes
+        from . import ewald as E
+        require_cuda()
+        L_ = lib()
+        self.kind, self.kappa, self.h = int(kind), float(kappa), float(h)
+        P = E.EwaldParameters(h)
+        self.params = P
+        sx = np.ascontiguousarray(sx, dtype=float); sy = np.ascontiguousarray(sy, dtype=float)
+        self.nsrc = sx.size
+        xs, ys = [sx], [sy]
+        if grid_nodes is not None:
+            gix, giy = np.asarray(grid_nodes[0], dtype=np.int64), np.asarray(grid_nodes[1], dtype=np.int64)
+            xs.append(grid_x0 + h*np.array([gix.min(), gix.max()], dtype=float))
+            ys.append(grid_y0 + h*np.array([giy.min(), giy.max()], dtype=float))
+        if points is not None:
+            ptx = np.ascontiguousarray(points[0], dtype=float); pty = np.ascontiguousarray(points[1], dtype=float)
+            xs.append(ptx); ys.append(pty)
+        ax, ay = np.concatenate(xs), np.concatenate(ys)
+        # largest source-target distance, bounded by the bounding-box diagonal and by twice the enclosing radius
+        cx, cy = 0.5*(ax.min() + ax.max()), 0.5*(ay.min() + ay.max())
+        D = min(np.hypot(ax.max() - ax.min(), ay.max() - ay.min()), 2.0*np.sqrt(((ax - cx)**2 + (ay - cy)**2).max()))
+        self.L = D + 2.0*np.sqrt(2.0)*P.m*h + 2.0*h
+        nxt = L_.ipde_fft_next_size
+        self.x0, self.px, self.ilo_x = E.choose_box(ax.min(), ax.max(), h, P.m, grid_x0, self.L, nxt)
+        self.y0, self.py, self.ilo_y = E.choose_box(ay.min(), ay.max(), h, P.m, grid_y0, self.L, nxt)
+        tab = E.local_tables(self.kind, self.kappa, P.xi, P.rc)
+        tix, tiy, tptr, tsrc, tmap = E.build_tiles(sx, sy, self.x0, self.y0, h, self.px, self.py, P.rc)
+        c0, c1, _ = E.trunc_kernel_constants(self.kind, self.kappa, self.L)
+        self.ntiles = int(tix.size)
+        d_sx, d_sy = to_dev(sx), to_dev(sy)
+        hnd = ctypes.c_void_p()
+        tS, tA = np.ascontiguousarray(tab['S']), np.ascontiguousarray(tab['A'])
+        tmap_c = np.ascontiguousarray(tmap, dtype=np.int32)
+        L_.ipde_ewald_plan_create(self.kind, self.kappa, float(P.xi), self.h, float(P.rc), int(P.m), float(self.x0),
+                                  float(self.y0), int(self.px), int(self.py), float(self.L), float(c0), float(c1),
+                                  self.nsrc, ptr(d_sx), ptr(d_sy), tab['nint'], tab['ndeg'], tab['nlog'], hptr(tS),
+                                  hptr(tA), self.ntiles, hptr(tix), hptr(tiy), hptr(tptr), hptr(tsrc), hptr(tmap_c),
+                                  ctypes.byref(hnd))
+        self.h_plan = hnd
+        self.n_grid = 0
+        self.n_points = 0
+        if grid_nodes is not None:
+            bix, biy = gix - self.ilo_x, giy - self.ilo_y          # node indices inside the FFT box
+            lin = bix*self.py + biy
+            t = tmap[bix//E.TILE, biy//E.TILE].astype(np.int64)
+            loc = np.where(t >= 0, t*(E.TILE*E.TILE) + (bix % E.TILE)*E.TILE + (biy % E.TILE), -1)
+            pos = np.ascontiguousarray(grid_out_pos, dtype=np.int64)
+            self.n_grid = int(lin.size)
+            d_lin, d_loc, d_pos = to_dev(lin), to_dev(loc), to_dev(pos)     # keep alive across the call
+            L_.ipde_ewald_set_grid_targets(hnd, self.n_grid, ptr(d_lin), ptr(d_loc), ptr(d_pos))
+        if points is not None:
+            self.n_points = int(ptx.size)
+            d_ptx, d_pty = to_dev(ptx), to_dev(pty)
+            L_.ipde_ewald_set_point_targets(hnd, self.n_points, ptr(d_ptx), ptr(d_pty))
+        torch.cuda.synchronize()
+
+    def __del__(self):
+        try:
+            lib().ipde_ewald_plan_destroy(self.h_plan)
+        except Exception:
+            pass
+
+    def __call__(self, q, grid_out=None, point_out=None, accumulate_points=False):
+        """q: weighted charges (device).  grid_out[grid_out_pos] += u; returns point values (device) or None."""
+        if self.n_points > 0 and point_out is None:
+            point_out = empty((self.n_points,))
+        lib().ipde_ewald_apply(self.h_plan, ptr(q), ptr(grid_out), ptr(point_out), 1 if accumulate_points else 0,
+                               stream())
+        return point_out
