@@ -92,6 +92,29 @@ class ScalarHelper(object):
         self._tau = empty((2*n,))
         self._w = empty((n,))
 
+    def set_evaluation(self, mode, grid, single):
+        """
+        mode 'direct': all-pairs sums in correct(); 'ewald': spectral-Ewald evaluators on a box around this
+        boundary, aligned with the background grid (own grid-side sources -> own interface, annulus-side sources ->
+        own radial points).  `single`: the collection has one boundary, so the field of the other boundaries on
+        this interface vanishes identically and the first evaluation is skipped (cf. the reference's own
+        `single_ebdy` shortcut in VectorHelper.correct, ipde/solvers/internals/vector.py:138-139).
+        """
+        self.evaluation = mode
+        self.single = single
+        self.evaluator_w = None
+        self.evaluator_r = None
+        if mode == 'ewald':
+            from ...device import FreeSpaceEvaluator
+            e = self.ebdy
+            g, r = self.interface_qfs_g.source, self.interface_qfs_r.source
+            x0, y0, h = float(grid.xv[0]), float(grid.yv[0]), float(grid.xh)
+            if not single:
+                self.evaluator_w = FreeSpaceEvaluator(self.kernel_kind, self.k, x0, y0, h, g.x, g.y,
+                                                      points=(e.interface.x, e.interface.y))
+            self.evaluator_r = FreeSpaceEvaluator(self.kernel_kind, self.k, x0, y0, h, r.x, r.y,
+                                                  points=(e.radial_x.ravel(), e.radial_y.ravel()))
+
     # ---- small (1 x M) . (M, n) products; host arrays in, host arrays out (drop-in use)
     def get_boundary_values(self, ur):
         return self._bv_estimator.dot(ur)
@@ -128,15 +151,26 @@ class ScalarHelper(object):
     def correct(self, ub):
         g, r = self.d_qfs_g, self.d_qfs_r
         n = self.ebdy.bdy.N
-        # field of our own grid-side sources on our own interface
-        q = empty((g.nsrc,))
-        lib().ipde_vec_mul(ptr(self.sigma_g), ptr(g.sw), ptr(q), g.nsrc, stream())
-        layer_apply_scalar(self.kernel_kind, self.k, g.sx, g.sy, q, self.d_ix, self.d_iy, out=self._w)
-        lib().ipde_vec_axpby(1.0, ptr(ub), -1.0, ptr(self._w), ptr(self._w), n, stream())
-        sigma_r_adj = r.u2s(self._w)
+        ewald = getattr(self, 'evaluation', 'direct') == 'ewald'
         qr = empty((r.nsrc,))
-        lib().ipde_vec_axpby(1.0, ptr(sigma_r_adj), 1.0, ptr(self.sigma_r), ptr(qr), r.nsrc, stream())
-        lib().ipde_vec_mul(ptr(qr), ptr(r.sw), ptr(qr), r.nsrc, stream())
-        layer_apply_scalar(self.kernel_kind, self.k, r.sx, r.sy, qr, self.d_rx, self.d_ry,
-                           out=self.ur.view(-1), accumulate=True)
+        if ewald and self.single:
+            # ub is the field of our own sources only: ub - w == 0 and the adjustment vanishes
+            lib().ipde_vec_mul(ptr(self.sigma_r), ptr(r.sw), ptr(qr), r.nsrc, stream())
+        else:
+            # field of our own grid-side sources on our own interface
+            q = empty((g.nsrc,))
+            lib().ipde_vec_mul(ptr(self.sigma_g), ptr(g.sw), ptr(q), g.nsrc, stream())
+            if ewald:
+                self.evaluator_w(q, point_out=self._w)
+            else:
+                layer_apply_scalar(self.kernel_kind, self.k, g.sx, g.sy, q, self.d_ix, self.d_iy, out=self._w)
+            lib().ipde_vec_axpby(1.0, ptr(ub), -1.0, ptr(self._w), ptr(self._w), n, stream())
+            sigma_r_adj = r.u2s(self._w)
+            lib().ipde_vec_axpby(1.0, ptr(sigma_r_adj), 1.0, ptr(self.sigma_r), ptr(qr), r.nsrc, stream())
+            lib().ipde_vec_mul(ptr(qr), ptr(r.sw), ptr(qr), r.nsrc, stream())
+        if ewald:
+            self.evaluator_r(qr, point_out=self.ur.view(-1), accumulate_points=True)
+        else:
+            layer_apply_scalar(self.kernel_kind, self.k, r.sx, r.sy, qr, self.d_rx, self.d_ry,
+                               out=self.ur.view(-1), accumulate=True)
         return self.ur

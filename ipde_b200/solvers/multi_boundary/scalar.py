@@ -41,8 +41,8 @@ class ScalarSolver(object):
         self.grid_step = self.ebdyc.grid_step
         self._define_layer_apply()
         self._collect_grid_sources()
-        self._define_grid_evaluator()
         self.dev = self.ebdyc.device
+        self._define_grid_evaluator()
         self.iteration_counts = None
         self.timer = None          # set to a device.StageTimer to get per-stage CUDA-event times
 
@@ -59,11 +59,38 @@ class ScalarSolver(object):
     def _get_helper(self, ebdy, helper):
         raise NotImplementedError
 
+    # S*T above which the all-pairs sum loses to the spectral-Ewald evaluator (csrc/ewald.cu)
+    EWALD_THRESHOLD = 2.0e8
+
     def _define_grid_evaluator(self):
-        if self.grid_backend not in (None, 'pybie2d', 'fmm2d', 'flexmm'):
+        """
+        Reference backends (multi_boundary/modified_helmholtz.py:48-67, poisson.py:40-62): 'pybie2d' / 'fmm2d' /
+        'flexmm' are all sums over all sources, a GridBackend object selects the Ewald-like grid evaluator.
+        Here: 'direct' = all-pairs device sum (csrc/layer.cu), 'ewald' = spectral-Ewald evaluator
+        (csrc/ewald.cu); the reference's names map to 'auto' (by problem size).
+        """
+        gb = self.grid_backend
+        if gb in (None, 'pybie2d', 'fmm2d', 'flexmm', 'auto'):
+            work = float(self.grid_sources.N)*float(self.ebdyc.grid_pnai.N)
+            gb = 'ewald' if work > self.EWALD_THRESHOLD else 'direct'
+        if gb not in ('direct', 'ewald'):
             raise Exception('grid_backend not recognized')
-        # every string backend of the reference is a sum over all sources; here: the direct device sum
-        self.split_grid_evaluation = False
+        g = self.ebdyc.grid
+        if gb == 'ewald' and abs(g.xh - g.yh) > 1e-14*g.xh:
+            gb = 'direct'           # the evaluator needs square cells
+        self.evaluation = gb
+        self.split_grid_evaluation = gb == 'ewald'
+        self.evaluator_g = None
+        if gb == 'ewald':
+            from ...device import FreeSpaceEvaluator
+            e = self.ebdyc
+            pix, piy = np.nonzero(e.phys_not_in_annulus)
+            self.evaluator_g = FreeSpaceEvaluator(
+                self.kernel_kind, self.k, float(g.xv[0]), float(g.yv[0]), float(g.xh),
+                self.grid_sources.x, self.grid_sources.y, grid_nodes=(pix, piy),
+                grid_out_pos=e.phys_inds[e.phys_not_in_annulus], points=(e.all_ivx, e.all_ivy))
+        for helper in self.helpers:
+            helper.set_evaluation(gb, g, single=self.ebdyc.N == 1)
 
     def _define_layer_apply(self):
         self.Layer_Apply = self.helpers[0].Layer_Apply
@@ -118,18 +145,20 @@ class ScalarSolver(object):
             L.ipde_vec_mul(ptr(sg), ptr(self.d_gsw[s0:s1]), ptr(sigmag[s0:s1]), int(s1 - s0), st)
         self.iteration_counts = [helper.iterations_last_call for helper in self.helpers]
         mark('annular_and_qfs')
-        # all grid-side sources -> (phys, not in annulus) U (interface points)
-        out = layer_apply_scalar(self.kernel_kind, self.k, self.d_gsx, self.d_gsy, sigmag, D.pnai_x, D.pnai_y)
-        mark('sources_to_grid')
-        # pack the result: grid part
+        # all grid-side sources -> (phys, not in annulus) U (interface points); pack the grid part of the result
         res = empty((self.ebdyc.dof,))
         L.ipde_grid_gather(ptr(D.uc), ptr(D.phys_lin), D.n_phys, ptr(res), st)
-        L.ipde_index_add(ptr(res), ptr(D.pna_pos), ptr(out), D.n_pna, st)
-        mark('pack_grid')
+        if self.evaluator_g is not None:
+            bu_all = self.evaluator_g(sigmag, grid_out=res)
+        else:
+            out = layer_apply_scalar(self.kernel_kind, self.k, self.d_gsx, self.d_gsy, sigmag, D.pnai_x, D.pnai_y)
+            L.ipde_index_add(ptr(res), ptr(D.pna_pos), ptr(out), D.n_pna, st)
+            bu_all = out[D.n_pna:]
+        mark('sources_to_grid')
         # radial part
         for b, helper in enumerate(self.helpers):
             o0, o1 = D.bdy_offsets[b], D.bdy_offsets[b + 1]
-            ur = helper.correct(out[D.n_pna + o0:D.n_pna + o1])
+            ur = helper.correct(bu_all[o0:o1])
             mark('correct')
             db = D.ebdys[b]
             db.radial_interp(ur, db.ia_theta, db.ia_t, out=res, out_pos=db.ia_pos)

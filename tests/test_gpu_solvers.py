@@ -83,3 +83,35 @@ def test_converges_to_manufactured_solution():
     err = np.abs(np.asarray(ue) + corr - np.asarray(ua)).max()
     # reference table errs16 at nb=600: 1.33e-9 (examples/interior_modified_helmholtz_using_multi.py:26)
     assert err < 2e-9, err
+
+
+@pytest.mark.parametrize('kind', ['modified_helmholtz', 'poisson'])
+def test_ewald_backend_single_boundary(kind):
+    """grid_backend='ewald' (spectral-Ewald evaluator for every sources->targets sum) against the CPU oracle,
+    whose sums are all-pairs."""
+    from ipde_b200.solvers.multi_boundary.modified_helmholtz import ModifiedHelmholtzSolver
+    from ipde_b200.solvers.multi_boundary.poisson import PoissonSolver
+    ebdyc = single_star(nb=300, M=8, bump=(kind == 'poisson'))
+    k = 2.0 if kind == 'modified_helmholtz' else 0.0
+    f, ua, _ = manufactured(ebdyc, k)
+    if kind == 'poisson':
+        solver = PoissonSolver(ebdyc, grid_backend='ewald')
+    else:
+        solver = ModifiedHelmholtzSolver(ebdyc, k, grid_backend='ewald')
+    assert solver.evaluation == 'ewald' and solver.helpers[0].evaluator_r is not None
+    ue = solver(f, tol=1e-13, restart=40, maxiter=5)
+    uo = oracle_for(solver, kind, k, 'spectral')(f, tol=1e-13, restart=40, maxiter=5)
+    linf, l2 = rel_errors(ue, uo)
+    assert linf < TOL and l2 < TOL, (linf, l2)
+
+
+def test_ewald_backend_three_boundaries():
+    from ipde_b200.solvers.multi_boundary.modified_helmholtz import ModifiedHelmholtzSolver
+    ebdyc = three_bodies(nb=100, M=8)
+    f, ua, _ = manufactured(ebdyc, 5.0, kk=10*np.pi/7)
+    solver = ModifiedHelmholtzSolver(ebdyc, 5.0, grid_backend='ewald')
+    assert all(h.evaluator_w is not None for h in solver.helpers)
+    ue = solver(f, tol=1e-13, restart=60, maxiter=5)
+    uo = oracle_for(solver, 'modified_helmholtz', 5.0, 'spectral')(f, tol=1e-13, restart=60, maxiter=5)
+    linf, l2 = rel_errors(ue, uo)
+    assert linf < TOL and l2 < TOL, (linf, l2)
