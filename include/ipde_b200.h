@@ -116,6 +116,10 @@ int ipde_eval_k1(const double* x, double* out, int64_t n, void* stream);
 int ipde_layer_apply_scalar(int kind, double k, const double* sx, const double* sy, const double* q,
                             int64_t nsrc, const double* tx, const double* ty, int64_t ntrg, double* out,
                             int accumulate, void* stream);
+/* setup (QFS): dense out[i*ns + j] = K(t_i, s_j) w_j; layer 0 single, 1 double (normal derivative at the source) */
+int ipde_kernel_matrix(int kind, double k, int layer, const double* tx, const double* ty, int64_t nt, const double* sx,
+                       const double* sy, const double* snx, const double* sny, const double* w, int64_t ns, double* out,
+                       void* stream);
 int ipde_layer_apply_stokes(const double* sx, const double* sy, const double* fx, const double* fy,
                             int64_t nsrc, const double* tx, const double* ty, int64_t ntrg, double* out_uvp,
                             int accumulate, void* stream);

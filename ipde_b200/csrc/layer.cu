@@ -224,3 +224,55 @@ int layer_apply_stokes(const double* sx, const double* sy, const double* fx, con
     KERNEL_CHECK();
     return IPDE_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// Dense kernel matrices for the QFS setup (ipde_b200/qfs.py): out[i*ns + j] = K(t_i, s_j) w_j with
+//   layer 0 (single): G(|t - s|);   layer 1 (double): d/dn_s G = grad_s G . n_s
+// for G = -log r/(2 pi) (kind 0) or K0(k r)/(2 pi) (kind 1).  Setup-time only, but O(N^2) evaluations of
+// K0/K1, which is why it runs here rather than in SciPy.
+template <int KIND, int LAYER>
+__global__ void k_kernel_matrix(const double* __restrict__ tx, const double* __restrict__ ty, int64_t nt,
+                                const double* __restrict__ sx, const double* __restrict__ sy,
+                                const double* __restrict__ snx, const double* __restrict__ sny,
+                                const double* __restrict__ w, int64_t ns, double kk, double* __restrict__ out) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= ns) return;
+    const double xs = sx[j], ys = sy[j], wj = w[j];
+    const double nxs = LAYER ? snx[j] : 0.0, nys = LAYER ? sny[j] : 0.0;
+    const double c2 = 0.15915494309189533577;     // 1/(2 pi)
+    for (int64_t i = blockIdx.y; i < nt; i += gridDim.y) {
+        const double dx = tx[i] - xs, dy = ty[i] - ys;
+        const double r2 = dx * dx + dy * dy;
+        double v;
+        if (LAYER == 0) {
+            if (KIND == 0) v = -0.5 * log(r2) * c2;
+            else v = bessel_k0(kk * sqrt(r2), kk * kk * r2) * c2;
+        } else {
+            const double dn = dx * nxs + dy * nys;
+            if (KIND == 0) v = dn / r2 * c2;
+            else {
+                const double r = sqrt(r2);
+                v = kk * bessel_k1(kk * r, kk * kk * r2) * dn / r * c2;
+            }
+        }
+        out[i * ns + j] = v * wj;
+    }
+}
+
+int layer_kernel_matrix(int kind, double k, int layer, const double* tx, const double* ty, int64_t nt, const double* sx,
+                        const double* sy, const double* snx, const double* sny, const double* w, int64_t ns, double* out,
+                        cudaStream_t st) {
+    if (nt <= 0 || ns <= 0) return IPDE_OK;
+    ARG_CHECK((kind == 0 || kind == 1) && (layer == 0 || layer == 1), "kind/layer must be 0 or 1");
+    if (kind == 1) ARG_CHECK(g_k0_ready, "K0 table not set (call ipde_set_k0_table)");
+    ARG_CHECK(layer == 0 || (snx && sny), "double layer needs source normals");
+    dim3 grid((unsigned)cdiv(ns, 128), (unsigned)std::min<int64_t>(nt, 4096));
+#define KM(K, L) k_kernel_matrix<K, L><<<grid, 128, 0, st>>>(tx, ty, nt, sx, sy, snx, sny, w, ns, k, out)
+    if (kind == 0 && layer == 0) KM(0, 0);
+    else if (kind == 0) KM(0, 1);
+    else if (layer == 0) KM(1, 0);
+    else KM(1, 1);
+#undef KM
+    KERNEL_CHECK();
+    return IPDE_OK;
+}

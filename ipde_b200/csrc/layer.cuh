@@ -9,3 +9,6 @@ int layer_apply_scalar(int kind, double k, const double* sx, const double* sy, c
 // out_uvp: (3, ntrg)
 int layer_apply_stokes(const double* sx, const double* sy, const double* fx, const double* fy, int64_t nsrc,
                        const double* tx, const double* ty, int64_t ntrg, double* out_uvp, int accumulate, cudaStream_t st);
+int layer_kernel_matrix(int kind, double k, int layer, const double* tx, const double* ty, int64_t nt, const double* sx,
+                        const double* sy, const double* snx, const double* sny, const double* w, int64_t ns, double* out,
+                        cudaStream_t st);

@@ -123,8 +123,12 @@ class QFS(object):
     interior:  True  -> represent the potential on the inside of the curve
     slp, dlp:  which layers the densities passed to __call__ contain (in that order)
     """
+    # boundaries with more nodes than this are factored on the device (scalar kernels; needs CUDA)
+    DEVICE_BUILD_MIN_N = 1500
+
     def __init__(self, bdy, interior, slp, dlp, kernel, tol=1e-12,
-                 source_upsample_factor=1.0, alpha_s=None, alpha_c=None, rho=None, rho_f=None):
+                 source_upsample_factor=1.0, alpha_s=None, alpha_c=None, rho=None, rho_f=None, u2s=True,
+                 device_build=None):
         self.bdy = bdy
         self.interior = interior
         self.has_slp, self.has_dlp = slp, dlp
@@ -136,9 +140,13 @@ class QFS(object):
         self.rho = (r if rho is None else rho)*source_upsample_factor
         self.rho_f = r_f if rho_f is None else rho_f
         self.svd_cut = min(1e-11, max(1e-14, tol))
-        self._build()
+        self.want_u2s = u2s
+        self.on_device = False
+        if device_build is None:
+            device_build = bdy.N > self.DEVICE_BUILD_MIN_N and kernel.ncomp == 1 and _cuda_available()
+        self._build(device_build)
 
-    def _build(self):
+    def _build(self, device_build=False):
         bdy, ker = self.bdy, self.kernel
         N = bdy.N
         nc = ker.ncomp
@@ -160,6 +168,8 @@ class QFS(object):
         self.source = GSB(c=offset_curve(bM, sgn*self.alpha_s*h))
         self.check = GSB(c=offset_curve(bM, -sgn*self.alpha_c*h))
         src, chk = self.source, self.check
+        if device_build:
+            return self._build_on_device(bM)
         w_s = np.tile(src.weights, nc)
         UM = fourier_resample_matrix(N, M)
         U_MN = UM if nc == 1 else scipy.linalg.block_diag(*([UM]*nc))
@@ -179,8 +189,85 @@ class QFS(object):
         # check <- source and boundary(M nodes) <- source, each as a truncated SVD  E = U S V^T
         E = ker.slp(chk.x, chk.y, src.x, src.y)*w_s[None, :]
         self.A, self.Sinv, self.V = self._factor(E, C)
-        Eb = ker.slp(bM.x, bM.y, src.x, src.y)*w_s[None, :]
-        self.Ab, self.Sinv_b, self.Vb = self._factor(Eb, U_MN)
+        if self.want_u2s:
+            Eb = ker.slp(bM.x, bM.y, src.x, src.y)*w_s[None, :]
+            self.Ab, self.Sinv_b, self.Vb = self._factor(Eb, U_MN)
+        else:
+            self.Ab = self.Sinv_b = self.Vb = None
+
+    def _build_on_device(self, bM):
+        """
+        The same operators, built on the GPU (setup only): kernel matrices by ipde_kernel_matrix (our K0/K1),
+        the product with the Fourier upsampling matrix as row FFTs (our Stockham FFT), SVD and the U^T C
+        products by torch.linalg (cuSOLVER / cuBLAS -- setup-time library calls, not on the per-solve path).
+        A, Sinv, V (and the u2s set) are left on the device as torch tensors.
+        """
+        import torch
+        from .device import to_dev, empty, ptr, stream, ensure_k0_table, FFT1D
+        from ._lib import lib
+        L = lib()
+        bdy, ker, src, chk = self.bdy, self.kernel, self.source, self.check
+        kind = 0 if ker.name == 'laplace' else 1
+        if kind == 1:
+            ensure_k0_table()
+        N, M = self.N, self.M
+        Nf = self.rho_f*N
+        bF = GSB(c=fourier_resample(bdy.c, Nf))
+        d = lambda a: to_dev(np.ascontiguousarray(a, dtype=float))
+        cx, cy = d(chk.x), d(chk.y)
+        fx, fy, fnx, fny, fw = d(bF.x), d(bF.y), d(bF.normal_x), d(bF.normal_y), d(bF.weights)
+        sx, sy, sw = d(src.x), d(src.y), d(src.weights)
+        fft_f, fft_c = FFT1D(Nf), FFT1D(N)
+        # coarse mode k' <- fine mode index (fourier_resample, upsampling branch)
+        hh = (N - 1)//2
+        idx = np.zeros(N, dtype=np.int64)
+        idx[:hh + 1] = np.arange(hh + 1)
+        idx[N - hh:] = Nf - hh + np.arange(hh)
+        d_idx = to_dev(idx)
+        layers = [l for l, on in ((0, self.has_slp), (1, self.has_dlp)) if on]
+        C = empty((M, len(layers)*N))
+        rows = max(1, min(M, int(2.0e9//(16*Nf))))
+        K = empty((rows, Nf))
+        for li, layer in enumerate(layers):
+            for r0 in range(0, M, rows):
+                r1 = min(M, r0 + rows)
+                nr = r1 - r0
+                L.ipde_kernel_matrix(kind, float(ker.k), layer, ptr(cx[r0:r1]), ptr(cy[r0:r1]), nr, ptr(fx), ptr(fy),
+                                     ptr(fnx), ptr(fny), ptr(fw), Nf, ptr(K), stream())
+                Kc = K[:nr].to(torch.complex128)
+                R = fft_f.c2c(Kc, +1)                       # sum_j r_j exp(+2 pi i j k / Nf)
+                Z = R[:, d_idx].contiguous()
+                if N % 2 == 0:
+                    q = N//2
+                    Z[:, q] = 0.5*(R[:, q] + R[:, Nf - q])
+                out = fft_c.c2c(Z, -1, 1.0/N)
+                C[r0:r1, li*N:(li + 1)*N] = out.real
+                del Kc, R, Z, out
+        del K
+        E = empty((M, M))
+        L.ipde_kernel_matrix(kind, float(ker.k), 0, ptr(cx), ptr(cy), M, ptr(sx), ptr(sy), 0, 0, ptr(sw), M, ptr(E),
+                             stream())
+        self.A, self.Sinv, self.V = self._factor_device(E, C)
+        del E, C
+        if self.want_u2s:
+            Eb = empty((M, M))
+            bx, by = d(bM.x), d(bM.y)
+            L.ipde_kernel_matrix(kind, float(ker.k), 0, ptr(bx), ptr(by), M, ptr(sx), ptr(sy), 0, 0, ptr(sw), M, ptr(Eb),
+                                 stream())
+            UM = to_dev(fourier_resample_matrix(N, M))
+            self.Ab, self.Sinv_b, self.Vb = self._factor_device(Eb, UM)
+            del Eb, UM
+        else:
+            self.Ab = self.Sinv_b = self.Vb = None
+        self.on_device = True
+
+    def _factor_device(self, E, rhs_op):
+        import torch
+        U, S, Vh = torch.linalg.svd(E, full_matrices=False, driver='gesvd')
+        keep = S > self.svd_cut*S[0]
+        Sinv = torch.where(keep, 1.0/torch.where(keep, S, torch.ones_like(S)), torch.zeros_like(S))
+        A = (U.T @ rhs_op).contiguous()
+        return A, Sinv.contiguous(), Vh.T.contiguous()
 
     def _factor(self, E, rhs_op):
         """E = U S V^T  ->  (U^T rhs_op, 1/S with tiny singular values dropped, V), all C-contiguous."""
@@ -197,22 +284,33 @@ class QFS(object):
 
     def __call__(self, tau_list):
         tau = np.concatenate([np.asarray(t, dtype=float).ravel() for t in tau_list])
+        if self.on_device:
+            import torch
+            t = torch.from_numpy(tau).to(self.A.device)
+            return (self.V @ (self.Sinv*(self.A @ t))).cpu().numpy()
         return self.V.dot(self.Sinv*self.A.dot(tau))
 
     def u2s(self, ub):
-        return self.Vb.dot(self.Sinv_b*self.Ab.dot(np.asarray(ub, dtype=float).ravel()))
+        if self.Ab is None:
+            raise Exception('this QFS object was built without the u2s operators (u2s=False)')
+        ub = np.asarray(ub, dtype=float).ravel()
+        if self.on_device:
+            import torch
+            t = torch.from_numpy(ub).to(self.Ab.device)
+            return (self.Vb @ (self.Sinv_b*(self.Ab @ t))).cpu().numpy()
+        return self.Vb.dot(self.Sinv_b*self.Ab.dot(ub))
+
+
+def _cuda_available():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
 
 
 def _svd(E):
-    """SVD on the host; large systems go through torch on the GPU when one is present (setup only)."""
-    if E.shape[0] > 2500:
-        try:
-            import torch
-            if torch.cuda.is_available():
-                U, S, Vh = torch.linalg.svd(torch.from_numpy(E).cuda())
-                return U.cpu().numpy(), S.cpu().numpy(), Vh.cpu().numpy()
-        except Exception:
-            pass
+    """SVD on the host (small systems and the CPU oracle); large boundaries use QFS._build_on_device."""
     return scipy.linalg.svd(E)
 
 

@@ -19,6 +19,6 @@ class ModifiedHelmholtzHelper(ScalarHelper):
         tol = min(getattr(self.ebdy, 'qfs_tolerance', 1e-12), 1e-12)
         suf = self.source_upsample_factor
         self.interface_qfs_g = Modified_Helmholtz_QFS(self.ebdy.interface, self.interior, True, True, self.k,
-                                                      source_upsample_factor=suf, tol=tol)
+                                                      source_upsample_factor=suf, tol=tol, u2s=False)
         self.interface_qfs_r = Modified_Helmholtz_QFS(self.ebdy.interface, not self.interior, True, True, self.k,
                                                       source_upsample_factor=suf, tol=tol)

@@ -16,5 +16,5 @@ class PoissonHelper(ScalarHelper):
 
     def _get_qfs(self):
         tol = getattr(self.ebdy, 'qfs_tolerance', 1e-12)
-        self.interface_qfs_g = Laplace_QFS(self.ebdy.interface, self.interior, True, True, tol=min(tol, 1e-12))
+        self.interface_qfs_g = Laplace_QFS(self.ebdy.interface, self.interior, True, True, tol=min(tol, 1e-12), u2s=False)
         self.interface_qfs_r = Laplace_QFS(self.ebdy.interface, not self.interior, True, True, tol=min(tol, 1e-12))

@@ -18,8 +18,12 @@ class DeviceQFS(object):
     def __init__(self, qfs):
         self.qfs = qfs
         self.M, self.N = qfs.M, qfs.N
-        self.A, self.Sinv, self.V = to_dev(qfs.A), to_dev(qfs.Sinv), to_dev(qfs.V)
-        self.Ab, self.Sinv_b, self.Vb = to_dev(qfs.Ab), to_dev(qfs.Sinv_b), to_dev(qfs.Vb)
+        up = (lambda a: a) if getattr(qfs, 'on_device', False) else to_dev
+        self.A, self.Sinv, self.V = up(qfs.A), up(qfs.Sinv), up(qfs.V)
+        if qfs.Ab is not None:
+            self.Ab, self.Sinv_b, self.Vb = up(qfs.Ab), up(qfs.Sinv_b), up(qfs.Vb)
+        else:
+            self.Ab = self.Sinv_b = self.Vb = None
         self.sx = to_dev(qfs.source.x)
         self.sy = to_dev(qfs.source.y)
         self.sw = to_dev(qfs.source.weights)
@@ -36,6 +40,8 @@ class DeviceQFS(object):
         return self._two_step(self.A, self.Sinv, self.V, tau)
 
     def u2s(self, ub):
+        if self.Ab is None:
+            raise Exception('QFS object built without u2s operators')
         return self._two_step(self.Ab, self.Sinv_b, self.Vb, ub)
 
 

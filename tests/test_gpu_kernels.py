@@ -313,3 +313,30 @@ def test_free_space_evaluator_matches_direct_sum(D, kind, kappa, N):
     out_grid2 = D.zeros((gix.size,))
     out_pts2 = ev(D.to_dev(q), grid_out=out_grid2)
     assert torch.equal(out_grid, out_grid2) and torch.equal(out_pts, out_pts2)
+
+
+@pytest.mark.parametrize('kind', ['laplace', 'modified_helmholtz'])
+@pytest.mark.parametrize('interior', [True, False])
+def test_qfs_device_build_matches_host_build(D, kind, interior):
+    """QFS operators built on the device (kernel matrices, FFT upsampling, cuSOLVER SVD) generate the same
+    source strengths as the NumPy build for smooth densities."""
+    from ipde_b200.geometry import GSB, star
+    from ipde_b200.qfs import Laplace_QFS, Modified_Helmholtz_QFS
+    bdy = GSB(c=star(240, a=0.15, f=5))
+    mk = (lambda **kw: Laplace_QFS(bdy, interior, True, True, **kw)) if kind == 'laplace' else \
+         (lambda **kw: Modified_Helmholtz_QFS(bdy, interior, True, True, 3.0, **kw))
+    qh = mk(device_build=False)
+    qd = mk(device_build=True)
+    assert qd.on_device and not qh.on_device
+    t = bdy.t
+    tau = [np.exp(np.cos(t))*np.sin(2*t), np.cos(3*t + 0.3)]
+    sh, sd = qh(tau), qd(tau)
+    # strengths agree up to the truncated directions; what has to agree is the potential they generate
+    th = np.linspace(0, 2*np.pi, 50, endpoint=False)
+    rad = 0.5 if interior else 2.0
+    tx, ty = rad*np.cos(th), rad*np.sin(th)
+    ker = qh.kernel
+    K = ker.slp(tx, ty, qh.source.x, qh.source.y)*qh.source.weights
+    assert rel(K.dot(sd), K.dot(sh)) < 1e-12
+    ub = np.exp(np.sin(t))
+    assert rel(K.dot(qd.u2s(ub)), K.dot(qh.u2s(ub))) < 1e-11
