@@ -1,7 +1,7 @@
-// FP64 Stockham FFT kernels (shared-memory staged, mixed radix 2/3/4/5/7/8/11/13) and a
+// FP64 Stockham FFT kernels (shared-memory tile engine of fft.cuh, mixed radix 2/3/4/5/7/8/11/13) and a
 // global-memory pass fallback for lines that do not fit one CTA's shared memory.
 // Replaces the reference's numpy.fft / mkl_fft calls (ipde/utilities.py:5-12).
-#include "fft.cuh"
+#include "fft_generic.cuh"
 #include <algorithm>
 
 // ------------------------------------------------------------------------------------------
@@ -9,9 +9,13 @@
 static bool factorize(int n, std::vector<int>& fac) {
     fac.clear();
     if (n < 1) return false;
-    while (n % 8 == 0) { fac.push_back(8); n /= 8; }
-    while (n % 4 == 0) { fac.push_back(4); n /= 4; }
-    while (n % 2 == 0) { fac.push_back(2); n /= 2; }
+    // powers of two: radix 8 with the remainder as radix 4 (or 4*4 instead of 8*2) so that no pass is radix 2
+    // unless n has a single factor of two -- every thread then owns 16 elements in every pass
+    int a = 0;
+    while (n % 2 == 0) { ++a; n /= 2; }
+    while (a >= 3 && a != 4) { fac.push_back(8); a -= 3; }
+    while (a >= 2) { fac.push_back(4); a -= 2; }
+    if (a == 1) fac.push_back(2);
     const int odd[] = {3, 5, 7, 11, 13};
     for (int p : odd)
         while (n % p == 0) { fac.push_back(p); n /= p; }
@@ -54,7 +58,12 @@ int fft_plan_create(int n, FftPlan** out) {
     FftPlan* p = new FftPlan();
     p->d.n = n;
     p->d.nfac = (int)fac.size();
-    for (int i = 0; i < p->d.nfac; ++i) p->d.fac[i] = fac[i];
+    p->pow2 = p->d.nfac > 0;
+    for (int i = 0; i < p->d.nfac; ++i) {
+        p->d.fac[i] = fac[i];
+        if (fac[i] > 5 && fac[i] != 8) p->fast = false;
+        if (fac[i] != 4 && fac[i] != 8) p->pow2 = false;
+    }
     std::vector<cplx> tw;
     fill_twiddles(tw, n, n, n);
     CUDA_TRY(cudaMalloc(&p->tw_dev, sizeof(cplx) * (size_t)n));
@@ -85,12 +94,39 @@ static int ensure_work(FftPlan* p, size_t elems) {
     return IPDE_OK;
 }
 
-static int pick_threads(int64_t items) {
-    if (items >= 2048) return 512;
-    if (items >= 512) return 256;
-    if (items >= 128) return 128;
-    return 64;
+static inline int pow2_floor(int64_t x) {
+    int p = 1;
+    while ((int64_t)p * 2 <= x) p *= 2;
+    return p;
 }
+static inline int ilog2(int x) {
+    int l = 0;
+    while ((1 << l) < x) ++l;
+    return l;
+}
+// lines per tile for contiguous rows of length n: tiles of ~2048 elements (256 threads, 2-3 CTAs per SM)
+static inline int rows_per_tile(int n, int64_t batch) {
+    int c = (n >= 2048) ? 1 : pow2_floor(2048 / n);
+    while (c > 1 && c > batch) c /= 2;
+    return c;
+}
+
+// elements per thread: 8 up to 4096-element tiles (<= 512 threads), 16 beyond
+static inline int tile_ept(int64_t elems) { return elems > 4096 ? 16 : 8; }
+
+// instantiate-and-launch over (elements per thread, radix class)
+#define FFT_TILE_LAUNCH_ONE(K, E_, C_, g, t, smem, st, ...)            \
+    do {                                                              \
+        rc = set_smem(K<E_, C_>, smem);                               \
+        if (!rc) K<E_, C_><<<g, t, smem, st>>>(__VA_ARGS__);          \
+    } while (0)
+#define FFT_TILE_LAUNCH(K, ept, pow2, g, t, smem, st, ...)                                   \
+    do {                                                                                    \
+        if ((ept) == 8 && (pow2)) FFT_TILE_LAUNCH_ONE(K, 8, 0, g, t, smem, st, __VA_ARGS__); \
+        else if ((ept) == 8) FFT_TILE_LAUNCH_ONE(K, 8, 1, g, t, smem, st, __VA_ARGS__);      \
+        else if (pow2) FFT_TILE_LAUNCH_ONE(K, 16, 0, g, t, smem, st, __VA_ARGS__);           \
+        else FFT_TILE_LAUNCH_ONE(K, 16, 1, g, t, smem, st, __VA_ARGS__);                     \
+    } while (0)
 
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
@@ -99,55 +135,64 @@ static int set_smem(K kernel, size_t bytes) {
 }
 
 // ------------------------------------------------------------------------------------------
-// contiguous rows, one line per CTA
-__global__ void k_fft_rows(FftPlanDev P, const cplx* __restrict__ in, cplx* __restrict__ out, int64_t in_pitch,
-                           int64_t out_pitch, int sign, double scale) {
+// contiguous rows, C lines per CTA
+template <int EPT, int CLS>
+__global__ void __launch_bounds__(512)
+k_fft_rows(FftPlanDev P, const cplx* __restrict__ in, cplx* __restrict__ out, int64_t batch, int64_t in_pitch,
+           int64_t out_pitch, int C, int sign, double scale) {
     extern __shared__ cplx smem[];
-    const int n = P.n;
-    cplx* a = smem;
-    cplx* b = smem + n;
-    const cplx* src = in + (int64_t)blockIdx.x * in_pitch;
-    cplx* dst = out + (int64_t)blockIdx.x * out_pitch;
-    for (int e = threadIdx.x; e < n; e += blockDim.x) a[e] = src[e];
+    const int n = P.n, tid = threadIdx.x, nt = blockDim.x;
+    const int64_t l0 = (int64_t)blockIdx.x * C;
+    const int cw = (int)min((int64_t)C, batch - l0);
+    for (int c = 0; c < C; ++c) {
+        if (c < cw) {
+            const cplx* src = in + (l0 + c) * in_pitch;
+            for (int e = tid; e < n; e += nt) smem[PADI(c * n + e)] = src[e];
+        } else {
+            for (int e = tid; e < n; e += nt) smem[PADI(c * n + e)] = make_double2(0.0, 0.0);
+        }
+    }
     __syncthreads();
-    cplx* r = stockham_smem(a, b, P, 1, sign, threadIdx.x, blockDim.x);
-    for (int e = threadIdx.x; e < n; e += blockDim.x) dst[e] = cscale(r[e], scale);
+    tile_fft<0, EPT, CLS>(smem, P, C, 0, sign, tid, nt);
+    for (int c = 0; c < cw; ++c) {
+        cplx* dst = out + (l0 + c) * out_pitch;
+        for (int e = tid; e < n; e += nt) dst[e] = cscale(smem[PADI(c * n + e)], scale);
+    }
 }
 
-// strided lines, C adjacent lines per CTA, optional four-step twiddle
-__global__ void k_fft_cols(FftPlanDev P, const cplx* __restrict__ in, cplx* __restrict__ out, int64_t elem_stride,
-                           int64_t n_inner, int64_t outer_stride, int C, int sign, double scale, int tw_mode,
-                           const cplx* __restrict__ tw_big, int64_t n_big) {
+// strided lines, C adjacent lines per CTA (C a power of two), optional four-step twiddle
+template <int EPT, int CLS>
+__global__ void __launch_bounds__(512)
+k_fft_cols(FftPlanDev P, const cplx* __restrict__ in, cplx* __restrict__ out, int64_t elem_stride, int64_t n_inner,
+           int64_t outer_stride, int C, int logC, int sign, double scale, int tw_mode, const cplx* __restrict__ tw_big) {
     extern __shared__ cplx smem[];
-    const int n = P.n;
-    cplx* a = smem;
-    cplx* b = smem + (size_t)n * C;
-    const int64_t tiles = (n_inner + C - 1) / C;
-    const int64_t o = blockIdx.x / tiles;
-    const int64_t c0 = (blockIdx.x % tiles) * C;
+    const int n = P.n, tid = threadIdx.x, nt = blockDim.x;
+    const int64_t tiles = (n_inner + C - 1) >> logC;
+    const int o = (int)(blockIdx.x / tiles);
+    const int64_t c0 = (blockIdx.x - (int64_t)o * tiles) << logC;
     const int cw = (int)min((int64_t)C, n_inner - c0);
-    const int64_t base = o * outer_stride + c0;
-    const int total = n * C;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int c = i % C, e = i / C;
+    const int64_t base = (int64_t)o * outer_stride + c0;
+    const int total = n << logC;
+    for (int i = tid; i < total; i += nt) {
+        const int c = i & (C - 1), e = i >> logC;
         cplx v = make_double2(0.0, 0.0);
         if (c < cw) {
             v = in[base + (int64_t)e * elem_stride + c];
             if (tw_mode == 2) {
-                cplx w = tw_big[(o * (int64_t)e) % n_big];
+                const cplx w = tw_big[o * e];
                 v = (sign < 0) ? cmul(v, w) : cmulc(v, w);
             }
         }
-        a[i] = v;
+        smem[PADI(i)] = v;
     }
     __syncthreads();
-    cplx* r = stockham_smem(a, b, P, C, sign, threadIdx.x, blockDim.x);
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int c = i % C, e = i / C;
+    tile_fft<1, EPT, CLS>(smem, P, C, logC, sign, tid, nt);
+    for (int i = tid; i < total; i += nt) {
+        const int c = i & (C - 1), e = i >> logC;
         if (c < cw) {
-            cplx v = r[i];
+            cplx v = smem[PADI(i)];
             if (tw_mode == 1) {
-                cplx w = tw_big[(o * (int64_t)e) % n_big];
+                const cplx w = tw_big[o * e];
                 v = (sign < 0) ? cmul(v, w) : cmulc(v, w);
             }
             out[base + (int64_t)e * elem_stride + c] = cscale(v, scale);
@@ -233,11 +278,16 @@ int fft_rows(FftPlan* p, const cplx* in, cplx* out, int64_t batch, int64_t in_pi
              double scale, cudaStream_t st) {
     if (batch <= 0) return IPDE_OK;
     const int n = p->d.n;
-    if (n > IPDE_FFT_SMEM_MAX) return fft_lines_global(p, in, out, batch, in_pitch, 1, out_pitch, 1, sign, scale, st);
-    const size_t smem = sizeof(cplx) * 2 * (size_t)n;
-    int rc = set_smem(k_fft_rows, smem);
+    if (!p->fast && n <= IPDE_FFT_GENERIC_MAX) return fft_rows_generic(p, in, out, batch, in_pitch, out_pitch, sign, scale, st);
+    if (n > IPDE_FFT_SMEM_MAX || !p->fast) return fft_lines_global(p, in, out, batch, in_pitch, 1, out_pitch, 1, sign, scale, st);
+    const int C = rows_per_tile(n, batch);
+    const size_t smem = fft_tile_smem((int64_t)n * C);
+    const int ept = tile_ept((int64_t)n * C);
+    const unsigned g = (unsigned)cdiv(batch, C);
+    const int t = fft_tile_threads(n, C, ept);
+    int rc = IPDE_OK;
+    FFT_TILE_LAUNCH(k_fft_rows, ept, p->pow2, g, t, smem, st, p->d, in, out, batch, in_pitch, out_pitch, C, sign, scale);
     if (rc) return rc;
-    k_fft_rows<<<(unsigned)batch, pick_threads(n / 4), smem, st>>>(p->d, in, out, in_pitch, out_pitch, sign, scale);
     KERNEL_CHECK();
     return IPDE_OK;
 }
@@ -247,7 +297,9 @@ int fft_cols(FftPlan* p, const cplx* in, cplx* out, int64_t elem_stride, int64_t
              cudaStream_t st) {
     if (n_inner <= 0 || n_outer <= 0) return IPDE_OK;
     const int n = p->d.n;
-    if (n > IPDE_FFT_SMEM_MAX) {
+    if (!p->fast && n <= IPDE_FFT_GENERIC_MAX)
+        return fft_cols_generic(p, in, out, elem_stride, n_inner, n_outer, outer_stride, sign, scale, tw_mode, tw_big, n_big, st);
+    if (n > IPDE_FFT_SMEM_MAX || !p->fast) {
         if (tw_mode != 0) {
             ipde_set_error("fft_cols: twiddled transform of length %d does not fit shared memory", n);
             return IPDE_ERR_UNSUPPORTED;
@@ -260,60 +312,84 @@ int fft_cols(FftPlan* p, const cplx* in, cplx* out, int64_t elem_stride, int64_t
         }
         return IPDE_OK;
     }
-    int C = IPDE_FFT_SMEM_MAX / n;
+    int C = pow2_floor(IPDE_FFT_SMEM_MAX / n);
     if (C > 16) C = 16;
-    if (C > n_inner) C = (int)n_inner;
-    if (C < 1) C = 1;
-    const size_t smem = sizeof(cplx) * 2 * (size_t)n * C;
-    int rc = set_smem(k_fft_cols, smem);
-    if (rc) return rc;
+    while (C > 1 && C / 2 >= n_inner) C /= 2;
+    const int logC = ilog2(C);
+    const size_t smem = fft_tile_smem((int64_t)n * C);
+    const int ept = tile_ept((int64_t)n * C);
     const int64_t tiles = cdiv(n_inner, C);
-    k_fft_cols<<<(unsigned)(tiles * n_outer), pick_threads((int64_t)n * C / 4), smem, st>>>(
-        p->d, in, out, elem_stride, n_inner, outer_stride, C, sign, scale, tw_mode, tw_big, n_big);
+    const unsigned g = (unsigned)(tiles * n_outer);
+    const int t = fft_tile_threads(n, C, ept);
+    int rc = IPDE_OK;
+    FFT_TILE_LAUNCH(k_fft_cols, ept, p->pow2, g, t, smem, st, p->d, in, out, elem_stride, n_inner, outer_stride, C, logC, sign, scale, tw_mode, tw_big);
+    if (rc) return rc;
     KERNEL_CHECK();
     return IPDE_OK;
 }
 
 // ------------------------------------------------------------------------------------------
-// real rows
-__global__ void k_r2c_rows(FftPlanDev P, const cplx* __restrict__ half_tw, const double* __restrict__ in,
-                           cplx* __restrict__ out, int64_t in_pitch, int64_t out_pitch) {
+// real rows (C lines per CTA): packed complex FFT of length n + untangling, fused
+template <int EPT, int CLS>
+__global__ void __launch_bounds__(512)
+k_r2c_rows(FftPlanDev P, const cplx* __restrict__ half_tw, const double* __restrict__ in, cplx* __restrict__ out,
+           int64_t batch, int64_t in_pitch, int64_t out_pitch, int C) {
     extern __shared__ cplx smem[];
-    const int n = P.n;   // complex length = real length / 2
-    cplx* a = smem;
-    cplx* b = smem + n;
-    const cplx* src = reinterpret_cast<const cplx*>(in + (int64_t)blockIdx.x * in_pitch);
-    cplx* dst = out + (int64_t)blockIdx.x * out_pitch;
-    for (int e = threadIdx.x; e < n; e += blockDim.x) a[e] = src[e];
+    const int n = P.n, tid = threadIdx.x, nt = blockDim.x;   // n = complex length = real length / 2
+    const int64_t l0 = (int64_t)blockIdx.x * C;
+    const int cw = (int)min((int64_t)C, batch - l0);
+    for (int c = 0; c < C; ++c) {
+        if (c < cw) {
+            const cplx* src = reinterpret_cast<const cplx*>(in + (l0 + c) * in_pitch);
+            for (int e = tid; e < n; e += nt) smem[PADI(c * n + e)] = src[e];
+        } else {
+            for (int e = tid; e < n; e += nt) smem[PADI(c * n + e)] = make_double2(0.0, 0.0);
+        }
+    }
     __syncthreads();
-    cplx* z = stockham_smem(a, b, P, 1, -1, threadIdx.x, blockDim.x);
-    for (int k = threadIdx.x; k <= n; k += blockDim.x) {
-        cplx zk = z[k == n ? 0 : k];
-        cplx zc = cconj(z[k == 0 ? 0 : n - k]);
-        cplx E = cscale(cadd(zk, zc), 0.5);
-        cplx O = cmulni(cscale(csub(zk, zc), 0.5));
-        dst[k] = cadd(E, cmul(half_tw[k], O));
+    tile_fft<0, EPT, CLS>(smem, P, C, 0, -1, tid, nt);
+    for (int c = 0; c < cw; ++c) {
+        cplx* dst = out + (l0 + c) * out_pitch;
+        const int b = c * n;
+        for (int k = tid; k <= n; k += nt) {
+            const cplx zk = smem[PADI(b + (k == n ? 0 : k))];
+            const cplx zc = cconj(smem[PADI(b + (k == 0 ? 0 : n - k))]);
+            const cplx E = cscale(cadd(zk, zc), 0.5);
+            const cplx O = cmulni(cscale(csub(zk, zc), 0.5));
+            dst[k] = cadd(E, cmul(half_tw[k], O));
+        }
     }
 }
 
-__global__ void k_c2r_rows(FftPlanDev P, const cplx* __restrict__ half_tw, const cplx* __restrict__ in,
-                           double* __restrict__ out, int64_t in_pitch, int64_t out_pitch, double scale) {
+template <int EPT, int CLS>
+__global__ void __launch_bounds__(512)
+k_c2r_rows(FftPlanDev P, const cplx* __restrict__ half_tw, const cplx* __restrict__ in, double* __restrict__ out,
+           int64_t batch, int64_t in_pitch, int64_t out_pitch, int C, double scale) {
     extern __shared__ cplx smem[];
-    const int n = P.n;
-    cplx* a = smem;
-    cplx* b = smem + n;
-    const cplx* src = in + (int64_t)blockIdx.x * in_pitch;
-    cplx* dst = reinterpret_cast<cplx*>(out + (int64_t)blockIdx.x * out_pitch);
-    for (int k = threadIdx.x; k < n; k += blockDim.x) {
-        cplx xk = src[k];
-        cplx xc = cconj(src[n - k]);
-        cplx E = cscale(cadd(xk, xc), 0.5);
-        cplx O = cmulc(cscale(csub(xk, xc), 0.5), half_tw[k]);
-        a[k] = cadd(E, cmuli(O));
+    const int n = P.n, tid = threadIdx.x, nt = blockDim.x;
+    const int64_t l0 = (int64_t)blockIdx.x * C;
+    const int cw = (int)min((int64_t)C, batch - l0);
+    for (int c = 0; c < C; ++c) {
+        const int b = c * n;
+        if (c < cw) {
+            const cplx* src = in + (l0 + c) * in_pitch;
+            for (int k = tid; k < n; k += nt) {
+                const cplx xk = src[k];
+                const cplx xc = cconj(src[n - k]);
+                const cplx E = cscale(cadd(xk, xc), 0.5);
+                const cplx O = cmulc(cscale(csub(xk, xc), 0.5), half_tw[k]);
+                smem[PADI(b + k)] = cadd(E, cmuli(O));
+            }
+        } else {
+            for (int k = tid; k < n; k += nt) smem[PADI(b + k)] = make_double2(0.0, 0.0);
+        }
     }
     __syncthreads();
-    cplx* z = stockham_smem(a, b, P, 1, +1, threadIdx.x, blockDim.x);
-    for (int e = threadIdx.x; e < n; e += blockDim.x) dst[e] = cscale(z[e], scale);
+    tile_fft<0, EPT, CLS>(smem, P, C, 0, +1, tid, nt);
+    for (int c = 0; c < cw; ++c) {
+        cplx* dst = reinterpret_cast<cplx*>(out + (l0 + c) * out_pitch);
+        for (int e = tid; e < n; e += nt) dst[e] = cscale(smem[PADI(c * n + e)], scale);
+    }
 }
 
 // Global-memory versions of the pack / unpack steps for long rows
@@ -350,7 +426,8 @@ int fft_r2c_rows(FftPlan* p, const double* in, cplx* out, int64_t batch, int64_t
                  cudaStream_t st) {
     if (batch <= 0) return IPDE_OK;
     const int n = p->d.n;
-    if (n > IPDE_FFT_SMEM_MAX) {
+    if (!p->fast && n <= IPDE_FFT_GENERIC_MAX) return fft_r2c_rows_generic(p, in, out, batch, in_pitch, out_pitch, st);
+    if (n > IPDE_FFT_SMEM_MAX || !p->fast) {
         // complex FFT of the packed rows into the front of each output row, then untangle in place is not
         // possible (aliasing), so go through the plan's work buffer
         int rc = ensure_work(p, (size_t)3 * n * batch);
@@ -363,10 +440,14 @@ int fft_r2c_rows(FftPlan* p, const double* in, cplx* out, int64_t batch, int64_t
         KERNEL_CHECK();
         return IPDE_OK;
     }
-    const size_t smem = sizeof(cplx) * 2 * (size_t)n;
-    int rc = set_smem(k_r2c_rows, smem);
+    const int C = rows_per_tile(n, batch);
+    const size_t smem = fft_tile_smem((int64_t)n * C);
+    const int ept = tile_ept((int64_t)n * C);
+    const unsigned g = (unsigned)cdiv(batch, C);
+    const int t = fft_tile_threads(n, C, ept);
+    int rc = IPDE_OK;
+    FFT_TILE_LAUNCH(k_r2c_rows, ept, p->pow2, g, t, smem, st, p->d, p->half_tw_dev, in, out, batch, in_pitch, out_pitch, C);
     if (rc) return rc;
-    k_r2c_rows<<<(unsigned)batch, pick_threads(n / 4), smem, st>>>(p->d, p->half_tw_dev, in, out, in_pitch, out_pitch);
     KERNEL_CHECK();
     return IPDE_OK;
 }
@@ -375,7 +456,8 @@ int fft_c2r_rows(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t
                  double scale, cudaStream_t st) {
     if (batch <= 0) return IPDE_OK;
     const int n = p->d.n;
-    if (n > IPDE_FFT_SMEM_MAX) {
+    if (!p->fast && n <= IPDE_FFT_GENERIC_MAX) return fft_c2r_rows_generic(p, in, out, batch, in_pitch, out_pitch, scale, st);
+    if (n > IPDE_FFT_SMEM_MAX || !p->fast) {
         int rc = ensure_work(p, (size_t)3 * n * batch);
         if (rc) return rc;
         cplx* z = p->work + (size_t)2 * n * batch;
@@ -384,32 +466,48 @@ int fft_c2r_rows(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t
         KERNEL_CHECK();
         return fft_lines_global(p, z, reinterpret_cast<cplx*>(out), batch, n, 1, out_pitch / 2, 1, +1, scale, st);
     }
-    const size_t smem = sizeof(cplx) * 2 * (size_t)n;
-    int rc = set_smem(k_c2r_rows, smem);
+    const int C = rows_per_tile(n, batch);
+    const size_t smem = fft_tile_smem((int64_t)n * C);
+    const int ept = tile_ept((int64_t)n * C);
+    const unsigned g = (unsigned)cdiv(batch, C);
+    const int t = fft_tile_threads(n, C, ept);
+    int rc = IPDE_OK;
+    FFT_TILE_LAUNCH(k_c2r_rows, ept, p->pow2, g, t, smem, st, p->d, p->half_tw_dev, in, out, batch, in_pitch, out_pitch, C, scale);
     if (rc) return rc;
-    k_c2r_rows<<<(unsigned)batch, pick_threads(n / 4), smem, st>>>(p->d, p->half_tw_dev, in, out, in_pitch, out_pitch, scale);
     KERNEL_CHECK();
     return IPDE_OK;
 }
 
 // ------------------------------------------------------------------------------------------
-// out = FFT(m * IFFT(in)) / n, fused in shared memory
-__global__ void k_fft_mul_fft_rows(FftPlanDev P, const cplx* __restrict__ in, cplx* __restrict__ out,
-                                   const double* __restrict__ m) {
+// out = FFT(m * IFFT(in)) / n, fused in shared memory, C lines per CTA
+template <int EPT, int CLS>
+__global__ void __launch_bounds__(512)
+k_fft_mul_fft_rows(FftPlanDev P, const cplx* __restrict__ in, cplx* __restrict__ out, const double* __restrict__ m,
+                   int64_t batch, int C) {
     extern __shared__ cplx smem[];
-    const int n = P.n;
-    cplx* a = smem;
-    cplx* b = smem + n;
-    const int64_t off = (int64_t)blockIdx.x * n;
-    for (int e = threadIdx.x; e < n; e += blockDim.x) a[e] = in[off + e];
+    const int n = P.n, tid = threadIdx.x, nt = blockDim.x;
+    const int64_t l0 = (int64_t)blockIdx.x * C;
+    const int cw = (int)min((int64_t)C, batch - l0);
+    for (int c = 0; c < C; ++c) {
+        const int64_t off = (l0 + c) * n;
+        for (int e = tid; e < n; e += nt) smem[PADI(c * n + e)] = (c < cw) ? in[off + e] : make_double2(0.0, 0.0);
+    }
     __syncthreads();
-    cplx* r = stockham_smem(a, b, P, 1, +1, threadIdx.x, blockDim.x);
+    tile_fft<0, EPT, CLS>(smem, P, C, 0, +1, tid, nt);
     const double inv = 1.0 / n;
-    for (int e = threadIdx.x; e < n; e += blockDim.x) r[e] = cscale(r[e], m[off + e] * inv);
+    for (int c = 0; c < cw; ++c) {
+        const int64_t off = (l0 + c) * n;
+        for (int e = tid; e < n; e += nt) {
+            const int sidx = PADI(c * n + e);
+            smem[sidx] = cscale(smem[sidx], m[off + e] * inv);
+        }
+    }
     __syncthreads();
-    cplx* other = (r == a) ? b : a;
-    cplx* f = stockham_smem(r, other, P, 1, -1, threadIdx.x, blockDim.x);
-    for (int e = threadIdx.x; e < n; e += blockDim.x) out[off + e] = f[e];
+    tile_fft<0, EPT, CLS>(smem, P, C, 0, -1, tid, nt);
+    for (int c = 0; c < cw; ++c) {
+        const int64_t off = (l0 + c) * n;
+        for (int e = tid; e < n; e += nt) out[off + e] = smem[PADI(c * n + e)];
+    }
 }
 
 __global__ void k_scale_by_real(cplx* __restrict__ z, const double* __restrict__ m, int64_t total, double s) {
@@ -420,7 +518,8 @@ __global__ void k_scale_by_real(cplx* __restrict__ z, const double* __restrict__
 int fft_mul_fft_rows(FftPlan* p, const cplx* in, cplx* out, const double* m, int64_t batch, cudaStream_t st) {
     if (batch <= 0) return IPDE_OK;
     const int n = p->d.n;
-    if (n > IPDE_FFT_SMEM_MAX) {
+    if (!p->fast && n <= IPDE_FFT_GENERIC_MAX) return fft_mul_fft_rows_generic(p, in, out, m, batch, st);
+    if (n > IPDE_FFT_SMEM_MAX || !p->fast) {
         int rc = fft_lines_global(p, in, out, batch, n, 1, n, 1, +1, 1.0, st);
         if (rc) return rc;
         const int64_t total = batch * n;
@@ -429,10 +528,14 @@ int fft_mul_fft_rows(FftPlan* p, const cplx* in, cplx* out, const double* m, int
         KERNEL_CHECK();
         return fft_lines_global(p, out, out, batch, n, 1, n, 1, -1, 1.0, st);
     }
-    const size_t smem = sizeof(cplx) * 2 * (size_t)n;
-    int rc = set_smem(k_fft_mul_fft_rows, smem);
+    const int C = rows_per_tile(n, batch);
+    const size_t smem = fft_tile_smem((int64_t)n * C);
+    const int ept = tile_ept((int64_t)n * C);
+    const unsigned g = (unsigned)cdiv(batch, C);
+    const int t = fft_tile_threads(n, C, ept);
+    int rc = IPDE_OK;
+    FFT_TILE_LAUNCH(k_fft_mul_fft_rows, ept, p->pow2, g, t, smem, st, p->d, in, out, m, batch, C);
     if (rc) return rc;
-    k_fft_mul_fft_rows<<<(unsigned)batch, pick_threads(n / 4), smem, st>>>(p->d, in, out, m);
     KERNEL_CHECK();
     return IPDE_OK;
 }

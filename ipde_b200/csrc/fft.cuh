@@ -1,12 +1,22 @@
-// Hand-written FP64 Stockham FFT for sm_100a: plans + shared-memory device routines.
+// Hand-written FP64 Stockham FFT for sm_100a: plans + the shared-memory tile engine.
 // No cuFFT anywhere.  See fft.cu for the kernels and DESIGN.md for the pass structure.
+//
+// Tile engine.  A CTA holds a tile of C lines of length n (n*C <= IPDE_FFT_SMEM_MAX complex numbers) in ONE
+// shared-memory buffer.  A radix-R pass is done in place through registers: every thread reads the R inputs of
+// its butterflies, the CTA synchronises, every thread twiddles, transforms and writes its R outputs to the
+// autosort (Stockham) positions.  Each thread owns 16 elements per pass (16/R butterflies), so a tile of 4096
+// elements runs on 256 threads and two CTAs fit an SM: one CTA's global loads overlap the other's passes.
+// Shared memory is skewed by one 16-byte slot every 8 (PADI) so that the stride-R writes of the first passes
+// are bank-conflict free.  Twiddles: one table load per butterfly, the remaining powers by a depth-log2(R)
+// product tree (<= 3 roundings for R = 8).
 #pragma once
 #include "common.cuh"
 
 #define IPDE_FFT_MAX_FACTORS 24
-#define IPDE_FFT_MAX_RADIX 32
-// ping-pong shared-memory capacity in complex elements (2 buffers x 16 B x n <= 227 KB)
-#define IPDE_FFT_SMEM_MAX 7168
+#define IPDE_FFT_MAX_RADIX 13
+// capacity of one tile in complex elements: 8192 * 9/8 * 16 B = 144 KB of shared memory, 512 threads
+#define IPDE_FFT_SMEM_MAX 8192
+#define PADI(u) ((u) + ((u) >> 3))
 
 struct FftPlanDev {
     int n;
@@ -20,6 +30,8 @@ struct FftPlan {
     cplx* tw_dev = nullptr;
     cplx* half_tw_dev = nullptr;  // exp(-2 pi i k / (2n)), k <= n : for real transforms of length 2n
     cplx* work = nullptr;         // scratch for the global-memory path
+    bool fast = true;             // all radices in {2,3,4,5,8}: tile engine; otherwise fft_generic.cu
+    bool pow2 = false;            // radices 4 and 8 only (lean kernel instantiation)
     size_t work_elems = 0;
 };
 
@@ -36,7 +48,8 @@ int fft_rows(FftPlan* p, const cplx* in, cplx* out, int64_t batch, int64_t in_pi
 // Batched transforms of strided lines.  Line (o, c): base = o*outer_stride + c, elements at
 // base + e*elem_stride; c in [0, n_inner) are adjacent in memory.  Optional four-step twiddle:
 // tw_mode 1 multiplies output element e of outer line o by exp(-/+ 2 pi i (o*e) / n_big) (sign
-// follows `sign`), tw_mode 2 multiplies the *input* likewise.
+// follows `sign`), tw_mode 2 multiplies the *input* likewise.  n_in <= n: only the first n_in elements of
+// every input line are read (the rest are zero); only the first n_out output elements are written.
 int fft_cols(FftPlan* p, const cplx* in, cplx* out, int64_t elem_stride, int64_t n_inner, int64_t n_outer,
              int64_t outer_stride, int sign, double scale, int tw_mode, const cplx* tw_big, int64_t n_big,
              cudaStream_t st);
@@ -124,62 +137,152 @@ __device__ __forceinline__ void dft_generic(cplx* v, int sign, const FftPlanDev&
 #pragma unroll
     for (int q = 0; q < R; ++q) v[q] = o[q];
 }
-template <> __device__ __forceinline__ void dft_small<3>(cplx* v, int s, const FftPlanDev& P) { dft_generic<3>(v, s, P); }
-template <> __device__ __forceinline__ void dft_small<5>(cplx* v, int s, const FftPlanDev& P) { dft_generic<5>(v, s, P); }
+template <>
+__device__ __forceinline__ void dft_small<3>(cplx* v, int sign, const FftPlanDev& P) {
+    const double s3 = 0.86602540378443864676;     // sin(2 pi / 3)
+    const cplx a = cadd(v[1], v[2]);
+    const cplx d = cscale(csub(v[1], v[2]), (sign < 0) ? -s3 : s3);
+    const cplx r = make_double2(v[0].x - 0.5 * a.x, v[0].y - 0.5 * a.y);
+    v[0] = cadd(v[0], a);
+    v[1] = make_double2(r.x - d.y, r.y + d.x);    // r + i d
+    v[2] = make_double2(r.x + d.y, r.y - d.x);    // r - i d
+}
+
+template <>
+__device__ __forceinline__ void dft_small<5>(cplx* v, int sign, const FftPlanDev& P) {
+    const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;   // cos(2 pi/5), cos(4 pi/5)
+    double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;          // sin(2 pi/5), sin(4 pi/5)
+    if (sign < 0) { s1 = -s1; s2 = -s2; }
+    const cplx a1 = cadd(v[1], v[4]), a2 = cadd(v[2], v[3]);
+    const cplx b1 = csub(v[1], v[4]), b2 = csub(v[2], v[3]);
+    const cplx r1 = make_double2(v[0].x + c1 * a1.x + c2 * a2.x, v[0].y + c1 * a1.y + c2 * a2.y);
+    const cplx r2 = make_double2(v[0].x + c2 * a1.x + c1 * a2.x, v[0].y + c2 * a1.y + c1 * a2.y);
+    const cplx i1 = make_double2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y);
+    const cplx i2 = make_double2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y);
+    v[0] = cadd(v[0], cadd(a1, a2));
+    v[1] = make_double2(r1.x - i1.y, r1.y + i1.x);
+    v[4] = make_double2(r1.x + i1.y, r1.y - i1.x);
+    v[2] = make_double2(r2.x - i2.y, r2.y + i2.x);
+    v[3] = make_double2(r2.x + i2.y, r2.y - i2.x);
+}
 template <> __device__ __forceinline__ void dft_small<7>(cplx* v, int s, const FftPlanDev& P) { dft_generic<7>(v, s, P); }
 template <> __device__ __forceinline__ void dft_small<11>(cplx* v, int s, const FftPlanDev& P) { dft_generic<11>(v, s, P); }
 template <> __device__ __forceinline__ void dft_small<13>(cplx* v, int s, const FftPlanDev& P) { dft_generic<13>(v, s, P); }
 
-// One Stockham pass of radix R over C interleaved lines held in src (element e of line c at
-// src[e*C + c]); result in dst.  All threads of the CTA participate; caller syncs.
-template <int R>
-__device__ __forceinline__ void stockham_pass(const cplx* __restrict__ src, cplx* __restrict__ dst,
-                                              const FftPlanDev& P, int Ns, int C, int sign, int tid, int nt) {
+// Tile layouts: element e of line c lives at logical slot
+//   LAYOUT 0 (rows):    c*n + e      (lines contiguous, as in global memory)
+//   LAYOUT 1 (columns): e*C + c      (C adjacent lines interleaved, C a power of two)
+// and at physical slot PADI(logical).
+template <int LAYOUT>
+__device__ __forceinline__ int tile_slot(int e, int c, int n, int logC) {
+    return PADI(LAYOUT == 0 ? c * n + e : (e << logC) + c);
+}
+
+// One in-place radix-R Stockham pass over the tile.  Begins and ends with the tile consistent; contains
+// two __syncthreads().  Every thread owns EPT elements per pass (IPT = ceil(EPT/R) butterflies).
+//   LAYOUT 1: butterfly index it = tid + q*nt -> (c = it % C, j = it / C), C a power of two;
+//   LAYOUT 0: the CTA is split into C groups of G = ceil(n/EPT) threads, group c works on line c
+//             (c = tid / G is computed once per kernel: no integer division per butterfly).
+struct TileThread {
+    int c;      // LAYOUT 0: my line (or -1: idle thread)
+    int lt;     // LAYOUT 0: my index inside the group
+    int G;      // LAYOUT 0: threads per line
+};
+
+template <int R, int LAYOUT, int EPT>
+__device__ __forceinline__ void tile_pass(cplx* __restrict__ s, const FftPlanDev& P, int Ns, int C, int logC, int sign,
+                                          int tid, int nt, const TileThread& T) {
+    constexpr int IPT = (EPT + R - 1) / R;
     const int n = P.n;
     const int m = n / R;
     const int tstep = n / (Ns * R);
-    const int items = m * C;
-    for (int it = tid; it < items; it += nt) {
-        const int c = it % C;
-        const int j = it / C;
-        const int k = j % Ns;
-        cplx v[R];
+    const bool ns_pow2 = (Ns & (Ns - 1)) == 0;
+    const int items = (LAYOUT == 1) ? (m << logC) : m;
+    const int stride = (LAYOUT == 1) ? nt : T.G;
+    const int first = (LAYOUT == 1) ? tid : T.lt;
+    const bool live = (LAYOUT == 1) || (T.c >= 0);
+    cplx v[IPT][R];
 #pragma unroll
-        for (int t = 0; t < R; ++t) v[t] = src[(j + t * m) * C + c];
-        if (Ns > 1) {
+    for (int q = 0; q < IPT; ++q) {
+        const int it = first + q * stride;
+        if (live && it < items) {
+            const int c = (LAYOUT == 1) ? (it & (C - 1)) : T.c;
+            const int j = (LAYOUT == 1) ? (it >> logC) : it;
 #pragma unroll
-            for (int t = 1; t < R; ++t) {
-                cplx w = P.tw[t * k * tstep];
-                v[t] = (sign < 0) ? cmul(v[t], w) : cmulc(v[t], w);
-            }
+            for (int t = 0; t < R; ++t) v[q][t] = s[tile_slot<LAYOUT>(j + t * m, c, n, logC)];
         }
-        dft_small<R>(v, sign, P);
-        const int j0 = (j - k) * R + k;
-#pragma unroll
-        for (int t = 0; t < R; ++t) dst[(j0 + t * Ns) * C + c] = v[t];
     }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < IPT; ++q) {
+        const int it = first + q * stride;
+        if (live && it < items) {
+            const int c = (LAYOUT == 1) ? (it & (C - 1)) : T.c;
+            const int j = (LAYOUT == 1) ? (it >> logC) : it;
+            const int k = ns_pow2 ? (j & (Ns - 1)) : (j % Ns);
+            if (Ns > 1) {
+                cplx w[R];
+                w[1] = P.tw[k * tstep];
+                if (sign > 0) w[1] = cconj(w[1]);
+#pragma unroll
+                for (int t = 2; t < R; ++t) w[t] = cmul(w[t >> 1], w[t - (t >> 1)]);
+#pragma unroll
+                for (int t = 1; t < R; ++t) v[q][t] = cmul(v[q][t], w[t]);
+            }
+            dft_small<R>(v[q], sign, P);
+            const int j0 = (j - k) * R + k;
+#pragma unroll
+            for (int t = 0; t < R; ++t) s[tile_slot<LAYOUT>(j0 + t * Ns, c, n, logC)] = v[q][t];
+        }
+    }
+    __syncthreads();
 }
 
-// Full transform in shared memory; returns the buffer holding the result.  Ends with __syncthreads().
-__device__ __forceinline__ cplx* stockham_smem(cplx* a, cplx* b, const FftPlanDev& P, int C, int sign, int tid,
-                                               int nt) {
+template <int LAYOUT, int EPT>
+__device__ __forceinline__ TileThread tile_thread(int n, int C, int tid) {
+    TileThread T;
+    T.G = (n + EPT - 1) / EPT;
+    if (LAYOUT == 0) {
+        const int c = tid / T.G;
+        T.lt = tid - c * T.G;
+        T.c = (c < C) ? c : -1;
+    } else {
+        T.c = 0; T.lt = tid;
+    }
+    return T;
+}
+
+// Full transform of the tile, in place.  Caller must have synchronised after filling the tile.
+// CLS 0: n is a power of two >= 4 (radices 4 and 8 only -- the lean instantiation every power-of-two grid uses);
+// CLS 1: radices 2, 3, 4, 5, 8.
+template <int LAYOUT, int EPT, int CLS>
+__device__ __forceinline__ void tile_fft(cplx* s, const FftPlanDev& P, int C, int logC, int sign, int tid, int nt) {
+    const TileThread T = tile_thread<LAYOUT, EPT>(P.n, C, tid);
     int Ns = 1;
     for (int f = 0; f < P.nfac; ++f) {
         const int R = P.fac[f];
-        switch (R) {
-            case 2: stockham_pass<2>(a, b, P, Ns, C, sign, tid, nt); break;
-            case 3: stockham_pass<3>(a, b, P, Ns, C, sign, tid, nt); break;
-            case 4: stockham_pass<4>(a, b, P, Ns, C, sign, tid, nt); break;
-            case 5: stockham_pass<5>(a, b, P, Ns, C, sign, tid, nt); break;
-            case 7: stockham_pass<7>(a, b, P, Ns, C, sign, tid, nt); break;
-            case 8: stockham_pass<8>(a, b, P, Ns, C, sign, tid, nt); break;
-            case 11: stockham_pass<11>(a, b, P, Ns, C, sign, tid, nt); break;
-            case 13: stockham_pass<13>(a, b, P, Ns, C, sign, tid, nt); break;
-            default: break;
+        if (CLS == 0) {
+            if (R == 8) tile_pass<8, LAYOUT, EPT>(s, P, Ns, C, logC, sign, tid, nt, T);
+            else tile_pass<4, LAYOUT, EPT>(s, P, Ns, C, logC, sign, tid, nt, T);
+        } else {
+            switch (R) {
+                case 2: tile_pass<2, LAYOUT, EPT>(s, P, Ns, C, logC, sign, tid, nt, T); break;
+                case 3: tile_pass<3, LAYOUT, EPT>(s, P, Ns, C, logC, sign, tid, nt, T); break;
+                case 4: tile_pass<4, LAYOUT, EPT>(s, P, Ns, C, logC, sign, tid, nt, T); break;
+                case 5: tile_pass<5, LAYOUT, EPT>(s, P, Ns, C, logC, sign, tid, nt, T); break;
+                case 8: tile_pass<8, LAYOUT, EPT>(s, P, Ns, C, logC, sign, tid, nt, T); break;
+                default: break;
+            }
         }
         Ns *= R;
-        __syncthreads();
-        cplx* t = a; a = b; b = t;
     }
-    return a;
 }
+
+// threads for a tile of `elems` complex numbers (multiple of 32, >= 32)
+static inline int fft_tile_threads(int n, int C, int ept) {
+    int64_t t = (int64_t)((n + ept - 1) / ept) * C;
+    t = (t + 31) / 32 * 32;
+    if (t < 32) t = 32;
+    return (int)t;
+}
+static inline size_t fft_tile_smem(int64_t elems) { return sizeof(cplx) * (size_t)(PADI(elems) + 1); }
