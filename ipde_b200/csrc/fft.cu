@@ -115,10 +115,15 @@ static inline int rows_per_tile(int n, int64_t batch) {
 static inline int tile_ept(int64_t elems) { return elems > 4096 ? 16 : 8; }
 
 // instantiate-and-launch over (elements per thread, radix class)
-#define FFT_TILE_LAUNCH_ONE(K, E_, C_, g, t, smem, st, ...)            \
-    do {                                                              \
-        rc = set_smem(K<E_, C_>, smem);                               \
-        if (!rc) K<E_, C_><<<g, t, smem, st>>>(__VA_ARGS__);          \
+#define FFT_TILE_LAUNCH_ONE(K, E_, C_, g, t, smem, st, ...)                          \
+    do {                                                                            \
+        if ((t) <= 256) {                                                           \
+            rc = set_smem(K<E_, C_, 256>, smem);                                    \
+            if (!rc) K<E_, C_, 256><<<g, t, smem, st>>>(__VA_ARGS__);               \
+        } else {                                                                    \
+            rc = set_smem(K<E_, C_, 512>, smem);                                    \
+            if (!rc) K<E_, C_, 512><<<g, t, smem, st>>>(__VA_ARGS__);               \
+        }                                                                           \
     } while (0)
 #define FFT_TILE_LAUNCH(K, ept, pow2, g, t, smem, st, ...)                                   \
     do {                                                                                    \
@@ -136,8 +141,8 @@ static int set_smem(K kernel, size_t bytes) {
 
 // ------------------------------------------------------------------------------------------
 // contiguous rows, C lines per CTA
-template <int EPT, int CLS>
-__global__ void __launch_bounds__(512)
+template <int EPT, int CLS, int NT>
+__global__ void __launch_bounds__(NT, (NT <= 256) ? 2 : 1)
 k_fft_rows(FftPlanDev P, const cplx* __restrict__ in, cplx* __restrict__ out, int64_t batch, int64_t in_pitch,
            int64_t out_pitch, int C, int sign, double scale) {
     extern __shared__ cplx smem[];
@@ -161,8 +166,8 @@ k_fft_rows(FftPlanDev P, const cplx* __restrict__ in, cplx* __restrict__ out, in
 }
 
 // strided lines, C adjacent lines per CTA (C a power of two), optional four-step twiddle
-template <int EPT, int CLS>
-__global__ void __launch_bounds__(512)
+template <int EPT, int CLS, int NT>
+__global__ void __launch_bounds__(NT, (NT <= 256) ? 2 : 1)
 k_fft_cols(FftPlanDev P, const cplx* __restrict__ in, cplx* __restrict__ out, int64_t elem_stride, int64_t n_inner,
            int64_t outer_stride, int C, int logC, int sign, double scale, int tw_mode, const cplx* __restrict__ tw_big) {
     extern __shared__ cplx smem[];
@@ -330,8 +335,8 @@ int fft_cols(FftPlan* p, const cplx* in, cplx* out, int64_t elem_stride, int64_t
 
 // ------------------------------------------------------------------------------------------
 // real rows (C lines per CTA): packed complex FFT of length n + untangling, fused
-template <int EPT, int CLS>
-__global__ void __launch_bounds__(512)
+template <int EPT, int CLS, int NT>
+__global__ void __launch_bounds__(NT, (NT <= 256) ? 2 : 1)
 k_r2c_rows(FftPlanDev P, const cplx* __restrict__ half_tw, const double* __restrict__ in, cplx* __restrict__ out,
            int64_t batch, int64_t in_pitch, int64_t out_pitch, int C) {
     extern __shared__ cplx smem[];
@@ -361,8 +366,8 @@ k_r2c_rows(FftPlanDev P, const cplx* __restrict__ half_tw, const double* __restr
     }
 }
 
-template <int EPT, int CLS>
-__global__ void __launch_bounds__(512)
+template <int EPT, int CLS, int NT>
+__global__ void __launch_bounds__(NT, (NT <= 256) ? 2 : 1)
 k_c2r_rows(FftPlanDev P, const cplx* __restrict__ half_tw, const cplx* __restrict__ in, double* __restrict__ out,
            int64_t batch, int64_t in_pitch, int64_t out_pitch, int C, double scale) {
     extern __shared__ cplx smem[];
@@ -480,8 +485,8 @@ int fft_c2r_rows(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t
 
 // ------------------------------------------------------------------------------------------
 // out = FFT(m * IFFT(in)) / n, fused in shared memory, C lines per CTA
-template <int EPT, int CLS>
-__global__ void __launch_bounds__(512)
+template <int EPT, int CLS, int NT>
+__global__ void __launch_bounds__(NT, (NT <= 256) ? 2 : 1)
 k_fft_mul_fft_rows(FftPlanDev P, const cplx* __restrict__ in, cplx* __restrict__ out, const double* __restrict__ m,
                    int64_t batch, int C) {
     extern __shared__ cplx smem[];

@@ -201,6 +201,15 @@ __device__ __forceinline__ void tile_pass(cplx* __restrict__ s, const FftPlanDev
     const int stride = (LAYOUT == 1) ? nt : T.G;
     const int first = (LAYOUT == 1) ? tid : T.lt;
     const bool live = (LAYOUT == 1) || (T.c >= 0);
+    // PADI(x + d) == PADI(x) + d*9/8 whenever d is a multiple of 8, and == PADI(x) + d when x is a multiple of 8
+    // and d < 8: the R slots of a butterfly are then equally spaced in the skewed buffer
+    const int ls = (LAYOUT == 1) ? (m << logC) : m;
+    const int ss = (LAYOUT == 1) ? (Ns << logC) : Ns;
+    const bool lin_l = (ls & 7) == 0;
+    const int step_l = ls + (ls >> 3);
+    const bool first8 = (LAYOUT == 0) && (Ns == 1) && (R == 8) && ((n & 7) == 0);
+    const bool lin_s = ((ss & 7) == 0) || first8;
+    const int step_s = first8 ? 1 : ss + (ss >> 3);
     cplx v[IPT][R];
 #pragma unroll
     for (int q = 0; q < IPT; ++q) {
@@ -208,8 +217,14 @@ __device__ __forceinline__ void tile_pass(cplx* __restrict__ s, const FftPlanDev
         if (live && it < items) {
             const int c = (LAYOUT == 1) ? (it & (C - 1)) : T.c;
             const int j = (LAYOUT == 1) ? (it >> logC) : it;
+            if (lin_l) {
+                const int a = tile_slot<LAYOUT>(j, c, n, logC);
 #pragma unroll
-            for (int t = 0; t < R; ++t) v[q][t] = s[tile_slot<LAYOUT>(j + t * m, c, n, logC)];
+                for (int t = 0; t < R; ++t) v[q][t] = s[a + t * step_l];
+            } else {
+#pragma unroll
+                for (int t = 0; t < R; ++t) v[q][t] = s[tile_slot<LAYOUT>(j + t * m, c, n, logC)];
+            }
         }
     }
     __syncthreads();
@@ -231,8 +246,14 @@ __device__ __forceinline__ void tile_pass(cplx* __restrict__ s, const FftPlanDev
             }
             dft_small<R>(v[q], sign, P);
             const int j0 = (j - k) * R + k;
+            if (lin_s) {
+                const int a = tile_slot<LAYOUT>(j0, c, n, logC);
 #pragma unroll
-            for (int t = 0; t < R; ++t) s[tile_slot<LAYOUT>(j0 + t * Ns, c, n, logC)] = v[q][t];
+                for (int t = 0; t < R; ++t) s[a + t * step_s] = v[q][t];
+            } else {
+#pragma unroll
+                for (int t = 0; t < R; ++t) s[tile_slot<LAYOUT>(j0 + t * Ns, c, n, logC)] = v[q][t];
+            }
         }
     }
     __syncthreads();
