@@ -54,7 +54,9 @@ def build_problem(ng, M=16):
     from ipde_b200.embedded_function import EmbeddedFunction
     from ipde_b200.slepian import SlepianMollifier
     h = 2.4/ng
-    nb = nice_size(2*np.pi*0.9/h)          # min speed of the a=0.1 star is 0.9 -> bh ~= h
+    # boundary spacing matched to the grid spacing (min speed of the a=0.1 star is 0.9: bh = h at nb = 2.36 ng);
+    # nb = 2 ng (bh = 1.18 h) keeps every FFT length of the path a power of two
+    nb = 2*ng if (ng & (ng - 1)) == 0 else nice_size(2*np.pi*0.9/h)
     bdy = GSB(c=star(nb, a=0.1, f=5))
     bh = bdy.dt*bdy.speed.min()
     grid = Grid([-1.2, 1.2], ng, [-1.2, 1.2], ng)

@@ -86,6 +86,11 @@ int ipde_nufft2_plan_destroy(void* plan);
 int ipde_nufft2_apply(void* plan, const double* spec, int cn1, int cn2, int dx, int dy, const double* x,
                       const double* y, int64_t npts, double* out, void* stream);
 
+/* u, u_x, u_y at the targets from one oversampled transform (the derivatives by differentiating the kernel):
+ * the three interpolations of ScalarSolver.__call__, ipde/solvers/multi_boundary/scalar.py:80-88 */
+int ipde_nufft2_apply3(void* plan, const double* spec, int cn1, int cn2, const double* x, const double* y,
+                       int64_t npts, double* out_v, double* out_dx, double* out_dy, void* stream);
+
 /* ---- radial block -> points: ebdy.interpolate_radial_to_points, ipde/embedded_boundary.py:419-443 */
 int ipde_nufft1_plan_create(int n, int fn, int w, double beta, const double* dec_host, void** plan);
 int ipde_nufft1_plan_destroy(void* plan);

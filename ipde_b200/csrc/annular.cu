@@ -111,20 +111,26 @@ __global__ void k_ann_stage3(const cplx* __restrict__ uh, const cplx* __restrict
     out[(int64_t)(M - 1) * n + i] = b;
 }
 
-// per-mode dense M x M mat-vec on mode-minor vectors
+// per-mode dense M x M mat-vec on mode-minor vectors; thread (mode i, output row j = blockIdx.y)
 __global__ void k_ann_precond(const cplx* __restrict__ x, cplx* __restrict__ out, int n, int M, const double* __restrict__ kinv) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    cplx v[ANN_MAX_M];
-    for (int r = 0; r < M; ++r) v[r] = x[(int64_t)r * n + i];
-    for (int j = 0; j < M; ++j) {
-        cplx acc = make_double2(0.0, 0.0);
-        for (int k = 0; k < M; ++k) {
-            const double a = kinv[((int64_t)j * M + k) * n + i];
-            acc.x += a * v[k].x; acc.y += a * v[k].y;
-        }
-        out[(int64_t)j * n + i] = acc;
+    const int j = blockIdx.y;
+    const double* a = kinv + (int64_t)j * M * n + i;
+    double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0;
+    int k = 0;
+    for (; k + 1 < M; k += 2) {
+        const double a0 = a[(int64_t)k * n], a1 = a[(int64_t)(k + 1) * n];
+        const cplx v0 = x[(int64_t)k * n + i], v1 = x[(int64_t)(k + 1) * n + i];
+        ax = fma(a0, v0.x, ax); ay = fma(a0, v0.y, ay);
+        bx = fma(a1, v1.x, bx); by = fma(a1, v1.y, by);
     }
+    if (k < M) {
+        const double a0 = a[(int64_t)k * n];
+        const cplx v0 = x[(int64_t)k * n + i];
+        ax = fma(a0, v0.x, ax); ay = fma(a0, v0.y, ay);
+    }
+    out[(int64_t)j * n + i] = make_double2(ax + bx, ay + by);
 }
 
 // rhs rows: [sign * R02 f ; ig ; og] as complex (ready for the theta-FFT)
@@ -172,7 +178,7 @@ struct AnnularScalarOp : public LinearOperator {
     }
     int precond(const cplx* in, cplx* out, cudaStream_t st) override {
         const int threads = 128, blocks = (p->n + threads - 1) / threads;
-        k_ann_precond<<<blocks, threads, 0, st>>>(in, out, p->n, p->M, p->kinv);
+        k_ann_precond<<<dim3(blocks, p->M), threads, 0, st>>>(in, out, p->n, p->M, p->kinv);
         KERNEL_CHECK();
         return IPDE_OK;
     }

@@ -91,11 +91,7 @@ int ipde_grid_solve_scalar(void* plan, int kind, double k, double* fc, const dou
         rc = grid_demean(g, fc, bumpy, ST(stream));
         if (rc) return rc;
     }
-    rc = grid_fft2_forward(g, fc, MP(uch), ST(stream));
-    if (rc) return rc;
-    rc = grid_scalar_multiply(g, MP(uch), kind, k, ST(stream));
-    if (rc) return rc;
-    return grid_fft2_inverse(g, CP(uch), MP(spec_work), uc, ST(stream));
+    return grid_solve_scalar_fused(g, kind, k, fc, MP(uch), MP(spec_work), uc, ST(stream));
 }
 int ipde_grid_solve_stokes(void* plan, double* fuc, double* fvc, const double* bumpy, double* uh, double* vh, double* ph,
                            double* spec_work, double* uc, double* vc, double* pc, void* stream) {
@@ -137,6 +133,10 @@ int ipde_nufft2_plan_create(int nx, int ny, double xh, double yh, int fx, int fy
     return rc;
 }
 int ipde_nufft2_plan_destroy(void* plan) { nufft2_plan_destroy((Nufft2Plan*)plan); return IPDE_OK; }
+int ipde_nufft2_apply3(void* plan, const double* spec, int cn1, int cn2, const double* x, const double* y, int64_t npts,
+                       double* out_v, double* out_dx, double* out_dy, void* stream) {
+    return nufft2_apply3((Nufft2Plan*)plan, CP(spec), cn1, cn2, x, y, npts, out_v, out_dx, out_dy, ST(stream));
+}
 int ipde_nufft2_apply(void* plan, const double* spec, int cn1, int cn2, int dx, int dy, const double* x, const double* y,
                       int64_t npts, double* out, void* stream) {
     return nufft2_apply((Nufft2Plan*)plan, CP(spec), cn1, cn2, dx, dy, x, y, npts, out, ST(stream));

@@ -314,24 +314,30 @@ int ewald_apply(EwaldPlan* p, const double* q, double* grid_out, double* point_o
                                                                    ck * wnorm, p->px, p->py, p->Sw, p->Lc, want_grid ? 1 : 0);
         KERNEL_CHECK();
     }
-    int rc = grid_fft2_forward(p->fft, p->Sw, p->spec, st);
+    GridPlan* G = p->fft;
+    const double c2r_scale = 1.0 / ((double)G->nx * (double)G->ny) * 2.0;
+    int rc = fft_r2c_rows(G->row, p->Sw, p->spec, G->nx, G->ny, G->pitch, st);
     if (rc) return rc;
-    const int64_t nspec = (int64_t)p->px * (p->py / 2 + 1);
-    const int mb = (int)std::min<int64_t>(cdiv(nspec, 256), (int64_t)ipde_num_sms() * 8);
+    ColMult MU, MH;
+    MU.kind = 3; MU.k2c = 0.0; MU.table = p->multU; MU.fmul = 1;
+    MH = MU; MH.table = p->multH;
+    // first field: forward columns, symbol, inverse columns in one pass (the plain 2-D spectrum is kept in
+    // p->spec when a second field follows); second field: symbol + inverse columns from that copy
+    rc = grid_cols_symbol(G, p->spec, p->specw, (want_grid && want_pts) ? p->spec : nullptr, 1, want_grid ? MU : MH, st);
+    if (rc) return rc;
+    rc = fft_c2r_rows(G->row, p->specw, p->R, G->nx, G->pitch, G->ny, c2r_scale, st);
+    if (rc) return rc;
     if (want_grid) {
-        k_ewald_apply_mult<<<mb, 256, 0, st>>>(p->spec, p->multU, p->specw, nspec);
-        KERNEL_CHECK();
-        rc = grid_fft2_inverse(p->fft, p->specw, p->specw, p->R, st);
-        if (rc) return rc;
         const int gb = (int)std::min<int64_t>(cdiv(p->n_og, 256), (int64_t)ipde_num_sms() * 8);
         k_ewald_grid_out<<<gb, 256, 0, st>>>(p->R, p->Lc, p->og_lin, p->og_loc, p->og_out, p->n_og, grid_out);
         KERNEL_CHECK();
     }
     if (want_pts) {
-        k_ewald_apply_mult<<<mb, 256, 0, st>>>(p->spec, p->multH, p->specw, nspec);
-        KERNEL_CHECK();
-        rc = grid_fft2_inverse(p->fft, p->specw, p->specw, p->R, st);
-        if (rc) return rc;
+        if (want_grid) {
+            rc = grid_cols_symbol_inverse(G, p->spec, p->specw, MH, st);
+            if (!rc) rc = fft_c2r_rows(G->row, p->specw, p->R, G->nx, G->pitch, G->ny, c2r_scale, st);
+            if (rc) return rc;
+        }
         const int pb = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(p->n_pt * 32, 256), (int64_t)ipde_num_sms() * 16));
         k_ewald_points<<<pb, 256, 0, st>>>(p->R, p->ptx, p->pty, p->n_pt, p->tile_map, p->ntx, p->nty, p->tile_ptr,
                                            p->tile_src, p->sx, p->sy, q, T, p->x0, p->y0, p->h, p->rc2, two_xi2,

@@ -97,6 +97,162 @@ int grid_fft2_inverse(GridPlan* g, const cplx* spec_in, cplx* spec_work, double*
 }
 
 // ------------------------------------------------------------------------------------------
+// Fused spectral pass over the columns of a half spectrum:
+//     load tile -> [forward FFT] -> multiply by a real symbol -> inverse FFT -> store
+// with an optional copy of the spectrum (before or after the multiplication) to a second array.  It is the
+// whole column direction of a grid whose columns fit one tile, and the inner ("B") pass of the four-step
+// split otherwise; either way the multiplier costs no pass over memory of its own.
+//   symbol kinds: IPDE_KIND_POISSON / IPDE_KIND_MODHELM analytic (reference multi_boundary/poisson.py:34-38,
+//   modified_helmholtz.py:43-46), 3: table with the layout of the spectrum (free-space evaluator, ewald.cu)
+template <int EPT, int CLS, int NT>
+__global__ void __launch_bounds__(NT, (NT <= 256) ? 2 : 1)
+k_cols_mult(FftPlanDev P, const cplx* in, cplx* out, cplx* copy, int64_t elem_stride,
+            int64_t n_inner, int64_t outer_stride, int C, int logC, int do_fwd, int copy_mode, ColMult M) {
+    extern __shared__ cplx smem[];
+    const int n = P.n, tid = threadIdx.x, nt = blockDim.x;
+    const int64_t tiles = (n_inner + C - 1) >> logC;
+    const int o = (int)(blockIdx.x / tiles);
+    const int64_t c0 = (blockIdx.x - (int64_t)o * tiles) << logC;
+    const int cw = (int)min((int64_t)C, n_inner - c0);
+    const int64_t base = (int64_t)o * outer_stride + c0;
+    const int total = n << logC;
+    for (int i = tid; i < total; i += nt) {
+        const int c = i & (C - 1), e = i >> logC;
+        smem[PADI(i)] = (c < cw) ? in[base + (int64_t)e * elem_stride + c] : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    if (do_fwd) tile_fft<1, EPT, CLS>(smem, P, C, logC, -1, tid, nt);
+    for (int i = tid; i < total; i += nt) {
+        const int c = i & (C - 1), e = i >> logC;
+        if (c < cw) {
+            const int64_t addr = base + (int64_t)e * elem_stride + c;
+            cplx v = smem[PADI(i)];
+            if (copy_mode == 1) copy[addr] = v;
+            double m;
+            if (M.kind == 3) {
+                m = M.table[addr];
+            } else {
+                const int fi = o + M.fmul * e;                                   // frequency index along x
+                const int si = (fi < (M.nx + 1) / 2) ? fi : fi - M.nx;
+                const int jy = (int)c0 + c;
+                const double kx = TWO_PI * (double)si / ((double)M.nx * M.xh);
+                const double ky = TWO_PI * (double)jy / ((double)M.ny * M.yh);
+                if (M.kind == IPDE_KIND_POISSON) m = (fi == 0 && jy == 0) ? 0.0 : -1.0 / (kx * kx + ky * ky);
+                else m = 1.0 / (M.k2c + kx * kx + ky * ky);
+            }
+            v = cscale(v, m);
+            if (copy_mode == 2) copy[addr] = v;
+            smem[PADI(i)] = v;
+        }
+    }
+    __syncthreads();
+    tile_fft<1, EPT, CLS>(smem, P, C, logC, +1, tid, nt);
+    for (int i = tid; i < total; i += nt) {
+        const int c = i & (C - 1), e = i >> logC;
+        if (c < cw) out[base + (int64_t)e * elem_stride + c] = smem[PADI(i)];
+    }
+}
+
+template <int EPT, int CLS, int NT>
+static int launch_cols_mult_one(FftPlan* p, unsigned g, int t, size_t smem, cudaStream_t st, const cplx* in, cplx* out,
+                                cplx* copy, int64_t elem_stride, int64_t n_inner, int64_t outer_stride, int C, int logC,
+                                int do_fwd, int copy_mode, const ColMult& M) {
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(k_cols_mult<EPT, CLS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_cols_mult<EPT, CLS, NT><<<g, t, smem, st>>>(p->d, in, out, copy, elem_stride, n_inner, outer_stride, C, logC, do_fwd,
+                                                  copy_mode, M);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+
+// columns of length p->d.n (must fit a tile with >= 4 adjacent columns and be tile-engine friendly)
+static int cols_mult(FftPlan* p, const cplx* in, cplx* out, cplx* copy, int64_t elem_stride, int64_t n_inner, int64_t n_outer,
+                     int64_t outer_stride, int do_fwd, int copy_mode, const ColMult& M, cudaStream_t st) {
+    const int n = p->d.n;
+    int C = 1;
+    while ((int64_t)C * 2 * n <= IPDE_FFT_SMEM_MAX && C < 16) C *= 2;
+    while (C > 1 && C / 2 >= n_inner) C /= 2;
+    int logC = 0;
+    while ((1 << logC) < C) ++logC;
+    const int64_t E = (int64_t)n * C;
+    const int ept = E > 4096 ? 16 : 8;
+    const size_t smem = fft_tile_smem(E);
+    const unsigned g = (unsigned)(cdiv(n_inner, C) * n_outer);
+    const int t = fft_tile_threads(n, C, ept);
+#define CM(E_, C_, N_) return launch_cols_mult_one<E_, C_, N_>(p, g, t, smem, st, in, out, copy, elem_stride, n_inner, \
+                                                              outer_stride, C, logC, do_fwd, copy_mode, M)
+    if (ept == 8) {
+        if (p->pow2) { if (t <= 256) CM(8, 0, 256); else CM(8, 0, 512); }
+        else { if (t <= 256) CM(8, 1, 256); else CM(8, 1, 512); }
+    } else {
+        if (p->pow2) { if (t <= 256) CM(16, 0, 256); else CM(16, 0, 512); }
+        else { if (t <= 256) CM(16, 1, 256); else CM(16, 1, 512); }
+    }
+#undef CM
+    return IPDE_OK;
+}
+
+static inline bool grid_fused_ok(const GridPlan* g) {
+    const FftPlan* inner = (g->n2 == 1) ? g->colA : g->colB;
+    return inner && inner->fast && (int64_t)inner->d.n * 4 <= IPDE_FFT_SMEM_MAX;
+}
+
+// spec_in (row transforms done, columns not) -> [column FFT, symbol, inverse column FFT] -> spec_out, ready for
+// the inverse row transforms.  spec_copy (may be null) receives the 2-D spectrum, before (copy_mode 1) or after
+// (2) the multiplication.  spec_in is overwritten when the column transform is split.
+int grid_cols_symbol(GridPlan* g, cplx* spec_in, cplx* spec_out, cplx* spec_copy, int copy_mode, const ColMult& M0,
+                     cudaStream_t st) {
+    const int64_t P = g->pitch;
+    ColMult M = M0;
+    M.nx = g->nx; M.ny = g->ny; M.xh = g->xh; M.yh = g->yh;
+    if (!spec_copy) copy_mode = 0;
+    if (g->n2 == 1) {
+        M.fmul = 1;
+        return cols_mult(g->colA, spec_in, spec_out, spec_copy, P, P, 1, 0, 1, copy_mode, M, st);
+    }
+    M.fmul = g->n1;
+    int rc = fft_cols(g->colA, spec_in, spec_in, (int64_t)g->n2 * P, P, g->n2, P, -1, 1.0, 1, g->tw_big, g->nx, st);
+    if (rc) return rc;
+    rc = cols_mult(g->colB, spec_in, spec_out, spec_copy, P, P, g->n1, (int64_t)g->n2 * P, 1, copy_mode, M, st);
+    if (rc) return rc;
+    return fft_cols(g->colA, spec_out, spec_out, (int64_t)g->n2 * P, P, g->n2, P, +1, 1.0, 2, g->tw_big, g->nx, st);
+}
+
+// 2-D spectrum (as left by grid_cols_symbol's copy) -> symbol -> inverse column FFT -> spec_out
+int grid_cols_symbol_inverse(GridPlan* g, const cplx* spec2d, cplx* spec_out, const ColMult& M0, cudaStream_t st) {
+    const int64_t P = g->pitch;
+    ColMult M = M0;
+    M.nx = g->nx; M.ny = g->ny; M.xh = g->xh; M.yh = g->yh;
+    if (g->n2 == 1) {
+        M.fmul = 1;
+        return cols_mult(g->colA, spec2d, spec_out, nullptr, P, P, 1, 0, 0, 0, M, st);
+    }
+    M.fmul = g->n1;
+    int rc = cols_mult(g->colB, spec2d, spec_out, nullptr, P, P, g->n1, (int64_t)g->n2 * P, 0, 0, M, st);
+    if (rc) return rc;
+    return fft_cols(g->colA, spec_out, spec_out, (int64_t)g->n2 * P, P, g->n2, P, +1, 1.0, 2, g->tw_big, g->nx, st);
+}
+
+// the whole scalar grid solve: fc (real) -> uch (2-D spectrum of the solution) and uc (real)
+int grid_solve_scalar_fused(GridPlan* g, int kind, double k, const double* fc, cplx* uch, cplx* spec_work, double* uc,
+                            cudaStream_t st) {
+    int rc = fft_r2c_rows(g->row, fc, uch, g->nx, g->ny, g->pitch, st);
+    if (rc) return rc;
+    if (grid_fused_ok(g)) {
+        ColMult M;
+        M.kind = kind; M.k2c = k * k; M.table = nullptr; M.fmul = 1;
+        rc = grid_cols_symbol(g, uch, spec_work, uch, 2, M, st);
+        if (rc) return rc;
+    } else {
+        rc = grid_cols_forward(g, uch, uch, st);
+        if (!rc) rc = grid_scalar_multiply(g, uch, kind, k, st);
+        if (!rc) rc = grid_cols_inverse(g, uch, spec_work, st);
+        if (rc) return rc;
+    }
+    return fft_c2r_rows(g->row, spec_work, uc, g->nx, g->pitch, g->ny, 1.0 / ((double)g->nx * (double)g->ny) * 2.0, st);
+}
+
+// ------------------------------------------------------------------------------------------
 // compact physical vector -> zero-filled grid, times the cutoff
 __global__ void k_scatter_cutoff(double* __restrict__ fc, const double* __restrict__ f, const int64_t* __restrict__ lin,
                                  const double* __restrict__ step, int64_t n) {

@@ -37,3 +37,18 @@ int grid_gather(const double* uc, const int64_t* lin, int64_t n, double* out, cu
 int grid_index_add(double* out, const int64_t* pos, const double* v, int64_t n, cudaStream_t st);
 int grid_index_set(double* out, const int64_t* pos, const double* v, int64_t n, cudaStream_t st);
 int grid_stokes_multiply(GridPlan* g, cplx* uh, cplx* vh, cplx* ph, cudaStream_t st);
+
+// real symbol applied between the forward and inverse column transforms (grid.cu: k_cols_mult)
+struct ColMult {
+    int kind;             // IPDE_KIND_POISSON, IPDE_KIND_MODHELM (analytic) or 3 (table)
+    double k2c;           // k^2 of the modified Helmholtz operator
+    int nx, ny;
+    double xh, yh;
+    int fmul;             // frequency index along x of element e of outer line o: o + fmul*e
+    const double* table;  // kind 3: one real per spectrum entry, same layout as the spectrum
+};
+int grid_cols_symbol(GridPlan* g, cplx* spec_in, cplx* spec_out, cplx* spec_copy, int copy_mode, const ColMult& M,
+                     cudaStream_t st);
+int grid_cols_symbol_inverse(GridPlan* g, const cplx* spec2d, cplx* spec_out, const ColMult& M, cudaStream_t st);
+int grid_solve_scalar_fused(GridPlan* g, int kind, double k, const double* fc, cplx* uch, cplx* spec_work, double* uc,
+                            cudaStream_t st);

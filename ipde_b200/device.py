@@ -232,6 +232,17 @@ class Nufft2(object):
         return out
 
 
+def _nufft2_apply3(self, spec):
+    """(u, u_x, u_y) at the plan's points from one fine-grid transform"""
+    v, dx, dy = empty((self.npts,)), empty((self.npts,)), empty((self.npts,))
+    lib().ipde_nufft2_apply3(self.h, ptr(spec), self.grid.n1, self.grid.n2, ptr(self.x), ptr(self.y), self.npts,
+                             ptr(v), ptr(dx), ptr(dy), stream())
+    return v, dx, dy
+
+
+Nufft2.apply3 = _nufft2_apply3
+
+
 class RadialInterpolator(object):
     """(M, n) radial block -> values at points (theta, t): embedded_boundary.py:419-434 on the device."""
     def __init__(self, M, n, eps=1e-14, sigma=2.0):
@@ -420,15 +431,18 @@ class FreeSpaceEvaluator(object):
         xs, ys = [sx], [sy]
         if grid_nodes is not None:
             gix, giy = np.asarray(grid_nodes[0], dtype=np.int64), np.asarray(grid_nodes[1], dtype=np.int64)
-            xs.append(grid_x0 + h*np.array([gix.min(), gix.max()], dtype=float))
-            ys.append(grid_y0 + h*np.array([giy.min(), giy.max()], dtype=float))
+            xs.append(grid_x0 + h*gix)
+            ys.append(grid_y0 + h*giy)
         if points is not None:
             ptx = np.ascontiguousarray(points[0], dtype=float); pty = np.ascontiguousarray(points[1], dtype=float)
             xs.append(ptx); ys.append(pty)
-        ax, ay = np.concatenate(xs), np.concatenate(ys)
         # largest source-target distance, bounded by the bounding-box diagonal and by twice the enclosing radius
-        cx, cy = 0.5*(ax.min() + ax.max()), 0.5*(ay.min() + ay.max())
-        D = min(np.hypot(ax.max() - ax.min(), ay.max() - ay.min()), 2.0*np.sqrt(((ax - cx)**2 + (ay - cy)**2).max()))
+        lox, hix = min(a.min() for a in xs), max(a.max() for a in xs)
+        loy, hiy = min(a.min() for a in ys), max(a.max() for a in ys)
+        cx, cy = 0.5*(lox + hix), 0.5*(loy + hiy)
+        r2max = max(((a - cx)**2 + (b - cy)**2).max() for a, b in zip(xs, ys))
+        D = min(np.hypot(hix - lox, hiy - loy), 2.0*np.sqrt(r2max))
+        ax, ay = np.array([lox, hix]), np.array([loy, hiy])
         self.L = D + 2.0*np.sqrt(2.0)*P.m*h + 2.0*h
         nxt = L_.ipde_fft_next_size
         self.x0, self.px, self.ilo_x = E.choose_box(ax.min(), ax.max(), h, P.m, grid_x0, self.L, nxt)

@@ -219,5 +219,11 @@ def choose_box(lo, hi, h, m, x_origin, span, next_size):
     i_lo = int(np.floor((lo - x_origin)/h)) - m - 1
     i_hi = int(np.ceil((hi - x_origin)/h)) + m + 1
     ext = i_hi - i_lo + 1
-    p = next_size(ext + int(np.ceil(span/h)) + 1)
+    need = ext + int(np.ceil(span/h)) + 1
+    p = next_size(need)
+    # the power-of-two FFT kernels move ~2.5x the bytes per second of the mixed-radix ones: prefer 2^a when the
+    # extra area does not eat that up
+    p2 = 1 << int(np.ceil(np.log2(need)))
+    if p2 != p and float(p2)**2 < 2.5*float(p)**2:
+        p = p2
     return x_origin + i_lo*h, p, i_lo

@@ -124,7 +124,7 @@ class ScalarSolver(object):
         # interface values and gradient of the grid solution
         if self.interpolation_order == np.inf:
             nu = D.nufft
-            bvs, bxs, bys = nu(D.uch, 0, 0), nu(D.uch, 1, 0), nu(D.uch, 0, 1)
+            bvs, bxs, bys = nu.apply3(D.uch)
         else:
             ucx, ucy = D.grid.new_real(), D.grid.new_real()
             L.ipde_grid_fd4(D.grid.h, ptr(D.uc), ptr(ucx), ptr(ucy), st)

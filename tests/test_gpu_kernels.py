@@ -340,3 +340,19 @@ def test_qfs_device_build_matches_host_build(D, kind, interior):
     assert rel(K.dot(sd), K.dot(sh)) < 1e-12
     ub = np.exp(np.sin(t))
     assert rel(K.dot(qd.u2s(ub)), K.dot(qh.u2s(ub))) < 1e-11
+
+
+def test_nufft2_apply3_matches_separate_transforms(D):
+    """value + gradient from one fine-grid transform (kernel differentiation) vs three spectral transforms"""
+    n = 96
+    rng = np.random.default_rng(5)
+    g = D.GridPlan(n, n, 2.4/n, 2.4/n)
+    f = rng.standard_normal((n, n))
+    spec = g.fft2(D.to_dev(f))
+    x, y = rng.uniform(0, 2*np.pi, 300), rng.uniform(0, 2*np.pi, 300)
+    nu = D.Nufft2(g, x, y)
+    v, dx, dy = nu.apply3(spec)
+    v0, dx0, dy0 = nu(spec, 0, 0), nu(spec, 1, 0), nu(spec, 0, 1)
+    assert rel(v.cpu().numpy(), v0.cpu().numpy()) < 1e-13
+    assert rel(dx.cpu().numpy(), dx0.cpu().numpy()) < 5e-13
+    assert rel(dy.cpu().numpy(), dy0.cpu().numpy()) < 5e-13
