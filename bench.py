@@ -162,14 +162,42 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def ncu_traffic(kernel):
+    """dram read+write bytes per launch of `kernel` from the committed ncu --set full summary (profiles/), or None"""
+    path = os.path.join(ROOT, 'profiles', 'r01_ncu_%s.json' % kernel)
+    try:
+        recs = json.load(open(path))
+    except Exception:
+        return None
+    tot = []
+    for r in recs:
+        try:
+            def val(key):
+                v, u = r[key].split()[:2]
+                return float(v)*{'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[u]
+            tot.append(val('dram__bytes_read.sum') + val('dram__bytes_write.sum'))
+        except Exception:
+            pass
+    return float(np.mean(tot)) if tot else None
+
+
+def parse_profile(text):
+    recs = []
+    for line in text.strip().splitlines():
+        parts = line.split()
+        if len(parts) == 4:
+            recs.append({'kernel': parts[0], 'launches': int(parts[1]), 'ms': float(parts[2]), 'bytes': float(parts[3])})
+    return recs
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ipde_b200')
-    ap.add_argument('--n', type=int, default=1024, help='background grid points per side')
-    ap.add_argument('--cpu-sample-n', type=int, default=192)
+    ap.add_argument('--n', type=int, default=2048, help='background grid points per side')
+    ap.add_argument('--cpu-sample-n', type=int, default=256)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
 
@@ -180,6 +208,7 @@ def main():
         run_reference(args, rank, world)
         return
 
+    import ctypes
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -188,26 +217,27 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     from ipde_b200._lib import lib
-    from ipde_b200.device import to_dev, StageTimer
+    from ipde_b200.device import to_dev, StageTimer, stream
     from ipde_b200.embedded_function import EmbeddedFunction
     from ipde_b200.solvers.multi_boundary.modified_helmholtz import ModifiedHelmholtzSolver
 
     t_setup = time.perf_counter()
     ebdyc, f, nb = build_problem(args.n)
-    solver = ModifiedHelmholtzSolver(ebdyc, HELMHOLTZ_K, solver_type='spectral')
+    solver = ModifiedHelmholtzSolver(ebdyc, HELMHOLTZ_K, solver_type='spectral', grid_backend='ewald')
     t_setup = time.perf_counter() - t_setup
     gmres = dict(tol=1e-12, restart=50, maxiter=10)
     # every rank its own forcing (weak scaling): same geometry, scaled right-hand side
     f_host = np.asarray(f)*(1.0 + 0.1*rank)
     f_dev = to_dev(f_host)
     npts = args.n*args.n
+    warmup = max(args.warmup, 3)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         solver.solve_device(f_dev, **gmres)
     barrier()
 
@@ -227,9 +257,8 @@ def main():
     launches = lib().ipde_launch_count() - launches0
     stages = timer.results()
     solver.timer = None
-    clocks = sampler.stop()
 
-    # ---- end to end through the public API with host arrays
+    # ---- end to end through the public API: host EmbeddedFunction in, host EmbeddedFunction out
     barrier()
     f_ef = EmbeddedFunction(ebdyc, linear_data=f_host)
     solver(f_ef, **gmres)
@@ -240,6 +269,16 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
+    clocks = sampler.stop()
+
+    # ---- per-kernel CUDA-event times of one more step (library profiler: an event after every launch)
+    prof_steps = 3
+    lib().ipde_profile_start(stream())
+    for _ in range(prof_steps):
+        solver.solve_device(f_dev, **gmres)
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib().ipde_profile_stop(buf, len(buf))
+    prof = parse_profile(buf.value.decode())
 
     times = torch.tensor([ms_total, e2e_s*1e3], dtype=torch.float64, device='cuda')
     if world > 1:
@@ -252,38 +291,49 @@ def main():
     if rank == 0:
         peak, peak_kind = measured_peak_gbs()
         per_step = {k: v/args.steps for k, v in stages.items()}
-        dominant = max(per_step, key=per_step.get)
-        # roofline of the periodic grid solve (the HBM-bound core named by the metric)
-        grid_ms = per_step.get('grid_solve', float('nan'))
-        alg_bytes = ALG_BYTES_PER_POINT_CORE*npts
-        achieved = alg_bytes/(grid_ms*1e-3)/1e9
-        roofline = {'bound': 'hbm', 'kernel': 'grid_solve stage (scatter+cutoff, r2c rows, column fft, multiplier, '
-                    'inverse column fft, c2r rows)', 'achieved': achieved, 'peak': peak, 'peak_source': peak_kind,
-                    'unit': 'GB/s', 'frac': achieved/peak, 'traffic': None,
-                    'algorithmic_bytes_per_launch': alg_bytes, 'ms_per_launch': grid_ms,
-                    'dominant_stage': dominant, 'stage_ms_per_step': per_step}
+        prof_ms = sum(r['ms'] for r in prof)
+        tagged = [r for r in prof if r['bytes'] > 0]
+        dom = max(tagged, key=lambda r: r['ms'])
+        achieved = dom['bytes']/(dom['ms']*1e-3)/1e9
+        roofline = {'bound': 'hbm', 'kernel': dom['kernel'], 'achieved': achieved, 'peak': peak,
+                    'peak_source': peak_kind, 'unit': 'GB/s', 'frac': achieved/peak, 'traffic': ncu_traffic(dom['kernel']),
+                    'algorithmic_bytes_per_launch': dom['bytes']/dom['launches'],
+                    'ms_per_launch': dom['ms']/dom['launches'], 'launches_per_step': dom['launches']/prof_steps,
+                    'share_of_step': dom['ms']/prof_ms,
+                    'how': 'CUDA event after every launch of libipde_b200 on the solve stream (ipde_profile_start/'
+                           'stop), %d profiled steps after the timed region' % prof_steps,
+                    'kernels_ms_per_step': {r['kernel']: r['ms']/prof_steps for r in prof[:12]},
+                    'kernels_gbs': {r['kernel']: r['bytes']/(r['ms']*1e-3)/1e9 for r in tagged[:10]},
+                    'stage_ms_per_step': per_step,
+                    'whole_step_algorithmic': {
+                        'bytes_per_point': ALG_BYTES_PER_POINT_CORE,
+                        'note': 'SURVEY 8(d) scalar core only; evaluator/NUFFT passes come on top (DESIGN.md)',
+                        'frac_of_peak': ALG_BYTES_PER_POINT_CORE*npts/(ms_per_step*1e-3)/1e9/peak}}
         line = {'metric': 'grid-point-solves/sec', 'value': value, 'unit': 'grid-point-solves/s', 'n_gpus': world,
-                'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
+                'steps': args.steps, 'warmup': warmup, 'ms_per_step': ms_per_step,
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
                 'data': 'synthetic',
-                'config': {'workload': 'interior_modified_helmholtz (configs[1]) %d^2 grid, 1 boundary nb=%d, M=16, '
-                           'k=2, spectral, gmres tol 1e-12' % (args.n, nb),
+                'config': {'workload': 'interior_modified_helmholtz (BASELINE configs[1]) %d^2 grid, 1 star boundary '
+                           'nb=%d, M=16, k=2, spectral interface interpolation, annular GMRES tol 1e-12, '
+                           'spectral-Ewald evaluation of the layer sums' % (args.n, nb),
                            'grid': [args.n, args.n], 'n_boundary': nb, 'dof': int(ebdyc.dof),
                            'gmres_iterations': solver.iteration_counts, 'setup_s': t_setup,
-                           'l2_note': 'working set per step (%.0f MB of grid arrays) exceeds the 126 MB L2' %
-                                      (npts*8*6/1e6) if npts*8*6 > 126e6 else
-                                      'grid arrays fit in L2 at this size; see DESIGN.md'},
+                           'l2': 'inputs larger than L2: every step streams ~%.1f GB of grid-sized arrays '
+                                 '(126 MB L2); no flush between steps' % (npts*8*40/1e9)
+                                 if npts*8*40 > 4*126e6 else 'working set comparable to L2 (126 MB) at this size'},
                 'clocks': clocks, 'gpu_launches': int(launches),
                 'e2e': {'value': e2e_value, 'unit': 'grid-point-solves/s',
                         'h2d_bytes_per_step': int(f_host.nbytes), 'd2h_bytes_per_step': int(np.asarray(ue).nbytes),
-                        'ms_per_step': e2e_ms/args.steps},
+                        'ms_per_step': e2e_ms/args.steps,
+                        'api': 'ModifiedHelmholtzSolver.__call__(EmbeddedFunction) -> EmbeddedFunction, pinned staging'},
                 'roofline': roofline}
         if not args.no_cpu_baseline and world == 1:
             rate, dt, nbs = cpu_solve_rate(args.cpu_sample_n, 1)
             line['cpu_baseline'] = {'value': rate, 'unit': 'grid-point-solves/s', 'cores': os.cpu_count(),
                                     'kind': 'port',
                                     'sample': 'one solve of the same problem at grid %d^2 (nb=%d) by the NumPy/SciPy '
-                                              'oracle port, %.1f s' % (args.cpu_sample_n, nbs, dt)}
+                                              'oracle port (direct NUDFT + all-pairs sums, as the reference\'s default '
+                                              'backend), %.1f s' % (args.cpu_sample_n, nbs, dt)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -32,6 +32,10 @@ const char* ipde_last_error(void);
 int ipde_version(void);
 int ipde_device_sm_count(void);
 int64_t ipde_launch_count(void);   /* kernels launched by this library since load */
+/* per-kernel CUDA-event timing of everything launched on `stream` between start and stop; stop writes lines
+ * "kernel_name launches total_ms algorithmic_bytes" (sorted by time) into the host buffer `out` */
+int ipde_profile_start(void* stream);
+int ipde_profile_stop(char* out, int64_t cap);
 
 /* ---- 1-D FFT (batched, contiguous lines).  Replaces numpy.fft.fft / ifft, ipde/utilities.py:5-12. */
 int ipde_fft_plan_create(int n, void** plan);
@@ -111,6 +115,38 @@ int ipde_annular_precond(void* plan, const double* in, double* out, void* stream
 int ipde_annular_solve(void* plan, const double* f, const double* ig, const double* og, double f_sign,
                        double tol, int restart, int maxiter, double* u_out, int* iters, double* relres,
                        void* stream);
+
+/* ---- annular Stokes solver: AnnularStokesSolver, ipde/annular/stokes.py:73-541 (mu = viscosity).  Vectors are
+ *      (3M-1, n) complex, rows [u_r | u_t | p], mode-minor, Nyquist column zero.  All setup arrays host. */
+int ipde_annular_stokes_plan_create(int n, int M, double mu, const double* D01, const double* D12, const double* R01,
+                                    const double* R12, const double* R02, const double* P10, const double* ibc,
+                                    const double* obc, const double* vi1, const double* ks, const double* psi0,
+                                    const double* psi1, const double* ipsi1, const double* ipsi2, const double* combo1,
+                                    const double* combo2, const double* m3, const double* kinv_mode_minor, void** plan);
+int ipde_annular_stokes_plan_destroy(void* plan);
+int ipde_annular_stokes_apply(void* plan, const double* in, double* out, void* stream);     /* _apply_optim_real :321-385 */
+int ipde_annular_stokes_precond(void* plan, const double* in, double* out, void* stream);   /* _preconditioner :200-210 */
+/* solve(RAG, fr, ft, irg, itg, org, otg, **gmres): :519-541; boundary data pointers may be NULL (zero) */
+int ipde_annular_stokes_solve(void* plan, const double* fr, const double* ft, const double* irg, const double* itg,
+                              const double* org, const double* otg, double tol, int restart, int maxiter, double* ur,
+                              double* ut, double* pr, int* iters, double* relres, void* stream);
+
+/* ---- Stokes (vector) helper glue, radial blocks (M, n), normals/tangents of the boundary curve (n) */
+/* inverse 0: (u, v) -> (r, t); 1: (r, t) -> (u, v).  ipde/embedded_boundary.py:521-530 */
+int ipde_uv_rt(const double* f0, const double* f1, const double* nx, const double* ny, const double* tx, const double* ty,
+               int M, int n, double* out0, double* out1, int inverse, void* stream);
+/* traction (x, y) of a radial (Ur, Ut, p) field on the curve picked by the evaluation row `est`; dUr = d/dt Ur;
+ * rsp = radial_speed (M, n).  VectorHelper._get_traction_rtp/_uvp, ipde/solvers/internals/vector.py:87-102 */
+int ipde_radial_traction(const double* Ur, const double* Ut, const double* dUr, const double* P, const double* D00,
+                         const double* est, const double* rsp, const double* nx, const double* ny, const double* tx,
+                         const double* ty, int M, int n, double* Tx, double* Ty, void* stream);
+/* tau (4n) = sign [rtx - btx | rty - bty | bu | bv], bt = stress . interface normal: vector.py:104-121 */
+int ipde_vector_jumps(const double* rtx, const double* rty, const double* txx, const double* txy, const double* tyy,
+                      const double* bu, const double* bv, const double* inx, const double* iny, int n, double sign,
+                      double* tau, void* stream);
+/* d/dt of `rows` real rows of length n (plan from ipde_fft_plan_create(n)); work_cplx: rows*n complex.
+ * EmbeddedBoundary._radial_grid_t_derivative, ipde/embedded_boundary.py:473-474 */
+int ipde_theta_derivative(void* fft_plan, const double* f, double* work_cplx, double* out, int rows, void* stream);
 
 /* ---- layer potentials from point sources: pybie2d *_Layer_Apply / pyfmmlib2d.SFMM,
  *      ipde/solvers/internals/poisson.py:34-35, modified_helmholtz.py:37, stokes.py:26-35 */

@@ -210,3 +210,139 @@ class AnnularPoissonSolver(AnnularModifiedHelmholtzSolver):
 
     def __init__(self, AAG, ia=1.0, ib=0.0, oa=1.0, ob=0.0):
         super().__init__(AAG, 0.0, ia=ia, ib=ib, oa=oa, ob=ob)
+
+
+class AnnularStokesSolver(object):
+    """
+    -mu Lap u + grad p = f, div u = 0 on the annulus, in (r, t) components, Dirichlet data at both radii
+    (reference ipde/annular/stokes.py:73-541).  Works on the Nyquist-dropped geometry
+    (ApproximateAnnularGeometry(..., drop_nyquist=True), the reference's annular.py).
+    `solve` accepts host or device arrays and returns the same kind.
+    """
+    def __init__(self, AAG, mu=1.0):
+        require_cuda()
+        self.AAG, self.mu = AAG, mu
+        self.M, self.ns, self.n = AAG.M, AAG.ns, AAG.n
+        if self.ns != self.n - 1:
+            raise Exception('the annular Stokes solver works on the Nyquist-dropped geometry')
+        self.u_shape = (self.M, self.n)
+        self._construct()
+        self._plan = None
+        self._plan_key = None
+        self.iterations_last_call = None
+
+    def _construct(self):
+        """per-mode (3M-1)^2 complex collocation matrices of the concentric-circle operator, inverted (:127-153)"""
+        AAG, CO, M, ns, mu = self.AAG, self.AAG.CO, self.M, self.ns, self.mu
+        ap0, ap1 = AAG.approx_psi0, AAG.approx_psi1
+        ai1, ai2 = AAG.approx_inv_psi1, AAG.approx_inv_psi2
+        ks = AAG.ks
+        D01, D12, R01, R12, R02 = CO.D01, CO.D12, CO.R01, CO.R12, CO.R02
+        A0 = ai2[:, None]*(D12 @ (ap1[:, None]*D01))
+        A1 = R12 @ (ai1[:, None]*R01)
+        K = np.zeros((ns, 3*M - 1, 3*M - 1), dtype=complex)
+        LL = A0[None] - (ks**2)[:, None, None]*A1[None]
+        diag = -LL + (ai2**2)[:, None]*R02
+        cross = (2*ai2**2)[:, None]*R02
+        ik = 1j*ks[:, None, None]
+        K[:, 0:M - 2, 0:M] = mu*diag
+        K[:, 0:M - 2, M:2*M] = mu*ik*cross[None]
+        K[:, 0:M - 2, 2*M:] = D12
+        K[:, M - 2, 0:M] = CO.ibc_dirichlet[0]
+        K[:, M - 1, 0:M] = CO.obc_dirichlet[0]
+        K[:, M:2*M - 2, 0:M] = -mu*ik*cross[None]
+        K[:, M:2*M - 2, M:2*M] = mu*diag
+        K[:, M:2*M - 2, 2*M:] = ik*(ai2[:, None]*R12)[None]
+        K[:, 2*M - 2, M:2*M] = CO.ibc_dirichlet[0]
+        K[:, 2*M - 1, M:2*M] = CO.obc_dirichlet[0]
+        K[:, 2*M:, 0:M] = ai1[:, None]*(D01*ap0[None, :])
+        K[:, 2*M:, M:2*M] = ik*(ai1[:, None]*R01)[None]
+        K[0, 2*M:, 2*M:] += CO.VI1[0]
+        self.Stacked_KINVS = np.linalg.inv(K)
+
+    def _get_plan(self, RAG):
+        key = id(RAG)
+        if self._plan is not None and self._plan_key == key:
+            return self._plan
+        if self._plan is not None:
+            lib().ipde_annular_stokes_plan_destroy(self._plan)
+            self._plan = None
+        CO, AAG, M, n = self.AAG.CO, self.AAG, self.M, self.n
+        c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        ks = AAG.k.copy()
+        ks[n//2] = 0.0
+        R = 3*M - 1
+        kinv = np.zeros((R, R, n), dtype=complex)
+        cols = np.concatenate([np.arange(n//2), np.arange(n//2 + 1, n)])
+        kinv[:, :, cols] = np.transpose(self.Stacked_KINVS, (1, 2, 0))
+        kinv = np.ascontiguousarray(kinv)
+        combo1 = 2*RAG.DR_psi2*RAG.inv_psi2**2
+        combo2 = RAG.DR_psi2**2*RAG.inv_psi2**2
+        arrs = [c(CO.D01), c(CO.D12), c(CO.R01), c(CO.R12), c(CO.R02), c(CO.P10), c(CO.ibc_dirichlet[0]),
+                c(CO.obc_dirichlet[0]), c(CO.VI1[0]), c(ks), c(RAG.psi0), c(RAG.psi1), c(RAG.inv_psi1), c(RAG.inv_psi2),
+                c(combo1), c(combo2), c(RAG.ipsi_DR_ipsi_DT_psi2)]
+        h = ctypes.c_void_p()
+        lib().ipde_annular_stokes_plan_create(n, M, float(self.mu), *[hptr(a) for a in arrs], hptr(kinv), ctypes.byref(h))
+        self._plan, self._plan_key = h, key
+        self._keep = RAG
+        return h
+
+    def __del__(self):
+        try:
+            if self._plan is not None:
+                lib().ipde_annular_stokes_plan_destroy(self._plan)
+        except Exception:
+            pass
+
+    def solve(self, RAG, fr, ft, irg, itg, org, otg, verbose=False, tol=1e-5, restart=20, maxiter=None, **kwargs):
+        self.RAG = RAG
+        plan = self._get_plan(RAG)
+        on_host = not torch.is_tensor(fr)
+        dv = lambda a: None if a is None else (a if torch.is_tensor(a) else to_dev(np.asarray(a, dtype=float)))
+        frd, ftd = dv(fr), dv(ft)
+        bcs = [dv(b) for b in (irg, itg, org, otg)]
+        ur, ut, pr = empty(self.u_shape), empty(self.u_shape), empty(self.u_shape)
+        iters = ctypes.c_int(0)
+        relres = ctypes.c_double(0.0)
+        if restart is None:
+            restart = 20
+        if maxiter is None:
+            maxiter = 100
+        lib().ipde_annular_stokes_solve(plan, ptr(frd), ptr(ftd), ptr(bcs[0]), ptr(bcs[1]), ptr(bcs[2]), ptr(bcs[3]),
+                                        float(tol), int(restart), int(maxiter), ptr(ur), ptr(ut), ptr(pr),
+                                        ctypes.byref(iters), ctypes.byref(relres), stream())
+        self.iterations_last_call = iters.value
+        self.relative_residual_last_call = relres.value
+        if verbose:
+            print('GMRES took:', iters.value, 'iterations.')
+        if on_host:
+            return ur.cpu().numpy(), ut.cpu().numpy(), pr.cpu().numpy()
+        return ur, ut, pr
+
+    # ---- exposed for tests: vectors in the reference's layout (ns = n-1 columns per row block, raveled)
+    def _to_dev_layout(self, v):
+        M, n, ns = self.M, self.n, self.ns
+        R = 3*M - 1
+        full = np.zeros((R, n), dtype=complex)
+        cols = np.concatenate([np.arange(n//2), np.arange(n//2 + 1, n)])
+        full[:, cols] = np.asarray(v, dtype=complex).reshape(R, ns)
+        return to_dev(full)
+
+    def _from_dev_layout(self, y):
+        n = self.n
+        cols = np.concatenate([np.arange(n//2), np.arange(n//2 + 1, n)])
+        return y.cpu().numpy()[:, cols].ravel()
+
+    def _apply_optim_real(self, uuh):
+        plan = self._get_plan(self.RAG)
+        x = self._to_dev_layout(uuh)
+        y = torch.empty_like(x)
+        lib().ipde_annular_stokes_apply(plan, ptr(x), ptr(y), stream())
+        return self._from_dev_layout(y)
+
+    def _preconditioner(self, ffh):
+        plan = self._get_plan(self.RAG)
+        x = self._to_dev_layout(ffh)
+        y = torch.empty_like(x)
+        lib().ipde_annular_stokes_precond(plan, ptr(x), ptr(y), stream())
+        return self._from_dev_layout(y)

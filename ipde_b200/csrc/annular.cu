@@ -178,6 +178,7 @@ struct AnnularScalarOp : public LinearOperator {
     }
     int precond(const cplx* in, cplx* out, cudaStream_t st) override {
         const int threads = 128, blocks = (p->n + threads - 1) / threads;
+        KERNEL_TAG("k_ann_precond", (8.0 * p->M + 32.0) * (double)p->M * (double)p->n);
         k_ann_precond<<<dim3(blocks, p->M), threads, 0, st>>>(in, out, p->n, p->M, p->kinv);
         KERNEL_CHECK();
         return IPDE_OK;

@@ -8,7 +8,9 @@
 #include "layer.cuh"
 #include "nufft.cuh"
 #include "radial.cuh"
+#include "vector.cuh"
 #include <cstdarg>
+#include <algorithm>
 #include <mutex>
 
 static thread_local char g_err[1024] = "";
@@ -24,6 +26,35 @@ void ipde_set_error(const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 void ipde_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// ---- per-kernel profile: one event after every launch, elapsed time between consecutive events
+#include <map>
+#include <string>
+#include <vector>
+struct ProfRec { std::string name; double bytes; cudaEvent_t ev; };
+static bool g_prof_on = false;
+static cudaStream_t g_prof_stream = 0;
+static cudaEvent_t g_prof_begin = nullptr;
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+static const char* g_prof_name = nullptr;
+static double g_prof_bytes = 0.0;
+void ipde_prof_tag(const char* name, double bytes) { g_prof_name = name; g_prof_bytes = bytes; }
+void ipde_prof_mark(const char* file, int line) {
+    if (!g_prof_on) { g_prof_name = nullptr; return; }
+    ProfRec r;
+    if (g_prof_name) { r.name = g_prof_name; r.bytes = g_prof_bytes; }
+    else {
+        const char* base = strrchr(file, '/');
+        r.name = std::string(base ? base + 1 : file) + ":" + std::to_string(line);
+        r.bytes = 0.0;
+    }
+    g_prof_name = nullptr;
+    if (!g_prof_pool.empty()) { r.ev = g_prof_pool.back(); g_prof_pool.pop_back(); }
+    else if (cudaEventCreate(&r.ev) != cudaSuccess) return;
+    cudaEventRecord(r.ev, g_prof_stream);
+    g_prof_recs.push_back(r);
+}
+
 #define ST(s) ((cudaStream_t)(s))
 #define CP(p) (reinterpret_cast<const cplx*>(p))
 #define MP(p) (reinterpret_cast<cplx*>(p))
@@ -34,6 +65,49 @@ const char* ipde_last_error(void) { return g_err; }
 int ipde_version(void) { return 100; }
 int ipde_device_sm_count(void) { return ipde_num_sms(); }
 int64_t ipde_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int ipde_profile_start(void* stream) {
+    g_prof_stream = ST(stream);
+    for (auto& r : g_prof_recs) g_prof_pool.push_back(r.ev);
+    g_prof_recs.clear();
+    if (!g_prof_begin) CUDA_TRY(cudaEventCreate(&g_prof_begin));
+    CUDA_TRY(cudaEventRecord(g_prof_begin, g_prof_stream));
+    g_prof_on = true;
+    return IPDE_OK;
+}
+
+// Writes one line per kernel name: "name count total_ms total_bytes\n" (sorted by time) into `out`.
+int ipde_profile_stop(char* out, int64_t cap) {
+    g_prof_on = false;
+    CUDA_TRY(cudaStreamSynchronize(g_prof_stream));
+    struct Acc { int64_t n = 0; double ms = 0.0, bytes = 0.0; };
+    std::map<std::string, Acc> acc;
+    cudaEvent_t prev = g_prof_begin;
+    for (auto& r : g_prof_recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, prev, r.ev);
+        Acc& a = acc[r.name];
+        a.n += 1; a.ms += ms; a.bytes += r.bytes;
+        prev = r.ev;
+    }
+    std::vector<std::pair<std::string, Acc>> v(acc.begin(), acc.end());
+    std::sort(v.begin(), v.end(), [](const std::pair<std::string, Acc>& a, const std::pair<std::string, Acc>& b) { return a.second.ms > b.second.ms; });
+    std::string text;
+    for (auto& kv : v) {
+        char line[512];
+        snprintf(line, sizeof(line), "%s %lld %.6f %.0f\n", kv.first.c_str(), (long long)kv.second.n, kv.second.ms, kv.second.bytes);
+        text += line;
+    }
+    if (out && cap > 0) {
+        const size_t nmax = (size_t)cap - 1;
+        const size_t ncopy = text.size() < nmax ? text.size() : nmax;
+        memcpy(out, text.data(), ncopy);
+        out[ncopy] = 0;
+    }
+    for (auto& r : g_prof_recs) g_prof_pool.push_back(r.ev);
+    g_prof_recs.clear();
+    return IPDE_OK;
+}
 
 // ---- FFT
 int ipde_fft_plan_create(int n, void** plan) {
@@ -173,6 +247,51 @@ int ipde_annular_precond(void* plan, const double* in, double* out, void* stream
 int ipde_annular_solve(void* plan, const double* f, const double* ig, const double* og, double f_sign, double tol,
                        int restart, int maxiter, double* u_out, int* iters, double* relres, void* stream) {
     return annular_solve((AnnularPlan*)plan, f, ig, og, f_sign, tol, restart, maxiter, u_out, iters, relres, ST(stream));
+}
+
+// ---- annular Stokes
+int ipde_annular_stokes_plan_create(int n, int M, double mu, const double* D01, const double* D12, const double* R01,
+                                    const double* R12, const double* R02, const double* P10, const double* ibc,
+                                    const double* obc, const double* vi1, const double* ks, const double* psi0,
+                                    const double* psi1, const double* ipsi1, const double* ipsi2, const double* combo1,
+                                    const double* combo2, const double* m3, const double* kinv_mode_minor, void** plan) {
+    AnnularStokesPlan* p = nullptr;
+    int rc = annular_stokes_plan_create(n, M, mu, D01, D12, R01, R12, R02, P10, ibc, obc, vi1, ks, psi0, psi1, ipsi1, ipsi2,
+                                        combo1, combo2, m3, kinv_mode_minor, &p);
+    *plan = p;
+    return rc;
+}
+int ipde_annular_stokes_plan_destroy(void* plan) { annular_stokes_plan_destroy((AnnularStokesPlan*)plan); return IPDE_OK; }
+int ipde_annular_stokes_apply(void* plan, const double* in, double* out, void* stream) {
+    return annular_stokes_apply((AnnularStokesPlan*)plan, CP(in), MP(out), ST(stream));
+}
+int ipde_annular_stokes_precond(void* plan, const double* in, double* out, void* stream) {
+    return annular_stokes_precond((AnnularStokesPlan*)plan, CP(in), MP(out), ST(stream));
+}
+int ipde_annular_stokes_solve(void* plan, const double* fr, const double* ft, const double* irg, const double* itg,
+                              const double* org, const double* otg, double tol, int restart, int maxiter, double* ur,
+                              double* ut, double* pr, int* iters, double* relres, void* stream) {
+    return annular_stokes_solve((AnnularStokesPlan*)plan, fr, ft, irg, itg, org, otg, tol, restart, maxiter, ur, ut, pr, iters,
+                                relres, ST(stream));
+}
+
+// ---- Stokes helper glue
+int ipde_uv_rt(const double* f0, const double* f1, const double* nx, const double* ny, const double* tx, const double* ty, int M,
+               int n, double* out0, double* out1, int inverse, void* stream) {
+    return vec_uv_rt(f0, f1, nx, ny, tx, ty, M, n, out0, out1, inverse, ST(stream));
+}
+int ipde_radial_traction(const double* Ur, const double* Ut, const double* dUr, const double* P, const double* D00,
+                         const double* est, const double* rsp, const double* nx, const double* ny, const double* tx,
+                         const double* ty, int M, int n, double* Tx, double* Ty, void* stream) {
+    return vec_radial_traction(Ur, Ut, dUr, P, D00, est, rsp, nx, ny, tx, ty, M, n, Tx, Ty, ST(stream));
+}
+int ipde_vector_jumps(const double* rtx, const double* rty, const double* txx, const double* txy, const double* tyy,
+                      const double* bu, const double* bv, const double* inx, const double* iny, int n, double sign,
+                      double* tau, void* stream) {
+    return vec_jumps(rtx, rty, txx, txy, tyy, bu, bv, inx, iny, n, sign, tau, ST(stream));
+}
+int ipde_theta_derivative(void* fft_plan, const double* f, double* work_cplx, double* out, int rows, void* stream) {
+    return vec_theta_derivative((FftPlan*)fft_plan, f, work_cplx, out, rows, ST(stream));
 }
 
 // ---- spectral-Ewald free-space evaluator

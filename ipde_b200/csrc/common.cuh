@@ -15,6 +15,11 @@
 
 void ipde_set_error(const char* fmt, ...);
 void ipde_count_launch();   // every kernel launch of this library is counted (bench.py: gpu_launches)
+// Per-kernel timing (off unless ipde_profile_start was called): KERNEL_CHECK records a CUDA event after the
+// launch on `prof_stream`; KERNEL_TAG names the launch and states its algorithmic bytes (bench.py: roofline).
+void ipde_prof_tag(const char* name, double bytes);
+void ipde_prof_mark(const char* file, int line);
+#define KERNEL_TAG(name, bytes) ipde_prof_tag(name, (double)(bytes))
 
 #define CUDA_TRY(expr)                                                              \
     do {                                                                            \
@@ -29,6 +34,7 @@ void ipde_count_launch();   // every kernel launch of this library is counted (b
 #define KERNEL_CHECK()                  \
     do {                                \
         ipde_count_launch();            \
+        ipde_prof_mark(__FILE__, __LINE__); \
         CUDA_TRY(cudaGetLastError());   \
     } while (0)
 

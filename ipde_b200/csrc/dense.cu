@@ -35,6 +35,7 @@ int dense_gemv(const double* A, const double* x, double* y, int64_t m, int64_t n
     if (m <= 0) return IPDE_OK;
     const int threads = 256;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(m * 32, threads), (int64_t)ipde_num_sms() * 8));
+    KERNEL_TAG("k_gemv", 8.0 * (double)m * (double)n);
     k_gemv<<<blocks, threads, 0, st>>>(A, x, y, m, n, n);
     KERNEL_CHECK();
     return IPDE_OK;

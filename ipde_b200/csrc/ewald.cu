@@ -309,6 +309,7 @@ int ewald_apply(EwaldPlan* p, const double* q, double* grid_out, double* point_o
     const double ck = (p->kind == 1) ? exp(-p->kappa * p->kappa / (4.0 * p->xi * p->xi)) : 1.0;
     const double wnorm = two_xi2 / 3.14159265358979323846;      // (2 xi^2 / pi)
     if (p->ntiles > 0) {
+        KERNEL_TAG("k_ewald_tiles", 16.0 * 256.0 * (double)p->ntiles);
         k_ewald_tiles<<<p->ntiles, dim3(EW_TILE, EW_TILE), 0, st>>>(p->tile_ix, p->tile_iy, p->tile_ptr, p->tile_src, p->sx,
                                                                    p->sy, q, T, p->x0, p->y0, p->h, p->rc2, p->rw2, two_xi2,
                                                                    ck * wnorm, p->px, p->py, p->Sw, p->Lc, want_grid ? 1 : 0);
@@ -339,6 +340,7 @@ int ewald_apply(EwaldPlan* p, const double* q, double* grid_out, double* point_o
             if (rc) return rc;
         }
         const int pb = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(p->n_pt * 32, 256), (int64_t)ipde_num_sms() * 16));
+        KERNEL_TAG("k_ewald_points", 8.0 * 961.0 * (double)p->n_pt);
         k_ewald_points<<<pb, 256, 0, st>>>(p->R, p->ptx, p->pty, p->n_pt, p->tile_map, p->ntx, p->nty, p->tile_ptr,
                                            p->tile_src, p->sx, p->sy, q, T, p->x0, p->y0, p->h, p->rc2, two_xi2,
                                            wnorm * p->h * p->h, p->m, p->px, p->py, point_out, accumulate_points);

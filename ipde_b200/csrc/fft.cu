@@ -291,6 +291,7 @@ int fft_rows(FftPlan* p, const cplx* in, cplx* out, int64_t batch, int64_t in_pi
     const unsigned g = (unsigned)cdiv(batch, C);
     const int t = fft_tile_threads(n, C, ept);
     int rc = IPDE_OK;
+    KERNEL_TAG("k_fft_rows", 32.0 * (double)n * (double)batch);
     FFT_TILE_LAUNCH(k_fft_rows, ept, p->pow2, g, t, smem, st, p->d, in, out, batch, in_pitch, out_pitch, C, sign, scale);
     if (rc) return rc;
     KERNEL_CHECK();
@@ -327,6 +328,7 @@ int fft_cols(FftPlan* p, const cplx* in, cplx* out, int64_t elem_stride, int64_t
     const unsigned g = (unsigned)(tiles * n_outer);
     const int t = fft_tile_threads(n, C, ept);
     int rc = IPDE_OK;
+    KERNEL_TAG("k_fft_cols", 32.0 * (double)n * (double)n_inner * (double)n_outer);
     FFT_TILE_LAUNCH(k_fft_cols, ept, p->pow2, g, t, smem, st, p->d, in, out, elem_stride, n_inner, outer_stride, C, logC, sign, scale, tw_mode, tw_big);
     if (rc) return rc;
     KERNEL_CHECK();
@@ -451,6 +453,7 @@ int fft_r2c_rows(FftPlan* p, const double* in, cplx* out, int64_t batch, int64_t
     const unsigned g = (unsigned)cdiv(batch, C);
     const int t = fft_tile_threads(n, C, ept);
     int rc = IPDE_OK;
+    KERNEL_TAG("k_r2c_rows", (16.0 * n + 16.0 * (n + 1)) * (double)batch);
     FFT_TILE_LAUNCH(k_r2c_rows, ept, p->pow2, g, t, smem, st, p->d, p->half_tw_dev, in, out, batch, in_pitch, out_pitch, C);
     if (rc) return rc;
     KERNEL_CHECK();
@@ -477,6 +480,7 @@ int fft_c2r_rows(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t
     const unsigned g = (unsigned)cdiv(batch, C);
     const int t = fft_tile_threads(n, C, ept);
     int rc = IPDE_OK;
+    KERNEL_TAG("k_c2r_rows", (16.0 * n + 16.0 * (n + 1)) * (double)batch);
     FFT_TILE_LAUNCH(k_c2r_rows, ept, p->pow2, g, t, smem, st, p->d, p->half_tw_dev, in, out, batch, in_pitch, out_pitch, C, scale);
     if (rc) return rc;
     KERNEL_CHECK();
@@ -539,6 +543,7 @@ int fft_mul_fft_rows(FftPlan* p, const cplx* in, cplx* out, const double* m, int
     const unsigned g = (unsigned)cdiv(batch, C);
     const int t = fft_tile_threads(n, C, ept);
     int rc = IPDE_OK;
+    KERNEL_TAG("k_fft_mul_fft_rows", 40.0 * (double)n * (double)batch);
     FFT_TILE_LAUNCH(k_fft_mul_fft_rows, ept, p->pow2, g, t, smem, st, p->d, in, out, m, batch, C);
     if (rc) return rc;
     KERNEL_CHECK();

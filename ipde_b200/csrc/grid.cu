@@ -159,6 +159,8 @@ static int launch_cols_mult_one(FftPlan* p, unsigned g, int t, size_t smem, cuda
                                 int do_fwd, int copy_mode, const ColMult& M) {
     if (smem > 48 * 1024)
         CUDA_TRY(cudaFuncSetAttribute(k_cols_mult<EPT, CLS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KERNEL_TAG("k_cols_mult", (32.0 + (copy_mode ? 16.0 : 0.0) + (M.kind == 3 ? 8.0 : 0.0)) * (double)p->d.n * (double)n_inner *
+                                  (double)(g / cdiv(n_inner, C)));
     k_cols_mult<EPT, CLS, NT><<<g, t, smem, st>>>(p->d, in, out, copy, elem_stride, n_inner, outer_stride, C, logC, do_fwd,
                                                   copy_mode, M);
     KERNEL_CHECK();

@@ -119,6 +119,41 @@ def golden_annular_scalar():
     print('annular Poisson err vs exact', np.abs(up - sol(rx, ry)).max(), 'its', P.iterations_last_call)
 
 
+def golden_annular_stokes():
+    from ipde.annular.annular import ApproximateAnnularGeometry, RealAnnularGeometry
+    from ipde.annular.stokes import AnnularStokesSolver
+    out = {}
+    n, M, width = 64, 8, 0.2
+    c, nc, sp, cur = star_geometry(n, a=0.08, f=3)
+    AAG = ApproximateAnnularGeometry(n, M, width, np.mean(np.abs(c)))
+    RAG = RealAnnularGeometry(sp, cur, AAG)
+    S = AnnularStokesSolver(AAG, mu=1.0)
+    rng = np.random.default_rng(11)
+    t = np.linspace(0, 2*np.pi, n, endpoint=False)
+    rv = AAG.rv0[:, None]
+    fr = np.cos(2*t)[None, :]*np.exp(rv) + 0.3*np.sin(t)[None, :]
+    ft = np.sin(3*t)[None, :]*(1 + rv) - 0.2*np.cos(t)[None, :]*rv**2
+    irg, itg = 0.1*np.cos(t), 0.05*np.sin(2*t)
+    org, otg = 0.2*np.sin(t), -0.1*np.cos(3*t)
+    ur, ut, p = S.solve(RAG, fr, ft, irg, itg, org, otg, tol=1e-14, restart=80, maxiter=4)
+    # one operator / preconditioner application on a Hermitian-symmetric random vector
+    def herm(rows):
+        f = rng.standard_normal((rows, n))
+        fh = np.fft.fft(f, axis=1)
+        return np.concatenate([fh[:, :n//2], fh[:, n//2 + 1:]], axis=1)
+    x = np.concatenate([herm(M).ravel(), herm(M).ravel(), herm(M - 1).ravel()])
+    S.RAG = RAG
+    S.combo1 = 2*RAG.DR_psi2*RAG.inv_psi2**2
+    S.combo2 = RAG.DR_psi2**2*RAG.inv_psi2**2
+    S.ik = AAG.k*1j
+    S.iks = AAG.ks*1j
+    out.update(n=n, M=M, width=width, radius=np.mean(np.abs(c)), speed=sp, curvature=cur, fr=fr, ft=ft,
+               irg=irg, itg=itg, org=org, otg=otg, ur=ur, ut=ut, p=p, x=x,
+               Ax=S._apply_optim_real(x), Px=S._preconditioner(x), Ax_complex=S._apply(x))
+    np.savez_compressed(os.path.join(GOLD, 'annular_stokes.npz'), **out)
+    print('annular_stokes.npz written')
+
+
 def golden_slepian():
     from ipde.slepian.chebeval_bump_step import SlepianMollifier
     x = np.linspace(-1.25, 1.25, 501)
@@ -150,9 +185,7 @@ if __name__ == '__main__':
     install_shims()
     os.makedirs(GOLD, exist_ok=True)
     golden_annular_scalar()
+    golden_annular_stokes()
     golden_slepian()
     golden_misc()
-    if os.path.exists(os.path.join(HERE, 'make_golden_stokes.py')):
-        from make_golden_stokes import golden_annular_stokes
-        golden_annular_stokes(GOLD)
     print('golden vectors written to', GOLD)

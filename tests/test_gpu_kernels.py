@@ -356,3 +356,17 @@ def test_nufft2_apply3_matches_separate_transforms(D):
     assert rel(v.cpu().numpy(), v0.cpu().numpy()) < 1e-13
     assert rel(dx.cpu().numpy(), dx0.cpu().numpy()) < 5e-13
     assert rel(dy.cpu().numpy(), dy0.cpu().numpy()) < 5e-13
+
+
+def test_annular_stokes_against_reference_golden(D, golden_dir):
+    """device annular Stokes operator, preconditioner and GMRES solve against the reference's own outputs"""
+    from ipde_b200.annular import ApproximateAnnularGeometry, RealAnnularGeometry, AnnularStokesSolver
+    g = np.load(os.path.join(golden_dir, 'annular_stokes.npz'))
+    AAG = ApproximateAnnularGeometry(int(g['n']), int(g['M']), float(g['width']), float(g['radius']), drop_nyquist=True)
+    RAG = RealAnnularGeometry(g['speed'], g['curvature'], AAG)
+    S = AnnularStokesSolver(AAG, 1.0)
+    S.RAG = RAG
+    assert rel(S._apply_optim_real(g['x']), g['Ax']) < 1e-12
+    assert rel(S._preconditioner(g['x']), g['Px']) < 1e-11
+    ur, ut, p = S.solve(RAG, g['fr'], g['ft'], g['irg'], g['itg'], g['org'], g['otg'], tol=1e-14, restart=80, maxiter=4)
+    assert rel(ur, g['ur']) < 1e-11 and rel(ut, g['ut']) < 1e-11 and rel(p, g['p']) < 1e-10

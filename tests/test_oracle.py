@@ -78,3 +78,19 @@ def test_radial_interpolation_reproduces_nodes():
     tq, tt = rng.uniform(0, np.pi, 20), rng.uniform(0, 2*np.pi, 20)
     v = osol.interpolate_radial_to_points(fr, tq, tt)
     assert np.abs(v - (np.cos(2*tq)*np.sin(3*tt) + 0.3*np.cos(tq))).max() < 1e-13
+
+
+def test_oracle_annular_stokes_matches_reference_golden(golden_dir):
+    """oracle/annular_stokes.py against inputs/outputs of the reference's own AnnularStokesSolver"""
+    from oracle.annular import ApproximateAnnularGeometry, RealAnnularGeometry
+    from oracle.annular_stokes import AnnularStokesSolver
+    g = np.load(os.path.join(golden_dir, 'annular_stokes.npz'))
+    AAG = ApproximateAnnularGeometry(int(g['n']), int(g['M']), float(g['width']), float(g['radius']), drop_nyquist=True)
+    RAG = RealAnnularGeometry(g['speed'], g['curvature'], AAG)
+    S = AnnularStokesSolver(AAG, 1.0)
+    S.RAG = RAG
+    rel = lambda a, b: np.abs(a - b).max()/np.abs(b).max()
+    assert rel(S.apply(g['x']), g['Ax']) < 1e-13
+    assert rel(S.preconditioner(g['x']), g['Px']) < 1e-11
+    ur, ut, p = S.solve(RAG, g['fr'], g['ft'], g['irg'], g['itg'], g['org'], g['otg'], tol=1e-14, restart=80, maxiter=4)
+    assert rel(ur, g['ur']) < 1e-12 and rel(ut, g['ut']) < 1e-12 and rel(p, g['p']) < 1e-11
