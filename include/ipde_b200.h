@@ -70,6 +70,10 @@ int ipde_grid_solve_scalar(void* plan, int kind, double k, double* fc, const dou
 /* Stokes `_grid_solve`, ipde/solvers/multi_boundary/stokes.py:34-45: specs of u, v, p are returned too */
 int ipde_grid_solve_stokes(void* plan, double* fuc, double* fvc, const double* bumpy, double* uh, double* vh,
                            double* ph, double* spec_work, double* uc, double* vc, double* pc, void* stream);
+/* spectra of the grid stress txx = 2u_x - p, txy = u_y + v_x, tyy = 2v_y - p with the spectral derivative of
+ * ipde/derivatives.py:25-28 (Nyquist row/column dropped by its .real): ipde/solvers/multi_boundary/vector.py:68-73 */
+int ipde_grid_stokes_stress(void* plan, const double* uh, const double* vh, const double* ph, double* txx, double* txy,
+                            double* tyy, void* stream);
 /* 4th-order centred differences, zero in the 2-cell border: ipde/derivatives.py:3-23 */
 int ipde_grid_fd4(void* plan, const double* f, double* fx, double* fy, void* stream);
 /* periodic cubic interpolation to points: fast_interp.interp2d(k=3) at ipde/ebdy_collection.py:594-603 */

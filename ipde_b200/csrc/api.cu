@@ -181,6 +181,10 @@ int ipde_grid_solve_stokes(void* plan, double* fuc, double* fvc, const double* b
     if (!rc) rc = grid_fft2_inverse(g, CP(ph), MP(spec_work), pc, ST(stream));
     return rc;
 }
+int ipde_grid_stokes_stress(void* plan, const double* uh, const double* vh, const double* ph, double* txx, double* txy,
+                            double* tyy, void* stream) {
+    return grid_stokes_stress((GridPlan*)plan, CP(uh), CP(vh), CP(ph), MP(txx), MP(txy), MP(tyy), ST(stream));
+}
 int ipde_grid_fd4(void* plan, const double* f, double* fx, double* fy, void* stream) {
     return grid_fd4((GridPlan*)plan, f, fx, fy, ST(stream));
 }

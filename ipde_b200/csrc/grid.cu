@@ -509,3 +509,35 @@ int grid_stokes_multiply(GridPlan* g, cplx* uh, cplx* vh, cplx* ph, cudaStream_t
     KERNEL_CHECK();
     return IPDE_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// Spectra of the grid stress of the Stokes solve, reference ipde/solvers/multi_boundary/vector.py:68-73 with the
+// spectral derivative of ipde/derivatives.py:25-28: d/dx f = ifft2(i kx fft2(f)).real.  Taking the real part of
+// that product removes the (self-conjugate) Nyquist row for d/dx and the Nyquist column for d/dy exactly, so the
+// derivative symbols are zero there.
+//   txx = 2 u_x - p ;  txy = u_y + v_x ;  tyy = 2 v_y - p
+__global__ void k_stokes_stress(const cplx* __restrict__ uh, const cplx* __restrict__ vh, const cplx* __restrict__ ph,
+                                cplx* __restrict__ txx, cplx* __restrict__ txy, cplx* __restrict__ tyy, int nx, int ny,
+                                int64_t pitch, int n1, int n2, double xh, double yh) {
+    const int64_t total = (int64_t)nx * pitch;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int pos = (int)(t / pitch), j = (int)(t % pitch);
+        const int i = freq_of_row(pos, n1, n2);
+        const double kx = (nx % 2 == 0 && i == nx / 2) ? 0.0 : wavenumber(i, nx, xh);
+        const double ky = (j == ny / 2) ? 0.0 : wavenumber(j, ny, yh);
+        const cplx u = uh[t], v = vh[t], p = ph[t];
+        // i k z = (-k z.y, k z.x)
+        txx[t] = make_double2(-2.0 * kx * u.y - p.x, 2.0 * kx * u.x - p.y);
+        txy[t] = make_double2(-ky * u.y - kx * v.y, ky * u.x + kx * v.x);
+        tyy[t] = make_double2(-2.0 * ky * v.y - p.x, 2.0 * ky * v.x - p.y);
+    }
+}
+
+int grid_stokes_stress(GridPlan* g, const cplx* uh, const cplx* vh, const cplx* ph, cplx* txx, cplx* txy, cplx* tyy,
+                       cudaStream_t st) {
+    const int64_t total = (int64_t)g->nx * g->pitch;
+    k_stokes_stress<<<grid_blocks(total, 256), 256, 0, st>>>(uh, vh, ph, txx, txy, tyy, g->nx, g->ny, g->pitch, g->n1, g->n2,
+                                                             g->xh, g->yh);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}

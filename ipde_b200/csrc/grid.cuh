@@ -52,3 +52,5 @@ int grid_cols_symbol(GridPlan* g, cplx* spec_in, cplx* spec_out, cplx* spec_copy
 int grid_cols_symbol_inverse(GridPlan* g, const cplx* spec2d, cplx* spec_out, const ColMult& M, cudaStream_t st);
 int grid_solve_scalar_fused(GridPlan* g, int kind, double k, const double* fc, cplx* uch, cplx* spec_work, double* uc,
                             cudaStream_t st);
+int grid_stokes_stress(GridPlan* g, const cplx* uh, const cplx* vh, const cplx* ph, cplx* txx, cplx* txy, cplx* tyy,
+                       cudaStream_t st);

@@ -232,3 +232,150 @@ class OracleScalarSolver(object):
                 interpolate_radial_to_points(ur, ebdy.grid_ia_r_transf, ebdy.grid_ia_t)
         uc *= e.phys
         return np.concatenate([uc[e.phys]] + [ur.ravel() for ur in urs])
+
+
+# ---------------------------------------------------------------------------------------------
+# vector (Stokes) path
+def layer_apply_stokes(sx, sy, fx_w, fy_w, tx, ty, chunk=3000):
+    """stokeslet velocity (1/4pi)(-log r I + rr/r^2) f and pressure (1/2pi) r.f/r^2 (weighted forces);
+    ipde/solvers/internals/stokes.py:26-35 (pyfmmlib2d.SFMM), stokes_save.py:29-38"""
+    u = np.empty(tx.size); v = np.empty(tx.size); p = np.empty(tx.size)
+    for a in range(0, tx.size, chunk):
+        b = min(tx.size, a + chunk)
+        dx = tx[a:b, None] - sx[None, :]
+        dy = ty[a:b, None] - sy[None, :]
+        r2 = dx*dx + dy*dy
+        L = -0.5*np.log(r2)
+        rf = (dx*fx_w + dy*fy_w)/r2
+        u[a:b] = (L*fx_w + rf*dx).sum(axis=1)/(4*np.pi)
+        v[a:b] = (L*fy_w + rf*dy).sum(axis=1)/(4*np.pi)
+        p[a:b] = rf.sum(axis=1)/(2*np.pi)
+    return u, v, p
+
+
+class OracleVectorHelper(object):
+    """ipde/solvers/internals/vector.py:8-162 with the Stokes pieces of internals/stokes.py:10-35"""
+    def __init__(self, ebdy, qfs_g, qfs_r):
+        from .annular_stokes import AnnularStokesSolver
+        self.ebdy = ebdy
+        self.interior = ebdy.interior
+        self.AAG = ApproximateAnnularGeometry(ebdy.bdy.N, ebdy.M, ebdy.radial_width, ebdy.approximate_radius,
+                                              drop_nyquist=True)
+        self.annular_solver = AnnularStokesSolver(self.AAG, mu=1.0)
+        bb = ebdy.bdy if self.interior else ebdy.interface
+        self.RAG = RealAnnularGeometry(bb.speed, bb.curvature, self.AAG)
+        CO = self.AAG.CO
+        self._bv = CO.obc_dirichlet[0] if self.interior else CO.ibc_dirichlet[0]
+        self._iv = CO.ibc_dirichlet[0] if self.interior else CO.obc_dirichlet[0]
+        self.qfs_g, self.qfs_r = qfs_g, qfs_r
+
+    def traction_uvp(self, u, v, p, est):
+        e = self.ebdy
+        Ur, Ut = e.convert_uv_to_rt(u, v)
+        Urr = e._radial_grid_r_derivative(Ur)
+        Urt = e._radial_grid_tau_derivative(Ur)
+        Utr = e.radial_speed*e._radial_grid_r_derivative(Ut*e.inverse_radial_speed)
+        Tr = 2*est.dot(Urr) - est.dot(p)
+        Tt = est.dot(Utr) + est.dot(Urt)
+        return e.convert_rt_to_uv(Tr, Tt)
+
+    def __call__(self, fur, fvr, bu, bv, btxx, btxy, btyy, **kwargs):
+        e = self.ebdy
+        btx = btxx*e.interface.normal_x + btxy*e.interface.normal_y
+        bty = btxy*e.interface.normal_x + btyy*e.interface.normal_y
+        fr, ft = e.convert_uv_to_rt(fur, fvr)
+        zer = np.zeros(e.bdy.N)
+        rr, tr, pr = self.annular_solver.solve(self.RAG, fr, ft, zer, zer, zer, zer, **kwargs)
+        self.iterations_last_call = self.annular_solver.iterations_last_call
+        ur, vr = e.convert_rt_to_uv(rr, tr)
+        rtx, rty = self.traction_uvp(ur, vr, pr, self._iv)
+        taus = np.concatenate([rtx - btx, rty - bty])
+        taud = np.concatenate([bu, bv])
+        if not self.interior:
+            taus, taud = -taus, -taud
+        self.sigma_g = self.qfs_g([taus, taud]).reshape(2, -1)
+        self.sigma_r = self.qfs_r([taus, taud]).reshape(2, -1)
+        self.ur, self.vr, self.pr = ur, vr, pr
+        return self.sigma_g
+
+    def correct(self, ub, vb, pb, single_ebdy):
+        e = self.ebdy
+        if single_ebdy:
+            tot = self.sigma_r
+        else:
+            s = self.qfs_g.source
+            w = layer_apply_stokes(s.x, s.y, self.sigma_g[0]*s.weights, self.sigma_g[1]*s.weights,
+                                   e.interface.x, e.interface.y)
+            tot = self.qfs_r.u2s(np.concatenate([ub - w[0], vb - w[1]])).reshape(2, -1) + self.sigma_r
+        s = self.qfs_r.source
+        r = layer_apply_stokes(s.x, s.y, tot[0]*s.weights, tot[1]*s.weights, e.radial_x.ravel(), e.radial_y.ravel())
+        self.ur = self.ur + r[0].reshape(self.ur.shape)
+        self.vr = self.vr + r[1].reshape(self.ur.shape)
+        self.pr = self.pr + r[2].reshape(self.ur.shape)
+        return self.ur, self.vr, self.pr
+
+
+class OracleVectorSolver(object):
+    """ipde/solvers/multi_boundary/vector.py:57-112 + stokes.py:34-50, spectral or 'fourth'"""
+    def __init__(self, ebdyc, solver_type='spectral', qfs_pairs=None):
+        self.ebdyc, self.solver_type = ebdyc, solver_type
+        self.helpers = [OracleVectorHelper(e, g, r) for e, (g, r) in zip(ebdyc, qfs_pairs)]
+        self.ikx, self.iky = ebdyc.ikx, ebdyc.iky
+        lap = (-ebdyc.kx*ebdyc.kx - ebdyc.ky*ebdyc.ky).copy()
+        lap[0, 0] = np.inf
+        self.ilap = 1.0/lap
+
+    def __call__(self, fu, fv, **kwargs):
+        e = self.ebdyc
+        N = e.grid_phys.N
+        g = e.grid
+        def comps(f):
+            f = np.asarray(f)
+            fg = np.zeros(g.shape)
+            fg[e.phys] = f[:N]
+            return fg*e.grid_step, [r.copy() for r in e.v2r(f[N:])]
+        fuc, fur_list = comps(fu)
+        fvc, fvr_list = comps(fv)
+        dem = lambda f: f - (np.sum(f)*g.xh*g.yh)*e.bumpy
+        fuch, fvch = np.fft.fft2(dem(fuc)), np.fft.fft2(dem(fvc))
+        cph = self.ilap*(self.ikx*fuch + self.iky*fvch)
+        cuh = self.ilap*(self.ikx*cph - fuch)
+        cvh = self.ilap*(self.iky*cph - fvch)
+        uc, vc, pc = np.fft.ifft2(cuh).real, np.fft.ifft2(cvh).real, np.fft.ifft2(cph).real
+        if self.solver_type == 'spectral':
+            I = lambda a: nudft2d_type2(np.fft.fft2(a)[None], e.interfaces_x_transf, e.interfaces_y_transf)[0].real
+            dx = lambda a: np.fft.ifft2(np.fft.fft2(a)*self.ikx).real
+            dy = lambda a: np.fft.ifft2(np.fft.fft2(a)*self.iky).real
+        else:
+            I = lambda a: lagrange_interp2d_periodic(a, g.xv[0], g.yv[0], g.xh, g.yh, e.all_ivx, e.all_ivy, 3)
+            dx = lambda a: fd_x_4(a, g.xh)
+            dy = lambda a: fd_y_4(a, g.yh)
+        bus, bvs = I(uc), I(vc)
+        ucx, ucy, vcx, vcy = dx(uc), dy(uc), dx(vc), dy(vc)
+        btxxs, btxys, btyys = I(2*ucx - pc), I(ucy + vcx), I(2*vcy - pc)
+        L = e.v2l
+        sig = [h(fur, fvr, bu, bv, a, b, c, **kwargs) for h, fur, fvr, bu, bv, a, b, c in
+               zip(self.helpers, fur_list, fvr_list, L(bus), L(bvs), L(btxxs), L(btxys), L(btyys))]
+        self.iteration_counts = [h.iterations_last_call for h in self.helpers]
+        sx = np.concatenate([h.qfs_g.source.x for h in self.helpers])
+        sy = np.concatenate([h.qfs_g.source.y for h in self.helpers])
+        sw = np.concatenate([h.qfs_g.source.weights for h in self.helpers])
+        sg = np.column_stack(sig)
+        out = layer_apply_stokes(sx, sy, sg[0]*sw, sg[1]*sw, e.grid_pnai.x, e.grid_pnai.y)
+        fields = [uc, vc, pc]
+        bis = []
+        for k in range(3):
+            gk, bk = e.divide_pnai(out[k])
+            fields[k][e.phys_not_in_annulus] += gk
+            bis.append(bk)
+        single = len(e) == 1
+        rads = [h.correct(bu, bv, bp, single) for h, bu, bv, bp in zip(self.helpers, *bis)]
+        res = []
+        for k in range(3):
+            fk = fields[k]
+            for ebdy, r in zip(e, rads):
+                fk[ebdy.grid_ia_xind, ebdy.grid_ia_yind] = interpolate_radial_to_points(r[k], ebdy.grid_ia_r_transf,
+                                                                                        ebdy.grid_ia_t)
+            fk *= e.phys
+            res.append(np.concatenate([fk[e.phys]] + [r[k].ravel() for r in rads]))
+        return res

@@ -46,3 +46,34 @@ def manufactured(ebdyc, helmholtz_k, kk=8*np.pi/3):
     f = EmbeddedFunction(ebdyc, function=force if helmholtz_k != 0 else lap)
     ua = EmbeddedFunction(ebdyc, function=sol)
     return f, ua, sol
+
+
+def stokes_star(nb=200, M=8, ng=None):
+    """examples/interior_stokes_with_multi.py geometry: star in [-pi/2, pi/2]^2, radial spacing 0.75*grid spacing"""
+    bdy = GSB(c=star(nb, a=0.1, f=5))
+    if ng is None:
+        ng = 2*int(nb/4)
+    L = np.pi/2
+    grid = Grid([-L, L], ng, [-L, L], ng)
+    MOL = SlepianMollifier(2*M)
+    ebdy = EmbeddedBoundary(bdy, True, M, grid.xh*0.75, heaviside=MOL.step)
+    ebdyc = EmbeddedBoundaryCollection([ebdy])
+    ebdyc.register_grid(grid)
+    ebdyc.ready_bump(MOL.bump, (L - ebdy.radial_width, L - ebdy.radial_width), ebdy.radial_width)
+    return ebdyc
+
+
+def stokes_manufactured(ebdyc):
+    """examples/interior_stokes_with_multi.py:58-85"""
+    a, b, p_a, p_b = 3.0, 2.0, 2.0, 1.0
+    sin, cos = np.sin, np.cos
+    esin = lambda x: np.exp(sin(x))
+    psix = lambda x, y: esin(a*x)*cos(b*y)
+    psiy = lambda x, y: esin(a*x)*sin(b*y)
+    u_f = lambda x, y: psix(x, y)
+    v_f = lambda x, y: -a/b*cos(a*x)*psiy(x, y)
+    p_f = lambda x, y: cos(p_a*x) + esin(p_b*y)
+    fu_f = lambda x, y: (a**2*(sin(a*x) - cos(a*x)**2) + b**2)*psix(x, y) - p_a*sin(p_a*x)
+    fv_f = lambda x, y: -a*b*cos(a*x)*psiy(x, y)*(1 + (a/b)**2*sin(a*x)*(3 + sin(a*x))) + p_b*cos(p_b*y)*esin(p_b*y)
+    E = lambda f: EmbeddedFunction(ebdyc, function=f)
+    return E(fu_f), E(fv_f), E(u_f), E(v_f), E(p_f), (u_f, v_f, p_f)

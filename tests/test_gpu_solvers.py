@@ -115,3 +115,66 @@ def test_ewald_backend_three_boundaries():
     uo = oracle_for(solver, 'modified_helmholtz', 5.0, 'spectral')(f, tol=1e-13, restart=60, maxiter=5)
     linf, l2 = rel_errors(ue, uo)
     assert linf < TOL and l2 < TOL, (linf, l2)
+
+
+# ---------------------------------------------------------------------------------------------
+# Stokes
+def vector_oracle_for(solver, solver_type):
+    from oracle.solvers import OracleVectorSolver
+    pairs = [(h.interface_qfs_g, h.interface_qfs_r) for h in solver.helpers]
+    return OracleVectorSolver(solver.ebdyc, solver_type, pairs)
+
+
+@pytest.mark.parametrize('solver_type', ['spectral', 'fourth'])
+def test_stokes_single_boundary(solver_type):
+    from problems import stokes_star, stokes_manufactured
+    from ipde_b200.solvers.multi_boundary.stokes import StokesSolver
+    ebdyc = stokes_star(nb=200, M=8)
+    fu, fv, ua, va, pa, _ = stokes_manufactured(ebdyc)
+    solver = StokesSolver(ebdyc, solver_type=solver_type)
+    u, v, p = solver(fu, fv, tol=1e-13, restart=60, maxiter=4)
+    O = vector_oracle_for(solver, solver_type)
+    uo, vo, po = O(fu, fv, tol=1e-13, restart=60, maxiter=4)
+    scale = max(np.abs(uo).max(), np.abs(vo).max())
+    for got, ref, s in ((u, uo, scale), (v, vo, scale), (p, po, np.abs(po).max())):
+        linf = np.abs(np.asarray(got) - ref).max()/s
+        l2 = np.linalg.norm(np.asarray(got) - ref)/np.linalg.norm(ref)
+        assert linf < 1e-10 and l2 < 1e-10, (solver_type, linf, l2)
+    assert abs(solver.iteration_counts[0] - O.iteration_counts[0]) <= 2
+    assert u.shape == fu.shape and u[0].shape == (8, 200)
+
+
+def test_stokes_converges_to_manufactured_solution():
+    """inhomogeneous Stokes solve + homogeneous Dirichlet correction by stokeslets (MFS) reproduces the analytic
+    (u, v) of examples/interior_stokes_with_multi.py (published errs_U at nb=300: 6.65e-07, :30)"""
+    from problems import stokes_star, stokes_manufactured
+    from ipde_b200.solvers.multi_boundary.stokes import StokesSolver
+    from ipde_b200.qfs import Stokes_QFS
+    ebdyc = stokes_star(nb=300, M=12, ng=150)
+    fu, fv, ua, va, pa, (u_f, v_f, p_f) = stokes_manufactured(ebdyc)
+    solver = StokesSolver(ebdyc)
+    u, v, p = solver(fu, fv, tol=1e-13, restart=60, maxiter=4)
+    bdy = ebdyc[0].bdy
+    bu = solver.helpers[0].get_boundary_values(u[0])
+    bv = solver.helpers[0].get_boundary_values(v[0])
+    qb = Stokes_QFS(bdy, True, True, True, tol=1e-13)
+    sig = qb.u2s(np.concatenate([u_f(bdy.x, bdy.y) - bu, v_f(bdy.x, bdy.y) - bv])).reshape(2, -1)
+    pts = ebdyc.grid_and_radial_pts
+    cu, cv, cp = solver.Layer_Apply(qb.source, pts, sig)
+    err = max(np.abs(np.asarray(u) + cu - np.asarray(ua)).max(), np.abs(np.asarray(v) + cv - np.asarray(va)).max())
+    assert err < 5e-6, err
+
+
+def test_stokes_three_boundaries():
+    """multi-boundary Stokes (exercises the non-single correct() path: own-source subtraction + u2s) vs the oracle"""
+    from problems import stokes_manufactured
+    from ipde_b200.solvers.multi_boundary.stokes import StokesSolver
+    ebdyc = three_bodies(nb=100, M=8, bump=True)
+    fu, fv, ua, va, pa, _ = stokes_manufactured(ebdyc)
+    solver = StokesSolver(ebdyc)
+    u, v, p = solver(fu, fv, tol=1e-13, restart=80, maxiter=4)
+    uo, vo, po = vector_oracle_for(solver, 'spectral')(fu, fv, tol=1e-13, restart=80, maxiter=4)
+    scale = max(np.abs(uo).max(), np.abs(vo).max())
+    for got, ref, s in ((u, uo, scale), (v, vo, scale), (p, po, np.abs(po).max())):
+        linf = np.abs(np.asarray(got) - ref).max()/s
+        assert linf < 1e-9, linf
