@@ -74,6 +74,20 @@ int ipde_grid_solve_stokes(void* plan, double* fuc, double* fvc, const double* b
  * ipde/derivatives.py:25-28 (Nyquist row/column dropped by its .real): ipde/solvers/multi_boundary/vector.py:68-73 */
 int ipde_grid_stokes_stress(void* plan, const double* uh, const double* vh, const double* ph, double* txx, double* txy,
                             double* tyy, void* stream);
+/* ---- slab-decomposed periodic grid (one slab of rows per rank; ipde_b200/distributed.py).  The same fft2 /
+ *      symbol / ifft2 as ipde_grid_solve_scalar, split at the two all-to-all transposes. */
+/* real rows (batch, in_pitch doubles) <-> half-complex rows (batch, out_pitch complex); plan: ipde_fft_plan_create(n/2) */
+int ipde_fft_r2c_rows(void* plan, const double* in, double* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
+                      void* stream);
+int ipde_fft_c2r_rows(void* plan, const double* in, double* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
+                      double scale, void* stream);
+/* (rows, P) -> (R, rows, Pc) column blocks, zero padded past P, and back */
+int ipde_slab_pack(const double* in, int64_t rows, int64_t P, int R, int64_t Pc, double* out, void* stream);
+int ipde_slab_unpack(const double* in, int64_t rows, int64_t P, int R, int64_t Pc, double* out, void* stream);
+/* column FFT + symbol + inverse column FFT on a block of columns [col_offset, col_offset + Pc) of the global
+ * half spectrum; plan = ipde_grid_plan_create(nx, 2*(Pc-1), xh, yh) */
+int ipde_grid_cols_symbol_slab(void* plan, double* spec_in, double* spec_out, double* spec_copy, int copy_mode, int kind,
+                               double k, int ny_global, double yh, int col_offset, void* stream);
 /* 4th-order centred differences, zero in the 2-cell border: ipde/derivatives.py:3-23 */
 int ipde_grid_fd4(void* plan, const double* f, double* fx, double* fy, void* stream);
 /* periodic cubic interpolation to points: fast_interp.interp2d(k=3) at ipde/ebdy_collection.py:594-603 */

@@ -185,6 +185,25 @@ int ipde_grid_stokes_stress(void* plan, const double* uh, const double* vh, cons
                             double* tyy, void* stream) {
     return grid_stokes_stress((GridPlan*)plan, CP(uh), CP(vh), CP(ph), MP(txx), MP(txy), MP(tyy), ST(stream));
 }
+// ---- slab-decomposed grid (ipde_b200/distributed.py)
+int ipde_fft_r2c_rows(void* plan, const double* in, double* out, int64_t batch, int64_t in_pitch, int64_t out_pitch, void* stream) {
+    return fft_r2c_rows((FftPlan*)plan, in, MP(out), batch, in_pitch, out_pitch, ST(stream));
+}
+int ipde_fft_c2r_rows(void* plan, const double* in, double* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
+                      double scale, void* stream) {
+    return fft_c2r_rows((FftPlan*)plan, CP(in), out, batch, in_pitch, out_pitch, scale, ST(stream));
+}
+int ipde_slab_pack(const double* in, int64_t rows, int64_t P, int R, int64_t Pc, double* out, void* stream) {
+    return grid_slab_pack(CP(in), rows, P, R, Pc, MP(out), ST(stream));
+}
+int ipde_slab_unpack(const double* in, int64_t rows, int64_t P, int R, int64_t Pc, double* out, void* stream) {
+    return grid_slab_unpack(CP(in), rows, P, R, Pc, MP(out), ST(stream));
+}
+int ipde_grid_cols_symbol_slab(void* plan, double* spec_in, double* spec_out, double* spec_copy, int copy_mode, int kind,
+                               double k, int ny_global, double yh, int col_offset, void* stream) {
+    return grid_cols_symbol_slab((GridPlan*)plan, MP(spec_in), MP(spec_out), MP(spec_copy), copy_mode, kind, k, ny_global, yh,
+                                 col_offset, ST(stream));
+}
 int ipde_grid_fd4(void* plan, const double* f, double* fx, double* fy, void* stream) {
     return grid_fd4((GridPlan*)plan, f, fx, fy, ST(stream));
 }

@@ -320,7 +320,7 @@ int ewald_apply(EwaldPlan* p, const double* q, double* grid_out, double* point_o
     int rc = fft_r2c_rows(G->row, p->Sw, p->spec, G->nx, G->ny, G->pitch, st);
     if (rc) return rc;
     ColMult MU, MH;
-    MU.kind = 3; MU.k2c = 0.0; MU.table = p->multU; MU.fmul = 1;
+    MU.kind = 3; MU.k2c = 0.0; MU.table = p->multU; MU.fmul = 1; MU.ny = 0; MU.col_offset = 0;
     MH = MU; MH.table = p->multH;
     // first field: forward columns, symbol, inverse columns in one pass (the plain 2-D spectrum is kept in
     // p->spec when a second field follows); second field: symbol + inverse columns from that copy

@@ -134,7 +134,7 @@ k_cols_mult(FftPlanDev P, const cplx* in, cplx* out, cplx* copy, int64_t elem_st
             } else {
                 const int fi = o + M.fmul * e;                                   // frequency index along x
                 const int si = (fi < (M.nx + 1) / 2) ? fi : fi - M.nx;
-                const int jy = (int)c0 + c;
+                const int jy = (int)c0 + c + M.col_offset;
                 const double kx = TWO_PI * (double)si / ((double)M.nx * M.xh);
                 const double ky = TWO_PI * (double)jy / ((double)M.ny * M.yh);
                 if (M.kind == IPDE_KIND_POISSON) m = (fi == 0 && jy == 0) ? 0.0 : -1.0 / (kx * kx + ky * ky);
@@ -206,7 +206,8 @@ int grid_cols_symbol(GridPlan* g, cplx* spec_in, cplx* spec_out, cplx* spec_copy
                      cudaStream_t st) {
     const int64_t P = g->pitch;
     ColMult M = M0;
-    M.nx = g->nx; M.ny = g->ny; M.xh = g->xh; M.yh = g->yh;
+    M.nx = g->nx; M.xh = g->xh;
+    if (M.ny <= 0) { M.ny = g->ny; M.yh = g->yh; M.col_offset = 0; }
     if (!spec_copy) copy_mode = 0;
     if (g->n2 == 1) {
         M.fmul = 1;
@@ -224,7 +225,8 @@ int grid_cols_symbol(GridPlan* g, cplx* spec_in, cplx* spec_out, cplx* spec_copy
 int grid_cols_symbol_inverse(GridPlan* g, const cplx* spec2d, cplx* spec_out, const ColMult& M0, cudaStream_t st) {
     const int64_t P = g->pitch;
     ColMult M = M0;
-    M.nx = g->nx; M.ny = g->ny; M.xh = g->xh; M.yh = g->yh;
+    M.nx = g->nx; M.xh = g->xh;
+    if (M.ny <= 0) { M.ny = g->ny; M.yh = g->yh; M.col_offset = 0; }
     if (g->n2 == 1) {
         M.fmul = 1;
         return cols_mult(g->colA, spec2d, spec_out, nullptr, P, P, 1, 0, 0, 0, M, st);
@@ -242,7 +244,7 @@ int grid_solve_scalar_fused(GridPlan* g, int kind, double k, const double* fc, c
     if (rc) return rc;
     if (grid_fused_ok(g)) {
         ColMult M;
-        M.kind = kind; M.k2c = k * k; M.table = nullptr; M.fmul = 1;
+        M.kind = kind; M.k2c = k * k; M.table = nullptr; M.fmul = 1; M.ny = 0; M.col_offset = 0;
         rc = grid_cols_symbol(g, uch, spec_work, uch, 2, M, st);
         if (rc) return rc;
     } else {
@@ -540,4 +542,45 @@ int grid_stokes_stress(GridPlan* g, const cplx* uh, const cplx* vh, const cplx* 
                                                              g->xh, g->yh);
     KERNEL_CHECK();
     return IPDE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// slab decomposition helpers
+__global__ void k_slab_pack(const cplx* __restrict__ in, int64_t rows, int64_t P, int R, int64_t Pc, cplx* __restrict__ out) {
+    const int64_t total = (int64_t)R * rows * Pc;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t kc = t % Pc, l = (t / Pc) % rows, q = t / (Pc * rows);
+        const int64_t k = q * Pc + kc;
+        out[t] = (k < P) ? in[l * P + k] : make_double2(0.0, 0.0);
+    }
+}
+__global__ void k_slab_unpack(const cplx* __restrict__ in, int64_t rows, int64_t P, int R, int64_t Pc, cplx* __restrict__ out) {
+    const int64_t total = rows * P;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = t % P, l = t / P;
+        const int64_t q = k / Pc, kc = k - q * Pc;
+        out[t] = in[(q * rows + l) * Pc + kc];
+    }
+}
+int grid_slab_pack(const cplx* in, int64_t rows, int64_t P, int R, int64_t Pc, cplx* out, cudaStream_t st) {
+    const int64_t total = (int64_t)R * rows * Pc;
+    KERNEL_TAG("k_slab_pack", 16.0 * (double)(rows * P) + 16.0 * (double)total);
+    k_slab_pack<<<grid_blocks(total, 256), 256, 0, st>>>(in, rows, P, R, Pc, out);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+int grid_slab_unpack(const cplx* in, int64_t rows, int64_t P, int R, int64_t Pc, cplx* out, cudaStream_t st) {
+    const int64_t total = rows * P;
+    KERNEL_TAG("k_slab_unpack", 32.0 * (double)total);
+    k_slab_unpack<<<grid_blocks(total, 256), 256, 0, st>>>(in, rows, P, R, Pc, out);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+int grid_cols_symbol_slab(GridPlan* g, cplx* spec_in, cplx* spec_out, cplx* spec_copy, int copy_mode, int kind, double k,
+                          int ny_global, double yh, int col_offset, cudaStream_t st) {
+    ARG_CHECK(grid_fused_ok(g), "column length of the slab plan is not supported by the fused column pass");
+    ColMult M;
+    M.kind = kind; M.k2c = k * k; M.table = nullptr; M.fmul = 1;
+    M.ny = ny_global; M.yh = yh; M.col_offset = col_offset;
+    return grid_cols_symbol(g, spec_in, spec_out, spec_copy, copy_mode, M, st);
 }

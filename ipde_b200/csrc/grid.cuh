@@ -46,6 +46,7 @@ struct ColMult {
     double xh, yh;
     int fmul;             // frequency index along x of element e of outer line o: o + fmul*e
     const double* table;  // kind 3: one real per spectrum entry, same layout as the spectrum
+    int col_offset;       // global index of column 0 (slab-decomposed grids hold a block of columns)
 };
 int grid_cols_symbol(GridPlan* g, cplx* spec_in, cplx* spec_out, cplx* spec_copy, int copy_mode, const ColMult& M,
                      cudaStream_t st);
@@ -54,3 +55,11 @@ int grid_solve_scalar_fused(GridPlan* g, int kind, double k, const double* fc, c
                             cudaStream_t st);
 int grid_stokes_stress(GridPlan* g, const cplx* uh, const cplx* vh, const cplx* ph, cplx* txx, cplx* txy, cplx* tyy,
                        cudaStream_t st);
+
+// ---- slab decomposition (ipde_b200/distributed.py): a rank holds `rows` rows of a half spectrum of pitch P; the
+// all-to-all transpose sends column block q (Pc columns, zero padded past P) to rank q.
+int grid_slab_pack(const cplx* in, int64_t rows, int64_t P, int R, int64_t Pc, cplx* out, cudaStream_t st);
+int grid_slab_unpack(const cplx* in, int64_t rows, int64_t P, int R, int64_t Pc, cplx* out, cudaStream_t st);
+// column pass of a column slab: plan g has nx = global nx and pitch == Pc; ky is taken from the global grid
+int grid_cols_symbol_slab(GridPlan* g, cplx* spec_in, cplx* spec_out, cplx* spec_copy, int copy_mode, int kind, double k,
+                          int ny_global, double yh, int col_offset, cudaStream_t st);

@@ -1,0 +1,155 @@
+"""
+Slab-decomposed periodic grid solve across the GPUs of one box.
+
+The reference has no multi-process code; what is distributed here is its `_grid_solve`
+(ipde/solvers/multi_boundary/modified_helmholtz.py:40-46, poisson.py:30-38): rank p owns rows
+[p nx/R, (p+1) nx/R) of every (nx, ny) grid field.
+
+    local real rows -> half-complex rows        k_r2c_rows
+    pack column blocks                          k_slab_pack            (rows, P) -> (R, rows, Pc)
+    all-to-all                                  NCCL over NVLink (torch.distributed.all_to_all_single)
+    column FFT + symbol + inverse column FFT    k_fft_cols / k_cols_mult on the (nx, Pc) column slab
+    all-to-all back                             NCCL
+    unpack, half-complex rows -> real rows      k_slab_unpack, k_c2r_rows
+
+Two all-to-alls per scalar solve, each moving 16 B * (nx/R) * Pc to every peer.  The received blocks are already the
+column slab in row order (rank q' sends rows q' nx/R ...), so only the sending side of the forward transpose and the
+receiving side of the backward one need a pack/unpack pass.
+
+`SlabLayout` holds the index arithmetic with NumPy stand-ins for the local transforms, so the partition/exchange
+logic is tested on CPU with the gloo backend (tests/test_distributed.py); `SlabGridSolver` is the device path.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class SlabLayout(object):
+    def __init__(self, nx, ny, world, rank):
+        if nx % world:
+            raise Exception('slab decomposition needs nx divisible by the number of ranks')
+        self.nx, self.ny, self.R, self.rank = nx, ny, world, rank
+        self.rows = nx//world
+        self.row0 = rank*self.rows
+        self.P = ny//2 + 1
+        self.Pc = -(-self.P//world)
+        if self.Pc < 3:
+            self.Pc = 3
+        self.col0 = rank*self.Pc
+
+    # NumPy statements of the pack / unpack passes (the CUDA kernels are checked against these)
+    def pack(self, spec_rows):
+        out = np.zeros((self.R, self.rows, self.Pc), dtype=complex)
+        for q in range(self.R):
+            a, b = q*self.Pc, min(self.P, (q + 1)*self.Pc)
+            if b > a:
+                out[q, :, :b - a] = spec_rows[:, a:b]
+        return out
+
+    def unpack(self, blocks):
+        out = np.empty((self.rows, self.P), dtype=complex)
+        for q in range(self.R):
+            a, b = q*self.Pc, min(self.P, (q + 1)*self.Pc)
+            if b > a:
+                out[:, a:b] = blocks[q, :, :b - a]
+        return out
+
+
+def exchange(send, recv, group=None):
+    """all-to-all of equal contiguous blocks along dim 0; NCCL collective on the device, point-to-point on gloo"""
+    if dist.get_backend(group) == 'nccl':
+        dist.all_to_all_single(recv, send, group=group)
+        return
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    reqs = []
+    for q in range(world):
+        if q == rank:
+            recv[q].copy_(send[q])
+        else:
+            reqs.append(dist.isend(send[q].contiguous(), q, group=group))
+            reqs.append(dist.irecv(recv[q], q, group=group))
+    for r in reqs:
+        r.wait()
+
+
+def slab_grid_solve_numpy(layout, f_local, symbol, group=None):
+    """CPU statement of the distributed solve (NumPy local transforms + the same exchanges): returns the local rows of
+    Re ifft2(symbol * fft2(f)).  `symbol(kx_index_array, ky_index_array)` gives the real multiplier."""
+    L = layout
+    spec = np.fft.rfft(f_local, axis=1)                                   # (rows, P)
+    send = torch.from_numpy(L.pack(spec))
+    recv = torch.empty_like(send)
+    exchange(send, recv, group)
+    cols = recv.numpy().reshape(L.nx, L.Pc)                               # column slab, rows in global order
+    ch = np.fft.fft(cols, axis=0)
+    j = L.col0 + np.arange(L.Pc)
+    valid = j < L.P
+    m = np.zeros((L.nx, L.Pc))
+    m[:, valid] = symbol(np.arange(L.nx)[:, None], j[valid][None, :])
+    back = np.fft.ifft(ch*m, axis=0)
+    send2 = torch.from_numpy(np.ascontiguousarray(back.reshape(L.R, L.rows, L.Pc)))
+    recv2 = torch.empty_like(send2)
+    exchange(send2, recv2, group)
+    return np.fft.irfft(L.unpack(recv2.numpy()), n=L.ny, axis=1)
+
+
+class SlabGridSolver(object):
+    """
+    Device path.  kind: 0 Poisson (zero mode -> 0; the caller demeans), 1 modified Helmholtz.
+    solve(f_local (rows, ny) float64 cuda) -> u_local (rows, ny); timings of the stages are kept in `last_ms`
+    when `timed=True` (CUDA events on the current stream).
+    """
+    def __init__(self, nx, ny, xh, yh, kind, k, group=None):
+        import ctypes
+        from ._lib import lib
+        from .device import require_cuda, empty, C128
+        require_cuda()
+        self.group = group
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.L = SlabLayout(nx, ny, world, rank)
+        self.nx, self.ny, self.xh, self.yh, self.kind, self.k = nx, ny, float(xh), float(yh), int(kind), float(k)
+        L_ = lib()
+        self.row_plan = ctypes.c_void_p()
+        L_.ipde_fft_plan_create(ny//2, ctypes.byref(self.row_plan))
+        self.col_plan = ctypes.c_void_p()
+        L_.ipde_grid_plan_create(nx, 2*(self.L.Pc - 1), float(xh), float(yh), ctypes.byref(self.col_plan))
+        Ls = self.L
+        self.spec = empty((Ls.rows, Ls.P), C128)
+        self.send = empty((Ls.R, Ls.rows, Ls.Pc), C128)
+        self.recv = empty((Ls.R, Ls.rows, Ls.Pc), C128)
+        self.work = empty((Ls.R, Ls.rows, Ls.Pc), C128)
+        self.alltoall_bytes_per_rank = 2*16*Ls.rows*Ls.Pc*(Ls.R - 1)
+
+    def __del__(self):
+        try:
+            from ._lib import lib
+            lib().ipde_fft_plan_destroy(self.row_plan)
+            lib().ipde_grid_plan_destroy(self.col_plan)
+        except Exception:
+            pass
+
+    def solve(self, f_local, out=None):
+        from ._lib import lib
+        from .device import ptr, stream, empty
+        L_, Ls, st = lib(), self.L, stream()
+        if out is None:
+            out = empty((Ls.rows, self.ny))
+        L_.ipde_fft_r2c_rows(self.row_plan, ptr(f_local), ptr(self.spec), Ls.rows, self.ny, Ls.P, st)
+        if Ls.R > 1:
+            L_.ipde_slab_pack(ptr(self.spec), Ls.rows, Ls.P, Ls.R, Ls.Pc, ptr(self.send), st)
+            exchange(self.send, self.recv, self.group)
+        else:
+            L_.ipde_slab_pack(ptr(self.spec), Ls.rows, Ls.P, 1, Ls.Pc, ptr(self.recv), st)
+        # column slab (nx, Pc): forward columns, symbol, inverse columns
+        L_.ipde_grid_cols_symbol_slab(self.col_plan, ptr(self.recv), ptr(self.work), 0, 0, self.kind, self.k, self.ny,
+                                      self.yh, Ls.col0, st)
+        if Ls.R > 1:
+            exchange(self.work, self.send, self.group)
+            back = self.send
+        else:
+            back = self.work
+        L_.ipde_slab_unpack(ptr(back), Ls.rows, Ls.P, Ls.R, Ls.Pc, ptr(self.spec), st)
+        L_.ipde_fft_c2r_rows(self.row_plan, ptr(self.spec), ptr(out), Ls.rows, Ls.P, self.ny,
+                             2.0/(float(self.nx)*float(self.ny)), st)
+        return out
