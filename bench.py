@@ -11,8 +11,10 @@ forcing (= Nx*Ny grid-point-solves).  metric = grid-point-solves/s.
 
   value   whole job, inputs already resident in HBM (solver.solve_device), CUDA-event timed
   e2e     the same through the public API solver(f) with host arrays: H2D of f and D2H of u inside the timing
-  N > 1   every rank runs its own forcing on its own replica of the problem (no data-path collective,
-          "scaling": "weak"); the slab-decomposed single-solve path is DESIGN.md "next".
+  N > 1   `value`: every rank solves its own forcing on its own copy of the problem (independent solves are the
+          unit that shards without a data-path collective: "scaling": "weak").  `slab_grid_solve`: ONE 16384^2
+          periodic grid solve slab-decomposed over all ranks with NCCL all-to-all transposes (strong scaling of
+          the FFT core, ipde_b200/distributed.py).
   --impl reference   the CPU path (oracle port of the reference's NumPy/SciPy algorithm; the reference itself
           cannot run: pybie2d/qfs/near_finder/finufft are not installable here) on a bounded sample.
 """
@@ -196,9 +198,11 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ipde_b200')
-    ap.add_argument('--n', type=int, default=2048, help='background grid points per side')
+    ap.add_argument('--grid', '--n', dest='n', type=int, default=2048, help='background grid points per side')
     ap.add_argument('--cpu-sample-n', type=int, default=256)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--slab-grid', type=int, default=16384,
+                    help='grid size of the slab-decomposed (all ranks, one problem) grid-solve timing; 0 = skip')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -279,6 +283,38 @@ def main():
     buf = ctypes.create_string_buffer(1 << 16)
     lib().ipde_profile_stop(buf, len(buf))
     prof = parse_profile(buf.value.decode())
+    gmres_its = solver.iteration_counts
+
+    # ---- one problem over all ranks: slab-decomposed periodic grid solve (NCCL all-to-all transposes)
+    slab = None
+    if args.slab_grid > 0 and args.slab_grid % world == 0:
+        from ipde_b200.distributed import SlabGridSolver
+        ns = args.slab_grid
+        del solver, res
+        torch.cuda.empty_cache()
+        S = SlabGridSolver(ns, ns, 2.4/ns, 2.4/ns, 1, HELMHOLTZ_K)
+        gen = torch.Generator(device='cuda')
+        gen.manual_seed(rank)
+        fl = torch.randn((S.L.rows, ns), dtype=torch.float64, device='cuda', generator=gen)
+        out = torch.empty_like(fl)
+        for _ in range(3):
+            S.solve(fl, out=out)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            S.solve(fl, out=out)
+        s1.record()
+        barrier()
+        tt = torch.tensor([s0.elapsed_time(s1)/args.steps], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        slab = {'what': 'periodic grid solve (r2c rows, all-to-all, column FFT + symbol + inverse, all-to-all, c2r rows) '
+                        'of ONE %d^2 grid slab-decomposed over all ranks; strong scaling of the FFT core' % ns,
+                'grid': [ns, ns], 'n_gpus': world, 'ms_per_solve': float(tt[0]),
+                'grid_point_solves_per_s': ns*ns/(float(tt[0])*1e-3),
+                'alltoall_bytes_per_rank_per_solve': int(S.alltoall_bytes_per_rank)}
+        del S, fl, out
 
     times = torch.tensor([ms_total, e2e_s*1e3], dtype=torch.float64, device='cuda')
     if world > 1:
@@ -317,7 +353,7 @@ def main():
                            'nb=%d, M=16, k=2, spectral interface interpolation, annular GMRES tol 1e-12, '
                            'spectral-Ewald evaluation of the layer sums' % (args.n, nb),
                            'grid': [args.n, args.n], 'n_boundary': nb, 'dof': int(ebdyc.dof),
-                           'gmres_iterations': solver.iteration_counts, 'setup_s': t_setup,
+                           'gmres_iterations': gmres_its, 'setup_s': t_setup,
                            'l2': 'inputs larger than L2: every step streams ~%.1f GB of grid-sized arrays '
                                  '(126 MB L2); no flush between steps' % (npts*8*40/1e9)
                                  if npts*8*40 > 4*126e6 else 'working set comparable to L2 (126 MB) at this size'},
@@ -327,6 +363,8 @@ def main():
                         'ms_per_step': e2e_ms/args.steps,
                         'api': 'ModifiedHelmholtzSolver.__call__(EmbeddedFunction) -> EmbeddedFunction, pinned staging'},
                 'roofline': roofline}
+        if slab is not None:
+            line['slab_grid_solve'] = slab
         if not args.no_cpu_baseline and world == 1:
             rate, dt, nbs = cpu_solve_rate(args.cpu_sample_n, 1)
             line['cpu_baseline'] = {'value': rate, 'unit': 'grid-point-solves/s', 'cores': os.cpu_count(),

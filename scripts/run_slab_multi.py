@@ -1,6 +1,6 @@
 """Multi-GPU check + timing of the slab-decomposed grid solve.  Launch:
    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
-       scripts/run_slab_multi.py --n 8192 [--check]
+       scripts/run_slab_multi.py --grid 8192 [--check]
 Every rank holds its slab of a seeded random forcing; --check gathers the result on rank 0 and compares with NumPy
 (small n only).  Timing: CUDA events, max over ranks."""
 import argparse, json, os, sys
@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'
 import numpy as np, torch, torch.distributed as dist
 
 ap = argparse.ArgumentParser()
-ap.add_argument('--n', type=int, default=4096)
+ap.add_argument('--grid', '--n', dest='n', type=int, default=4096)
 ap.add_argument('--steps', type=int, default=10)
 ap.add_argument('--check', action='store_true')
 a = ap.parse_args()
