@@ -39,6 +39,10 @@ struct EwaldPlan {
     cplx *spec = nullptr, *specw = nullptr;
     int64_t n_og = 0;
     int64_t *og_lin = nullptr, *og_out = nullptr, *og_loc = nullptr;
+    unsigned* tile_mask = nullptr;
+    int in_lo = 0, in_hi = 0;            // rows of S_w that can be nonzero (active tiles)
+    int grid_lo = 0, grid_hi = 0;        // rows holding grid targets
+    int pts_lo = 0, pts_hi = 0;          // rows touched by the gather windows of the point targets   // 256 bits per tile: which nodes are grid targets (need the local sum)
     int64_t n_pt = 0;
     double *ptx = nullptr, *pty = nullptr;
 };
@@ -82,7 +86,7 @@ k_ewald_tiles(const int* __restrict__ tile_ix, const int* __restrict__ tile_iy, 
               const int* __restrict__ tile_src, const double* __restrict__ sx, const double* __restrict__ sy,
               const double* __restrict__ q, EwaldTab T, double x0, double y0, double h, double rc2, double rw2,
               double two_xi2, double norm, int px, int py, double* __restrict__ Sw, double* __restrict__ Lc,
-              int want_local) {
+              const unsigned* __restrict__ tile_mask, int want_local) {
     __shared__ double shx[EW_CHUNK], shy[EW_CHUNK], shq[EW_CHUNK];
     __shared__ double sS[EW_MAX_TAB], sA[EW_MAX_TAB];
     const int tid = threadIdx.y * EW_TILE + threadIdx.x;
@@ -94,6 +98,8 @@ k_ewald_tiles(const int* __restrict__ tile_ix, const int* __restrict__ tile_iy, 
     const double x = x0 + ix * h, y = y0 + iy * h;
     const int s0 = tile_ptr[t], s1 = tile_ptr[t + 1];
     double spread = 0.0, loc = 0.0;
+    // the local sum is only needed at nodes that are grid targets
+    if (want_local && tile_mask) want_local = (tile_mask[t * 8 + (tid >> 5)] >> (tid & 31)) & 1u;
     for (int base = s0; base < s1; base += EW_CHUNK) {
         const int cnt = min(EW_CHUNK, s1 - base);
         __syncthreads();
@@ -112,6 +118,13 @@ k_ewald_tiles(const int* __restrict__ tile_ix, const int* __restrict__ tile_iy, 
     }
     if (ix < px && iy < py) Sw[(int64_t)ix * py + iy] = spread * norm;
     if (want_local) Lc[(int64_t)t * (EW_TILE * EW_TILE) + tid] = loc;
+}
+
+__global__ void k_ewald_build_mask(const int64_t* __restrict__ loc, int64_t n, unsigned* __restrict__ mask) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t l = loc[i];
+        if (l >= 0) atomicOr(&mask[l >> 5], 1u << (unsigned)(l & 31));
+    }
 }
 
 // multiplier tables on the half spectrum (plan row order)
@@ -250,6 +263,13 @@ int ewald_plan_create(int kind, double kappa, double xi, double h, double rc, in
     EW_UP(upload_arr(&p->tile_src, tile_src_host, (size_t)tile_ptr_host[ntiles], cudaMemcpyHostToDevice))
     EW_UP(upload_arr(&p->tile_map, tile_map_host, (size_t)p->ntx * p->nty, cudaMemcpyHostToDevice))
 #undef EW_UP
+    p->in_lo = px; p->in_hi = 0;
+    for (int t = 0; t < ntiles; ++t) {
+        p->in_lo = std::min(p->in_lo, tile_ix_host[t] * EW_TILE);
+        p->in_hi = std::max(p->in_hi, std::min(px, (tile_ix_host[t] + 1) * EW_TILE));
+    }
+    if (p->in_hi <= p->in_lo) { p->in_lo = 0; p->in_hi = px; }
+    p->grid_lo = 0; p->grid_hi = px; p->pts_lo = 0; p->pts_hi = px;
     const size_t nreal = (size_t)px * py, nspec = (size_t)px * (py / 2 + 1);
     CUDA_TRY(cudaMalloc(&p->Sw, sizeof(double) * nreal));
     CUDA_TRY(cudaMemset(p->Sw, 0, sizeof(double) * nreal));
@@ -276,6 +296,7 @@ void ewald_plan_destroy(EwaldPlan* p) {
     cudaFree(p->multH); cudaFree(p->multU); cudaFree(p->Sw); cudaFree(p->R); cudaFree(p->Lc);
     cudaFree(p->spec); cudaFree(p->specw);
     cudaFree(p->og_lin); cudaFree(p->og_out); cudaFree(p->og_loc); cudaFree(p->ptx); cudaFree(p->pty);
+    cudaFree(p->tile_mask);
     delete p;
 }
 
@@ -286,7 +307,26 @@ int ewald_set_grid_targets(EwaldPlan* p, int64_t n, const int64_t* lin_dev, cons
     int rc = upload_arr(&p->og_lin, lin_dev, (size_t)n, cudaMemcpyDeviceToDevice);
     if (!rc) rc = upload_arr(&p->og_loc, loc_dev, (size_t)n, cudaMemcpyDeviceToDevice);
     if (!rc) rc = upload_arr(&p->og_out, out_pos_dev, (size_t)n, cudaMemcpyDeviceToDevice);
-    return rc;
+    if (rc) return rc;
+    p->grid_lo = 0; p->grid_hi = p->px;
+    if (n > 0) {
+        std::vector<int64_t> h((size_t)n);
+        CUDA_TRY(cudaMemcpy(h.data(), lin_dev, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost));
+        int64_t lo = h[0], hi = h[0];
+        for (int64_t i = 1; i < n; ++i) { lo = std::min(lo, h[i]); hi = std::max(hi, h[i]); }
+        p->grid_lo = (int)(lo / p->py);
+        p->grid_hi = (int)(hi / p->py) + 1;
+    }
+    cudaFree(p->tile_mask);
+    p->tile_mask = nullptr;
+    if (n > 0 && p->ntiles > 0) {
+        CUDA_TRY(cudaMalloc(&p->tile_mask, sizeof(unsigned) * 8 * (size_t)p->ntiles));
+        CUDA_TRY(cudaMemset(p->tile_mask, 0, sizeof(unsigned) * 8 * (size_t)p->ntiles));
+        k_ewald_build_mask<<<(int)std::min<int64_t>(cdiv(n, 256), 4096), 256>>>(p->og_loc, n, p->tile_mask);
+        KERNEL_CHECK();
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
+    return IPDE_OK;
 }
 
 int ewald_set_point_targets(EwaldPlan* p, int64_t n, const double* tx_dev, const double* ty_dev) {
@@ -295,7 +335,17 @@ int ewald_set_point_targets(EwaldPlan* p, int64_t n, const double* tx_dev, const
     p->n_pt = n;
     int rc = upload_arr(&p->ptx, tx_dev, (size_t)n, cudaMemcpyDeviceToDevice);
     if (!rc) rc = upload_arr(&p->pty, ty_dev, (size_t)n, cudaMemcpyDeviceToDevice);
-    return rc;
+    if (rc) return rc;
+    p->pts_lo = 0; p->pts_hi = p->px;
+    if (n > 0) {
+        std::vector<double> h((size_t)n);
+        CUDA_TRY(cudaMemcpy(h.data(), tx_dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+        double lo = h[0], hi = h[0];
+        for (int64_t i = 1; i < n; ++i) { lo = std::min(lo, h[i]); hi = std::max(hi, h[i]); }
+        p->pts_lo = std::max(0, (int)floor((lo - p->x0) / p->h) - p->m - 1);
+        p->pts_hi = std::min(p->px, (int)ceil((hi - p->x0) / p->h) + p->m + 2);
+    }
+    return IPDE_OK;
 }
 
 int ewald_apply(EwaldPlan* p, const double* q, double* grid_out, double* point_out, int accumulate_points, cudaStream_t st) {
@@ -312,21 +362,27 @@ int ewald_apply(EwaldPlan* p, const double* q, double* grid_out, double* point_o
         KERNEL_TAG("k_ewald_tiles", 16.0 * 256.0 * (double)p->ntiles);
         k_ewald_tiles<<<p->ntiles, dim3(EW_TILE, EW_TILE), 0, st>>>(p->tile_ix, p->tile_iy, p->tile_ptr, p->tile_src, p->sx,
                                                                    p->sy, q, T, p->x0, p->y0, p->h, p->rc2, p->rw2, two_xi2,
-                                                                   ck * wnorm, p->px, p->py, p->Sw, p->Lc, want_grid ? 1 : 0);
+                                                                   ck * wnorm, p->px, p->py, p->Sw, p->Lc, p->tile_mask,
+                                                                   want_grid ? 1 : 0);
         KERNEL_CHECK();
     }
     GridPlan* G = p->fft;
     const double c2r_scale = 1.0 / ((double)G->nx * (double)G->ny) * 2.0;
-    int rc = fft_r2c_rows(G->row, p->Sw, p->spec, G->nx, G->ny, G->pitch, st);
+    // zero padding: only rows [in_lo, in_hi) of S_w are nonzero, only the target rows of the result are needed
+    const int out_lo = want_grid ? p->grid_lo : p->pts_lo, out_hi = want_grid ? p->grid_hi : p->pts_hi;
+    const int win1[4] = {p->in_lo, p->in_hi, out_lo, out_hi};
+    int rc = fft_r2c_rows(G->row, p->Sw + (size_t)p->in_lo * G->ny, p->spec + (size_t)p->in_lo * G->pitch, p->in_hi - p->in_lo,
+                          G->ny, G->pitch, st);
     if (rc) return rc;
     ColMult MU, MH;
     MU.kind = 3; MU.k2c = 0.0; MU.table = p->multU; MU.fmul = 1; MU.ny = 0; MU.col_offset = 0;
     MH = MU; MH.table = p->multH;
     // first field: forward columns, symbol, inverse columns in one pass (the plain 2-D spectrum is kept in
     // p->spec when a second field follows); second field: symbol + inverse columns from that copy
-    rc = grid_cols_symbol(G, p->spec, p->specw, (want_grid && want_pts) ? p->spec : nullptr, 1, want_grid ? MU : MH, st);
+    rc = grid_cols_symbol(G, p->spec, p->specw, (want_grid && want_pts) ? p->spec : nullptr, 1, want_grid ? MU : MH, st, win1);
     if (rc) return rc;
-    rc = fft_c2r_rows(G->row, p->specw, p->R, G->nx, G->pitch, G->ny, c2r_scale, st);
+    rc = fft_c2r_rows(G->row, p->specw + (size_t)out_lo * G->pitch, p->R + (size_t)out_lo * G->ny, out_hi - out_lo, G->pitch,
+                      G->ny, c2r_scale, st);
     if (rc) return rc;
     if (want_grid) {
         const int gb = (int)std::min<int64_t>(cdiv(p->n_og, 256), (int64_t)ipde_num_sms() * 8);
@@ -335,8 +391,10 @@ int ewald_apply(EwaldPlan* p, const double* q, double* grid_out, double* point_o
     }
     if (want_pts) {
         if (want_grid) {
-            rc = grid_cols_symbol_inverse(G, p->spec, p->specw, MH, st);
-            if (!rc) rc = fft_c2r_rows(G->row, p->specw, p->R, G->nx, G->pitch, G->ny, c2r_scale, st);
+            const int win2[2] = {p->pts_lo, p->pts_hi};
+            rc = grid_cols_symbol_inverse(G, p->spec, p->specw, MH, st, win2);
+            if (!rc) rc = fft_c2r_rows(G->row, p->specw + (size_t)p->pts_lo * G->pitch, p->R + (size_t)p->pts_lo * G->ny,
+                                       p->pts_hi - p->pts_lo, G->pitch, G->ny, c2r_scale, st);
             if (rc) return rc;
         }
         const int pb = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(p->n_pt * 32, 256), (int64_t)ipde_num_sms() * 16));

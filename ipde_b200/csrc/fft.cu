@@ -169,11 +169,13 @@ k_fft_rows(FftPlanDev P, const cplx* __restrict__ in, cplx* __restrict__ out, in
 template <int EPT, int CLS, int NT>
 __global__ void __launch_bounds__(NT, (NT <= 256) ? 2 : 1)
 k_fft_cols(FftPlanDev P, const cplx* __restrict__ in, cplx* __restrict__ out, int64_t elem_stride, int64_t n_inner,
-           int64_t outer_stride, int C, int logC, int sign, double scale, int tw_mode, const cplx* __restrict__ tw_big) {
+           int64_t outer_stride, int C, int logC, int sign, double scale, int tw_mode, const cplx* __restrict__ tw_big,
+           RowWindow W) {
     extern __shared__ cplx smem[];
     const int n = P.n, tid = threadIdx.x, nt = blockDim.x;
     const int64_t tiles = (n_inner + C - 1) >> logC;
     const int o = (int)(blockIdx.x / tiles);
+    const int row_base = o * W.row_o;
     const int64_t c0 = (blockIdx.x - (int64_t)o * tiles) << logC;
     const int cw = (int)min((int64_t)C, n_inner - c0);
     const int64_t base = (int64_t)o * outer_stride + c0;
@@ -181,7 +183,8 @@ k_fft_cols(FftPlanDev P, const cplx* __restrict__ in, cplx* __restrict__ out, in
     for (int i = tid; i < total; i += nt) {
         const int c = i & (C - 1), e = i >> logC;
         cplx v = make_double2(0.0, 0.0);
-        if (c < cw) {
+        const int row = row_base + e * W.row_e;
+        if (c < cw && row >= W.in_lo && row < W.in_hi) {
             v = in[base + (int64_t)e * elem_stride + c];
             if (tw_mode == 2) {
                 const cplx w = tw_big[o * e];
@@ -194,7 +197,8 @@ k_fft_cols(FftPlanDev P, const cplx* __restrict__ in, cplx* __restrict__ out, in
     tile_fft<1, EPT, CLS>(smem, P, C, logC, sign, tid, nt);
     for (int i = tid; i < total; i += nt) {
         const int c = i & (C - 1), e = i >> logC;
-        if (c < cw) {
+        const int row = row_base + e * W.row_e;
+        if (c < cw && row >= W.out_lo && row < W.out_hi) {
             cplx v = smem[PADI(i)];
             if (tw_mode == 1) {
                 const cplx w = tw_big[o * e];
@@ -303,6 +307,9 @@ int fft_cols(FftPlan* p, const cplx* in, cplx* out, int64_t elem_stride, int64_t
              cudaStream_t st) {
     if (n_inner <= 0 || n_outer <= 0) return IPDE_OK;
     const int n = p->d.n;
+    if (p->fast && n <= IPDE_FFT_SMEM_MAX)
+        return fft_cols_windowed(p, in, out, elem_stride, n_inner, n_outer, outer_stride, sign, scale, tw_mode, tw_big,
+                                 row_window_all(), st);
     if (!p->fast && n <= IPDE_FFT_GENERIC_MAX)
         return fft_cols_generic(p, in, out, elem_stride, n_inner, n_outer, outer_stride, sign, scale, tw_mode, tw_big, n_big, st);
     if (n > IPDE_FFT_SMEM_MAX || !p->fast) {
@@ -318,6 +325,16 @@ int fft_cols(FftPlan* p, const cplx* in, cplx* out, int64_t elem_stride, int64_t
         }
         return IPDE_OK;
     }
+    ipde_set_error("fft_cols: unreachable");
+    return IPDE_ERR_UNSUPPORTED;
+}
+
+int fft_cols_windowed(FftPlan* p, const cplx* in, cplx* out, int64_t elem_stride, int64_t n_inner, int64_t n_outer,
+                      int64_t outer_stride, int sign, double scale, int tw_mode, const cplx* tw_big, RowWindow W,
+                      cudaStream_t st) {
+    if (n_inner <= 0 || n_outer <= 0) return IPDE_OK;
+    const int n = p->d.n;
+    ARG_CHECK(p->fast && n <= IPDE_FFT_SMEM_MAX, "windowed column transform needs a tile-engine length");
     int C = pow2_floor(IPDE_FFT_SMEM_MAX / n);
     if (C > 16) C = 16;
     while (C > 1 && C / 2 >= n_inner) C /= 2;
@@ -328,8 +345,15 @@ int fft_cols(FftPlan* p, const cplx* in, cplx* out, int64_t elem_stride, int64_t
     const unsigned g = (unsigned)(tiles * n_outer);
     const int t = fft_tile_threads(n, C, ept);
     int rc = IPDE_OK;
-    KERNEL_TAG("k_fft_cols", 32.0 * (double)n * (double)n_inner * (double)n_outer);
-    FFT_TILE_LAUNCH(k_fft_cols, ept, p->pow2, g, t, smem, st, p->d, in, out, elem_stride, n_inner, outer_stride, C, logC, sign, scale, tw_mode, tw_big);
+    // algorithmic bytes: rows actually read + rows actually written
+    double fin = 1.0, fout = 1.0;
+    if (W.row_e != 0 || W.row_o != 0) {
+        const double rows = (double)n * (double)n_outer;
+        fin = std::min(1.0, std::max(0.0, (double)(W.in_hi - W.in_lo)) / rows);
+        fout = std::min(1.0, std::max(0.0, (double)(W.out_hi - W.out_lo)) / rows);
+    }
+    KERNEL_TAG("k_fft_cols", 16.0 * (fin + fout) * (double)n * (double)n_inner * (double)n_outer);
+    FFT_TILE_LAUNCH(k_fft_cols, ept, p->pow2, g, t, smem, st, p->d, in, out, elem_stride, n_inner, outer_stride, C, logC, sign, scale, tw_mode, tw_big, W);
     if (rc) return rc;
     KERNEL_CHECK();
     return IPDE_OK;

@@ -53,6 +53,17 @@ int fft_rows(FftPlan* p, const cplx* in, cplx* out, int64_t batch, int64_t in_pi
 int fft_cols(FftPlan* p, const cplx* in, cplx* out, int64_t elem_stride, int64_t n_inner, int64_t n_outer,
              int64_t outer_stride, int sign, double scale, int tw_mode, const cplx* tw_big, int64_t n_big,
              cudaStream_t st);
+// Row windows for zero-padded data (free-space evaluator): element e of outer line o sits in row
+// o*row_o + e*row_e of the array; rows outside [in_lo, in_hi) are known to be zero and are not read, rows outside
+// [out_lo, out_hi) are not needed and are not written.
+struct RowWindow {
+    int row_o, row_e;
+    int in_lo, in_hi, out_lo, out_hi;
+};
+static inline RowWindow row_window_all() { RowWindow w = {0, 0, 0, 1, 0, 1}; return w; }
+int fft_cols_windowed(FftPlan* p, const cplx* in, cplx* out, int64_t elem_stride, int64_t n_inner, int64_t n_outer,
+                      int64_t outer_stride, int sign, double scale, int tw_mode, const cplx* tw_big, RowWindow W,
+                      cudaStream_t st);
 
 // Real <-> half-complex rows (length nr = 2*p->d.n reals <-> nr/2+1 complex), plan is for nr/2.
 int fft_r2c_rows(FftPlan* p, const double* in, cplx* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,

@@ -107,7 +107,7 @@ int grid_fft2_inverse(GridPlan* g, const cplx* spec_in, cplx* spec_work, double*
 template <int EPT, int CLS, int NT>
 __global__ void __launch_bounds__(NT, (NT <= 256) ? 2 : 1)
 k_cols_mult(FftPlanDev P, const cplx* in, cplx* out, cplx* copy, int64_t elem_stride,
-            int64_t n_inner, int64_t outer_stride, int C, int logC, int do_fwd, int copy_mode, ColMult M) {
+            int64_t n_inner, int64_t outer_stride, int C, int logC, int do_fwd, int copy_mode, ColMult M, RowWindow W) {
     extern __shared__ cplx smem[];
     const int n = P.n, tid = threadIdx.x, nt = blockDim.x;
     const int64_t tiles = (n_inner + C - 1) >> logC;
@@ -116,9 +116,12 @@ k_cols_mult(FftPlanDev P, const cplx* in, cplx* out, cplx* copy, int64_t elem_st
     const int cw = (int)min((int64_t)C, n_inner - c0);
     const int64_t base = (int64_t)o * outer_stride + c0;
     const int total = n << logC;
+    const int row_base = o * W.row_o;
     for (int i = tid; i < total; i += nt) {
         const int c = i & (C - 1), e = i >> logC;
-        smem[PADI(i)] = (c < cw) ? in[base + (int64_t)e * elem_stride + c] : make_double2(0.0, 0.0);
+        const int row = row_base + e * W.row_e;
+        smem[PADI(i)] = (c < cw && row >= W.in_lo && row < W.in_hi) ? in[base + (int64_t)e * elem_stride + c]
+                                                                    : make_double2(0.0, 0.0);
     }
     __syncthreads();
     if (do_fwd) tile_fft<1, EPT, CLS>(smem, P, C, logC, -1, tid, nt);
@@ -149,27 +152,28 @@ k_cols_mult(FftPlanDev P, const cplx* in, cplx* out, cplx* copy, int64_t elem_st
     tile_fft<1, EPT, CLS>(smem, P, C, logC, +1, tid, nt);
     for (int i = tid; i < total; i += nt) {
         const int c = i & (C - 1), e = i >> logC;
-        if (c < cw) out[base + (int64_t)e * elem_stride + c] = smem[PADI(i)];
+        const int row = row_base + e * W.row_e;
+        if (c < cw && row >= W.out_lo && row < W.out_hi) out[base + (int64_t)e * elem_stride + c] = smem[PADI(i)];
     }
 }
 
 template <int EPT, int CLS, int NT>
 static int launch_cols_mult_one(FftPlan* p, unsigned g, int t, size_t smem, cudaStream_t st, const cplx* in, cplx* out,
                                 cplx* copy, int64_t elem_stride, int64_t n_inner, int64_t outer_stride, int C, int logC,
-                                int do_fwd, int copy_mode, const ColMult& M) {
+                                int do_fwd, int copy_mode, const ColMult& M, const RowWindow& W) {
     if (smem > 48 * 1024)
         CUDA_TRY(cudaFuncSetAttribute(k_cols_mult<EPT, CLS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KERNEL_TAG("k_cols_mult", (32.0 + (copy_mode ? 16.0 : 0.0) + (M.kind == 3 ? 8.0 : 0.0)) * (double)p->d.n * (double)n_inner *
                                   (double)(g / cdiv(n_inner, C)));
     k_cols_mult<EPT, CLS, NT><<<g, t, smem, st>>>(p->d, in, out, copy, elem_stride, n_inner, outer_stride, C, logC, do_fwd,
-                                                  copy_mode, M);
+                                                  copy_mode, M, W);
     KERNEL_CHECK();
     return IPDE_OK;
 }
 
 // columns of length p->d.n (must fit a tile with >= 4 adjacent columns and be tile-engine friendly)
 static int cols_mult(FftPlan* p, const cplx* in, cplx* out, cplx* copy, int64_t elem_stride, int64_t n_inner, int64_t n_outer,
-                     int64_t outer_stride, int do_fwd, int copy_mode, const ColMult& M, cudaStream_t st) {
+                     int64_t outer_stride, int do_fwd, int copy_mode, const ColMult& M, const RowWindow& W, cudaStream_t st) {
     const int n = p->d.n;
     int C = 1;
     while ((int64_t)C * 2 * n <= IPDE_FFT_SMEM_MAX && C < 16) C *= 2;
@@ -182,7 +186,7 @@ static int cols_mult(FftPlan* p, const cplx* in, cplx* out, cplx* copy, int64_t 
     const unsigned g = (unsigned)(cdiv(n_inner, C) * n_outer);
     const int t = fft_tile_threads(n, C, ept);
 #define CM(E_, C_, N_) return launch_cols_mult_one<E_, C_, N_>(p, g, t, smem, st, in, out, copy, elem_stride, n_inner, \
-                                                              outer_stride, C, logC, do_fwd, copy_mode, M)
+                                                              outer_stride, C, logC, do_fwd, copy_mode, M, W)
     if (ept == 8) {
         if (p->pow2) { if (t <= 256) CM(8, 0, 256); else CM(8, 0, 512); }
         else { if (t <= 256) CM(8, 1, 256); else CM(8, 1, 512); }
@@ -203,38 +207,50 @@ static inline bool grid_fused_ok(const GridPlan* g) {
 // the inverse row transforms.  spec_copy (may be null) receives the 2-D spectrum, before (copy_mode 1) or after
 // (2) the multiplication.  spec_in is overwritten when the column transform is split.
 int grid_cols_symbol(GridPlan* g, cplx* spec_in, cplx* spec_out, cplx* spec_copy, int copy_mode, const ColMult& M0,
-                     cudaStream_t st) {
+                     cudaStream_t st, const int* win) {
     const int64_t P = g->pitch;
+    // win = {in_lo, in_hi, out_lo, out_hi}: rows of spec_in outside [in_lo, in_hi) are zero (not read), rows of
+    // spec_out outside [out_lo, out_hi) are not needed (not written)
+    const int in_lo = win ? win[0] : 0, in_hi = win ? win[1] : g->nx;
+    const int out_lo = win ? win[2] : 0, out_hi = win ? win[3] : g->nx;
     ColMult M = M0;
     M.nx = g->nx; M.xh = g->xh;
     if (M.ny <= 0) { M.ny = g->ny; M.yh = g->yh; M.col_offset = 0; }
     if (!spec_copy) copy_mode = 0;
     if (g->n2 == 1) {
         M.fmul = 1;
-        return cols_mult(g->colA, spec_in, spec_out, spec_copy, P, P, 1, 0, 1, copy_mode, M, st);
+        RowWindow W = {0, 1, in_lo, in_hi, out_lo, out_hi};
+        return cols_mult(g->colA, spec_in, spec_out, spec_copy, P, P, 1, 0, 1, copy_mode, M, W, st);
     }
     M.fmul = g->n1;
-    int rc = fft_cols(g->colA, spec_in, spec_in, (int64_t)g->n2 * P, P, g->n2, P, -1, 1.0, 1, g->tw_big, g->nx, st);
+    // four-step: element e of line b of the first pass is row b + n2*e
+    RowWindow Wa = {1, g->n2, in_lo, in_hi, 0, g->nx};
+    int rc = fft_cols_windowed(g->colA, spec_in, spec_in, (int64_t)g->n2 * P, P, g->n2, P, -1, 1.0, 1, g->tw_big, Wa, st);
     if (rc) return rc;
-    rc = cols_mult(g->colB, spec_in, spec_out, spec_copy, P, P, g->n1, (int64_t)g->n2 * P, 1, copy_mode, M, st);
+    rc = cols_mult(g->colB, spec_in, spec_out, spec_copy, P, P, g->n1, (int64_t)g->n2 * P, 1, copy_mode, M, row_window_all(), st);
     if (rc) return rc;
-    return fft_cols(g->colA, spec_out, spec_out, (int64_t)g->n2 * P, P, g->n2, P, +1, 1.0, 2, g->tw_big, g->nx, st);
+    RowWindow Wb = {1, g->n2, 0, g->nx, out_lo, out_hi};
+    return fft_cols_windowed(g->colA, spec_out, spec_out, (int64_t)g->n2 * P, P, g->n2, P, +1, 1.0, 2, g->tw_big, Wb, st);
 }
 
 // 2-D spectrum (as left by grid_cols_symbol's copy) -> symbol -> inverse column FFT -> spec_out
-int grid_cols_symbol_inverse(GridPlan* g, const cplx* spec2d, cplx* spec_out, const ColMult& M0, cudaStream_t st) {
+int grid_cols_symbol_inverse(GridPlan* g, const cplx* spec2d, cplx* spec_out, const ColMult& M0, cudaStream_t st,
+                             const int* win) {
     const int64_t P = g->pitch;
+    const int out_lo = win ? win[0] : 0, out_hi = win ? win[1] : g->nx;
     ColMult M = M0;
     M.nx = g->nx; M.xh = g->xh;
     if (M.ny <= 0) { M.ny = g->ny; M.yh = g->yh; M.col_offset = 0; }
     if (g->n2 == 1) {
         M.fmul = 1;
-        return cols_mult(g->colA, spec2d, spec_out, nullptr, P, P, 1, 0, 0, 0, M, st);
+        RowWindow W = {0, 1, 0, g->nx, out_lo, out_hi};
+        return cols_mult(g->colA, spec2d, spec_out, nullptr, P, P, 1, 0, 0, 0, M, W, st);
     }
     M.fmul = g->n1;
-    int rc = cols_mult(g->colB, spec2d, spec_out, nullptr, P, P, g->n1, (int64_t)g->n2 * P, 0, 0, M, st);
+    int rc = cols_mult(g->colB, spec2d, spec_out, nullptr, P, P, g->n1, (int64_t)g->n2 * P, 0, 0, M, row_window_all(), st);
     if (rc) return rc;
-    return fft_cols(g->colA, spec_out, spec_out, (int64_t)g->n2 * P, P, g->n2, P, +1, 1.0, 2, g->tw_big, g->nx, st);
+    RowWindow Wb = {1, g->n2, 0, g->nx, out_lo, out_hi};
+    return fft_cols_windowed(g->colA, spec_out, spec_out, (int64_t)g->n2 * P, P, g->n2, P, +1, 1.0, 2, g->tw_big, Wb, st);
 }
 
 // the whole scalar grid solve: fc (real) -> uch (2-D spectrum of the solution) and uc (real)

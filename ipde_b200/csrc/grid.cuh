@@ -48,9 +48,12 @@ struct ColMult {
     const double* table;  // kind 3: one real per spectrum entry, same layout as the spectrum
     int col_offset;       // global index of column 0 (slab-decomposed grids hold a block of columns)
 };
+// win (optional): {in_lo, in_hi, out_lo, out_hi} row windows of zero-padded data, see RowWindow in fft.cuh
 int grid_cols_symbol(GridPlan* g, cplx* spec_in, cplx* spec_out, cplx* spec_copy, int copy_mode, const ColMult& M,
-                     cudaStream_t st);
-int grid_cols_symbol_inverse(GridPlan* g, const cplx* spec2d, cplx* spec_out, const ColMult& M, cudaStream_t st);
+                     cudaStream_t st, const int* win = nullptr);
+// win (optional): {out_lo, out_hi}
+int grid_cols_symbol_inverse(GridPlan* g, const cplx* spec2d, cplx* spec_out, const ColMult& M, cudaStream_t st,
+                             const int* win = nullptr);
 int grid_solve_scalar_fused(GridPlan* g, int kind, double k, const double* fc, cplx* uch, cplx* spec_work, double* uc,
                             cudaStream_t st);
 int grid_stokes_stress(GridPlan* g, const cplx* uh, const cplx* vh, const cplx* ph, cplx* txx, cplx* txy, cplx* tyy,

@@ -80,15 +80,19 @@ class ScalarSolver(object):
             gb = 'direct'           # the evaluator needs square cells
         self.evaluation = gb
         self.split_grid_evaluation = gb == 'ewald'
+        self._no_interface_field = empty((self.ebdyc.all_ivx.size,))
         self.evaluator_g = None
         if gb == 'ewald':
             from ...device import FreeSpaceEvaluator
             e = self.ebdyc
             pix, piy = np.nonzero(e.phys_not_in_annulus)
+            # a single boundary never uses the field on its own interface (helper.correct: it cancels
+            # identically), so the second inverse transform + gather is skipped
+            pts = (e.all_ivx, e.all_ivy) if e.N > 1 else None
             self.evaluator_g = FreeSpaceEvaluator(
                 self.kernel_kind, self.k, float(g.xv[0]), float(g.yv[0]), float(g.xh),
                 self.grid_sources.x, self.grid_sources.y, grid_nodes=(pix, piy),
-                grid_out_pos=e.phys_inds[e.phys_not_in_annulus], points=(e.all_ivx, e.all_ivy))
+                grid_out_pos=e.phys_inds[e.phys_not_in_annulus], points=pts)
         for helper in self.helpers:
             helper.set_evaluation(gb, g, single=self.ebdyc.N == 1)
 
@@ -150,6 +154,8 @@ class ScalarSolver(object):
         L.ipde_grid_gather(ptr(D.uc), ptr(D.phys_lin), D.n_phys, ptr(res), st)
         if self.evaluator_g is not None:
             bu_all = self.evaluator_g(sigmag, grid_out=res)
+            if bu_all is None:
+                bu_all = self._no_interface_field
         else:
             out = layer_apply_scalar(self.kernel_kind, self.k, self.d_gsx, self.d_gsy, sigmag, D.pnai_x, D.pnai_y)
             L.ipde_index_add(ptr(res), ptr(D.pna_pos), ptr(out), D.n_pna, st)
@@ -175,12 +181,19 @@ class ScalarSolver(object):
                            torch.empty(n, dtype=torch.float64).pin_memory(), empty((n,)))
         return self._stage
 
-    def __call__(self, f, **kwargs):
-        """f must be of type EmbeddedFunction"""
+    def __call__(self, f, out=None, **kwargs):
+        """
+        f must be of type EmbeddedFunction; returns a fresh EmbeddedFunction (as the reference does).
+        Extension: `out=` an EmbeddedFunction of the same collection to receive the result (a time-stepping caller
+        avoids the page faults of a fresh 8*dof-byte host array per call).
+        """
         h_in, h_out, d_in = self._staging()
-        h_in.numpy()[:] = np.asarray(f, dtype=float).ravel()
+        h_in.copy_(torch.from_numpy(np.ascontiguousarray(f, dtype=float).reshape(-1)))
         d_in.copy_(h_in, non_blocking=True)
         res = self.solve_device(d_in, **kwargs)
         h_out.copy_(res, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return EmbeddedFunction(self.ebdyc, linear_data=h_out.numpy().copy())
+        if out is None:
+            out = EmbeddedFunction(self.ebdyc)
+        torch.from_numpy(np.asarray(out).reshape(-1)).copy_(h_out)
+        return out
