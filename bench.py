@@ -82,8 +82,12 @@ class ClockSampler(object):
         try:
             self.f = open(self.path, 'w')
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + q,
-                                       '--format=csv,noheader,nounits', '-lms', '100'],
+                                       '--format=csv,noheader,nounits', '-lms', '50'],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
+            # nvidia-smi needs a moment to start: wait for its first sample so that short timed regions are covered
+            t0 = time.time()
+            while time.time() - t0 < 5.0 and os.path.getsize(self.path) == 0:
+                time.sleep(0.05)
         except Exception:
             self.p = None
 

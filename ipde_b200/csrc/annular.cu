@@ -30,85 +30,68 @@ struct AnnularPlan {
     AnnularScalarOp* op = nullptr;
 };
 
+// The three small-matrix stages are parallel over (mode column i, output row q = blockIdx.y): one thread produces one
+// output entry from the M (or M-1) entries of its column (coalesced across the threads of a block, re-read from
+// L1/L2 by the other rows) -- M times more threads in flight than a thread-per-column loop.
 // stage 1:  W1[0:M-1] = D01 uh ;  W1[M-1:2M-2] = R01 (i k uh)
 __global__ void k_ann_stage1(const cplx* __restrict__ uh, cplx* __restrict__ W1, int n, int M, const double* __restrict__ D01,
                              const double* __restrict__ R01, const double* __restrict__ ks) {
-    extern __shared__ double shm[];
-    double* sD = shm;
-    double* sR = shm + (M - 1) * M;
-    for (int t = threadIdx.x; t < (M - 1) * M; t += blockDim.x) { sD[t] = D01[t]; sR[t] = R01[t]; }
-    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    cplx u[ANN_MAX_M];
-    for (int r = 0; r < M; ++r) u[r] = uh[(int64_t)r * n + i];
-    const double k = ks[i];
-    for (int q = 0; q < M - 1; ++q) {
-        cplx a = make_double2(0.0, 0.0), b = make_double2(0.0, 0.0);
-        for (int r = 0; r < M; ++r) {
-            a.x += sD[q * M + r] * u[r].x; a.y += sD[q * M + r] * u[r].y;
-            b.x += sR[q * M + r] * u[r].x; b.y += sR[q * M + r] * u[r].y;
-        }
-        W1[(int64_t)q * n + i] = a;
-        W1[(int64_t)(M - 1 + q) * n + i] = make_double2(-k * b.y, k * b.x);
+    const int q = blockIdx.y;                       // 0 .. M-2
+    const double* d = D01 + q * M;
+    const double* r = R01 + q * M;
+    cplx a = make_double2(0.0, 0.0), b = make_double2(0.0, 0.0);
+    for (int t = 0; t < M; ++t) {
+        const cplx u = uh[(int64_t)t * n + i];
+        const double dd = d[t], rr = r[t];
+        a.x = fma(dd, u.x, a.x); a.y = fma(dd, u.y, a.y);
+        b.x = fma(rr, u.x, b.x); b.y = fma(rr, u.y, b.y);
     }
+    const double k = ks[i];
+    W1[(int64_t)q * n + i] = a;
+    W1[(int64_t)(M - 1 + q) * n + i] = make_double2(-k * b.y, k * b.x);
 }
 
 // stage 2:  W2 = D12 A + R12 (i k B),  A = W1[0:M-1], B = W1[M-1:2M-2] (after the variable-coefficient multiplies)
 __global__ void k_ann_stage2(const cplx* __restrict__ W1, cplx* __restrict__ W2, int n, int M, const double* __restrict__ D12,
                              const double* __restrict__ R12, const double* __restrict__ ks) {
-    extern __shared__ double shm[];
-    double* sD = shm;
-    double* sR = shm + (M - 2) * (M - 1);
-    for (int t = threadIdx.x; t < (M - 2) * (M - 1); t += blockDim.x) { sD[t] = D12[t]; sR[t] = R12[t]; }
-    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    cplx A[ANN_MAX_M], B[ANN_MAX_M];
+    const int q = blockIdx.y;                       // 0 .. M-3
+    const double* d = D12 + q * (M - 1);
+    const double* r = R12 + q * (M - 1);
     const double k = ks[i];
-    for (int r = 0; r < M - 1; ++r) {
-        A[r] = W1[(int64_t)r * n + i];
-        cplx b = W1[(int64_t)(M - 1 + r) * n + i];
-        B[r] = make_double2(-k * b.y, k * b.x);
+    cplx acc = make_double2(0.0, 0.0);
+    for (int t = 0; t < M - 1; ++t) {
+        const cplx A = W1[(int64_t)t * n + i];
+        const cplx b = W1[(int64_t)(M - 1 + t) * n + i];
+        const double dd = d[t], rr = r[t];
+        acc.x = fma(dd, A.x, fma(rr, -k * b.y, acc.x));
+        acc.y = fma(dd, A.y, fma(rr, k * b.x, acc.y));
     }
-    for (int q = 0; q < M - 2; ++q) {
-        cplx acc = make_double2(0.0, 0.0);
-        for (int r = 0; r < M - 1; ++r) {
-            acc.x += sD[q * (M - 1) + r] * A[r].x + sR[q * (M - 1) + r] * B[r].x;
-            acc.y += sD[q * (M - 1) + r] * A[r].y + sR[q * (M - 1) + r] * B[r].y;
-        }
-        W2[(int64_t)q * n + i] = acc;
-    }
+    W2[(int64_t)q * n + i] = acc;
 }
 
 // stage 3:  out[0:M-2] = k^2 R02 uh - W2 ; out[M-2] = ibc . uh ; out[M-1] = obc . uh
 __global__ void k_ann_stage3(const cplx* __restrict__ uh, const cplx* __restrict__ W2, cplx* __restrict__ out, int n, int M,
                              const double* __restrict__ R02, const double* __restrict__ ibc, const double* __restrict__ obc,
                              double k2) {
-    extern __shared__ double shm[];
-    double* sR = shm;
-    double* sI = shm + (M - 2) * M;
-    double* sO = sI + M;
-    for (int t = threadIdx.x; t < (M - 2) * M; t += blockDim.x) sR[t] = R02[t];
-    for (int t = threadIdx.x; t < M; t += blockDim.x) { sI[t] = ibc[t]; sO[t] = obc[t]; }
-    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    cplx u[ANN_MAX_M];
-    for (int r = 0; r < M; ++r) u[r] = uh[(int64_t)r * n + i];
-    for (int q = 0; q < M - 2; ++q) {
-        cplx acc = make_double2(0.0, 0.0);
-        for (int r = 0; r < M; ++r) { acc.x += sR[q * M + r] * u[r].x; acc.y += sR[q * M + r] * u[r].y; }
-        cplx l = W2[(int64_t)q * n + i];
-        out[(int64_t)q * n + i] = make_double2(k2 * acc.x - l.x, k2 * acc.y - l.y);
+    const int q = blockIdx.y;                       // 0 .. M-1
+    const double* row = (q < M - 2) ? R02 + q * M : (q == M - 2 ? ibc : obc);
+    cplx acc = make_double2(0.0, 0.0);
+    for (int t = 0; t < M; ++t) {
+        const cplx u = uh[(int64_t)t * n + i];
+        const double rr = row[t];
+        acc.x = fma(rr, u.x, acc.x); acc.y = fma(rr, u.y, acc.y);
     }
-    cplx a = make_double2(0.0, 0.0), b = make_double2(0.0, 0.0);
-    for (int r = 0; r < M; ++r) {
-        a.x += sI[r] * u[r].x; a.y += sI[r] * u[r].y;
-        b.x += sO[r] * u[r].x; b.y += sO[r] * u[r].y;
+    if (q < M - 2) {
+        const cplx l = W2[(int64_t)q * n + i];
+        acc = make_double2(k2 * acc.x - l.x, k2 * acc.y - l.y);
     }
-    out[(int64_t)(M - 2) * n + i] = a;
-    out[(int64_t)(M - 1) * n + i] = b;
+    out[(int64_t)q * n + i] = acc;
 }
 
 // per-mode dense M x M mat-vec on mode-minor vectors; thread (mode i, output row j = blockIdx.y)
@@ -163,16 +146,15 @@ struct AnnularScalarOp : public LinearOperator {
     int apply(const cplx* in, cplx* out, cudaStream_t st) override {
         const int n = p->n, M = p->M;
         const int threads = 128, blocks = (n + threads - 1) / threads;
-        k_ann_stage1<<<blocks, threads, sizeof(double) * 2 * (M - 1) * M, st>>>(in, p->W1, n, M, p->D01, p->R01, p->ks);
+        k_ann_stage1<<<dim3(blocks, M - 1), threads, 0, st>>>(in, p->W1, n, M, p->D01, p->R01, p->ks);
         KERNEL_CHECK();
         int rc = fft_mul_fft_rows(p->fft, p->W1, p->W1, p->mul1, 2 * (M - 1), st);
         if (rc) return rc;
-        k_ann_stage2<<<blocks, threads, sizeof(double) * 2 * (M - 2) * (M - 1), st>>>(p->W1, p->W2, n, M, p->D12, p->R12, p->ks);
+        k_ann_stage2<<<dim3(blocks, M - 2), threads, 0, st>>>(p->W1, p->W2, n, M, p->D12, p->R12, p->ks);
         KERNEL_CHECK();
         rc = fft_mul_fft_rows(p->fft, p->W2, p->W2, p->mul2, M - 2, st);
         if (rc) return rc;
-        k_ann_stage3<<<blocks, threads, sizeof(double) * ((M - 2) * M + 2 * M), st>>>(in, p->W2, out, n, M, p->R02, p->ibc,
-                                                                                     p->obc, p->k2);
+        k_ann_stage3<<<dim3(blocks, M), threads, 0, st>>>(in, p->W2, out, n, M, p->R02, p->ibc, p->obc, p->k2);
         KERNEL_CHECK();
         return IPDE_OK;
     }

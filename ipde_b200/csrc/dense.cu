@@ -16,15 +16,33 @@ __global__ void k_gemv(const double* __restrict__ A, const double* __restrict__ 
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool vec2 = ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     for (int64_t r = warp; r < m; r += nwarps) {
         const double* a = A + r * lda;
         double acc0 = 0.0, acc1 = 0.0;
-        int64_t c = lane;
-        for (; c + 32 < n; c += 64) {
-            acc0 = fma(a[c], x[c], acc0);
-            acc1 = fma(a[c + 32], x[c + 32], acc1);
+        int64_t c = 0;
+        if (vec2) {
+            // 16-byte loads: 4 independent double2 loads of the row per lane per iteration (2 KB per warp)
+            const double2* a2 = reinterpret_cast<const double2*>(a);
+            const double2* x2 = reinterpret_cast<const double2*>(x);
+            const int64_t n2 = n >> 1;
+            int64_t d = lane;
+            for (; d + 96 < n2; d += 128) {
+                const double2 p0 = a2[d], p1 = a2[d + 32], p2 = a2[d + 64], p3 = a2[d + 96];
+                const double2 q0 = x2[d], q1 = x2[d + 32], q2 = x2[d + 64], q3 = x2[d + 96];
+                acc0 = fma(p0.x, q0.x, acc0); acc1 = fma(p0.y, q0.y, acc1);
+                acc0 = fma(p1.x, q1.x, acc0); acc1 = fma(p1.y, q1.y, acc1);
+                acc0 = fma(p2.x, q2.x, acc0); acc1 = fma(p2.y, q2.y, acc1);
+                acc0 = fma(p3.x, q3.x, acc0); acc1 = fma(p3.y, q3.y, acc1);
+            }
+            for (; d < n2; d += 32) {
+                const double2 p0 = a2[d], q0 = x2[d];
+                acc0 = fma(p0.x, q0.x, acc0); acc1 = fma(p0.y, q0.y, acc1);
+            }
+            c = n2 << 1;
         }
-        if (c < n) acc0 = fma(a[c], x[c], acc0);
+        for (c += lane; c < n; c += 32) acc0 = fma(a[c], x[c], acc0);
         double acc = acc0 + acc1;
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) y[r] = acc;

@@ -25,10 +25,12 @@ __device__ __forceinline__ cplx block_reduce_cplx(cplx v, cplx* sh) {
     return r;
 }
 
-// partial[i*gridDim.x + b] = sum over this block's elements of conj(V_i[e]) * w[e]
+// h[i] = sum_e conj(V_i[e]) * w[e] for i < nvec, in ONE launch: every block writes its partial sums, the last block
+// to finish (atomic ticket) adds the partials in block order -- deterministic, no second kernel.
 __global__ void k_multi_dot(const cplx* __restrict__ V, int nvec, const cplx* __restrict__ w, int64_t len,
-                            cplx* __restrict__ partial) {
+                            cplx* __restrict__ partial, cplx* __restrict__ h, unsigned* __restrict__ ticket) {
     __shared__ cplx sh[32];
+    __shared__ bool last;
     for (int i = 0; i < nvec; ++i) {
         const cplx* v = V + (int64_t)i * len;
         cplx acc = make_double2(0.0, 0.0);
@@ -40,15 +42,23 @@ __global__ void k_multi_dot(const cplx* __restrict__ V, int nvec, const cplx* __
         cplx r = block_reduce_cplx(acc, sh);
         if (threadIdx.x == 0) partial[(int64_t)i * gridDim.x + blockIdx.x] = r;
     }
-}
-
-__global__ void k_reduce_dots(const cplx* __restrict__ partial, int nvec, int nblocks, cplx* __restrict__ h) {
-    __shared__ cplx sh[32];
-    const int i = blockIdx.x;
-    cplx acc = make_double2(0.0, 0.0);
-    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) acc = cadd(acc, partial[(int64_t)i * nblocks + b]);
-    cplx r = block_reduce_cplx(acc, sh);
-    if (threadIdx.x == 0) h[i] = r;
+    __threadfence();
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const int nb = gridDim.x;
+    for (int i = threadIdx.x >> 5; i < nvec; i += blockDim.x >> 5) {      // one warp per vector
+        const int lane = threadIdx.x & 31;
+        cplx acc = make_double2(0.0, 0.0);
+        for (int b = lane; b < nb; b += 32) acc = cadd(acc, partial[(int64_t)i * nb + b]);
+        for (int o = 16; o > 0; o >>= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        }
+        if (lane == 0) h[i] = acc;
+    }
+    if (threadIdx.x == 0) *ticket = 0;
 }
 
 __global__ void k_sub_combination(cplx* __restrict__ w, const cplx* __restrict__ V, int nvec, const cplx* __restrict__ h,
@@ -92,7 +102,11 @@ int gmres_workspace_ensure(GmresWorkspace* ws, int64_t len, int restart) {
     CUDA_TRY(cudaMalloc(&ws->y, sizeof(cplx) * (size_t)len));
     CUDA_TRY(cudaMalloc(&ws->hbuf, sizeof(cplx) * (size_t)(3 * (restart + 2))));
     CUDA_TRY(cudaMalloc(&ws->partial, sizeof(cplx) * (size_t)(restart + 2) * ws->nblocks));
-    CUDA_TRY(cudaMallocHost(&ws->host, sizeof(cplx) * (size_t)(3 * (restart + 2))));
+    CUDA_TRY(cudaMallocHost(&ws->host, sizeof(cplx) * (size_t)(3 * 3 * (restart + 2))));
+    CUDA_TRY(cudaEventCreateWithFlags(&ws->ev[0], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ws->ev[1], cudaEventDisableTiming));
+    CUDA_TRY(cudaMalloc(&ws->ticket, sizeof(unsigned)));
+    CUDA_TRY(cudaMemset(ws->ticket, 0, sizeof(unsigned)));
     ws->len = len;
     ws->restart = restart;
     return IPDE_OK;
@@ -100,14 +114,15 @@ int gmres_workspace_ensure(GmresWorkspace* ws, int64_t len, int restart) {
 
 void gmres_workspace_free(GmresWorkspace* ws) {
     cudaFree(ws->V); cudaFree(ws->w); cudaFree(ws->z); cudaFree(ws->y); cudaFree(ws->hbuf); cudaFree(ws->partial);
+    cudaFree(ws->ticket);
     if (ws->host) cudaFreeHost(ws->host);
+    if (ws->ev[0]) cudaEventDestroy(ws->ev[0]);
+    if (ws->ev[1]) cudaEventDestroy(ws->ev[1]);
     *ws = GmresWorkspace();
 }
 
 static int dots(GmresWorkspace* ws, const cplx* V, int nvec, const cplx* w, int64_t len, cplx* h, cudaStream_t st) {
-    k_multi_dot<<<ws->nblocks, DOT_THREADS, 0, st>>>(V, nvec, w, len, reinterpret_cast<cplx*>(ws->partial));
-    KERNEL_CHECK();
-    k_reduce_dots<<<nvec, 128, 0, st>>>(reinterpret_cast<cplx*>(ws->partial), nvec, ws->nblocks, h);
+    k_multi_dot<<<ws->nblocks, DOT_THREADS, 0, st>>>(V, nvec, w, len, reinterpret_cast<cplx*>(ws->partial), h, ws->ticket);
     KERNEL_CHECK();
     return IPDE_OK;
 }
@@ -127,7 +142,8 @@ int gmres_solve(LinearOperator* op, GmresWorkspace* ws, const cplx* b, cplx* x, 
     cplx* d_h = ws->hbuf;
     cplx* d_h2 = ws->hbuf + R1;
     cplx* d_n = ws->hbuf + 2 * R1;
-    cplx* hst = ws->host;
+    cplx* hst = ws->host;                            // two slots for the in-flight iterations ...
+    cplx* hmisc = ws->host + (size_t)2 * 3 * R1;     // ... and one for norms / the small solution vector
     cplx* V = ws->V;
     const int eb = ew_blocks(len);
     int total_its = 0;
@@ -137,9 +153,9 @@ int gmres_solve(LinearOperator* op, GmresWorkspace* ws, const cplx* b, cplx* x, 
     // ||b||
     rc = dots(ws, b, 1, b, len, d_n, st);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(hst, d_n, sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(hmisc, d_n, sizeof(cplx), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    const double bnorm = sqrt(hst[0].x);
+    const double bnorm = sqrt(hmisc[0].x);
     CUDA_TRY(cudaMemsetAsync(ws->y, 0, sizeof(cplx) * (size_t)len, st));
     if (bnorm == 0.0) {
         CUDA_TRY(cudaMemsetAsync(x, 0, sizeof(cplx) * (size_t)len, st));
@@ -159,35 +175,44 @@ int gmres_solve(LinearOperator* op, GmresWorkspace* ws, const cplx* b, cplx* x, 
             KERNEL_CHECK();
         }
         rc = dots(ws, ws->w, 1, ws->w, len, d_n, st); if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(hst, d_n, sizeof(cplx), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(hmisc, d_n, sizeof(cplx), cudaMemcpyDeviceToHost, st));
         k_normalize<<<eb, 256, 0, st>>>(ws->w, V, d_n, len);
         KERNEL_CHECK();
         CUDA_TRY(cudaStreamSynchronize(st));
-        const double beta = sqrt(hst[0].x);
+        const double beta = sqrt(hmisc[0].x);
         if (beta <= tol * bnorm) { *relres = beta / bnorm; converged = true; break; }
         std::fill(H.begin(), H.end(), hc(0.0));
         std::fill(g.begin(), g.end(), hc(0.0));
         g[0] = beta;
         int kdone = 0;
-        for (int j = 0; j < restart; ++j) {
+        // Software pipeline of depth one: iteration j+1 is enqueued before the host looks at the Hessenberg column
+        // of iteration j, so the device never waits for the host round trip (one iteration of speculative work is
+        // discarded when convergence is detected).
+        auto enqueue = [&](int j) -> int {
             cplx* vj = V + (int64_t)j * len;
-            rc = op->precond(vj, ws->z, st); if (rc) return rc;
-            rc = op->apply(ws->z, ws->w, st); if (rc) return rc;
+            int r = op->precond(vj, ws->z, st); if (r) return r;
+            r = op->apply(ws->z, ws->w, st); if (r) return r;
             // classical Gram-Schmidt, twice
-            rc = dots(ws, V, j + 1, ws->w, len, d_h, st); if (rc) return rc;
+            r = dots(ws, V, j + 1, ws->w, len, d_h, st); if (r) return r;
             k_sub_combination<<<eb, 256, 0, st>>>(ws->w, V, j + 1, d_h, len);
             KERNEL_CHECK();
-            rc = dots(ws, V, j + 1, ws->w, len, d_h2, st); if (rc) return rc;
+            r = dots(ws, V, j + 1, ws->w, len, d_h2, st); if (r) return r;
             k_sub_combination<<<eb, 256, 0, st>>>(ws->w, V, j + 1, d_h2, len);
             KERNEL_CHECK();
-            rc = dots(ws, ws->w, 1, ws->w, len, d_n, st); if (rc) return rc;
+            r = dots(ws, ws->w, 1, ws->w, len, d_n, st); if (r) return r;
             k_normalize<<<eb, 256, 0, st>>>(ws->w, V + (int64_t)(j + 1) * len, d_n, len);
             KERNEL_CHECK();
-            CUDA_TRY(cudaMemcpyAsync(hst, ws->hbuf, sizeof(cplx) * (size_t)(2 * R1 + 1), cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
-            const double hn = sqrt(hst[2 * R1].x);
+            cplx* slot = hst + (size_t)(j & 1) * (3 * R1);
+            CUDA_TRY(cudaMemcpyAsync(slot, ws->hbuf, sizeof(cplx) * (size_t)(2 * R1 + 1), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaEventRecord(ws->ev[j & 1], st));
+            return IPDE_OK;
+        };
+        auto process = [&](int j) -> int {
+            CUDA_TRY(cudaEventSynchronize(ws->ev[j & 1]));
+            const cplx* slot = hst + (size_t)(j & 1) * (3 * R1);
+            const double hn = sqrt(slot[2 * R1].x);
             for (int i = 0; i <= j; ++i)
-                H[(size_t)i * restart + j] = hc(hst[i].x + hst[R1 + i].x, hst[i].y + hst[R1 + i].y);
+                H[(size_t)i * restart + j] = hc(slot[i].x + slot[R1 + i].x, slot[i].y + slot[R1 + i].y);
             H[(size_t)(j + 1) * restart + j] = hn;
             for (int i = 0; i < j; ++i) {
                 hc a = H[(size_t)i * restart + j], bb = H[(size_t)(i + 1) * restart + j];
@@ -210,7 +235,15 @@ int gmres_solve(LinearOperator* op, GmresWorkspace* ws, const cplx* b, cplx* x, 
             ++total_its;
             const double rel = std::abs(g[j + 1]) / bnorm;
             *relres = rel;
-            if (rel <= tol || hn == 0.0) { converged = true; break; }
+            if (rel <= tol || hn == 0.0) converged = true;
+            return IPDE_OK;
+        };
+        for (int j = 0; j < restart && !converged; ++j) {
+            rc = enqueue(j); if (rc) return rc;
+            if (j >= 1) { rc = process(j - 1); if (rc) return rc; }
+        }
+        if (!converged && kdone < restart) {       // the last enqueued iteration has not been looked at yet
+            rc = process(kdone); if (rc) return rc;
         }
         // back substitution for the small triangular system, then y += V^T yk
         std::vector<hc> yk(kdone);
@@ -219,8 +252,8 @@ int gmres_solve(LinearOperator* op, GmresWorkspace* ws, const cplx* b, cplx* x, 
             for (int l = i + 1; l < kdone; ++l) s -= H[(size_t)i * restart + l] * yk[l];
             yk[i] = s / H[(size_t)i * restart + i];
         }
-        for (int i = 0; i < kdone; ++i) hst[i] = make_double2(yk[i].real(), yk[i].imag());
-        CUDA_TRY(cudaMemcpyAsync(d_h, hst, sizeof(cplx) * (size_t)kdone, cudaMemcpyHostToDevice, st));
+        for (int i = 0; i < kdone; ++i) hmisc[i] = make_double2(yk[i].real(), yk[i].imag());
+        CUDA_TRY(cudaMemcpyAsync(d_h, hmisc, sizeof(cplx) * (size_t)kdone, cudaMemcpyHostToDevice, st));
         k_add_combination<<<eb, 256, 0, st>>>(ws->y, V, kdone, d_h, len);
         KERNEL_CHECK();
         CUDA_TRY(cudaStreamSynchronize(st));   // hst is reused next cycle

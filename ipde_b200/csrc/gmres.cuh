@@ -21,6 +21,8 @@ struct GmresWorkspace {
     double* partial = nullptr;
     cplx* host = nullptr;    // pinned mirror of hbuf
     int nblocks = 0;
+    cudaEvent_t ev[2] = {nullptr, nullptr};   // completion of the host copies of two in-flight iterations
+    unsigned* ticket = nullptr;   // last-block-done counter of the fused dot-product kernel
 };
 
 int gmres_workspace_ensure(GmresWorkspace* ws, int64_t len, int restart);
