@@ -111,6 +111,12 @@ static inline int rows_per_tile(int n, int64_t batch) {
     return c;
 }
 
+// the cp.async double-buffered column kernel can be switched off (IPDE_FFT_PIPELINE=0) for A/B measurements
+bool fft_pipeline_enabled();
+static const bool g_fft_pipeline = []() { const char* e = getenv("IPDE_FFT_PIPELINE"); return !(e && e[0] == '0'); }();
+
+bool fft_pipeline_enabled() { return g_fft_pipeline; }
+
 // elements per thread: 8 up to 4096-element tiles (<= 512 threads), 16 beyond
 static inline int tile_ept(int64_t elems) { return elems > 4096 ? 16 : 8; }
 
@@ -206,6 +212,78 @@ k_fft_cols(FftPlanDev P, const cplx* __restrict__ in, cplx* __restrict__ out, in
             }
             out[base + (int64_t)e * elem_stride + c] = cscale(v, scale);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Persistent, double-buffered version of k_fft_cols: a CTA walks over tiles with stride gridDim.x; while tile t is
+// transformed in one shared-memory buffer, the 16-byte cp.async copies of tile t+1 are already in flight into the
+// other one (zero-fill form for rows outside the input window), so the global-load latency is off the critical
+// path regardless of how many CTAs fit an SM.
+template <int EPT, int CLS, int NT>
+__global__ void __launch_bounds__(NT, (NT <= 256) ? 2 : 1)
+k_fft_cols_pipe(FftPlanDev P, const cplx* in, cplx* out, int64_t elem_stride, int64_t n_inner, int64_t outer_stride, int C,
+                int logC, int sign, double scale, int tw_mode, const cplx* __restrict__ tw_big, RowWindow W,
+                int64_t ntiles_total, int buf_elems) {
+    extern __shared__ cplx smem[];
+    const int n = P.n, tid = threadIdx.x, nt = blockDim.x;
+    const int64_t tiles = (n_inner + C - 1) >> logC;
+    const int total = n << logC;
+    auto issue = [&](int64_t tile, cplx* buf) {
+        const int o = (int)(tile / tiles);
+        const int64_t c0 = (tile - (int64_t)o * tiles) << logC;
+        const int cw = (int)min((int64_t)C, n_inner - c0);
+        const int64_t base = (int64_t)o * outer_stride + c0;
+        const int row_base = o * W.row_o;
+        for (int i = tid; i < total; i += nt) {
+            const int c = i & (C - 1), e = i >> logC;
+            const int row = row_base + e * W.row_e;
+            const bool live = (c < cw) && row >= W.in_lo && row < W.in_hi;
+            cp_async16(buf + PADI(i), live ? in + base + (int64_t)e * elem_stride + c : in, live ? 16 : 0);
+        }
+        cp_async_commit();
+    };
+    int64_t tile = blockIdx.x;
+    int cur = 0;
+    if (tile < ntiles_total) issue(tile, smem);
+    for (; tile < ntiles_total; tile += gridDim.x, cur ^= 1) {
+        cplx* buf = smem + (size_t)cur * buf_elems;
+        const int64_t next = tile + gridDim.x;
+        if (next < ntiles_total) {
+            issue(next, smem + (size_t)(cur ^ 1) * buf_elems);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const int o = (int)(tile / tiles);
+        const int64_t c0 = (tile - (int64_t)o * tiles) << logC;
+        const int cw = (int)min((int64_t)C, n_inner - c0);
+        const int64_t base = (int64_t)o * outer_stride + c0;
+        const int row_base = o * W.row_o;
+        if (tw_mode == 2) {
+            for (int i = tid; i < total; i += nt) {
+                const int e = i >> logC;
+                const cplx w = tw_big[o * e];
+                const cplx v = buf[PADI(i)];
+                buf[PADI(i)] = (sign < 0) ? cmul(v, w) : cmulc(v, w);
+            }
+            __syncthreads();
+        }
+        tile_fft<1, EPT, CLS>(buf, P, C, logC, sign, tid, nt);
+        for (int i = tid; i < total; i += nt) {
+            const int c = i & (C - 1), e = i >> logC;
+            const int row = row_base + e * W.row_e;
+            if (c < cw && row >= W.out_lo && row < W.out_hi) {
+                cplx v = buf[PADI(i)];
+                if (tw_mode == 1) {
+                    const cplx w = tw_big[o * e];
+                    v = (sign < 0) ? cmul(v, w) : cmulc(v, w);
+                }
+                out[base + (int64_t)e * elem_stride + c] = cscale(v, scale);
+            }
+        }
+        __syncthreads();     // the buffer is refilled two iterations from now by other threads' copies
     }
 }
 
@@ -353,7 +431,18 @@ int fft_cols_windowed(FftPlan* p, const cplx* in, cplx* out, int64_t elem_stride
         fout = std::min(1.0, std::max(0.0, (double)(W.out_hi - W.out_lo)) / rows);
     }
     KERNEL_TAG("k_fft_cols", 16.0 * (fin + fout) * (double)n * (double)n_inner * (double)n_outer);
-    FFT_TILE_LAUNCH(k_fft_cols, ept, p->pow2, g, t, smem, st, p->d, in, out, elem_stride, n_inner, outer_stride, C, logC, sign, scale, tw_mode, tw_big, W);
+    const int64_t ntiles_total = (int64_t)tiles * n_outer;
+    const int buf_elems = (int)(PADI((int64_t)n * C) + 1);
+    const size_t smem2 = 2 * sizeof(cplx) * (size_t)buf_elems;
+    const int per_sm = std::max<int>(1, std::min<int>(4, (int)((200 * 1024) / smem2)));
+    const int64_t pgrid = (int64_t)ipde_num_sms() * per_sm;
+    if (g_fft_pipeline && smem2 <= 200 * 1024 && ntiles_total >= 2 * pgrid) {
+        const unsigned gp = (unsigned)pgrid;
+        FFT_TILE_LAUNCH(k_fft_cols_pipe, ept, p->pow2, gp, t, smem2, st, p->d, in, out, elem_stride, n_inner, outer_stride, C, logC,
+                        sign, scale, tw_mode, tw_big, W, ntiles_total, buf_elems);
+    } else {
+        FFT_TILE_LAUNCH(k_fft_cols, ept, p->pow2, g, t, smem, st, p->d, in, out, elem_stride, n_inner, outer_stride, C, logC, sign, scale, tw_mode, tw_big, W);
+    }
     if (rc) return rc;
     KERNEL_CHECK();
     return IPDE_OK;

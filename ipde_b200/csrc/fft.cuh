@@ -318,3 +318,14 @@ static inline int fft_tile_threads(int n, int C, int ept) {
     return (int)t;
 }
 static inline size_t fft_tile_smem(int64_t elems) { return sizeof(cplx) * (size_t)(PADI(elems) + 1); }
+
+// ---- cp.async helpers (16-byte global -> shared copies, zero fill when src_bytes == 0) for the double-buffered
+// persistent tile kernels
+__device__ __forceinline__ void cp_async16(cplx* smem_dst, const cplx* gmem_src, int src_bytes) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+bool fft_pipeline_enabled();
