@@ -77,3 +77,22 @@ def stokes_manufactured(ebdyc):
     fv_f = lambda x, y: -a*b*cos(a*x)*psiy(x, y)*(1 + (a/b)**2*sin(a*x)*(3 + sin(a*x))) + p_b*cos(p_b*y)*esin(p_b*y)
     E = lambda f: EmbeddedFunction(ebdyc, function=f)
     return E(fu_f), E(fv_f), E(u_f), E(v_f), E(p_f), (u_f, v_f, p_f)
+
+
+def four_bodies(nb=100, M=8, bump=False):
+    """BASELINE configs[2]: examples/multi_modified_helmholtz.py:34-36 (interior star + exterior squished circle +
+    exterior star), scaled to a unit interior star, plus the 4th exterior body BASELINE asks for (declared in
+    SURVEY.md 8(d).3: a 4-armed star)."""
+    bdy1 = GSB(c=star(4*nb, r=1.0, a=0.05, f=7))
+    bdy2 = GSB(c=squished_circle(nb, x=-0.4, y=-0.25, r=0.25, b=0.6, rot=-np.pi/4))
+    bdy3 = GSB(c=star(nb, x=0.35, y=0.2, r=0.22, a=0.1, f=3))
+    bdy4 = GSB(c=star(nb, x=-0.17, y=0.5, r=0.2, a=0.15, f=4))
+    bdys = [bdy1, bdy2, bdy3, bdy4]
+    bh = min(b.dt*b.speed.min() for b in bdys)
+    MOL = SlepianMollifier(2*M)
+    ebdys = [EmbeddedBoundary(b, b is bdy1, M, bh, heaviside=MOL.step) for b in bdys]
+    ebdyc = EmbeddedBoundaryCollection(ebdys)
+    ebdyc.generate_grid(force_square=True)
+    if bump:
+        ebdyc.ready_bump(MOL.bump)
+    return ebdyc

@@ -178,3 +178,19 @@ def test_stokes_three_boundaries():
     for got, ref, s in ((u, uo, scale), (v, vo, scale), (p, po, np.abs(po).max())):
         linf = np.abs(np.asarray(got) - ref).max()/s
         assert linf < 1e-9, linf
+
+
+@pytest.mark.parametrize('backend', ['direct', 'ewald'])
+def test_modified_helmholtz_four_boundaries(backend):
+    """BASELINE configs[2] geometry (4-boundary collection), both evaluation back-ends, against the CPU oracle"""
+    from problems import four_bodies
+    from ipde_b200.solvers.multi_boundary.modified_helmholtz import ModifiedHelmholtzSolver
+    ebdyc = four_bodies(nb=100, M=8)
+    assert ebdyc.N == 4
+    f, ua, _ = manufactured(ebdyc, 5.0, kk=10*np.pi/7)
+    solver = ModifiedHelmholtzSolver(ebdyc, 5.0, grid_backend=backend)
+    ue = solver(f, tol=1e-13, restart=60, maxiter=5)
+    uo = oracle_for(solver, 'modified_helmholtz', 5.0, 'spectral')(f, tol=1e-13, restart=60, maxiter=5)
+    linf, l2 = rel_errors(ue, uo)
+    assert linf < TOL and l2 < TOL, (backend, linf, l2)
+    assert len(solver.iteration_counts) == 4
