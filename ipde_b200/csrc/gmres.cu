@@ -174,12 +174,20 @@ int gmres_solve(LinearOperator* op, GmresWorkspace* ws, const cplx* b, cplx* x, 
             k_residual<<<eb, 256, 0, st>>>(b, ws->w, ws->w, len);
             KERNEL_CHECK();
         }
-        rc = dots(ws, ws->w, 1, ws->w, len, d_n, st); if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(hmisc, d_n, sizeof(cplx), cudaMemcpyDeviceToHost, st));
-        k_normalize<<<eb, 256, 0, st>>>(ws->w, V, d_n, len);
-        KERNEL_CHECK();
-        CUDA_TRY(cudaStreamSynchronize(st));
-        const double beta = sqrt(hmisc[0].x);
+        double beta;
+        if (cycle == 0) {
+            // r = b: its norm is already on the host (and still in d_n on the device)
+            k_normalize<<<eb, 256, 0, st>>>(ws->w, V, d_n, len);
+            KERNEL_CHECK();
+            beta = bnorm;
+        } else {
+            rc = dots(ws, ws->w, 1, ws->w, len, d_n, st); if (rc) return rc;
+            CUDA_TRY(cudaMemcpyAsync(hmisc, d_n, sizeof(cplx), cudaMemcpyDeviceToHost, st));
+            k_normalize<<<eb, 256, 0, st>>>(ws->w, V, d_n, len);
+            KERNEL_CHECK();
+            CUDA_TRY(cudaStreamSynchronize(st));
+            beta = sqrt(hmisc[0].x);
+        }
         if (beta <= tol * bnorm) { *relres = beta / bnorm; converged = true; break; }
         std::fill(H.begin(), H.end(), hc(0.0));
         std::fill(g.begin(), g.end(), hc(0.0));
@@ -238,12 +246,23 @@ int gmres_solve(LinearOperator* op, GmresWorkspace* ws, const cplx* b, cplx* x, 
             if (rel <= tol || hn == 0.0) converged = true;
             return IPDE_OK;
         };
-        for (int j = 0; j < restart && !converged; ++j) {
-            rc = enqueue(j); if (rc) return rc;
-            if (j >= 1) { rc = process(j - 1); if (rc) return rc; }
-        }
-        if (!converged && kdone < restart) {       // the last enqueued iteration has not been looked at yet
-            rc = process(kdone); if (rc) return rc;
+        // Speculation is suspended when the residual history predicts convergence in the iteration that is still in
+        // flight (geometric extrapolation of the last two reductions): then the host looks first.
+        double rel_hist[2] = {1.0, 1.0};      // rel after the last two processed iterations
+        int enq = 0;                          // iterations enqueued so far
+        while (!converged && kdone < restart) {
+            const bool in_flight = enq > kdone;
+            bool speculate = enq < restart;
+            if (in_flight && kdone >= 2) {
+                const double rho = rel_hist[1] / rel_hist[0];
+                if (rel_hist[1] * rho <= 4.0 * tol) speculate = false;
+            }
+            if (in_flight && enq - kdone >= 2) speculate = false;          // at most one iteration ahead
+            if (speculate) { rc = enqueue(enq); if (rc) return rc; ++enq; }
+            if (enq > kdone && (!speculate || enq - kdone >= 2 || enq == restart)) {
+                rc = process(kdone); if (rc) return rc;
+                rel_hist[0] = rel_hist[1]; rel_hist[1] = *relres;
+            }
         }
         // back substitution for the small triangular system, then y += V^T yk
         std::vector<hc> yk(kdone);
@@ -256,7 +275,7 @@ int gmres_solve(LinearOperator* op, GmresWorkspace* ws, const cplx* b, cplx* x, 
         CUDA_TRY(cudaMemcpyAsync(d_h, hmisc, sizeof(cplx) * (size_t)kdone, cudaMemcpyHostToDevice, st));
         k_add_combination<<<eb, 256, 0, st>>>(ws->y, V, kdone, d_h, len);
         KERNEL_CHECK();
-        CUDA_TRY(cudaStreamSynchronize(st));   // hst is reused next cycle
+        if (!converged) CUDA_TRY(cudaStreamSynchronize(st));   // the host staging is reused by the next cycle
     }
     *iters = total_its;
     return op->precond(ws->y, x, st);

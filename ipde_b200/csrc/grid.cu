@@ -107,77 +107,53 @@ int grid_fft2_inverse(GridPlan* g, const cplx* spec_in, cplx* spec_work, double*
 template <int EPT, int CLS, int NT>
 __global__ void __launch_bounds__(NT, (NT <= 256) ? 2 : 1)
 k_cols_mult(FftPlanDev P, const cplx* in, cplx* out, cplx* copy, int64_t elem_stride,
-            int64_t n_inner, int64_t outer_stride, int C, int logC, int do_fwd, int copy_mode, ColMult M, RowWindow W,
-            int64_t ntiles_total, int buf_elems) {
-    // persistent and double buffered: the cp.async copies of the next tile are in flight while this one is transformed
+            int64_t n_inner, int64_t outer_stride, int C, int logC, int do_fwd, int copy_mode, ColMult M, RowWindow W) {
     extern __shared__ cplx smem[];
     const int n = P.n, tid = threadIdx.x, nt = blockDim.x;
     const int64_t tiles = (n_inner + C - 1) >> logC;
+    const int o = (int)(blockIdx.x / tiles);
+    const int64_t c0 = (blockIdx.x - (int64_t)o * tiles) << logC;
+    const int cw = (int)min((int64_t)C, n_inner - c0);
+    const int64_t base = (int64_t)o * outer_stride + c0;
     const int total = n << logC;
-    auto issue = [&](int64_t tile, cplx* buf) {
-        const int o = (int)(tile / tiles);
-        const int64_t c0 = (tile - (int64_t)o * tiles) << logC;
-        const int cw = (int)min((int64_t)C, n_inner - c0);
-        const int64_t base = (int64_t)o * outer_stride + c0;
-        const int row_base = o * W.row_o;
-        for (int i = tid; i < total; i += nt) {
-            const int c = i & (C - 1), e = i >> logC;
-            const int row = row_base + e * W.row_e;
-            const bool live = (c < cw) && row >= W.in_lo && row < W.in_hi;
-            cp_async16(buf + PADI(i), live ? in + base + (int64_t)e * elem_stride + c : in, live ? 16 : 0);
-        }
-        cp_async_commit();
-    };
-    int64_t tile = blockIdx.x;
-    int cur = 0;
-    if (tile < ntiles_total) issue(tile, smem);
-    for (; tile < ntiles_total; tile += gridDim.x, cur ^= 1) {
-        cplx* buf = smem + (size_t)cur * buf_elems;
-        const int64_t next = tile + gridDim.x;
-        if (next < ntiles_total && buf_elems > 0) {
-            issue(next, smem + (size_t)(cur ^ 1) * buf_elems);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();
-        const int o = (int)(tile / tiles);
-        const int64_t c0 = (tile - (int64_t)o * tiles) << logC;
-        const int cw = (int)min((int64_t)C, n_inner - c0);
-        const int64_t base = (int64_t)o * outer_stride + c0;
-        const int row_base = o * W.row_o;
-        if (do_fwd) tile_fft<1, EPT, CLS>(buf, P, C, logC, -1, tid, nt);
-        for (int i = tid; i < total; i += nt) {
-            const int c = i & (C - 1), e = i >> logC;
-            if (c < cw) {
-                const int64_t addr = base + (int64_t)e * elem_stride + c;
-                cplx v = buf[PADI(i)];
-                if (copy_mode == 1) copy[addr] = v;
-                double m;
-                if (M.kind == 3) {
-                    m = M.table[addr];
-                } else {
-                    const int fi = o + M.fmul * e;                                   // frequency index along x
-                    const int si = (fi < (M.nx + 1) / 2) ? fi : fi - M.nx;
-                    const int jy = (int)c0 + c + M.col_offset;
-                    const double kx = TWO_PI * (double)si / ((double)M.nx * M.xh);
-                    const double ky = TWO_PI * (double)jy / ((double)M.ny * M.yh);
-                    if (M.kind == IPDE_KIND_POISSON) m = (fi == 0 && jy == 0) ? 0.0 : -1.0 / (kx * kx + ky * ky);
-                    else m = 1.0 / (M.k2c + kx * kx + ky * ky);
-                }
-                v = cscale(v, m);
-                if (copy_mode == 2) copy[addr] = v;
-                buf[PADI(i)] = v;
+    const int row_base = o * W.row_o;
+    for (int i = tid; i < total; i += nt) {
+        const int c = i & (C - 1), e = i >> logC;
+        const int row = row_base + e * W.row_e;
+        smem[PADI(i)] = (c < cw && row >= W.in_lo && row < W.in_hi) ? in[base + (int64_t)e * elem_stride + c]
+                                                                    : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    if (do_fwd) tile_fft<1, EPT, CLS>(smem, P, C, logC, -1, tid, nt);
+    for (int i = tid; i < total; i += nt) {
+        const int c = i & (C - 1), e = i >> logC;
+        if (c < cw) {
+            const int64_t addr = base + (int64_t)e * elem_stride + c;
+            cplx v = smem[PADI(i)];
+            if (copy_mode == 1) copy[addr] = v;
+            double m;
+            if (M.kind == 3) {
+                m = M.table[addr];
+            } else {
+                const int fi = o + M.fmul * e;                                   // frequency index along x
+                const int si = (fi < (M.nx + 1) / 2) ? fi : fi - M.nx;
+                const int jy = (int)c0 + c + M.col_offset;
+                const double kx = TWO_PI * (double)si / ((double)M.nx * M.xh);
+                const double ky = TWO_PI * (double)jy / ((double)M.ny * M.yh);
+                if (M.kind == IPDE_KIND_POISSON) m = (fi == 0 && jy == 0) ? 0.0 : -1.0 / (kx * kx + ky * ky);
+                else m = 1.0 / (M.k2c + kx * kx + ky * ky);
             }
+            v = cscale(v, m);
+            if (copy_mode == 2) copy[addr] = v;
+            smem[PADI(i)] = v;
         }
-        __syncthreads();
-        tile_fft<1, EPT, CLS>(buf, P, C, logC, +1, tid, nt);
-        for (int i = tid; i < total; i += nt) {
-            const int c = i & (C - 1), e = i >> logC;
-            const int row = row_base + e * W.row_e;
-            if (c < cw && row >= W.out_lo && row < W.out_hi) out[base + (int64_t)e * elem_stride + c] = buf[PADI(i)];
-        }
-        __syncthreads();
+    }
+    __syncthreads();
+    tile_fft<1, EPT, CLS>(smem, P, C, logC, +1, tid, nt);
+    for (int i = tid; i < total; i += nt) {
+        const int c = i & (C - 1), e = i >> logC;
+        const int row = row_base + e * W.row_e;
+        if (c < cw && row >= W.out_lo && row < W.out_hi) out[base + (int64_t)e * elem_stride + c] = smem[PADI(i)];
     }
 }
 
@@ -187,23 +163,10 @@ static int launch_cols_mult_one(FftPlan* p, unsigned g, int t, size_t smem, cuda
                                 int do_fwd, int copy_mode, const ColMult& M, const RowWindow& W) {
     KERNEL_TAG("k_cols_mult", (32.0 + (copy_mode ? 16.0 : 0.0) + (M.kind == 3 ? 8.0 : 0.0)) * (double)p->d.n * (double)n_inner *
                                   (double)(g / cdiv(n_inner, C)));
-    // one buffer and one tile per CTA when the tile is too large to double buffer or the grid is small
-    const int64_t ntiles_total = g;
-    const int buf_elems = (int)(smem / sizeof(cplx));
-    const size_t smem2 = 2 * smem;
-    const int per_sm = std::max<int>(1, std::min<int>(4, (int)((200 * 1024) / smem2)));
-    const int64_t pgrid = (int64_t)ipde_num_sms() * per_sm;
-    // measured on B200: double buffering pays for the plain column pass (k_fft_cols, +15%) but not here, where two
-    // transforms and the symbol sit between load and store (0.38 -> 0.59 ms per step at 2048^2): off by default
-    static const bool pipe_mult = []() { const char* e = getenv("IPDE_COLS_MULT_PIPELINE"); return e && e[0] == '1'; }();
-    if (pipe_mult && fft_pipeline_enabled() && smem2 <= 200 * 1024 && ntiles_total >= 2 * pgrid) {
-        g = (unsigned)pgrid;
-        smem = smem2;
-    }
     if (smem > 48 * 1024)
         CUDA_TRY(cudaFuncSetAttribute(k_cols_mult<EPT, CLS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_cols_mult<EPT, CLS, NT><<<g, t, smem, st>>>(p->d, in, out, copy, elem_stride, n_inner, outer_stride, C, logC, do_fwd,
-                                                  copy_mode, M, W, ntiles_total, buf_elems);
+                                                  copy_mode, M, W);
     KERNEL_CHECK();
     return IPDE_OK;
 }
