@@ -108,14 +108,15 @@ class ScalarHelper(object):
         """
         self.evaluation = mode
         self.single = single
-        self.evaluator_w = None
-        self.evaluator_r = None
-        if mode == 'ewald':
+        if not hasattr(self, 'evaluator_w'):
+            self.evaluator_w = None
+            self.evaluator_r = None
+        if mode == 'ewald' and self.evaluator_r is None:
             from ...device import FreeSpaceEvaluator
             e = self.ebdy
             g, r = self.interface_qfs_g.source, self.interface_qfs_r.source
             x0, y0, h = float(grid.xv[0]), float(grid.yv[0]), float(grid.xh)
-            if not single:
+            if not single and self.evaluator_w is None:
                 self.evaluator_w = FreeSpaceEvaluator(self.kernel_kind, self.k, x0, y0, h, g.x, g.y,
                                                       points=(e.interface.x, e.interface.y))
             self.evaluator_r = FreeSpaceEvaluator(self.kernel_kind, self.k, x0, y0, h, r.x, r.y,

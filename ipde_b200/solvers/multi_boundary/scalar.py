@@ -95,6 +95,7 @@ class ScalarSolver(object):
                 grid_out_pos=e.phys_inds[e.phys_not_in_annulus], points=pts)
         for helper in self.helpers:
             helper.set_evaluation(gb, g, single=self.ebdyc.N == 1)
+        self._helper_mode = (gb, self.ebdyc.N == 1)
 
     def _define_layer_apply(self):
         self.Layer_Apply = self.helpers[0].Layer_Apply
@@ -138,6 +139,9 @@ class ScalarSolver(object):
                                          ptr(dst), st)
         self._interface_values = (bvs, bxs, bys)
         mark('interface_interp')
+        # helpers may be shared between solvers (helpers=...): make them use this solver's evaluation mode
+        for helper in self.helpers:
+            helper.evaluation, helper.single = self._helper_mode
         # per-boundary annular solves and effective sources
         sigmag = empty((self.grid_sources.N,))
         for b, helper in enumerate(self.helpers):

@@ -194,3 +194,39 @@ def test_modified_helmholtz_four_boundaries(backend):
     linf, l2 = rel_errors(ue, uo)
     assert linf < TOL and l2 < TOL, (backend, linf, l2)
     assert len(solver.iteration_counts) == 4
+
+
+def test_full_size_properties_1024():
+    """BASELINE configs[1] at 1024^2 (n_b = 2048, M = 16), where the oracle is out of reach: size-independent
+    properties -- the two evaluation back-ends agree, the solve is linear and deterministic, and the solution
+    (after the homogeneous Dirichlet correction) reproduces the analytic one."""
+    import bench
+    import torch
+    from ipde_b200.solvers.multi_boundary.modified_helmholtz import ModifiedHelmholtzSolver
+    from ipde_b200.qfs import Modified_Helmholtz_QFS
+    import ipde_b200.device as D
+    ebdyc, f, nb = bench.build_problem(1024)
+    k = bench.HELMHOLTZ_K
+    kw = dict(tol=1e-13, restart=50, maxiter=10)
+    s_e = ModifiedHelmholtzSolver(ebdyc, k, grid_backend='ewald')
+    s_d = ModifiedHelmholtzSolver(ebdyc, k, grid_backend='direct', helpers=s_e.helpers)
+    ue = s_e(f, **kw)
+    ud = s_d(f, **kw)
+    linf, l2 = rel_errors(ue, ud)
+    assert linf < 1e-11 and l2 < 1e-11, (linf, l2)
+    # determinism and linearity
+    assert np.array_equal(np.asarray(s_e(f, **kw)), np.asarray(ue))
+    u2 = s_e(2.5*np.asarray(f) if False else 2.5*f, **kw)
+    assert rel_errors(u2, 2.5*np.asarray(ue))[0] < 1e-10
+    # analytic solution (examples/interior_modified_helmholtz.py:49-52) after an MFS Dirichlet correction
+    kk = np.pi/3
+    sol = lambda x, y: np.exp(np.sin(kk*x))*np.sin(kk*y)
+    bdy = ebdyc[0].bdy
+    qb = Modified_Helmholtz_QFS(bdy, True, True, True, k, tol=1e-13)
+    sig = qb.u2s(sol(bdy.x, bdy.y) - s_e.get_boundary_values(ue)[0])
+    pts = ebdyc.grid_and_radial_pts
+    corr = D.layer_apply_scalar(1, k, D.to_dev(qb.source.x), D.to_dev(qb.source.y), D.to_dev(sig*qb.source.weights),
+                                D.to_dev(pts.x), D.to_dev(pts.y)).cpu().numpy()
+    ua = sol(pts.x, pts.y)
+    err = np.abs(np.asarray(ue) + corr - ua).max()
+    assert err < 1e-10, err
