@@ -105,6 +105,7 @@ class EmbeddedBoundaryCollection(object):
                 print('Registering ebdy #', ei + 1, 'of', self.N)
             ebdy.register_grid(grid, index=ei + 1,
                                danger_zone_distance=danger_zone_distance, verbose=verbose)
+            ebdy.ebdyc = self          # lets the single-boundary adapters find the collection an ebdy belongs to
         # physical region: inside the interior boundary, outside every exterior one
         phys = np.ones(grid.shape, dtype=bool)
         for ebdy in self:

@@ -1,0 +1,3 @@
+from .modified_helmholtz import ModifiedHelmholtzSolver
+from .poisson import PoissonSolver
+from .stokes import StokesSolver

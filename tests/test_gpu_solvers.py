@@ -230,3 +230,18 @@ def test_full_size_properties_1024():
     ua = sol(pts.x, pts.y)
     err = np.abs(np.asarray(ue) + corr - ua).max()
     assert err < 1e-10, err
+
+
+def test_single_boundary_adapters():
+    """(f, fr) -> (uc, ur) signatures of ipde/solvers/single_boundary/interior/* on a one-boundary collection"""
+    from ipde_b200.solvers.single_boundary.interior import ModifiedHelmholtzSolver as SB_MH
+    from ipde_b200.solvers.multi_boundary.modified_helmholtz import ModifiedHelmholtzSolver
+    ebdyc = single_star(nb=200, M=8)
+    f, ua, _ = manufactured(ebdyc, 2.0)
+    multi = ModifiedHelmholtzSolver(ebdyc, 2.0)
+    ue = multi(f, tol=1e-13, restart=40, maxiter=5)
+    sb = SB_MH(ebdyc[0], 2.0)
+    uc, ur = sb(f.get_grid_value(), f[0], tol=1e-13, restart=40, maxiter=5)
+    assert uc.shape == ebdyc.grid.shape and ur.shape == (8, 200)
+    assert np.abs(uc - ue.get_grid_value()).max() < 1e-12 and np.abs(ur - ue[0]).max() < 1e-12
+    assert sb.get_bv(ur).shape == (200,)
