@@ -128,7 +128,7 @@ class QFS(object):
 
     def __init__(self, bdy, interior, slp, dlp, kernel, tol=1e-12,
                  source_upsample_factor=1.0, alpha_s=None, alpha_c=None, rho=None, rho_f=None, u2s=True,
-                 device_build=None):
+                 device_build=None, operators=True):
         self.bdy = bdy
         self.interior = interior
         self.has_slp, self.has_dlp = slp, dlp
@@ -141,6 +141,7 @@ class QFS(object):
         self.rho_f = r_f if rho_f is None else rho_f
         self.svd_cut = min(1e-11, max(1e-14, tol))
         self.want_u2s = u2s
+        self.want_operators = operators      # False: source/check geometry only (boundaries owned by another rank)
         self.on_device = False
         if device_build is None:
             device_build = bdy.N > self.DEVICE_BUILD_MIN_N and kernel.ncomp == 1 and _cuda_available()
@@ -168,6 +169,9 @@ class QFS(object):
         self.source = GSB(c=offset_curve(bM, sgn*self.alpha_s*h))
         self.check = GSB(c=offset_curve(bM, -sgn*self.alpha_c*h))
         src, chk = self.source, self.check
+        if not self.want_operators:
+            self.A = self.Sinv = self.V = self.Ab = self.Sinv_b = self.Vb = None
+            return
         if device_build:
             return self._build_on_device(bM)
         w_s = np.tile(src.weights, nc)

@@ -49,10 +49,18 @@ class ScalarHelper(object):
     kernel_kind = None       # 0 Laplace, 1 modified Helmholtz (csrc/layer.cu)
     k = 0.0
 
-    def __init__(self, ebdy, helper=None, grid_backend='pybie2d'):
+    def __init__(self, ebdy, helper=None, grid_backend='pybie2d', owned=True):
         self.ebdy = ebdy
         self.grid_backend = grid_backend
         self.interior = ebdy.interior
+        # owned=False: this boundary's annular solve / QFS / correction run on another rank (boundary sharding);
+        # only the source geometry is built here
+        self.owned = owned
+        if not owned:
+            self._get_qfs()
+            self._define_layer_apply()
+            self.iterations_last_call = -1
+            return
         if helper is None:
             self.AAG = ApproximateAnnularGeometry(ebdy.bdy.N, ebdy.M, ebdy.radial_width, ebdy.approximate_radius)
             self._define_annular_solver()

@@ -8,10 +8,10 @@ class ModifiedHelmholtzSolver(ScalarSolver):
     grid_kind = 1
 
     def __init__(self, ebdyc, k, solver_type='spectral', helpers=None, grid_backend='pybie2d',
-                 source_upsample_factor=1.0):
+                 source_upsample_factor=1.0, shard_boundaries=False):
         self.k = k
         self.source_upsample_factor = source_upsample_factor
-        super().__init__(ebdyc, solver_type, helpers, grid_backend)
+        super().__init__(ebdyc, solver_type, helpers, grid_backend, shard_boundaries=shard_boundaries)
 
     def _get_helper_combatibility(self, ebdy, helper):
         """0: start over, 1: annular solver reusable, 2: helper reusable as is"""
@@ -23,11 +23,11 @@ class ModifiedHelmholtzSolver(ScalarSolver):
             return 0
         return 1 if helper.ebdy is not ebdy else 2
 
-    def _get_helper(self, ebdy, helper):
+    def _get_helper(self, ebdy, helper, owned=True):
         c = self._get_helper_combatibility(ebdy, helper)
         if c == 0:
             return ModifiedHelmholtzHelper(ebdy, k=self.k, source_upsample_factor=self.source_upsample_factor,
-                                           grid_backend=self.grid_backend)
+                                           grid_backend=self.grid_backend, owned=owned)
         if c == 1:
             return ModifiedHelmholtzHelper(ebdy, helper.annular_solver, k=self.k,
                                            source_upsample_factor=self.source_upsample_factor,

@@ -8,8 +8,8 @@ class PoissonSolver(ScalarSolver):
     grid_kind = 0
     k = 0.0
 
-    def __init__(self, ebdyc, solver_type='spectral', AS_list=None, grid_backend=None):
-        super().__init__(ebdyc, solver_type, AS_list, grid_backend)
+    def __init__(self, ebdyc, solver_type='spectral', AS_list=None, grid_backend=None, shard_boundaries=False):
+        super().__init__(ebdyc, solver_type, AS_list, grid_backend, shard_boundaries=shard_boundaries)
 
-    def _get_helper(self, ebdy, helper):
-        return PoissonHelper(ebdy, helper, grid_backend=self.grid_backend)
+    def _get_helper(self, ebdy, helper, owned=True):
+        return PoissonHelper(ebdy, helper, grid_backend=self.grid_backend, owned=owned)

@@ -26,13 +26,15 @@ class ScalarSolver(object):
     grid_kind = None
     k = 0.0
 
-    def __init__(self, ebdyc, solver_type, helpers, grid_backend):
+    def __init__(self, ebdyc, solver_type, helpers, grid_backend, shard_boundaries=False):
         self.ebdyc = ebdyc
         self.solver_type = solver_type
         self.grid_backend = grid_backend
         if helpers is None:
             helpers = [None]*self.ebdyc.N
-        self.helpers = [self._get_helper(ebdy, helper) for ebdy, helper in zip(self.ebdyc, helpers)]
+        self._assign_boundaries(shard_boundaries)
+        self.helpers = [self._get_helper(ebdy, helper, owned=(self.owner[b] == self.rank))
+                        for b, (ebdy, helper) in enumerate(zip(self.ebdyc, helpers))]
         self.grid = self.ebdyc.grid
         self.kx, self.ky = self.ebdyc.kx, self.ebdyc.ky
         self.ikx, self.iky = self.ebdyc.ikx, self.ebdyc.iky
@@ -45,6 +47,31 @@ class ScalarSolver(object):
         self._define_grid_evaluator()
         self.iteration_counts = None
         self.timer = None          # set to a device.StageTimer to get per-stage CUDA-event times
+
+    def _assign_boundaries(self, shard):
+        """
+        Boundary sharding: with `shard_boundaries=True` under torch.distributed every boundary's
+        annular solve, QFS applies and correction run on ONE rank (greedy assignment by n_b*M, largest first); the
+        grid-sized work is replicated.  Exchanges per solve: a broadcast of every boundary's effective sources
+        (S_b doubles) before the evaluation to the grid and of its radial solution (M*n_b doubles) after the
+        correction -- both from the owning rank.  Results are bitwise identical on all ranks and to the unsharded run.
+        """
+        import torch.distributed as dist
+        self.world, self.rank = 1, 0
+        if shard and dist.is_available() and dist.is_initialized():
+            self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        cost = [e.bdy.N*e.M for e in self.ebdyc]
+        load = [0]*self.world
+        self.owner = [0]*len(cost)
+        for b in sorted(range(len(cost)), key=lambda i: -cost[i]):
+            r = min(range(self.world), key=lambda i: load[i])
+            self.owner[b] = r
+            load[r] += cost[b]
+
+    def _bcast(self, t, src):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.broadcast(t, src=src)
 
     def _collect_grid_sources(self):
         self.grid_sources = BoundaryCollection()
@@ -94,7 +121,8 @@ class ScalarSolver(object):
                 self.grid_sources.x, self.grid_sources.y, grid_nodes=(pix, piy),
                 grid_out_pos=e.phys_inds[e.phys_not_in_annulus], points=pts)
         for helper in self.helpers:
-            helper.set_evaluation(gb, g, single=self.ebdyc.N == 1)
+            if helper.owned:
+                helper.set_evaluation(gb, g, single=self.ebdyc.N == 1)
         self._helper_mode = (gb, self.ebdyc.N == 1)
 
     def _define_layer_apply(self):
@@ -142,16 +170,29 @@ class ScalarSolver(object):
         # helpers may be shared between solvers (helpers=...): make them use this solver's evaluation mode
         for helper in self.helpers:
             helper.evaluation, helper.single = self._helper_mode
+        if self.world > 1 and D.bumpy is None and self.grid_kind == 0:
+            raise Exception('Poisson solver requires ebdyc.ready_bump(...) before solving.')
         # per-boundary annular solves and effective sources
         sigmag = empty((self.grid_sources.N,))
+        its = torch.zeros(len(self.helpers), dtype=torch.int64, device=sigmag.device)
         for b, helper in enumerate(self.helpers):
+            if self.owner[b] != self.rank:
+                continue
             r0, r1 = D.radial_offsets[b], D.radial_offsets[b + 1]
             o0, o1 = D.bdy_offsets[b], D.bdy_offsets[b + 1]
             fr = f_dev[r0:r1].view(helper.ebdy.M, helper.ebdy.bdy.N)
             sg = helper(fr, bvs[o0:o1], bxs[o0:o1], bys[o0:o1], **kwargs)
             s0, s1 = self.source_offsets[b], self.source_offsets[b + 1]
             L.ipde_vec_mul(ptr(sg), ptr(self.d_gsw[s0:s1]), ptr(sigmag[s0:s1]), int(s1 - s0), st)
-        self.iteration_counts = [helper.iterations_last_call for helper in self.helpers]
+            its[b] = helper.iterations_last_call
+        if self.world > 1:
+            for b in range(len(self.helpers)):
+                s0, s1 = self.source_offsets[b], self.source_offsets[b + 1]
+                self._bcast(sigmag[s0:s1], self.owner[b])
+                self._bcast(its[b:b + 1], self.owner[b])
+            self.iteration_counts = [int(v) for v in its.cpu()]
+        else:
+            self.iteration_counts = [helper.iterations_last_call for helper in self.helpers]
         mark('annular_and_qfs')
         # all grid-side sources -> (phys, not in annulus) U (interface points); pack the grid part of the result
         res = empty((self.ebdyc.dof,))
@@ -168,7 +209,11 @@ class ScalarSolver(object):
         # radial part
         for b, helper in enumerate(self.helpers):
             o0, o1 = D.bdy_offsets[b], D.bdy_offsets[b + 1]
-            ur = helper.correct(bu_all[o0:o1])
+            if self.owner[b] == self.rank:
+                ur = helper.correct(bu_all[o0:o1])
+            else:
+                ur = empty((helper.ebdy.M, helper.ebdy.bdy.N))
+            self._bcast(ur, self.owner[b])
             mark('correct')
             db = D.ebdys[b]
             db.radial_interp(ur, db.ia_theta, db.ia_t, out=res, out_pos=db.ia_pos)
