@@ -269,17 +269,21 @@ class QFS(object):
         import torch
         U, S, Vh = torch.linalg.svd(E, full_matrices=False, driver='gesvd')
         keep = S > self.svd_cut*S[0]
-        Sinv = torch.where(keep, 1.0/torch.where(keep, S, torch.ones_like(S)), torch.zeros_like(S))
-        A = (U.T @ rhs_op).contiguous()
-        return A, Sinv.contiguous(), Vh.T.contiguous()
+        if int(keep.sum().item()) % 2:          # even count: rows stay 16-byte aligned for the device GEMV
+            keep[torch.nonzero(keep)[-1, 0]] = False
+        A = (U.T[keep] @ rhs_op).contiguous()
+        return A, (1.0/S[keep]).contiguous(), Vh[keep].T.contiguous()
 
     def _factor(self, E, rhs_op):
         """E = U S V^T  ->  (U^T rhs_op, 1/S with tiny singular values dropped, V), all C-contiguous."""
         U, S, Vt = _svd(E)
         keep = S > self.svd_cut*S[0]
-        Sinv = np.where(keep, 1.0/np.where(keep, S, 1.0), 0.0)
-        return (np.ascontiguousarray(U.T.dot(rhs_op)), np.ascontiguousarray(Sinv),
-                np.ascontiguousarray(Vt.T))
+        if int(keep.sum()) % 2:                 # even count: rows stay 16-byte aligned for the device GEMV
+            keep[np.nonzero(keep)[0][-1]] = False
+        # truncated directions contribute nothing: drop their rows of U^T rhs and columns of V (~25% of the
+        # per-solve operator traffic)
+        return (np.ascontiguousarray(U.T[keep].dot(rhs_op)), np.ascontiguousarray(1.0/S[keep]),
+                np.ascontiguousarray(Vt[keep].T))
 
     @staticmethod
     def _times_upsample(K, UF, nc):

@@ -28,13 +28,15 @@ class DeviceQFS(object):
         self.sy = to_dev(qfs.source.y)
         self.sw = to_dev(qfs.source.weights)
         self.nsrc = qfs.source.N
-        self._w = empty((self.A.shape[0],))
+        nw = self.A.shape[0] if self.Ab is None else max(self.A.shape[0], self.Ab.shape[0])
+        self._w = empty((nw,))
 
     def _two_step(self, A, Sinv, V, x):
-        n = self._w.numel()
-        gemv(A, x, out=self._w)
-        lib().ipde_vec_mul(ptr(self._w), ptr(Sinv), ptr(self._w), n, stream())
-        return gemv(V, self._w)
+        n = A.shape[0]                      # number of retained singular directions
+        w = self._w[:n]
+        gemv(A, x, out=w)
+        lib().ipde_vec_mul(ptr(w), ptr(Sinv), ptr(w), n, stream())
+        return gemv(V, w)
 
     def __call__(self, tau):
         return self._two_step(self.A, self.Sinv, self.V, tau)
