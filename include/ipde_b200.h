@@ -201,6 +201,15 @@ int ipde_ewald_set_point_targets(void* plan, int64_t n, const double* tx, const 
  * point_out = u or += u at the point targets */
 int ipde_ewald_apply(void* plan, const double* q, double* grid_out, double* point_out, int accumulate_points, void* stream);
 
+/* value and gradient with affine weights (stokeslet evaluation, ipde_b200/ewald.py: StokesEvaluator): field c
+ * (0 value, 1 d/dx, 2 d/dy) of the potential of q is added to up to two destinations,
+ *     dst[.] += (w0 + wx (x - xc) + wy (y - yc)) field_c,
+ * gdst_host / pdst_host: host arrays of 6 device addresses [field][2] (0 = unused) for the grid / point targets,
+ * gw_host / pw_host: host arrays [field][2][3] of (w0, wx, wy).  Replaces the pyfmmlib2d.SFMM sums of
+ * ipde/solvers/internals/stokes.py:26-35 at scale. */
+int ipde_ewald_set_gradient_tables(void* plan, const double* dS_host, const double* dA_host);
+int ipde_ewald_apply_fields(void* plan, const double* q, double xc, double yc, const double* gw_host,
+                            const int64_t* gdst_host, const double* pw_host, const int64_t* pdst_host, void* stream);
 /* tests: device pointer/length of a work array: 0 spread S_w, 1 last inverse transform, 2 local sums */
 int ipde_ewald_debug_buffer(void* plan, int which, double** ptr, int64_t* n);
 

@@ -341,6 +341,14 @@ int ipde_ewald_apply(void* plan, const double* q, double* grid_out, double* poin
     return ewald_apply((EwaldPlan*)plan, q, grid_out, point_out, accumulate_points, ST(stream));
 }
 
+int ipde_ewald_set_gradient_tables(void* plan, const double* dS_host, const double* dA_host) {
+    return ewald_set_gradient_tables((EwaldPlan*)plan, dS_host, dA_host);
+}
+int ipde_ewald_apply_fields(void* plan, const double* q, double xc, double yc, const double* gw_host, const int64_t* gdst_host,
+                            const double* pw_host, const int64_t* pdst_host, void* stream) {
+    return ewald_apply_fields((EwaldPlan*)plan, q, xc, yc, gw_host, reinterpret_cast<double* const*>(gdst_host), pw_host,
+                              reinterpret_cast<double* const*>(pdst_host), ST(stream));
+}
 int ipde_ewald_debug_buffer(void* plan, int which, double** ptr, int64_t* n) {
     return ewald_debug_buffer((EwaldPlan*)plan, which, ptr, n);
 }

@@ -32,6 +32,9 @@ struct EwaldPlan {
     double *sx = nullptr, *sy = nullptr;
     int nint = 0, ndeg = 0, nlog = 0;
     double *tabS = nullptr, *tabA = nullptr;
+    double *tabdS = nullptr, *tabdA = nullptr;      // d/dz tables (gradient evaluation)
+    double *Lcx = nullptr, *Lcy = nullptr;          // local gradient sums per active-tile node
+    double *pv = nullptr;                           // (3, n_pt): value, d/dx, d/dy at the point targets
     int ntiles = 0, ntx = 0, nty = 0;
     int *tile_ix = nullptr, *tile_iy = nullptr, *tile_ptr = nullptr, *tile_src = nullptr, *tile_map = nullptr;
     double *multH = nullptr, *multU = nullptr;
@@ -297,6 +300,7 @@ void ewald_plan_destroy(EwaldPlan* p) {
     cudaFree(p->spec); cudaFree(p->specw);
     cudaFree(p->og_lin); cudaFree(p->og_out); cudaFree(p->og_loc); cudaFree(p->ptx); cudaFree(p->pty);
     cudaFree(p->tile_mask);
+    cudaFree(p->tabdS); cudaFree(p->tabdA); cudaFree(p->Lcx); cudaFree(p->Lcy); cudaFree(p->pv);
     delete p;
 }
 
@@ -375,7 +379,7 @@ int ewald_apply(EwaldPlan* p, const double* q, double* grid_out, double* point_o
                           G->ny, G->pitch, st);
     if (rc) return rc;
     ColMult MU, MH;
-    MU.kind = 3; MU.k2c = 0.0; MU.table = p->multU; MU.fmul = 1; MU.ny = 0; MU.col_offset = 0;
+    MU.kind = 3; MU.k2c = 0.0; MU.table = p->multU; MU.fmul = 1; MU.ny = 0; MU.col_offset = 0; MU.deriv = 0;
     MH = MU; MH.table = p->multH;
     // first field: forward columns, symbol, inverse columns in one pass (the plain 2-D spectrum is kept in
     // p->spec when a second field follows); second field: symbol + inverse columns from that copy
@@ -403,6 +407,297 @@ int ewald_apply(EwaldPlan* p, const double* q, double* grid_out, double* point_o
                                            p->tile_src, p->sx, p->sy, q, T, p->x0, p->y0, p->h, p->rc2, two_xi2,
                                            wnorm * p->h * p->h, p->m, p->px, p->py, point_out, accumulate_points);
         KERNEL_CHECK();
+    }
+    return IPDE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Value AND gradient of the potential, accumulated with affine weights: the building block of the stokeslet
+// evaluation (ipde_b200/ewald.py: StokesEvaluator).  Field c (0 value, 1 d/dx, 2 d/dy) of the potential of the
+// charges q is added to up to two destination arrays as
+//      dst[pos] += (w0 + wx (x - xc) + wy (y - yc)) * field_c(x, y)
+// at the grid targets (dst indexed by the targets' out_pos) and at the point targets (dst indexed by point).
+struct EwaldTabG {
+    const double *S, *A, *dS, *dA;
+    int nint, ndeg, nlog;
+    double inv_dz;
+};
+
+__device__ __forceinline__ double ew_clenshaw(const double* __restrict__ c, int ndeg, double t) {
+    const double t2 = 2.0 * t;
+    double b0 = 0.0, b1 = 0.0;
+    for (int k = ndeg - 1; k >= 1; --k) {
+        const double tmp = fma(t2, b0, c[k]) - b1;
+        b1 = b0; b0 = tmp;
+    }
+    return fma(t, b0, c[0]) - b1;
+}
+
+// G_loc and dG_loc/dz at z = r^2 (tables in shared memory: S, A, dS, dA consecutively, each nint*ndeg)
+__device__ __forceinline__ void ewald_gloc_grad(double z, const double* __restrict__ sh, int nint, int ndeg, int nlog,
+                                                double inv_dz, double* g, double* dg) {
+    const double u = z * inv_dz;
+    int i = (int)u;
+    if (i > nint - 1) i = nint - 1;
+    const double t = 2.0 * (u - (double)i) - 1.0;
+    const int ntab = nint * ndeg;
+    double s = ew_clenshaw(sh + i * ndeg, ndeg, t);
+    double ds = ew_clenshaw(sh + 2 * ntab + i * ndeg, ndeg, t);
+    if (i < nlog) {
+        const double a = ew_clenshaw(sh + ntab + i * ndeg, ndeg, t);
+        const double da = ew_clenshaw(sh + 3 * ntab + i * ndeg, ndeg, t);
+        const double lg = log(z);
+        s -= a * lg;
+        ds -= da * lg + a / z;
+    }
+    *g = s; *dg = ds;
+}
+
+__global__ void __launch_bounds__(EW_TILE* EW_TILE)
+k_ewald_tiles_grad(const int* __restrict__ tile_ix, const int* __restrict__ tile_iy, const int* __restrict__ tile_ptr,
+                   const int* __restrict__ tile_src, const double* __restrict__ sx, const double* __restrict__ sy,
+                   const double* __restrict__ q, EwaldTabG T, double x0, double y0, double h, double rc2, double rw2,
+                   double two_xi2, double norm, int px, int py, double* __restrict__ Sw, double* __restrict__ Lc,
+                   double* __restrict__ Lcx, double* __restrict__ Lcy, const unsigned* __restrict__ tile_mask) {
+    __shared__ double shx[EW_CHUNK], shy[EW_CHUNK], shq[EW_CHUNK];
+    __shared__ double stab[4 * EW_MAX_TAB / 2];      // S, A, dS, dA (nint*ndeg <= 512 each)
+    const int tid = threadIdx.y * EW_TILE + threadIdx.x;
+    const int ntab = T.nint * T.ndeg;
+    for (int i = tid; i < ntab; i += EW_TILE * EW_TILE) {
+        stab[i] = T.S[i]; stab[ntab + i] = T.A[i]; stab[2 * ntab + i] = T.dS[i]; stab[3 * ntab + i] = T.dA[i];
+    }
+    const int t = blockIdx.x;
+    const int ix = tile_ix[t] * EW_TILE + threadIdx.y;
+    const int iy = tile_iy[t] * EW_TILE + threadIdx.x;
+    const double x = x0 + ix * h, y = y0 + iy * h;
+    const int s0 = tile_ptr[t], s1 = tile_ptr[t + 1];
+    const bool want_local = tile_mask ? ((tile_mask[t * 8 + (tid >> 5)] >> (tid & 31)) & 1u) : false;
+    double spread = 0.0, loc = 0.0, lx = 0.0, ly = 0.0;
+    for (int base = s0; base < s1; base += EW_CHUNK) {
+        const int cnt = min(EW_CHUNK, s1 - base);
+        __syncthreads();
+        if (tid < cnt) {
+            const int s = tile_src[base + tid];
+            shx[tid] = sx[s]; shy[tid] = sy[s]; shq[tid] = q[s];
+        }
+        __syncthreads();
+        for (int i = 0; i < cnt; ++i) {
+            const double dx = x - shx[i], dy = y - shy[i];
+            const double d2 = dx * dx + dy * dy;
+            if (d2 < rw2) spread = fma(shq[i], exp(-two_xi2 * d2), spread);
+            if (want_local && d2 < rc2 && d2 > 0.0) {
+                double g, dg;
+                ewald_gloc_grad(d2, stab, T.nint, T.ndeg, T.nlog, T.inv_dz, &g, &dg);
+                loc = fma(shq[i], g, loc);
+                const double c = 2.0 * shq[i] * dg;
+                lx = fma(c, dx, lx); ly = fma(c, dy, ly);
+            }
+        }
+    }
+    if (ix < px && iy < py) Sw[(int64_t)ix * py + iy] = spread * norm;
+    if (want_local) {
+        const int64_t o = (int64_t)t * (EW_TILE * EW_TILE) + tid;
+        Lc[o] = loc; Lcx[o] = lx; Lcy[o] = ly;
+    }
+}
+
+// dst[pos[i]] += (w0 + wx (x - xc) + wy (y - yc)) (U[node] + local[node])
+__global__ void k_ewald_grid_out_w(const double* __restrict__ U, const double* __restrict__ Lc, const int64_t* __restrict__ lin,
+                                   const int64_t* __restrict__ loc, const int64_t* __restrict__ pos, int64_t n, int py,
+                                   double x0, double y0, double h, double xc, double yc, double w0, double wx, double wy,
+                                   double* __restrict__ dst) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t li = lin[i];
+        double v = U[li];
+        const int64_t l = loc[i];
+        if (l >= 0) v += Lc[l];
+        const double x = x0 + (double)(li / py) * h - xc, y = y0 + (double)(li % py) * h - yc;
+        dst[pos[i]] += (w0 + wx * x + wy * y) * v;
+    }
+}
+
+// one warp per point target: value and gradient (far: Gaussian window and its derivative on H; local: tables)
+__global__ void k_ewald_points_grad(const double* __restrict__ H, const double* __restrict__ tx, const double* __restrict__ ty,
+                                    int64_t npts, const int* __restrict__ tile_map, int ntx, int nty,
+                                    const int* __restrict__ tile_ptr, const int* __restrict__ tile_src,
+                                    const double* __restrict__ sx, const double* __restrict__ sy, const double* __restrict__ q,
+                                    EwaldTabG T, double x0, double y0, double h, double rc2, double two_xi2, double wnorm, int m,
+                                    int px, int py, double* __restrict__ pv) {
+    __shared__ double stab[4 * EW_MAX_TAB / 2];
+    const int ntab = T.nint * T.ndeg;
+    for (int i = threadIdx.x; i < ntab; i += blockDim.x) {
+        stab[i] = T.S[i]; stab[ntab + i] = T.A[i]; stab[2 * ntab + i] = T.dS[i]; stab[3 * ntab + i] = T.dA[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int W = 2 * m + 1;
+    for (int64_t p = warp; p < npts; p += nwarps) {
+        const double x = tx[p], y = ty[p];
+        const double X = (x - x0) / h, Y = (y - y0) / h;
+        const int i0 = (int)ceil(X - m), j0 = (int)ceil(Y - m);
+        // lane b: weights of column b and (same index) of row b, and their derivatives
+        double wy = 0.0, wx = 0.0, dwy = 0.0, dwx = 0.0;
+        if (lane < W) {
+            const double ddx = x - (x0 + (double)(i0 + lane) * h), ddy = y - (y0 + (double)(j0 + lane) * h);
+            wx = exp(-two_xi2 * ddx * ddx);
+            wy = exp(-two_xi2 * ddy * ddy);
+            dwx = -2.0 * two_xi2 * ddx * wx;         // d/dx exp(-2 xi^2 (x - xl)^2)
+            dwy = -2.0 * two_xi2 * ddy * wy;
+        }
+        double a0 = 0.0, a1 = 0.0;     // sum_a wx_a H[a][b], sum_a dwx_a H[a][b]  for this lane's column b
+        const bool in_cols = (lane < W) && (j0 + lane >= 0) && (j0 + lane < py);
+        for (int a = 0; a < W; ++a) {
+            const double wa = __shfl_sync(0xffffffffu, wx, a);
+            const double dwa = __shfl_sync(0xffffffffu, dwx, a);
+            const int ii = i0 + a;
+            if (in_cols && ii >= 0 && ii < px) {
+                const double hv = H[(int64_t)ii * py + j0 + lane];
+                a0 = fma(wa, hv, a0); a1 = fma(dwa, hv, a1);
+            }
+        }
+        double val = a0 * wy * wnorm, gx = a1 * wy * wnorm, gy = a0 * dwy * wnorm;
+        const int fxi = (int)floor(X), fyi = (int)floor(Y);
+        const int tix = fxi / EW_TILE, tiy = fyi / EW_TILE;
+        if (fxi >= 0 && tix < ntx && fyi >= 0 && tiy < nty) {
+            const int t = tile_map[tix * nty + tiy];
+            if (t >= 0) {
+                const int s0 = tile_ptr[t], s1 = tile_ptr[t + 1];
+                for (int s = s0 + lane; s < s1; s += 32) {
+                    const int k = tile_src[s];
+                    const double dx = x - sx[k], dy = y - sy[k];
+                    const double d2 = dx * dx + dy * dy;
+                    if (d2 < rc2 && d2 > 0.0) {
+                        double g, dg;
+                        ewald_gloc_grad(d2, stab, T.nint, T.ndeg, T.nlog, T.inv_dz, &g, &dg);
+                        val = fma(q[k], g, val);
+                        const double c = 2.0 * q[k] * dg;
+                        gx = fma(c, dx, gx); gy = fma(c, dy, gy);
+                    }
+                }
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            val += __shfl_xor_sync(0xffffffffu, val, o);
+            gx += __shfl_xor_sync(0xffffffffu, gx, o);
+            gy += __shfl_xor_sync(0xffffffffu, gy, o);
+        }
+        if (lane == 0) { pv[p] = val; pv[npts + p] = gx; pv[2 * npts + p] = gy; }
+    }
+}
+
+__global__ void k_ewald_points_accum(const double* __restrict__ v, const double* __restrict__ tx, const double* __restrict__ ty,
+                                     int64_t n, double xc, double yc, double w0, double wx, double wy, double* __restrict__ dst) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] += (w0 + wx * (tx[i] - xc) + wy * (ty[i] - yc)) * v[i];
+}
+
+int ewald_set_gradient_tables(EwaldPlan* p, const double* dS_host, const double* dA_host) {
+    cudaFree(p->tabdS); cudaFree(p->tabdA);
+    p->tabdS = p->tabdA = nullptr;
+    ARG_CHECK(p->nint * p->ndeg <= EW_MAX_TAB / 2, "local-kernel table too large for the gradient kernels");
+    int rc = upload_arr(&p->tabdS, dS_host, (size_t)p->nint * p->ndeg, cudaMemcpyHostToDevice);
+    if (!rc) rc = upload_arr(&p->tabdA, dA_host, (size_t)p->nint * p->ndeg, cudaMemcpyHostToDevice);
+    return rc;
+}
+
+// gdst/pdst: host arrays of 6 device pointers [field][2] (null = unused); gw/pw: host arrays [field][2][3] of
+// (w0, wx, wy).  (xc, yc): origin of the affine weights.
+int ewald_apply_fields(EwaldPlan* p, const double* q, double xc, double yc, const double* gw, double* const* gdst,
+                       const double* pw, double* const* pdst, cudaStream_t st) {
+    ARG_CHECK(p->tabdS && p->tabdA, "gradient tables not set (ipde_ewald_set_gradient_tables)");
+    bool gf[3] = {false, false, false}, pf[3] = {false, false, false};
+    bool want_grid = false, want_pts = false;
+    for (int c = 0; c < 3; ++c)
+        for (int d = 0; d < 2; ++d) {
+            if (p->n_og > 0 && gdst && gdst[c * 2 + d]) { gf[c] = true; want_grid = true; }
+            if (p->n_pt > 0 && pdst && pdst[c * 2 + d]) { pf[c] = true; want_pts = true; }
+        }
+    if (!want_grid && !want_pts) return IPDE_OK;
+    const size_t nloc = (size_t)std::max(1, p->ntiles) * EW_TILE * EW_TILE;
+    if (!p->Lcx) {
+        CUDA_TRY(cudaMalloc(&p->Lcx, sizeof(double) * nloc));
+        CUDA_TRY(cudaMalloc(&p->Lcy, sizeof(double) * nloc));
+    }
+    if (want_pts && !p->pv) CUDA_TRY(cudaMalloc(&p->pv, sizeof(double) * 3 * (size_t)p->n_pt));
+    EwaldTabG T;
+    T.S = p->tabS; T.A = p->tabA; T.dS = p->tabdS; T.dA = p->tabdA;
+    T.nint = p->nint; T.ndeg = p->ndeg; T.nlog = p->nlog;
+    T.inv_dz = (double)p->nint / p->rc2;
+    const double two_xi2 = 2.0 * p->xi * p->xi;
+    const double ck = (p->kind == 1) ? exp(-p->kappa * p->kappa / (4.0 * p->xi * p->xi)) : 1.0;
+    const double wnorm = two_xi2 / 3.14159265358979323846;
+    if (p->ntiles > 0) {
+        KERNEL_TAG("k_ewald_tiles_grad", 32.0 * 256.0 * (double)p->ntiles);
+        k_ewald_tiles_grad<<<p->ntiles, dim3(EW_TILE, EW_TILE), 0, st>>>(p->tile_ix, p->tile_iy, p->tile_ptr, p->tile_src, p->sx,
+                                                                        p->sy, q, T, p->x0, p->y0, p->h, p->rc2, p->rw2,
+                                                                        two_xi2, ck * wnorm, p->px, p->py, p->Sw, p->Lc, p->Lcx,
+                                                                        p->Lcy, want_grid ? p->tile_mask : nullptr);
+        KERNEL_CHECK();
+    }
+    GridPlan* G = p->fft;
+    const double c2r_scale = 1.0 / ((double)G->nx * (double)G->ny) * 2.0;
+    int rc = fft_r2c_rows(G->row, p->Sw + (size_t)p->in_lo * G->ny, p->spec + (size_t)p->in_lo * G->pitch, p->in_hi - p->in_lo,
+                          G->ny, G->pitch, st);
+    if (rc) return rc;
+    ColMult M0;
+    M0.kind = 3; M0.k2c = 0.0; M0.table = p->multU; M0.fmul = 1; M0.ny = 0; M0.col_offset = 0; M0.deriv = 0;
+    // The first pass does the forward column transform and leaves the plain 2-D spectrum in p->spec; every further
+    // field is one "symbol + inverse columns" pass from that copy followed by the inverse row transform.
+    bool first = true;
+    const int gb = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(p->n_og, 256), (int64_t)ipde_num_sms() * 8));
+    const double* Ls[3] = {p->Lc, p->Lcx, p->Lcy};
+    auto field_pass = [&](const double* table, int deriv, int lo, int hi) -> int {
+        ColMult M = M0;
+        M.table = table; M.deriv = deriv;
+        int r;
+        if (first) {
+            const int win1[4] = {p->in_lo, p->in_hi, lo, hi};
+            r = grid_cols_symbol(G, p->spec, p->specw, p->spec, 1, M, st, win1);
+            first = false;
+        } else {
+            const int win2[2] = {lo, hi};
+            r = grid_cols_symbol_inverse(G, p->spec, p->specw, M, st, win2);
+        }
+        if (r) return r;
+        return fft_c2r_rows(G->row, p->specw + (size_t)lo * G->pitch, p->R + (size_t)lo * G->ny, hi - lo, G->pitch, G->ny,
+                            c2r_scale, st);
+    };
+    if (want_grid) {
+        for (int c = 0; c < 3; ++c) {
+            if (!gf[c]) continue;
+            rc = field_pass(p->multU, c, p->grid_lo, p->grid_hi);
+            if (rc) return rc;
+            for (int d = 0; d < 2; ++d) {
+                double* dst = gdst[c * 2 + d];
+                if (!dst) continue;
+                const double* w = gw + (c * 2 + d) * 3;
+                k_ewald_grid_out_w<<<gb, 256, 0, st>>>(p->R, Ls[c], p->og_lin, p->og_loc, p->og_out, p->n_og, p->py, p->x0, p->y0,
+                                                       p->h, xc, yc, w[0], w[1], w[2], dst);
+                KERNEL_CHECK();
+            }
+        }
+    }
+    if (want_pts) {
+        rc = field_pass(p->multH, 0, p->pts_lo, p->pts_hi);
+        if (rc) return rc;
+        const int pb = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(p->n_pt * 32, 256), (int64_t)ipde_num_sms() * 16));
+        KERNEL_TAG("k_ewald_points_grad", 8.0 * 961.0 * (double)p->n_pt);
+        k_ewald_points_grad<<<pb, 256, 0, st>>>(p->R, p->ptx, p->pty, p->n_pt, p->tile_map, p->ntx, p->nty, p->tile_ptr,
+                                                p->tile_src, p->sx, p->sy, q, T, p->x0, p->y0, p->h, p->rc2, two_xi2,
+                                                wnorm * p->h * p->h, p->m, p->px, p->py, p->pv);
+        KERNEL_CHECK();
+        const int ab = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(p->n_pt, 256), 2048));
+        for (int c = 0; c < 3; ++c)
+            for (int d = 0; d < 2; ++d) {
+                double* dst = pdst[c * 2 + d];
+                if (!dst) continue;
+                const double* w = pw + (c * 2 + d) * 3;
+                k_ewald_points_accum<<<ab, 256, 0, st>>>(p->pv + (size_t)c * p->n_pt, p->ptx, p->pty, p->n_pt, xc, yc, w[0], w[1],
+                                                         w[2], dst);
+                KERNEL_CHECK();
+            }
     }
     return IPDE_OK;
 }

@@ -13,3 +13,6 @@ int ewald_set_grid_targets(EwaldPlan* p, int64_t n, const int64_t* lin_dev, cons
 int ewald_set_point_targets(EwaldPlan* p, int64_t n, const double* tx_dev, const double* ty_dev);
 int ewald_apply(EwaldPlan* p, const double* q, double* grid_out, double* point_out, int accumulate_points, cudaStream_t st);
 int ewald_debug_buffer(EwaldPlan* p, int which, double** ptr, int64_t* n);
+int ewald_set_gradient_tables(EwaldPlan* p, const double* dS_host, const double* dA_host);
+int ewald_apply_fields(EwaldPlan* p, const double* q, double xc, double yc, const double* gw, double* const* gdst,
+                       const double* pw, double* const* pdst, cudaStream_t st);

@@ -134,6 +134,19 @@ k_cols_mult(FftPlanDev P, const cplx* in, cplx* out, cplx* copy, int64_t elem_st
             double m;
             if (M.kind == 3) {
                 m = M.table[addr];
+                if (M.deriv) {
+                    // spectral derivative of the far field: multiply by i k (zero on the unpaired Nyquist line)
+                    double kk;
+                    if (M.deriv == 1) {
+                        const int fi = o + M.fmul * e;
+                        const int si = (fi < (M.nx + 1) / 2) ? fi : fi - M.nx;
+                        kk = (M.nx % 2 == 0 && fi == M.nx / 2) ? 0.0 : TWO_PI * (double)si / ((double)M.nx * M.xh);
+                    } else {
+                        const int jy = (int)c0 + c + M.col_offset;
+                        kk = (jy == M.ny / 2) ? 0.0 : TWO_PI * (double)jy / ((double)M.ny * M.yh);
+                    }
+                    v = make_double2(-kk * v.y, kk * v.x);
+                }
             } else {
                 const int fi = o + M.fmul * e;                                   // frequency index along x
                 const int si = (fi < (M.nx + 1) / 2) ? fi : fi - M.nx;
@@ -260,7 +273,7 @@ int grid_solve_scalar_fused(GridPlan* g, int kind, double k, const double* fc, c
     if (rc) return rc;
     if (grid_fused_ok(g)) {
         ColMult M;
-        M.kind = kind; M.k2c = k * k; M.table = nullptr; M.fmul = 1; M.ny = 0; M.col_offset = 0;
+        M.kind = kind; M.k2c = k * k; M.table = nullptr; M.fmul = 1; M.ny = 0; M.col_offset = 0; M.deriv = 0;
         rc = grid_cols_symbol(g, uch, spec_work, uch, 2, M, st);
         if (rc) return rc;
     } else {
@@ -596,7 +609,7 @@ int grid_cols_symbol_slab(GridPlan* g, cplx* spec_in, cplx* spec_out, cplx* spec
                           int ny_global, double yh, int col_offset, cudaStream_t st) {
     ARG_CHECK(grid_fused_ok(g), "column length of the slab plan is not supported by the fused column pass");
     ColMult M;
-    M.kind = kind; M.k2c = k * k; M.table = nullptr; M.fmul = 1;
+    M.kind = kind; M.k2c = k * k; M.table = nullptr; M.fmul = 1; M.deriv = 0;
     M.ny = ny_global; M.yh = yh; M.col_offset = col_offset;
     return grid_cols_symbol(g, spec_in, spec_out, spec_copy, copy_mode, M, st);
 }

@@ -47,6 +47,7 @@ struct ColMult {
     int fmul;             // frequency index along x of element e of outer line o: o + fmul*e
     const double* table;  // kind 3: one real per spectrum entry, same layout as the spectrum
     int col_offset;       // global index of column 0 (slab-decomposed grids hold a block of columns)
+    int deriv;            // kind 3 only: 0 plain, 1 times i kx, 2 times i ky (Nyquist row/column -> 0)
 };
 // win (optional): {in_lo, in_hi, out_lo, out_hi} row windows of zero-padded data, see RowWindow in fft.cuh
 int grid_cols_symbol(GridPlan* g, cplx* spec_in, cplx* spec_out, cplx* spec_copy, int copy_mode, const ColMult& M,

@@ -461,6 +461,10 @@ class FreeSpaceEvaluator(object):
                                   hptr(tA), self.ntiles, hptr(tix), hptr(tiy), hptr(tptr), hptr(tsrc), hptr(tmap_c),
                                   ctypes.byref(hnd))
         self.h_plan = hnd
+        self._tab = tab
+        self._grad_ready = False
+        self.xc, self.yc = float(cx), float(cy)         # origin of the affine weights of apply_fields
+        self.d_sx, self.d_sy = d_sx, d_sy
         self.n_grid = 0
         self.n_points = 0
         if grid_nodes is not None:
@@ -484,10 +488,83 @@ class FreeSpaceEvaluator(object):
         except Exception:
             pass
 
+    def apply_fields(self, q, grid_terms=(), point_terms=()):
+        """
+        Value and gradient with affine weights: every term is (field, dst, (w0, wx, wy)) with field 0 value,
+        1 d/dx, 2 d/dy; dst[.] += (w0 + wx (x - xc) + wy (y - yc)) field  at the grid targets (dst indexed by
+        grid_out_pos) or at the point targets (dst indexed by point).  At most two terms per field and target set.
+        """
+        L_ = lib()
+        if not self._grad_ready:
+            dS, dA = np.ascontiguousarray(self._tab['dS']), np.ascontiguousarray(self._tab['dA'])
+            L_.ipde_ewald_set_gradient_tables(self.h_plan, hptr(dS), hptr(dA))
+            self._grad_ready = True
+        def pack(terms):
+            w = np.zeros((3, 2, 3))
+            d = np.zeros((3, 2), dtype=np.int64)
+            used = [0, 0, 0]
+            for field, dst, wt in terms:
+                k = used[field]
+                if k >= 2:
+                    raise IpdeError('at most two destinations per field')
+                w[field, k] = wt
+                d[field, k] = dst.data_ptr()
+                used[field] += 1
+            return np.ascontiguousarray(w), np.ascontiguousarray(d)
+        gw, gd = pack(grid_terms)
+        pw, pd = pack(point_terms)
+        L_.ipde_ewald_apply_fields(self.h_plan, ptr(q), self.xc, self.yc, hptr(gw), hptr(gd), hptr(pw), hptr(pd), stream())
+
     def __call__(self, q, grid_out=None, point_out=None, accumulate_points=False):
         """q: weighted charges (device).  grid_out[grid_out_pos] += u; returns point values (device) or None."""
         if self.n_points > 0 and point_out is None:
             point_out = empty((self.n_points,))
         lib().ipde_ewald_apply(self.h_plan, ptr(q), ptr(grid_out), ptr(point_out), 1 if accumulate_points else 0,
                                stream())
+        return point_out
+
+
+class StokesFreeSpaceEvaluator(object):
+    """
+    Stokeslet velocity and pressure sums (the pyfmmlib2d.SFMM call of ipde/solvers/internals/stokes.py:26-35) through
+    the Laplace spectral-Ewald evaluator:  with phi_j = sum G_L f_j, chi = sum G_L (y_s . f_s), G_L = -log r / 2 pi,
+        u_i = (phi_i - x_j d_i phi_j + d_i chi) / 2 ,      p = -d_j phi_j
+    (x, y_s measured from the centre of the evaluator box).  Three charge sets, each one spread + forward transform;
+    8 inverse field passes for grid targets, 3 for point targets.
+    """
+    def __init__(self, grid_x0, grid_y0, h, sx, sy, grid_nodes=None, grid_out_pos=None, points=None):
+        self.ev = FreeSpaceEvaluator(0, 0.0, grid_x0, grid_y0, h, sx, sy, grid_nodes=grid_nodes,
+                                     grid_out_pos=grid_out_pos, points=points)
+        e = self.ev
+        self.sxc = to_dev(np.ascontiguousarray(sx, dtype=float) - e.xc)
+        self.syc = to_dev(np.ascontiguousarray(sy, dtype=float) - e.yc)
+        self.n_points = e.n_points
+        self._chi = empty((e.nsrc,))
+        self._tmp = empty((e.nsrc,))
+
+    def __call__(self, fx, fy, grid_out=None, point_out=None):
+        """fx, fy: weighted force components (device, nsrc).  grid_out: (u, v, p) device vectors indexed by
+        grid_out_pos (accumulated into); point_out: (3, npts) device array (accumulated into; allocated zeroed if
+        None and the evaluator has point targets).  Returns point_out."""
+        e = self.ev
+        L_ = lib()
+        n = e.nsrc
+        L_.ipde_vec_mul(ptr(self.sxc), ptr(fx), ptr(self._chi), n, stream())
+        L_.ipde_vec_mul(ptr(self.syc), ptr(fy), ptr(self._tmp), n, stream())
+        L_.ipde_vec_axpby(1.0, ptr(self._chi), 1.0, ptr(self._tmp), ptr(self._chi), n, stream())
+        if e.n_points > 0 and point_out is None:
+            point_out = zeros((3, e.n_points))          # a tuple of three device vectors is accepted as well
+        def terms(dst):
+            if dst is None:
+                return (), (), ()
+            u, v, p = dst
+            t1 = [(0, u, (0.5, 0, 0)), (1, u, (0, -0.5, 0)), (1, p, (-1.0, 0, 0)), (2, v, (0, -0.5, 0))]
+            t2 = [(0, v, (0.5, 0, 0)), (1, u, (0, 0, -0.5)), (2, v, (0, 0, -0.5)), (2, p, (-1.0, 0, 0))]
+            t3 = [(1, u, (0.5, 0, 0)), (2, v, (0.5, 0, 0))]
+            return t1, t2, t3
+        g1, g2, g3 = terms(grid_out if e.n_grid > 0 else None)
+        p1, p2, p3 = terms((point_out[0], point_out[1], point_out[2]) if point_out is not None else None)
+        e.apply_fields(fx, g1, p1)
+        e.apply_fields(fy, g2, p2)
+        e.apply_fields(self._chi, g3, p3)
         return point_out

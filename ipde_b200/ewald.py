@@ -144,8 +144,28 @@ def local_tables(kind, kappa, xi, rc, nint=NINT, ndeg=NDEG, nlog=NLOG, check=Tru
             a = np.zeros_like(z)
         S[i] = cheb.chebfit(tn, s, ndeg - 1)
         A[i] = cheb.chebfit(tn, a, ndeg - 1)
-    tab = {'S': np.ascontiguousarray(S), 'A': np.ascontiguousarray(A), 'rc2': rc2, 'nint': nint, 'nlog': nlog,
-           'ndeg': ndeg}
+    # derivative tables d/dz (z = r^2) of both series, for gradients: dG/dz = S' - A' log z - A/z and
+    # grad G_loc = 2 (x - y) dG/dz.  d/dz = (2 nint / rc^2) d/dt on every interval.
+    scale = 2.0*nint/rc2
+    dS = np.zeros((nint, ndeg))
+    dA = np.zeros((nint, ndeg))
+    dS[:, :ndeg - 1] = np.array([cheb.chebder(S[i]) for i in range(nint)])*scale
+    dA[:, :ndeg - 1] = np.array([cheb.chebder(A[i]) for i in range(nint)])*scale
+    if kind == 0:
+        # Laplace: fit the closed forms instead of differentiating the fits (which costs 2-3 digits):
+        #   log-split intervals: A = 1/4pi (A' = 0), S' = xi^2 (1 - exp(-x))/(4 pi x), x = xi^2 z
+        #   elsewhere:           dG/dz = -exp(-xi^2 z)/(4 pi z)
+        for i in range(nint):
+            z = (i + 0.5*(tn + 1.0))*dz
+            x = xi*xi*z
+            if i < nlog:
+                val = xi*xi*(-np.expm1(-x))/(4*np.pi*x)
+            else:
+                val = -np.exp(-x)/(4*np.pi*z)
+            dS[i] = cheb.chebfit(tn, val, ndeg - 1)
+            dA[i] = 0.0
+    tab = {'S': np.ascontiguousarray(S), 'A': np.ascontiguousarray(A), 'dS': np.ascontiguousarray(dS),
+           'dA': np.ascontiguousarray(dA), 'rc2': rc2, 'nint': nint, 'nlog': nlog, 'ndeg': ndeg}
     if check:
         rng = np.random.default_rng(1)
         r = np.sqrt(rng.uniform(1e-6, 1.0, 400))*rc
@@ -175,6 +195,23 @@ def eval_local(tab, z):
     with np.errstate(divide='ignore', invalid='ignore'):
         lg = np.where(i < tab['nlog'], np.log(np.maximum(z, 1e-300)), 0.0)
     return s - a*lg
+
+
+def eval_local_dz(tab, z):
+    """d G_loc / d z from the derivative tables (NumPy statement of the device evaluation)"""
+    z = np.asarray(z, dtype=float)
+    u = np.clip(z*(tab['nint']/tab['rc2']), 0.0, tab['nint'] - 1e-9)
+    i = np.minimum(u.astype(np.int64), tab['nint'] - 1)
+    t = 2.0*(u - i) - 1.0
+    def clenshaw(C):
+        b0 = np.zeros_like(z); b1 = np.zeros_like(z)
+        for c in range(tab['ndeg'] - 1, 0, -1):
+            b0, b1 = 2.0*t*b0 - b1 + C[i, c], b0
+        return t*b0 - b1 + C[i, 0]
+    ds, da, a = clenshaw(tab['dS']), clenshaw(tab['dA']), clenshaw(tab['A'])
+    zs = np.maximum(z, 1e-300)
+    lg = np.where(i < tab['nlog'], np.log(zs), 0.0)
+    return ds - da*lg - np.where(i < tab['nlog'], a/zs, 0.0)
 
 
 def build_tiles(sx, sy, x0, y0, h, px, py, rc):

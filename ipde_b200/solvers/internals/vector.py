@@ -78,6 +78,25 @@ class VectorHelper(object):
         self._dur = empty((M, n))
         self._tau = empty((4*n,))
 
+    def set_evaluation(self, mode, grid, single):
+        """'direct': all-pairs stokeslet sums in correct(); 'ewald': spectral-Ewald evaluators on a box around this
+        boundary (annulus-side sources -> own radial points; own grid-side sources -> own interface unless the
+        collection has a single boundary, where that term is never used)."""
+        self.evaluation = mode
+        self.single = single
+        if not hasattr(self, 'evaluator_r'):
+            self.evaluator_r = None
+            self.evaluator_w = None
+        if mode == 'ewald' and self.evaluator_r is None:
+            from ...device import StokesFreeSpaceEvaluator
+            e = self.ebdy
+            g, r = self.interface_qfs_g.source, self.interface_qfs_r.source
+            x0, y0, h = float(grid.xv[0]), float(grid.yv[0]), float(grid.xh)
+            if not single:
+                self.evaluator_w = StokesFreeSpaceEvaluator(x0, y0, h, g.x, g.y, points=(e.interface.x, e.interface.y))
+            self.evaluator_r = StokesFreeSpaceEvaluator(x0, y0, h, r.x, r.y,
+                                                        points=(e.radial_x.ravel(), e.radial_y.ravel()))
+
     # ---- host conveniences with the reference's names (host arrays in, host arrays out)
     def get_boundary_values(self, fr):
         return self._bv_estimator.dot(fr)
@@ -140,14 +159,21 @@ class VectorHelper(object):
         lib().ipde_vec_mul(ptr(sigma[1]), ptr(w), ptr(q[1]), m, stream())
         return q
 
-    def correct(self, ub, vb, pb, single_ebdy):
+    def correct(self, ub, vb, pb, single_ebdy, own_field=None):
         g, r = self.d_qfs_g, self.d_qfs_r
         n = self.ebdy.bdy.N
+        ewald = getattr(self, 'evaluation', 'direct') == 'ewald'
         if single_ebdy:
             sigma_r_tot = self.sigma_r
         else:
-            q = self._weighted(self.sigma_g, g.sw)
-            w = layer_apply_stokes(g.sx, g.sy, q[0], q[1], self.d_ix, self.d_iy)
+            if own_field is not None:
+                w = own_field                  # caller-provided field of our own grid-side sources on our interface
+            else:
+                q = self._weighted(self.sigma_g, g.sw)
+                if ewald and self.evaluator_w is not None:
+                    w = self.evaluator_w(q[0], q[1])
+                else:
+                    w = layer_apply_stokes(g.sx, g.sy, q[0], q[1], self.d_ix, self.d_iy)
             Ub = empty((2*n,))
             lib().ipde_vec_axpby(1.0, ptr(ub), -1.0, ptr(w[0]), ptr(Ub[:n]), n, stream())
             lib().ipde_vec_axpby(1.0, ptr(vb), -1.0, ptr(w[1]), ptr(Ub[n:]), n, stream())
@@ -157,7 +183,11 @@ class VectorHelper(object):
                                  int(sigma_r_tot.numel()), stream())
         q = self._weighted(sigma_r_tot, r.sw)
         nt = int(self.d_rx.numel())
-        rslp = layer_apply_stokes(r.sx, r.sy, q[0], q[1], self.d_rx, self.d_ry)
-        for dst, k in ((self.ur, 0), (self.vr, 1), (self.pr, 2)):
-            lib().ipde_vec_axpby(1.0, ptr(dst), 1.0, ptr(rslp[k]), ptr(dst), nt, stream())
+        if ewald:
+            # accumulated straight into the radial blocks
+            self.evaluator_r(q[0], q[1], point_out=(self.ur.view(-1), self.vr.view(-1), self.pr.view(-1)))
+        else:
+            rslp = layer_apply_stokes(r.sx, r.sy, q[0], q[1], self.d_rx, self.d_ry)
+            for dst, k in ((self.ur, 0), (self.vr, 1), (self.pr, 2)):
+                lib().ipde_vec_axpby(1.0, ptr(dst), 1.0, ptr(rslp[k]), ptr(dst), nt, stream())
         return self.ur, self.vr, self.pr

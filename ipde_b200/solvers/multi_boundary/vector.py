@@ -42,6 +42,37 @@ class VectorSolver(object):
         self._collect_grid_sources()
         self.dev = self.ebdyc.device
         self.iteration_counts = None
+        self._define_grid_evaluator()
+
+    # S*T above which the all-pairs stokeslet sum loses to the spectral-Ewald evaluator
+    EWALD_THRESHOLD = 2.0e8
+
+    def _define_grid_evaluator(self):
+        """'direct' = all-pairs stokeslet sums (csrc/layer.cu), 'ewald' = StokesFreeSpaceEvaluator (three Laplace
+        spectral-Ewald passes with gradient fields); None / 'auto' chooses by problem size."""
+        gb = getattr(self, 'grid_backend', None)
+        if gb in (None, 'auto', 'pybie2d'):
+            work = float(self.grid_sources.N)*float(self.ebdyc.grid_pnai.N)
+            gb = 'ewald' if work > self.EWALD_THRESHOLD else 'direct'
+        if gb not in ('direct', 'ewald'):
+            raise Exception('grid_backend not recognized')
+        g = self.ebdyc.grid
+        if gb == 'ewald' and abs(g.xh - g.yh) > 1e-14*g.xh:
+            gb = 'direct'
+        self.evaluation = gb
+        self.evaluator_g = None
+        e = self.ebdyc
+        single = e.N == 1
+        if gb == 'ewald':
+            from ...device import StokesFreeSpaceEvaluator
+            pix, piy = np.nonzero(e.phys_not_in_annulus)
+            pts = (e.all_ivx, e.all_ivy) if not single else None
+            self.evaluator_g = StokesFreeSpaceEvaluator(float(g.xv[0]), float(g.yv[0]), float(g.xh), self.grid_sources.x,
+                                                        self.grid_sources.y, grid_nodes=(pix, piy),
+                                                        grid_out_pos=e.phys_inds[e.phys_not_in_annulus], points=pts)
+        for helper in self.helpers:
+            helper.set_evaluation(gb, g, single)
+        self._helper_mode = (gb, single)
 
     def _collect_grid_sources(self):
         self.grid_sources = BoundaryCollection()
@@ -54,7 +85,7 @@ class VectorSolver(object):
         self.source_offsets = np.concatenate([[0], np.cumsum(self.grid_sources.Ns)])
 
     def _extract_extra_kwargs(self, **kwargs):
-        pass
+        self.grid_backend = kwargs.get('grid_backend', None)
     def _get_helper(self, ebdy, AS):
         raise NotImplementedError
     def _get_specific_operators(self):
@@ -107,6 +138,8 @@ class VectorSolver(object):
             for src, dst in zip((uc, vc, ucx, ucy, vcy), outs):
                 L.ipde_grid_interp_cubic(G.h, ptr(src), D.x0, D.y0, ptr(D.iv_x), ptr(D.iv_y), n_iv, ptr(dst), st)
             bus, bvs, btxx, btxy, btyy = outs
+        for helper in self.helpers:
+            helper.evaluation, helper.single = self._helper_mode
         # per-boundary annular solves and effective sources
         nsrc = self.grid_sources.N
         sigmag = empty((2, nsrc))
@@ -121,16 +154,23 @@ class VectorSolver(object):
                 L.ipde_vec_mul(ptr(sg[c]), ptr(self.d_gsw[s0:s1]), ptr(sigmag[c, s0:s1]), int(s1 - s0), st)
         self.iteration_counts = [helper.iterations_last_call for helper in self.helpers]
         # all grid-side stokeslets -> (phys, not in annulus) U (interface points)
-        out = layer_apply_stokes(self.d_gsx, self.d_gsy, sigmag[0], sigmag[1], D.pnai_x, D.pnai_y)
         dof = self.ebdyc.dof
         res = [empty((dof,)) for _ in range(3)]
         for k, field in enumerate((uc, vc, pc)):
             L.ipde_grid_gather(ptr(field), ptr(D.phys_lin), D.n_phys, ptr(res[k]), st)
-            L.ipde_index_add(ptr(res[k]), ptr(D.pna_pos), ptr(out[k]), D.n_pna, st)
         single = len(self.ebdyc) == 1
+        if self.evaluator_g is not None:
+            iface = self.evaluator_g(sigmag[0].contiguous(), sigmag[1].contiguous(), grid_out=(res[0], res[1], res[2]))
+            if iface is None:
+                iface = empty((3, n_iv))           # single boundary: never read
+        else:
+            out = layer_apply_stokes(self.d_gsx, self.d_gsy, sigmag[0], sigmag[1], D.pnai_x, D.pnai_y)
+            for k in range(3):
+                L.ipde_index_add(ptr(res[k]), ptr(D.pna_pos), ptr(out[k]), D.n_pna, st)
+            iface = out[:, D.n_pna:]
         for b, helper in enumerate(self.helpers):
             o0, o1 = D.bdy_offsets[b], D.bdy_offsets[b + 1]
-            bi = [out[k, D.n_pna + o0:D.n_pna + o1].contiguous() for k in range(3)]
+            bi = [iface[k, o0:o1].contiguous() for k in range(3)]
             urs = helper.correct(bi[0], bi[1], bi[2], single)
             db = D.ebdys[b]
             r0, r1 = D.radial_offsets[b], D.radial_offsets[b + 1]
