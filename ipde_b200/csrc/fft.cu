@@ -2,6 +2,7 @@
 // global-memory pass fallback for lines that do not fit one CTA's shared memory.
 // Replaces the reference's numpy.fft / mkl_fft calls (ipde/utilities.py:5-12).
 #include "fft_generic.cuh"
+#include "fft_short.cuh"
 #include <algorithm>
 
 // ------------------------------------------------------------------------------------------
@@ -287,6 +288,85 @@ k_fft_cols_pipe(FftPlanDev P, const cplx* in, cplx* out, int64_t elem_stride, in
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Short power-of-two strided lines (N = RA*RB in {16, 32, 64}) held in registers, see fft_short.cuh.
+// Same contract as k_fft_cols (four-step twiddles, row windows, in == out allowed: tiles are disjoint and a tile is
+// read completely before it is written).
+template <int RA, int RB, int SIGN>
+__global__ void __launch_bounds__(128, 4)
+k_fft_cols_short(const cplx* __restrict__ tw, const cplx* in, cplx* out, int64_t elem_stride, int64_t n_inner,
+                 int64_t outer_stride, double scale, int tw_mode, const cplx* __restrict__ tw_big, RowWindow W,
+                 int tiles_per_outer, int ntiles_total) {
+    using K = ShortCfg<RA, RB>;
+    __shared__ cplx sm[2][K::TILE];
+    const int tid = threadIdx.x;
+    const int c = tid & (K::C - 1), jt = tid >> K::LOGC;
+    cplx v[8], nx[8];
+    auto load = [&](int tile, cplx (&d)[8]) {
+        const ShortTile S = short_tile<K::LOGC>(tile, tiles_per_outer, c, n_inner, outer_stride, W.row_o);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const int e = short_elem_a<RA, RB>(jt, s);
+            const int row = S.row_base + e * W.row_e;
+            d[s] = (S.colok && row >= W.in_lo && row < W.in_hi) ? in[S.base + (int64_t)e * elem_stride]
+                                                                : make_double2(0.0, 0.0);
+        }
+    };
+    int tile = blockIdx.x;
+    if (tile < ntiles_total) load(tile, v);
+    for (int buf = 0; tile < ntiles_total; tile += gridDim.x, buf ^= 1) {
+        const int next = tile + gridDim.x;
+        if (next < ntiles_total) load(next, nx);
+        const ShortTile S = short_tile<K::LOGC>(tile, tiles_per_outer, c, n_inner, outer_stride, W.row_o);
+        if (tw_mode == 2) {
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                const cplx w = tw_big[S.o * short_elem_a<RA, RB>(jt, s)];
+                v[s] = (SIGN < 0) ? cmul(v[s], w) : cmulc(v[s], w);
+            }
+        }
+        short_fft<RA, RB, SIGN>(v, sm[buf], c, jt, tw);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const int e = short_elem_b<RA, RB>(jt, s);
+            const int row = S.row_base + e * W.row_e;
+            if (S.colok && row >= W.out_lo && row < W.out_hi) {
+                cplx r = v[s];
+                if (tw_mode == 1) {
+                    const cplx w = tw_big[S.o * e];
+                    r = (SIGN < 0) ? cmul(r, w) : cmulc(r, w);
+                }
+                out[S.base + (int64_t)e * elem_stride] = cscale(r, scale);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < 8; ++s) v[s] = nx[s];
+    }
+}
+
+static const bool g_fft_short = []() { const char* e = getenv("IPDE_FFT_SHORT"); return !(e && e[0] == '0'); }();
+bool fft_short_enabled() { return g_fft_short; }
+
+template <int RA, int RB>
+static int launch_cols_short(FftPlan* p, const cplx* in, cplx* out, int64_t elem_stride, int64_t n_inner, int64_t n_outer,
+                             int64_t outer_stride, int sign, double scale, int tw_mode, const cplx* tw_big, RowWindow W,
+                             cudaStream_t st) {
+    using K = ShortCfg<RA, RB>;
+    const int64_t tiles = cdiv(n_inner, (int64_t)K::C);
+    const int64_t total = tiles * n_outer;
+    ARG_CHECK(total < (int64_t)1 << 30, "short column transform: too many tiles");
+    const int64_t per_sm = 4;
+    const unsigned g = (unsigned)std::min<int64_t>(total, (int64_t)ipde_num_sms() * per_sm);
+    if (sign < 0)
+        k_fft_cols_short<RA, RB, -1><<<g, 128, 0, st>>>(p->d.tw, in, out, elem_stride, n_inner, outer_stride, scale, tw_mode,
+                                                        tw_big, W, (int)tiles, (int)total);
+    else
+        k_fft_cols_short<RA, RB, +1><<<g, 128, 0, st>>>(p->d.tw, in, out, elem_stride, n_inner, outer_stride, scale, tw_mode,
+                                                        tw_big, W, (int)tiles, (int)total);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+
 // global-memory Stockham pass (any line length): one work item per butterfly
 template <int R>
 __global__ void k_fft_pass_global(FftPlanDev P, const cplx* __restrict__ src, cplx* __restrict__ dst, int64_t batch,
@@ -431,6 +511,11 @@ int fft_cols_windowed(FftPlan* p, const cplx* in, cplx* out, int64_t elem_stride
         fout = std::min(1.0, std::max(0.0, (double)(W.out_hi - W.out_lo)) / rows);
     }
     KERNEL_TAG("k_fft_cols", 16.0 * (fin + fout) * (double)n * (double)n_inner * (double)n_outer);
+    if (g_fft_short && p->pow2 && fft_short_size(n)) {
+        if (n == 64) return launch_cols_short<8, 8>(p, in, out, elem_stride, n_inner, n_outer, outer_stride, sign, scale, tw_mode, tw_big, W, st);
+        if (n == 32) return launch_cols_short<8, 4>(p, in, out, elem_stride, n_inner, n_outer, outer_stride, sign, scale, tw_mode, tw_big, W, st);
+        return launch_cols_short<4, 4>(p, in, out, elem_stride, n_inner, n_outer, outer_stride, sign, scale, tw_mode, tw_big, W, st);
+    }
     const int64_t ntiles_total = (int64_t)tiles * n_outer;
     const int buf_elems = (int)(PADI((int64_t)n * C) + 1);
     const size_t smem2 = 2 * sizeof(cplx) * (size_t)buf_elems;

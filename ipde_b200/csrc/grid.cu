@@ -24,7 +24,11 @@ int grid_plan_create(int nx, int ny, double xh, double yh, GridPlan** out) {
     if (rc) { delete g; return rc; }
     // columns: one pass if at least 4 adjacent columns fit next to each other in shared memory,
     // otherwise a four-step split nx = n1*n2
-    if ((int64_t)nx * 4 <= IPDE_FFT_SMEM_MAX) {
+    // (power-of-two lengths from 1024 are always split: both factors are then <= 64 up to nx = 4096 and run in the
+    // register-resident short-line kernels of fft_short.cuh, three streaming passes that beat one shared-memory
+    // pass with a single resident CTA per SM)
+    const bool split_pow2 = fft_short_enabled() && nx >= 1024 && (nx & (nx - 1)) == 0;
+    if ((int64_t)nx * 4 <= IPDE_FFT_SMEM_MAX && !split_pow2) {
         g->n1 = nx; g->n2 = 1;
         rc = fft_plan_create(nx, &g->colA);
         if (rc) { grid_plan_destroy(g); return rc; }
@@ -104,6 +108,8 @@ int grid_fft2_inverse(GridPlan* g, const cplx* spec_in, cplx* spec_work, double*
 // split otherwise; either way the multiplier costs no pass over memory of its own.
 //   symbol kinds: IPDE_KIND_POISSON / IPDE_KIND_MODHELM analytic (reference multi_boundary/poisson.py:34-38,
 //   modified_helmholtz.py:43-46), 3: table with the layout of the spectrum (free-space evaluator, ewald.cu)
+__device__ __forceinline__ cplx colmult_apply(const ColMult& M, cplx v, int64_t addr, int o, int e, int col);
+
 template <int EPT, int CLS, int NT>
 __global__ void __launch_bounds__(NT, (NT <= 256) ? 2 : 1)
 k_cols_mult(FftPlanDev P, const cplx* in, cplx* out, cplx* copy, int64_t elem_stride,
@@ -131,32 +137,7 @@ k_cols_mult(FftPlanDev P, const cplx* in, cplx* out, cplx* copy, int64_t elem_st
             const int64_t addr = base + (int64_t)e * elem_stride + c;
             cplx v = smem[PADI(i)];
             if (copy_mode == 1) copy[addr] = v;
-            double m;
-            if (M.kind == 3) {
-                m = M.table[addr];
-                if (M.deriv) {
-                    // spectral derivative of the far field: multiply by i k (zero on the unpaired Nyquist line)
-                    double kk;
-                    if (M.deriv == 1) {
-                        const int fi = o + M.fmul * e;
-                        const int si = (fi < (M.nx + 1) / 2) ? fi : fi - M.nx;
-                        kk = (M.nx % 2 == 0 && fi == M.nx / 2) ? 0.0 : TWO_PI * (double)si / ((double)M.nx * M.xh);
-                    } else {
-                        const int jy = (int)c0 + c + M.col_offset;
-                        kk = (jy == M.ny / 2) ? 0.0 : TWO_PI * (double)jy / ((double)M.ny * M.yh);
-                    }
-                    v = make_double2(-kk * v.y, kk * v.x);
-                }
-            } else {
-                const int fi = o + M.fmul * e;                                   // frequency index along x
-                const int si = (fi < (M.nx + 1) / 2) ? fi : fi - M.nx;
-                const int jy = (int)c0 + c + M.col_offset;
-                const double kx = TWO_PI * (double)si / ((double)M.nx * M.xh);
-                const double ky = TWO_PI * (double)jy / ((double)M.ny * M.yh);
-                if (M.kind == IPDE_KIND_POISSON) m = (fi == 0 && jy == 0) ? 0.0 : -1.0 / (kx * kx + ky * ky);
-                else m = 1.0 / (M.k2c + kx * kx + ky * ky);
-            }
-            v = cscale(v, m);
+            v = colmult_apply(M, v, addr, o, e, (int)c0 + c);
             if (copy_mode == 2) copy[addr] = v;
             smem[PADI(i)] = v;
         }
@@ -168,6 +149,107 @@ k_cols_mult(FftPlanDev P, const cplx* in, cplx* out, cplx* copy, int64_t elem_st
         const int row = row_base + e * W.row_e;
         if (c < cw && row >= W.out_lo && row < W.out_hi) out[base + (int64_t)e * elem_stride + c] = smem[PADI(i)];
     }
+}
+
+// The multiplier of one spectrum entry (shared by the tile kernel and the register kernel below).
+// o: outer line, e: element of the line, col: global column inside the half spectrum (without col_offset).
+__device__ __forceinline__ cplx colmult_apply(const ColMult& M, cplx v, int64_t addr, int o, int e, int col) {
+    double m;
+    if (M.kind == 3) {
+        m = M.table[addr];
+        if (M.deriv) {
+            double kk;
+            if (M.deriv == 1) {
+                const int fi = o + M.fmul * e;
+                const int si = (fi < (M.nx + 1) / 2) ? fi : fi - M.nx;
+                kk = (M.nx % 2 == 0 && fi == M.nx / 2) ? 0.0 : TWO_PI * (double)si / ((double)M.nx * M.xh);
+            } else {
+                const int jy = col + M.col_offset;
+                kk = (jy == M.ny / 2) ? 0.0 : TWO_PI * (double)jy / ((double)M.ny * M.yh);
+            }
+            v = make_double2(-kk * v.y, kk * v.x);
+        }
+    } else {
+        const int fi = o + M.fmul * e;
+        const int si = (fi < (M.nx + 1) / 2) ? fi : fi - M.nx;
+        const int jy = col + M.col_offset;
+        const double kx = TWO_PI * (double)si / ((double)M.nx * M.xh);
+        const double ky = TWO_PI * (double)jy / ((double)M.ny * M.yh);
+        if (M.kind == IPDE_KIND_POISSON) m = (fi == 0 && jy == 0) ? 0.0 : -1.0 / (kx * kx + ky * ky);
+        else m = 1.0 / (M.k2c + kx * kx + ky * ky);
+    }
+    return cscale(v, m);
+}
+
+// Register-resident version of k_cols_mult for lines of 16, 32 or 64 (fft_short.cuh): forward transform, multiplier
+// and inverse transform of a tile with the 8 elements of a thread never leaving its registers except for the two
+// exchanges; the next tile's loads are in flight meanwhile.
+template <int RA, int RB>
+__global__ void __launch_bounds__(128, 4)
+k_cols_mult_short(const cplx* __restrict__ tw, const cplx* in, cplx* out, cplx* copy, int64_t elem_stride, int64_t n_inner,
+                  int64_t outer_stride, int do_fwd, int copy_mode, ColMult M, RowWindow W, int tiles_per_outer,
+                  int ntiles_total) {
+    using K = ShortCfg<RA, RB>;
+    __shared__ cplx sm[2][K::TILE];
+    const int tid = threadIdx.x;
+    const int c = tid & (K::C - 1), jt = tid >> K::LOGC;
+    cplx v[8], nx[8];
+    auto load = [&](int tile, cplx (&d)[8]) {
+        const ShortTile S = short_tile<K::LOGC>(tile, tiles_per_outer, c, n_inner, outer_stride, W.row_o);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const int e = do_fwd ? short_elem_a<RA, RB>(jt, s) : short_elem_b<RA, RB>(jt, s);
+            const int row = S.row_base + e * W.row_e;
+            d[s] = (S.colok && row >= W.in_lo && row < W.in_hi) ? in[S.base + (int64_t)e * elem_stride]
+                                                                : make_double2(0.0, 0.0);
+        }
+    };
+    int tile = blockIdx.x;
+    if (tile < ntiles_total) load(tile, v);
+    for (int par = 0; tile < ntiles_total; tile += gridDim.x, par ^= 1) {
+        const int next = tile + gridDim.x;
+        if (next < ntiles_total) load(next, nx);
+        const ShortTile S = short_tile<K::LOGC>(tile, tiles_per_outer, c, n_inner, outer_stride, W.row_o);
+        if (do_fwd) short_fft<RA, RB, -1>(v, sm[0], c, jt, tw);
+        if (S.colok) {
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                const int e = short_elem_b<RA, RB>(jt, s);
+                const int64_t addr = S.base + (int64_t)e * elem_stride;
+                if (copy_mode == 1) copy[addr] = v[s];
+                v[s] = colmult_apply(M, v[s], addr, S.o, e, S.col);
+                if (copy_mode == 2) copy[addr] = v[s];
+            }
+        }
+        // with the forward transform the two exchanges of a tile alternate buffers by themselves; without it
+        // consecutive tiles must
+        short_fft<RB, RA, +1>(v, sm[do_fwd ? 1 : par], c, jt, tw);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const int e = short_elem_a<RA, RB>(jt, s);
+            const int row = S.row_base + e * W.row_e;
+            if (S.colok && row >= W.out_lo && row < W.out_hi) out[S.base + (int64_t)e * elem_stride] = v[s];
+        }
+#pragma unroll
+        for (int s = 0; s < 8; ++s) v[s] = nx[s];
+    }
+}
+
+template <int RA, int RB>
+static int launch_cols_mult_short(FftPlan* p, const cplx* in, cplx* out, cplx* copy, int64_t elem_stride, int64_t n_inner,
+                                  int64_t n_outer, int64_t outer_stride, int do_fwd, int copy_mode, const ColMult& M,
+                                  const RowWindow& W, cudaStream_t st) {
+    using K = ShortCfg<RA, RB>;
+    const int64_t tiles = cdiv(n_inner, (int64_t)K::C);
+    const int64_t total = tiles * n_outer;
+    ARG_CHECK(total < (int64_t)1 << 30, "short column transform: too many tiles");
+    KERNEL_TAG("k_cols_mult", (32.0 + (copy_mode ? 16.0 : 0.0) + (M.kind == 3 ? 8.0 : 0.0)) * (double)p->d.n * (double)n_inner *
+                                  (double)n_outer);
+    const unsigned g = (unsigned)std::min<int64_t>(total, (int64_t)ipde_num_sms() * 4);
+    k_cols_mult_short<RA, RB><<<g, 128, 0, st>>>(p->d.tw, in, out, copy, elem_stride, n_inner, outer_stride, do_fwd, copy_mode,
+                                                 M, W, (int)tiles, (int)total);
+    KERNEL_CHECK();
+    return IPDE_OK;
 }
 
 template <int EPT, int CLS, int NT>
@@ -188,6 +270,11 @@ static int launch_cols_mult_one(FftPlan* p, unsigned g, int t, size_t smem, cuda
 static int cols_mult(FftPlan* p, const cplx* in, cplx* out, cplx* copy, int64_t elem_stride, int64_t n_inner, int64_t n_outer,
                      int64_t outer_stride, int do_fwd, int copy_mode, const ColMult& M, const RowWindow& W, cudaStream_t st) {
     const int n = p->d.n;
+    if (fft_short_enabled() && p->pow2 && fft_short_size(n)) {
+        if (n == 64) return launch_cols_mult_short<8, 8>(p, in, out, copy, elem_stride, n_inner, n_outer, outer_stride, do_fwd, copy_mode, M, W, st);
+        if (n == 32) return launch_cols_mult_short<8, 4>(p, in, out, copy, elem_stride, n_inner, n_outer, outer_stride, do_fwd, copy_mode, M, W, st);
+        return launch_cols_mult_short<4, 4>(p, in, out, copy, elem_stride, n_inner, n_outer, outer_stride, do_fwd, copy_mode, M, W, st);
+    }
     int C = 1;
     while ((int64_t)C * 2 * n <= IPDE_FFT_SMEM_MAX && C < 16) C *= 2;
     while (C > 1 && C / 2 >= n_inner) C /= 2;

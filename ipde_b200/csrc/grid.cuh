@@ -1,5 +1,6 @@
 #pragma once
 #include "fft.cuh"
+#include "fft_short.cuh"
 
 #define IPDE_KIND_POISSON 0
 #define IPDE_KIND_MODHELM 1

@@ -46,7 +46,8 @@ def test_fft_mul_fft(D, n):
     assert rel(y, np.fft.fft(m*np.fft.ifft(x))) < 1e-13
 
 
-@pytest.mark.parametrize('shape', [(64, 64), (96, 80), (100, 36), (2048, 128), (128, 2048), (4096, 64), (6000, 20)])
+@pytest.mark.parametrize('shape', [(64, 64), (96, 80), (100, 36), (1024, 40), (2048, 128), (128, 2048), (4096, 64), (4096, 100),
+                                   (6000, 20)])
 def test_grid_fft2(D, shape):
     nx, ny = shape
     rng = np.random.default_rng(nx + ny)
@@ -60,7 +61,7 @@ def test_grid_fft2(D, shape):
 
 
 @pytest.mark.parametrize('kind,k', [(1, 2.5), (0, 0.0)])
-@pytest.mark.parametrize('shape', [(96, 80), (2048, 64)])
+@pytest.mark.parametrize('shape', [(96, 80), (1024, 48), (2048, 64), (4096, 36)])
 def test_grid_solve_scalar(D, kind, k, shape):
     from ipde_b200._lib import lib
     nx, ny = shape
