@@ -3,6 +3,7 @@
 // Replaces the reference's numpy.fft / mkl_fft calls (ipde/utilities.py:5-12).
 #include "fft_generic.cuh"
 #include "fft_short.cuh"
+#include "fft_reg.cuh"
 #include <algorithm>
 
 // ------------------------------------------------------------------------------------------
@@ -298,14 +299,15 @@ k_fft_cols_short(const cplx* __restrict__ tw, const cplx* in, cplx* out, int64_t
                  int64_t outer_stride, double scale, int tw_mode, const cplx* __restrict__ tw_big, RowWindow W,
                  int tiles_per_outer, int ntiles_total) {
     using K = ShortCfg<RA, RB>;
-    __shared__ cplx sm[2][K::TILE];
+    constexpr int E = K::EPT;
+    __shared__ cplx sm[K::NBUF][K::TILE];
     const int tid = threadIdx.x;
     const int c = tid & (K::C - 1), jt = tid >> K::LOGC;
-    cplx v[8], nx[8];
-    auto load = [&](int tile, cplx (&d)[8]) {
+    cplx v[E], nx[K::PREFETCH ? E : 1];
+    auto load = [&](int tile, cplx* d) {
         const ShortTile S = short_tile<K::LOGC>(tile, tiles_per_outer, c, n_inner, outer_stride, W.row_o);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
+        for (int s = 0; s < E; ++s) {
             const int e = short_elem_a<RA, RB>(jt, s);
             const int row = S.row_base + e * W.row_e;
             d[s] = (S.colok && row >= W.in_lo && row < W.in_hi) ? in[S.base + (int64_t)e * elem_stride]
@@ -313,21 +315,25 @@ k_fft_cols_short(const cplx* __restrict__ tw, const cplx* in, cplx* out, int64_t
         }
     };
     int tile = blockIdx.x;
-    if (tile < ntiles_total) load(tile, v);
-    for (int buf = 0; tile < ntiles_total; tile += gridDim.x, buf ^= 1) {
-        const int next = tile + gridDim.x;
-        if (next < ntiles_total) load(next, nx);
+    if (K::PREFETCH && tile < ntiles_total) load(tile, v);
+    for (int buf = 0; tile < ntiles_total; tile += gridDim.x, buf ^= (K::NBUF - 1)) {
+        if (K::PREFETCH) {
+            const int next = tile + gridDim.x;
+            if (next < ntiles_total) load(next, nx);
+        } else {
+            load(tile, v);
+        }
         const ShortTile S = short_tile<K::LOGC>(tile, tiles_per_outer, c, n_inner, outer_stride, W.row_o);
         if (tw_mode == 2) {
 #pragma unroll
-            for (int s = 0; s < 8; ++s) {
+            for (int s = 0; s < E; ++s) {
                 const cplx w = tw_big[S.o * short_elem_a<RA, RB>(jt, s)];
                 v[s] = (SIGN < 0) ? cmul(v[s], w) : cmulc(v[s], w);
             }
         }
         short_fft<RA, RB, SIGN>(v, sm[buf], c, jt, tw);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
+        for (int s = 0; s < E; ++s) {
             const int e = short_elem_b<RA, RB>(jt, s);
             const int row = S.row_base + e * W.row_e;
             if (S.colok && row >= W.out_lo && row < W.out_hi) {
@@ -339,8 +345,10 @@ k_fft_cols_short(const cplx* __restrict__ tw, const cplx* in, cplx* out, int64_t
                 out[S.base + (int64_t)e * elem_stride] = cscale(r, scale);
             }
         }
+        if (K::PREFETCH) {
 #pragma unroll
-        for (int s = 0; s < 8; ++s) v[s] = nx[s];
+            for (int s = 0; s < E; ++s) v[s] = nx[s];
+        }
     }
 }
 
@@ -512,9 +520,9 @@ int fft_cols_windowed(FftPlan* p, const cplx* in, cplx* out, int64_t elem_stride
     }
     KERNEL_TAG("k_fft_cols", 16.0 * (fin + fout) * (double)n * (double)n_inner * (double)n_outer);
     if (g_fft_short && p->pow2 && fft_short_size(n)) {
-        if (n == 64) return launch_cols_short<8, 8>(p, in, out, elem_stride, n_inner, n_outer, outer_stride, sign, scale, tw_mode, tw_big, W, st);
-        if (n == 32) return launch_cols_short<8, 4>(p, in, out, elem_stride, n_inner, n_outer, outer_stride, sign, scale, tw_mode, tw_big, W, st);
-        return launch_cols_short<4, 4>(p, in, out, elem_stride, n_inner, n_outer, outer_stride, sign, scale, tw_mode, tw_big, W, st);
+#define CALL_SHORT(RA_, RB_) return launch_cols_short<RA_, RB_>(p, in, out, elem_stride, n_inner, n_outer, outer_stride, sign, scale, tw_mode, tw_big, W, st)
+        SHORT_DISPATCH(n, CALL_SHORT);
+#undef CALL_SHORT
     }
     const int64_t ntiles_total = (int64_t)tiles * n_outer;
     const int buf_elems = (int)(PADI((int64_t)n * C) + 1);
@@ -597,6 +605,108 @@ k_c2r_rows(FftPlanDev P, const cplx* __restrict__ half_tw, const cplx* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Real rows through the register-resident line transform (fft_reg.cuh).  One tile of L lines per CTA.
+// r2c: packed complex transform, then the untangling step needs Z[k] and Z[n-k]: one more trip through the line
+// buffer.  c2r: the tangling step reads X[k] and X[n-k] straight from global memory (the mirrored read is
+// coalesced too and hits L1/L2), so the transform starts in registers.
+static const bool g_fft_reg = []() { const char* e = getenv("IPDE_FFT_REG"); return !(e && e[0] == '0'); }();
+bool fft_reg_enabled() { return g_fft_reg; }
+
+template <int N>
+__global__ void __launch_bounds__(RegGeom<N>::NT, RegGeom<N>::MINB)
+k_r2c_rows_reg(const cplx* __restrict__ tw, const cplx* __restrict__ half_tw, const double* __restrict__ in,
+               cplx* __restrict__ out, int64_t batch, int64_t in_pitch, int64_t out_pitch) {
+    using G = RegGeom<N>;
+    using K = RegCfg<N>;
+    extern __shared__ cplx smem[];
+    const int tid = threadIdx.x;
+    const int l = tid >> G::LOGT, jt = tid & (G::T - 1);
+    cplx* line = smem + l * G::LINE;
+    const int64_t row = (int64_t)blockIdx.x * G::L + l;
+    const bool live = row < batch;
+    cplx v[G::EPT];
+    const cplx* src = reinterpret_cast<const cplx*>(in + (live ? row : 0) * in_pitch);
+#pragma unroll
+    for (int s = 0; s < G::EPT; ++s) v[s] = live ? src[reg_elem<N, K::R0>(jt, s)] : make_double2(0.0, 0.0);
+    reg_fft<N, -1, false>(v, line, jt, tw);
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < G::EPT; ++s) line[reg_pad<G::SH>(reg_elem<N, G::RLAST>(jt, s))] = v[s];
+    __syncthreads();
+    if (live) {
+        cplx* dst = out + row * out_pitch;
+#pragma unroll
+        for (int s = 0; s < G::EPT; ++s) {
+            const int k = reg_elem<N, G::RLAST>(jt, s);
+            const cplx zk = v[s];
+            const cplx zc = cconj(line[reg_pad<G::SH>(k == 0 ? 0 : N - k)]);
+            const cplx E = cscale(cadd(zk, zc), 0.5);
+            const cplx O = cmulni(cscale(csub(zk, zc), 0.5));
+            dst[k] = cadd(E, cmul(half_tw[k], O));
+            if (k == 0) dst[N] = cadd(E, cmul(half_tw[N], O));
+        }
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(RegGeom<N>::NT, RegGeom<N>::MINB)
+k_c2r_rows_reg(const cplx* __restrict__ tw, const cplx* __restrict__ half_tw, const cplx* __restrict__ in,
+               double* __restrict__ out, int64_t batch, int64_t in_pitch, int64_t out_pitch, double scale) {
+    using G = RegGeom<N>;
+    using K = RegCfg<N>;
+    extern __shared__ cplx smem[];
+    const int tid = threadIdx.x;
+    const int l = tid >> G::LOGT, jt = tid & (G::T - 1);
+    cplx* line = smem + l * G::LINE;
+    const int64_t row = (int64_t)blockIdx.x * G::L + l;
+    const bool live = row < batch;
+    cplx v[G::EPT];
+    const cplx* src = in + (live ? row : 0) * in_pitch;
+#pragma unroll
+    for (int s = 0; s < G::EPT; ++s) {
+        const int k = reg_elem<N, K::R0>(jt, s);
+        if (live) {
+            const cplx xk = src[k];
+            const cplx xc = cconj(src[N - k]);
+            const cplx E = cscale(cadd(xk, xc), 0.5);
+            const cplx O = cmulc(cscale(csub(xk, xc), 0.5), half_tw[k]);
+            v[s] = cadd(E, cmuli(O));
+        } else {
+            v[s] = make_double2(0.0, 0.0);
+        }
+    }
+    reg_fft<N, +1, false>(v, line, jt, tw);
+    if (live) {
+        cplx* dst = reinterpret_cast<cplx*>(out + row * out_pitch);
+#pragma unroll
+        for (int s = 0; s < G::EPT; ++s) dst[reg_elem<N, G::RLAST>(jt, s)] = cscale(v[s], scale);
+    }
+}
+
+template <int N>
+static int launch_r2c_reg(FftPlan* p, const double* in, cplx* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
+                          cudaStream_t st) {
+    using G = RegGeom<N>;
+    int rc = set_smem(k_r2c_rows_reg<N>, G::SMEM);
+    if (rc) return rc;
+    k_r2c_rows_reg<N><<<(unsigned)cdiv(batch, (int64_t)G::L), G::NT, G::SMEM, st>>>(p->d.tw, p->half_tw_dev, in, out, batch,
+                                                                                   in_pitch, out_pitch);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+template <int N>
+static int launch_c2r_reg(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
+                          double scale, cudaStream_t st) {
+    using G = RegGeom<N>;
+    int rc = set_smem(k_c2r_rows_reg<N>, G::SMEM);
+    if (rc) return rc;
+    k_c2r_rows_reg<N><<<(unsigned)cdiv(batch, (int64_t)G::L), G::NT, G::SMEM, st>>>(p->d.tw, p->half_tw_dev, in, out, batch,
+                                                                                   in_pitch, out_pitch, scale);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+
 // Global-memory versions of the pack / unpack steps for long rows
 __global__ void k_r2c_untangle(int n, const cplx* __restrict__ half_tw, const cplx* __restrict__ z, cplx* __restrict__ out,
                                int64_t batch, int64_t z_pitch, int64_t out_pitch) {
@@ -645,13 +755,18 @@ int fft_r2c_rows(FftPlan* p, const double* in, cplx* out, int64_t batch, int64_t
         KERNEL_CHECK();
         return IPDE_OK;
     }
+    KERNEL_TAG("k_r2c_rows", (16.0 * n + 16.0 * (n + 1)) * (double)batch);
+    if (g_fft_reg && fft_reg_size(n)) {
+#define CALL_REG(N_) return launch_r2c_reg<N_>(p, in, out, batch, in_pitch, out_pitch, st)
+        REG_DISPATCH(n, CALL_REG);
+#undef CALL_REG
+    }
     const int C = rows_per_tile(n, batch);
     const size_t smem = fft_tile_smem((int64_t)n * C);
     const int ept = tile_ept((int64_t)n * C);
     const unsigned g = (unsigned)cdiv(batch, C);
     const int t = fft_tile_threads(n, C, ept);
     int rc = IPDE_OK;
-    KERNEL_TAG("k_r2c_rows", (16.0 * n + 16.0 * (n + 1)) * (double)batch);
     FFT_TILE_LAUNCH(k_r2c_rows, ept, p->pow2, g, t, smem, st, p->d, p->half_tw_dev, in, out, batch, in_pitch, out_pitch, C);
     if (rc) return rc;
     KERNEL_CHECK();
@@ -672,13 +787,18 @@ int fft_c2r_rows(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t
         KERNEL_CHECK();
         return fft_lines_global(p, z, reinterpret_cast<cplx*>(out), batch, n, 1, out_pitch / 2, 1, +1, scale, st);
     }
+    KERNEL_TAG("k_c2r_rows", (16.0 * n + 16.0 * (n + 1)) * (double)batch);
+    if (g_fft_reg && fft_reg_size(n)) {
+#define CALL_REG(N_) return launch_c2r_reg<N_>(p, in, out, batch, in_pitch, out_pitch, scale, st)
+        REG_DISPATCH(n, CALL_REG);
+#undef CALL_REG
+    }
     const int C = rows_per_tile(n, batch);
     const size_t smem = fft_tile_smem((int64_t)n * C);
     const int ept = tile_ept((int64_t)n * C);
     const unsigned g = (unsigned)cdiv(batch, C);
     const int t = fft_tile_threads(n, C, ept);
     int rc = IPDE_OK;
-    KERNEL_TAG("k_c2r_rows", (16.0 * n + 16.0 * (n + 1)) * (double)batch);
     FFT_TILE_LAUNCH(k_c2r_rows, ept, p->pow2, g, t, smem, st, p->d, p->half_tw_dev, in, out, batch, in_pitch, out_pitch, C, scale);
     if (rc) return rc;
     KERNEL_CHECK();

@@ -122,6 +122,33 @@ __device__ __forceinline__ void dft_small<8>(cplx* v, int sign, const FftPlanDev
     v[3] = cadd(e[3], o3);    v[7] = csub(e[3], o3);
 }
 
+// 16 = 4 x 4 (input index 4 n1 + n2, output index k1 + 4 k2), constant inner twiddles w16^(n2 k1)
+template <>
+__device__ __forceinline__ void dft_small<16>(cplx* v, int sign, const FftPlanDev& P) {
+    const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173, h = 0.70710678118654752440;
+    const double sg = (sign < 0) ? -1.0 : 1.0;
+    cplx y[4][4];
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) {
+        cplx a[4] = {v[n2], v[4 + n2], v[8 + n2], v[12 + n2]};
+        dft_small<4>(a, sign, P);
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) y[n2][k1] = a[k1];
+    }
+    const cplx w1 = make_double2(c1, sg * s1), w2 = make_double2(h, sg * h), w3 = make_double2(s1, sg * c1);
+    const cplx w6 = make_double2(-h, sg * h), w9 = make_double2(-c1, -sg * s1);
+    y[1][1] = cmul(y[1][1], w1); y[1][2] = cmul(y[1][2], w2); y[1][3] = cmul(y[1][3], w3);
+    y[2][1] = cmul(y[2][1], w2); y[2][2] = (sign < 0) ? cmulni(y[2][2]) : cmuli(y[2][2]); y[2][3] = cmul(y[2][3], w6);
+    y[3][1] = cmul(y[3][1], w3); y[3][2] = cmul(y[3][2], w6); y[3][3] = cmul(y[3][3], w9);
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {
+        cplx b[4] = {y[0][k1], y[1][k1], y[2][k1], y[3][k1]};
+        dft_small<4>(b, sign, P);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) v[k1 + 4 * k2] = b[k2];
+    }
+}
+
 // generic prime radix: O(R^2) with root-of-unity lookups from the plan's table
 template <int R>
 __device__ __forceinline__ void dft_generic(cplx* v, int sign, const FftPlanDev& P) {

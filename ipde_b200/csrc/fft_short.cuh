@@ -1,5 +1,5 @@
 // Register-resident short column transforms for the passes of the four-step split (power-of-two lengths
-// N = RA*RB in {16, 32, 64}).
+// N = RA*RB in {16, 32, 64, 128}).
 //
 // The tile engine of fft.cuh stages every tile in shared memory and runs its passes there (six shared-memory
 // accesses and ~180 issued instructions per element for a 64-point line).  For the short strided lines of a
@@ -30,14 +30,20 @@
 template <int RA, int RB>
 struct ShortCfg {
     static constexpr int N = RA * RB;
-    static constexpr int EPT = 8;
+    static constexpr int EPT = (N > 64) ? 16 : 8;   // elements per thread (N = 128: one radix-16 butterfly)
     static constexpr int T = N / EPT;            // threads per line
     static constexpr int C = 128 / T;            // columns per tile (128 threads per CTA)
     static constexpr int LOGC = (C == 16) ? 4 : (C == 32) ? 5 : 6;
     static constexpr int BA = EPT / RA;          // radix-RA butterflies per thread
     static constexpr int BB = EPT / RB;
-    static constexpr int TILE = N * C;           // = 1024 elements
-    static_assert(N == 16 || N == 32 || N == 64, "short transforms: N in {16, 32, 64}");
+    static constexpr int TILE = N * C;           // 1024 elements (2048 for N = 128)
+    // EPT 8: a second register set prefetches the next tile and two shared buffers alternate (one barrier per
+    // exchange).  EPT 16: the registers are taken by the tile itself; latency is hidden by the 4 resident CTAs,
+    // one shared buffer (32 KB) with a barrier before it is rewritten.
+    static constexpr bool PREFETCH = (EPT == 8);
+    static constexpr int NBUF = PREFETCH ? 2 : 1;
+    static_assert(N == 16 || N == 32 || N == 64 || N == 128, "short transforms: N in {16, 32, 64, 128}");
+    static_assert(BA >= 1 && BB >= 1, "radix larger than the elements of a thread");
 };
 
 // element index held in slot s of layout A / B
@@ -53,9 +59,11 @@ __device__ __forceinline__ int short_elem_b(int jt, int s) {
 // v: layout A on entry, layout B on exit.  sm: TILE elements.  tw[j] = exp(-2 pi i j / N).
 // Contains one __syncthreads(); the caller alternates between two buffers from one call to the next.
 template <int RA, int RB, int SIGN>
-__device__ __forceinline__ void short_fft(cplx (&v)[8], cplx* __restrict__ sm, int c, int jt, const cplx* __restrict__ tw) {
+__device__ __forceinline__ void short_fft(cplx (&v)[ShortCfg<RA, RB>::EPT], cplx* __restrict__ sm, int c, int jt,
+                                          const cplx* __restrict__ tw) {
     using K = ShortCfg<RA, RB>;
-    FftPlanDev dummy;   // dft_small<4|8> never touches the plan
+    FftPlanDev dummy;   // dft_small<4|8|16> never touches the plan
+    if (K::NBUF == 1) __syncthreads();   // readers of the previous exchange are done
 #pragma unroll
     for (int q = 0; q < K::BA; ++q) {
         dft_small<RA>(&v[q * RA], SIGN, dummy);
@@ -69,13 +77,23 @@ __device__ __forceinline__ void short_fft(cplx (&v)[8], cplx* __restrict__ sm, i
         const int j = jt + q * K::T;
 #pragma unroll
         for (int t = 0; t < RB; ++t) v[q * RB + t] = sm[((j + t * RA) << K::LOGC) + c];
-        cplx w[RB];
-        w[1] = tw[j];
-        if (SIGN > 0) w[1] = cconj(w[1]);
+        if (RB <= 8) {
+            // one table load, the other powers by a product tree (<= 3 roundings)
+            cplx w[RB];
+            w[1] = tw[j];
+            if (SIGN > 0) w[1] = cconj(w[1]);
 #pragma unroll
-        for (int t = 2; t < RB; ++t) w[t] = cmul(w[t >> 1], w[t - (t >> 1)]);
+            for (int t = 2; t < RB; ++t) w[t] = cmul(w[t >> 1], w[t - (t >> 1)]);
 #pragma unroll
-        for (int t = 1; t < RB; ++t) v[q * RB + t] = cmul(v[q * RB + t], w[t]);
+            for (int t = 1; t < RB; ++t) v[q * RB + t] = cmul(v[q * RB + t], w[t]);
+        } else {
+            // radix 16: fifteen powers would not fit the register budget next to the tile; j*t < N, read them
+#pragma unroll
+            for (int t = 1; t < RB; ++t) {
+                const cplx w = tw[j * t];
+                v[q * RB + t] = (SIGN > 0) ? cmulc(v[q * RB + t], w) : cmul(v[q * RB + t], w);
+            }
+        }
         dft_small<RB>(&v[q * RB], SIGN, dummy);
     }
 }
@@ -101,4 +119,13 @@ __device__ __forceinline__ ShortTile short_tile(int tile, int tiles_per_outer, i
 }
 
 bool fft_short_enabled();
-static inline bool fft_short_size(int n) { return n == 16 || n == 32 || n == 64; }
+static inline bool fft_short_size(int n) { return n == 16 || n == 32 || n == 64 || n == 128; }
+
+// SHORT_DISPATCH(n, CALL): CALL is a macro taking (RA, RB)
+#define SHORT_DISPATCH(n, CALL)            \
+    do {                                   \
+        if ((n) == 128) { CALL(16, 8); }   \
+        else if ((n) == 64) { CALL(8, 8); } \
+        else if ((n) == 32) { CALL(8, 4); } \
+        else { CALL(4, 4); }               \
+    } while (0)

@@ -190,14 +190,15 @@ k_cols_mult_short(const cplx* __restrict__ tw, const cplx* in, cplx* out, cplx* 
                   int64_t outer_stride, int do_fwd, int copy_mode, ColMult M, RowWindow W, int tiles_per_outer,
                   int ntiles_total) {
     using K = ShortCfg<RA, RB>;
-    __shared__ cplx sm[2][K::TILE];
+    constexpr int E = K::EPT;
+    __shared__ cplx sm[K::NBUF][K::TILE];
     const int tid = threadIdx.x;
     const int c = tid & (K::C - 1), jt = tid >> K::LOGC;
-    cplx v[8], nx[8];
-    auto load = [&](int tile, cplx (&d)[8]) {
+    cplx v[E], nx[K::PREFETCH ? E : 1];
+    auto load = [&](int tile, cplx* d) {
         const ShortTile S = short_tile<K::LOGC>(tile, tiles_per_outer, c, n_inner, outer_stride, W.row_o);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
+        for (int s = 0; s < E; ++s) {
             const int e = do_fwd ? short_elem_a<RA, RB>(jt, s) : short_elem_b<RA, RB>(jt, s);
             const int row = S.row_base + e * W.row_e;
             d[s] = (S.colok && row >= W.in_lo && row < W.in_hi) ? in[S.base + (int64_t)e * elem_stride]
@@ -205,15 +206,19 @@ k_cols_mult_short(const cplx* __restrict__ tw, const cplx* in, cplx* out, cplx* 
         }
     };
     int tile = blockIdx.x;
-    if (tile < ntiles_total) load(tile, v);
+    if (K::PREFETCH && tile < ntiles_total) load(tile, v);
     for (int par = 0; tile < ntiles_total; tile += gridDim.x, par ^= 1) {
-        const int next = tile + gridDim.x;
-        if (next < ntiles_total) load(next, nx);
+        if (K::PREFETCH) {
+            const int next = tile + gridDim.x;
+            if (next < ntiles_total) load(next, nx);
+        } else {
+            load(tile, v);
+        }
         const ShortTile S = short_tile<K::LOGC>(tile, tiles_per_outer, c, n_inner, outer_stride, W.row_o);
         if (do_fwd) short_fft<RA, RB, -1>(v, sm[0], c, jt, tw);
         if (S.colok) {
 #pragma unroll
-            for (int s = 0; s < 8; ++s) {
+            for (int s = 0; s < E; ++s) {
                 const int e = short_elem_b<RA, RB>(jt, s);
                 const int64_t addr = S.base + (int64_t)e * elem_stride;
                 if (copy_mode == 1) copy[addr] = v[s];
@@ -221,17 +226,19 @@ k_cols_mult_short(const cplx* __restrict__ tw, const cplx* in, cplx* out, cplx* 
                 if (copy_mode == 2) copy[addr] = v[s];
             }
         }
-        // with the forward transform the two exchanges of a tile alternate buffers by themselves; without it
-        // consecutive tiles must
-        short_fft<RB, RA, +1>(v, sm[do_fwd ? 1 : par], c, jt, tw);
+        // two buffers: with the forward transform the two exchanges of a tile alternate by themselves, without it
+        // consecutive tiles must; one buffer: short_fft synchronises before rewriting it
+        short_fft<RB, RA, +1>(v, sm[K::NBUF == 1 ? 0 : (do_fwd ? 1 : par)], c, jt, tw);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
+        for (int s = 0; s < E; ++s) {
             const int e = short_elem_a<RA, RB>(jt, s);
             const int row = S.row_base + e * W.row_e;
             if (S.colok && row >= W.out_lo && row < W.out_hi) out[S.base + (int64_t)e * elem_stride] = v[s];
         }
+        if (K::PREFETCH) {
 #pragma unroll
-        for (int s = 0; s < 8; ++s) v[s] = nx[s];
+            for (int s = 0; s < E; ++s) v[s] = nx[s];
+        }
     }
 }
 
@@ -271,9 +278,9 @@ static int cols_mult(FftPlan* p, const cplx* in, cplx* out, cplx* copy, int64_t 
                      int64_t outer_stride, int do_fwd, int copy_mode, const ColMult& M, const RowWindow& W, cudaStream_t st) {
     const int n = p->d.n;
     if (fft_short_enabled() && p->pow2 && fft_short_size(n)) {
-        if (n == 64) return launch_cols_mult_short<8, 8>(p, in, out, copy, elem_stride, n_inner, n_outer, outer_stride, do_fwd, copy_mode, M, W, st);
-        if (n == 32) return launch_cols_mult_short<8, 4>(p, in, out, copy, elem_stride, n_inner, n_outer, outer_stride, do_fwd, copy_mode, M, W, st);
-        return launch_cols_mult_short<4, 4>(p, in, out, copy, elem_stride, n_inner, n_outer, outer_stride, do_fwd, copy_mode, M, W, st);
+#define CALL_SHORT(RA_, RB_) return launch_cols_mult_short<RA_, RB_>(p, in, out, copy, elem_stride, n_inner, n_outer, outer_stride, do_fwd, copy_mode, M, W, st)
+        SHORT_DISPATCH(n, CALL_SHORT);
+#undef CALL_SHORT
     }
     int C = 1;
     while ((int64_t)C * 2 * n <= IPDE_FFT_SMEM_MAX && C < 16) C *= 2;

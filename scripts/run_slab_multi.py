@@ -11,6 +11,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--grid', '--n', dest='n', type=int, default=4096)
 ap.add_argument('--steps', type=int, default=10)
 ap.add_argument('--check', action='store_true')
+ap.add_argument('--profile', action='store_true', help='per-kernel CUDA-event times of one solve (library profiler)')
 a = ap.parse_args()
 rank, world, lr = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
 torch.cuda.set_device(lr)
@@ -62,5 +63,15 @@ if rank == 0:
                                            'grid_point_solves_per_s': n*n/(ms*1e-3),
                                            'alltoall_bytes_per_rank_per_solve': S.alltoall_bytes_per_rank,
                                            'alg_GBps_64B_per_point': 64.0*n*n/(ms*1e-3)/1e9}}))
+if a.profile and rank == 0:
+    import ctypes
+    from ipde_b200._lib import lib
+    lib().ipde_profile_start(D.stream())
+    S.solve(fl, out=out)
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib().ipde_profile_stop(buf, len(buf))
+    for line in buf.value.decode().strip().splitlines():
+        k, nl, ms, by = line.split()
+        print('%-24s n=%3s %8.3f ms  %8.1f GB/s' % (k, nl, float(ms), float(by)/(float(ms)*1e-3)/1e9 if float(ms) > 0 else 0))
 if world > 1:
     dist.destroy_process_group()

@@ -47,7 +47,8 @@ def test_fft_mul_fft(D, n):
 
 
 @pytest.mark.parametrize('shape', [(64, 64), (96, 80), (100, 36), (1024, 40), (2048, 128), (128, 2048), (4096, 64), (4096, 100),
-                                   (6000, 20)])
+                                   (6000, 20), (8192, 40), (16384, 36),
+                                   (9, 512), (15, 1024), (20, 2048), (10, 4096), (6, 8192), (8, 16384)])
 def test_grid_fft2(D, shape):
     nx, ny = shape
     rng = np.random.default_rng(nx + ny)
@@ -61,7 +62,7 @@ def test_grid_fft2(D, shape):
 
 
 @pytest.mark.parametrize('kind,k', [(1, 2.5), (0, 0.0)])
-@pytest.mark.parametrize('shape', [(96, 80), (1024, 48), (2048, 64), (4096, 36)])
+@pytest.mark.parametrize('shape', [(96, 80), (1024, 48), (2048, 64), (4096, 36), (8192, 36), (16384, 40)])
 def test_grid_solve_scalar(D, kind, k, shape):
     from ipde_b200._lib import lib
     nx, ny = shape
