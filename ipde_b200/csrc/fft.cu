@@ -118,6 +118,12 @@ bool fft_pipeline_enabled();
 static const bool g_fft_pipeline = []() { const char* e = getenv("IPDE_FFT_PIPELINE"); return !(e && e[0] == '0'); }();
 
 bool fft_pipeline_enabled() { return g_fft_pipeline; }
+static const bool g_fft_reg = []() { const char* e = getenv("IPDE_FFT_REG"); return !(e && e[0] == '0'); }();
+bool fft_reg_enabled() { return g_fft_reg; }
+template <int N>
+static int launch_rows_reg(FftPlan* p, const cplx* in, cplx* out, int64_t batch, int64_t in_pitch, int64_t out_pitch, int sign,
+                           double scale, cudaStream_t st);
+
 
 // elements per thread: 8 up to 4096-element tiles (<= 512 threads), 16 beyond
 static inline int tile_ept(int64_t elems) { return elems > 4096 ? 16 : 8; }
@@ -462,6 +468,11 @@ int fft_rows(FftPlan* p, const cplx* in, cplx* out, int64_t batch, int64_t in_pi
     const int t = fft_tile_threads(n, C, ept);
     int rc = IPDE_OK;
     KERNEL_TAG("k_fft_rows", 32.0 * (double)n * (double)batch);
+    if (g_fft_reg && fft_reg_size(n)) {
+#define CALL_REG(N_) return launch_rows_reg<N_>(p, in, out, batch, in_pitch, out_pitch, sign, scale, st)
+        REG_DISPATCH(n, CALL_REG);
+#undef CALL_REG
+    }
     FFT_TILE_LAUNCH(k_fft_rows, ept, p->pow2, g, t, smem, st, p->d, in, out, batch, in_pitch, out_pitch, C, sign, scale);
     if (rc) return rc;
     KERNEL_CHECK();
@@ -610,8 +621,6 @@ k_c2r_rows(FftPlanDev P, const cplx* __restrict__ half_tw, const cplx* __restric
 // r2c: packed complex transform, then the untangling step needs Z[k] and Z[n-k]: one more trip through the line
 // buffer.  c2r: the tangling step reads X[k] and X[n-k] straight from global memory (the mirrored read is
 // coalesced too and hits L1/L2), so the transform starts in registers.
-static const bool g_fft_reg = []() { const char* e = getenv("IPDE_FFT_REG"); return !(e && e[0] == '0'); }();
-bool fft_reg_enabled() { return g_fft_reg; }
 
 template <int N>
 __global__ void __launch_bounds__(RegGeom<N>::NT, RegGeom<N>::MINB)
@@ -703,6 +712,101 @@ static int launch_c2r_reg(FftPlan* p, const cplx* in, double* out, int64_t batch
     if (rc) return rc;
     k_c2r_rows_reg<N><<<(unsigned)cdiv(batch, (int64_t)G::L), G::NT, G::SMEM, st>>>(p->d.tw, p->half_tw_dev, in, out, batch,
                                                                                    in_pitch, out_pitch, scale);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+
+// Complex rows and the annular variable-coefficient multiply through the register-resident line transform.
+template <int N, int SIGN>
+__global__ void __launch_bounds__(RegGeom<N>::NT, RegGeom<N>::MINB)
+k_fft_rows_reg(const cplx* __restrict__ tw, const cplx* in, cplx* out, int64_t batch,
+               int64_t in_pitch, int64_t out_pitch, double scale) {
+    using G = RegGeom<N>;
+    using K = RegCfg<N>;
+    extern __shared__ cplx smem[];
+    const int tid = threadIdx.x;
+    const int l = tid >> G::LOGT, jt = tid & (G::T - 1);
+    cplx* line = smem + l * G::LINE;
+    const int64_t row = (int64_t)blockIdx.x * G::L + l;
+    const bool live = row < batch;
+    cplx v[G::EPT];
+    const cplx* src = in + (live ? row : 0) * in_pitch;
+#pragma unroll
+    for (int s = 0; s < G::EPT; ++s) v[s] = live ? src[reg_elem<N, K::R0>(jt, s)] : make_double2(0.0, 0.0);
+    reg_fft<N, SIGN, false>(v, line, jt, tw);
+    if (live) {
+        cplx* dst = out + row * out_pitch;
+#pragma unroll
+        for (int s = 0; s < G::EPT; ++s) dst[reg_elem<N, G::RLAST>(jt, s)] = cscale(v[s], scale);
+    }
+}
+
+// (launched with a handful of lines from the GMRES operator: latency matters, occupancy does not -- no register cap)
+template <int N>
+__global__ void __launch_bounds__(RegGeom<N>::NT, 1)
+k_fft_mul_fft_rows_reg(const cplx* __restrict__ tw, const cplx* in, cplx* out,
+                       const double* __restrict__ m, int64_t batch) {
+    using G = RegGeom<N>;
+    using K = RegCfg<N>;
+    extern __shared__ cplx smem[];
+    const int tid = threadIdx.x;
+    const int l = tid >> G::LOGT, jt = tid & (G::T - 1);
+    cplx* line = smem + l * G::LINE;
+    const int64_t row = (int64_t)blockIdx.x * G::L + l;
+    const bool live = row < batch;
+    const int64_t off = (live ? row : 0) * N;
+    cplx v[G::EPT];
+#pragma unroll
+    for (int s = 0; s < G::EPT; ++s) v[s] = live ? in[off + reg_elem<N, K::R0>(jt, s)] : make_double2(0.0, 0.0);
+    reg_fft<N, +1, false>(v, line, jt, tw);
+    const double inv = 1.0 / N;
+    if constexpr (G::RLAST == K::R0) {
+        // the outputs of the last stage sit exactly where the first stage of the next transform wants its inputs
+#pragma unroll
+        for (int s = 0; s < G::EPT; ++s)
+            v[s] = cscale(v[s], live ? m[off + reg_elem<N, K::R0>(jt, s)] * inv : 0.0);
+    } else {
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < G::EPT; ++s) {
+            const int e = reg_elem<N, G::RLAST>(jt, s);
+            line[reg_pad<G::SH>(e)] = cscale(v[s], live ? m[off + e] * inv : 0.0);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < G::EPT; ++s) v[s] = line[reg_pad<G::SH>(reg_elem<N, K::R0>(jt, s))];
+    }
+    reg_fft<N, -1, true>(v, line, jt, tw);
+    if (live) {
+#pragma unroll
+        for (int s = 0; s < G::EPT; ++s) out[off + reg_elem<N, G::RLAST>(jt, s)] = v[s];
+    }
+}
+
+template <int N>
+static int launch_rows_reg(FftPlan* p, const cplx* in, cplx* out, int64_t batch, int64_t in_pitch, int64_t out_pitch, int sign,
+                           double scale, cudaStream_t st) {
+    using G = RegGeom<N>;
+    const unsigned g = (unsigned)cdiv(batch, (int64_t)G::L);
+    int rc;
+    if (sign < 0) {
+        rc = set_smem(k_fft_rows_reg<N, -1>, G::SMEM);
+        if (rc) return rc;
+        k_fft_rows_reg<N, -1><<<g, G::NT, G::SMEM, st>>>(p->d.tw, in, out, batch, in_pitch, out_pitch, scale);
+    } else {
+        rc = set_smem(k_fft_rows_reg<N, +1>, G::SMEM);
+        if (rc) return rc;
+        k_fft_rows_reg<N, +1><<<g, G::NT, G::SMEM, st>>>(p->d.tw, in, out, batch, in_pitch, out_pitch, scale);
+    }
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+template <int N>
+static int launch_mul_fft_reg(FftPlan* p, const cplx* in, cplx* out, const double* m, int64_t batch, cudaStream_t st) {
+    using G = RegGeom<N>;
+    int rc = set_smem(k_fft_mul_fft_rows_reg<N>, G::SMEM);
+    if (rc) return rc;
+    k_fft_mul_fft_rows_reg<N><<<(unsigned)cdiv(batch, (int64_t)G::L), G::NT, G::SMEM, st>>>(p->d.tw, in, out, m, batch);
     KERNEL_CHECK();
     return IPDE_OK;
 }
@@ -862,6 +966,11 @@ int fft_mul_fft_rows(FftPlan* p, const cplx* in, cplx* out, const double* m, int
     const int t = fft_tile_threads(n, C, ept);
     int rc = IPDE_OK;
     KERNEL_TAG("k_fft_mul_fft_rows", 40.0 * (double)n * (double)batch);
+    if (g_fft_reg && fft_reg_size(n)) {
+#define CALL_REG(N_) return launch_mul_fft_reg<N_>(p, in, out, m, batch, st)
+        REG_DISPATCH(n, CALL_REG);
+#undef CALL_REG
+    }
     FFT_TILE_LAUNCH(k_fft_mul_fft_rows, ept, p->pow2, g, t, smem, st, p->d, in, out, m, batch, C);
     if (rc) return rc;
     KERNEL_CHECK();

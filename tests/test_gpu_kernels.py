@@ -21,7 +21,7 @@ def D():
     return dev
 
 
-@pytest.mark.parametrize('n', [8, 60, 64, 96, 100, 1000, 1024, 1430, 4096, 7168, 8192, 30030])
+@pytest.mark.parametrize('n', [8, 60, 64, 96, 100, 256, 512, 1000, 1024, 1430, 2048, 4096, 7168, 8192, 30030])
 def test_fft_c2c(D, n):
     rng = np.random.default_rng(n)
     x = rng.standard_normal((3, n)) + 1j*rng.standard_normal((3, n))
@@ -36,7 +36,7 @@ def test_fft_c2c(D, n):
     assert rel(xd.cpu().numpy(), np.fft.fft(x)) < 1e-14*np.log2(n)
 
 
-@pytest.mark.parametrize('n', [96, 1024, 9000])
+@pytest.mark.parametrize('n', [96, 256, 512, 1024, 2048, 4096, 8192, 9000])
 def test_fft_mul_fft(D, n):
     rng = np.random.default_rng(n)
     x = rng.standard_normal((5, n)) + 1j*rng.standard_normal((5, n))
