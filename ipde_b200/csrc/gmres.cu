@@ -61,6 +61,87 @@ __global__ void k_multi_dot(const cplx* __restrict__ V, int nvec, const cplx* __
     if (threadIdx.x == 0) *ticket = 0;
 }
 
+// Fused Gram-Schmidt step, one launch:
+//     w -= sum_{i<nsub} hsub[i] V_i          (skipped when nsub == 0)
+//     h[i] = <D_i, w>,  i < ndot              D = V, or w itself when `self` (the norm)
+// Every thread owns the elements e = gtid + r*stride: it finishes its part of w before it starts on the dot products,
+// so no grid-wide dependency arises.  Dot products go eight vectors at a time (one pass over w per chunk, all loads
+// independent), partials per block, the last block to arrive (ticket) adds them in block order: deterministic.
+__global__ void __launch_bounds__(256)
+k_sub_dot(cplx* __restrict__ w, const cplx* __restrict__ V, int nsub, const cplx* __restrict__ hsub, int ndot, int self,
+          int64_t len, cplx* __restrict__ partial, cplx* __restrict__ h, unsigned* __restrict__ ticket) {
+    __shared__ cplx sh[8][8];
+    __shared__ bool last;
+    const int64_t g0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (nsub > 0) {
+        for (int64_t e = g0; e < len; e += stride) {
+            cplx acc = w[e];
+            int i = 0;
+            for (; i + 4 <= nsub; i += 4) {
+                const cplx v0 = V[(int64_t)i * len + e], v1 = V[(int64_t)(i + 1) * len + e];
+                const cplx v2 = V[(int64_t)(i + 2) * len + e], v3 = V[(int64_t)(i + 3) * len + e];
+                acc = csub(acc, cmul(hsub[i], v0));
+                acc = csub(acc, cmul(hsub[i + 1], v1));
+                acc = csub(acc, cmul(hsub[i + 2], v2));
+                acc = csub(acc, cmul(hsub[i + 3], v3));
+            }
+            for (; i < nsub; ++i) acc = csub(acc, cmul(hsub[i], V[(int64_t)i * len + e]));
+            w[e] = acc;
+        }
+    }
+    for (int c0 = 0; c0 < ndot; c0 += 8) {
+        const int nc = min(8, ndot - c0);
+        cplx acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = make_double2(0.0, 0.0);
+        for (int64_t e = g0; e < len; e += stride) {
+            const cplx b = w[e];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (i < nc) {
+                    const cplx a = self ? b : V[(int64_t)(c0 + i) * len + e];
+                    acc[i].x += a.x * b.x + a.y * b.y;
+                    acc[i].y += a.x * b.y - a.y * b.x;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i < nc) {
+                for (int o = 16; o > 0; o >>= 1) {
+                    acc[i].x += __shfl_xor_sync(0xffffffffu, acc[i].x, o);
+                    acc[i].y += __shfl_xor_sync(0xffffffffu, acc[i].y, o);
+                }
+                if (lane == 0) sh[warp][i] = acc[i];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < nc) {
+            cplx r = make_double2(0.0, 0.0);
+            for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) r = cadd(r, sh[wv][threadIdx.x]);
+            partial[(int64_t)(c0 + threadIdx.x) * gridDim.x + blockIdx.x] = r;
+        }
+        __syncthreads();
+    }
+    __threadfence();
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const int nb = gridDim.x;
+    for (int i = warp; i < ndot; i += blockDim.x >> 5) {      // one warp per vector
+        cplx acc = make_double2(0.0, 0.0);
+        for (int b = lane; b < nb; b += 32) acc = cadd(acc, partial[(int64_t)i * nb + b]);
+        for (int o = 16; o > 0; o >>= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        }
+        if (lane == 0) h[i] = acc;
+    }
+    if (threadIdx.x == 0) *ticket = 0;
+}
+
 __global__ void k_sub_combination(cplx* __restrict__ w, const cplx* __restrict__ V, int nvec, const cplx* __restrict__ h,
                                   int64_t len) {
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < len; e += (int64_t)gridDim.x * blockDim.x) {
@@ -95,7 +176,7 @@ __global__ void k_residual(const cplx* __restrict__ b, const cplx* __restrict__ 
 int gmres_workspace_ensure(GmresWorkspace* ws, int64_t len, int restart) {
     if (ws->len >= len && ws->restart >= restart) return IPDE_OK;
     gmres_workspace_free(ws);
-    ws->nblocks = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(len, DOT_THREADS * 4), (int64_t)ipde_num_sms() * 2));
+    ws->nblocks = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(len, DOT_THREADS), (int64_t)ipde_num_sms() * 4));
     CUDA_TRY(cudaMalloc(&ws->V, sizeof(cplx) * (size_t)(restart + 1) * len));
     CUDA_TRY(cudaMalloc(&ws->w, sizeof(cplx) * (size_t)len));
     CUDA_TRY(cudaMalloc(&ws->z, sizeof(cplx) * (size_t)len));
@@ -201,13 +282,13 @@ int gmres_solve(LinearOperator* op, GmresWorkspace* ws, const cplx* b, cplx* x, 
             int r = op->precond(vj, ws->z, st); if (r) return r;
             r = op->apply(ws->z, ws->w, st); if (r) return r;
             // classical Gram-Schmidt, twice
-            r = dots(ws, V, j + 1, ws->w, len, d_h, st); if (r) return r;
-            k_sub_combination<<<eb, 256, 0, st>>>(ws->w, V, j + 1, d_h, len);
+            cplx* part = reinterpret_cast<cplx*>(ws->partial);
+            k_sub_dot<<<ws->nblocks, DOT_THREADS, 0, st>>>(ws->w, V, 0, nullptr, j + 1, 0, len, part, d_h, ws->ticket);
             KERNEL_CHECK();
-            r = dots(ws, V, j + 1, ws->w, len, d_h2, st); if (r) return r;
-            k_sub_combination<<<eb, 256, 0, st>>>(ws->w, V, j + 1, d_h2, len);
+            k_sub_dot<<<ws->nblocks, DOT_THREADS, 0, st>>>(ws->w, V, j + 1, d_h, j + 1, 0, len, part, d_h2, ws->ticket);
             KERNEL_CHECK();
-            r = dots(ws, ws->w, 1, ws->w, len, d_n, st); if (r) return r;
+            k_sub_dot<<<ws->nblocks, DOT_THREADS, 0, st>>>(ws->w, V, j + 1, d_h2, 1, 1, len, part, d_n, ws->ticket);
+            KERNEL_CHECK();
             k_normalize<<<eb, 256, 0, st>>>(ws->w, V + (int64_t)(j + 1) * len, d_n, len);
             KERNEL_CHECK();
             cplx* slot = hst + (size_t)(j & 1) * (3 * R1);
