@@ -207,6 +207,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--slab-grid', type=int, default=16384,
                     help='grid size of the slab-decomposed (all ranks, one problem) grid-solve timing; 0 = skip')
+    ap.add_argument('--slab-chunks', type=int, default=4,
+                    help='sub-blocks of the column slab whose all-to-all overlaps the column pass (ranks > 1)')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -297,7 +299,7 @@ def main():
         ns = args.slab_grid
         del solver, res
         torch.cuda.empty_cache()
-        S = SlabGridSolver(ns, ns, 2.4/ns, 2.4/ns, 1, HELMHOLTZ_K)
+        S = SlabGridSolver(ns, ns, 2.4/ns, 2.4/ns, 1, HELMHOLTZ_K, chunks=args.slab_chunks)
         gen = torch.Generator(device='cuda')
         gen.manual_seed(rank)
         fl = torch.randn((S.L.rows, ns), dtype=torch.float64, device='cuda', generator=gen)
@@ -316,7 +318,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         slab = {'what': 'periodic grid solve (r2c rows, all-to-all, column FFT + symbol + inverse, all-to-all, c2r rows) '
                         'of ONE %d^2 grid slab-decomposed over all ranks; strong scaling of the FFT core' % ns,
-                'grid': [ns, ns], 'n_gpus': world, 'ms_per_solve': float(tt[0]),
+                'grid': [ns, ns], 'n_gpus': world, 'chunks': S.K, 'ms_per_solve': float(tt[0]),
                 'grid_point_solves_per_s': ns*ns/(float(tt[0])*1e-3),
                 'alltoall_bytes_per_rank_per_solve': int(S.alltoall_bytes_per_rank)}
         del S, fl, out

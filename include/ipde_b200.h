@@ -84,6 +84,12 @@ int ipde_fft_c2r_rows(void* plan, const double* in, double* out, int64_t batch, 
 /* (rows, P) -> (R, rows, Pc) column blocks, zero padded past P, and back */
 int ipde_slab_pack(const double* in, int64_t rows, int64_t P, int R, int64_t Pc, double* out, void* stream);
 int ipde_slab_unpack(const double* in, int64_t rows, int64_t P, int R, int64_t Pc, double* out, void* stream);
+/* the same for the sub-block [koff, koff + Pk) of every column block: (rows, P) <-> (R, rows, Pk).  Chunks let the
+ * all-to-all of one part of the column slab overlap the column pass of another (ipde_b200/distributed.py) */
+int ipde_slab_pack_chunk(const double* in, int64_t rows, int64_t P, int R, int64_t Pc, int64_t koff, int64_t Pk, double* out,
+                         void* stream);
+int ipde_slab_unpack_chunk(const double* in, int64_t rows, int64_t P, int R, int64_t Pc, int64_t koff, int64_t Pk, double* out,
+                           void* stream);
 /* column FFT + symbol + inverse column FFT on a block of columns [col_offset, col_offset + Pc) of the global
  * half spectrum; plan = ipde_grid_plan_create(nx, 2*(Pc-1), xh, yh) */
 int ipde_grid_cols_symbol_slab(void* plan, double* spec_in, double* spec_out, double* spec_copy, int copy_mode, int kind,

@@ -194,10 +194,18 @@ int ipde_fft_c2r_rows(void* plan, const double* in, double* out, int64_t batch, 
     return fft_c2r_rows((FftPlan*)plan, CP(in), out, batch, in_pitch, out_pitch, scale, ST(stream));
 }
 int ipde_slab_pack(const double* in, int64_t rows, int64_t P, int R, int64_t Pc, double* out, void* stream) {
-    return grid_slab_pack(CP(in), rows, P, R, Pc, MP(out), ST(stream));
+    return grid_slab_pack(CP(in), rows, P, R, Pc, 0, Pc, MP(out), ST(stream));
 }
 int ipde_slab_unpack(const double* in, int64_t rows, int64_t P, int R, int64_t Pc, double* out, void* stream) {
-    return grid_slab_unpack(CP(in), rows, P, R, Pc, MP(out), ST(stream));
+    return grid_slab_unpack(CP(in), rows, P, R, Pc, 0, Pc, MP(out), ST(stream));
+}
+int ipde_slab_pack_chunk(const double* in, int64_t rows, int64_t P, int R, int64_t Pc, int64_t koff, int64_t Pk, double* out,
+                         void* stream) {
+    return grid_slab_pack(CP(in), rows, P, R, Pc, koff, Pk, MP(out), ST(stream));
+}
+int ipde_slab_unpack_chunk(const double* in, int64_t rows, int64_t P, int R, int64_t Pc, int64_t koff, int64_t Pk, double* out,
+                           void* stream) {
+    return grid_slab_unpack(CP(in), rows, P, R, Pc, koff, Pk, MP(out), ST(stream));
 }
 int ipde_grid_cols_symbol_slab(void* plan, double* spec_in, double* spec_out, double* spec_copy, int copy_mode, int kind,
                                double k, int ny_global, double yh, int col_offset, void* stream) {

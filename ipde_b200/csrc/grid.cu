@@ -669,33 +669,41 @@ int grid_stokes_stress(GridPlan* g, const cplx* uh, const cplx* vh, const cplx* 
 
 // ------------------------------------------------------------------------------------------
 // slab decomposition helpers
-__global__ void k_slab_pack(const cplx* __restrict__ in, int64_t rows, int64_t P, int R, int64_t Pc, cplx* __restrict__ out) {
-    const int64_t total = (int64_t)R * rows * Pc;
+// Column block q of the half spectrum is [q*Pc, (q+1)*Pc); a chunk is the sub-block [koff, koff + Pk) of every block
+// (koff = 0, Pk = Pc: the whole block).  Chunks let the all-to-all of one part overlap the column pass of another.
+__global__ void k_slab_pack(const cplx* __restrict__ in, int64_t rows, int64_t P, int R, int64_t Pc, int64_t koff, int64_t Pk,
+                            cplx* __restrict__ out) {
+    const int64_t total = (int64_t)R * rows * Pk;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t kc = t % Pc, l = (t / Pc) % rows, q = t / (Pc * rows);
-        const int64_t k = q * Pc + kc;
+        const int64_t kc = t % Pk, l = (t / Pk) % rows, q = t / (Pk * rows);
+        const int64_t k = q * Pc + koff + kc;
         out[t] = (k < P) ? in[l * P + k] : make_double2(0.0, 0.0);
     }
 }
-__global__ void k_slab_unpack(const cplx* __restrict__ in, int64_t rows, int64_t P, int R, int64_t Pc, cplx* __restrict__ out) {
-    const int64_t total = rows * P;
+__global__ void k_slab_unpack(const cplx* __restrict__ in, int64_t rows, int64_t P, int R, int64_t Pc, int64_t koff, int64_t Pk,
+                              cplx* __restrict__ out) {
+    const int64_t total = (int64_t)R * rows * Pk;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t k = t % P, l = t / P;
-        const int64_t q = k / Pc, kc = k - q * Pc;
-        out[t] = in[(q * rows + l) * Pc + kc];
+        const int64_t kc = t % Pk, l = (t / Pk) % rows, q = t / (Pk * rows);
+        const int64_t k = q * Pc + koff + kc;
+        if (k < P) out[l * P + k] = in[t];
     }
 }
-int grid_slab_pack(const cplx* in, int64_t rows, int64_t P, int R, int64_t Pc, cplx* out, cudaStream_t st) {
-    const int64_t total = (int64_t)R * rows * Pc;
-    KERNEL_TAG("k_slab_pack", 16.0 * (double)(rows * P) + 16.0 * (double)total);
-    k_slab_pack<<<grid_blocks(total, 256), 256, 0, st>>>(in, rows, P, R, Pc, out);
+int grid_slab_pack(const cplx* in, int64_t rows, int64_t P, int R, int64_t Pc, int64_t koff, int64_t Pk, cplx* out,
+                   cudaStream_t st) {
+    ARG_CHECK(koff >= 0 && Pk > 0 && koff + Pk <= Pc, "slab pack: chunk outside the column block");
+    const int64_t total = (int64_t)R * rows * Pk;
+    KERNEL_TAG("k_slab_pack", 32.0 * (double)total);
+    k_slab_pack<<<grid_blocks(total, 256), 256, 0, st>>>(in, rows, P, R, Pc, koff, Pk, out);
     KERNEL_CHECK();
     return IPDE_OK;
 }
-int grid_slab_unpack(const cplx* in, int64_t rows, int64_t P, int R, int64_t Pc, cplx* out, cudaStream_t st) {
-    const int64_t total = rows * P;
+int grid_slab_unpack(const cplx* in, int64_t rows, int64_t P, int R, int64_t Pc, int64_t koff, int64_t Pk, cplx* out,
+                     cudaStream_t st) {
+    ARG_CHECK(koff >= 0 && Pk > 0 && koff + Pk <= Pc, "slab unpack: chunk outside the column block");
+    const int64_t total = (int64_t)R * rows * Pk;
     KERNEL_TAG("k_slab_unpack", 32.0 * (double)total);
-    k_slab_unpack<<<grid_blocks(total, 256), 256, 0, st>>>(in, rows, P, R, Pc, out);
+    k_slab_unpack<<<grid_blocks(total, 256), 256, 0, st>>>(in, rows, P, R, Pc, koff, Pk, out);
     KERNEL_CHECK();
     return IPDE_OK;
 }

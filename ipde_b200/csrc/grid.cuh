@@ -63,8 +63,10 @@ int grid_stokes_stress(GridPlan* g, const cplx* uh, const cplx* vh, const cplx* 
 
 // ---- slab decomposition (ipde_b200/distributed.py): a rank holds `rows` rows of a half spectrum of pitch P; the
 // all-to-all transpose sends column block q (Pc columns, zero padded past P) to rank q.
-int grid_slab_pack(const cplx* in, int64_t rows, int64_t P, int R, int64_t Pc, cplx* out, cudaStream_t st);
-int grid_slab_unpack(const cplx* in, int64_t rows, int64_t P, int R, int64_t Pc, cplx* out, cudaStream_t st);
+int grid_slab_pack(const cplx* in, int64_t rows, int64_t P, int R, int64_t Pc, int64_t koff, int64_t Pk, cplx* out,
+                   cudaStream_t st);
+int grid_slab_unpack(const cplx* in, int64_t rows, int64_t P, int R, int64_t Pc, int64_t koff, int64_t Pk, cplx* out,
+                     cudaStream_t st);
 // column pass of a column slab: plan g has nx = global nx and pitch == Pc; ky is taken from the global grid
 int grid_cols_symbol_slab(GridPlan* g, cplx* spec_in, cplx* spec_out, cplx* spec_copy, int copy_mode, int kind, double k,
                           int ny_global, double yh, int col_offset, cudaStream_t st);

@@ -96,10 +96,13 @@ def slab_grid_solve_numpy(layout, f_local, symbol, group=None):
 class SlabGridSolver(object):
     """
     Device path.  kind: 0 Poisson (zero mode -> 0; the caller demeans), 1 modified Helmholtz.
-    solve(f_local (rows, ny) float64 cuda) -> u_local (rows, ny); timings of the stages are kept in `last_ms`
-    when `timed=True` (CUDA events on the current stream).
+    solve(f_local (rows, ny) float64 cuda) -> u_local (rows, ny).
+
+    chunks > 1 (ranks > 1 only): every rank's column block is cut into `chunks` sub-blocks; the all-to-all of
+    sub-block k+1 (NCCL's own stream, async_op) runs while the column pass of sub-block k does, and the way back
+    likewise, so only the first pack and the last unpack are exposed next to the row transforms.
     """
-    def __init__(self, nx, ny, xh, yh, kind, k, group=None):
+    def __init__(self, nx, ny, xh, yh, kind, k, group=None, chunks=1):
         import ctypes
         from ._lib import lib
         from .device import require_cuda, empty, C128
@@ -108,17 +111,28 @@ class SlabGridSolver(object):
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.L = SlabLayout(nx, ny, world, rank)
+        Ls = self.L
+        K = max(1, int(chunks)) if world > 1 else 1
+        while K > 1 and -(-Ls.Pc//K) < 3:
+            K -= 1
+        self.K = K
+        if world > 1:
+            # the column plan is a grid plan of width 2 (Pk - 1): round the chunk width up to a supported length
+            # (a few zero columns), and make Pc a multiple of the number of chunks
+            Pk = lib().ipde_fft_next_size(max(2, -(-Ls.Pc//K) - 1)) + 1
+            Ls.Pc = Pk*K
+            Ls.col0 = rank*Ls.Pc
+        self.Pk = Ls.Pc//K
         self.nx, self.ny, self.xh, self.yh, self.kind, self.k = nx, ny, float(xh), float(yh), int(kind), float(k)
         L_ = lib()
         self.row_plan = ctypes.c_void_p()
         L_.ipde_fft_plan_create(ny//2, ctypes.byref(self.row_plan))
         self.col_plan = ctypes.c_void_p()
-        L_.ipde_grid_plan_create(nx, 2*(self.L.Pc - 1), float(xh), float(yh), ctypes.byref(self.col_plan))
-        Ls = self.L
+        L_.ipde_grid_plan_create(nx, 2*(self.Pk - 1), float(xh), float(yh), ctypes.byref(self.col_plan))
         self.spec = empty((Ls.rows, Ls.P), C128)
-        self.send = empty((Ls.R, Ls.rows, Ls.Pc), C128)
-        self.recv = empty((Ls.R, Ls.rows, Ls.Pc), C128)
-        self.work = empty((Ls.R, Ls.rows, Ls.Pc), C128)
+        self.send = [empty((Ls.R, Ls.rows, self.Pk), C128) for _ in range(K)]
+        self.recv = [empty((Ls.R, Ls.rows, self.Pk), C128) for _ in range(K)]
+        self.work = [empty((Ls.R, Ls.rows, self.Pk), C128) for _ in range(K)]
         self.alltoall_bytes_per_rank = 2*16*Ls.rows*Ls.Pc*(Ls.R - 1)
 
     def __del__(self):
@@ -129,6 +143,13 @@ class SlabGridSolver(object):
         except Exception:
             pass
 
+    def _exchange(self, send, recv):
+        """all-to-all; on NCCL asynchronously (returns the work handle, None otherwise)"""
+        if dist.get_backend(self.group) == 'nccl':
+            return dist.all_to_all_single(recv, send, group=self.group, async_op=True)
+        exchange(send, recv, self.group)
+        return None
+
     def solve(self, f_local, out=None):
         from ._lib import lib
         from .device import ptr, stream, empty
@@ -136,20 +157,31 @@ class SlabGridSolver(object):
         if out is None:
             out = empty((Ls.rows, self.ny))
         L_.ipde_fft_r2c_rows(self.row_plan, ptr(f_local), ptr(self.spec), Ls.rows, self.ny, Ls.P, st)
-        if Ls.R > 1:
-            L_.ipde_slab_pack(ptr(self.spec), Ls.rows, Ls.P, Ls.R, Ls.Pc, ptr(self.send), st)
-            exchange(self.send, self.recv, self.group)
+        if Ls.R == 1:
+            # one rank: the row spectrum already is the column slab (Pc == P), no pack
+            L_.ipde_grid_cols_symbol_slab(self.col_plan, ptr(self.spec), ptr(self.work[0]), 0, 0, self.kind, self.k,
+                                          self.ny, self.yh, 0, st)
+            back = self.work[0]
         else:
-            L_.ipde_slab_pack(ptr(self.spec), Ls.rows, Ls.P, 1, Ls.Pc, ptr(self.recv), st)
-        # column slab (nx, Pc): forward columns, symbol, inverse columns
-        L_.ipde_grid_cols_symbol_slab(self.col_plan, ptr(self.recv), ptr(self.work), 0, 0, self.kind, self.k, self.ny,
-                                      self.yh, Ls.col0, st)
-        if Ls.R > 1:
-            exchange(self.work, self.send, self.group)
-            back = self.send
-        else:
-            back = self.work
-        L_.ipde_slab_unpack(ptr(back), Ls.rows, Ls.P, Ls.R, Ls.Pc, ptr(self.spec), st)
-        L_.ipde_fft_c2r_rows(self.row_plan, ptr(self.spec), ptr(out), Ls.rows, Ls.P, self.ny,
+            K, Pk = self.K, self.Pk
+            fwd = []
+            for c in range(K):
+                L_.ipde_slab_pack_chunk(ptr(self.spec), Ls.rows, Ls.P, Ls.R, Ls.Pc, c*Pk, Pk, ptr(self.send[c]), st)
+                fwd.append(self._exchange(self.send[c], self.recv[c]))
+            bwd = []
+            for c in range(K):
+                if fwd[c] is not None:
+                    fwd[c].wait()
+                # column sub-slab (nx, Pk): forward columns, symbol, inverse columns; the received blocks are already
+                # in global row order
+                L_.ipde_grid_cols_symbol_slab(self.col_plan, ptr(self.recv[c]), ptr(self.work[c]), 0, 0, self.kind,
+                                              self.k, self.ny, self.yh, Ls.col0 + c*Pk, st)
+                bwd.append(self._exchange(self.work[c], self.send[c]))
+            for c in range(K):
+                if bwd[c] is not None:
+                    bwd[c].wait()
+                L_.ipde_slab_unpack_chunk(ptr(self.send[c]), Ls.rows, Ls.P, Ls.R, Ls.Pc, c*Pk, Pk, ptr(self.spec), st)
+            back = self.spec
+        L_.ipde_fft_c2r_rows(self.row_plan, ptr(back), ptr(out), Ls.rows, Ls.P, self.ny,
                              2.0/(float(self.nx)*float(self.ny)), st)
         return out

@@ -11,6 +11,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--grid', '--n', dest='n', type=int, default=4096)
 ap.add_argument('--steps', type=int, default=10)
 ap.add_argument('--check', action='store_true')
+ap.add_argument('--chunks', type=int, default=1)
 ap.add_argument('--profile', action='store_true', help='per-kernel CUDA-event times of one solve (library profiler)')
 a = ap.parse_args()
 rank, world, lr = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
@@ -21,7 +22,7 @@ from ipde_b200.distributed import SlabGridSolver
 import ipde_b200.device as D
 n = a.n
 xh = 2.4/n
-S = SlabGridSolver(n, n, xh, xh, 1, 2.0)
+S = SlabGridSolver(n, n, xh, xh, 1, 2.0, chunks=a.chunks)
 L = S.L
 if a.check:
     f = np.random.default_rng(0).standard_normal((n, n))
@@ -59,7 +60,7 @@ if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
     ms = float(t[0])
-    print(json.dumps({'slab_grid_solve': {'grid': [n, n], 'n_gpus': world, 'ms_per_solve': ms,
+    print(json.dumps({'slab_grid_solve': {'grid': [n, n], 'n_gpus': world, 'chunks': S.K, 'ms_per_solve': ms,
                                            'grid_point_solves_per_s': n*n/(ms*1e-3),
                                            'alltoall_bytes_per_rank_per_solve': S.alltoall_bytes_per_rank,
                                            'alg_GBps_64B_per_point': 64.0*n*n/(ms*1e-3)/1e9}}))
