@@ -123,7 +123,7 @@ class QFS(object):
     interior:  True  -> represent the potential on the inside of the curve
     slp, dlp:  which layers the densities passed to __call__ contain (in that order)
     """
-    # boundaries with more nodes than this are factored on the device (scalar kernels; needs CUDA)
+    # boundaries with more nodes than this are factored on the device (needs CUDA)
     DEVICE_BUILD_MIN_N = 1500
 
     def __init__(self, bdy, interior, slp, dlp, kernel, tol=1e-12,
@@ -144,7 +144,7 @@ class QFS(object):
         self.want_operators = operators      # False: source/check geometry only (boundaries owned by another rank)
         self.on_device = False
         if device_build is None:
-            device_build = bdy.N > self.DEVICE_BUILD_MIN_N and kernel.ncomp == 1 and _cuda_available()
+            device_build = bdy.N > self.DEVICE_BUILD_MIN_N and _cuda_available()
         self._build(device_build)
 
     def _build(self, device_build=False):
@@ -173,7 +173,7 @@ class QFS(object):
             self.A = self.Sinv = self.V = self.Ab = self.Sinv_b = self.Vb = None
             return
         if device_build:
-            return self._build_on_device(bM)
+            return self._build_stokes_on_device(bM) if nc == 2 else self._build_on_device(bM)
         w_s = np.tile(src.weights, nc)
         UM = fourier_resample_matrix(N, M)
         U_MN = UM if nc == 1 else scipy.linalg.block_diag(*([UM]*nc))
@@ -261,6 +261,69 @@ class QFS(object):
             UM = to_dev(fourier_resample_matrix(N, M))
             self.Ab, self.Sinv_b, self.Vb = self._factor_device(Eb, UM)
             del Eb, UM
+        else:
+            self.Ab = self.Sinv_b = self.Vb = None
+        self.on_device = True
+
+    def _build_stokes_on_device(self, bM):
+        """
+        Stokes operators of a large boundary (setup only): the 2x2 block kernel matrices are formed with torch
+        elementwise ops on the GPU in row chunks, multiplied by the Fourier upsampling matrix and factored there
+        (torch.linalg -- setup-time library calls).  Same matrices as the host branch of _build.
+        """
+        import torch
+        from .device import to_dev
+        bdy, src, chk = self.bdy, self.source, self.check
+        N, M = self.N, self.M
+        Nf = self.rho_f*N
+        bF = GSB(c=fourier_resample(bdy.c, Nf))
+        d = lambda a: to_dev(np.ascontiguousarray(a, dtype=float))
+        UF = d(fourier_resample_matrix(N, Nf))                 # (Nf, N)
+        fx, fy, fnx, fny, fw = d(bF.x), d(bF.y), d(bF.normal_x), d(bF.normal_y), d(bF.weights)
+        cx, cy = d(chk.x), d(chk.y)
+        c4 = 1.0/(4.0*np.pi)
+
+        def stokeslet(tx, ty, sx, sy, w):
+            dx, dy = tx[:, None] - sx[None, :], ty[:, None] - sy[None, :]
+            r2 = dx*dx + dy*dy
+            Lg = -0.5*torch.log(r2)
+            xy = c4*dx*dy/r2*w
+            return (c4*(Lg + dx*dx/r2)*w, xy, xy, c4*(Lg + dy*dy/r2)*w)      # xx, xy, yx, yy
+
+        def stresslet(tx, ty, sx, sy, nx, ny, w):
+            dx, dy = tx[:, None] - sx[None, :], ty[:, None] - sy[None, :]
+            r2 = dx*dx + dy*dy
+            f = (dx*nx[None, :] + dy*ny[None, :])/(r2*r2)/np.pi*w
+            xy = f*dx*dy
+            return (f*dx*dx, xy, xy, f*dy*dy)
+
+        layers = [l for l, on in ((0, self.has_slp), (1, self.has_dlp)) if on]
+        C = torch.empty((2*M, len(layers)*2*N), dtype=torch.float64, device=UF.device)
+        rows = max(1, min(M, int(1.0e8//Nf)))
+        for li, layer in enumerate(layers):
+            for r0 in range(0, M, rows):
+                r1 = min(M, r0 + rows)
+                if layer == 0:
+                    blocks = stokeslet(cx[r0:r1], cy[r0:r1], fx, fy, fw[None, :])
+                else:
+                    blocks = stresslet(cx[r0:r1], cy[r0:r1], fx, fy, fnx, fny, fw[None, :])
+                for a in range(2):                      # target component
+                    for i in range(2):                  # source component
+                        C[a*M + r0:a*M + r1, li*2*N + i*N:li*2*N + (i + 1)*N] = blocks[2*a + i] @ UF
+                del blocks
+        sx, sy, sw = d(src.x), d(src.y), d(src.weights)
+
+        def slp_matrix(tx, ty):
+            xx, xy, yx, yy = stokeslet(tx, ty, sx, sy, sw[None, :])
+            return torch.cat([torch.cat([xx, xy], dim=1), torch.cat([yx, yy], dim=1)], dim=0)
+
+        self.A, self.Sinv, self.V = self._factor_device(slp_matrix(cx, cy), C)
+        del C
+        if self.want_u2s:
+            UM = d(fourier_resample_matrix(N, M))
+            Z = torch.zeros_like(UM)
+            U_MN = torch.cat([torch.cat([UM, Z], dim=1), torch.cat([Z, UM], dim=1)], dim=0)
+            self.Ab, self.Sinv_b, self.Vb = self._factor_device(slp_matrix(d(bM.x), d(bM.y)), U_MN)
         else:
             self.Ab = self.Sinv_b = self.Vb = None
         self.on_device = True

@@ -344,6 +344,27 @@ def test_qfs_device_build_matches_host_build(D, kind, interior):
     assert rel(K.dot(qd.u2s(ub)), K.dot(qh.u2s(ub))) < 1e-11
 
 
+@pytest.mark.parametrize('interior', [True, False])
+def test_stokes_qfs_device_build_matches_host_build(D, interior):
+    """Stokes QFS operators formed and factored on the device generate the same velocity field as the NumPy build"""
+    from ipde_b200.geometry import GSB, star
+    from ipde_b200.qfs import Stokes_QFS
+    bdy = GSB(c=star(200, a=0.15, f=5))
+    qh = Stokes_QFS(bdy, interior, True, True, device_build=False)
+    qd = Stokes_QFS(bdy, interior, True, True, device_build=True)
+    assert qd.on_device and not qh.on_device
+    t = bdy.t
+    tau = [np.concatenate([np.exp(np.cos(t))*np.sin(2*t), np.cos(t)]), np.concatenate([np.cos(3*t + 0.3), np.sin(2*t)])]
+    sh, sd = qh(tau), qd(tau)
+    th = np.linspace(0, 2*np.pi, 50, endpoint=False)
+    rad = 0.5 if interior else 2.0
+    tx, ty = rad*np.cos(th), rad*np.sin(th)
+    K = qh.kernel.slp(tx, ty, qh.source.x, qh.source.y)*np.tile(qh.source.weights, 2)
+    assert rel(K.dot(sd), K.dot(sh)) < 1e-11
+    ub = np.concatenate([np.exp(np.sin(t)), np.cos(2*t)])
+    assert rel(K.dot(qd.u2s(ub)), K.dot(qh.u2s(ub))) < 1e-10
+
+
 def test_nufft2_apply3_matches_separate_transforms(D):
     """value + gradient from one fine-grid transform (kernel differentiation) vs three spectral transforms"""
     n = 96
