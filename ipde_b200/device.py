@@ -396,9 +396,13 @@ class DeviceBoundary(object):
     def __init__(self, ebdy):
         self.M, self.n = ebdy.M, ebdy.bdy.N
         self.interior = ebdy.interior
-        self.ia_theta = to_dev(ebdy.grid_ia_r_transf)
-        self.ia_t = to_dev(np.mod(ebdy.grid_ia_t, 2*np.pi))
-        self.ia_pos = to_dev(np.asarray(ebdy.ia_inds, dtype=np.int64))
+        # in-annulus grid points that the inside test calls exterior (within round-off of the boundary) have no slot
+        # in the compact vector: drop them (the reference writes them into the full grid and masks them afterwards,
+        # multi_boundary/scalar.py:110-114)
+        ok = np.asarray(getattr(ebdy, 'ia_is_phys', np.ones(ebdy.ia_inds.shape, dtype=bool)), dtype=bool)
+        self.ia_theta = to_dev(np.ascontiguousarray(ebdy.grid_ia_r_transf[ok]))
+        self.ia_t = to_dev(np.ascontiguousarray(np.mod(ebdy.grid_ia_t, 2*np.pi)[ok]))
+        self.ia_pos = to_dev(np.ascontiguousarray(np.asarray(ebdy.ia_inds, dtype=np.int64)[ok]))
         self.n_ia = int(self.ia_pos.numel())
         self.radial_x = to_dev(ebdy.radial_x.ravel())
         self.radial_y = to_dev(ebdy.radial_y.ravel())

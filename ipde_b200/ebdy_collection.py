@@ -88,6 +88,17 @@ class EmbeddedBoundaryCollection(object):
                 raise Exception('Provided value of Ny is too small')
         if force_square:
             Nx = Ny = max(Nx, Ny)
+        if Ns is None:
+            # the device FFT handles lengths with prime factors <= 13: an automatically chosen size outside that set
+            # is padded on the high side to the next friendly one (same origin, same spacing; only more exterior cells)
+            from ._lib import lib
+            ok = lambda n: lib().ipde_fft_size_supported(n) and lib().ipde_fft_size_supported(n//2)
+            if not ok(Nx):
+                Nx = 2*lib().ipde_fft_next_size(-(-Nx//2))
+            if not ok(Ny):
+                Ny = 2*lib().ipde_fft_next_size(-(-Ny//2))
+            if force_square:
+                Nx = Ny = max(Nx, Ny)
         grid = Grid([xmin, xmin + Nx*h], Nx, [ymin, ymin + Ny*h], Ny,
                     x_endpoints=[True, False], y_endpoints=[True, False])
         assert np.abs(grid.xh - h) < 1e-15, 'Gridspacing not what was requested'
@@ -132,7 +143,7 @@ class EmbeddedBoundaryCollection(object):
         self.in_annulus = ia
         self.phys_not_in_annulus = np.logical_and(phys, np.logical_not(ia))
         for ebdy in self:
-            ebdy.register_ia_inds(self.phys_inds)
+            ebdy.register_ia_inds(self.phys_inds, self.phys)
 
         self.grid_step = phys.astype(float)
         for ebdy in self:

@@ -138,8 +138,13 @@ class EmbeddedBoundary(object):
             self.grid_in_danger_zone_y = iay[idz]
             self.grid_in_danger_zone_gi = (t[idz]//self.bdy.dt).astype(int)
 
-    def register_ia_inds(self, phys_inds):
+    def register_ia_inds(self, phys_inds, phys=None):
+        """positions of the in-annulus grid points inside the compact physical vector.  `ia_is_phys`: a point within
+        round-off of the boundary can carry annular coordinates and still be classified exterior by the inside test;
+        it has no slot in the compact vector (phys_inds is 0 there) and must not be written."""
         self.ia_inds = phys_inds[self.grid_ia_xind, self.grid_ia_yind]
+        self.ia_is_phys = (np.ones(self.ia_inds.shape, dtype=bool) if phys is None
+                           else phys[self.grid_ia_xind, self.grid_ia_yind])
 
     ############################################################################
     def _generate_radial_grid(self):
@@ -245,7 +250,8 @@ class EmbeddedBoundary(object):
 
     def interpolate_radial_to_grid2(self, fr, f):
         vals = self.interpolate_radial_to_points(fr, self.grid_ia_r_transf, self.grid_ia_t)
-        f[self.ia_inds] = vals
+        ok = self.ia_is_phys
+        f[self.ia_inds[ok]] = vals[ok]
 
     ############################################################################
     def _radial_grid_t_derivative(self, f):

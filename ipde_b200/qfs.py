@@ -128,7 +128,7 @@ class QFS(object):
 
     def __init__(self, bdy, interior, slp, dlp, kernel, tol=1e-12,
                  source_upsample_factor=1.0, alpha_s=None, alpha_c=None, rho=None, rho_f=None, u2s=True,
-                 device_build=None, operators=True):
+                 device_build=None, operators=True, b2c=True):
         self.bdy = bdy
         self.interior = interior
         self.has_slp, self.has_dlp = slp, dlp
@@ -141,6 +141,7 @@ class QFS(object):
         self.rho_f = r_f if rho_f is None else rho_f
         self.svd_cut = min(1e-11, max(1e-14, tol))
         self.want_u2s = u2s
+        self.want_b2c = b2c                  # False: only the u2s operators (homogeneous correction)
         self.want_operators = operators      # False: source/check geometry only (boundaries owned by another rank)
         self.on_device = False
         if device_build is None:
@@ -182,17 +183,20 @@ class QFS(object):
         bF = GSB(c=fourier_resample(bdy.c, Nf))
         UF = fourier_resample_matrix(N, Nf)
         w_f = bF.weights
-        blocks = []
-        if self.has_slp:
-            K = ker.slp(chk.x, chk.y, bF.x, bF.y)*np.tile(w_f, nc)[None, :]
-            blocks.append(self._times_upsample(K, UF, nc))
-        if self.has_dlp:
-            K = ker.dlp(chk.x, chk.y, bF.x, bF.y, bF.normal_x, bF.normal_y)*np.tile(w_f, nc)[None, :]
-            blocks.append(self._times_upsample(K, UF, nc))
-        C = np.hstack(blocks)                                  # (nc*M) x (nlayers*nc*N)
-        # check <- source and boundary(M nodes) <- source, each as a truncated SVD  E = U S V^T
-        E = ker.slp(chk.x, chk.y, src.x, src.y)*w_s[None, :]
-        self.A, self.Sinv, self.V = self._factor(E, C)
+        if self.want_b2c:
+            blocks = []
+            if self.has_slp:
+                K = ker.slp(chk.x, chk.y, bF.x, bF.y)*np.tile(w_f, nc)[None, :]
+                blocks.append(self._times_upsample(K, UF, nc))
+            if self.has_dlp:
+                K = ker.dlp(chk.x, chk.y, bF.x, bF.y, bF.normal_x, bF.normal_y)*np.tile(w_f, nc)[None, :]
+                blocks.append(self._times_upsample(K, UF, nc))
+            C = np.hstack(blocks)                                  # (nc*M) x (nlayers*nc*N)
+            # check <- source and boundary(M nodes) <- source, each as a truncated SVD  E = U S V^T
+            E = ker.slp(chk.x, chk.y, src.x, src.y)*w_s[None, :]
+            self.A, self.Sinv, self.V = self._factor(E, C)
+        else:
+            self.A = self.Sinv = self.V = None
         if self.want_u2s:
             Eb = ker.slp(bM.x, bM.y, src.x, src.y)*w_s[None, :]
             self.Ab, self.Sinv_b, self.Vb = self._factor(Eb, U_MN)
@@ -229,7 +233,9 @@ class QFS(object):
         idx[N - hh:] = Nf - hh + np.arange(hh)
         d_idx = to_dev(idx)
         layers = [l for l, on in ((0, self.has_slp), (1, self.has_dlp)) if on]
-        C = empty((M, len(layers)*N))
+        if not self.want_b2c:
+            layers = []
+        C = empty((M, max(1, len(layers))*N))
         rows = max(1, min(M, int(2.0e9//(16*Nf))))
         K = empty((rows, Nf))
         for li, layer in enumerate(layers):
@@ -248,11 +254,15 @@ class QFS(object):
                 C[r0:r1, li*N:(li + 1)*N] = out.real
                 del Kc, R, Z, out
         del K
-        E = empty((M, M))
-        L.ipde_kernel_matrix(kind, float(ker.k), 0, ptr(cx), ptr(cy), M, ptr(sx), ptr(sy), 0, 0, ptr(sw), M, ptr(E),
-                             stream())
-        self.A, self.Sinv, self.V = self._factor_device(E, C)
-        del E, C
+        if self.want_b2c:
+            E = empty((M, M))
+            L.ipde_kernel_matrix(kind, float(ker.k), 0, ptr(cx), ptr(cy), M, ptr(sx), ptr(sy), 0, 0, ptr(sw), M, ptr(E),
+                                 stream())
+            self.A, self.Sinv, self.V = self._factor_device(E, C)
+            del E
+        else:
+            self.A = self.Sinv = self.V = None
+        del C
         if self.want_u2s:
             Eb = empty((M, M))
             bx, by = d(bM.x), d(bM.y)

@@ -19,7 +19,10 @@ class DeviceQFS(object):
         self.qfs = qfs
         self.M, self.N = qfs.M, qfs.N
         up = (lambda a: a) if getattr(qfs, 'on_device', False) else to_dev
-        self.A, self.Sinv, self.V = up(qfs.A), up(qfs.Sinv), up(qfs.V)
+        if qfs.A is not None:
+            self.A, self.Sinv, self.V = up(qfs.A), up(qfs.Sinv), up(qfs.V)
+        else:
+            self.A = self.Sinv = self.V = None          # built with b2c=False: u2s only
         if qfs.Ab is not None:
             self.Ab, self.Sinv_b, self.Vb = up(qfs.Ab), up(qfs.Sinv_b), up(qfs.Vb)
         else:
@@ -28,7 +31,7 @@ class DeviceQFS(object):
         self.sy = to_dev(qfs.source.y)
         self.sw = to_dev(qfs.source.weights)
         self.nsrc = qfs.source.N
-        nw = self.A.shape[0] if self.Ab is None else max(self.A.shape[0], self.Ab.shape[0])
+        nw = max(a.shape[0] for a in (self.A, self.Ab) if a is not None)
         self._w = empty((nw,))
 
     def _two_step(self, A, Sinv, V, x):

@@ -1,0 +1,130 @@
+"""
+Homogeneous (boundary-condition) correction -- the step every caller of the reference performs right after the
+inhomogeneous solve:
+
+    examples/interior_modified_helmholtz.py:73-86       single boundary, Dirichlet
+    examples/multi_modified_helmholtz.py:113-177        boundary collection, Dirichlet
+    examples/poisson_for_paper.py:88-105                Poisson, Dirichlet
+
+The reference solves a dense second-kind integral equation for a double-layer density on all boundaries (pybie2d
+self-quadratures + numpy.linalg.solve), turns it into effective sources with QFS and sums them onto
+`ebdyc.grid_and_radial_pts`.  Here the homogeneous solution is represented by the same kind of effective sources on
+the QFS source curve of every boundary (outside the physical domain), found from the boundary data directly:
+
+    tau_i  : values the homogeneous solution has to take on boundary i           (unknown blocks)
+    sigma_i = u2s_i(tau_i)                                                       (QFS boundary -> source operator)
+    tau_i + sum_{j != i} S(bdy_i <- src_j) sigma_j = bc_i - u_inhomogeneous|_i   (well conditioned: I + compact)
+
+one boundary: tau = g, no solve; several: GMRES on the block system (the Krylov bookkeeping runs on the host on
+vectors of sum n_b numbers, every operator application -- QFS mat-vecs, boundary <- source sums -- on the device).
+The sources are then summed onto all physical grid points and all radial points by the same device evaluators the
+inhomogeneous solve uses (spectral Ewald, or all pairs for small problems), and added to `ue`.
+Both routes compute the unique solution of the homogeneous Dirichlet problem; they agree to the QFS tolerance.
+"""
+import numpy as np
+import scipy.sparse.linalg
+
+from ...device import to_dev, empty, gemv, layer_apply_scalar, FreeSpaceEvaluator
+from ...embedded_function import EmbeddedFunction
+from ...qfs import Laplace_QFS, Modified_Helmholtz_QFS
+from ..internals.scalar import DeviceQFS
+
+
+class DirichletCorrection(object):
+    """
+    corr = DirichletCorrection(solver)            # solver: PoissonSolver / ModifiedHelmholtzSolver of ipde_b200
+    ue = solver(f, **gmres_kwargs)
+    u = corr(ue, bc)                              # bc: BoundaryFunction / concatenated boundary values
+    """
+    EWALD_THRESHOLD = 2.0e8         # sources x targets above which the spectral-Ewald evaluator is used
+
+    def __init__(self, solver, tol=1e-12, evaluation='auto'):
+        self.solver = solver
+        e = self.ebdyc = solver.ebdyc
+        self.kind, self.k = solver.kernel_kind, float(solver.k)
+        self.qfs, self.dqfs = [], []
+        for ebdy in e:
+            if self.kind == 0:
+                q = Laplace_QFS(ebdy.bdy, ebdy.interior, True, False, tol=tol, b2c=False)
+            else:
+                q = Modified_Helmholtz_QFS(ebdy.bdy, ebdy.interior, True, False, self.k, tol=tol, b2c=False)
+            self.qfs.append(q)
+            self.dqfs.append(DeviceQFS(q))
+        self.nb = [ebdy.bdy.N for ebdy in e]
+        self.boff = np.concatenate([[0], np.cumsum(self.nb)])
+        self.d_bx = [to_dev(ebdy.bdy.x) for ebdy in e]
+        self.d_by = [to_dev(ebdy.bdy.y) for ebdy in e]
+        sx = np.concatenate([q.source.x for q in self.qfs])
+        sy = np.concatenate([q.source.y for q in self.qfs])
+        self.soff = np.concatenate([[0], np.cumsum([q.source.N for q in self.qfs])])
+        self.d_sx, self.d_sy = to_dev(sx), to_dev(sy)
+        pts = e.grid_and_radial_pts
+        g = e.grid
+        if evaluation == 'auto':
+            evaluation = 'ewald' if float(sx.size)*float(pts.N) > self.EWALD_THRESHOLD else 'direct'
+        if evaluation == 'ewald' and abs(g.xh - g.yh) > 1e-14*g.xh:
+            evaluation = 'direct'
+        self.evaluation = evaluation
+        self.n_phys = int(e.phys.sum())
+        if evaluation == 'ewald':
+            pix, piy = np.nonzero(e.phys)
+            rp = e.radial_pts
+            self.evaluator = FreeSpaceEvaluator(self.kind, self.k, float(g.xv[0]), float(g.yv[0]), float(g.xh), sx, sy,
+                                                grid_nodes=(pix, piy), grid_out_pos=e.phys_inds[e.phys],
+                                                points=(rp.x, rp.y))
+        else:
+            self.d_tx, self.d_ty = to_dev(pts.x), to_dev(pts.y)
+        self.iterations = 0
+
+    # ---- boundary data -> weighted source strengths of every boundary (one flat device vector)
+    def _sources(self, tau_blocks, out):
+        for i, dq in enumerate(self.dqfs):
+            s = dq.u2s(tau_blocks[i])
+            out[self.soff[i]:self.soff[i + 1]] = s*dq.sw
+        return out
+
+    def _apply(self, tau_host):
+        """(A tau)_i = tau_i + sum_{j != i} S(bdy_i <- src_j) u2s_j(tau_j)"""
+        n = len(self.dqfs)
+        t = to_dev(np.ascontiguousarray(tau_host, dtype=float))
+        blocks = [t[self.boff[i]:self.boff[i + 1]] for i in range(n)]
+        q = self._sources(blocks, empty((int(self.soff[-1]),)))
+        res = t.clone()
+        for i in range(n):
+            for j in range(n):
+                if i != j:
+                    layer_apply_scalar(self.kind, self.k, self.d_sx[self.soff[j]:self.soff[j + 1]],
+                                       self.d_sy[self.soff[j]:self.soff[j + 1]], q[self.soff[j]:self.soff[j + 1]],
+                                       self.d_bx[i], self.d_by[i], out=res[self.boff[i]:self.boff[i + 1]], accumulate=True)
+        return res.cpu().numpy()
+
+    def densities(self, g, tol=1e-13, restart=50, maxiter=10):
+        """boundary data tau (host vector, all boundaries) with the homogeneous solution equal to g on every boundary"""
+        g = np.asarray(g, dtype=float).ravel()
+        if len(self.dqfs) == 1:
+            self.iterations = 0
+            return g
+        count = [0]
+        def cb(_):
+            count[0] += 1
+        A = scipy.sparse.linalg.LinearOperator((g.size, g.size), matvec=self._apply, dtype=float)
+        tau, info = scipy.sparse.linalg.gmres(A, g, rtol=tol, atol=0.0, restart=restart, maxiter=maxiter, callback=cb,
+                                              callback_type='pr_norm')
+        self.iterations = count[0]
+        if info != 0:
+            raise Exception('DirichletCorrection: GMRES on the boundary system did not converge (info = %d)' % info)
+        return tau
+
+    def __call__(self, ue, bc, **kwargs):
+        bv = self.solver.get_boundary_values(ue)
+        g = np.asarray(bc, dtype=float).ravel() - np.asarray(bv, dtype=float).ravel()
+        tau = self.densities(g, **kwargs)
+        t = to_dev(tau)
+        q = self._sources([t[self.boff[i]:self.boff[i + 1]] for i in range(len(self.dqfs))],
+                          empty((int(self.soff[-1]),)))
+        u = to_dev(np.ascontiguousarray(np.asarray(ue), dtype=float))
+        if self.evaluation == 'ewald':
+            self.evaluator(q, grid_out=u, point_out=u[self.n_phys:], accumulate_points=True)
+        else:
+            layer_apply_scalar(self.kind, self.k, self.d_sx, self.d_sy, q, self.d_tx, self.d_ty, out=u, accumulate=True)
+        return EmbeddedFunction(self.ebdyc, linear_data=u.cpu().numpy())

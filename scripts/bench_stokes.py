@@ -12,6 +12,7 @@ ap.add_argument('--grid', type=int, default=1024)
 ap.add_argument('--M', type=int, default=16)
 ap.add_argument('--steps', type=int, default=5)
 ap.add_argument('--check', action='store_true')
+ap.add_argument('--profile', action='store_true', help='per-kernel CUDA-event times of one solve')
 a = ap.parse_args()
 from problems import stokes_star, stokes_manufactured
 from ipde_b200.solvers.multi_boundary.stokes import StokesSolver
@@ -67,4 +68,15 @@ if a.check:
     err = max(np.abs(np.asarray(u)[idx] + cu - np.asarray(ua)[idx]).max(),
               np.abs(np.asarray(v)[idx] + cv - np.asarray(va)[idx]).max())
     out['stokes_solve']['max_velocity_error_vs_analytic'] = float(err)
+if a.profile:
+    import ctypes
+    lib().ipde_profile_start(D.stream())
+    solver.solve_device(fud, fvd, **kw)
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib().ipde_profile_stop(buf, len(buf))
+    prof = {}
+    for line in buf.value.decode().strip().splitlines()[:14]:
+        k, nl, t, by = line.split()
+        prof[k] = {'launches': int(nl), 'ms': float(t)}
+    out['stokes_solve']['kernels_ms_per_solve'] = prof
 print(json.dumps(out))

@@ -277,3 +277,48 @@ def test_stokes_ewald_backend(problem):
         assert np.abs(blk - blk.mean()).max()/ps < 1e-9, (problem, b)
         if problem == 'single':
             assert np.abs(blk).max()/ps < 1e-9
+
+
+def test_dirichlet_correction_single_boundary():
+    """inhomogeneous solve + homogeneous Dirichlet correction reproduces the analytic solution of
+    examples/interior_modified_helmholtz.py:49-52.  The geometry has a grid point within round-off of the boundary
+    that carries annular coordinates but is classified exterior (regression: it used to be scattered onto slot 0 of
+    the compact vector, racing with the legitimate value)."""
+    from ipde_b200.solvers.multi_boundary.modified_helmholtz import ModifiedHelmholtzSolver
+    from ipde_b200.solvers.multi_boundary.homogeneous import DirichletCorrection
+    from ipde_b200.embedded_function import BoundaryFunction
+    ebdyc = single_star(nb=400, M=12, ng=480)
+    assert int((~ebdyc[0].ia_is_phys).sum()) >= 1
+    f, ua, sol = manufactured(ebdyc, 2.0, kk=np.pi/3)
+    solver = ModifiedHelmholtzSolver(ebdyc, 2.0)
+    bc = BoundaryFunction(ebdyc, function=sol)
+    us = []
+    for rep, ev in enumerate(('direct', 'ewald', 'direct')):
+        ue = solver(f, tol=1e-13, restart=60, maxiter=5)
+        u = DirichletCorrection(solver, evaluation=ev)(ue, bc)
+        assert np.abs(np.asarray(u) - np.asarray(ua)).max() < 1e-7, ev
+        us.append(np.asarray(u))
+    assert np.abs(us[0] - us[1]).max() < 1e-11
+    assert np.array_equal(us[0], us[2])
+
+
+def test_dirichlet_correction_three_boundaries():
+    """examples/multi_modified_helmholtz.py:113-177 (boundary collection): GMRES on the block boundary system,
+    sources summed onto all grid and radial points, against the analytic solution"""
+    from ipde_b200.solvers.multi_boundary.modified_helmholtz import ModifiedHelmholtzSolver
+    from ipde_b200.solvers.multi_boundary.homogeneous import DirichletCorrection
+    from ipde_b200.embedded_function import BoundaryFunction
+    ebdyc = three_bodies(nb=200, M=12)
+    f, ua, sol = manufactured(ebdyc, 5.0, kk=10*np.pi/7)
+    solver = ModifiedHelmholtzSolver(ebdyc, 5.0)
+    ue = solver(f, tol=1e-13, restart=60, maxiter=5)
+    bc = BoundaryFunction(ebdyc, function=sol)
+    errs = []
+    for ev in ('direct', 'ewald'):
+        corr = DirichletCorrection(solver, evaluation=ev)
+        u = corr(ue, bc)
+        assert 1 <= corr.iterations <= 25
+        errs.append(np.abs(np.asarray(u) - np.asarray(ua)).max())
+        # the corrected solution takes the boundary values
+        assert np.abs(np.asarray(solver.get_boundary_values(u)) - np.asarray(bc)).max() < 1e-8
+    assert max(errs) < 1e-9, errs

@@ -95,3 +95,22 @@ def test_c_abi_exports_every_declared_symbol():
     assert set(protos) <= exported
     # nothing torch-typed in the ABI
     assert 'torch' not in open(os.path.join(os.path.dirname(LIB_PATH), '..', 'include', 'ipde_b200.h')).read()
+
+
+def test_annulus_points_outside_the_physical_mask_are_flagged():
+    """A grid point within round-off of the boundary can get annular coordinates and still fail the inside test; it
+    has no slot in the compact vector and must be excluded from compact scatters (ia_is_phys).  generate_grid pads
+    automatically chosen sizes to lengths the device FFT supports."""
+    from problems import single_star, three_bodies
+    from ipde_b200._lib import lib
+    e = single_star(nb=400, M=12, ng=480)
+    eb = e[0]
+    assert eb.ia_is_phys.shape == eb.ia_inds.shape
+    n_out = int((~eb.ia_is_phys).sum())
+    assert n_out >= 1
+    assert int(e.phys.sum()) == int(e.phys_not_in_annulus.sum()) + int(eb.ia_is_phys.sum())
+    # every physical in-annulus point has its own slot; the flagged ones map to the placeholder slot 0
+    slots = eb.ia_inds[eb.ia_is_phys]
+    assert np.unique(slots).size == slots.size and np.all(eb.ia_inds[~eb.ia_is_phys] == 0)
+    g = three_bodies(nb=200, M=12).grid
+    assert lib().ipde_fft_size_supported(g.Nx) and lib().ipde_fft_size_supported(g.Ny//2)
