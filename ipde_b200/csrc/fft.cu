@@ -23,6 +23,18 @@ static bool factorize(int n, std::vector<int>& fac) {
         while (n % p == 0) { fac.push_back(p); n /= p; }
     return n == 1 && (int)fac.size() <= IPDE_FFT_MAX_FACTORS;
 }
+// the same plus the remaining (large) prime factors: lengths the tile / generic kernels cannot do still get a plan;
+// they run pass by pass through global memory with an O(R^2) butterfly (k_fft_pass_global_any) -- slow but exact,
+// so a user grid of any size works as it does with numpy.fft
+static bool factorize_any(int n, std::vector<int>& fac) {
+    if (factorize(n, fac)) return true;
+    int rest = n;
+    for (int f : fac) rest /= f;
+    for (int p = 17; (int64_t)p * p <= rest; p += 2)
+        while (rest % p == 0) { fac.push_back(p); rest /= p; }
+    if (rest > 1) fac.push_back(rest);
+    return (int)fac.size() <= IPDE_FFT_MAX_FACTORS;
+}
 
 bool fft_size_supported(int n) {
     std::vector<int> f;
@@ -53,8 +65,8 @@ static void fill_twiddles(std::vector<cplx>& t, int64_t n, int64_t count, int64_
 
 int fft_plan_create(int n, FftPlan** out) {
     std::vector<int> fac;
-    if (!factorize(n, fac)) {
-        ipde_set_error("fft_plan_create: length %d has a prime factor > 13 (unsupported)", n);
+    if (n < 1 || !factorize_any(n, fac)) {
+        ipde_set_error("fft_plan_create: length %d is not supported", n);
         return IPDE_ERR_UNSUPPORTED;
     }
     FftPlan* p = new FftPlan();
@@ -65,6 +77,7 @@ int fft_plan_create(int n, FftPlan** out) {
         p->d.fac[i] = fac[i];
         if (fac[i] > 5 && fac[i] != 8) p->fast = false;
         if (fac[i] != 4 && fac[i] != 8) p->pow2 = false;
+        if (fac[i] > IPDE_FFT_MAX_RADIX) p->any = true;
     }
     std::vector<cplx> tw;
     fill_twiddles(tw, n, n, n);
@@ -413,6 +426,39 @@ __global__ void k_fft_pass_global(FftPlanDev P, const cplx* __restrict__ src, cp
     }
 }
 
+__global__ void k_gather_lines(const cplx* __restrict__ src, cplx* __restrict__ dst, int64_t batch, int n, int64_t src_line,
+                               int64_t src_elem) {
+    const int64_t total = batch * n;
+    for (int64_t it = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x)
+        dst[it] = src[(it / n) * src_line + (it % n) * src_elem];
+}
+
+// the same pass for an arbitrary (large prime) radix: one work item per OUTPUT, an O(R) sum each
+__global__ void k_fft_pass_global_any(FftPlanDev P, const cplx* __restrict__ src, cplx* __restrict__ dst, int64_t batch,
+                                      int64_t src_line, int64_t src_elem, int64_t dst_line, int64_t dst_elem, int Ns, int R,
+                                      int sign, double scale) {
+    const int n = P.n;
+    const int m = n / R;
+    const int tstep = n / (Ns * R);
+    const int64_t total = batch * n;
+    for (int64_t it = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t line = it / n;
+        const int rem = (int)(it % n);
+        const int j = rem % m, t = rem / m;
+        const int k = j % Ns;
+        const cplx* s = src + line * src_line;
+        cplx acc = make_double2(0.0, 0.0);
+        for (int q = 0; q < R; ++q) {
+            // twiddle w_{Ns R}^{k q} times the butterfly root w_R^{q t}, both as powers of w_n
+            const int64_t e = ((int64_t)q * k * tstep + (int64_t)(((int64_t)q * t) % R) * m) % n;
+            const cplx w = P.tw[e];
+            const cplx x = s[(int64_t)(j + q * m) * src_elem];
+            acc = cadd(acc, (sign < 0) ? cmul(x, w) : cmulc(x, w));
+        }
+        dst[line * dst_line + (int64_t)((j - k) * R + k + t * Ns) * dst_elem] = cscale(acc, scale);
+    }
+}
+
 // Lines too long for shared memory: pass-per-launch through `work` (contiguous lines of n).
 static int fft_lines_global(FftPlan* p, const cplx* in, cplx* out, int64_t batch, int64_t in_line, int64_t in_elem,
                             int64_t out_line, int64_t out_elem, int sign, double scale, cudaStream_t st) {
@@ -443,6 +489,19 @@ static int fft_lines_global(FftPlan* p, const cplx* in, cplx* out, int64_t batch
             case 8: LAUNCH(8); break;
             case 11: LAUNCH(11); break;
             case 13: LAUNCH(13); break;
+            default: {
+                // every output reads the whole butterfly: an in-place single pass (prime n) goes through a copy
+                if (src == dst) {
+                    const int64_t tot = batch * n;
+                    const int b3 = (int)std::min<int64_t>(cdiv(tot, threads), (int64_t)ipde_num_sms() * 16);
+                    k_gather_lines<<<b3, threads, 0, st>>>(src, w1, batch, n, sl, se);
+                    KERNEL_CHECK();
+                    src = w1; sl = n; se = 1;
+                }
+                const int64_t outs = batch * n;
+                const int b2 = (int)std::min<int64_t>(cdiv(outs, threads), (int64_t)ipde_num_sms() * 16);
+                k_fft_pass_global_any<<<b2, threads, 0, st>>>(p->d, src, dst, batch, sl, se, dl, de, Ns, R, sign, sc);
+            }
         }
 #undef LAUNCH
         KERNEL_CHECK();
@@ -459,7 +518,7 @@ int fft_rows(FftPlan* p, const cplx* in, cplx* out, int64_t batch, int64_t in_pi
              double scale, cudaStream_t st) {
     if (batch <= 0) return IPDE_OK;
     const int n = p->d.n;
-    if (!p->fast && n <= IPDE_FFT_GENERIC_MAX) return fft_rows_generic(p, in, out, batch, in_pitch, out_pitch, sign, scale, st);
+    if (!p->fast && !p->any && n <= IPDE_FFT_GENERIC_MAX) return fft_rows_generic(p, in, out, batch, in_pitch, out_pitch, sign, scale, st);
     if (n > IPDE_FFT_SMEM_MAX || !p->fast) return fft_lines_global(p, in, out, batch, in_pitch, 1, out_pitch, 1, sign, scale, st);
     const int C = rows_per_tile(n, batch);
     const size_t smem = fft_tile_smem((int64_t)n * C);
@@ -487,7 +546,7 @@ int fft_cols(FftPlan* p, const cplx* in, cplx* out, int64_t elem_stride, int64_t
     if (p->fast && n <= IPDE_FFT_SMEM_MAX)
         return fft_cols_windowed(p, in, out, elem_stride, n_inner, n_outer, outer_stride, sign, scale, tw_mode, tw_big,
                                  row_window_all(), st);
-    if (!p->fast && n <= IPDE_FFT_GENERIC_MAX)
+    if (!p->fast && !p->any && n <= IPDE_FFT_GENERIC_MAX)
         return fft_cols_generic(p, in, out, elem_stride, n_inner, n_outer, outer_stride, sign, scale, tw_mode, tw_big, n_big, st);
     if (n > IPDE_FFT_SMEM_MAX || !p->fast) {
         if (tw_mode != 0) {
@@ -845,7 +904,7 @@ int fft_r2c_rows(FftPlan* p, const double* in, cplx* out, int64_t batch, int64_t
                  cudaStream_t st) {
     if (batch <= 0) return IPDE_OK;
     const int n = p->d.n;
-    if (!p->fast && n <= IPDE_FFT_GENERIC_MAX) return fft_r2c_rows_generic(p, in, out, batch, in_pitch, out_pitch, st);
+    if (!p->fast && !p->any && n <= IPDE_FFT_GENERIC_MAX) return fft_r2c_rows_generic(p, in, out, batch, in_pitch, out_pitch, st);
     if (n > IPDE_FFT_SMEM_MAX || !p->fast) {
         // complex FFT of the packed rows into the front of each output row, then untangle in place is not
         // possible (aliasing), so go through the plan's work buffer
@@ -881,7 +940,7 @@ int fft_c2r_rows(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t
                  double scale, cudaStream_t st) {
     if (batch <= 0) return IPDE_OK;
     const int n = p->d.n;
-    if (!p->fast && n <= IPDE_FFT_GENERIC_MAX) return fft_c2r_rows_generic(p, in, out, batch, in_pitch, out_pitch, scale, st);
+    if (!p->fast && !p->any && n <= IPDE_FFT_GENERIC_MAX) return fft_c2r_rows_generic(p, in, out, batch, in_pitch, out_pitch, scale, st);
     if (n > IPDE_FFT_SMEM_MAX || !p->fast) {
         int rc = ensure_work(p, (size_t)3 * n * batch);
         if (rc) return rc;
@@ -949,7 +1008,7 @@ __global__ void k_scale_by_real(cplx* __restrict__ z, const double* __restrict__
 int fft_mul_fft_rows(FftPlan* p, const cplx* in, cplx* out, const double* m, int64_t batch, cudaStream_t st) {
     if (batch <= 0) return IPDE_OK;
     const int n = p->d.n;
-    if (!p->fast && n <= IPDE_FFT_GENERIC_MAX) return fft_mul_fft_rows_generic(p, in, out, m, batch, st);
+    if (!p->fast && !p->any && n <= IPDE_FFT_GENERIC_MAX) return fft_mul_fft_rows_generic(p, in, out, m, batch, st);
     if (n > IPDE_FFT_SMEM_MAX || !p->fast) {
         int rc = fft_lines_global(p, in, out, batch, n, 1, n, 1, +1, 1.0, st);
         if (rc) return rc;

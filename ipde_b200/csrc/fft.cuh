@@ -32,6 +32,7 @@ struct FftPlan {
     cplx* work = nullptr;         // scratch for the global-memory path
     bool fast = true;             // all radices in {2,3,4,5,8}: tile engine; otherwise fft_generic.cu
     bool pow2 = false;            // radices 4 and 8 only (lean kernel instantiation)
+    bool any = false;             // has a prime factor > 13: global-memory passes with an O(R^2) butterfly
     size_t work_elems = 0;
 };
 

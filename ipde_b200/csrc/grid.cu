@@ -153,30 +153,34 @@ k_cols_mult(FftPlanDev P, const cplx* in, cplx* out, cplx* copy, int64_t elem_st
 
 // The multiplier of one spectrum entry (shared by the tile kernel and the register kernel below).
 // o: outer line, e: element of the line, col: global column inside the half spectrum (without col_offset).
+__device__ __forceinline__ cplx colmult_apply_table(const ColMult& M, cplx v, double m, int o, int e, int col);
 __device__ __forceinline__ cplx colmult_apply(const ColMult& M, cplx v, int64_t addr, int o, int e, int col) {
+    if (M.kind == 3) return colmult_apply_table(M, v, M.table[addr], o, e, col);
+    const int fi = o + M.fmul * e;                                   // frequency index along x
+    const int si = (fi < (M.nx + 1) / 2) ? fi : fi - M.nx;
+    const int jy = col + M.col_offset;
+    const double kx = TWO_PI * (double)si / ((double)M.nx * M.xh);
+    const double ky = TWO_PI * (double)jy / ((double)M.ny * M.yh);
     double m;
-    if (M.kind == 3) {
-        m = M.table[addr];
-        if (M.deriv) {
-            double kk;
-            if (M.deriv == 1) {
-                const int fi = o + M.fmul * e;
-                const int si = (fi < (M.nx + 1) / 2) ? fi : fi - M.nx;
-                kk = (M.nx % 2 == 0 && fi == M.nx / 2) ? 0.0 : TWO_PI * (double)si / ((double)M.nx * M.xh);
-            } else {
-                const int jy = col + M.col_offset;
-                kk = (jy == M.ny / 2) ? 0.0 : TWO_PI * (double)jy / ((double)M.ny * M.yh);
-            }
-            v = make_double2(-kk * v.y, kk * v.x);
+    if (M.kind == IPDE_KIND_POISSON) m = (fi == 0 && jy == 0) ? 0.0 : -1.0 / (kx * kx + ky * ky);
+    else m = 1.0 / (M.k2c + kx * kx + ky * ky);
+    return cscale(v, m);
+}
+
+// kind 3 with the table value already in a register
+__device__ __forceinline__ cplx colmult_apply_table(const ColMult& M, cplx v, double m, int o, int e, int col) {
+    if (M.deriv) {
+        // spectral derivative of the far field: multiply by i k (zero on the unpaired Nyquist line)
+        double kk;
+        if (M.deriv == 1) {
+            const int fi = o + M.fmul * e;
+            const int si = (fi < (M.nx + 1) / 2) ? fi : fi - M.nx;
+            kk = (M.nx % 2 == 0 && fi == M.nx / 2) ? 0.0 : TWO_PI * (double)si / ((double)M.nx * M.xh);
+        } else {
+            const int jy = col + M.col_offset;
+            kk = (jy == M.ny / 2) ? 0.0 : TWO_PI * (double)jy / ((double)M.ny * M.yh);
         }
-    } else {
-        const int fi = o + M.fmul * e;
-        const int si = (fi < (M.nx + 1) / 2) ? fi : fi - M.nx;
-        const int jy = col + M.col_offset;
-        const double kx = TWO_PI * (double)si / ((double)M.nx * M.xh);
-        const double ky = TWO_PI * (double)jy / ((double)M.ny * M.yh);
-        if (M.kind == IPDE_KIND_POISSON) m = (fi == 0 && jy == 0) ? 0.0 : -1.0 / (kx * kx + ky * ky);
-        else m = 1.0 / (M.k2c + kx * kx + ky * ky);
+        v = make_double2(-kk * v.y, kk * v.x);
     }
     return cscale(v, m);
 }
@@ -215,6 +219,13 @@ k_cols_mult_short(const cplx* __restrict__ tw, const cplx* in, cplx* out, cplx* 
             load(tile, v);
         }
         const ShortTile S = short_tile<K::LOGC>(tile, tiles_per_outer, c, n_inner, outer_stride, W.row_o);
+        // table symbol: issue its loads now, they arrive while the forward transform runs
+        double mt[K::PREFETCH ? E : 1];
+        const bool table_early = K::PREFETCH && M.kind == 3 && S.colok;
+        if (table_early) {
+#pragma unroll
+            for (int s = 0; s < E; ++s) mt[s] = M.table[S.base + (int64_t)short_elem_b<RA, RB>(jt, s) * elem_stride];
+        }
         if (do_fwd) short_fft<RA, RB, -1>(v, sm[0], c, jt, tw);
         if (S.colok) {
 #pragma unroll
@@ -222,7 +233,7 @@ k_cols_mult_short(const cplx* __restrict__ tw, const cplx* in, cplx* out, cplx* 
                 const int e = short_elem_b<RA, RB>(jt, s);
                 const int64_t addr = S.base + (int64_t)e * elem_stride;
                 if (copy_mode == 1) copy[addr] = v[s];
-                v[s] = colmult_apply(M, v[s], addr, S.o, e, S.col);
+                v[s] = table_early ? colmult_apply_table(M, v[s], mt[s], S.o, e, S.col) : colmult_apply(M, v[s], addr, S.o, e, S.col);
                 if (copy_mode == 2) copy[addr] = v[s];
             }
         }

@@ -15,8 +15,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ --csv --l
     python bench.py --steps 2 --warmup 3 --slab-grid 0 --no-cpu-baseline > $out/${tag}_ncu_launches.log 2>&1
 python scripts/summarize_launches.py $out/${tag}_launches.csv --tail 2000 > $out/${tag}_launches_summary.txt
 head -25 $out/${tag}_launches_summary.txt
-# one step's worth of launches of each kernel, taken after the three warm-up steps (7 / 4 / 4 launches per step)
-for spec in k_fft_cols:14:7 k_cols_mult:8:4 k_gemv:8:4; do
+# one step's worth of launches of each kernel, taken after the three warm-up steps (8 / 4 / 4 launches per step)
+for spec in k_fft_cols:24:8 k_cols_mult:12:4 k_gemv:12:4; do
   k=${spec%%:*}; r=${spec#*:}; skip=${r%%:*}; cnt=${r#*:}
   ncu --set full --clock-control none -k regex:^${k} -s $skip -c $cnt -f -o $out/${tag}_${k} \
       python bench.py --steps 1 --warmup 3 --slab-grid 0 --no-cpu-baseline > $out/${tag}_ncu_${k}.log 2>&1
@@ -27,3 +27,8 @@ for spec in k_fft_cols:14:7 k_cols_mult:8:4 k_gemv:8:4; do
   fi
 done
 du -sh $out
+# Stokes solve timing (rows a5, a6, a10, a12) and the slab grid solve kernel split
+python scripts/bench_stokes.py --grid 1024 --check --profile > $out/${tag}_stokes_1024.json 2> $out/${tag}_stokes_1024.err
+tail -c 400 $out/${tag}_stokes_1024.json
+python scripts/run_slab_multi.py --grid 16384 --profile > $out/${tag}_slab_16384_1gpu.txt 2>&1
+cat $out/${tag}_slab_16384_1gpu.txt | tail -6

@@ -21,7 +21,8 @@ def D():
     return dev
 
 
-@pytest.mark.parametrize('n', [8, 60, 64, 96, 100, 256, 512, 1000, 1024, 1430, 2048, 4096, 7168, 8192, 30030])
+@pytest.mark.parametrize('n', [8, 60, 64, 79, 96, 100, 256, 474, 512, 1000, 1022, 1024, 1430, 2048, 4096, 7168, 8192,
+                               30030])
 def test_fft_c2c(D, n):
     rng = np.random.default_rng(n)
     x = rng.standard_normal((3, n)) + 1j*rng.standard_normal((3, n))
@@ -36,7 +37,7 @@ def test_fft_c2c(D, n):
     assert rel(xd.cpu().numpy(), np.fft.fft(x)) < 1e-14*np.log2(n)
 
 
-@pytest.mark.parametrize('n', [96, 256, 512, 1024, 2048, 4096, 8192, 9000])
+@pytest.mark.parametrize('n', [96, 256, 474, 512, 1024, 2048, 4096, 8192, 9000])
 def test_fft_mul_fft(D, n):
     rng = np.random.default_rng(n)
     x = rng.standard_normal((5, n)) + 1j*rng.standard_normal((5, n))
@@ -48,7 +49,8 @@ def test_fft_mul_fft(D, n):
 
 @pytest.mark.parametrize('shape', [(64, 64), (96, 80), (100, 36), (1024, 40), (2048, 128), (128, 2048), (4096, 64), (4096, 100),
                                    (6000, 20), (8192, 40), (16384, 36),
-                                   (9, 512), (15, 1024), (20, 2048), (10, 4096), (6, 8192), (8, 16384)])
+                                   (9, 512), (15, 1024), (20, 2048), (10, 4096), (6, 8192), (8, 16384),
+                                   (474, 474), (94, 158), (2102, 34)])
 def test_grid_fft2(D, shape):
     nx, ny = shape
     rng = np.random.default_rng(nx + ny)
@@ -62,7 +64,7 @@ def test_grid_fft2(D, shape):
 
 
 @pytest.mark.parametrize('kind,k', [(1, 2.5), (0, 0.0)])
-@pytest.mark.parametrize('shape', [(96, 80), (1024, 48), (2048, 64), (4096, 36), (8192, 36), (16384, 40)])
+@pytest.mark.parametrize('shape', [(96, 80), (1024, 48), (2048, 64), (4096, 36), (8192, 36), (16384, 40), (474, 94)])
 def test_grid_solve_scalar(D, kind, k, shape):
     from ipde_b200._lib import lib
     nx, ny = shape

@@ -322,3 +322,17 @@ def test_dirichlet_correction_three_boundaries():
         # the corrected solution takes the boundary values
         assert np.abs(np.asarray(solver.get_boundary_values(u)) - np.asarray(bc)).max() < 1e-8
     assert max(errs) < 1e-9, errs
+
+
+def test_grid_and_boundary_sizes_with_large_prime_factors():
+    """numpy.fft takes any length; the device FFT falls back to global-memory passes with an O(R^2) butterfly for
+    prime factors > 13 (grid 94 = 2*47, boundary 158 = 2*79): same parity bar as everywhere else"""
+    from ipde_b200.solvers.multi_boundary.modified_helmholtz import ModifiedHelmholtzSolver
+    ebdyc = single_star(nb=158, M=8, ng=94)
+    f, ua, _ = manufactured(ebdyc, 2.0)
+    for solver_type in ('spectral', 'fourth'):
+        solver = ModifiedHelmholtzSolver(ebdyc, 2.0, solver_type=solver_type)
+        ue = solver(f, tol=1e-13, restart=40, maxiter=5)
+        uo = oracle_for(solver, 'modified_helmholtz', 2.0, solver_type)(f, tol=1e-13, restart=40, maxiter=5)
+        linf, l2 = rel_errors(ue, uo)
+        assert linf < TOL and l2 < TOL, (solver_type, linf, l2)
