@@ -4,10 +4,10 @@ from ..internals.stokes import StokesHelper
 
 
 class StokesSolver(VectorSolver):
-    def __init__(self, ebdyc, solver_type='spectral', helpers=None, grid_backend=None):
+    def __init__(self, ebdyc, solver_type='spectral', helpers=None, grid_backend=None, shard_boundaries=False):
         if not ebdyc.bumpy_readied:
             raise Exception('Stokes solver requires embedded boundary collection with a bump function.')
-        super().__init__(ebdyc, solver_type, helpers, grid_backend=grid_backend)
+        super().__init__(ebdyc, solver_type, helpers, grid_backend=grid_backend, shard_boundaries=shard_boundaries)
 
     def _get_helper_compatability(self, ebdy, helper):
         """0: start over, 1: annular solver reusable, 2: helper reusable as is"""

@@ -43,6 +43,32 @@ class VectorSolver(object):
         self.dev = self.ebdyc.device
         self.iteration_counts = None
         self._define_grid_evaluator()
+        self._assign_boundaries(bool(kwargs.get('shard_boundaries', False)))
+
+    def _assign_boundaries(self, shard):
+        """
+        Boundary sharding, per-solve work only: with `shard_boundaries=True` under torch.distributed
+        every boundary's annular Stokes solve, QFS applies and correction run on ONE rank (greedy by n_b*M, largest
+        first); the grid-sized work is replicated.  Exchanges per solve: a broadcast of every boundary's effective
+        sources (2 S_b doubles) and of its radial solution (3 M n_b doubles) from the owner.  Unlike the scalar
+        solver, all ranks still build every helper (setup is replicated).
+        """
+        import torch.distributed as dist
+        self.world, self.rank = 1, 0
+        if shard and dist.is_available() and dist.is_initialized():
+            self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        cost = [e.bdy.N*e.M for e in self.ebdyc]
+        load = [0]*self.world
+        self.owner = [0]*len(cost)
+        for b in sorted(range(len(cost)), key=lambda i: -cost[i]):
+            r = min(range(self.world), key=lambda i: load[i])
+            self.owner[b] = r
+            load[r] += cost[b]
+
+    def _bcast(self, t, src):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.broadcast(t, src=src)
 
     # S*T above which the all-pairs stokeslet sum loses to the spectral-Ewald evaluator
     EWALD_THRESHOLD = 2.0e8
@@ -143,7 +169,11 @@ class VectorSolver(object):
         # per-boundary annular solves and effective sources
         nsrc = self.grid_sources.N
         sigmag = empty((2, nsrc))
+        import torch
+        its = torch.zeros(len(self.helpers), dtype=torch.int64, device=sigmag.device)
         for b, helper in enumerate(self.helpers):
+            if self.owner[b] != self.rank:
+                continue
             r0, r1 = D.radial_offsets[b], D.radial_offsets[b + 1]
             o0, o1 = D.bdy_offsets[b], D.bdy_offsets[b + 1]
             M, n = helper.ebdy.M, helper.ebdy.bdy.N
@@ -152,7 +182,16 @@ class VectorSolver(object):
             s0, s1 = self.source_offsets[b], self.source_offsets[b + 1]
             for c in range(2):
                 L.ipde_vec_mul(ptr(sg[c]), ptr(self.d_gsw[s0:s1]), ptr(sigmag[c, s0:s1]), int(s1 - s0), st)
-        self.iteration_counts = [helper.iterations_last_call for helper in self.helpers]
+            its[b] = helper.iterations_last_call
+        if self.world > 1:
+            for b in range(len(self.helpers)):
+                s0, s1 = self.source_offsets[b], self.source_offsets[b + 1]
+                for c in range(2):
+                    self._bcast(sigmag[c, s0:s1], self.owner[b])
+                self._bcast(its[b:b + 1], self.owner[b])
+            self.iteration_counts = [int(v) for v in its.cpu()]
+        else:
+            self.iteration_counts = [helper.iterations_last_call for helper in self.helpers]
         # all grid-side stokeslets -> (phys, not in annulus) U (interface points)
         dof = self.ebdyc.dof
         res = [empty((dof,)) for _ in range(3)]
@@ -170,8 +209,13 @@ class VectorSolver(object):
             iface = out[:, D.n_pna:]
         for b, helper in enumerate(self.helpers):
             o0, o1 = D.bdy_offsets[b], D.bdy_offsets[b + 1]
-            bi = [iface[k, o0:o1].contiguous() for k in range(3)]
-            urs = helper.correct(bi[0], bi[1], bi[2], single)
+            if self.owner[b] == self.rank:
+                bi = [iface[k, o0:o1].contiguous() for k in range(3)]
+                urs = [u.contiguous() for u in helper.correct(bi[0], bi[1], bi[2], single)]
+            else:
+                urs = [empty((helper.ebdy.M, helper.ebdy.bdy.N)) for _ in range(3)]
+            for k in range(3):
+                self._bcast(urs[k], self.owner[b])
             db = D.ebdys[b]
             r0, r1 = D.radial_offsets[b], D.radial_offsets[b + 1]
             for k in range(3):

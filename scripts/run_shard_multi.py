@@ -40,5 +40,26 @@ if rank == 0:
           'ms per solve sharded %.2f vs unsharded %.2f' % (world, sharded.owner, sharded.iteration_counts,
                                                             max(gathered), ts*1e3, tf*1e3))
     assert max(gathered) == 0.0
+
+# ---- the same for the Stokes solver (three bodies): python ... run_shard_multi.py 100 ewald stokes
+if len(sys.argv) > 3 and sys.argv[3] == 'stokes':
+    from problems import three_bodies, stokes_manufactured
+    from ipde_b200.solvers.multi_boundary.stokes import StokesSolver
+    eb3 = three_bodies(nb=nb, M=8, bump=True)
+    fu, fv, _, _, _, _ = stokes_manufactured(eb3)
+    kws = dict(tol=1e-13, restart=80, maxiter=4)
+    sh = StokesSolver(eb3, grid_backend=backend, shard_boundaries=True)
+    fl = StokesSolver(eb3, grid_backend=backend)
+    rs, rf = sh(fu, fv, **kws), fl(fu, fv, **kws)
+    d = float(max(np.abs(np.asarray(a) - np.asarray(b)).max() for a, b in zip(rs, rf)))
+    g2 = [None]*world
+    if world > 1:
+        dist.all_gather_object(g2, d)
+    else:
+        g2 = [d]
+    if rank == 0:
+        print('Stokes boundary sharding: world %d, owners %s, iterations %s / %s, max |sharded - unsharded| %.2e' %
+              (world, sh.owner, sh.iteration_counts, fl.iteration_counts, max(g2)))
+        assert max(g2) == 0.0
 if world > 1:
     dist.destroy_process_group()
