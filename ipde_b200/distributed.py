@@ -54,6 +54,31 @@ class SlabLayout(object):
                 out[:, a:b] = blocks[q, :, :b - a]
         return out
 
+    # sub-block [koff, koff + Pk) of every rank's column block (chunked, overlapped exchange)
+    def set_chunks(self, K, round_up=lambda n: n):
+        """make Pc a multiple of K chunks of width Pk, with Pk - 1 rounded up by `round_up` (a supported FFT length)"""
+        Pk = round_up(max(2, -(-self.Pc//K) - 1)) + 1
+        self.Pc = Pk*K
+        self.col0 = self.rank*self.Pc
+        return Pk
+
+    def pack_chunk(self, spec_rows, koff, Pk):
+        out = np.zeros((self.R, self.rows, Pk), dtype=complex)
+        for q in range(self.R):
+            a = q*self.Pc + koff
+            b = min(self.P, a + Pk)
+            if b > a:
+                out[q, :, :b - a] = spec_rows[:, a:b]
+        return out
+
+    def unpack_chunk(self, blocks, koff, Pk, out):
+        for q in range(self.R):
+            a = q*self.Pc + koff
+            b = min(self.P, a + Pk)
+            if b > a:
+                out[:, a:b] = blocks[q, :, :b - a]
+        return out
+
 
 def exchange(send, recv, group=None):
     """all-to-all of equal contiguous blocks along dim 0; NCCL collective on the device, point-to-point on gloo"""
@@ -72,11 +97,30 @@ def exchange(send, recv, group=None):
         r.wait()
 
 
-def slab_grid_solve_numpy(layout, f_local, symbol, group=None):
+def slab_grid_solve_numpy(layout, f_local, symbol, group=None, chunks=1):
     """CPU statement of the distributed solve (NumPy local transforms + the same exchanges): returns the local rows of
-    Re ifft2(symbol * fft2(f)).  `symbol(kx_index_array, ky_index_array)` gives the real multiplier."""
+    Re ifft2(symbol * fft2(f)).  `symbol(kx_index_array, ky_index_array)` gives the real multiplier.  chunks > 1
+    follows the sub-block schedule of SlabGridSolver (one exchange per sub-block each way)."""
     L = layout
     spec = np.fft.rfft(f_local, axis=1)                                   # (rows, P)
+    if chunks > 1:
+        Pk = L.set_chunks(chunks)
+        back_spec = np.zeros((L.rows, L.P), dtype=complex)
+        for c in range(chunks):
+            send = torch.from_numpy(L.pack_chunk(spec, c*Pk, Pk))
+            recv = torch.empty_like(send)
+            exchange(send, recv, group)
+            cols = recv.numpy().reshape(L.nx, Pk)
+            j = L.col0 + c*Pk + np.arange(Pk)
+            valid = j < L.P
+            m = np.zeros((L.nx, Pk))
+            m[:, valid] = symbol(np.arange(L.nx)[:, None], j[valid][None, :])
+            back = np.fft.ifft(np.fft.fft(cols, axis=0)*m, axis=0)
+            send2 = torch.from_numpy(np.ascontiguousarray(back.reshape(L.R, L.rows, Pk)))
+            recv2 = torch.empty_like(send2)
+            exchange(send2, recv2, group)
+            L.unpack_chunk(recv2.numpy(), c*Pk, Pk, back_spec)
+        return np.fft.irfft(back_spec, n=L.ny, axis=1)
     send = torch.from_numpy(L.pack(spec))
     recv = torch.empty_like(send)
     exchange(send, recv, group)
@@ -119,9 +163,7 @@ class SlabGridSolver(object):
         if world > 1:
             # the column plan is a grid plan of width 2 (Pk - 1): round the chunk width up to a supported length
             # (a few zero columns), and make Pc a multiple of the number of chunks
-            Pk = lib().ipde_fft_next_size(max(2, -(-Ls.Pc//K) - 1)) + 1
-            Ls.Pc = Pk*K
-            Ls.col0 = rank*Ls.Pc
+            Ls.set_chunks(K, lib().ipde_fft_next_size)
         self.Pk = Ls.Pc//K
         self.nx, self.ny, self.xh, self.yh, self.kind, self.k = nx, ny, float(xh), float(yh), int(kind), float(k)
         L_ = lib()

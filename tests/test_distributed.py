@@ -16,7 +16,7 @@ def _reference(f, xh, yh, k):
     return np.fft.ifft2(np.fft.fft2(f)/(k*k + kx*kx + ky*ky)).real
 
 
-def _worker(rank, world, port, nx, ny, q):
+def _worker(rank, world, port, nx, ny, q, chunks=1):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -29,19 +29,19 @@ def _worker(rank, world, port, nx, ny, q):
             kx = np.fft.fftfreq(nx, xh/(2*np.pi))[i]
             ky = 2*np.pi*j/(ny*yh)
             return 1.0/(k*k + kx*kx + ky*ky)
-        u = slab_grid_solve_numpy(L, f[L.row0:L.row0 + L.rows], symbol)
+        u = slab_grid_solve_numpy(L, f[L.row0:L.row0 + L.rows], symbol, chunks=chunks)
         ref = _reference(f, xh, yh, k)[L.row0:L.row0 + L.rows]
         q.put((rank, float(np.abs(u - ref).max()/np.abs(ref).max())))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world,nx,ny', [(2, 32, 48), (3, 36, 40)])
-def test_slab_solve_gloo(world, nx, ny):
+@pytest.mark.parametrize('world,nx,ny,chunks', [(2, 32, 48, 1), (3, 36, 40, 1), (2, 32, 48, 3), (3, 36, 64, 2)])
+def test_slab_solve_gloo(world, nx, ny, chunks):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 1000) + world
-    procs = [ctx.Process(target=_worker, args=(r, world, port, nx, ny, q)) for r in range(world)]
+    port = 29500 + (os.getpid() % 1000) + world + 10*chunks
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nx, ny, q, chunks)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in range(world)]
@@ -59,6 +59,15 @@ def test_slab_pack_unpack_roundtrip():
         s = rng.standard_normal((L.rows, L.P)) + 1j*rng.standard_normal((L.rows, L.P))
         assert np.array_equal(L.unpack(L.pack(s)), s)
         assert L.Pc*world >= L.P
+        # chunked: the sub-blocks tile every rank's block, widths rounded up
+        for K in (2, 3):
+            Lc = SlabLayout(nx, ny, world, 0)
+            Pk = Lc.set_chunks(K, round_up=lambda n: n + (n % 2))
+            assert Lc.Pc == Pk*K and Lc.Pc*world >= Lc.P
+            back = np.zeros_like(s)
+            for c in range(K):
+                Lc.unpack_chunk(Lc.pack_chunk(s, c*Pk, Pk), c*Pk, Pk, back)
+            assert np.array_equal(back, s)
 
 
 @pytest.mark.gpu
@@ -84,4 +93,14 @@ def test_slab_grid_solver_single_gpu(n):
     assert np.array_equal(packed.cpu().numpy(), L.pack(s))
     back = D.empty((L.rows, L.P), torch.complex128)
     lib().ipde_slab_unpack(D.ptr(packed), L.rows, L.P, L.R, L.Pc, D.ptr(back), D.stream())
+    assert np.array_equal(back.cpu().numpy(), s)
+    # chunked variants
+    Lc = SlabLayout(64, 50, 4, 1)
+    Pk = Lc.set_chunks(2, lib().ipde_fft_next_size)
+    back = torch.zeros((Lc.rows, Lc.P), dtype=torch.complex128, device='cuda')
+    for c in range(2):
+        pc = D.empty((Lc.R, Lc.rows, Pk), torch.complex128)
+        lib().ipde_slab_pack_chunk(D.ptr(ds), Lc.rows, Lc.P, Lc.R, Lc.Pc, c*Pk, Pk, D.ptr(pc), D.stream())
+        assert np.array_equal(pc.cpu().numpy(), Lc.pack_chunk(s, c*Pk, Pk))
+        lib().ipde_slab_unpack_chunk(D.ptr(pc), Lc.rows, Lc.P, Lc.R, Lc.Pc, c*Pk, Pk, D.ptr(back), D.stream())
     assert np.array_equal(back.cpu().numpy(), s)
