@@ -196,6 +196,36 @@ def parse_profile(text):
     return recs
 
 
+def run_slab(args, world, rank, barrier):
+    """periodic grid solve of ONE grid slab-decomposed over all ranks (strong scaling of the FFT core)"""
+    import torch
+    import torch.distributed as dist
+    from ipde_b200.distributed import SlabGridSolver
+    ns = args.slab_grid
+    S = SlabGridSolver(ns, ns, 2.4/ns, 2.4/ns, 1, HELMHOLTZ_K, chunks=args.slab_chunks)
+    gen = torch.Generator(device='cuda')
+    gen.manual_seed(rank)
+    fl = torch.randn((S.L.rows, ns), dtype=torch.float64, device='cuda', generator=gen)
+    out = torch.empty_like(fl)
+    for _ in range(3):
+        S.solve(fl, out=out)
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(args.steps):
+        S.solve(fl, out=out)
+    s1.record()
+    barrier()
+    tt = torch.tensor([s0.elapsed_time(s1)/args.steps], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    return {'what': 'periodic grid solve (r2c rows, all-to-all, column FFT + symbol + inverse, all-to-all, c2r rows) '
+                    'of ONE %d^2 grid slab-decomposed over all ranks; strong scaling of the FFT core' % ns,
+            'grid': [ns, ns], 'n_gpus': world, 'chunks': S.K, 'ms_per_solve': float(tt[0]),
+            'grid_point_solves_per_s': ns*ns/(float(tt[0])*1e-3),
+            'alltoall_bytes_per_rank_per_solve': int(S.alltoall_bytes_per_rank)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -292,40 +322,18 @@ def main():
     prof = parse_profile(buf.value.decode())
     gmres_its = solver.iteration_counts
 
-    # ---- one problem over all ranks: slab-decomposed periodic grid solve (NCCL all-to-all transposes)
-    slab = None
-    if args.slab_grid > 0 and args.slab_grid % world == 0:
-        from ipde_b200.distributed import SlabGridSolver
-        ns = args.slab_grid
-        del solver, res
-        torch.cuda.empty_cache()
-        S = SlabGridSolver(ns, ns, 2.4/ns, 2.4/ns, 1, HELMHOLTZ_K, chunks=args.slab_chunks)
-        gen = torch.Generator(device='cuda')
-        gen.manual_seed(rank)
-        fl = torch.randn((S.L.rows, ns), dtype=torch.float64, device='cuda', generator=gen)
-        out = torch.empty_like(fl)
-        for _ in range(3):
-            S.solve(fl, out=out)
-        barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        for _ in range(args.steps):
-            S.solve(fl, out=out)
-        s1.record()
-        barrier()
-        tt = torch.tensor([s0.elapsed_time(s1)/args.steps], dtype=torch.float64, device='cuda')
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        slab = {'what': 'periodic grid solve (r2c rows, all-to-all, column FFT + symbol + inverse, all-to-all, c2r rows) '
-                        'of ONE %d^2 grid slab-decomposed over all ranks; strong scaling of the FFT core' % ns,
-                'grid': [ns, ns], 'n_gpus': world, 'chunks': S.K, 'ms_per_solve': float(tt[0]),
-                'grid_point_solves_per_s': ns*ns/(float(tt[0])*1e-3),
-                'alltoall_bytes_per_rank_per_solve': int(S.alltoall_bytes_per_rank)}
-        del S, fl, out
-
     times = torch.tensor([ms_total, e2e_s*1e3], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    # ---- one problem over all ranks: slab-decomposed periodic grid solve (NCCL all-to-all transposes)
+    slab = None
+    if args.slab_grid > 0 and args.slab_grid % world == 0:
+        del solver, res
+        torch.cuda.empty_cache()
+        try:
+            slab = run_slab(args, world, rank, barrier)
+        except Exception as exc:          # the headline numbers above are already reduced over the ranks
+            slab = {'error': '%s: %s' % (type(exc).__name__, exc)}
     ms_total, e2e_ms = float(times[0]), float(times[1])
     ms_per_step = ms_total/args.steps
     value = world*npts*args.steps/(ms_total*1e-3)
