@@ -336,3 +336,26 @@ def test_grid_and_boundary_sizes_with_large_prime_factors():
         uo = oracle_for(solver, 'modified_helmholtz', 2.0, solver_type)(f, tol=1e-13, restart=40, maxiter=5)
         linf, l2 = rel_errors(ue, uo)
         assert linf < TOL and l2 < TOL, (solver_type, linf, l2)
+
+
+def test_dirichlet_correction_matches_oracle():
+    """device homogeneous correction against its all-pairs NumPy statement (oracle/homogeneous.py) on identical
+    inputs: three boundaries, both evaluation back-ends"""
+    from ipde_b200.solvers.multi_boundary.modified_helmholtz import ModifiedHelmholtzSolver
+    from ipde_b200.solvers.multi_boundary.homogeneous import DirichletCorrection
+    from ipde_b200.embedded_function import BoundaryFunction
+    from oracle.homogeneous import OracleDirichletCorrection
+    ebdyc = three_bodies(nb=100, M=8)
+    f, ua, sol = manufactured(ebdyc, 5.0, kk=10*np.pi/7)
+    solver = ModifiedHelmholtzSolver(ebdyc, 5.0)
+    ue = solver(f, tol=1e-13, restart=60, maxiter=5)
+    bc = BoundaryFunction(ebdyc, function=sol)
+    corr = DirichletCorrection(solver, evaluation='direct')
+    O = OracleDirichletCorrection(ebdyc, 'modified_helmholtz', 5.0, corr.qfs)
+    uo = O(ue, bc)
+    for ev in ('direct', 'ewald'):
+        c = corr if ev == 'direct' else DirichletCorrection(solver, evaluation=ev)
+        u = c(ue, bc)
+        linf, l2 = rel_errors(u, uo)
+        assert linf < 1e-10 and l2 < 1e-10, (ev, linf, l2)
+        assert abs(c.iterations - O.iterations) <= 3

@@ -94,3 +94,28 @@ def test_oracle_annular_stokes_matches_reference_golden(golden_dir):
     assert rel(S.preconditioner(g['x']), g['Px']) < 1e-11
     ur, ut, p = S.solve(RAG, g['fr'], g['ft'], g['irg'], g['itg'], g['org'], g['otg'], tol=1e-14, restart=80, maxiter=4)
     assert rel(ur, g['ur']) < 1e-12 and rel(ut, g['ut']) < 1e-12 and rel(p, g['p']) < 1e-11
+
+
+def test_oracle_dirichlet_correction_reproduces_manufactured_solution():
+    """SURVEY 8(f).1 on the CPU: oracle inhomogeneous solve + homogeneous Dirichlet correction lands on the analytic
+    solution of examples/interior_modified_helmholtz.py:49-52 (what pins this step in the absence of pybie2d)"""
+    from problems import single_star, manufactured
+    from oracle.solvers import OracleScalarSolver
+    from oracle.homogeneous import OracleDirichletCorrection
+    from ipde_b200.qfs import Modified_Helmholtz_QFS
+    from ipde_b200.embedded_function import EmbeddedFunction, BoundaryFunction
+    k = 2.0
+    ebdyc = single_star(nb=300, M=8)
+    f, ua, sol = manufactured(ebdyc, k, kk=np.pi/3)
+    ebdy = ebdyc[0]
+    tolq = getattr(ebdy, 'qfs_tolerance', 1e-12)
+    pair = (Modified_Helmholtz_QFS(ebdy.interface, True, True, True, k, tol=min(tolq, 1e-12), u2s=False, device_build=False),
+            Modified_Helmholtz_QFS(ebdy.interface, False, True, True, k, tol=min(tolq, 1e-12), device_build=False))
+    O = OracleScalarSolver(ebdyc, 'modified_helmholtz', k, 'spectral', [pair])
+    uo = EmbeddedFunction(ebdyc, linear_data=np.asarray(O(f, tol=1e-13, restart=60, maxiter=5)))
+    qb = Modified_Helmholtz_QFS(ebdy.bdy, True, True, False, k, tol=1e-12, b2c=False, device_build=False)
+    corr = OracleDirichletCorrection(ebdyc, 'modified_helmholtz', k, [qb])
+    u = corr(uo, BoundaryFunction(ebdyc, function=sol))
+    err = np.abs(u - np.asarray(ua)).max()
+    assert np.abs(np.asarray(uo) - np.asarray(ua)).max() > 0.1      # the correction matters
+    assert err < 1e-6, err          # 2.2e-7 at this resolution (n_b = 300, M = 8)
