@@ -1,13 +1,23 @@
-"""NumPy prototype of the spectral-Ewald free-space evaluator (eta = 1 split, no 4x grid): validates the math the
-CUDA evaluator (csrc/ewald.cu) implements.  Spread with w = Gaussian(2 xi^2), multiply by the truncated kernel
-sampled directly on the FFT grid (period >= extent + L), on-grid values via the extra factor exp(-k^2/8xi^2),
-off-grid values by gathering H with the same window; local part G - G_far within rc."""
-import sys, os
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
-import numpy as np, scipy.special as ss
+"""
+ORACLE (test infrastructure, CPU, NumPy) -- never imported by the product.
+
+NumPy statement of the spectral-Ewald free-space evaluator that csrc/ewald.cu implements (mathematics and host
+tables: ipde_b200/ewald.py): spread with the Gaussian w, multiply the FFT by the truncated kernel sampled directly on
+the FFT grid (period >= extent + L), on-grid values via the extra factor exp(-k^2/8 xi^2), off-grid values by
+gathering H with the same window, local part G - G_far within rc from the piecewise Chebyshev tables.  It replaces the
+reference's Grid_Evaluator / Layer_Apply sums (ipde/grid_evaluators/scalar_grid_evaluator.py:188-231,299-307;
+kernels laplace_grid_evaluator.py:8-12, modified_helmholtz_grid_evaluator.py:8-9) and is pinned by the all-pairs sum
+of exactly those kernels (tests/test_oracle.py).
+"""
+import numpy as np
+import scipy.special as ss
+
 from ipde_b200.ewald import EwaldParameters, trunc_kernel_hat, local_tables, eval_local
 
-def run(N=96, kind=1, hk=2.0, seed=0):
+
+def ewald_against_direct_sum(N=96, kind=1, hk=2.0, seed=0):
+    """returns (relative error at grid targets, at off-grid targets) of the NumPy spectral-Ewald evaluation against
+    the all-pairs sum, for 150 sources on an ellipse and targets inside it"""
     h = 2.4/N
     xv = -1.2 + h*np.arange(N)
     rng = np.random.default_rng(seed)
@@ -53,12 +63,5 @@ def run(N=96, kind=1, hk=2.0, seed=0):
         dd2 = (XP - tx[t])**2 + (YP - ty[t])**2
         far_off[t - ngrid] = h*h*(np.where(dd2 < rw*rw, 2*xi*xi/np.pi*np.exp(-2*xi*xi*dd2), 0.0)*H).sum()
     err_off = np.abs(far_off + loc[ngrid:] - exact[ngrid:]).max()/np.abs(exact).max()
-    print('kind %d k=%g N=%d P2=%d m=%d sw=%d: rel err grid %.2e off-grid %.2e (min dist/h %.2f)'
-          % (kind, hk, N, P2, m, int(round(rc/h)), err_grid, err_off, d.min()/h))
+    return err_grid, err_off
 
-if __name__ == '__main__':
-    run(96, 0)
-    run(96, 1, 2.0)
-    run(128, 1, 5.0)
-    run(64, 1, 20.0)
-    run(128, 1, 0.3)

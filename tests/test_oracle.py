@@ -1,6 +1,7 @@
 """CPU: the oracle against golden vectors produced by the reference's own code (oracle/make_golden.py)."""
 import os
 import numpy as np
+import pytest
 from oracle.annular import (ApproximateAnnularGeometry, RealAnnularGeometry,
                             AnnularModifiedHelmholtzSolver, AnnularPoissonSolver)
 from oracle import solvers as osol
@@ -119,3 +120,13 @@ def test_oracle_dirichlet_correction_reproduces_manufactured_solution():
     err = np.abs(u - np.asarray(ua)).max()
     assert np.abs(np.asarray(uo) - np.asarray(ua)).max() > 0.1      # the correction matters
     assert err < 1e-6, err          # 2.2e-7 at this resolution (n_b = 300, M = 8)
+
+
+@pytest.mark.parametrize('kind,kappa,N', [(0, 0.0, 96), (1, 2.0, 96), (1, 20.0, 64)])
+def test_numpy_spectral_ewald_matches_direct_sum(kind, kappa, N):
+    """host tables and mathematics of the free-space evaluator (ipde_b200/ewald.py) on the CPU: truncated kernel,
+    Gaussian split, local Chebyshev tables -- against the all-pairs sum of the reference's kernels"""
+    from oracle.ewald import ewald_against_direct_sum
+    err_grid, err_off = ewald_against_direct_sum(N, kind, kappa)
+    bound = 1e-12 if kappa >= 20.0 else 1e-13
+    assert err_grid < bound and err_off < bound, (err_grid, err_off)
