@@ -83,6 +83,25 @@ __device__ __forceinline__ double ewald_gloc(double z, const double* __restrict_
     return s;
 }
 
+// The Gaussian window is separable: exp(-2 xi^2 |x - y_s|^2) = e_x(s, row) * e_y(s, col).  One pass fills the 2 * 16
+// factors of every source of the chunk (8 exp per thread instead of one per node-source pair); a factor is zero beyond
+// the window half width along its axis (square window: the corners it adds to the radial one are < 6e-15 of the peak).
+#define EW_SCHUNK 64
+__device__ __forceinline__ void ewald_window_factors(const double* shx, const double* shy, int cnt, double tx0, double ty0,
+                                                     double h, double rw2, double two_xi2, double (*shex)[EW_TILE],
+                                                     double (*shey)[EW_TILE], int tid) {
+    for (int idx = tid; idx < cnt * 2 * EW_TILE; idx += EW_TILE * EW_TILE) {
+        const int s = idx / (2 * EW_TILE), r = idx % (2 * EW_TILE);
+        if (r < EW_TILE) {
+            const double d = tx0 + r * h - shx[s];
+            shex[s][r] = (d * d < rw2) ? exp(-two_xi2 * d * d) : 0.0;
+        } else {
+            const double d = ty0 + (r - EW_TILE) * h - shy[s];
+            shey[s][r - EW_TILE] = (d * d < rw2) ? exp(-two_xi2 * d * d) : 0.0;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(EW_TILE* EW_TILE)
 k_ewald_tiles(const int* __restrict__ tile_ix, const int* __restrict__ tile_iy, const int* __restrict__ tile_ptr,
@@ -90,7 +109,8 @@ k_ewald_tiles(const int* __restrict__ tile_ix, const int* __restrict__ tile_iy, 
               const double* __restrict__ q, EwaldTab T, double x0, double y0, double h, double rc2, double rw2,
               double two_xi2, double norm, int px, int py, double* __restrict__ Sw, double* __restrict__ Lc,
               const unsigned* __restrict__ tile_mask, int want_local) {
-    __shared__ double shx[EW_CHUNK], shy[EW_CHUNK], shq[EW_CHUNK];
+    __shared__ double shx[EW_SCHUNK], shy[EW_SCHUNK], shq[EW_SCHUNK];
+    __shared__ double shex[EW_SCHUNK][EW_TILE], shey[EW_SCHUNK][EW_TILE];
     __shared__ double sS[EW_MAX_TAB], sA[EW_MAX_TAB];
     const int tid = threadIdx.y * EW_TILE + threadIdx.x;
     const int ntab = T.nint * T.ndeg;
@@ -103,20 +123,25 @@ k_ewald_tiles(const int* __restrict__ tile_ix, const int* __restrict__ tile_iy, 
     double spread = 0.0, loc = 0.0;
     // the local sum is only needed at nodes that are grid targets
     if (want_local && tile_mask) want_local = (tile_mask[t * 8 + (tid >> 5)] >> (tid & 31)) & 1u;
-    for (int base = s0; base < s1; base += EW_CHUNK) {
-        const int cnt = min(EW_CHUNK, s1 - base);
+    for (int base = s0; base < s1; base += EW_SCHUNK) {
+        const int cnt = min(EW_SCHUNK, s1 - base);
         __syncthreads();
         if (tid < cnt) {
             const int s = tile_src[base + tid];
             shx[tid] = sx[s]; shy[tid] = sy[s]; shq[tid] = q[s];
         }
         __syncthreads();
+        ewald_window_factors(shx, shy, cnt, x0 + tile_ix[t] * EW_TILE * h, y0 + tile_iy[t] * EW_TILE * h, h, rw2, two_xi2,
+                             shex, shey, tid);
+        __syncthreads();
         for (int i = 0; i < cnt; ++i) {
-            const double dx = x - shx[i], dy = y - shy[i];
-            const double d2 = dx * dx + dy * dy;
-            if (d2 < rw2) spread = fma(shq[i], exp(-two_xi2 * d2), spread);
-            if (want_local && d2 < rc2 && d2 > 0.0)
-                loc = fma(shq[i], ewald_gloc(d2, sS, sA, T.nint, T.ndeg, T.nlog, T.inv_dz), loc);
+            spread = fma(shq[i] * shex[i][threadIdx.y], shey[i][threadIdx.x], spread);
+            if (want_local) {
+                const double dx = x - shx[i], dy = y - shy[i];
+                const double d2 = dx * dx + dy * dy;
+                if (d2 < rc2 && d2 > 0.0)
+                    loc = fma(shq[i], ewald_gloc(d2, sS, sA, T.nint, T.ndeg, T.nlog, T.inv_dz), loc);
+            }
         }
     }
     if (ix < px && iy < py) Sw[(int64_t)ix * py + iy] = spread * norm;
@@ -459,7 +484,8 @@ k_ewald_tiles_grad(const int* __restrict__ tile_ix, const int* __restrict__ tile
                    const double* __restrict__ q, EwaldTabG T, double x0, double y0, double h, double rc2, double rw2,
                    double two_xi2, double norm, int px, int py, double* __restrict__ Sw, double* __restrict__ Lc,
                    double* __restrict__ Lcx, double* __restrict__ Lcy, const unsigned* __restrict__ tile_mask) {
-    __shared__ double shx[EW_CHUNK], shy[EW_CHUNK], shq[EW_CHUNK];
+    __shared__ double shx[EW_SCHUNK], shy[EW_SCHUNK], shq[EW_SCHUNK];
+    __shared__ double shex[EW_SCHUNK][EW_TILE], shey[EW_SCHUNK][EW_TILE];
     __shared__ double stab[4 * EW_MAX_TAB / 2];      // S, A, dS, dA (nint*ndeg <= 512 each)
     const int tid = threadIdx.y * EW_TILE + threadIdx.x;
     const int ntab = T.nint * T.ndeg;
@@ -473,24 +499,29 @@ k_ewald_tiles_grad(const int* __restrict__ tile_ix, const int* __restrict__ tile
     const int s0 = tile_ptr[t], s1 = tile_ptr[t + 1];
     const bool want_local = tile_mask ? ((tile_mask[t * 8 + (tid >> 5)] >> (tid & 31)) & 1u) : false;
     double spread = 0.0, loc = 0.0, lx = 0.0, ly = 0.0;
-    for (int base = s0; base < s1; base += EW_CHUNK) {
-        const int cnt = min(EW_CHUNK, s1 - base);
+    for (int base = s0; base < s1; base += EW_SCHUNK) {
+        const int cnt = min(EW_SCHUNK, s1 - base);
         __syncthreads();
         if (tid < cnt) {
             const int s = tile_src[base + tid];
             shx[tid] = sx[s]; shy[tid] = sy[s]; shq[tid] = q[s];
         }
         __syncthreads();
+        ewald_window_factors(shx, shy, cnt, x0 + tile_ix[t] * EW_TILE * h, y0 + tile_iy[t] * EW_TILE * h, h, rw2, two_xi2,
+                             shex, shey, tid);
+        __syncthreads();
         for (int i = 0; i < cnt; ++i) {
-            const double dx = x - shx[i], dy = y - shy[i];
-            const double d2 = dx * dx + dy * dy;
-            if (d2 < rw2) spread = fma(shq[i], exp(-two_xi2 * d2), spread);
-            if (want_local && d2 < rc2 && d2 > 0.0) {
-                double g, dg;
-                ewald_gloc_grad(d2, stab, T.nint, T.ndeg, T.nlog, T.inv_dz, &g, &dg);
-                loc = fma(shq[i], g, loc);
-                const double c = 2.0 * shq[i] * dg;
-                lx = fma(c, dx, lx); ly = fma(c, dy, ly);
+            spread = fma(shq[i] * shex[i][threadIdx.y], shey[i][threadIdx.x], spread);
+            if (want_local) {
+                const double dx = x - shx[i], dy = y - shy[i];
+                const double d2 = dx * dx + dy * dy;
+                if (d2 < rc2 && d2 > 0.0) {
+                    double g, dg;
+                    ewald_gloc_grad(d2, stab, T.nint, T.ndeg, T.nlog, T.inv_dz, &g, &dg);
+                    loc = fma(shq[i], g, loc);
+                    const double c = 2.0 * shq[i] * dg;
+                    lx = fma(c, dx, lx); ly = fma(c, dy, ly);
+                }
             }
         }
     }
