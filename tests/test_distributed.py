@@ -104,3 +104,47 @@ def test_slab_grid_solver_single_gpu(n):
         assert np.array_equal(pc.cpu().numpy(), Lc.pack_chunk(s, c*Pk, Pk))
         lib().ipde_slab_unpack_chunk(D.ptr(pc), Lc.rows, Lc.P, Lc.R, Lc.Pc, c*Pk, Pk, D.ptr(back), D.stream())
     assert np.array_equal(back.cpu().numpy(), s)
+
+
+def _assign_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from types import SimpleNamespace as NS
+        from ipde_b200.solvers.multi_boundary.scalar import ScalarSolver
+        from ipde_b200.solvers.multi_boundary.vector import VectorSolver
+        ebdyc = [NS(bdy=NS(N=n), M=m) for n, m in ((800, 16), (200, 16), (200, 16), (120, 12))]
+        out = []
+        for cls in (ScalarSolver, VectorSolver):
+            s = NS(ebdyc=ebdyc)
+            cls._assign_boundaries(s, True)
+            out.append((s.world, s.rank, tuple(s.owner)))
+            s2 = NS(ebdyc=ebdyc)
+            cls._assign_boundaries(s2, False)
+            out.append((s2.world, s2.rank, tuple(s2.owner)))
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_boundary_sharding_assignment_gloo():
+    """greedy cost-weighted assignment of boundaries to ranks: identical on every rank, the big interior
+    boundary alone on one rank; without sharding everything stays on the calling rank"""
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 1000) + 77
+    procs = [ctx.Process(target=_assign_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    for rank in range(world):
+        for k, (w, r, owner) in enumerate(res[rank]):
+            if k % 2 == 0:
+                assert (w, r) == (world, rank) and owner == (0, 1, 1, 1)
+            else:
+                assert (w, r) == (1, 0) and owner == (0, 0, 0, 0)
+    assert res[0][0][2] == res[1][0][2]
