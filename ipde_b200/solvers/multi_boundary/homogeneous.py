@@ -24,7 +24,7 @@ Both routes compute the unique solution of the homogeneous Dirichlet problem; th
 import numpy as np
 import scipy.sparse.linalg
 
-from ...device import to_dev, empty, gemv, layer_apply_scalar, FreeSpaceEvaluator
+from ...device import to_dev, empty, layer_apply_scalar, FreeSpaceEvaluator
 from ...embedded_function import EmbeddedFunction
 from ...qfs import Laplace_QFS, Modified_Helmholtz_QFS
 from ..internals.scalar import DeviceQFS

@@ -169,7 +169,6 @@ class VectorSolver(object):
         # per-boundary annular solves and effective sources
         nsrc = self.grid_sources.N
         sigmag = empty((2, nsrc))
-        import torch
         its = torch.zeros(len(self.helpers), dtype=torch.int64, device=sigmag.device)
         for b, helper in enumerate(self.helpers):
             if self.owner[b] != self.rank:
