@@ -1,5 +1,5 @@
 """Microbenchmark of the FFT kernels: 2-D real FFT pairs of a GridPlan and batched 1-D rows, GB/s of algorithmic
-traffic (each pass reads and writes its array once)."""
+traffic (each pass reads and writes its array once), with cuFFT (torch.fft) as a comparison line."""
 import sys, os
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
 import torch, numpy as np
@@ -32,6 +32,13 @@ for n in sizes:
     bytes_f = real_b + spec_b + npass_cols*2*spec_b
     print('n=%5d (cols %dx%d): fft2 r2c %.3f ms  %.0f GB/s | c2r %.3f ms %.0f GB/s' %
           (n, g.n1, g.n2, t_f, bytes_f/t_f/1e6, t_i, bytes_f/t_i/1e6), flush=True)
+    # comparison line only (north_star): cuFFT through torch.fft on the same arrays -- never used by the library
+    t_cf = timeit(lambda: torch.fft.rfft2(f))
+    sp = torch.fft.rfft2(f)
+    t_ci = timeit(lambda: torch.fft.irfft2(sp, s=(n, n)))
+    del sp
+    print('        cuFFT (torch.fft) rfft2 %.3f ms | irfft2 %.3f ms   -> ours/cuFFT %.2f / %.2f' %
+          (t_cf, t_ci, t_f/t_cf, t_i/t_ci), flush=True)
     # rows only: batched c2c of length n/2
     p = D.FFT1D(n//2)
     x = torch.randn(n, n//2, dtype=torch.complex128, device='cuda')
