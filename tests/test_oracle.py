@@ -130,3 +130,22 @@ def test_numpy_spectral_ewald_matches_direct_sum(kind, kappa, N):
     err_grid, err_off = ewald_against_direct_sum(N, kind, kappa)
     bound = 1e-12 if kappa >= 20.0 else 1e-13
     assert err_grid < bound and err_off < bound, (err_grid, err_off)
+
+
+def test_oracle_dirichlet_correction_poisson():
+    """the same for the Poisson path (examples/poisson_for_paper.py:88-105): log sources outside the domain"""
+    from problems import single_star, manufactured
+    from oracle.solvers import OracleScalarSolver
+    from oracle.homogeneous import OracleDirichletCorrection
+    from ipde_b200.qfs import Laplace_QFS
+    from ipde_b200.embedded_function import EmbeddedFunction, BoundaryFunction
+    ebdyc = single_star(nb=300, M=8, bump=True)
+    f, ua, sol = manufactured(ebdyc, 0.0, kk=np.pi/3)
+    e = ebdyc[0]
+    pair = (Laplace_QFS(e.interface, True, True, True, tol=1e-12, u2s=False, device_build=False),
+            Laplace_QFS(e.interface, False, True, True, tol=1e-12, device_build=False))
+    O = OracleScalarSolver(ebdyc, 'poisson', 0.0, 'spectral', [pair])
+    uo = EmbeddedFunction(ebdyc, linear_data=np.asarray(O(f, tol=1e-13, restart=60, maxiter=5)))
+    qb = Laplace_QFS(e.bdy, True, True, False, tol=1e-12, b2c=False, device_build=False)
+    u = OracleDirichletCorrection(ebdyc, 'poisson', 0.0, [qb])(uo, BoundaryFunction(ebdyc, function=sol))
+    assert np.abs(u - np.asarray(ua)).max() < 2e-7        # 2.6e-8 at this resolution
