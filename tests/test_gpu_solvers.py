@@ -374,4 +374,4 @@ def test_dirichlet_correction_poisson():
     bc = BoundaryFunction(ebdyc, function=sol)
     us = [np.asarray(DirichletCorrection(solver, evaluation=ev)(ue, bc)) for ev in ('direct', 'ewald')]
     assert np.abs(us[0] - np.asarray(ua)).max() < 2e-7
-    assert np.abs(us[0] - us[1]).max() < 1e-11
+    assert np.abs(us[0] - us[1]).max() < 1e-10
