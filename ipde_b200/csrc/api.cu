@@ -407,5 +407,15 @@ int ipde_scalar_jumps(const double* bv, const double* bx, const double* by, cons
                       const double* ur, const double* in_est, int M, int64_t n, double sign, double* tau, void* stream) {
     return scalar_jumps(bv, bx, by, nx, ny, ur, in_est, M, n, sign, tau, ST(stream));
 }
+int ipde_banded_apply_z(const double* xhat, int n_in, int64_t N, const double* band, const double* lowT, int n_out, int BH,
+                        int KL, int64_t Ks, double* yhat, int64_t M, void* stream) {
+    return banded_apply_z(CP(xhat), n_in, N, CP(band), CP(lowT), n_out, BH, KL, Ks, MP(yhat), M, ST(stream));
+}
+int ipde_real_to_complex(const double* x, double* z, int64_t n, void* stream) {
+    return real_to_complex(x, MP(z), n, ST(stream));
+}
+int ipde_complex_parts(const double* z, double* re, double* im, int64_t n, void* stream) {
+    return complex_parts(CP(z), re, im, n, ST(stream));
+}
 
 }  // extern "C"

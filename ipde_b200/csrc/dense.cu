@@ -282,3 +282,116 @@ int scalar_jumps(const double* bv, const double* bx, const double* by, const dou
     KERNEL_CHECK();
     return IPDE_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// Structured QFS apply (ipde_b200/qfs_structured.py; replaces the dense factors of the reference's qfs objects used
+// at ipde/solvers/internals/scalar.py:87-88,106 and internals/vector.py:124-125,150):
+//   out_hat_o[k] = sum_i ( sum_{|p|<=BH} band[o,i,p,k] in_i[k-p]  +  [|k|<=KL] sum_{|k'|<=KL} low[o,i,k,k'] in_i[k'] )
+// in_i[k'] = coefficient of exp(i k' t) of the i-th density (N-point FFT / N, Nyquist mode split evenly);
+// output modes |k| <= Ks are written into a length-M spectrum in FFT order (zero elsewhere); two real outputs share
+// one complex spectrum (out_{2q} + i out_{2q+1}), so a single inverse transform returns both.
+__device__ __forceinline__ cplx banded_in_mode(const cplx* __restrict__ xh, int64_t N, int64_t h, bool even, int64_t kp,
+                                               double invN) {
+    if (kp < -h || kp > h) return make_double2(0.0, 0.0);
+    const cplx v = xh[kp >= 0 ? kp : kp + N];
+    const double s = (even && (kp == h || kp == -h)) ? 0.5 * invN : invN;
+    return make_double2(v.x * s, v.y * s);
+}
+
+template <int PS>
+__global__ void __launch_bounds__(32 * PS)
+k_banded_apply(const cplx* __restrict__ xh, int n_in, int64_t N, const cplx* __restrict__ band,
+               const cplx* __restrict__ lowT, int n_out, int BH, int KL, int64_t Ks, cplx* __restrict__ yh, int64_t M) {
+    __shared__ double red[PS][32][4];
+    const int lane = threadIdx.x, ps = threadIdx.y;
+    const int64_t m = blockIdx.x * 32LL + lane;
+    const int o0 = 2 * blockIdx.y, o1 = o0 + 1;
+    const bool two = o1 < n_out;
+    const int64_t k = (m < (M + 1) / 2) ? m : m - M;
+    const bool live = (m < M) && (k >= -Ks) && (k <= Ks);
+    const int64_t nk = 2 * Ks + 1, ks = k + Ks;
+    const int64_t h = N / 2;
+    const bool even = (N % 2) == 0;
+    const int64_t hh = even ? h : (N - 1) / 2;
+    const double invN = 1.0 / (double)N;
+    const int nb = 2 * BH + 1, nl = 2 * KL + 1;
+    cplx a0 = make_double2(0.0, 0.0), a1 = a0;
+    if (live) {
+        for (int i = 0; i < n_in; ++i) {
+            const cplx* x = xh + (int64_t)i * N;
+            const cplx* b0 = band + ((int64_t)(o0 * n_in + i) * nb) * nk + ks;
+            const cplx* b1 = band + ((int64_t)((two ? o1 : o0) * n_in + i) * nb) * nk + ks;
+            for (int p = -BH + ps; p <= BH; p += PS) {
+                const cplx v = banded_in_mode(x, N, hh, even, k - p, invN);
+                const cplx c0 = b0[(int64_t)(p + BH) * nk];
+                a0.x = fma(c0.x, v.x, fma(-c0.y, v.y, a0.x));
+                a0.y = fma(c0.x, v.y, fma(c0.y, v.x, a0.y));
+                if (two) {
+                    const cplx c1 = b1[(int64_t)(p + BH) * nk];
+                    a1.x = fma(c1.x, v.x, fma(-c1.y, v.y, a1.x));
+                    a1.y = fma(c1.x, v.y, fma(c1.y, v.x, a1.y));
+                }
+            }
+            if (k >= -KL && k <= KL) {
+                const cplx* l0 = lowT + ((int64_t)(o0 * n_in + i) * nl) * nl + (k + KL);
+                const cplx* l1 = lowT + ((int64_t)((two ? o1 : o0) * n_in + i) * nl) * nl + (k + KL);
+                for (int kp = -KL + ps; kp <= KL; kp += PS) {
+                    const cplx v = banded_in_mode(x, N, hh, even, kp, invN);
+                    const cplx c0 = l0[(int64_t)(kp + KL) * nl];
+                    a0.x = fma(c0.x, v.x, fma(-c0.y, v.y, a0.x));
+                    a0.y = fma(c0.x, v.y, fma(c0.y, v.x, a0.y));
+                    if (two) {
+                        const cplx c1 = l1[(int64_t)(kp + KL) * nl];
+                        a1.x = fma(c1.x, v.x, fma(-c1.y, v.y, a1.x));
+                        a1.y = fma(c1.x, v.y, fma(c1.y, v.x, a1.y));
+                    }
+                }
+            }
+        }
+    }
+    red[ps][lane][0] = a0.x; red[ps][lane][1] = a0.y; red[ps][lane][2] = a1.x; red[ps][lane][3] = a1.y;
+    __syncthreads();
+    if (ps == 0 && m < M) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int q = 0; q < PS; ++q) { s0 += red[q][lane][0]; s1 += red[q][lane][1]; s2 += red[q][lane][2]; s3 += red[q][lane][3]; }
+        // (s0 + i s1) + i (s2 + i s3)
+        yh[(int64_t)blockIdx.y * M + m] = make_double2(s0 - s3, s1 + s2);
+    }
+}
+
+int banded_apply_z(const cplx* xh, int n_in, int64_t N, const cplx* band, const cplx* lowT, int n_out, int BH, int KL,
+                   int64_t Ks, cplx* yh, int64_t M, cudaStream_t st) {
+    ARG_CHECK(n_in >= 1 && n_out >= 1 && N >= 2 && M >= 2 * Ks + 1 && BH >= 0 && KL >= 0 && KL <= Ks, "banded_apply_z sizes");
+    constexpr int PS = 8;
+    dim3 grid((unsigned)cdiv(M, 32), (unsigned)((n_out + 1) / 2));
+    KERNEL_TAG("k_banded_apply", 16.0 * ((double)n_out * n_in * ((2.0 * BH + 1) * (2.0 * Ks + 1) + (2.0 * KL + 1) * (2.0 * KL + 1))));
+    k_banded_apply<PS><<<grid, dim3(32, PS), 0, st>>>(xh, n_in, N, band, lowT, n_out, BH, KL, Ks, yh, M);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+
+__global__ void k_real_to_complex(const double* __restrict__ x, cplx* __restrict__ z, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        z[i] = make_double2(x[i], 0.0);
+}
+int real_to_complex(const double* x, cplx* z, int64_t n, cudaStream_t st) {
+    if (n <= 0) return IPDE_OK;
+    k_real_to_complex<<<vblocks(n), 256, 0, st>>>(x, z, n);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+// re[i] = Re z[i] (* wr[i]), im[i] = Im z[i] (* wi[i]); im / weights may be null
+__global__ void k_complex_parts(const cplx* __restrict__ z, double* __restrict__ re, double* __restrict__ im, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const cplx v = z[i];
+        re[i] = v.x;
+        if (im) im[i] = v.y;
+    }
+}
+int complex_parts(const cplx* z, double* re, double* im, int64_t n, cudaStream_t st) {
+    if (n <= 0) return IPDE_OK;
+    k_complex_parts<<<vblocks(n), 256, 0, st>>>(z, re, im, n);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}

@@ -395,22 +395,50 @@ def _svd(E):
     return scipy.linalg.svd(E)
 
 
-class Laplace_QFS(QFS):
-    def __init__(self, bdy, interior, slp, dlp, options=None, **kw):
-        kw.update(options or {})
-        super().__init__(bdy, interior, slp, dlp, LaplaceKernel(), **kw)
+# boundaries with at least this many nodes get the structured (Fourier-banded) operators of qfs_structured.py;
+# IPDE_QFS=dense / IPDE_QFS=structured overrides, as does the `structured=` keyword
+STRUCTURED_MIN_N = 1024
+STRUCTURED_STOKES = True
 
 
-class Modified_Helmholtz_QFS(QFS):
-    def __init__(self, bdy, interior, slp, dlp, k, options=None, closer_source=True, **kw):
-        kw.update(options or {})
-        super().__init__(bdy, interior, slp, dlp, ModifiedHelmholtzKernel(k), **kw)
+def _make_qfs(kernel, bdy, interior, slp, dlp, options=None, structured=None, **kw):
+    """
+    Factory behind the reference's constructor names (qfs.Laplace_QFS(bdy, interior, slp, dlp, options), ...):
+    dense SVD-factored operators for small boundaries (and whenever `device_build` is given explicitly), structured
+    O(n log n) operators for large ones.  Both expose `source`, `__call__([slp, dlp])`, `u2s(ub)`, `N`, `M`.
+    """
+    import os
+    kw.update(options or {})
+    explicit = structured is not None
+    if structured is None:
+        env = os.environ.get('IPDE_QFS', '')
+        if env == 'structured':
+            structured = True
+        elif env == 'dense' or 'device_build' in kw:
+            structured = False
+        else:
+            structured = bdy.N >= STRUCTURED_MIN_N and (kernel.ncomp == 1 or STRUCTURED_STOKES)
+    if structured:
+        from .qfs_structured import StructuredQFS, NotResolved
+        skw = {k: v for k, v in kw.items() if k != 'device_build'}
+        try:
+            return StructuredQFS(bdy, interior, slp, dlp, kernel, **skw)
+        except NotResolved:
+            if explicit:
+                raise
+    return QFS(bdy, interior, slp, dlp, kernel, **kw)
 
 
-class Stokes_QFS(QFS):
-    def __init__(self, bdy, interior, slp, dlp, options=None, **kw):
-        kw.update(options or {})
-        super().__init__(bdy, interior, slp, dlp, StokesKernel(), **kw)
+def Laplace_QFS(bdy, interior, slp, dlp, options=None, **kw):
+    return _make_qfs(LaplaceKernel(), bdy, interior, slp, dlp, options, **kw)
+
+
+def Modified_Helmholtz_QFS(bdy, interior, slp, dlp, k, options=None, closer_source=True, **kw):
+    return _make_qfs(ModifiedHelmholtzKernel(k), bdy, interior, slp, dlp, options, **kw)
+
+
+def Stokes_QFS(bdy, interior, slp, dlp, options=None, **kw):
+    return _make_qfs(StokesKernel(), bdy, interior, slp, dlp, options, **kw)
 
 
 # ---------------------------------------------------------------------------

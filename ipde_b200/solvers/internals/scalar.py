@@ -50,6 +50,70 @@ class DeviceQFS(object):
         return self._two_step(self.Ab, self.Sinv_b, self.Vb, ub)
 
 
+class DeviceStructuredOperator(object):
+    """densities (n_in, N) -> charges (n_out, M): FFT, banded + low-block mat-vec in Fourier space, inverse FFT
+    (ipde_b200/qfs_structured.py; kernels k_banded_apply etc. in csrc/dense.cu)"""
+    _ffts = {}
+
+    def __init__(self, op):
+        self.op = op
+        self.N, self.M, self.n_in, self.n_out = op.N, op.M, op.n_in, op.n_out
+        self.band = to_dev(op.band)
+        self.lowT = to_dev(np.ascontiguousarray(op.low.transpose(0, 1, 3, 2)))
+        self.npair = (op.n_out + 1)//2
+        self._zin = empty((op.n_in, op.N), torch.complex128)
+        self._xh = empty((op.n_in, op.N), torch.complex128)
+        self._yh = empty((self.npair, op.M), torch.complex128)
+        self._yz = empty((self.npair, op.M), torch.complex128)
+
+    @classmethod
+    def fft(cls, n):
+        from ...device import FFT1D
+        if n not in cls._ffts:
+            cls._ffts[n] = FFT1D(n)
+        return cls._ffts[n]
+
+    def __call__(self, x, out=None):
+        L, st, op = lib(), stream(), self.op
+        if out is None:
+            out = empty((op.n_out*op.M,))
+        L.ipde_real_to_complex(ptr(x), ptr(self._zin), op.n_in*op.N, st)
+        self.fft(op.N).c2c(self._zin, -1, 1.0, out=self._xh)
+        L.ipde_banded_apply_z(ptr(self._xh), op.n_in, op.N, ptr(self.band), ptr(self.lowT), op.n_out, op.BH, op.KL, op.Ks,
+                              ptr(self._yh), op.M, st)
+        self.fft(op.M).c2c(self._yh, +1, 1.0, out=self._yz)
+        o = out.view(op.n_out, op.M)
+        for q in range(self.npair):
+            im = o[2*q + 1] if 2*q + 1 < op.n_out else None
+            L.ipde_complex_parts(ptr(self._yz[q]), ptr(o[2*q]), ptr(im), op.M, st)
+        return out
+
+
+class DeviceStructuredQFS(object):
+    """device side of ipde_b200.qfs_structured.StructuredQFS; same surface as DeviceQFS"""
+    def __init__(self, qfs):
+        self.qfs = qfs
+        self.M, self.N = qfs.M, qfs.N
+        self.op = DeviceStructuredOperator(qfs.op) if qfs.op is not None else None
+        self.op_u2s = DeviceStructuredOperator(qfs.op_u2s) if qfs.op_u2s is not None else None
+        self.sx = to_dev(qfs.source.x)
+        self.sy = to_dev(qfs.source.y)
+        self.sw = to_dev(qfs.source.weights)
+        self.nsrc = qfs.source.N
+
+    def __call__(self, tau):
+        return self.op(tau)
+
+    def u2s(self, ub):
+        if self.op_u2s is None:
+            raise Exception('QFS object built without u2s operators')
+        return self.op_u2s(ub)
+
+
+def device_qfs(qfs):
+    return DeviceStructuredQFS(qfs) if getattr(qfs, 'structured', False) else DeviceQFS(qfs)
+
+
 class ScalarHelper(object):
     kernel_kind = None       # 0 Laplace, 1 modified Helmholtz (csrc/layer.cu)
     k = 0.0
@@ -99,8 +163,8 @@ class ScalarHelper(object):
     def _to_device(self):
         e = self.ebdy
         self.d_in_estimator = to_dev(self._in_estimator)
-        self.d_qfs_g = DeviceQFS(self.interface_qfs_g)
-        self.d_qfs_r = DeviceQFS(self.interface_qfs_r)
+        self.d_qfs_g = device_qfs(self.interface_qfs_g)
+        self.d_qfs_r = device_qfs(self.interface_qfs_r)
         self.d_inx = to_dev(e.interface.normal_x)
         self.d_iny = to_dev(e.interface.normal_y)
         self.d_ix = to_dev(e.interface.x)

@@ -12,7 +12,7 @@ import torch
 from ..._lib import lib
 from ...annular import ApproximateAnnularGeometry, RealAnnularGeometry
 from ...device import to_dev, empty, ptr, stream, gemv, layer_apply_stokes, FFT1D
-from .scalar import DeviceQFS
+from .scalar import DeviceQFS, device_qfs
 
 
 def v2f(x):
@@ -62,8 +62,8 @@ class VectorHelper(object):
     def _to_device(self):
         e = self.ebdy
         n, M = e.bdy.N, e.M
-        self.d_qfs_g = DeviceQFS(self.interface_qfs_g)
-        self.d_qfs_r = DeviceQFS(self.interface_qfs_r)
+        self.d_qfs_g = device_qfs(self.interface_qfs_g)
+        self.d_qfs_r = device_qfs(self.interface_qfs_r)
         d = lambda a: to_dev(np.ascontiguousarray(a, dtype=float))
         self.d_bnx, self.d_bny = d(e.bdy.normal_x), d(e.bdy.normal_y)
         self.d_btx, self.d_bty = d(e.bdy.tangent_x), d(e.bdy.tangent_y)

@@ -27,7 +27,7 @@ import scipy.sparse.linalg
 from ...device import to_dev, empty, layer_apply_scalar, FreeSpaceEvaluator
 from ...embedded_function import EmbeddedFunction
 from ...qfs import Laplace_QFS, Modified_Helmholtz_QFS
-from ..internals.scalar import DeviceQFS
+from ..internals.scalar import DeviceQFS, device_qfs
 
 
 class DirichletCorrection(object):
@@ -49,7 +49,7 @@ class DirichletCorrection(object):
             else:
                 q = Modified_Helmholtz_QFS(ebdy.bdy, ebdy.interior, True, False, self.k, tol=tol, b2c=False)
             self.qfs.append(q)
-            self.dqfs.append(DeviceQFS(q))
+            self.dqfs.append(device_qfs(q))
         self.nb = [ebdy.bdy.N for ebdy in e]
         self.boff = np.concatenate([[0], np.cumsum(self.nb)])
         self.d_bx = [to_dev(ebdy.bdy.x) for ebdy in e]

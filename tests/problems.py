@@ -96,3 +96,30 @@ def four_bodies(nb=100, M=8, bump=False):
     if bump:
         ebdyc.ready_bump(MOL.bump)
     return ebdyc
+
+
+def four_bodies_box(N, M=20, nb_outer=None, nb_small=None, bump=False, three=False):
+    """
+    BASELINE configs[2] / [4] at full scale: the geometry of examples/multi_modified_helmholtz.py:34-36 on its own box
+    [-3.5, 3.5]^2 (interior star r = 3, a = 0.05, f = 7; exterior squished circle at (-1.2, -0.7); exterior star
+    a = 0.2, f = 3 at (1, 0.5)) plus the 4th exterior body declared in SURVEY.md 8(d).3 (star x = -0.5, y = 1.5,
+    r = 0.6, a = 0.15, f = 4) on an N x N grid.  Boundary node counts default to 3N (outer) and 3N/4 (bodies), i.e.
+    node spacing ~ grid spacing, with FFT-friendly lengths; the radial width is M grid cells.
+    """
+    L = 3.5
+    grid = Grid([-L, L], N, [-L, L], N)
+    h = grid.xh
+    n1 = 3*N if nb_outer is None else nb_outer
+    n2 = (3*N)//4 if nb_small is None else nb_small
+    bdy1 = GSB(c=star(n1, r=3.0, a=0.05, f=7))
+    bdy2 = GSB(c=squished_circle(n2, x=-1.2, y=-0.7, r=1.0, b=0.6, rot=-np.pi/4))
+    bdy3 = GSB(c=star(n2, x=1.0, y=0.5, r=1.0, a=0.2, f=3))
+    bdy4 = GSB(c=star(max(n2*6//10, 16)//4*4, x=-0.5, y=1.5, r=0.6, a=0.15, f=4))
+    bdys = [bdy1, bdy2, bdy3] if three else [bdy1, bdy2, bdy3, bdy4]
+    MOL = SlepianMollifier(2*M)
+    ebdys = [EmbeddedBoundary(b, b is bdy1, M, h, heaviside=MOL.step) for b in bdys]
+    ebdyc = EmbeddedBoundaryCollection(ebdys)
+    ebdyc.register_grid(grid)
+    if bump:
+        ebdyc.ready_bump(MOL.bump, (L - ebdys[0].radial_width, L - ebdys[0].radial_width), ebdys[0].radial_width)
+    return ebdyc

@@ -426,3 +426,40 @@ def test_stokes_free_space_evaluator_matches_direct_sum(D):
     for k, name in enumerate(('u', 'v', 'p')):
         err = np.abs(got[k] - ref[k]).max()/np.abs(ref[k]).max()
         assert err < 5e-11, (name, err)
+
+
+@pytest.mark.parametrize('kind', ['laplace', 'modified_helmholtz'])
+@pytest.mark.parametrize('n', [1200, 4096])
+def test_structured_qfs_device_apply(D, kind, n):
+    """k_banded_apply + FFTs (DeviceStructuredQFS) against the NumPy statement of the same operator, and the
+    potential of the device-computed sources against Green's formula half a node spacing from the curve."""
+    import torch
+    from ipde_b200.geometry import GSB, star
+    from ipde_b200 import qfs as Q
+    from ipde_b200.solvers.internals.scalar import device_qfs
+    from test_host import _green_case
+    k = 3.0 if kind == 'modified_helmholtz' else 0.0
+    bdy = GSB(c=star(n, a=0.15, f=5))
+    mk = (lambda i: Q.Laplace_QFS(bdy, i, True, True, tol=1e-13, structured=True)) if k == 0 else \
+         (lambda i: Q.Modified_Helmholtz_QFS(bdy, i, True, True, k, tol=1e-13, structured=True))
+    for interior in (True, False):
+        q = mk(interior)
+        dq = device_qfs(q)
+        rng = np.random.default_rng(5)
+        t = bdy.t
+        tau = np.concatenate([np.exp(np.cos(t))*np.sin(2*t) + 1e-6*rng.standard_normal(n), np.cos(3*t + 0.3)])
+        sd = dq(D.to_dev(tau)).cpu().numpy()
+        sh = q([tau[:n], tau[n:]])
+        assert rel(sd, sh) < 1e-12
+        ub = np.exp(np.sin(t))
+        assert rel(dq.u2s(D.to_dev(ub)).cpu().numpy(), q.u2s(ub)) < 1e-12
+
+        class OnDevice(object):          # the same Green-identity check, sources computed by the device apply
+            kernel, source = q.kernel, q.source
+            def __call__(self, taus):
+                return dq(D.to_dev(np.concatenate(taus))).cpu().numpy()
+            def u2s(self, u):
+                return dq.u2s(D.to_dev(u)).cpu().numpy()
+        val, val2, ex = _green_case(bdy, interior, k, OnDevice(), 0.5)
+        assert np.abs(val - ex).max() < 1e-12*max(1.0, np.abs(ex).max())
+        assert np.abs(val2 - ex).max() < 1e-12*max(1.0, np.abs(ex).max())

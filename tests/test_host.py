@@ -114,3 +114,76 @@ def test_annulus_points_outside_the_physical_mask_are_flagged():
     assert np.unique(slots).size == slots.size and np.all(eb.ia_inds[~eb.ia_is_phys] == 0)
     g = three_bodies(nb=200, M=12).grid
     assert lib().ipde_fft_size_supported(g.Nx) and lib().ipde_fft_size_supported(g.Ny//2)
+
+
+def _green_case(bdy, interior, k, q, dist):
+    """densities of a known PDE solution on the curve -> sources; returns (potential of the sources, exact) on a
+    test curve `dist` node spacings into the evaluation side, and the same for u2s"""
+    import scipy.special as ss
+    tt = np.linspace(0, 2*np.pi, 333, endpoint=False)
+    N = bdy.N
+    E = np.exp(1j*np.outer(tt, np.fft.fftfreq(N, 1.0/N)))
+    ch = np.fft.fft(bdy.c)/N
+    Z = E.dot(ch)
+    Zp = E.dot(ch*1j*np.fft.fftfreq(N, 1.0/N))
+    z = Z + (-1j*Zp/np.abs(Zp))*(-dist*bdy.dt*np.abs(Zp) if interior else dist*bdy.dt*np.abs(Zp))
+    if interior:
+        u = (lambda x, y: np.exp(k*(0.6*x + 0.8*y))/10) if k > 0 else (lambda x, y: np.exp(0.6*x)*np.cos(0.6*y))
+        eps = 1e-6
+        ub = u(bdy.x, bdy.y)
+        if k > 0:
+            un = k*ub*(0.6*bdy.normal_x + 0.8*bdy.normal_y)
+        else:
+            un = 0.6*np.exp(0.6*bdy.x)*(np.cos(0.6*bdy.y)*bdy.normal_x - np.sin(0.6*bdy.y)*bdy.normal_y)
+        sig = q([un, -ub])
+        ex = u(z.real, z.imag)
+    else:
+        x0, y0 = 0.1, 0.2
+        dx, dy = bdy.x - x0, bdy.y - y0
+        r = np.hypot(dx, dy)
+        if k > 0:
+            ub = ss.k0(k*r)/(2*np.pi)
+            un = -k*ss.k1(k*r)/(2*np.pi)*(dx*bdy.normal_x + dy*bdy.normal_y)/r
+            ex = ss.k0(k*np.hypot(z.real - x0, z.imag - y0))/(2*np.pi)
+        else:
+            ub = dx/r**2
+            un = (1/r**2 - 2*dx*dx/r**4)*bdy.normal_x + (-2*dx*dy/r**4)*bdy.normal_y
+            ex = (z.real - x0)/((z.real - x0)**2 + (z.imag - y0)**2)
+        sig = q([-un, ub])
+    val = Q.layer_apply_matrix_free(q.kernel, q.source, z.real, z.imag, sig)
+    val2 = Q.layer_apply_matrix_free(q.kernel, q.source, z.real, z.imag, q.u2s(ub))
+    return val, val2, ex
+
+
+@pytest.mark.parametrize('interior', [True, False])
+@pytest.mark.parametrize('k', [0.0, 3.0])
+def test_structured_qfs_green_identity(interior, k):
+    """Structured (Fourier-banded) QFS: Green's representation formula half a node spacing away from the curve and
+    the u2s map, at 1e-12 (the reference's qfs objects are absent; this identity is what pins the restatement)."""
+    from ipde_b200.qfs_structured import StructuredQFS
+    bdy = GSB(c=star(1200, a=0.15, f=5))
+    ker = Q.ModifiedHelmholtzKernel(k) if k > 0 else Q.LaplaceKernel()
+    q = StructuredQFS(bdy, interior, True, True, ker, tol=1e-13, device='cpu')
+    assert q.op.BH < 400 and q.source.N == q.M
+    val, val2, ex = _green_case(bdy, interior, k, q, 0.5)
+    assert np.abs(val - ex).max() < 1e-12*max(1.0, np.abs(ex).max())
+    assert np.abs(val2 - ex).max() < 1e-12*max(1.0, np.abs(ex).max())
+
+
+def test_structured_qfs_matches_dense_qfs():
+    """same densities through the dense SVD-factored operators and through the structured ones: the potentials on
+    the evaluation side agree to 1e-12 (the source curves differ, the represented field does not)"""
+    from ipde_b200.qfs_structured import StructuredQFS
+    bdy = GSB(c=star(600, a=0.1, f=3))
+    k = 2.0
+    ker = Q.ModifiedHelmholtzKernel(k)
+    qs = StructuredQFS(bdy, True, True, True, ker, tol=1e-13, device='cpu')
+    qd = Q.QFS(bdy, True, True, True, ker, tol=1e-13, device_build=False)
+    t = bdy.t
+    tau = [np.exp(np.cos(t))*np.sin(2*t), np.cos(3*t + 0.3)]
+    th = np.linspace(0, 2*np.pi, 200, endpoint=False)
+    for fac in (0.3, 0.9, 0.995):
+        z = (1 + 0.1*np.cos(3*th))*np.exp(1j*th)*fac
+        vs = Q.layer_apply_matrix_free(ker, qs.source, z.real, z.imag, qs(tau))
+        vd = Q.layer_apply_matrix_free(ker, qd.source, z.real, z.imag, qd(tau))
+        assert np.abs(vs - vd).max() < 1e-12
