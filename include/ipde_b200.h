@@ -247,6 +247,10 @@ int ipde_banded_apply_z(const double* xhat, int n_in, int64_t N, const double* b
                         int KL, int64_t Ks, double* yhat, int64_t M, void* stream);
 int ipde_real_to_complex(const double* x, double* z, int64_t n, void* stream);
 int ipde_complex_parts(const double* z, double* re, double* im, int64_t n, void* stream);
+/* re[j] (+)= Re z[j*stride], im[j] (+)= Im z[j*stride] (im may be null): sampling of the curve operators' output,
+ * Layer_Apply(source -> interface / radial targets) of ipde/solvers/internals/scalar.py:101,113 */
+int ipde_complex_parts_strided(const double* z, double* re, double* im, int64_t n, int64_t stride, int accumulate,
+                               void* stream);
 
 #ifdef __cplusplus
 }

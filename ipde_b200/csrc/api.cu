@@ -417,5 +417,9 @@ int ipde_real_to_complex(const double* x, double* z, int64_t n, void* stream) {
 int ipde_complex_parts(const double* z, double* re, double* im, int64_t n, void* stream) {
     return complex_parts(CP(z), re, im, n, ST(stream));
 }
+int ipde_complex_parts_strided(const double* z, double* re, double* im, int64_t n, int64_t stride, int accumulate,
+                               void* stream) {
+    return complex_parts_strided(CP(z), re, im, n, stride, accumulate, ST(stream));
+}
 
 }  // extern "C"

@@ -395,3 +395,19 @@ int complex_parts(const cplx* z, double* re, double* im, int64_t n, cudaStream_t
     KERNEL_CHECK();
     return IPDE_OK;
 }
+// re[j] (+)= Re z[j*stride], im[j] (+)= Im z[j*stride]  (curve operators: the field is transformed back on the
+// source grid of M = stride*N points and every stride-th sample is a target node)
+__global__ void k_complex_parts_strided(const cplx* __restrict__ z, double* __restrict__ re, double* __restrict__ im,
+                                        int64_t n, int64_t stride, int accumulate) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const cplx v = z[i * stride];
+        if (accumulate) { re[i] += v.x; if (im) im[i] += v.y; }
+        else { re[i] = v.x; if (im) im[i] = v.y; }
+    }
+}
+int complex_parts_strided(const cplx* z, double* re, double* im, int64_t n, int64_t stride, int accumulate, cudaStream_t st) {
+    if (n <= 0) return IPDE_OK;
+    k_complex_parts_strided<<<vblocks(n), 256, 0, st>>>(z, re, im, n, stride, accumulate);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}

@@ -16,3 +16,4 @@ int banded_apply_z(const cplx* xh, int n_in, int64_t N, const cplx* band, const 
                    int64_t Ks, cplx* yh, int64_t M, cudaStream_t st);
 int real_to_complex(const double* x, cplx* z, int64_t n, cudaStream_t st);
 int complex_parts(const cplx* z, double* re, double* im, int64_t n, cudaStream_t st);
+int complex_parts_strided(const cplx* z, double* re, double* im, int64_t n, int64_t stride, int accumulate, cudaStream_t st);

@@ -123,6 +123,12 @@ class _Stokes(object):
         xy = c*dx*dy/r2
         return [(0, 0, c*(L + dx*dx/r2)), (0, 1, xy), (1, 0, xy), (1, 1, c*(L + dy*dy/r2))]
 
+    def P(self, d):
+        """pressure of a point force: (1/2pi) d.f/r^2 (ipde/solvers/internals/stokes_save.py:29-38)"""
+        dx, dy = d.real, d.imag
+        r2 = dx*dx + dy*dy
+        return [(2, 0, dx/r2/TWO_PI), (2, 1, dy/r2/TWO_PI)]
+
     def dG(self, d, nrm):
         dx, dy = d.real, d.imag
         r2 = dx*dx + dy*dy
@@ -147,11 +153,12 @@ def _operator_band(ker, layer, tc, t_delta, n_t, sc, s_delta, n_d, J, Ks, chunk_
     """
     dev = tc.dev
     nc = ker.ncomp
+    n_o = nc + 1 if layer == 'cp' else nc               # 'cp': Stokes velocity + pressure of point forces
     kr = torch.arange(-Ks, Ks + 1, device=dev)
     s = TWO_PI*torch.arange(J, dtype=torch.float64, device=dev)/J
     S = sc.at(s, delta=s_delta)
     Sp = sc.at(s, delta=s_delta, deriv=1)
-    g1 = torch.empty((nc, nc, J, kr.numel()), dtype=torch.complex128, device=dev)
+    g1 = torch.zeros((n_o, nc, J, kr.numel()), dtype=torch.complex128, device=dev)
     rows = max(1, int(chunk_elems//n_d))
     w = TWO_PI/n_d
     for m0 in range(0, J, rows):
@@ -160,6 +167,8 @@ def _operator_band(ker, layer, tc, t_delta, n_t, sc, s_delta, n_d, J, Ks, chunk_
         d = T - S[m0:m1, None]
         if layer == 'c':
             terms = ker.G(d)
+        elif layer == 'cp':
+            terms = ker.G(d) + ker.P(d)
         elif layer == 's':
             terms = [(o, i, v*(Sp[m0:m1, None].abs()*w)) for o, i, v in ker.G(d)]
         else:
@@ -247,21 +256,21 @@ def _solve_windows(Eb, Cb_list, J, Ks, h_in, col_block, Bw, scale_r, scale_c, pi
     """
     X = E^-1 [C_1 | C_2 ...] column block by column block from windows of the banded system.
     Eb: band of E (nc, nc, J, 2Ks+1); Cb_list: bands of the right-hand sides (same layout) or None for the identity.
-    Input modes k' in [-h_in, h_in]; returns a list of dense-by-column arrays X_l (nc, 2Ks+1, nc, 2h_in+1) holding
-    only the rows inside each column's window (zero elsewhere).
+    Input modes k' in [-h_in, h_in].  Returns (Bx, [X_l]) with X_l (nc, nc, 2Bx+1, 2h_in+1) stored by column:
+    X_l[o, i, p + Bx, k' + h_in] = entry (output mode k' + p, input mode k'); zero outside the column's window.
     """
     dev = Eb.device
     nc = Eb.shape[0]
-    nk = 2*Ks + 1
     ncol = 2*h_in + 1
-    outs = [torch.zeros((nc, nk, nc, ncol), dtype=torch.complex128, device=dev) for _ in Cb_list]
+    Bx = Bw + col_block
+    outs = [torch.zeros((nc, nc, 2*Bx + 1, ncol), dtype=torch.complex128, device=dev) for _ in Cb_list]
     a = -h_in
     while a <= h_in:
         b = min(h_in + 1, a + col_block)
         lo, hi = max(-Ks, a - Bw), min(Ks, b - 1 + Bw)
         rows = torch.arange(lo, hi + 1, device=dev)
         cols = torch.arange(a, b, device=dev)
-        nr = rows.numel()
+        nr, ncb = rows.numel(), cols.numel()
         E = _dense_window(Eb, J, rows, rows)
         sr = scale_r(rows).repeat(nc)
         sc_ = scale_c(rows).repeat(nc)
@@ -269,11 +278,11 @@ def _solve_windows(Eb, Cb_list, J, Ks, h_in, col_block, Bw, scale_r, scale_c, pi
         rhs = []
         for Cb in Cb_list:
             if Cb is None:
-                C = torch.zeros((nc, nr, nc, cols.numel()), dtype=torch.complex128, device=dev)
+                C = torch.zeros((nc, nr, nc, ncb), dtype=torch.complex128, device=dev)
                 idx = (cols - lo)
                 for c in range(nc):
-                    C[c, idx, c, torch.arange(cols.numel(), device=dev)] = 1.0
-                C = C.reshape(nc*nr, nc*cols.numel())
+                    C[c, idx, c, torch.arange(ncb, device=dev)] = 1.0
+                C = C.reshape(nc*nr, nc*ncb)
             else:
                 C = _dense_window(Cb, J, rows, cols)
             rhs.append(C*sr[:, None])
@@ -285,65 +294,149 @@ def _solve_windows(Eb, Cb_list, J, Ks, h_in, col_block, Bw, scale_r, scale_c, pi
         else:
             Y = torch.linalg.solve(Es, R)
         Y = Y*sc_[:, None]
-        w = nc*cols.numel()
+        w = nc*ncb
+        pidx = rows[:, None] - cols[None, :] + Bx                       # (nr, ncb), in [0, 2Bx]
+        cidx = (cols + h_in)[None, :].expand(nr, ncb)
         for l, out in enumerate(outs):
-            out[:, lo + Ks:hi + Ks + 1, :, a + h_in:b + h_in] = Y[:, l*w:(l + 1)*w].reshape(nc, nr, nc, cols.numel())
+            Yl = Y[:, l*w:(l + 1)*w].reshape(nc, nr, nc, ncb)
+            for o in range(nc):
+                for i in range(nc):
+                    out[o, i][pidx, cidx] = Yl[o, :, i, :]
+        del E, Es, R, Y
         a = b
-    return outs
+    return Bx, outs
 
 
-def _significant(X, att, tol, far):
+def _significant(X, Bx, Ks, att, tol, far):
     """
-    X (nc, 2Ks+1, nc, 2h+1) by-column solution; att[k]: attenuation of source mode k on the way back to the curve.
-    An entry matters if its attenuated size exceeds tol * (largest attenuated entry of its column) and stands out of
-    the column's round-off floor.  The floor is measured |k - k'| >= far away from the diagonal (inside the solve
-    window, where the exact solution has decayed to nothing): the exponentially small high-mode entries of the
-    banded operators come out of an FFT with absolute, not relative, accuracy.
+    X by-column solution (nc, nc, 2Bx+1, ncol); att[k + Ks]: attenuation of source mode k on the way back to the
+    curve.  An entry matters if its attenuated size exceeds tol * (largest attenuated entry of its column) and stands
+    out of the column's round-off floor.  The floor is measured |k - k'| ~ far away from the diagonal, at the edge
+    of the operator bands, where the exact solution has decayed to nothing: the exponentially small high-mode
+    entries of the banded operators come out of an FFT with absolute, not relative, accuracy.
     """
     dev = X.device
-    Ks, h_in = (X.shape[1] - 1)//2, (X.shape[3] - 1)//2
-    mag = (X.abs()*att[None, :, None, None]).amax(dim=(0, 2))            # (nk, ncol)
-    k = torch.arange(-Ks, Ks + 1, device=dev)
+    ncol = X.shape[3]
+    h_in = (ncol - 1)//2
+    p = torch.arange(-Bx, Bx + 1, device=dev)
     kp = torch.arange(-h_in, h_in + 1, device=dev)
-    p = (k[:, None] - kp[None, :]).abs()
-    ring = (p >= far) & (p <= (4*far)//3)
-    floor = torch.where(ring, mag, torch.zeros_like(mag)).amax(dim=0, keepdim=True)
+    k = p[:, None] + kp[None, :]
+    ok = k.abs() <= Ks
+    a = torch.where(ok, att[(k.clamp(-Ks, Ks) + Ks)], torch.zeros((), dtype=att.dtype, device=dev))
+    mag = X.abs().amax(dim=(0, 1))*a                                     # (2Bx+1, ncol)
+    ring = (p.abs() >= far) & (p.abs() <= (4*far)//3)
+    floor = mag[ring].amax(dim=0, keepdim=True)
     return mag > torch.maximum(tol*mag.amax(dim=0, keepdim=True), 4.0*floor)
 
 
-def _choose(sig, Ks, h_in, KL_candidates):
+def _choose(sig, Bx, Ks, h_in, KL_candidates):
     """two-tier storage (dense low block |k|,|k'| <= KL, band half-width BH elsewhere) of least size"""
     dev = sig.device
-    k = torch.arange(-Ks, Ks + 1, device=dev)
+    p = torch.arange(-Bx, Bx + 1, device=dev)
     kp = torch.arange(-h_in, h_in + 1, device=dev)
-    p = (k[:, None] - kp[None, :]).abs()
+    k = p[:, None] + kp[None, :]
+    pa = p.abs()[:, None].expand_as(k)
     best = None
     for KL in KL_candidates:
-        KL = min(KL, h_in)
-        inlow = (k.abs()[:, None] <= KL) & (kp.abs()[None, :] <= KL)
+        KL = min(KL, h_in, Bx)
+        inlow = (k.abs() <= KL) & (kp.abs()[None, :] <= KL)
         rest = sig & ~inlow
-        BH = int(p[rest].max().item()) if bool(rest.any()) else 0
+        BH = int(pa[rest].max().item()) if bool(rest.any()) else 0
         cost = (2*KL + 1)**2 + (2*Ks + 1)*(2*BH + 1)
         if best is None or cost < best[0]:
             best = (cost, KL, BH)
-        if KL == h_in:
+        if KL == min(h_in, Bx):
             break
     return best[1], best[2]
 
 
-def _fill(X, Ks, h_in, KL, BH):
+def _fill(X, Bx, Ks, h_in, KL, BH):
+    """by-column solution -> (low (nc, nc, 2KL+1 [k], 2KL+1 [k']), band (nc, nc, 2BH+1 [p], 2Ks+1 [k]))"""
     dev = X.device
     nc = X.shape[0]
+    kl = torch.arange(-KL, KL + 1, device=dev)
+    pl = kl[:, None] - kl[None, :]                                       # (k, k')
+    inb = pl.abs() <= Bx
+    cl = (kl + h_in)[None, :].expand_as(pl)
+    low = (X[:, :, pl.clamp(-Bx, Bx) + Bx, cl]*inb[None, None]).contiguous()
     k = torch.arange(-Ks, Ks + 1, device=dev)
-    low = X[:, Ks - KL:Ks + KL + 1, :, h_in - KL:h_in + KL + 1].permute(0, 2, 1, 3).contiguous()
-    band = torch.zeros((nc, nc, 2*BH + 1, 2*Ks + 1), dtype=torch.complex128, device=dev)
-    for pp in range(-BH, BH + 1):
-        src_k = k - pp                                                  # input mode
-        ok = (src_k.abs() <= h_in) & ~((k.abs() <= KL) & (src_k.abs() <= KL))
-        rows = torch.nonzero(ok)[:, 0]
-        vals = X[:, rows, :, src_k[rows] + h_in]                        # (len, nc_out, nc_in)
-        band[:, :, pp + BH, rows] = vals.permute(1, 2, 0)
-    return low, band
+    pb = torch.arange(-BH, BH + 1, device=dev)
+    src_k = k[None, :] - pb[:, None]                                     # input mode, (2BH+1, nk)
+    ok = (src_k.abs() <= h_in) & ~((k.abs()[None, :] <= KL) & (src_k.abs() <= KL))
+    pi = (pb + Bx)[:, None].expand_as(src_k)
+    ci = src_k.clamp(-h_in, h_in) + h_in
+    band = X[:, :, pi, ci]*ok[None, None]
+    return low, band.contiguous()
+
+
+class CurveOperator(object):
+    """
+    charges on the source curve (n_in components, M sources) -> field on target curves (n_out rows of N nodes):
+    same two-tier Fourier-space storage as StructuredOperator; the field spectrum (modes |k| <= Ks) is transformed
+    back on the M-point grid and every rho-th sample is a target node.
+    """
+    def __init__(self, N, M, n_in, n_out, KL, BH, Ks, low, band):
+        self.N, self.M, self.n_in, self.n_out = N, M, n_in, n_out
+        self.KL, self.BH, self.Ks = KL, BH, Ks
+        self.low, self.band = low, band
+
+    def apply(self, q):
+        """NumPy statement of the device apply; q (n_in, M) charges -> (n_out, N) field values"""
+        M, KL, BH, Ks = self.M, self.KL, self.BH, self.Ks
+        qh = np.fft.fft(np.asarray(q, dtype=float).reshape(self.n_in, M), axis=1)/M
+        kk = np.arange(-Ks - BH, Ks + BH + 1)
+        ok = np.abs(kk) < M//2
+        xe = np.where(ok[None, :], qh[:, kk % M], 0.0)                       # index k' + Ks + BH
+        oh = np.zeros((self.n_out, 2*Ks + 1), dtype=complex)
+        for o in range(self.n_out):
+            for i in range(self.n_in):
+                for p in range(-BH, BH + 1):
+                    oh[o] += self.band[o, i, p + BH]*xe[i, BH - p:BH - p + 2*Ks + 1]
+                oh[o, Ks - KL:Ks + KL + 1] += self.low[o, i].dot(xe[i, Ks + BH - KL:Ks + BH + KL + 1])
+        buf = np.zeros((self.n_out, M), dtype=complex)
+        buf[:, np.arange(-Ks, Ks + 1) % M] = oh
+        return (np.fft.ifft(buf, axis=1)*M).real[:, ::M//self.N]
+
+
+def source_to_curves(qfs, curves, pressure=False, tol=2e-15, KLc=(32, 64, 128, 256, 512)):
+    """
+    Field of the point sources of a StructuredQFS object on curves given by N samples each (same parametrisation as
+    the QFS curve: its own nodes, the radial levels X(t_j) + r_i n(t_j) of the annulus): the operator of
+    ScalarHelper.correct / VectorHelper.correct (ipde/solvers/internals/scalar.py:101,113, vector.py:141,156) as a
+    Fourier-banded map, O(n) bytes per level instead of an all-pairs sum or a free-space evaluator per boundary.
+    Entries below tol * (largest entry) are at the round-off floor of the sampled bands and are dropped.
+    """
+    cv, dev = qfs._cv, qfs.dev
+    N, M, J, Ks_src = qfs.N, qfs.M, qfs.J, qfs.Ks
+    ker = qfs.ker
+    nc = ker.ncomp
+    Ks = min(Ks_src + J//2, M//2 - 1)
+    layer = 'cp' if (pressure and nc == 2) else 'c'
+    Bx = J//2 - 1
+    k_src = torch.arange(-Ks_src, Ks_src + 1, device=dev)
+    p = torch.arange(-Bx, Bx + 1, device=dev)
+    kk = p[:, None] + k_src[None, :]                                     # output mode of entry (p, k')
+    okk = kk.abs() <= Ks
+    def columns(c):
+        tc = _Curve(np.asarray(c), dev, cut=1e-15)
+        band, _ = _operator_band(ker, layer, tc, 0.0, N, cv, qfs.d_src, M, J, Ks)
+        # by-column layout X[o, i, p + Bx, k' + Ks_src] = band[o, i, p, k' + p]
+        return band[:, :, (p % J)[:, None].expand_as(kk), kk.clamp(-Ks, Ks) + Ks]*okk[None, None]
+    # pass 1: which entries matter (relative to the largest entry over all curves); pass 2: fill the two-tier storage
+    mags = [columns(c).abs().amax(dim=(0, 1)) for c in curves]
+    top = max(float(m.max()) for m in mags)
+    sig = mags[0] > tol*top
+    for m in mags[1:]:
+        sig |= m > tol*top
+    del mags
+    KL, BH = _choose(sig, Bx, Ks, Ks_src, list(KLc))
+    lows, bands = [], []
+    for c in curves:
+        lo_, ba_ = _fill(columns(c), Bx, Ks, Ks_src, KL, BH)
+        lows.append(lo_.cpu().numpy())
+        bands.append(ba_.cpu().numpy())
+    low, band = np.concatenate(lows, axis=0), np.concatenate(bands, axis=0)
+    return CurveOperator(N, M, nc, low.shape[0], KL, BH, Ks, low, band)
 
 
 class _Source(object):
@@ -442,6 +535,7 @@ class StructuredQFS(object):
         if tail > 1e-13 and Jc < 2*N:
             raise NotResolved('band not resolved (tail %.1e at J = %d)' % (tail, Jc))
         self.J, self.W = Jc, W
+        self._cv, self.Ks, self.h_in = cv, Ks, h_in
         KLc = [32, 64, 128, 256, 512, 1024, 2048]
         att = torch.exp(-self.alpha_s*dt*torch.arange(-Ks, Ks + 1, device=dev).abs().double())
         pinv_low = self.ker.ncomp == 2
@@ -465,15 +559,16 @@ class StructuredQFS(object):
             self.op_u2s = self._pack(Xs, Ks, h_in, att, KLc)
             del Xs, Ebb
 
-    def _pack(self, Xs, Ks, h_in, att, KLc):
+    def _pack(self, sol, Ks, h_in, att, KLc):
         """several by-column solutions (one per layer) -> one StructuredOperator with n_in = nlayers*ncomp"""
+        Bx, Xs = sol
         nc = self.ker.ncomp
         far = (3*self.W)//4
-        sig = _significant(Xs[0], att, 1e-15, far)
+        sig = _significant(Xs[0], Bx, Ks, att, 1e-15, far)
         for X in Xs[1:]:
-            sig |= _significant(X, att, 1e-15, far)
-        KL, BH = _choose(sig, Ks, h_in, KLc)
-        parts = [_fill(X, Ks, h_in, KL, BH) for X in Xs]
+            sig |= _significant(X, Bx, Ks, att, 1e-15, far)
+        KL, BH = _choose(sig, Bx, Ks, h_in, KLc)
+        parts = [_fill(X, Bx, Ks, h_in, KL, BH) for X in Xs]
         low = torch.cat([p[0] for p in parts], dim=1)
         band = torch.cat([p[1] for p in parts], dim=1)
         return StructuredOperator(self.N, self.M, nc*len(Xs), nc, KL, BH, Ks, low.cpu().numpy(), band.cpu().numpy())

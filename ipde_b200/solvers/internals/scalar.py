@@ -110,6 +110,39 @@ class DeviceStructuredQFS(object):
         return self.op_u2s(ub)
 
 
+class DeviceCurveOperator(object):
+    """
+    charges on a StructuredQFS source curve -> field on curves sampled at the boundary parameters (own interface,
+    radial levels): FFT of the charges, banded + low-block mat-vec (k_banded_apply), inverse FFTs on the source grid,
+    every rho-th sample kept.  Replaces the per-boundary sums of ScalarHelper.correct / VectorHelper.correct
+    (ipde/solvers/internals/scalar.py:101,113; vector.py:141,156) for boundaries with structured QFS operators.
+    """
+    def __init__(self, op):
+        self.op = op
+        self.band = to_dev(op.band)
+        self.lowT = to_dev(np.ascontiguousarray(op.low.transpose(0, 1, 3, 2)))
+        self.npair = (op.n_out + 1)//2
+        self._zin = empty((op.n_in, op.M), torch.complex128)
+        self._xh = empty((op.n_in, op.M), torch.complex128)
+        self._yh = empty((self.npair, op.M), torch.complex128)
+        self._yz = empty((self.npair, op.M), torch.complex128)
+
+    def __call__(self, q, out, accumulate=False):
+        """q: (n_in*M,) charges; out: (n_out, N) rows (any row-contiguous device views, given as a list or a tensor)"""
+        L, st, op = lib(), stream(), self.op
+        L.ipde_real_to_complex(ptr(q), ptr(self._zin), op.n_in*op.M, st)
+        DeviceStructuredOperator.fft(op.M).c2c(self._zin, -1, 1.0, out=self._xh)
+        L.ipde_banded_apply_z(ptr(self._xh), op.n_in, op.M, ptr(self.band), ptr(self.lowT), op.n_out, op.BH, op.KL, op.Ks,
+                              ptr(self._yh), op.M, st)
+        DeviceStructuredOperator.fft(op.M).c2c(self._yh, +1, 1.0, out=self._yz)
+        rho = op.M//op.N
+        for qp in range(self.npair):
+            re = out[2*qp]
+            im = out[2*qp + 1] if 2*qp + 1 < op.n_out else None
+            L.ipde_complex_parts_strided(ptr(self._yz[qp]), ptr(re), ptr(im), op.N, rho, 1 if accumulate else 0, st)
+        return out
+
+
 def device_qfs(qfs):
     return DeviceStructuredQFS(qfs) if getattr(qfs, 'structured', False) else DeviceQFS(qfs)
 
@@ -174,6 +207,12 @@ class ScalarHelper(object):
         n = e.bdy.N
         self._tau = empty((2*n,))
         self._w = empty((n,))
+        self.curve_w = self.curve_r = None
+        if getattr(self.interface_qfs_g, 'structured', False) and getattr(self.interface_qfs_r, 'structured', False):
+            from ...qfs_structured import source_to_curves
+            self.curve_w = DeviceCurveOperator(source_to_curves(self.interface_qfs_g, [e.interface.c]))
+            levels = [e.radial_x[i] + 1j*e.radial_y[i] for i in range(e.M)]
+            self.curve_r = DeviceCurveOperator(source_to_curves(self.interface_qfs_r, levels))
 
     def set_evaluation(self, mode, grid, single):
         """
@@ -188,7 +227,7 @@ class ScalarHelper(object):
         if not hasattr(self, 'evaluator_w'):
             self.evaluator_w = None
             self.evaluator_r = None
-        if mode == 'ewald' and self.evaluator_r is None:
+        if mode == 'ewald' and self.evaluator_r is None and self.curve_r is None:
             from ...device import FreeSpaceEvaluator
             e = self.ebdy
             g, r = self.interface_qfs_g.source, self.interface_qfs_r.source
@@ -237,6 +276,18 @@ class ScalarHelper(object):
         n = self.ebdy.bdy.N
         ewald = getattr(self, 'evaluation', 'direct') == 'ewald'
         qr = empty((r.nsrc,))
+        if self.curve_r is not None:
+            # structured QFS: own-source fields on the own interface and the radial levels as Fourier-banded maps
+            # (source weights are 1: the strengths are charges)
+            if ewald and self.single:
+                qr = self.sigma_r
+            else:
+                self.curve_w(self.sigma_g, [self._w])
+                lib().ipde_vec_axpby(1.0, ptr(ub), -1.0, ptr(self._w), ptr(self._w), n, stream())
+                sigma_r_adj = r.u2s(self._w)
+                lib().ipde_vec_axpby(1.0, ptr(sigma_r_adj), 1.0, ptr(self.sigma_r), ptr(qr), r.nsrc, stream())
+            self.curve_r(qr, self.ur, accumulate=True)
+            return self.ur
         if ewald and self.single:
             # ub is the field of our own sources only: ub - w == 0 and the adjustment vanishes
             lib().ipde_vec_mul(ptr(self.sigma_r), ptr(r.sw), ptr(qr), r.nsrc, stream())

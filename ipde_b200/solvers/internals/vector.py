@@ -12,7 +12,7 @@ import torch
 from ..._lib import lib
 from ...annular import ApproximateAnnularGeometry, RealAnnularGeometry
 from ...device import to_dev, empty, ptr, stream, gemv, layer_apply_stokes, FFT1D
-from .scalar import DeviceQFS, device_qfs
+from .scalar import DeviceQFS, device_qfs, DeviceCurveOperator
 
 
 def v2f(x):
@@ -77,6 +77,12 @@ class VectorHelper(object):
         self._work = empty((M, n), torch.complex128)
         self._dur = empty((M, n))
         self._tau = empty((4*n,))
+        self.curve_w = self.curve_r = None
+        if getattr(self.interface_qfs_g, 'structured', False) and getattr(self.interface_qfs_r, 'structured', False):
+            from ...qfs_structured import source_to_curves
+            self.curve_w = DeviceCurveOperator(source_to_curves(self.interface_qfs_g, [e.interface.c]))
+            levels = [e.radial_x[i] + 1j*e.radial_y[i] for i in range(M)]
+            self.curve_r = DeviceCurveOperator(source_to_curves(self.interface_qfs_r, levels, pressure=True))
 
     def set_evaluation(self, mode, grid, single):
         """'direct': all-pairs stokeslet sums in correct(); 'ewald': spectral-Ewald evaluators on a box around this
@@ -87,7 +93,7 @@ class VectorHelper(object):
         if not hasattr(self, 'evaluator_r'):
             self.evaluator_r = None
             self.evaluator_w = None
-        if mode == 'ewald' and self.evaluator_r is None:
+        if mode == 'ewald' and self.evaluator_r is None and self.curve_r is None:
             from ...device import StokesFreeSpaceEvaluator
             e = self.ebdy
             g, r = self.interface_qfs_g.source, self.interface_qfs_r.source
@@ -168,6 +174,9 @@ class VectorHelper(object):
         else:
             if own_field is not None:
                 w = own_field                  # caller-provided field of our own grid-side sources on our interface
+            elif self.curve_w is not None:
+                w = empty((2, n))
+                self.curve_w(self.sigma_g.reshape(-1), [w[0], w[1]])
             else:
                 q = self._weighted(self.sigma_g, g.sw)
                 if ewald and self.evaluator_w is not None:
@@ -181,6 +190,13 @@ class VectorHelper(object):
             sigma_r_tot = torch.empty_like(self.sigma_r)
             lib().ipde_vec_axpby(1.0, ptr(sigma_r_adj), 1.0, ptr(self.sigma_r), ptr(sigma_r_tot),
                                  int(sigma_r_tot.numel()), stream())
+        if self.curve_r is not None:
+            # structured QFS: stokeslet velocity and pressure on the radial levels as Fourier-banded maps
+            rows = []
+            for i in range(self.ebdy.M):
+                rows += [self.ur[i], self.vr[i], self.pr[i]]
+            self.curve_r(sigma_r_tot.reshape(-1), rows, accumulate=True)
+            return self.ur, self.vr, self.pr
         q = self._weighted(sigma_r_tot, r.sw)
         nt = int(self.d_rx.numel())
         if ewald:

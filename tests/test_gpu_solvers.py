@@ -375,3 +375,122 @@ def test_dirichlet_correction_poisson():
     us = [np.asarray(DirichletCorrection(solver, evaluation=ev)(ue, bc)) for ev in ('direct', 'ewald')]
     assert np.abs(us[0] - np.asarray(ua)).max() < 2e-7
     assert np.abs(us[0] - us[1]).max() < 1e-10
+
+
+def test_traction_computation():
+    """examples/test_traction_computation.py:97-147 (the traction check of BASELINE configs[3]): the traction of an
+    analytic Stokes field on the interface / boundary from (i) the grid stress through the spectral interface
+    interpolation and (ii) the radial (u, v, p) through VectorHelper.get_{interface,boundary}_traction_{uvp,rtp}.
+    Five error figures, as the reference prints them."""
+    from ipde_b200.solvers.internals.stokes import StokesHelper
+    ebdyc = single_star(nb=600, M=16)
+    ebdy = ebdyc[0]
+    grid = ebdyc.grid
+    w = 2.4
+    kk = 2*np.pi/w
+    a, b, p_a, p_b = 3*kk, kk, 2*kk, 5*kk
+    sin, cos = np.sin, np.cos
+    esin = lambda x: np.exp(sin(x))
+    esin_x = lambda x: np.exp(sin(x))*cos(x)
+    psix = lambda x, y: esin(a*x)*cos(b*y)
+    psiy = lambda x, y: esin(a*x)*sin(b*y)
+    u_f = lambda x, y: psix(x, y)
+    v_f = lambda x, y: -a/b*cos(a*x)*psiy(x, y)
+    p_f = lambda x, y: cos(p_a*x) + esin(p_b*y)
+    ux_f = lambda x, y: a*esin_x(a*x)*cos(b*y)
+    uy_f = lambda x, y: -b*esin(a*x)*sin(b*y)
+    vx_f = lambda x, y: a**2/b*sin(a*x)*psiy(x, y) - a/b*cos(a*x)*a*esin_x(a*x)*sin(b*y)
+    vy_f = lambda x, y: -a/b*cos(a*x)*b*esin(a*x)*cos(b*y)
+    txx_f = lambda x, y: 2*ux_f(x, y) - p_f(x, y)
+    txy_f = lambda x, y: uy_f(x, y) + vx_f(x, y)
+    tyy_f = lambda x, y: 2*vy_f(x, y) - p_f(x, y)
+    on = lambda pts, fs: [f(pts[0], pts[1]) for f in fs]
+    txx, txy, tyy = on((grid.xg, grid.yg), (txx_f, txy_f, tyy_f))
+    ru, rv, rp = on((ebdy.radial_x, ebdy.radial_y), (u_f, v_f, p_f))
+    I, B = ebdy.interface, ebdy.bdy
+    itxx, itxy, ityy = on((I.x, I.y), (txx_f, txy_f, tyy_f))
+    btxx, btxy, btyy = on((B.x, B.y), (txx_f, txy_f, tyy_f))
+    itx, ity = itxx*I.normal_x + itxy*I.normal_y, itxy*I.normal_x + ityy*I.normal_y
+    scale = max(np.abs(itx).max(), np.abs(ity).max())
+    errs = []
+    # 1: grid stress -> interface (trigonometric interpolation; the fields are periodic on the box)
+    e = [ebdyc.interpolate_grid_to_interface(t, order=np.inf, cutoff=False) for t in (txx, txy, tyy)]
+    etx, ety = e[0]*I.normal_x + e[1]*I.normal_y, e[1]*I.normal_x + e[2]*I.normal_y
+    errs.append(max(np.abs(etx - itx).max(), np.abs(ety - ity).max()))
+    helper = StokesHelper(ebdy)
+    # 2, 3: radial (u, v, p) -> interface traction, in (x, y) and in (r, t) components
+    etx, ety = helper.get_interface_traction_uvp(ru, rv, rp)
+    errs.append(max(np.abs(etx - itx).max(), np.abs(ety - ity).max()))
+    itr, itt = ebdy.convert_uv_to_rt(itx, ity)
+    rr, rt = ebdy.convert_uv_to_rt(ru, rv)
+    etr, ett = helper.get_interface_traction_rtp(rr, rt, rp)
+    errs.append(max(np.abs(etr - itr).max(), np.abs(ett - itt).max()))
+    # 4, 5: the same on the boundary
+    btx, bty = btxx*B.normal_x + btxy*B.normal_y, btxy*B.normal_x + btyy*B.normal_y
+    etx, ety = helper.get_boundary_traction_uvp(ru, rv, rp)
+    errs.append(max(np.abs(etx - btx).max(), np.abs(ety - bty).max()))
+    btr, btt = ebdy.convert_uv_to_rt(btx, bty)
+    etr, ett = helper.get_boundary_traction_rtp(rr, rt, rp)
+    errs.append(max(np.abs(etr - btr).max(), np.abs(ett - btt).max()))
+    print('traction errors (relative to %.2f):' % scale, ['%.2e' % (x/scale) for x in errs])
+    assert errs[0]/scale < 1e-11
+    for x in errs[1:]:
+        assert x/scale < 1e-10
+
+
+def _mid_size_bodies(nb=256, M=10):
+    """four bodies with the boundary counts of the structured-QFS regime (>= 1024 on the outer star) on a grid the
+    all-pairs / direct-NUDFT oracle still finishes in about a minute"""
+    from ipde_b200.geometry import GSB, star, squished_circle
+    from ipde_b200.embedded_boundary import EmbeddedBoundary
+    from ipde_b200.ebdy_collection import EmbeddedBoundaryCollection
+    from ipde_b200.slepian import SlepianMollifier
+    bdy1 = GSB(c=star(4*nb, r=1.0, a=0.05, f=7))
+    bdy2 = GSB(c=squished_circle(nb, x=-0.4, y=-0.25, r=0.25, b=0.6, rot=-np.pi/4))
+    bdy3 = GSB(c=star(nb, x=0.35, y=0.2, r=0.22, a=0.1, f=3))
+    bdy4 = GSB(c=star(nb, x=-0.17, y=0.5, r=0.2, a=0.15, f=4))
+    bdys = [bdy1, bdy2, bdy3, bdy4]
+    bh = min(b.dt*b.speed.min() for b in bdys)
+    MOL = SlepianMollifier(2*M)
+    ebdys = [EmbeddedBoundary(b, b is bdy1, M, bh, heaviside=MOL.step) for b in bdys]
+    ebdyc = EmbeddedBoundaryCollection(ebdys)
+    ebdyc.generate_grid(force_square=True)
+    return ebdyc
+
+
+def test_mid_size_four_bodies_structured_qfs_vs_oracle(monkeypatch):
+    """BASELINE configs[2] at the largest size the all-pairs oracle does in about a minute (grid ~450^2, outer
+    boundary 1024 nodes): the device path runs the structured QFS operators (k_banded_apply) and the Fourier-banded
+    curve operators of correct() for the outer boundary, dense operators for the small bodies; the oracle applies
+    the same QFS objects in NumPy and sums all pairs directly."""
+    from ipde_b200.solvers.multi_boundary.modified_helmholtz import ModifiedHelmholtzSolver
+    ebdyc = _mid_size_bodies()
+    f, ua, _ = manufactured(ebdyc, 5.0, kk=10*np.pi/7)
+    solver = ModifiedHelmholtzSolver(ebdyc, 5.0)
+    assert getattr(solver.helpers[0].interface_qfs_g, 'structured', False)
+    assert solver.helpers[0].curve_r is not None
+    ue = solver(f, tol=1e-13, restart=60, maxiter=5)
+    uo = oracle_for(solver, 'modified_helmholtz', 5.0, 'spectral')(f, tol=1e-13, restart=60, maxiter=5)
+    linf, l2 = rel_errors(ue, uo)
+    print('mid-size 4 bodies, grid %d^2, dof %d: linf %.2e l2 %.2e' % (ebdyc.grid.Nx, ebdyc.dof, linf, l2))
+    assert linf < TOL and l2 < TOL, (linf, l2)
+    # the same problem with the dense SVD-factored QFS on every boundary: different source curves, same potentials
+    monkeypatch.setenv('IPDE_QFS', 'dense')
+    dense = ModifiedHelmholtzSolver(ebdyc, 5.0)
+    assert not getattr(dense.helpers[0].interface_qfs_g, 'structured', False)
+    ud = dense(f, tol=1e-13, restart=60, maxiter=5)
+    linf, l2 = rel_errors(ue, ud)
+    print('structured vs dense QFS: linf %.2e l2 %.2e' % (linf, l2))
+    assert linf < TOL and l2 < TOL, (linf, l2)
+
+
+def test_poisson_single_boundary_structured_qfs_vs_oracle():
+    from ipde_b200.solvers.multi_boundary.poisson import PoissonSolver
+    ebdyc = single_star(nb=1024, M=10, bump=True)
+    f, ua, _ = manufactured(ebdyc, 0.0)
+    solver = PoissonSolver(ebdyc, grid_backend='direct')
+    assert getattr(solver.helpers[0].interface_qfs_g, 'structured', False)
+    ue = solver(f, tol=1e-13, restart=40, maxiter=5)
+    uo = oracle_for(solver, 'poisson', 0.0, 'spectral')(f, tol=1e-13, restart=40, maxiter=5)
+    linf, l2 = rel_errors(ue, uo)
+    assert linf < TOL and l2 < TOL, (linf, l2)
