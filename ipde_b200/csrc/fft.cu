@@ -93,6 +93,7 @@ int fft_plan_create(int n, FftPlan** out) {
 
 void fft_plan_destroy(FftPlan* p) {
     if (!p) return;
+    fft_plan_destroy(p->half);
     cudaFree(p->tw_dev);
     cudaFree(p->half_tw_dev);
     cudaFree(p->work);
@@ -589,9 +590,9 @@ int fft_cols_windowed(FftPlan* p, const cplx* in, cplx* out, int64_t elem_stride
         fout = std::min(1.0, std::max(0.0, (double)(W.out_hi - W.out_lo)) / rows);
     }
     KERNEL_TAG("k_fft_cols", 16.0 * (fin + fout) * (double)n * (double)n_inner * (double)n_outer);
-    if (g_fft_short && p->pow2 && fft_short_size(n)) {
+    if (g_fft_short && p->pow2 && fft_short_size_plain(n)) {
 #define CALL_SHORT(RA_, RB_) return launch_cols_short<RA_, RB_>(p, in, out, elem_stride, n_inner, n_outer, outer_stride, sign, scale, tw_mode, tw_big, W, st)
-        SHORT_DISPATCH(n, CALL_SHORT);
+        SHORT_DISPATCH_PLAIN(n, CALL_SHORT);
 #undef CALL_SHORT
     }
     const int64_t ntiles_total = (int64_t)tiles * n_outer;
@@ -870,6 +871,136 @@ static int launch_mul_fft_reg(FftPlan* p, const cplx* in, cplx* out, const doubl
     return IPDE_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Long contiguous lines, n = 2m with m a register-kernel length (n = 16384: the rows of the 32768-point boxes of the
+// free-space evaluator and of the NUFFT fine grid at 16384^2).  One radix-2 step around the m-point register
+// transform instead of five global-memory passes:
+//   forward  (decimation in time):  E_r = FFT_m(z[2j + r]), r = 0, 1  -- the m-point kernel reads its line with an
+//            element stride of 2 (both sub-lines of a row are read by neighbouring CTAs, the sectors are shared
+//            through L2) --, then Z[k] = E_0[k] + w^k E_1[k], Z[k + m] = E_0[k] - w^k E_1[k] in the consumer;
+//   inverse  (decimation in frequency):  A[k] = Z[k] + Z[k+m], B[k] = (Z[k] - Z[k+m]) conj(w^k) in the producer,
+//            then z[2j] = IFFT_m(A)[j], z[2j+1] = IFFT_m(B)[j]: the m-point kernel stores with an element stride 2.
+template <int N, int SIGN>
+__global__ void __launch_bounds__(RegGeom<N>::NT, RegGeom<N>::MINB)
+k_fft_rows_reg_sub(const cplx* __restrict__ tw, const cplx* in, cplx* out, int64_t nsub, int64_t in_pitch, int64_t in_sub,
+                   int in_es, int64_t out_pitch, int64_t out_sub, int out_es, double scale) {
+    using G = RegGeom<N>;
+    using K = RegCfg<N>;
+    extern __shared__ cplx smem[];
+    const int tid = threadIdx.x;
+    const int l = tid >> G::LOGT, jt = tid & (G::T - 1);
+    cplx* line = smem + l * G::LINE;
+    const int64_t sub = (int64_t)blockIdx.x * G::L + l;          // sub-line index: 2*row + r
+    const bool live = sub < nsub;
+    const int64_t row = (live ? sub : 0) >> 1;
+    const int r = (int)(sub & 1);
+    cplx v[G::EPT];
+    const cplx* src = in + row * in_pitch + r * in_sub;
+#pragma unroll
+    for (int s = 0; s < G::EPT; ++s)
+        v[s] = live ? src[(int64_t)reg_elem<N, K::R0>(jt, s) * in_es] : make_double2(0.0, 0.0);
+    reg_fft<N, SIGN, false>(v, line, jt, tw);
+    if (live) {
+        cplx* dst = out + row * out_pitch + r * out_sub;
+#pragma unroll
+        for (int s = 0; s < G::EPT; ++s) dst[(int64_t)reg_elem<N, G::RLAST>(jt, s) * out_es] = cscale(v[s], scale);
+    }
+}
+
+template <int N>
+static int launch_rows_reg_sub(FftPlan* ph, const cplx* in, cplx* out, int64_t nsub, int64_t in_pitch, int64_t in_sub, int in_es,
+                               int64_t out_pitch, int64_t out_sub, int out_es, int sign, double scale, cudaStream_t st) {
+    using G = RegGeom<N>;
+    const unsigned g = (unsigned)cdiv(nsub, (int64_t)G::L);
+    int rc;
+    if (sign < 0) {
+        rc = set_smem(k_fft_rows_reg_sub<N, -1>, G::SMEM);
+        if (rc) return rc;
+        k_fft_rows_reg_sub<N, -1><<<g, G::NT, G::SMEM, st>>>(ph->d.tw, in, out, nsub, in_pitch, in_sub, in_es, out_pitch,
+                                                             out_sub, out_es, scale);
+    } else {
+        rc = set_smem(k_fft_rows_reg_sub<N, +1>, G::SMEM);
+        if (rc) return rc;
+        k_fft_rows_reg_sub<N, +1><<<g, G::NT, G::SMEM, st>>>(ph->d.tw, in, out, nsub, in_pitch, in_sub, in_es, out_pitch,
+                                                             out_sub, out_es, scale);
+    }
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+
+static bool fft_split_size(int n) { return n % 2 == 0 && fft_reg_size(n / 2) && n / 2 >= 4096; }
+static int ensure_half(FftPlan* p) {
+    if (p->half) return IPDE_OK;
+    return fft_plan_create(p->d.n / 2, &p->half);
+}
+static int rows_reg_sub(FftPlan* p, const cplx* in, cplx* out, int64_t nsub, int64_t in_pitch, int64_t in_sub, int in_es,
+                        int64_t out_pitch, int64_t out_sub, int out_es, int sign, double scale, cudaStream_t st) {
+    const int m = p->d.n / 2;
+#define CALL_SUB(N_) return launch_rows_reg_sub<N_>(p->half, in, out, nsub, in_pitch, in_sub, in_es, out_pitch, out_sub, out_es, sign, scale, st)
+    if (m == 4096) { CALL_SUB(4096); }
+    CALL_SUB(8192);
+#undef CALL_SUB
+}
+
+// r2c of rows of 2n reals (n = 2m complex): E_0 | E_1 sit in the first 2m slots of the output row; every thread
+// owns the closed orbit {k, m-k, m+k, n-k} and rewrites it in place with the half spectrum X[0..n].
+__global__ void k_r2c_untangle_split(int m, const cplx* __restrict__ twn, const cplx* __restrict__ half_tw, cplx* __restrict__ out,
+                                     int64_t batch, int64_t out_pitch) {
+    const int n = 2 * m;
+    const int per = m / 2 + 1;                                    // k = 0 .. m/2
+    const int64_t total = batch * per;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / per;
+        const int k = (int)(i % per);
+        cplx* o = out + row * out_pitch;
+        const int km = (k == 0) ? 0 : m - k;                      // index of E[m - k] (periodic in m)
+        const cplx e0k = o[k], e1k = o[m + k], e0m = o[km], e1m = o[m + km];
+        const cplx tk = cmul(twn[k], e1k);
+        // w_n^{m-k} = -conj(w_n^k)
+        const cplx wm = (k == 0) ? make_double2(1.0, 0.0) : make_double2(-twn[k].x, twn[k].y);
+        const cplx tm = cmul(wm, e1m);
+        const cplx Zk = cadd(e0k, tk), Zkm = csub(e0k, tk);       // Z[k], Z[k + m]
+        const cplx Zmk = cadd(e0m, tm), Znk = csub(e0m, tm);      // Z[m - k], Z[n - k]   (k = 0: Z[0], Z[m])
+        auto X = [&](cplx za, cplx zb, int kk) {                  // half-spectrum entry kk from Z[kk], Z[n - kk]
+            const cplx zc = cconj(zb);
+            const cplx E = cscale(cadd(za, zc), 0.5);
+            const cplx O = cmulni(cscale(csub(za, zc), 0.5));
+            return cadd(E, cmul(half_tw[kk], O));
+        };
+        if (k == 0) {
+            // Z[0] = Zk, Z[m] = Zkm; X[0] pairs Z[0] with itself, X[n] likewise, X[m] pairs Z[m] with Z[m]
+            o[0] = X(Zk, Zk, 0);
+            o[n] = X(Zk, Zk, n);
+            o[m] = X(Zkm, Zkm, m);
+        } else {
+            const cplx x_k = X(Zk, Znk, k), x_nk = X(Znk, Zk, n - k);
+            const cplx x_mk = X(Zmk, Zkm, m - k), x_km = X(Zkm, Zmk, m + k);
+            o[k] = x_k; o[n - k] = x_nk;
+            o[m - k] = x_mk; o[m + k] = x_km;          // 2k == m: the same two entries, the same values
+        }
+    }
+}
+// c2r of rows of 2n reals: spectrum X[0..n] -> A | B sub-lines (2m slots) of the work row
+__global__ void k_c2r_tangle_split(int m, const cplx* __restrict__ twn, const cplx* __restrict__ half_tw, const cplx* __restrict__ in,
+                                   cplx* __restrict__ z, int64_t batch, int64_t in_pitch, int64_t z_pitch) {
+    const int n = 2 * m;
+    const int64_t total = batch * m;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / m;
+        const int k = (int)(i % m);
+        const cplx* src = in + row * in_pitch;
+        auto Z = [&](int kk) {                                    // packed-transform entry kk < n from X[kk], X[n - kk]
+            const cplx xk = src[kk];
+            const cplx xc = cconj(src[n - kk]);
+            const cplx E = cscale(cadd(xk, xc), 0.5);
+            const cplx O = cmulc(cscale(csub(xk, xc), 0.5), half_tw[kk]);
+            return cadd(E, cmuli(O));
+        };
+        const cplx z0 = Z(k), z1 = Z(k + m);
+        z[row * z_pitch + k] = cadd(z0, z1);
+        z[row * z_pitch + m + k] = cmulc(csub(z0, z1), twn[k]);
+    }
+}
 // Global-memory versions of the pack / unpack steps for long rows
 __global__ void k_r2c_untangle(int n, const cplx* __restrict__ half_tw, const cplx* __restrict__ z, cplx* __restrict__ out,
                                int64_t batch, int64_t z_pitch, int64_t out_pitch) {
@@ -905,6 +1036,20 @@ int fft_r2c_rows(FftPlan* p, const double* in, cplx* out, int64_t batch, int64_t
     if (batch <= 0) return IPDE_OK;
     const int n = p->d.n;
     if (!p->fast && !p->any && n <= IPDE_FFT_GENERIC_MAX) return fft_r2c_rows_generic(p, in, out, batch, in_pitch, out_pitch, st);
+    if (g_fft_reg && fft_split_size(n)) {
+        int rc = ensure_half(p);
+        if (rc) return rc;
+        const int m = n / 2;
+        KERNEL_TAG("k_r2c_rows_long", (16.0 * n + 16.0 * (n + 1)) * (double)batch);
+        // packed row z[j] = (x[2j], x[2j+1]); sub-line r = z[2i + r]: element stride 2, offset r
+        rc = rows_reg_sub(p, reinterpret_cast<const cplx*>(in), out, 2 * batch, in_pitch / 2, 1, 2, out_pitch, m, 1, -1, 1.0, st);
+        if (rc) return rc;
+        const int blocks = (int)std::min<int64_t>(cdiv(batch * (m / 2 + 1), 256), (int64_t)ipde_num_sms() * 16);
+        KERNEL_TAG("k_r2c_untangle_split", 32.0 * n * (double)batch);
+        k_r2c_untangle_split<<<blocks, 256, 0, st>>>(m, p->d.tw, p->half_tw_dev, out, batch, out_pitch);
+        KERNEL_CHECK();
+        return IPDE_OK;
+    }
     if (n > IPDE_FFT_SMEM_MAX || !p->fast) {
         // complex FFT of the packed rows into the front of each output row, then untangle in place is not
         // possible (aliasing), so go through the plan's work buffer
@@ -941,6 +1086,27 @@ int fft_c2r_rows(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t
     if (batch <= 0) return IPDE_OK;
     const int n = p->d.n;
     if (!p->fast && !p->any && n <= IPDE_FFT_GENERIC_MAX) return fft_c2r_rows_generic(p, in, out, batch, in_pitch, out_pitch, scale, st);
+    if (g_fft_reg && fft_split_size(n)) {
+        int rc = ensure_half(p);
+        if (rc) return rc;
+        const int m = n / 2;
+        // row chunks bound the scratch (A | B sub-lines) to 256 MB
+        const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(batch, ((int64_t)1 << 24) / n));
+        rc = ensure_work(p, (size_t)n * chunk);
+        if (rc) return rc;
+        for (int64_t r0 = 0; r0 < batch; r0 += chunk) {
+            const int64_t nb = std::min<int64_t>(chunk, batch - r0);
+            const int blocks = (int)std::min<int64_t>(cdiv(nb * m, 256), (int64_t)ipde_num_sms() * 16);
+            KERNEL_TAG("k_c2r_tangle_split", 32.0 * n * (double)nb);
+            k_c2r_tangle_split<<<blocks, 256, 0, st>>>(m, p->d.tw, p->half_tw_dev, in + r0 * in_pitch, p->work, nb, in_pitch, n);
+            KERNEL_CHECK();
+            KERNEL_TAG("k_c2r_rows_long", (16.0 * n + 16.0 * (n + 1)) * (double)nb);
+            rc = rows_reg_sub(p, p->work, reinterpret_cast<cplx*>(out + r0 * out_pitch), 2 * nb, n, m, 1, out_pitch / 2, 1, 2,
+                              +1, scale, st);
+            if (rc) return rc;
+        }
+        return IPDE_OK;
+    }
     if (n > IPDE_FFT_SMEM_MAX || !p->fast) {
         int rc = ensure_work(p, (size_t)3 * n * batch);
         if (rc) return rc;

@@ -33,7 +33,7 @@ struct ShortCfg {
     static constexpr int EPT = (N > 64) ? 16 : 8;   // elements per thread (N = 128: one radix-16 butterfly)
     static constexpr int T = N / EPT;            // threads per line
     static constexpr int C = 128 / T;            // columns per tile (128 threads per CTA)
-    static constexpr int LOGC = (C == 16) ? 4 : (C == 32) ? 5 : 6;
+    static constexpr int LOGC = (C == 8) ? 3 : (C == 16) ? 4 : (C == 32) ? 5 : 6;
     static constexpr int BA = EPT / RA;          // radix-RA butterflies per thread
     static constexpr int BB = EPT / RB;
     static constexpr int TILE = N * C;           // 1024 elements (2048 for N = 128)
@@ -42,7 +42,7 @@ struct ShortCfg {
     // one shared buffer (32 KB) with a barrier before it is rewritten.
     static constexpr bool PREFETCH = (EPT == 8);
     static constexpr int NBUF = PREFETCH ? 2 : 1;
-    static_assert(N == 16 || N == 32 || N == 64 || N == 128, "short transforms: N in {16, 32, 64, 128}");
+    static_assert(N == 16 || N == 32 || N == 64 || N == 128 || N == 256, "short transforms: N in {16, ..., 256}");
     static_assert(BA >= 1 && BB >= 1, "radix larger than the elements of a thread");
 };
 
@@ -120,6 +120,14 @@ __device__ __forceinline__ ShortTile short_tile(int tile, int tiles_per_outer, i
 
 bool fft_short_enabled();
 static inline bool fft_short_size(int n) { return n == 16 || n == 32 || n == 64 || n == 128; }
+// the plain (unfused) column pass also has a 256-point instance (16 x 16, 8 columns per tile): first/last pass of
+// the four-step split of 32768-point columns
+static inline bool fft_short_size_plain(int n) { return fft_short_size(n) || n == 256; }
+#define SHORT_DISPATCH_PLAIN(n, CALL)        \
+    do {                                     \
+        if ((n) == 256) { CALL(16, 16); }    \
+        else SHORT_DISPATCH(n, CALL);        \
+    } while (0)
 
 // SHORT_DISPATCH(n, CALL): CALL is a macro taking (RA, RB)
 #define SHORT_DISPATCH(n, CALL)            \

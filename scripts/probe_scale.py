@@ -56,4 +56,16 @@ torch.cuda.synchronize()
 dt = (time.time() - t0)/5
 print('solve_device %.3f ms  -> %.3e grid-point-solves/s' % (dt*1e3, N*N/dt))
 print('peak mem GB', torch.cuda.max_memory_allocated()/1e9)
+import ctypes
+from ipde_b200._lib import lib
+from ipde_b200.device import stream
+lib().ipde_profile_start(stream())
+solver.solve_device(d_in, tol=1e-12, restart=40, maxiter=5)
+buf = ctypes.create_string_buffer(1 << 16)
+lib().ipde_profile_stop(buf, len(buf))
+print('kernel launches ms bytes GB/s')
+for line in buf.value.decode().strip().splitlines():
+    pr = line.split()
+    if len(pr) == 4 and float(pr[2]) > 0.05:
+        print('  %-28s %5d %9.3f %12.4g %8.0f' % (pr[0], int(pr[1]), float(pr[2]), float(pr[3]), float(pr[3])/float(pr[2])/1e6))
 json.dump({'N': N, 'setup': T, 'stages_ms': st, 'solve_ms': dt*1e3}, open(os.path.join(ROOT, 'gpurun_out', 'probe_%s_%d.json' % (what, N)), 'w'))

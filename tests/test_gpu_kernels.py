@@ -50,7 +50,7 @@ def test_fft_mul_fft(D, n):
 @pytest.mark.parametrize('shape', [(64, 64), (96, 80), (100, 36), (1024, 40), (2048, 128), (128, 2048), (4096, 64), (4096, 100),
                                    (6000, 20), (8192, 40), (16384, 36),
                                    (9, 512), (15, 1024), (20, 2048), (10, 4096), (6, 8192), (8, 16384),
-                                   (474, 474), (94, 158), (2102, 34)])
+                                   (474, 474), (94, 158), (2102, 34), (32768, 20), (7, 32768), (2500, 32768)])
 def test_grid_fft2(D, shape):
     nx, ny = shape
     rng = np.random.default_rng(nx + ny)
@@ -64,7 +64,8 @@ def test_grid_fft2(D, shape):
 
 
 @pytest.mark.parametrize('kind,k', [(1, 2.5), (0, 0.0)])
-@pytest.mark.parametrize('shape', [(96, 80), (1024, 48), (2048, 64), (4096, 36), (8192, 36), (16384, 40), (474, 94)])
+@pytest.mark.parametrize('shape', [(96, 80), (1024, 48), (2048, 64), (4096, 36), (8192, 36), (16384, 40), (474, 94),
+                                   (32768, 36), (40, 32768), (24, 16384)])
 def test_grid_solve_scalar(D, kind, k, shape):
     from ipde_b200._lib import lib
     nx, ny = shape
@@ -450,17 +451,17 @@ def test_structured_qfs_device_apply(D, kind, n):
         tau = np.concatenate([np.exp(np.cos(t))*np.sin(2*t) + 1e-6*rng.standard_normal(n), np.cos(3*t + 0.3)])
         sd = dq(D.to_dev(tau)).cpu().numpy()
         sh = q([tau[:n], tau[n:]])
-        # the strengths amplify the top density modes by exp(alpha_s pi) ~ 1e5: round-off differences of the two
-        # FFTs show up at 1e-11 in sigma, not in the field sigma generates
+        # the strengths amplify the top density modes by exp(alpha_s pi) ~ 1e6: the round-off (1e-16) of the two
+        # different FFTs in those modes shows up at ~5e-9 of max|sigma|, not in the field sigma generates
         th = np.linspace(0, 2*np.pi, 97, endpoint=False)
         z = (1 + 0.15*np.cos(5*th))*np.exp(1j*th)*(1 - 2*np.pi/n if interior else 1 + 2*np.pi/n)
         field = lambda sg: Q.layer_apply_matrix_free(q.kernel, q.source, z.real, z.imag, sg)
-        assert rel(sd, sh) < 1e-9
+        assert rel(sd, sh) < 1e-7
         dfield = np.abs(field(sd) - field(sh)).max()/max(1.0, np.abs(field(sh)).max())
         assert dfield < 1e-12, dfield
         ub = np.exp(np.sin(t))
         su, suh = dq.u2s(D.to_dev(ub)).cpu().numpy(), q.u2s(ub)
-        assert rel(su, suh) < 1e-9
+        assert rel(su, suh) < 1e-7
         dfield = np.abs(field(su) - field(suh)).max()/max(1.0, np.abs(field(suh)).max())
         assert dfield < 1e-12, dfield
 
