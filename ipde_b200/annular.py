@@ -118,8 +118,7 @@ class AnnularModifiedHelmholtzSolver(object):
         self.small_shape = (self.M, self.ns)
         self.shape = (self.M, self.n)
         self._construct()
-        self._plan = None
-        self._plan_key = None
+        self._plans = {}
         self.iterations_last_call = None
 
     def _construct(self):
@@ -134,11 +133,15 @@ class AnnularModifiedHelmholtzSolver(object):
 
     def _get_plan(self, RAG):
         key = (id(RAG), self.ia, self.ib, self.oa, self.ob)
-        if self._plan is not None and self._plan_key == key:
-            return self._plan
-        if self._plan is not None:
-            lib().ipde_annular_plan_destroy(self._plan)
-            self._plan = None
+        # one device plan per (geometry, boundary rows): an annular solver shared between boundaries of the same size
+        # (helpers= / AS_list= reuse, as in the reference) keeps a plan for each instead of rebuilding it every solve
+        hit = self._plans.get(key)
+        if hit is not None:
+            return hit[0]
+        if len(self._plans) >= 16:
+            for h_old, _ in self._plans.values():
+                lib().ipde_annular_plan_destroy(h_old)
+            self._plans.clear()
         CO, AAG = self.AAG.CO, self.AAG
         c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
         ibc = c((self.ia*CO.ibc_dirichlet + self.ib*CO.ibc_neumann)[0])
@@ -148,14 +151,13 @@ class AnnularModifiedHelmholtzSolver(object):
                 c(RAG.psi1), c(RAG.inv_psi1), c(RAG.inv_psi2), kinv]
         h = ctypes.c_void_p()
         lib().ipde_annular_plan_create(self.n, self.M, float(self.k), *[hptr(a) for a in arrs], ctypes.byref(h))
-        self._plan, self._plan_key = h, key
-        self._keep = RAG
+        self._plans[key] = (h, RAG)          # the RAG reference keeps id(RAG) unique while the plan lives
         return h
 
     def __del__(self):
         try:
-            if self._plan is not None:
-                lib().ipde_annular_plan_destroy(self._plan)
+            for h_old, _ in self._plans.values():
+                lib().ipde_annular_plan_destroy(h_old)
         except Exception:
             pass
 
@@ -227,8 +229,7 @@ class AnnularStokesSolver(object):
             raise Exception('the annular Stokes solver works on the Nyquist-dropped geometry')
         self.u_shape = (self.M, self.n)
         self._construct()
-        self._plan = None
-        self._plan_key = None
+        self._plans = {}
         self.iterations_last_call = None
 
     def _construct(self):
@@ -262,11 +263,15 @@ class AnnularStokesSolver(object):
 
     def _get_plan(self, RAG):
         key = id(RAG)
-        if self._plan is not None and self._plan_key == key:
-            return self._plan
-        if self._plan is not None:
-            lib().ipde_annular_stokes_plan_destroy(self._plan)
-            self._plan = None
+        # one device plan per (geometry, boundary rows): an annular solver shared between boundaries of the same size
+        # (helpers= / AS_list= reuse, as in the reference) keeps a plan for each instead of rebuilding it every solve
+        hit = self._plans.get(key)
+        if hit is not None:
+            return hit[0]
+        if len(self._plans) >= 16:
+            for h_old, _ in self._plans.values():
+                lib().ipde_annular_stokes_plan_destroy(h_old)
+            self._plans.clear()
         CO, AAG, M, n = self.AAG.CO, self.AAG, self.M, self.n
         c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
         ks = AAG.k.copy()
@@ -283,14 +288,13 @@ class AnnularStokesSolver(object):
                 c(combo1), c(combo2), c(RAG.ipsi_DR_ipsi_DT_psi2)]
         h = ctypes.c_void_p()
         lib().ipde_annular_stokes_plan_create(n, M, float(self.mu), *[hptr(a) for a in arrs], hptr(kinv), ctypes.byref(h))
-        self._plan, self._plan_key = h, key
-        self._keep = RAG
+        self._plans[key] = (h, RAG)          # the RAG reference keeps id(RAG) unique while the plan lives
         return h
 
     def __del__(self):
         try:
-            if self._plan is not None:
-                lib().ipde_annular_stokes_plan_destroy(self._plan)
+            for h_old, _ in self._plans.values():
+                lib().ipde_annular_stokes_plan_destroy(h_old)
         except Exception:
             pass
 

@@ -515,10 +515,18 @@ static int fft_lines_global(FftPlan* p, const cplx* in, cplx* out, int64_t batch
     return IPDE_OK;
 }
 
+static int fft_split_radix(int n);
+static int fft_rows_split(FftPlan* p, int R, const cplx* in, cplx* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
+                          int sign, double scale, cudaStream_t st);
+
 int fft_rows(FftPlan* p, const cplx* in, cplx* out, int64_t batch, int64_t in_pitch, int64_t out_pitch, int sign,
              double scale, cudaStream_t st) {
     if (batch <= 0) return IPDE_OK;
     const int n = p->d.n;
+    if (g_fft_reg && p->fast) {
+        const int R = fft_split_radix(n);
+        if (R) return fft_rows_split(p, R, in, out, batch, in_pitch, out_pitch, sign, scale, st);
+    }
     if (!p->fast && !p->any && n <= IPDE_FFT_GENERIC_MAX) return fft_rows_generic(p, in, out, batch, in_pitch, out_pitch, sign, scale, st);
     if (n > IPDE_FFT_SMEM_MAX || !p->fast) return fft_lines_global(p, in, out, batch, in_pitch, 1, out_pitch, 1, sign, scale, st);
     const int C = rows_per_tile(n, batch);
@@ -882,23 +890,33 @@ static int launch_mul_fft_reg(FftPlan* p, const cplx* in, cplx* out, const doubl
 //            then z[2j] = IFFT_m(A)[j], z[2j+1] = IFFT_m(B)[j]: the m-point kernel stores with an element stride 2.
 template <int N, int SIGN>
 __global__ void __launch_bounds__(RegGeom<N>::NT, RegGeom<N>::MINB)
-k_fft_rows_reg_sub(const cplx* __restrict__ tw, const cplx* in, cplx* out, int64_t nsub, int64_t in_pitch, int64_t in_sub,
-                   int in_es, int64_t out_pitch, int64_t out_sub, int out_es, double scale) {
+k_fft_rows_reg_sub(const cplx* __restrict__ tw, const cplx* in, cplx* out, int64_t nsub, int R, int64_t in_pitch, int64_t in_sub,
+                   int in_es, int64_t out_pitch, int64_t out_sub, int out_es, double scale, const double* __restrict__ mul,
+                   int64_t mul_pitch) {
     using G = RegGeom<N>;
     using K = RegCfg<N>;
     extern __shared__ cplx smem[];
     const int tid = threadIdx.x;
     const int l = tid >> G::LOGT, jt = tid & (G::T - 1);
     cplx* line = smem + l * G::LINE;
-    const int64_t sub = (int64_t)blockIdx.x * G::L + l;          // sub-line index: 2*row + r
+    const int64_t sub = (int64_t)blockIdx.x * G::L + l;          // sub-line index: R*row + r
     const bool live = sub < nsub;
-    const int64_t row = (live ? sub : 0) >> 1;
-    const int r = (int)(sub & 1);
+    const int64_t row = (live ? sub : 0) / R;
+    const int r = (int)((live ? sub : 0) - row * R);
     cplx v[G::EPT];
     const cplx* src = in + row * in_pitch + r * in_sub;
+    if (mul) {
+        const double* mm = mul + row * mul_pitch + r * in_sub;
 #pragma unroll
-    for (int s = 0; s < G::EPT; ++s)
-        v[s] = live ? src[(int64_t)reg_elem<N, K::R0>(jt, s) * in_es] : make_double2(0.0, 0.0);
+        for (int s = 0; s < G::EPT; ++s) {
+            const int64_t a = (int64_t)reg_elem<N, K::R0>(jt, s) * in_es;
+            v[s] = live ? cscale(src[a], mm[a]) : make_double2(0.0, 0.0);
+        }
+    } else {
+#pragma unroll
+        for (int s = 0; s < G::EPT; ++s)
+            v[s] = live ? src[(int64_t)reg_elem<N, K::R0>(jt, s) * in_es] : make_double2(0.0, 0.0);
+    }
     reg_fft<N, SIGN, false>(v, line, jt, tw);
     if (live) {
         cplx* dst = out + row * out_pitch + r * out_sub;
@@ -908,38 +926,140 @@ k_fft_rows_reg_sub(const cplx* __restrict__ tw, const cplx* in, cplx* out, int64
 }
 
 template <int N>
-static int launch_rows_reg_sub(FftPlan* ph, const cplx* in, cplx* out, int64_t nsub, int64_t in_pitch, int64_t in_sub, int in_es,
-                               int64_t out_pitch, int64_t out_sub, int out_es, int sign, double scale, cudaStream_t st) {
+static int launch_rows_reg_sub(FftPlan* ph, const cplx* in, cplx* out, int64_t nsub, int R, int64_t in_pitch, int64_t in_sub, int in_es,
+                               int64_t out_pitch, int64_t out_sub, int out_es, int sign, double scale, const double* mul,
+                               int64_t mul_pitch, cudaStream_t st) {
     using G = RegGeom<N>;
     const unsigned g = (unsigned)cdiv(nsub, (int64_t)G::L);
     int rc;
     if (sign < 0) {
         rc = set_smem(k_fft_rows_reg_sub<N, -1>, G::SMEM);
         if (rc) return rc;
-        k_fft_rows_reg_sub<N, -1><<<g, G::NT, G::SMEM, st>>>(ph->d.tw, in, out, nsub, in_pitch, in_sub, in_es, out_pitch,
-                                                             out_sub, out_es, scale);
+        k_fft_rows_reg_sub<N, -1><<<g, G::NT, G::SMEM, st>>>(ph->d.tw, in, out, nsub, R, in_pitch, in_sub, in_es, out_pitch,
+                                                             out_sub, out_es, scale, mul, mul_pitch);
     } else {
         rc = set_smem(k_fft_rows_reg_sub<N, +1>, G::SMEM);
         if (rc) return rc;
-        k_fft_rows_reg_sub<N, +1><<<g, G::NT, G::SMEM, st>>>(ph->d.tw, in, out, nsub, in_pitch, in_sub, in_es, out_pitch,
-                                                             out_sub, out_es, scale);
+        k_fft_rows_reg_sub<N, +1><<<g, G::NT, G::SMEM, st>>>(ph->d.tw, in, out, nsub, R, in_pitch, in_sub, in_es, out_pitch,
+                                                             out_sub, out_es, scale, mul, mul_pitch);
     }
     KERNEL_CHECK();
     return IPDE_OK;
 }
 
 static bool fft_split_size(int n) { return n % 2 == 0 && fft_reg_size(n / 2) && n / 2 >= 4096; }
-static int ensure_half(FftPlan* p) {
-    if (p->half) return IPDE_OK;
-    return fft_plan_create(p->d.n / 2, &p->half);
+// smallest R <= 16 with n / R a register-kernel length (3*2^k lines, power-of-two lines longer than 8192)
+static int fft_split_radix(int n) {
+    if (fft_reg_size(n)) return 0;
+    for (int R = 2; R <= 16; ++R)
+        if (n % R == 0 && fft_reg_size(n / R) && (n / R >= 1024 || n <= 8192)) return R;
+    return 0;
 }
+static int ensure_split(FftPlan* p, int R) {
+    if (p->half && p->splitR == R) return IPDE_OK;
+    fft_plan_destroy(p->half);
+    p->half = nullptr;
+    p->splitR = R;
+    return fft_plan_create(p->d.n / R, &p->half);
+}
+static int ensure_half(FftPlan* p) { return ensure_split(p, 2); }
 static int rows_reg_sub(FftPlan* p, const cplx* in, cplx* out, int64_t nsub, int64_t in_pitch, int64_t in_sub, int in_es,
-                        int64_t out_pitch, int64_t out_sub, int out_es, int sign, double scale, cudaStream_t st) {
-    const int m = p->d.n / 2;
-#define CALL_SUB(N_) return launch_rows_reg_sub<N_>(p->half, in, out, nsub, in_pitch, in_sub, in_es, out_pitch, out_sub, out_es, sign, scale, st)
-    if (m == 4096) { CALL_SUB(4096); }
-    CALL_SUB(8192);
+                        int64_t out_pitch, int64_t out_sub, int out_es, int sign, double scale, cudaStream_t st,
+                        const double* mul = nullptr, int64_t mul_pitch = 0) {
+    const int R = p->splitR;
+    const int m = p->d.n / R;
+#define CALL_SUB(N_) return launch_rows_reg_sub<N_>(p->half, in, out, nsub, R, in_pitch, in_sub, in_es, out_pitch, out_sub, out_es, sign, scale, mul, mul_pitch, st)
+    REG_DISPATCH(m, CALL_SUB);
 #undef CALL_SUB
+}
+
+// Radix-R steps around the m-point sub-transforms (n = R m), all indices natural:
+//   combine (decimation in time, after the sub-transforms E_s = FFT_m(z[R i + s])):
+//       Z[k' + m r] = sum_s (w_n^{s k'} E_s[k']) w_R^{s r}
+//   split (decimation in frequency, before the sub-transforms):
+//       A_s[k'] = w_n^{s k'} sum_r Z[k' + m r] w_R^{s r},   then z[R i + s] = FFT_m(A_s)[i]
+// (w = exp(-/+ 2 pi i / .) for sign -/+).  One thread per k': 2R complex loads/stores, O(R^2) flops.
+template <bool SPLIT>
+__global__ void k_radix_step(int m, int R, const cplx* __restrict__ twn, const cplx* __restrict__ in, cplx* __restrict__ out,
+                             int64_t batch, int64_t in_pitch, int64_t out_pitch, int sign, double scale) {
+    const int64_t total = batch * m;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / m;
+        const int k = (int)(i - row * m);
+        const cplx* src = in + row * in_pitch;
+        cplx* dst = out + row * out_pitch;
+        cplx x[16];
+        for (int s = 0; s < R; ++s) {
+            cplx v = src[k + (int64_t)m * s];
+            if (!SPLIT && s > 0) {
+                const cplx w = twn[(int64_t)s * k];                  // s k < R m = n
+                v = (sign < 0) ? cmul(v, w) : cmulc(v, w);
+            }
+            x[s] = v;
+        }
+        for (int r = 0; r < R; ++r) {
+            cplx acc = x[0];
+            for (int s = 1; s < R; ++s) {
+                const cplx w = twn[(int64_t)((s * r) % R) * m];      // w_R^{s r}
+                acc = cadd(acc, (sign < 0) ? cmul(x[s], w) : cmulc(x[s], w));
+            }
+            if (SPLIT && r > 0) {
+                const cplx w = twn[(int64_t)r * k];
+                acc = (sign < 0) ? cmul(acc, w) : cmulc(acc, w);
+            }
+            dst[k + (int64_t)m * r] = cscale(acc, scale);
+        }
+    }
+}
+static int radix_step(bool split, FftPlan* p, const cplx* in, cplx* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
+                      int sign, double scale, cudaStream_t st) {
+    const int R = p->splitR, m = p->d.n / R;
+    const int blocks = (int)std::min<int64_t>(cdiv(batch * m, 256), (int64_t)ipde_num_sms() * 16);
+    KERNEL_TAG("k_radix_step", 32.0 * p->d.n * (double)batch);
+    if (split) k_radix_step<true><<<blocks, 256, 0, st>>>(m, R, p->d.tw, in, out, batch, in_pitch, out_pitch, sign, scale);
+    else k_radix_step<false><<<blocks, 256, 0, st>>>(m, R, p->d.tw, in, out, batch, in_pitch, out_pitch, sign, scale);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+// complex rows through the split: sub-transforms with strided loads into the scratch, combine into `out`
+static int fft_rows_split(FftPlan* p, int R, const cplx* in, cplx* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
+                          int sign, double scale, cudaStream_t st) {
+    int rc = ensure_split(p, R);
+    if (rc) return rc;
+    const int n = p->d.n, m = n / R;
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(batch, ((int64_t)1 << 24) / n));
+    rc = ensure_work(p, (size_t)n * chunk);
+    if (rc) return rc;
+    for (int64_t r0 = 0; r0 < batch; r0 += chunk) {
+        const int64_t nb = std::min<int64_t>(chunk, batch - r0);
+        KERNEL_TAG("k_fft_rows_long", 32.0 * n * (double)nb);
+        rc = rows_reg_sub(p, in + r0 * in_pitch, p->work, R * nb, in_pitch, 1, R, n, m, 1, sign, 1.0, st);
+        if (rc) return rc;
+        rc = radix_step(false, p, p->work, out + r0 * out_pitch, nb, n, out_pitch, sign, scale, st);
+        if (rc) return rc;
+    }
+    return IPDE_OK;
+}
+// out = FFT(mul * IFFT(in)) / n for lines of length n = R m: split step, inverse sub-transforms with strided stores
+// (time order), forward sub-transforms reading time order with the multiplier applied on the loads, combine
+static int fft_mul_fft_rows_split(FftPlan* p, int R, const cplx* in, cplx* out, const double* mul, int64_t batch,
+                                  cudaStream_t st) {
+    int rc = ensure_split(p, R);
+    if (rc) return rc;
+    const int n = p->d.n, m = n / R;
+    rc = ensure_work(p, (size_t)2 * n * batch);
+    if (rc) return rc;
+    cplx* w0 = p->work;
+    cplx* w1 = p->work + (size_t)n * batch;
+    rc = radix_step(true, p, in, w0, batch, n, n, +1, 1.0, st);
+    if (rc) return rc;
+    KERNEL_TAG("k_fft_rows_long", 32.0 * n * (double)batch);
+    rc = rows_reg_sub(p, w0, w1, R * batch, n, m, 1, n, 1, R, +1, 1.0 / n, st);
+    if (rc) return rc;
+    KERNEL_TAG("k_fft_rows_long", 40.0 * n * (double)batch);
+    rc = rows_reg_sub(p, w1, w0, R * batch, n, 1, R, n, m, 1, -1, 1.0, st, mul, n);
+    if (rc) return rc;
+    return radix_step(false, p, w0, out, batch, n, n, -1, 1.0, st);
 }
 
 // r2c of rows of 2n reals (n = 2m complex): E_0 | E_1 sit in the first 2m slots of the output row; every thread
@@ -1174,6 +1294,10 @@ __global__ void k_scale_by_real(cplx* __restrict__ z, const double* __restrict__
 int fft_mul_fft_rows(FftPlan* p, const cplx* in, cplx* out, const double* m, int64_t batch, cudaStream_t st) {
     if (batch <= 0) return IPDE_OK;
     const int n = p->d.n;
+    if (g_fft_reg && p->fast) {
+        const int R = fft_split_radix(n);
+        if (R) return fft_mul_fft_rows_split(p, R, in, out, m, batch, st);
+    }
     if (!p->fast && !p->any && n <= IPDE_FFT_GENERIC_MAX) return fft_mul_fft_rows_generic(p, in, out, m, batch, st);
     if (n > IPDE_FFT_SMEM_MAX || !p->fast) {
         int rc = fft_lines_global(p, in, out, batch, n, 1, n, 1, +1, 1.0, st);

@@ -34,7 +34,8 @@ struct FftPlan {
     bool pow2 = false;            // radices 4 and 8 only (lean kernel instantiation)
     bool any = false;             // has a prime factor > 13: global-memory passes with an O(R^2) butterfly
     size_t work_elems = 0;
-    FftPlan* half = nullptr;      // plan of length n/2 for the split long-line path (n = 2m, m a register-kernel size)
+    FftPlan* half = nullptr;      // plan of length m = n/R for the split long-line path (m a register-kernel size)
+    int splitR = 0;               // R of that split (0: not split)
 };
 
 int fft_plan_create(int n, FftPlan** out);

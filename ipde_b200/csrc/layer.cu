@@ -22,8 +22,15 @@ __constant__ double c_k0_a[16];
 __constant__ double c_k0_b[16];
 __constant__ double c_k1_a[16];
 __constant__ double c_k1_b[16];
-static bool g_k0_ready = false;
-bool bessel_tables_ready() { return g_k0_ready; }
+// the K0/K1 tables live in __constant__ memory, i.e. once per device: the flag is per device too
+static bool g_k0_ready_dev[64] = {false};
+static bool k0_ready() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 0 && dev < 64 && g_k0_ready_dev[dev];
+}
+#define g_k0_ready k0_ready()
+bool bessel_tables_ready() { return k0_ready(); }
 
 int layer_set_k0_table(const double* cheb, const double* cheb1, int ncheb) {
     ARG_CHECK(ncheb >= 2 && ncheb <= K0_MAX_CHEB, "bad Chebyshev table length");
@@ -44,7 +51,9 @@ int layer_set_k0_table(const double* cheb, const double* cheb1, int ncheb) {
     CUDA_TRY(cudaMemcpyToSymbol(c_k0_b, b, sizeof(b)));
     CUDA_TRY(cudaMemcpyToSymbol(c_k1_a, a1, sizeof(a1)));
     CUDA_TRY(cudaMemcpyToSymbol(c_k1_b, b1, sizeof(b1)));
-    g_k0_ready = true;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64) g_k0_ready_dev[dev] = true;
     return IPDE_OK;
 }
 
@@ -159,17 +168,14 @@ __global__ void k_layer_reduce(const double* __restrict__ partial, int nchunks, 
     }
 }
 
-static double* g_partial = nullptr;
-static size_t g_partial_cap = 0;
-
-static int ensure_partial(size_t n) {
-    if (g_partial_cap >= n) return IPDE_OK;
-    cudaFree(g_partial);
-    g_partial = nullptr; g_partial_cap = 0;
-    CUDA_TRY(cudaMalloc(&g_partial, sizeof(double) * n));
-    g_partial_cap = n;
-    return IPDE_OK;
-}
+// per-call scratch from the stream-ordered allocator: no state shared between streams or devices
+struct PartialScratch {
+    double* ptr = nullptr;
+    cudaStream_t st;
+    explicit PartialScratch(cudaStream_t s) : st(s) {}
+    int get(size_t n) { CUDA_TRY(cudaMallocAsync(&ptr, sizeof(double) * n, st)); return IPDE_OK; }
+    ~PartialScratch() { if (ptr) cudaFreeAsync(ptr, st); }
+};
 
 static void choose_chunks(int64_t nsrc, int64_t ntrg, int* nchunks, int64_t* chunk_len) {
     const int64_t tblocks = cdiv(ntrg, LAYER_THREADS);
@@ -193,15 +199,17 @@ int layer_apply_scalar(int kind, double k, const double* sx, const double* sy, c
     if (kind == 1) ARG_CHECK(g_k0_ready, "K0 table not set (call ipde_set_k0_table)");
     int nchunks; int64_t chunk_len;
     choose_chunks(nsrc, ntrg, &nchunks, &chunk_len);
-    int rc = ensure_partial((size_t)nchunks * ntrg);
+    PartialScratch scratch(st);
+    int rc = scratch.get((size_t)nchunks * ntrg);
     if (rc) return rc;
+    double* partial = scratch.ptr;
     dim3 grid((unsigned)cdiv(ntrg, LAYER_THREADS), (unsigned)nchunks);
     if (kind == 0)
-        k_layer_scalar<0><<<grid, LAYER_THREADS, 0, st>>>(sx, sy, q, nsrc, tx, ty, ntrg, k, chunk_len, g_partial);
+        k_layer_scalar<0><<<grid, LAYER_THREADS, 0, st>>>(sx, sy, q, nsrc, tx, ty, ntrg, k, chunk_len, partial);
     else
-        k_layer_scalar<1><<<grid, LAYER_THREADS, 0, st>>>(sx, sy, q, nsrc, tx, ty, ntrg, k, chunk_len, g_partial);
+        k_layer_scalar<1><<<grid, LAYER_THREADS, 0, st>>>(sx, sy, q, nsrc, tx, ty, ntrg, k, chunk_len, partial);
     KERNEL_CHECK();
-    k_layer_reduce<<<(int)std::max<int64_t>(1, std::min<int64_t>(cdiv(ntrg, 256), 2048)), 256, 0, st>>>(g_partial, nchunks, ntrg, out, accumulate);
+    k_layer_reduce<<<(int)std::max<int64_t>(1, std::min<int64_t>(cdiv(ntrg, 256), 2048)), 256, 0, st>>>(partial, nchunks, ntrg, out, accumulate);
     KERNEL_CHECK();
     return IPDE_OK;
 }
@@ -215,12 +223,14 @@ int layer_apply_stokes(const double* sx, const double* sy, const double* fx, con
     }
     int nchunks; int64_t chunk_len;
     choose_chunks(nsrc, ntrg, &nchunks, &chunk_len);
-    int rc = ensure_partial((size_t)nchunks * 3 * ntrg);
+    PartialScratch scratch(st);
+    int rc = scratch.get((size_t)nchunks * 3 * ntrg);
     if (rc) return rc;
+    double* partial = scratch.ptr;
     dim3 grid((unsigned)cdiv(ntrg, LAYER_THREADS), (unsigned)nchunks);
-    k_layer_stokes<<<grid, LAYER_THREADS, 0, st>>>(sx, sy, fx, fy, nsrc, tx, ty, ntrg, chunk_len, g_partial);
+    k_layer_stokes<<<grid, LAYER_THREADS, 0, st>>>(sx, sy, fx, fy, nsrc, tx, ty, ntrg, chunk_len, partial);
     KERNEL_CHECK();
-    k_layer_reduce<<<(int)std::max<int64_t>(1, std::min<int64_t>(cdiv(3 * ntrg, 256), 2048)), 256, 0, st>>>(g_partial, nchunks, 3 * ntrg, out_uvp, accumulate);
+    k_layer_reduce<<<(int)std::max<int64_t>(1, std::min<int64_t>(cdiv(3 * ntrg, 256), 2048)), 256, 0, st>>>(partial, nchunks, 3 * ntrg, out_uvp, accumulate);
     KERNEL_CHECK();
     return IPDE_OK;
 }

@@ -71,14 +71,14 @@ def es_deconvolution(w, beta, n, fn):
     return 2.0/(w*I)
 
 
-_k0_table_set = False
+_k0_table_set = set()
 
 
 def ensure_k0_table():
-    """Chebyshev fits of sqrt(x) e^x K0(x) and sqrt(x) e^x K1(x) in t = 4/x - 1 on x >= 2, uploaded once
-    (csrc/bessel.cuh)."""
-    global _k0_table_set
-    if _k0_table_set:
+    """Chebyshev fits of sqrt(x) e^x K0(x) and sqrt(x) e^x K1(x) in t = 4/x - 1 on x >= 2, uploaded once per device
+    (constant memory, csrc/bessel.cuh)."""
+    dev = torch.cuda.current_device()
+    if dev in _k0_table_set:
         return
     nc = 36
     t, _ = np.polynomial.chebyshev.chebgauss(4*nc)
@@ -88,7 +88,7 @@ def ensure_k0_table():
     c0 = np.ascontiguousarray(c0, dtype=np.float64)
     c1 = np.ascontiguousarray(c1, dtype=np.float64)
     lib().ipde_set_k0_table(hptr(c0), hptr(c1), nc)
-    _k0_table_set = True
+    _k0_table_set.add(dev)
 
 
 class StageTimer(object):

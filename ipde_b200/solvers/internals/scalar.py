@@ -227,16 +227,19 @@ class ScalarHelper(object):
         if not hasattr(self, 'evaluator_w'):
             self.evaluator_w = None
             self.evaluator_r = None
-        if mode == 'ewald' and self.evaluator_r is None and self.curve_r is None:
+        if mode == 'ewald' and self.curve_r is None:
             from ...device import FreeSpaceEvaluator
             e = self.ebdy
             g, r = self.interface_qfs_g.source, self.interface_qfs_r.source
             x0, y0, h = float(grid.xv[0]), float(grid.yv[0]), float(grid.xh)
+            # a helper first used in a single-boundary collection and later reused in a larger one still needs the
+            # own-interface evaluator: created whenever it is missing, independent of evaluator_r
             if not single and self.evaluator_w is None:
                 self.evaluator_w = FreeSpaceEvaluator(self.kernel_kind, self.k, x0, y0, h, g.x, g.y,
                                                       points=(e.interface.x, e.interface.y))
-            self.evaluator_r = FreeSpaceEvaluator(self.kernel_kind, self.k, x0, y0, h, r.x, r.y,
-                                                  points=(e.radial_x.ravel(), e.radial_y.ravel()))
+            if self.evaluator_r is None:
+                self.evaluator_r = FreeSpaceEvaluator(self.kernel_kind, self.k, x0, y0, h, r.x, r.y,
+                                                      points=(e.radial_x.ravel(), e.radial_y.ravel()))
 
     # ---- small (1 x M) . (M, n) products; host arrays in, host arrays out (drop-in use)
     def get_boundary_values(self, ur):

@@ -29,7 +29,11 @@ class ModifiedHelmholtzSolver(ScalarSolver):
             return ModifiedHelmholtzHelper(ebdy, k=self.k, source_upsample_factor=self.source_upsample_factor,
                                            grid_backend=self.grid_backend, owned=owned)
         if c == 1:
-            return ModifiedHelmholtzHelper(ebdy, helper.annular_solver, k=self.k,
-                                           source_upsample_factor=self.source_upsample_factor,
-                                           grid_backend=self.grid_backend)
+            # a donor helper built with owned=False (boundary sharding) has no annular solver to lend
+            donor = getattr(helper, 'annular_solver', None)
+            return ModifiedHelmholtzHelper(ebdy, donor, k=self.k, source_upsample_factor=self.source_upsample_factor,
+                                           grid_backend=self.grid_backend, owned=owned)
+        if owned and not helper.owned:
+            return ModifiedHelmholtzHelper(ebdy, k=self.k, source_upsample_factor=self.source_upsample_factor,
+                                           grid_backend=self.grid_backend, owned=True)
         return helper

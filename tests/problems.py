@@ -103,7 +103,8 @@ def four_bodies_box(N, M=20, nb_outer=None, nb_small=None, bump=False, three=Fal
     BASELINE configs[2] / [4] at full scale: the geometry of examples/multi_modified_helmholtz.py:34-36 on its own box
     [-3.5, 3.5]^2 (interior star r = 3, a = 0.05, f = 7; exterior squished circle at (-1.2, -0.7); exterior star
     a = 0.2, f = 3 at (1, 0.5)) plus the 4th exterior body declared in SURVEY.md 8(d).3 (star x = -0.5, y = 1.5,
-    r = 0.6, a = 0.15, f = 4) on an N x N grid.  Boundary node counts default to 3N (outer) and 3N/4 (bodies), i.e.
+    r = 0.6, a = 0.15, f = 4) on an N x N grid.  Boundary node counts default to 3N (outer), 3N/4 (unit bodies) and
+    3N/8 (4th body), i.e.
     node spacing ~ grid spacing, with FFT-friendly lengths; the radial width is M grid cells.
     """
     L = 3.5
@@ -114,7 +115,7 @@ def four_bodies_box(N, M=20, nb_outer=None, nb_small=None, bump=False, three=Fal
     bdy1 = GSB(c=star(n1, r=3.0, a=0.05, f=7))
     bdy2 = GSB(c=squished_circle(n2, x=-1.2, y=-0.7, r=1.0, b=0.6, rot=-np.pi/4))
     bdy3 = GSB(c=star(n2, x=1.0, y=0.5, r=1.0, a=0.2, f=3))
-    bdy4 = GSB(c=star(max(n2*6//10, 16)//4*4, x=-0.5, y=1.5, r=0.6, a=0.15, f=4))
+    bdy4 = GSB(c=star(max(n2//2, 16), x=-0.5, y=1.5, r=0.6, a=0.15, f=4))
     bdys = [bdy1, bdy2, bdy3] if three else [bdy1, bdy2, bdy3, bdy4]
     MOL = SlepianMollifier(2*M)
     ebdys = [EmbeddedBoundary(b, b is bdy1, M, h, heaviside=MOL.step) for b in bdys]
@@ -123,3 +124,10 @@ def four_bodies_box(N, M=20, nb_outer=None, nb_small=None, bump=False, three=Fal
     if bump:
         ebdyc.ready_bump(MOL.bump, (L - ebdys[0].radial_width, L - ebdys[0].radial_width), ebdys[0].radial_width)
     return ebdyc
+
+
+def stokes_star_box(N, M=20, nb=None):
+    """BASELINE configs[3] at full scale: examples/interior_stokes_with_multi.py geometry (star a=0.1, f=5 in
+    [-pi/2, pi/2]^2, radial spacing 0.75 * grid spacing) on an N x N grid; nb defaults to 3N (node spacing ~ the
+    radial spacing, FFT-friendly)."""
+    return stokes_star(nb=3*N if nb is None else nb, M=M, ng=N)

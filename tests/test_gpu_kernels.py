@@ -22,7 +22,7 @@ def D():
 
 
 @pytest.mark.parametrize('n', [8, 60, 64, 79, 96, 100, 256, 474, 512, 1000, 1022, 1024, 1430, 2048, 4096, 7168, 8192,
-                               30030])
+                               30030, 768, 1536, 3072, 6144, 12288, 24576, 49152, 16384, 32768, 65536, 98304])
 def test_fft_c2c(D, n):
     rng = np.random.default_rng(n)
     x = rng.standard_normal((3, n)) + 1j*rng.standard_normal((3, n))
@@ -37,7 +37,8 @@ def test_fft_c2c(D, n):
     assert rel(xd.cpu().numpy(), np.fft.fft(x)) < 1e-14*np.log2(n)
 
 
-@pytest.mark.parametrize('n', [96, 256, 474, 512, 1024, 2048, 4096, 8192, 9000])
+@pytest.mark.parametrize('n', [96, 256, 474, 512, 1024, 2048, 4096, 8192, 9000, 768, 3072, 6144, 12288, 16384, 24576,
+                               49152])
 def test_fft_mul_fft(D, n):
     rng = np.random.default_rng(n)
     x = rng.standard_normal((5, n)) + 1j*rng.standard_normal((5, n))

@@ -149,3 +149,27 @@ def test_oracle_dirichlet_correction_poisson():
     qb = Laplace_QFS(e.bdy, True, True, False, tol=1e-12, b2c=False, device_build=False)
     u = OracleDirichletCorrection(ebdyc, 'poisson', 0.0, [qb])(uo, BoundaryFunction(ebdyc, function=sol))
     assert np.abs(u - np.asarray(ua)).max() < 2e-7        # 2.6e-8 at this resolution
+
+
+def test_fast_oracle_matches_direct_oracle():
+    """oracle/fast.py (FFT-based NUFFT + spectral-Ewald sums, the CPU baseline of bench.py) against the direct
+    statement (NUDFT + all-pairs sums) on the same inputs"""
+    from problems import three_bodies, manufactured
+    from oracle.solvers import OracleScalarSolver, nudft2d_type2
+    from oracle.fast import FastScalarSolver, nufft2d2
+    from ipde_b200.qfs import Modified_Helmholtz_QFS
+    rng = np.random.default_rng(0)
+    fh = rng.standard_normal((2, 48, 40)) + 1j*rng.standard_normal((2, 48, 40))
+    x, y = rng.uniform(0, 2*np.pi, 50), rng.uniform(0, 2*np.pi, 50)
+    ref = nudft2d_type2(fh, x, y)
+    assert np.abs(nufft2d2(fh, x, y) - ref).max() < 1e-13*np.abs(ref).max()
+    ebdyc = three_bodies(nb=80, M=8)
+    k = 5.0
+    f, ua, _ = manufactured(ebdyc, k, kk=10*np.pi/7)
+    pairs = [(Modified_Helmholtz_QFS(e.interface, e.interior, True, True, k, tol=1e-12, u2s=False, device_build=False),
+              Modified_Helmholtz_QFS(e.interface, not e.interior, True, True, k, tol=1e-12, device_build=False))
+             for e in ebdyc]
+    gm = dict(tol=1e-13, restart=60, maxiter=5)
+    uo = OracleScalarSolver(ebdyc, 'modified_helmholtz', k, 'spectral', pairs)(f, **gm)
+    uf = FastScalarSolver(ebdyc, 'modified_helmholtz', k, pairs, workers=2)(f, **gm)
+    assert np.abs(uf - uo).max() < 1e-12*np.abs(uo).max()
