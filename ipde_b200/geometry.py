@@ -118,6 +118,37 @@ def fourier_resample_matrix(N, n):
     return fourier_resample(np.eye(N), n)
 
 
+def arc_length_parameterize(x, y, tol=1e-14, maxiter=50):
+    """
+    Resample a closed curve at equal arc-length increments (personal_utilities.arc_length_reparametrization.
+    arc_length_parameterize as the reference's examples use it, e.g. examples/interior_stokes_with_multi.py:54-55:
+    `bdy = GSB(*arc_length_parameterize(bdy.x, bdy.y))`).  Spectral: arc length from the Fourier series of the speed,
+    Newton iteration for the parameters, trigonometric interpolation of the curve.  Returns (x, y).
+    """
+    c = np.asarray(x, dtype=float) + 1j*np.asarray(y, dtype=float)
+    N = c.size
+    k = np.fft.fftfreq(N, 1.0/N)
+    ch = np.fft.fft(c)/N
+    sp = np.abs(np.fft.ifft(np.fft.fft(c)*1j*k))
+    sh = np.fft.fft(sp)/N
+    nz = k != 0
+    def L(t):
+        E = np.exp(1j*np.outer(t, k[nz]))
+        return (sh[0]*t + ((E - 1.0)*(sh[nz]/(1j*k[nz]))).sum(axis=1)).real
+    def S(t):
+        return (np.exp(1j*np.outer(t, k)).dot(sh)).real
+    total = 2*np.pi*sh[0].real
+    target = total*np.arange(N)/N
+    t = 2*np.pi*np.arange(N)/N
+    for _ in range(maxiter):
+        dt = (L(t) - target)/S(t)
+        t = t - dt
+        if np.abs(dt).max() < tol:
+            break
+    cn = np.exp(1j*np.outer(t, k)).dot(ch)
+    return cn.real.copy(), cn.imag.copy()
+
+
 class Grid(object):
     """
     Uniform tensor grid, following pybie2d.grid.Grid as the reference uses it

@@ -252,6 +252,31 @@ class StructuredOperator(object):
         return (np.fft.ifft(buf, axis=1)*M).real
 
 
+def _solve_deflated(Es, R, null_tol=1e-9):
+    """
+    Solve Es Y = R when Es may have ONE null direction (Stokes: a uniform normal force on a closed curve generates no
+    velocity; the window holding the lowest modes sees it).  The null pair (u, v) comes from two steps of inverse
+    iteration on the LU factors; Es + s1 u v^H is then well conditioned and its LU solve equals the pseudo-inverse
+    solution up to a multiple of the field-free vector v.  An SVD-based pseudo-inverse would smear cond * eps of
+    round-off over every row of the window and defeat the band truncation.
+    """
+    n = Es.shape[0]
+    LU, piv = torch.linalg.lu_factor(Es)
+    g = torch.Generator(device='cpu').manual_seed(7)
+    def null_vec(adjoint):
+        x = torch.randn(n, 1, dtype=torch.float64, generator=g).to(Es.device).to(Es.dtype)
+        for _ in range(3):
+            x = torch.linalg.lu_solve(LU, piv, x, adjoint=adjoint)
+            x = x/torch.linalg.vector_norm(x)
+        return x
+    v = null_vec(False)
+    s1 = float(Es.abs().sum(dim=1).max())
+    if float(torch.linalg.vector_norm(Es @ v)) > null_tol*s1:
+        return torch.linalg.lu_solve(LU, piv, R)
+    u = null_vec(True)
+    return torch.linalg.solve(Es + s1*(u @ v.conj().T), R)
+
+
 def _solve_windows(Eb, Cb_list, J, Ks, h_in, col_block, Bw, scale_r, scale_c, pinv_low=False, svd_cut=1e-13):
     """
     X = E^-1 [C_1 | C_2 ...] column block by column block from windows of the banded system.
@@ -288,9 +313,7 @@ def _solve_windows(Eb, Cb_list, J, Ks, h_in, col_block, Bw, scale_r, scale_c, pi
             rhs.append(C*sr[:, None])
         R = torch.cat(rhs, dim=1)
         if pinv_low and lo <= 0 <= hi:
-            U, S, Vh = torch.linalg.svd(Es, full_matrices=False)
-            keep = S > svd_cut*S[0]
-            Y = (Vh.conj().T[:, keep]*(1.0/S[keep])[None, :]) @ (U.conj().T[keep] @ R)
+            Y = _solve_deflated(Es, R)
         else:
             Y = torch.linalg.solve(Es, R)
         Y = Y*sc_[:, None]
@@ -326,7 +349,9 @@ def _significant(X, Bx, Ks, att, tol, far):
     mag = X.abs().amax(dim=(0, 1))*a                                     # (2Bx+1, ncol)
     ring = (p.abs() >= far) & (p.abs() <= (4*far)//3)
     floor = mag[ring].amax(dim=0, keepdim=True)
-    return mag > torch.maximum(tol*mag.amax(dim=0, keepdim=True), 4.0*floor)
+    # ... and is not negligible against the largest gain of the whole operator (a column whose exact content is zero,
+    # e.g. the double layer of a constant density on the exterior side, is round-off from top to bottom)
+    return (mag > torch.maximum(tol*mag.amax(dim=0, keepdim=True), 4.0*floor)) & (mag > tol*mag.max())
 
 
 def _choose(sig, Bx, Ks, h_in, KL_candidates):

@@ -494,3 +494,108 @@ def test_poisson_single_boundary_structured_qfs_vs_oracle():
     uo = oracle_for(solver, 'poisson', 0.0, 'spectral')(f, tol=1e-13, restart=40, maxiter=5)
     linf, l2 = rel_errors(ue, uo)
     assert linf < TOL and l2 < TOL, (linf, l2)
+
+
+def _fit_order(ns, errs):
+    """least-squares slope of log(err) against n (spectral convergence: err ~ exp(-c n)) -> decay rate c"""
+    return -np.polyfit(np.asarray(ns, dtype=float), np.log(np.asarray(errs)), 1)[0]
+
+
+def test_convergence_sweep_modified_helmholtz():
+    """examples/interior_modified_helmholtz_using_multi.py:22-26 -- the published M=16 error curve errs16 (k=2 star,
+    grid spacing = half the boundary spacing) at five resolutions: every error within 3x of the published value and
+    the fitted exponential decay rate within 10 % of the published one."""
+    from ipde_b200.solvers.multi_boundary.modified_helmholtz import ModifiedHelmholtzSolver
+    from ipde_b200.qfs import Modified_Helmholtz_QFS
+    import ipde_b200.device as D
+    published = {400: 5.16e-6, 500: 3.61e-8, 600: 1.33e-9, 700: 1.30e-10, 800: 1.51e-11}
+    got = {}
+    for nb in sorted(published):
+        bh = 2*np.pi/nb*0.9*0.999            # dt * min speed of the a=0.1, f=5 star (speed >= 0.9)
+        ng = 2*int(1.0*2.4//bh)              # :67 of the example: two grid cells per boundary spacing
+        ebdyc = single_star(nb=nb, M=16, ng=ng)
+        f, ua, sol = manufactured(ebdyc, 2.0)
+        solver = ModifiedHelmholtzSolver(ebdyc, 2.0)
+        ue = solver(f, tol=1e-14, restart=60, maxiter=5)
+        bdy = ebdyc[0].bdy
+        qb = Modified_Helmholtz_QFS(bdy, True, True, True, 2.0, tol=1e-13)
+        sig = qb.u2s(sol(bdy.x, bdy.y) - solver.get_boundary_values(ue)[0])
+        pts = ebdyc.grid_and_radial_pts
+        corr = D.layer_apply_scalar(1, 2.0, D.to_dev(qb.source.x), D.to_dev(qb.source.y),
+                                    D.to_dev(sig*qb.source.weights), D.to_dev(pts.x), D.to_dev(pts.y)).cpu().numpy()
+        got[nb] = np.abs(np.asarray(ue) + corr - np.asarray(ua)).max()
+    ns = sorted(published)
+    print('MH errs16 sweep:', {n: '%.2e (published %.2e)' % (got[n], published[n]) for n in ns})
+    for n in ns:
+        assert got[n] < 3.0*published[n], (n, got[n], published[n])
+    r_got, r_pub = _fit_order(ns, [got[n] for n in ns]), _fit_order(ns, [published[n] for n in ns])
+    assert abs(r_got - r_pub) < 0.1*r_pub, (r_got, r_pub)
+
+
+def test_convergence_sweep_stokes():
+    """examples/interior_stokes_with_multi.py:46-75 -- published velocity errors errs_U of the single-star Stokes problem
+    (arc-length reparametrised star, ng = nb/2, M = min(20, 4 nb/100), radial spacing 0.75 grid spacing, Slepian
+    parameter 1.5 M) at five resolutions, each within 3x of the published value, decay rate within 10 %."""
+    from problems import stokes_manufactured
+    from ipde_b200.geometry import GSB, Grid, star, arc_length_parameterize
+    from ipde_b200.embedded_boundary import EmbeddedBoundary
+    from ipde_b200.ebdy_collection import EmbeddedBoundaryCollection
+    from ipde_b200.slepian import SlepianMollifier
+    from ipde_b200.solvers.multi_boundary.stokes import StokesSolver
+    from ipde_b200.qfs import Stokes_QFS
+    published_U = {200: 1.91e-04, 300: 6.65e-07, 400: 7.98e-09, 500: 9.74e-11, 600: 1.52e-12}
+    published_its = {200: 28, 300: 29, 400: 30, 500: 31, 600: 24}
+    got, its = {}, {}
+    for nb in sorted(published_U):
+        M = min(20, max(4, 4*int(nb/100)))
+        bdy = GSB(c=star(nb, a=0.1, f=5))
+        bdy = GSB(*arc_length_parameterize(bdy.x, bdy.y))
+        ng = int(nb/2)
+        Lb = np.pi/2
+        grid = Grid([-Lb, Lb], ng, [-Lb, Lb], ng)
+        MOL = SlepianMollifier(int(1.5*M))
+        ebdy = EmbeddedBoundary(bdy, True, M, grid.xh*0.75, heaviside=MOL.step)
+        ebdyc = EmbeddedBoundaryCollection([ebdy])
+        ebdyc.register_grid(grid)
+        ebdyc.ready_bump(MOL.bump, (Lb - ebdy.radial_width, Lb - ebdy.radial_width), ebdy.radial_width)
+        fu, fv, ua, va, pa, (u_f, v_f, p_f) = stokes_manufactured(ebdyc)
+        solver = StokesSolver(ebdyc)
+        u, v, p = solver(fu, fv, tol=1e-14, restart=50, maxiter=4)
+        its[nb] = solver.iteration_counts[0]
+        bu = solver.helpers[0].get_boundary_values(u[0])
+        bv = solver.helpers[0].get_boundary_values(v[0])
+        qb = Stokes_QFS(bdy, True, True, True, tol=1e-13)
+        sig = qb.u2s(np.concatenate([u_f(bdy.x, bdy.y) - bu, v_f(bdy.x, bdy.y) - bv])).reshape(2, -1)
+        pts = ebdyc.grid_and_radial_pts
+        cu, cv, cp = solver.Layer_Apply(qb.source, pts, sig)
+        eu = np.abs(np.asarray(u) + cu - np.asarray(ua)).max()
+        ev = np.abs(np.asarray(v) + cv - np.asarray(va)).max()
+        got[nb] = max(eu, ev)
+    ns = sorted(published_U)
+    print('Stokes errs_U sweep:', {n: '%.2e (published %.2e), %d its (published %d)' % (got[n], published_U[n], its[n],
+                                                                                       published_its[n]) for n in ns})
+    for n in ns:
+        assert got[n] < 3.0*published_U[n], (n, got[n], published_U[n])
+    r_got = _fit_order(ns, [got[n] for n in ns])
+    r_pub = _fit_order(ns, [published_U[n] for n in ns])
+    assert abs(r_got - r_pub) < 0.1*r_pub, (r_got, r_pub)
+
+
+def test_stokes_structured_qfs_vs_oracle():
+    """Stokes solve with the structured (Fourier-banded) QFS operators and curve operators (n_b = 1024) against the
+    CPU oracle, which applies the same QFS objects in NumPy and sums all stokeslets directly"""
+    from problems import stokes_star, stokes_manufactured
+    from ipde_b200.solvers.multi_boundary.stokes import StokesSolver
+    ebdyc = stokes_star(nb=1024, M=10, ng=256)
+    fu, fv, ua, va, pa, _ = stokes_manufactured(ebdyc)
+    solver = StokesSolver(ebdyc)
+    h = solver.helpers[0]
+    assert getattr(h.interface_qfs_g, 'structured', False) and h.curve_r is not None
+    gm = dict(tol=1e-13, restart=60, maxiter=4)
+    u, v, p = solver(fu, fv, **gm)
+    uo, vo, po = vector_oracle_for(solver, 'spectral')(fu, fv, **gm)
+    scale = max(np.abs(uo).max(), np.abs(vo).max())
+    errs = [np.abs(np.asarray(u) - uo).max()/scale, np.abs(np.asarray(v) - vo).max()/scale,
+            np.abs(np.asarray(p) - po).max()/np.abs(po).max()]
+    print('Stokes nb=1024 structured QFS vs oracle: u %.2e v %.2e p %.2e' % tuple(errs))
+    assert max(errs[:2]) < TOL and errs[2] < 1e-10, errs
