@@ -947,6 +947,60 @@ static int launch_rows_reg_sub(FftPlan* ph, const cplx* in, cplx* out, int64_t n
     return IPDE_OK;
 }
 
+// c2r of rows of 2n reals, n = 2m: the tangle step (half spectrum X[0..n] -> packed spectrum Z) and the radix-2
+// split (A = Z[k] + Z[k+m], B = (Z[k] - Z[k+m]) conj(w^k)) are applied on the loads of the m-point inverse transform;
+// sub-line r = 0 / 1 of a row produces the even / odd packed samples, stored with element stride 2.
+template <int N>
+__global__ void __launch_bounds__(RegGeom<N>::NT, RegGeom<N>::MINB)
+k_c2r_rows_long(const cplx* __restrict__ tw, const cplx* __restrict__ twn, const cplx* __restrict__ half_tw,
+                const cplx* __restrict__ in, cplx* out, int64_t nsub, int64_t in_pitch, int64_t out_pitch, double scale) {
+    using G = RegGeom<N>;
+    using K = RegCfg<N>;
+    extern __shared__ cplx smem[];
+    constexpr int m = N, n = 2 * N;
+    const int tid = threadIdx.x;
+    const int l = tid >> G::LOGT, jt = tid & (G::T - 1);
+    cplx* line = smem + l * G::LINE;
+    const int64_t sub = (int64_t)blockIdx.x * G::L + l;
+    const bool live = sub < nsub;
+    const int64_t row = (live ? sub : 0) >> 1;
+    const int r = (int)(sub & 1);
+    const cplx* src = in + row * in_pitch;
+    cplx v[G::EPT];
+#pragma unroll
+    for (int s = 0; s < G::EPT; ++s) {
+        const int k = reg_elem<N, K::R0>(jt, s);
+        if (live) {
+            // Z[kk] = E + i O,  E = (X[kk] + conj X[n-kk])/2,  O = (X[kk] - conj X[n-kk])/2 * conj(half_tw[kk])
+            const cplx x0 = src[k], c0 = cconj(src[n - k]);
+            const cplx x1 = src[k + m], c1 = cconj(src[m - k]);
+            const cplx z0 = cadd(cscale(cadd(x0, c0), 0.5), cmuli(cmulc(cscale(csub(x0, c0), 0.5), half_tw[k])));
+            const cplx z1 = cadd(cscale(cadd(x1, c1), 0.5), cmuli(cmulc(cscale(csub(x1, c1), 0.5), half_tw[k + m])));
+            v[s] = (r == 0) ? cadd(z0, z1) : cmulc(csub(z0, z1), twn[k]);
+        } else {
+            v[s] = make_double2(0.0, 0.0);
+        }
+    }
+    reg_fft<N, +1, false>(v, line, jt, tw);
+    if (live) {
+        cplx* dst = out + row * out_pitch + r;
+#pragma unroll
+        for (int s = 0; s < G::EPT; ++s) dst[(int64_t)reg_elem<N, G::RLAST>(jt, s) * 2] = cscale(v[s], scale);
+    }
+}
+template <int N>
+static int launch_c2r_long(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
+                           double scale, cudaStream_t st) {
+    using G = RegGeom<N>;
+    int rc = set_smem(k_c2r_rows_long<N>, G::SMEM);
+    if (rc) return rc;
+    const unsigned g = (unsigned)cdiv(2 * batch, (int64_t)G::L);
+    k_c2r_rows_long<N><<<g, G::NT, G::SMEM, st>>>(p->half->d.tw, p->d.tw, p->half_tw_dev, in, reinterpret_cast<cplx*>(out),
+                                                  2 * batch, in_pitch, out_pitch / 2, scale);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+
 static bool fft_split_size(int n) { return n % 2 == 0 && fft_reg_size(n / 2) && n / 2 >= 4096; }
 // smallest R <= 16 with n / R a register-kernel length (3*2^k lines, power-of-two lines longer than 8192)
 static int fft_split_radix(int n) {
@@ -1100,27 +1154,6 @@ __global__ void k_r2c_untangle_split(int m, const cplx* __restrict__ twn, const 
         }
     }
 }
-// c2r of rows of 2n reals: spectrum X[0..n] -> A | B sub-lines (2m slots) of the work row
-__global__ void k_c2r_tangle_split(int m, const cplx* __restrict__ twn, const cplx* __restrict__ half_tw, const cplx* __restrict__ in,
-                                   cplx* __restrict__ z, int64_t batch, int64_t in_pitch, int64_t z_pitch) {
-    const int n = 2 * m;
-    const int64_t total = batch * m;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = i / m;
-        const int k = (int)(i % m);
-        const cplx* src = in + row * in_pitch;
-        auto Z = [&](int kk) {                                    // packed-transform entry kk < n from X[kk], X[n - kk]
-            const cplx xk = src[kk];
-            const cplx xc = cconj(src[n - kk]);
-            const cplx E = cscale(cadd(xk, xc), 0.5);
-            const cplx O = cmulc(cscale(csub(xk, xc), 0.5), half_tw[kk]);
-            return cadd(E, cmuli(O));
-        };
-        const cplx z0 = Z(k), z1 = Z(k + m);
-        z[row * z_pitch + k] = cadd(z0, z1);
-        z[row * z_pitch + m + k] = cmulc(csub(z0, z1), twn[k]);
-    }
-}
 // Global-memory versions of the pack / unpack steps for long rows
 __global__ void k_r2c_untangle(int n, const cplx* __restrict__ half_tw, const cplx* __restrict__ z, cplx* __restrict__ out,
                                int64_t batch, int64_t z_pitch, int64_t out_pitch) {
@@ -1210,22 +1243,9 @@ int fft_c2r_rows(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t
         int rc = ensure_half(p);
         if (rc) return rc;
         const int m = n / 2;
-        // row chunks bound the scratch (A | B sub-lines) to 256 MB
-        const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(batch, ((int64_t)1 << 24) / n));
-        rc = ensure_work(p, (size_t)n * chunk);
-        if (rc) return rc;
-        for (int64_t r0 = 0; r0 < batch; r0 += chunk) {
-            const int64_t nb = std::min<int64_t>(chunk, batch - r0);
-            const int blocks = (int)std::min<int64_t>(cdiv(nb * m, 256), (int64_t)ipde_num_sms() * 16);
-            KERNEL_TAG("k_c2r_tangle_split", 32.0 * n * (double)nb);
-            k_c2r_tangle_split<<<blocks, 256, 0, st>>>(m, p->d.tw, p->half_tw_dev, in + r0 * in_pitch, p->work, nb, in_pitch, n);
-            KERNEL_CHECK();
-            KERNEL_TAG("k_c2r_rows_long", (16.0 * n + 16.0 * (n + 1)) * (double)nb);
-            rc = rows_reg_sub(p, p->work, reinterpret_cast<cplx*>(out + r0 * out_pitch), 2 * nb, n, m, 1, out_pitch / 2, 1, 2,
-                              +1, scale, st);
-            if (rc) return rc;
-        }
-        return IPDE_OK;
+        KERNEL_TAG("k_c2r_rows_long", (16.0 * n + 16.0 * (n + 1)) * (double)batch);
+        if (m == 4096) return launch_c2r_long<4096>(p, in, out, batch, in_pitch, out_pitch, scale, st);
+        return launch_c2r_long<8192>(p, in, out, batch, in_pitch, out_pitch, scale, st);
     }
     if (n > IPDE_FFT_SMEM_MAX || !p->fast) {
         int rc = ensure_work(p, (size_t)3 * n * batch);

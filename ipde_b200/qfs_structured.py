@@ -274,7 +274,9 @@ def _solve_deflated(Es, R, null_tol=1e-9):
     if float(torch.linalg.vector_norm(Es @ v)) > null_tol*s1:
         return torch.linalg.lu_solve(LU, piv, R)
     u = null_vec(True)
-    return torch.linalg.solve(Es + s1*(u @ v.conj().T), R)
+    Y = torch.linalg.solve(Es + s1*(u @ v.conj().T), R)
+    # remove the field-free component: the minimum-norm (pseudo-inverse) solution, localised like the rest of E^-1
+    return Y - v @ (v.conj().T @ Y)
 
 
 def _solve_windows(Eb, Cb_list, J, Ks, h_in, col_block, Bw, scale_r, scale_c, pinv_low=False, svd_cut=1e-13):
@@ -391,7 +393,12 @@ def _fill(X, Bx, Ks, h_in, KL, BH):
     pi = (pb + Bx)[:, None].expand_as(src_k)
     ci = src_k.clamp(-h_in, h_in) + h_in
     band = X[:, :, pi, ci]*ok[None, None]
-    return low, band.contiguous()
+    # The operators map real densities to real strengths: Q(-k, -k') = conj Q(k, k').  Enforce it exactly -- the device
+    # apply packs two real outputs into one complex spectrum and relies on it, and the deflated Stokes solve adds a
+    # complex multiple of the (field-free) null vector, whose imaginary part must not reach the other component.
+    low = 0.5*(low + low.flip(2, 3).conj())
+    band = 0.5*(band + band.flip(2, 3).conj())
+    return low.contiguous(), band.contiguous()
 
 
 class CurveOperator(object):
