@@ -258,6 +258,54 @@ def run_slab(args, world, rank, barrier):
             'max_abs_error_vs_single_gpu_solve': float(err[0]), 'relative': float(err[0]/err[1])}
 
 
+def run_stokes(args, N, barrier):
+    """BASELINE configs[3]: examples/interior_stokes_with_multi.py (star a=0.1 f=5 in [-pi/2, pi/2]^2, radial spacing
+    0.75 grid spacing, M=20) at N^2: one Stokes solve = N^2 grid-point-solves (three fields out)."""
+    import torch
+    from problems import stokes_star_box, stokes_manufactured
+    from ipde_b200.device import to_dev
+    from ipde_b200.solvers.multi_boundary.stokes import StokesSolver
+    t0 = time.perf_counter()
+    ebdyc = stokes_star_box(N, M=RADIAL_M)
+    fu, fv, ua, va, pa, _ = stokes_manufactured(ebdyc)
+    t_geom = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    solver = StokesSolver(ebdyc)
+    torch.cuda.synchronize()
+    t_solver = time.perf_counter() - t0
+    gm = dict(tol=1e-12, restart=50, maxiter=4)
+    fu_d, fv_d = to_dev(np.asarray(fu)), to_dev(np.asarray(fv))
+    for _ in range(3):
+        solver.solve_device(fu_d, fv_d, **gm)
+    barrier()
+    steps = max(3, min(args.steps, 10))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        solver.solve_device(fu_d, fv_d, **gm)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)/steps
+    t0 = time.perf_counter()
+    for _ in range(3):
+        u, v, p = solver(fu, fv, **gm)
+    torch.cuda.synchronize()
+    e2e = (time.perf_counter() - t0)/3
+    out = {'workload': 'interior_stokes_with_multi (BASELINE configs[3]): %d^2 grid on [-pi/2,pi/2]^2, star n_b=%d, M=%d, '
+                       'spectral interface interpolation, annular Stokes GMRES tol 1e-12' % (N, ebdyc[0].bdy.N, RADIAL_M),
+           'grid': [N, N], 'steps': steps, 'ms_per_step': ms, 'value': N*N/(ms*1e-3), 'unit': 'grid-point-solves/s',
+           'e2e': {'value': N*N/e2e, 'ms_per_step': e2e*1e3, 'h2d_bytes_per_step': int(2*np.asarray(fu).nbytes),
+                   'd2h_bytes_per_step': int(3*np.asarray(fu).nbytes)},
+           'gmres_iterations': solver.iteration_counts,
+           'setup_s': {'geometry_and_registration': t_geom, 'solver_constructor': t_solver},
+           'algorithmic_bytes_per_point': 168.0,
+           'core_frac_of_peak': 168.0*N*N/(ms*1e-3)/1e9/measured_peak_gbs()[0],
+           'peak_device_memory_gb': torch.cuda.max_memory_allocated()/1e9}
+    del solver
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -271,6 +319,7 @@ def main():
                     help='grid size of the slab-decomposed (all ranks, one problem) grid-solve timing; 0 = skip')
     ap.add_argument('--slab-chunks', type=int, default=4)
     ap.add_argument('--slab-steps', type=int, default=20)
+    ap.add_argument('--stokes-grid', type=int, default=8192, help='grid of the Stokes line (BASELINE configs[3]); 0 = skip')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -369,6 +418,12 @@ def main():
             slab = run_slab(args, world, rank, barrier)
         except Exception as exc:          # the headline numbers above are already reduced over the ranks
             slab = {'error': '%s: %s' % (type(exc).__name__, exc)}
+    stokes = None
+    if args.stokes_grid > 0 and world == 1:
+        try:
+            stokes = run_stokes(args, min(args.stokes_grid, N), barrier)
+        except Exception as exc:
+            stokes = {'error': '%s: %s' % (type(exc).__name__, exc)}
     ms_total, e2e_ms = float(times[0]), float(times[1])
     ms_per_step = ms_total/args.steps
     value = world*npts*args.steps/(ms_total*1e-3)
@@ -422,6 +477,8 @@ def main():
                 'roofline': roofline}
         if slab is not None:
             line['slab_grid_solve'] = slab
+        if stokes is not None:
+            line['stokes'] = stokes
         if not args.no_cpu_baseline and world == 1:
             info = cpu_lines(args.cpu_sample_n, steps=1, warmup=0, both=True)
             line['cpu_baseline'] = {'value': info['threaded']['rate'], 'unit': 'grid-point-solves/s',

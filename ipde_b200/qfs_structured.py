@@ -356,7 +356,7 @@ def _significant(X, Bx, Ks, att, tol, far):
     return (mag > torch.maximum(tol*mag.amax(dim=0, keepdim=True), 4.0*floor)) & (mag > tol*mag.max())
 
 
-def _choose(sig, Bx, Ks, h_in, KL_candidates):
+def _choose(sig, Bx, Ks, h_in, KL_candidates, bh_cap=None):
     """two-tier storage (dense low block |k|,|k'| <= KL, band half-width BH elsewhere) of least size"""
     dev = sig.device
     p = torch.arange(-Bx, Bx + 1, device=dev)
@@ -369,6 +369,8 @@ def _choose(sig, Bx, Ks, h_in, KL_candidates):
         inlow = (k.abs() <= KL) & (kp.abs()[None, :] <= KL)
         rest = sig & ~inlow
         BH = int(pa[rest].max().item()) if bool(rest.any()) else 0
+        if bh_cap is not None:
+            BH = min(BH, bh_cap)
         cost = (2*KL + 1)**2 + (2*Ks + 1)*(2*BH + 1)
         if best is None or cost < best[0]:
             best = (cost, KL, BH)
@@ -599,7 +601,11 @@ class StructuredQFS(object):
         sig = _significant(Xs[0], Bx, Ks, att, 1e-15, far)
         for X in Xs[1:]:
             sig |= _significant(X, Bx, Ks, att, 1e-15, far)
-        KL, BH = _choose(sig, Bx, Ks, h_in, KLc)
+        # the band never needs to be wider than the bands of the operators it is built from (W): what lies beyond
+        # is the tail of the windowed inverse, at or below 1e-13 of the column (tests/test_gpu_kernels.py)
+        import os
+        cap = int(os.environ.get('IPDE_QFS_BH_CAP', self.W))
+        KL, BH = _choose(sig, Bx, Ks, h_in, KLc, bh_cap=cap if cap > 0 else None)
         parts = [_fill(X, Bx, Ks, h_in, KL, BH) for X in Xs]
         low = torch.cat([p[0] for p in parts], dim=1)
         band = torch.cat([p[1] for p in parts], dim=1)

@@ -131,3 +131,22 @@ def stokes_star_box(N, M=20, nb=None):
     [-pi/2, pi/2]^2, radial spacing 0.75 * grid spacing) on an N x N grid; nb defaults to 3N (node spacing ~ the
     radial spacing, FFT-friendly)."""
     return stokes_star(nb=3*N if nb is None else nb, M=M, ng=N)
+
+
+def interior_star_box(ng, M=16, helmholtz_k=2.0):
+    """BASELINE configs[1]: examples/interior_modified_helmholtz.py scaled up -- one star (a=0.1, f=5) in [-1.2, 1.2]^2
+    on an ng x ng grid, boundary spacing matched to the grid spacing (nb = 2 ng), manufactured forcing of :49-52.
+    Returns (ebdyc, f, nb)."""
+    nb = 2*ng
+    bdy = GSB(c=star(nb, a=0.1, f=5))
+    bh = bdy.dt*bdy.speed.min()
+    grid = Grid([-1.2, 1.2], ng, [-1.2, 1.2], ng)
+    MOL = SlepianMollifier(2*M)
+    ebdy = EmbeddedBoundary(bdy, True, M, bh, heaviside=MOL.step)
+    ebdyc = EmbeddedBoundaryCollection([ebdy])
+    ebdyc.register_grid(grid)
+    kk = np.pi/3
+    sol = lambda x, y: np.exp(np.sin(kk*x))*np.sin(kk*y)
+    force = lambda x, y: helmholtz_k**2*sol(x, y) - \
+        kk**2*np.exp(np.sin(kk*x))*np.sin(kk*y)*(np.cos(kk*x)**2 - np.sin(kk*x) - 1.0)
+    return ebdyc, EmbeddedFunction(ebdyc, function=force), nb

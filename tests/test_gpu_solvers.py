@@ -200,13 +200,13 @@ def test_full_size_properties_1024():
     """BASELINE configs[1] at 1024^2 (n_b = 2048, M = 16), where the oracle is out of reach: size-independent
     properties -- the two evaluation back-ends agree, the solve is linear and deterministic, and the solution
     (after the homogeneous Dirichlet correction) reproduces the analytic one."""
-    import bench
     import torch
+    from problems import interior_star_box
     from ipde_b200.solvers.multi_boundary.modified_helmholtz import ModifiedHelmholtzSolver
     from ipde_b200.qfs import Modified_Helmholtz_QFS
     import ipde_b200.device as D
-    ebdyc, f, nb = bench.build_problem(1024)
-    k = bench.HELMHOLTZ_K
+    k = 2.0
+    ebdyc, f, nb = interior_star_box(1024, M=16, helmholtz_k=k)
     kw = dict(tol=1e-13, restart=50, maxiter=10)
     s_e = ModifiedHelmholtzSolver(ebdyc, k, grid_backend='ewald')
     s_d = ModifiedHelmholtzSolver(ebdyc, k, grid_backend='direct', helpers=s_e.helpers)
