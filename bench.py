@@ -286,9 +286,10 @@ def run_stokes(args, N, barrier):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)/steps
+    uvp = solver(fu, fv, **gm)
     t0 = time.perf_counter()
     for _ in range(3):
-        u, v, p = solver(fu, fv, **gm)
+        uvp = solver(fu, fv, out=uvp, **gm)        # host in, host out; result arrays reused across steps
     torch.cuda.synchronize()
     e2e = (time.perf_counter() - t0)/3
     out = {'workload': 'interior_stokes_with_multi (BASELINE configs[3]): %d^2 grid on [-pi/2,pi/2]^2, star n_b=%d, M=%d, '
@@ -464,6 +465,7 @@ def main():
                            'gmres_iterations': gmres_its,
                            'setup_s': {'geometry_and_registration': t_geom, 'solver_constructor': t_solver},
                            'peak_device_memory_gb': peak_mem,
+                           'host_max_rss_gb': __import__('resource').getrusage(__import__('resource').RUSAGE_SELF).ru_maxrss/1e6,
                            'multi_gpu': 'independent solves (one replica of the problem per rank, own forcing); '
                                         'no data-path collective' if world > 1 else 'single GPU',
                            'l2': 'inputs larger than L2: every step streams ~%.0f GB of grid-sized arrays (126 MB L2); '

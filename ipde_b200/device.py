@@ -353,8 +353,8 @@ class DeviceCollection(object):
         # positions (in the compact physical vector) of the phys-not-in-annulus points
         self.pna_pos = to_dev(ebdyc.phys_inds[ebdyc.phys_not_in_annulus].astype(np.int64))
         self.n_pna = int(self.pna_pos.numel())
-        self.pnai_x = to_dev(ebdyc.grid_pnai.x)
-        self.pnai_y = to_dev(ebdyc.grid_pnai.y)
+        self._ebdyc = ebdyc
+        self._pnai = None                 # (x, y) of grid_pnai on the device: only the all-pairs back-end reads them
         self.n_pnai = ebdyc.grid_pnai.N
         self.iv_x = to_dev(ebdyc.all_ivx)
         self.iv_y = to_dev(ebdyc.all_ivy)
@@ -371,6 +371,17 @@ class DeviceCollection(object):
         self.uc = self.grid.new_real()
         self.uch = self.grid.new_spec()
         self.spec_work = self.grid.new_spec()
+
+    @property
+    def pnai_x(self):
+        if self._pnai is None:
+            self._pnai = (to_dev(self._ebdyc.grid_pnai.x), to_dev(self._ebdyc.grid_pnai.y))
+        return self._pnai[0]
+
+    @property
+    def pnai_y(self):
+        self.pnai_x
+        return self._pnai[1]
 
     @property
     def nufft(self):

@@ -16,7 +16,7 @@ Registration is setup work and stays in NumPy.  The per-solve members
 are executed by the CUDA library (ipde_b200/device.py).
 """
 import numpy as np
-from .geometry import PointSet, Grid
+from .geometry import PointSet, LazyPointSet, Grid
 from .near import points_inside_curve
 from .embedded_boundary import EmbeddedBoundary, LoadEmbeddedBoundary
 from .embedded_function import EmbeddedFunction, BoundaryFunction
@@ -149,31 +149,39 @@ class EmbeddedBoundaryCollection(object):
         for ebdy in self:
             self.grid_step[ebdy.grid_ia_xind, ebdy.grid_ia_yind] *= ebdy.grid_to_radial_step
 
-        xg, yg = grid.xg, grid.yg
-        grid_phys_x, grid_phys_y = xg[phys], yg[phys]
-        self.grid_phys = PointSet(grid_phys_x, grid_phys_y)
+        # Collection-wide point sets (ipde/ebdy_collection.py:414-446).  Each is O(N^2) doubles; the device path needs
+        # only their sizes, so the coordinates are produced on first access (LazyPointSet) from the index lists.
+        xv, yv = grid.xv, grid.yv
+        def masked(mask):
+            def build():
+                ix, iy = np.nonzero(mask)
+                return xv[ix], yv[iy]
+            return build
         self.radial_x = np.concatenate([ebdy.radial_x.ravel() for ebdy in self])
         self.radial_y = np.concatenate([ebdy.radial_y.ravel() for ebdy in self])
         self.radial_pts = PointSet(self.radial_x, self.radial_y)
-        self.grid_and_radial_pts = PointSet(np.concatenate([grid_phys_x, self.radial_x]),
-                                            np.concatenate([grid_phys_y, self.radial_y]))
-        grid_pna_x = xg[self.phys_not_in_annulus]
-        grid_pna_y = yg[self.phys_not_in_annulus]
-        self.grid_pna = PointSet(grid_pna_x, grid_pna_y)
-        self.grid_pna_num = self.grid_pna.N
-        self.pnar = PointSet(np.concatenate([grid_pna_x, self.radial_x]),
-                             np.concatenate([grid_pna_y, self.radial_y]))
         self.all_bvx = np.concatenate([ebdy.bdy.x for ebdy in self])
         self.all_bvy = np.concatenate([ebdy.bdy.y for ebdy in self])
         self.all_bv = PointSet(self.all_bvx, self.all_bvy)
         self.all_ivx = np.concatenate([ebdy.interface.x for ebdy in self])
         self.all_ivy = np.concatenate([ebdy.interface.y for ebdy in self])
         self.all_iv = PointSet(self.all_ivx, self.all_ivy)
-        self.exterior_x = xg[self.ext]
-        self.exterior_y = yg[self.ext]
-        self.exterior_targ = PointSet(self.exterior_x, self.exterior_y)
-        self.grid_pnai = PointSet(np.concatenate([grid_pna_x, self.all_ivx]),
-                                  np.concatenate([grid_pna_y, self.all_ivy]))
+        n_phys = self.phys_n
+        n_pna = int(np.sum(self.phys_not_in_annulus))
+        n_ext = int(phys.size - n_phys)
+        nr, ni = self.radial_x.size, self.all_ivx.size
+        def plus(build, ex, ey):
+            def b():
+                x, y = build()
+                return np.concatenate([x, ex]), np.concatenate([y, ey])
+            return b
+        self.grid_phys = LazyPointSet(n_phys, masked(phys))
+        self.grid_and_radial_pts = LazyPointSet(n_phys + nr, plus(masked(phys), self.radial_x, self.radial_y))
+        self.grid_pna = LazyPointSet(n_pna, masked(self.phys_not_in_annulus))
+        self.grid_pna_num = n_pna
+        self.pnar = LazyPointSet(n_pna + nr, plus(masked(self.phys_not_in_annulus), self.radial_x, self.radial_y))
+        self.exterior_targ = LazyPointSet(n_ext, masked(self.ext))
+        self.grid_pnai = LazyPointSet(n_pna + ni, plus(masked(self.phys_not_in_annulus), self.all_ivx, self.all_ivy))
 
         self.bdy_Ns = [ebdy.bdy.N for ebdy in self]
         self.cumsum_bdy_Ns = np.cumsum(self.bdy_Ns)
@@ -187,6 +195,14 @@ class EmbeddedBoundaryCollection(object):
         self.radial_dof_list = [int(np.prod(ebdy.radial_shape)) for ebdy in self]
         self.radial_dof = int(np.sum(self.radial_dof_list))
         self.dof = self.grid_dof + self.radial_dof
+
+    @property
+    def exterior_x(self):
+        return self.exterior_targ.x
+
+    @property
+    def exterior_y(self):
+        return self.exterior_targ.y
 
     ############################################################################
     def divide_grid_and_radial(self, v):

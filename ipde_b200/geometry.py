@@ -34,15 +34,52 @@ def squished_circle(N, x=0.0, y=0.0, r=1.0, b=1.0, rot=0.0):
 
 
 class PointSet(object):
-    """Bare collection of points (x, y); `c` = x + iy."""
+    """Bare collection of points (x, y); `c` = x + iy (built on first use)."""
     def __init__(self, x=None, y=None, c=None):
         if c is not None:
             c = np.asarray(c)
             x, y = c.real.copy(), c.imag.copy()
         self.x = np.ascontiguousarray(x, dtype=float).ravel()
         self.y = np.ascontiguousarray(y, dtype=float).ravel()
-        self.c = self.x + 1j*self.y
         self.N = self.x.size
+
+    @property
+    def c(self):
+        return self.x + 1j*self.y
+
+    def get_stacked_boundary(self, T=True):
+        return np.vstack([self.x, self.y])
+
+
+class LazyPointSet(object):
+    """
+    PointSet whose coordinates are produced on first access.  The collection-wide point sets of a registered grid
+    (grid_phys, grid_pna, grid_pnai, exterior_targ, ... -- ipde/ebdy_collection.py:414-446) are O(N^2) each; at
+    16384^2 they add up to ~25 GB of host memory, and the device path needs only their sizes.
+    """
+    def __init__(self, n, build):
+        self.N = int(n)
+        self._build = build
+        self._xy = None
+
+    def _get(self):
+        if self._xy is None:
+            x, y = self._build()
+            self._xy = (np.ascontiguousarray(x, dtype=float).ravel(), np.ascontiguousarray(y, dtype=float).ravel())
+            assert self._xy[0].size == self.N
+        return self._xy
+
+    @property
+    def x(self):
+        return self._get()[0]
+
+    @property
+    def y(self):
+        return self._get()[1]
+
+    @property
+    def c(self):
+        return self.x + 1j*self.y
 
     def get_stacked_boundary(self, T=True):
         return np.vstack([self.x, self.y])

@@ -88,6 +88,8 @@ class ScalarSolver(object):
 
     # S*T above which the all-pairs sum loses to the spectral-Ewald evaluator (csrc/ewald.cu)
     EWALD_THRESHOLD = 2.0e8
+    # spacing of the interface-point evaluator in units of the grid spacing (None: 4 from 4096^2, else 1 = shared box)
+    POINT_EVAL_COARSENING = None
 
     def _define_grid_evaluator(self):
         """
@@ -109,6 +111,7 @@ class ScalarSolver(object):
         self.split_grid_evaluation = gb == 'ewald'
         self._no_interface_field = empty((self.ebdyc.all_ivx.size,))
         self.evaluator_g = None
+        self.evaluator_p = None
         if gb == 'ewald':
             from ...device import FreeSpaceEvaluator
             e = self.ebdyc
@@ -116,6 +119,19 @@ class ScalarSolver(object):
             # a single boundary never uses the field on its own interface (helper.correct: it cancels
             # identically), so the second inverse transform + gather is skipped
             pts = (e.all_ivx, e.all_ivy) if e.N > 1 else None
+            # Interface points on a coarser Ewald split: on the grid's own spacing the point targets cost a second
+            # full-size inverse transform (15 of 41 ms at 16384^2) for 8e4 values.  The split is exact for any
+            # spacing; with c*h the FFT box has 1/c^2 of the points and the local sums reach c times further
+            # (a few hundred sources per interface point).
+            c = self.POINT_EVAL_COARSENING
+            if c is None:
+                c = 4 if min(g.Nx, g.Ny) >= 4096 else 1
+            self.evaluator_p = None
+            if pts is not None and c > 1:
+                self.evaluator_p = FreeSpaceEvaluator(self.kernel_kind, self.k, float(g.xv[0]), float(g.yv[0]),
+                                                      float(g.xh)*c, self.grid_sources.x, self.grid_sources.y,
+                                                      points=pts)
+                pts = None
             self.evaluator_g = FreeSpaceEvaluator(
                 self.kernel_kind, self.k, float(g.xv[0]), float(g.yv[0]), float(g.xh),
                 self.grid_sources.x, self.grid_sources.y, grid_nodes=(pix, piy),
@@ -199,6 +215,8 @@ class ScalarSolver(object):
         L.ipde_grid_gather(ptr(D.uc), ptr(D.phys_lin), D.n_phys, ptr(res), st)
         if self.evaluator_g is not None:
             bu_all = self.evaluator_g(sigmag, grid_out=res)
+            if self.evaluator_p is not None:
+                bu_all = self.evaluator_p(sigmag)
             if bu_all is None:
                 bu_all = self._no_interface_field
         else:

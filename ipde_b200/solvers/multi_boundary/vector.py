@@ -222,8 +222,29 @@ class VectorSolver(object):
                 res[k][r0:r1].copy_(urs[k].reshape(-1))
         return res
 
-    def __call__(self, fu, fv, **kwargs):
-        fu_dev = to_dev(np.asarray(fu, dtype=float))
-        fv_dev = to_dev(np.asarray(fv, dtype=float))
-        res = self.solve_device(fu_dev, fv_dev, **kwargs)
-        return tuple(EmbeddedFunction(self.ebdyc, linear_data=r.cpu().numpy()) for r in res)
+    def _staging(self):
+        """persistent pinned host buffers + device input buffers for the public (host array) entry point"""
+        if getattr(self, '_stage', None) is None:
+            n = self.ebdyc.dof
+            pin = lambda: torch.empty(n, dtype=torch.float64).pin_memory()
+            self._stage = ([pin(), pin()], [pin(), pin(), pin()], [empty((n,)), empty((n,))])
+        return self._stage
+
+    def __call__(self, fu, fv, out=None, **kwargs):
+        """
+        fu, fv: EmbeddedFunctions -> (u, v, p) fresh EmbeddedFunctions, as ipde/solvers/multi_boundary/vector.py:57-112.
+        Extension: `out=(u, v, p)` EmbeddedFunctions of the same collection to receive the result (time stepping).
+        """
+        h_in, h_out, d_in = self._staging()
+        for src, hb, db in zip((fu, fv), h_in, d_in):
+            hb.copy_(torch.from_numpy(np.ascontiguousarray(src, dtype=float).reshape(-1)))
+            db.copy_(hb, non_blocking=True)
+        res = self.solve_device(d_in[0], d_in[1], **kwargs)
+        for r, hb in zip(res, h_out):
+            hb.copy_(r, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        if out is None:
+            out = tuple(EmbeddedFunction(self.ebdyc) for _ in range(3))
+        for o, hb in zip(out, h_out):
+            torch.from_numpy(np.asarray(o).reshape(-1)).copy_(hb)
+        return tuple(out)
