@@ -372,6 +372,178 @@ k_fft_cols_short(const cplx* __restrict__ tw, const cplx* in, cplx* out, int64_t
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// TMA variant of the plain short column pass (128- and 256-point lines, no row window): the tile of the NEXT
+// iteration is fetched by one cp.async.bulk.tensor (3-D tensor map over {columns, line element, outer line}) into a
+// second shared-memory buffer and signalled through an mbarrier, so no thread holds load addresses or waits on
+// global loads; the registers only ever hold the tile being transformed.  ncu of the register-load version: 25 % warps
+// active, long-scoreboard stalls 7-9 cycles per issued instruction (profiles/r02_ncu_k_fft_cols.txt).
+#include <cuda.h>
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+    static TensorMapEncodeFn fn = []() -> TensorMapEncodeFn {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return (TensorMapEncodeFn)f;
+    }();
+    return fn;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int RA, int RB, int SIGN>
+__global__ void __launch_bounds__(128, 3)
+k_fft_cols_short_tma(const __grid_constant__ CUtensorMap tmap, const cplx* __restrict__ tw, cplx* out, int64_t elem_stride,
+                     int64_t n_inner, int64_t outer_stride, double scale, int tw_mode, const cplx* __restrict__ tw_big,
+                     int e_first, int tiles_per_outer, int ntiles_total) {
+    using K = ShortCfg<RA, RB>;
+    constexpr int E = K::EPT;
+    extern __shared__ unsigned char smraw_[];
+    // TMA destinations must be 128-byte aligned: align the dynamic segment by hand (128 spare bytes are requested)
+    unsigned char* smraw = smraw_ + ((128u - (smem_u32(smraw_) & 127u)) & 127u);
+    // two tile buffers; the buffer a tile arrived in doubles as the exchange buffer of its transform (the registers
+    // hold the tile by then), which keeps a CTA at 64 KB and three CTAs on an SM
+    cplx* tile_in[2] = {reinterpret_cast<cplx*>(smraw), reinterpret_cast<cplx*>(smraw) + K::TILE};
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tile_in[1] + K::TILE);
+    const int tid = threadIdx.x;
+    const int c = tid & (K::C - 1), jt = tid >> K::LOGC;
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int tile, int b) {
+        const int o = tile / tiles_per_outer;
+        const int col0 = (tile - o * tiles_per_outer) << K::LOGC;
+        mbar_expect_tx(&bar[b], (uint32_t)(K::TILE * sizeof(cplx)));
+        // coordinates: (double index inside the row, second dimension, third dimension); e_first tells which of the
+        // two strided dimensions is the line element (the map orders them by stride)
+        if (e_first) tma_load_3d(tile_in[b], &tmap, 2 * col0, 0, o, &bar[b]);
+        else tma_load_3d(tile_in[b], &tmap, 2 * col0, o, 0, &bar[b]);
+    };
+    int tile = blockIdx.x;
+    uint32_t phase0 = 0, phase1 = 0;
+    if (tid == 0 && tile < ntiles_total) issue(tile, 0);
+    cplx v[E];
+    for (int b = 0; tile < ntiles_total; tile += gridDim.x, b ^= 1) {
+        const int next = tile + gridDim.x;
+        // buffer b^1 served the previous iteration (tile and exchange); the barrier at the end of that iteration has
+        // been passed by every thread
+        if (tid == 0 && next < ntiles_total) issue(next, b ^ 1);
+        if (b == 0) { mbar_wait(&bar[0], phase0); phase0 ^= 1; }
+        else { mbar_wait(&bar[1], phase1); phase1 ^= 1; }
+        const ShortTile S = short_tile<K::LOGC>(tile, tiles_per_outer, c, n_inner, outer_stride, 0);
+        const cplx* src = tile_in[b];
+#pragma unroll
+        for (int s = 0; s < E; ++s) v[s] = src[(short_elem_a<RA, RB>(jt, s) << K::LOGC) + c];
+        if (tw_mode == 2) {
+#pragma unroll
+            for (int s = 0; s < E; ++s) {
+                const cplx w = tw_big[S.o * short_elem_a<RA, RB>(jt, s)];
+                v[s] = (SIGN < 0) ? cmul(v[s], w) : cmulc(v[s], w);
+            }
+        }
+        short_fft<RA, RB, SIGN>(v, tile_in[b], c, jt, tw);     // NBUF == 1: starts with a barrier (tile reads done)
+        __syncthreads();                                       // exchange reads done: the buffer may be refilled
+#pragma unroll
+        for (int s = 0; s < E; ++s) {
+            const int e = short_elem_b<RA, RB>(jt, s);
+            if (S.colok) {
+                cplx r = v[s];
+                if (tw_mode == 1) {
+                    const cplx w = tw_big[S.o * e];
+                    r = (SIGN < 0) ? cmul(r, w) : cmulc(r, w);
+                }
+                out[S.base + (int64_t)e * elem_stride] = cscale(r, scale);
+            }
+        }
+    }
+}
+
+// Measured on B200 (16384^2 4-boundary solve, 8 launches of the 128/256-point passes, CUDA events): register loads
+// 19.7 ms (3.51 TB/s); TMA, 2 CTAs/SM with a separate exchange buffer 21.1 ms; TMA, 3 CTAs/SM with the tile buffer
+// reused for the exchange 21.8 ms.  The pass is limited by its strided 128-256-byte stores and the FP64 butterflies,
+// not by load latency, so the register-load kernel stays the default; IPDE_FFT_TMA=1 selects this one.
+static const bool g_fft_tma = []() { const char* e = getenv("IPDE_FFT_TMA"); return e && e[0] == '1'; }();
+
+template <int RA, int RB>
+static int launch_cols_short_tma(FftPlan* p, const cplx* in, cplx* out, int64_t elem_stride, int64_t n_inner, int64_t n_outer,
+                                 int64_t outer_stride, int sign, double scale, int tw_mode, const cplx* tw_big,
+                                 cudaStream_t st, bool* done) {
+    using K = ShortCfg<RA, RB>;
+    *done = false;
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    if (!enc) return IPDE_OK;
+    // tensor map over doubles: {2*n_inner, then the two strided dimensions by increasing stride}
+    const bool e_first = elem_stride <= outer_stride || n_outer == 1;
+    cuuint64_t dims[3], strides[2];
+    cuuint32_t box[3], estr[3] = {1, 1, 1};
+    dims[0] = (cuuint64_t)(2 * n_inner);
+    box[0] = (cuuint32_t)(2 * K::C);
+    if (e_first) {
+        dims[1] = K::N; dims[2] = (cuuint64_t)n_outer;
+        strides[0] = (cuuint64_t)elem_stride * 16; strides[1] = (cuuint64_t)(n_outer == 1 ? elem_stride * K::N : outer_stride) * 16;
+        box[1] = K::N; box[2] = 1;
+    } else {
+        dims[1] = (cuuint64_t)n_outer; dims[2] = K::N;
+        strides[0] = (cuuint64_t)outer_stride * 16; strides[1] = (cuuint64_t)elem_stride * 16;
+        box[1] = 1; box[2] = K::N;
+    }
+    CUtensorMap map;
+    CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<cplx*>(in), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return IPDE_OK;          // shapes the descriptor cannot express: register-load kernel
+    const int64_t tiles = cdiv(n_inner, (int64_t)K::C);
+    const int64_t total = tiles * n_outer;
+    ARG_CHECK(total < (int64_t)1 << 30, "short column transform: too many tiles");
+    const size_t smem = 2 * (size_t)K::TILE * sizeof(cplx) + 128 + 64;
+    const unsigned g = (unsigned)std::min<int64_t>(total, (int64_t)ipde_num_sms() * 3);
+    int rc;
+    if (sign < 0) {
+        rc = set_smem(k_fft_cols_short_tma<RA, RB, -1>, smem);
+        if (rc) return rc;
+        k_fft_cols_short_tma<RA, RB, -1><<<g, 128, smem, st>>>(map, p->d.tw, out, elem_stride, n_inner, outer_stride, scale,
+                                                               tw_mode, tw_big, e_first ? 1 : 0, (int)tiles, (int)total);
+    } else {
+        rc = set_smem(k_fft_cols_short_tma<RA, RB, +1>, smem);
+        if (rc) return rc;
+        k_fft_cols_short_tma<RA, RB, +1><<<g, 128, smem, st>>>(map, p->d.tw, out, elem_stride, n_inner, outer_stride, scale,
+                                                               tw_mode, tw_big, e_first ? 1 : 0, (int)tiles, (int)total);
+    }
+    KERNEL_CHECK();
+    *done = true;
+    return IPDE_OK;
+}
+
 static const bool g_fft_short = []() { const char* e = getenv("IPDE_FFT_SHORT"); return !(e && e[0] == '0'); }();
 bool fft_short_enabled() { return g_fft_short; }
 
@@ -598,6 +770,15 @@ int fft_cols_windowed(FftPlan* p, const cplx* in, cplx* out, int64_t elem_stride
         fout = std::min(1.0, std::max(0.0, (double)(W.out_hi - W.out_lo)) / rows);
     }
     KERNEL_TAG("k_fft_cols", 16.0 * (fin + fout) * (double)n * (double)n_inner * (double)n_outer);
+    if (g_fft_short && g_fft_tma && p->pow2 && (n == 128 || n == 256) && W.row_e == 0 && W.row_o == 0 &&
+        (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (elem_stride * 16) % 16 == 0) {
+        bool done = false;
+        int rc_t;
+        if (n == 128) rc_t = launch_cols_short_tma<16, 8>(p, in, out, elem_stride, n_inner, n_outer, outer_stride, sign, scale, tw_mode, tw_big, st, &done);
+        else rc_t = launch_cols_short_tma<16, 16>(p, in, out, elem_stride, n_inner, n_outer, outer_stride, sign, scale, tw_mode, tw_big, st, &done);
+        if (rc_t) return rc_t;
+        if (done) return IPDE_OK;
+    }
     if (g_fft_short && p->pow2 && fft_short_size_plain(n)) {
 #define CALL_SHORT(RA_, RB_) return launch_cols_short<RA_, RB_>(p, in, out, elem_stride, n_inner, n_outer, outer_stride, sign, scale, tw_mode, tw_big, W, st)
         SHORT_DISPATCH_PLAIN(n, CALL_SHORT);
