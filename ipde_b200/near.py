@@ -105,6 +105,85 @@ class NearCurveResult(object):
         return (self.n, self.ix, self.iy, self.r, self.t)[i]
 
 
+# grids with at least this many points are registered on the GPU when there is one (torch tensor ops: run-length
+# marking + prefix sums + compaction for the near-curve search and the inside test, Taylor-table Newton for the
+# coordinates); IPDE_REGISTER=host forces the NumPy path
+DEVICE_MIN_POINTS = 1 << 22
+
+
+def _torch_device(npoints):
+    import os
+    if os.environ.get('IPDE_REGISTER', '') == 'host' or npoints < DEVICE_MIN_POINTS:
+        return None
+    try:
+        import torch
+        return torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else None
+    except Exception:
+        return None
+
+
+def _mark_runs_device(dev, rows, lo, hi, ok, Nx, Ny):
+    """(ix, iy) of all grid points covered by at least one run [lo, hi) of row `rows` -- on the device, restricted to
+    the bounding box of the runs; same row-major order as np.nonzero"""
+    import torch
+    r = rows[ok]; a = lo[ok]; b = hi[ok]
+    if r.size == 0:
+        z = np.zeros(0, dtype=np.int64)
+        return z, z
+    r0, r1 = int(r.min()), int(r.max()) + 1
+    c0, c1 = int(a.min()), int(b.max())
+    diff = torch.zeros((r1 - r0, c1 - c0 + 1), dtype=torch.int32, device=dev)
+    tr = torch.from_numpy(r - r0).to(dev)
+    one = torch.ones(tr.numel(), dtype=torch.int32, device=dev)
+    diff.index_put_((tr, torch.from_numpy(a - c0).to(dev)), one, accumulate=True)
+    diff.index_put_((tr, torch.from_numpy(b - c0).to(dev)), -one, accumulate=True)
+    close = torch.cumsum(diff, dim=1, dtype=torch.int32)[:, :c1 - c0] > 0
+    idx = torch.nonzero(close)
+    return (idx[:, 0] + r0).cpu().numpy(), (idx[:, 1] + c0).cpu().numpy()
+
+
+def _local_coordinates_device(dev, ct, z, guess_ci, tol=1e-14, maxiter=50):
+    """compute_local_coordinates with torch tensors on `dev` (same iteration, all points advanced together)"""
+    import torch
+    tab = torch.from_numpy(ct.tab).to(dev)                     # (order+1, nc) complex
+    P, nc, dtc = ct.order, ct.nc, ct.dtc
+    zt = torch.from_numpy(z).to(dev)
+    ci = torch.from_numpy(np.asarray(guess_ci, dtype=np.int64) % nc).to(dev)
+    s = torch.zeros(zt.shape, dtype=torch.float64, device=dev)
+
+    def ev(ci_, s_):
+        X = tab[P][ci_].clone()
+        Xp = torch.zeros_like(X)
+        Xpp = torch.zeros_like(X)
+        for m in range(P - 1, -1, -1):
+            Xpp = Xpp*s_ + 2.0*Xp
+            Xp = Xp*s_ + X
+            X = X*s_ + tab[m][ci_]
+        return X, Xp, Xpp
+    active = torch.ones(zt.shape, dtype=torch.bool, device=dev)
+    for it in range(maxiter):
+        idx = torch.nonzero(active)[:, 0]
+        if idx.numel() == 0:
+            break
+        X, Xp, Xpp = ev(ci[idx], s[idx])
+        dd = X - zt[idx]
+        f = (dd*Xp.conj()).real
+        sp2 = (Xp*Xp.conj()).real
+        fp = sp2 + (dd*Xpp.conj()).real
+        fp = torch.where(fp <= 0.0, sp2, fp)
+        ds = torch.clamp(-f/fp, -4*dtc, 4*dtc)
+        snew = s[idx] + ds
+        shift = torch.round(snew/dtc).to(torch.int64)
+        ci[idx] = (ci[idx] + shift) % nc
+        s[idx] = snew - shift*dtc
+        active[idx] = ds.abs() > tol
+    X, Xp, _ = ev(ci, s)
+    n = -1j*Xp/Xp.abs()
+    r = ((zt - X)*n.conj()).real
+    t = (torch.from_numpy(ct.tc).to(dev)[ci] + s) % (2.0*np.pi)
+    return t.cpu().numpy(), r.cpu().numpy()
+
+
 def gridpoints_near_curve(bdy, xv, yv, d, tol=1e-14):
     """
     All grid points (xv[i], yv[j]) whose distance to the curve is <= d.
@@ -131,19 +210,26 @@ def gridpoints_near_curve(bdy, xv, yv, d, tol=1e-14):
     lo = np.clip(lo, 0, Ny)
     hi = np.clip(hi + 1, 0, Ny)
     ok = np.logical_and(ok, hi > lo)
-    diff = np.zeros((Nx, Ny + 1), dtype=np.int32)
-    np.add.at(diff, (rows[ok], lo[ok]), 1)
-    np.add.at(diff, (rows[ok], hi[ok]), -1)
-    close = np.cumsum(diff, axis=1)[:, :Ny] > 0
-    ix, iy = np.nonzero(close)
+    dev = _torch_device(Nx*Ny)
+    if dev is not None:
+        ix, iy = _mark_runs_device(dev, rows, lo, hi, ok, Nx, Ny)
+    else:
+        diff = np.zeros((Nx, Ny + 1), dtype=np.int32)
+        np.add.at(diff, (rows[ok], lo[ok]), 1)
+        np.add.at(diff, (rows[ok], hi[ok]), -1)
+        close = np.cumsum(diff, axis=1)[:, :Ny] > 0
+        ix, iy = np.nonzero(close)
     if ix.size == 0:
         e = np.zeros(0)
         return NearCurveResult(ix, iy, e, e)
     z = xv[ix] + 1j*yv[iy]
     ct = CurveTaylor(bdy.c)
     tree = cKDTree(np.column_stack([ct.tab[0].real, ct.tab[0].imag]))
-    _, gi = tree.query(np.column_stack([z.real, z.imag]))
-    t, r = compute_local_coordinates(ct, z, gi, tol=tol)
+    _, gi = tree.query(np.column_stack([z.real, z.imag]), workers=-1)
+    if dev is not None:
+        t, r = _local_coordinates_device(dev, ct, z, gi, tol=tol)
+    else:
+        t, r = compute_local_coordinates(ct, z, gi, tol=tol)
     keep = np.abs(r) <= d
     return NearCurveResult(ix[keep], iy[keep], r[keep], t[keep])
 
@@ -167,7 +253,7 @@ def points_inside_curve(bdy, xv, yv, near=None):
     ilo = np.ceil(a).astype(np.int64)
     ihi = np.ceil(b).astype(np.int64) - 1
     cnt = np.maximum(ihi - ilo + 1, 0)
-    diff = np.zeros((Nx, Ny + 1), dtype=np.int32)
+    cross_i, cross_j = [], []
     for m in range(int(cnt.max()) if cnt.size else 0):
         sel = cnt > m
         i = ilo[sel] + m
@@ -176,8 +262,25 @@ def points_inside_curve(bdy, xv, yv, near=None):
         yc = y0[sel] + (xs - x0[sel])/(x1[sel] - x0[sel])*(y1[sel] - y0[sel])
         j = np.floor((yc - yv[0])/yh).astype(np.int64) + 1
         j = np.clip(j, 0, Ny)
-        np.add.at(diff, (i[good], j[good]), 1)
-    inside = (np.cumsum(diff, axis=1)[:, :Ny] % 2) == 1
+        cross_i.append(i[good]); cross_j.append(j[good])
+    ci_ = np.concatenate(cross_i) if cross_i else np.zeros(0, dtype=np.int64)
+    cj_ = np.concatenate(cross_j) if cross_j else np.zeros(0, dtype=np.int64)
+    dev = _torch_device(Nx*Ny)
+    if dev is not None and ci_.size:
+        # parity fill on the device, restricted to the rows / columns the curve spans (outside: not inside)
+        import torch
+        r0, r1 = int(ci_.min()), int(ci_.max()) + 1
+        c0 = int(cj_.min())
+        diff = torch.zeros((r1 - r0, Ny + 1 - c0), dtype=torch.int32, device=dev)
+        diff.index_put_((torch.from_numpy(ci_ - r0).to(dev), torch.from_numpy(cj_ - c0).to(dev)),
+                        torch.ones(ci_.size, dtype=torch.int32, device=dev), accumulate=True)
+        sub = (torch.cumsum(diff, dim=1, dtype=torch.int32)[:, :Ny - c0] % 2) == 1
+        inside = np.zeros((Nx, Ny), dtype=bool)
+        inside[r0:r1, c0:] = sub.cpu().numpy()
+    else:
+        diff = np.zeros((Nx, Ny + 1), dtype=np.int32)
+        np.add.at(diff, (ci_, cj_), 1)
+        inside = (np.cumsum(diff, axis=1)[:, :Ny] % 2) == 1
     if near is not None and near.n > 0:
         inside[near.ix, near.iy] = near.r < 0.0
     return inside

@@ -615,3 +615,22 @@ def test_stokes_structured_qfs_vs_oracle():
             np.abs(np.asarray(p) - po).max()/np.abs(po).max()]
     print('Stokes nb=1024 structured QFS vs oracle: u %.2e v %.2e p %.2e' % tuple(errs))
     assert max(errs[:2]) < TOL and errs[2] < 1e-10, errs
+
+
+def test_registration_on_device_matches_host(monkeypatch):
+    """grid registration (near-curve search, (r, t) coordinates, inside test) on the GPU against the
+    NumPy path: identical point sets in identical order, coordinates to round-off"""
+    import ipde_b200.near as near
+    from problems import four_bodies
+    monkeypatch.setenv('IPDE_REGISTER', 'host')
+    a = four_bodies(nb=200, M=10)
+    monkeypatch.setenv('IPDE_REGISTER', '')
+    monkeypatch.setattr(near, 'DEVICE_MIN_POINTS', 0)
+    assert near._torch_device(1) is not None
+    b = four_bodies(nb=200, M=10)
+    assert np.array_equal(a.phys, b.phys)
+    assert np.abs(a.grid_step - b.grid_step).max() < 1e-12
+    for ea, eb in zip(a, b):
+        assert np.array_equal(ea.grid_ia_xind, eb.grid_ia_xind) and np.array_equal(ea.grid_ia_yind, eb.grid_ia_yind)
+        assert np.abs(ea.grid_ia_r - eb.grid_ia_r).max() < 1e-13
+        assert np.abs(np.angle(np.exp(1j*(ea.grid_ia_t - eb.grid_ia_t)))).max() < 1e-13

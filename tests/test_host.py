@@ -187,3 +187,20 @@ def test_structured_qfs_matches_dense_qfs():
         vs = Q.layer_apply_matrix_free(ker, qs.source, z.real, z.imag, qs(tau))
         vd = Q.layer_apply_matrix_free(ker, qd.source, z.real, z.imag, qd(tau))
         assert np.abs(vs - vd).max() < 1e-12
+
+
+def test_registration_torch_path_matches_numpy_path(monkeypatch):
+    """near.py: the tensor (GPU) statement of the near-curve search, Newton coordinates and inside test, run here on
+    CPU tensors, against the NumPy statement -- identical point sets in identical order, coordinates to round-off"""
+    import torch
+    import ipde_b200.near as near
+    from problems import four_bodies
+    a = four_bodies(nb=120, M=8)
+    monkeypatch.setattr(near, '_torch_device', lambda n: torch.device('cpu'))
+    b = four_bodies(nb=120, M=8)
+    assert np.array_equal(a.phys, b.phys)
+    assert np.abs(a.grid_step - b.grid_step).max() < 1e-12
+    for ea, eb in zip(a, b):
+        assert np.array_equal(ea.grid_ia_xind, eb.grid_ia_xind) and np.array_equal(ea.grid_ia_yind, eb.grid_ia_yind)
+        assert np.abs(ea.grid_ia_r - eb.grid_ia_r).max() < 1e-13
+        assert np.abs(np.angle(np.exp(1j*(ea.grid_ia_t - eb.grid_ia_t)))).max() < 1e-13
