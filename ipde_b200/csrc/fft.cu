@@ -1134,7 +1134,10 @@ static int launch_rows_reg_sub(FftPlan* ph, const cplx* in, cplx* out, int64_t n
 template <int N>
 __global__ void __launch_bounds__(RegGeom<N>::NT, RegGeom<N>::MINB)
 k_c2r_rows_long(const cplx* __restrict__ tw, const cplx* __restrict__ twn, const cplx* __restrict__ half_tw,
-                const cplx* __restrict__ in, cplx* out, int64_t nsub, int64_t in_pitch, int64_t out_pitch, double scale) {
+                const cplx* __restrict__ in, cplx* out, int64_t nsub, int64_t in_pitch, int64_t out_pitch, double scale,
+                int nz) {
+    // nz: only the first nz entries of an input row can be nonzero (zero-padded spectra: the NUFFT fine grid); the
+    // others are not read
     using G = RegGeom<N>;
     using K = RegCfg<N>;
     extern __shared__ cplx smem[];
@@ -1153,8 +1156,9 @@ k_c2r_rows_long(const cplx* __restrict__ tw, const cplx* __restrict__ twn, const
         const int k = reg_elem<N, K::R0>(jt, s);
         if (live) {
             // Z[kk] = E + i O,  E = (X[kk] + conj X[n-kk])/2,  O = (X[kk] - conj X[n-kk])/2 * conj(half_tw[kk])
-            const cplx x0 = src[k], c0 = cconj(src[n - k]);
-            const cplx x1 = src[k + m], c1 = cconj(src[m - k]);
+            const cplx zero = make_double2(0.0, 0.0);
+            const cplx x0 = (k < nz) ? src[k] : zero, c0 = (n - k < nz) ? cconj(src[n - k]) : zero;
+            const cplx x1 = (k + m < nz) ? src[k + m] : zero, c1 = (m - k < nz) ? cconj(src[m - k]) : zero;
             const cplx z0 = cadd(cscale(cadd(x0, c0), 0.5), cmuli(cmulc(cscale(csub(x0, c0), 0.5), half_tw[k])));
             const cplx z1 = cadd(cscale(cadd(x1, c1), 0.5), cmuli(cmulc(cscale(csub(x1, c1), 0.5), half_tw[k + m])));
             v[s] = (r == 0) ? cadd(z0, z1) : cmulc(csub(z0, z1), twn[k]);
@@ -1171,13 +1175,13 @@ k_c2r_rows_long(const cplx* __restrict__ tw, const cplx* __restrict__ twn, const
 }
 template <int N>
 static int launch_c2r_long(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
-                           double scale, cudaStream_t st) {
+                           double scale, int nz, cudaStream_t st) {
     using G = RegGeom<N>;
     int rc = set_smem(k_c2r_rows_long<N>, G::SMEM);
     if (rc) return rc;
     const unsigned g = (unsigned)cdiv(2 * batch, (int64_t)G::L);
     k_c2r_rows_long<N><<<g, G::NT, G::SMEM, st>>>(p->half->d.tw, p->d.tw, p->half_tw_dev, in, reinterpret_cast<cplx*>(out),
-                                                  2 * batch, in_pitch, out_pitch / 2, scale);
+                                                  2 * batch, in_pitch, out_pitch / 2, scale, nz);
     KERNEL_CHECK();
     return IPDE_OK;
 }
@@ -1417,6 +1421,11 @@ int fft_r2c_rows(FftPlan* p, const double* in, cplx* out, int64_t batch, int64_t
 
 int fft_c2r_rows(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
                  double scale, cudaStream_t st) {
+    return fft_c2r_rows_nz(p, in, out, batch, in_pitch, out_pitch, scale, p->d.n + 1, st);
+}
+
+int fft_c2r_rows_nz(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
+                    double scale, int nz, cudaStream_t st) {
     if (batch <= 0) return IPDE_OK;
     const int n = p->d.n;
     if (!p->fast && !p->any && n <= IPDE_FFT_GENERIC_MAX) return fft_c2r_rows_generic(p, in, out, batch, in_pitch, out_pitch, scale, st);
@@ -1424,9 +1433,9 @@ int fft_c2r_rows(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t
         int rc = ensure_half(p);
         if (rc) return rc;
         const int m = n / 2;
-        KERNEL_TAG("k_c2r_rows_long", (16.0 * n + 16.0 * (n + 1)) * (double)batch);
-        if (m == 4096) return launch_c2r_long<4096>(p, in, out, batch, in_pitch, out_pitch, scale, st);
-        return launch_c2r_long<8192>(p, in, out, batch, in_pitch, out_pitch, scale, st);
+        KERNEL_TAG("k_c2r_rows_long", (16.0 * n + 16.0 * std::min(n + 1, nz)) * (double)batch);
+        if (m == 4096) return launch_c2r_long<4096>(p, in, out, batch, in_pitch, out_pitch, scale, nz, st);
+        return launch_c2r_long<8192>(p, in, out, batch, in_pitch, out_pitch, scale, nz, st);
     }
     if (n > IPDE_FFT_SMEM_MAX || !p->fast) {
         int rc = ensure_work(p, (size_t)3 * n * batch);

@@ -81,11 +81,16 @@ int grid_cols_forward(GridPlan* g, const cplx* in, cplx* out, cudaStream_t st) {
 }
 
 int grid_cols_inverse(GridPlan* g, const cplx* in, cplx* out, cudaStream_t st) {
+    return grid_cols_inverse_n(g, in, out, g->pitch, st);
+}
+
+// the same for the first `ncols` columns only (zero-padded spectra: the columns beyond hold zeros and stay untouched)
+int grid_cols_inverse_n(GridPlan* g, const cplx* in, cplx* out, int64_t ncols, cudaStream_t st) {
     const int64_t P = g->pitch;
-    if (g->n2 == 1) return fft_cols(g->colA, in, out, P, P, 1, 0, +1, 1.0, 0, nullptr, 0, st);
-    int rc = fft_cols(g->colB, in, out, P, P, g->n1, (int64_t)g->n2 * P, +1, 1.0, 0, nullptr, 0, st);
+    if (g->n2 == 1) return fft_cols(g->colA, in, out, P, ncols, 1, 0, +1, 1.0, 0, nullptr, 0, st);
+    int rc = fft_cols(g->colB, in, out, P, ncols, g->n1, (int64_t)g->n2 * P, +1, 1.0, 0, nullptr, 0, st);
     if (rc) return rc;
-    return fft_cols(g->colA, out, out, (int64_t)g->n2 * P, P, g->n2, P, +1, 1.0, 2, g->tw_big, g->nx, st);
+    return fft_cols(g->colA, out, out, (int64_t)g->n2 * P, ncols, g->n2, P, +1, 1.0, 2, g->tw_big, g->nx, st);
 }
 
 int grid_fft2_forward(GridPlan* g, const double* real_in, cplx* spec, cudaStream_t st) {

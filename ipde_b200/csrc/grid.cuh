@@ -25,6 +25,7 @@ int grid_plan_create(int nx, int ny, double xh, double yh, GridPlan** out);
 void grid_plan_destroy(GridPlan* g);
 int grid_cols_forward(GridPlan* g, const cplx* in, cplx* out, cudaStream_t st);
 int grid_cols_inverse(GridPlan* g, const cplx* in, cplx* out, cudaStream_t st);
+int grid_cols_inverse_n(GridPlan* g, const cplx* in, cplx* out, int64_t ncols, cudaStream_t st);
 int grid_fft2_forward(GridPlan* g, const double* real_in, cplx* spec, cudaStream_t st);
 int grid_fft2_inverse(GridPlan* g, const cplx* spec_in, cplx* spec_work, double* real_out, cudaStream_t st);
 int grid_scatter_cutoff(GridPlan* g, const double* f_compact, const int64_t* phys_lin, const double* step_compact,

@@ -28,6 +28,7 @@ int nufft2_plan_create(int nx, int ny, double xh, double yh, int fx, int fy, int
     CUDA_TRY(cudaMemcpy(p->py, py_host, sizeof(double) * (ny / 2 + 1), cudaMemcpyHostToDevice));
     const size_t nspec = (size_t)fx * (fy / 2 + 1);
     CUDA_TRY(cudaMalloc(&p->fine_spec, sizeof(cplx) * nspec));
+    CUDA_TRY(cudaMemset(p->fine_spec, 0, sizeof(cplx) * nspec));     // columns beyond ny/2 stay zero for good
     CUDA_TRY(cudaMalloc(&p->fine_real, sizeof(double) * (size_t)fx * fy));
     *out = p;
     return IPDE_OK;
@@ -54,9 +55,12 @@ __global__ void k_nufft_pad(const cplx* __restrict__ spec, int nx, int ny, int64
                             cplx* __restrict__ fine, int fx, int fy, int64_t fpitch, int fn1, int fn2,
                             const double* __restrict__ px, const double* __restrict__ py, double xh, double yh, int dxp,
                             int dyp, double scale) {
-    const int64_t total = (int64_t)fx * fpitch;
+    // only the columns j <= ny/2 can be nonzero; the rest of the fine spectrum was zeroed at plan creation and is
+    // never written (the column passes are restricted to the same columns)
+    const int64_t ncols = ny / 2 + 1;
+    const int64_t total = (int64_t)fx * ncols;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int pos = (int)(t / fpitch), j = (int)(t % fpitch);
+        const int pos = (int)(t / ncols), j = (int)(t % ncols);
         const int I = freq_of_row2(pos, fn1, fn2);
         const int sI = (I < (fx + 1) / 2) ? I : I - fx;      // signed fine row frequency
         cplx v = make_double2(0.0, 0.0);
@@ -78,7 +82,7 @@ __global__ void k_nufft_pad(const cplx* __restrict__ spec, int nx, int ny, int64
             if (dyp) a = cscale(cmuli(a), ky);
             v = a;
         }
-        fine[t] = v;
+        fine[(int64_t)pos * fpitch + j] = v;
     }
 }
 
@@ -151,16 +155,25 @@ __global__ void k_nufft_interp3(const double* __restrict__ fine, int fx, int fy,
     }
 }
 
+// inverse transform of the zero-padded fine spectrum: column passes over the nonzero columns only, full row pass
+static int nufft2_inverse(Nufft2Plan* p, cudaStream_t st) {
+    GridPlan* f = p->fine;
+    int rc = grid_cols_inverse_n(f, p->fine_spec, p->fine_spec, p->ny / 2 + 1, st);
+    if (rc) return rc;
+    return fft_c2r_rows_nz(f->row, p->fine_spec, p->fine_real, f->nx, f->pitch, f->ny,
+                           1.0 / ((double)f->nx * (double)f->ny) * 2.0, p->ny / 2 + 1, st);
+}
+
 int nufft2_apply3(Nufft2Plan* p, const cplx* spec, int cn1, int cn2, const double* x, const double* y, int64_t npts,
                   double* out_v, double* out_dx, double* out_dy, cudaStream_t st) {
     GridPlan* f = p->fine;
-    const int64_t total = (int64_t)p->fx * f->pitch;
+    const int64_t total = (int64_t)p->fx * (p->ny / 2 + 1);
     const int blocks = (int)std::min<int64_t>(cdiv(total, 256), (int64_t)ipde_num_sms() * 8);
     const double scale = ((double)p->fx * (double)p->fy) / ((double)p->nx * (double)p->ny);
     k_nufft_pad<<<blocks, 256, 0, st>>>(spec, p->nx, p->ny, p->ny / 2 + 1, cn1, cn2, p->fine_spec, p->fx, p->fy, f->pitch,
                                         f->n1, f->n2, p->px, p->py, p->xh, p->yh, 0, 0, scale);
     KERNEL_CHECK();
-    int rc = grid_fft2_inverse(f, p->fine_spec, p->fine_spec, p->fine_real, st);
+    int rc = nufft2_inverse(p, st);
     if (rc) return rc;
     if (npts > 0) {
         const int b2 = (int)std::min<int64_t>(cdiv(npts * 32, 256), (int64_t)ipde_num_sms() * 16);
@@ -174,13 +187,13 @@ int nufft2_apply3(Nufft2Plan* p, const cplx* spec, int cn1, int cn2, const doubl
 int nufft2_apply(Nufft2Plan* p, const cplx* spec, int cn1, int cn2, int dxp, int dyp, const double* x, const double* y,
                  int64_t npts, double* out, cudaStream_t st) {
     GridPlan* f = p->fine;
-    const int64_t total = (int64_t)p->fx * f->pitch;
+    const int64_t total = (int64_t)p->fx * (p->ny / 2 + 1);
     const int blocks = (int)std::min<int64_t>(cdiv(total, 256), (int64_t)ipde_num_sms() * 8);
     const double scale = ((double)p->fx * (double)p->fy) / ((double)p->nx * (double)p->ny);
     k_nufft_pad<<<blocks, 256, 0, st>>>(spec, p->nx, p->ny, p->ny / 2 + 1, cn1, cn2, p->fine_spec, p->fx, p->fy, f->pitch,
                                         f->n1, f->n2, p->px, p->py, p->xh, p->yh, dxp, dyp, scale);
     KERNEL_CHECK();
-    int rc = grid_fft2_inverse(f, p->fine_spec, p->fine_spec, p->fine_real, st);
+    int rc = nufft2_inverse(p, st);
     if (rc) return rc;
     if (npts > 0) {
         const int b2 = (int)std::min<int64_t>(cdiv(npts * 32, 256), (int64_t)ipde_num_sms() * 16);
