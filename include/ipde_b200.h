@@ -240,9 +240,11 @@ int ipde_scalar_jumps(const double* bv, const double* bx, const double* by, cons
  * Replaces the dense factors of the reference's qfs objects (qfs.Laplace_QFS / Modified_Helmholtz_QFS / Stokes_QFS,
  * applied at ipde/solvers/internals/scalar.py:87-88,106 and internals/vector.py:124-125,150).
  * xhat: (n_in, N) complex, unnormalised N-point FFTs of the densities (FFT order);
- * band: (n_out, n_in, 2BH+1, 2Ks+1) complex, band[o,i,p+BH,k+Ks] multiplies mode k-p of input i into mode k of output o;
- * lowT: (n_out, n_in, 2KL+1, 2KL+1) complex, lowT[o,i,k'+KL,k+KL] (dense block of the lowest modes, transposed);
- * yhat: (ceil(n_out/2), M) complex spectra in FFT order, outputs 2q and 2q+1 packed as real and imaginary part. */
+ * The operators map real densities to real strengths, Q(-k,-k') = conj Q(k,k'): only output modes k >= 0 are stored.
+ * band: (n_out, n_in, 2BH+1, Ks+1) complex, band[o,i,p+BH,k] multiplies mode k-p of input i into mode k of output o;
+ * lowT: (n_out, n_in, 2KL+1, KL+1) complex, lowT[o,i,k'+KL,k] (dense block of the lowest modes, transposed);
+ * yhat: (ceil(n_out/2), M) complex spectra in FFT order (fully written: modes -k by conjugation, zero beyond Ks),
+ *       outputs 2q and 2q+1 packed as real and imaginary part; M >= 2 Ks + 2. */
 int ipde_banded_apply_z(const double* xhat, int n_in, int64_t N, const double* band, const double* lowT, int n_out, int BH,
                         int KL, int64_t Ks, double* yhat, int64_t M, void* stream);
 int ipde_real_to_complex(const double* x, double* z, int64_t n, void* stream);

@@ -298,29 +298,31 @@ __device__ __forceinline__ cplx banded_in_mode(const cplx* __restrict__ xh, int6
     return make_double2(v.x * s, v.y * s);
 }
 
+// The operators map real inputs to real outputs (Q(-k,-k') = conj Q(k,k'), enforced at setup), so only the output
+// modes k >= 0 are computed -- band[o,i,p,k] and lowT[o,i,k',k] are stored for k in [0, Ks] / [0, KL] only -- and
+// mode -k of every real output is the conjugate.
 template <int PS>
 __global__ void __launch_bounds__(32 * PS)
 k_banded_apply(const cplx* __restrict__ xh, int n_in, int64_t N, const cplx* __restrict__ band,
                const cplx* __restrict__ lowT, int n_out, int BH, int KL, int64_t Ks, cplx* __restrict__ yh, int64_t M) {
     __shared__ double red[PS][32][4];
     const int lane = threadIdx.x, ps = threadIdx.y;
-    const int64_t m = blockIdx.x * 32LL + lane;
+    const int64_t k = blockIdx.x * 32LL + lane;             // output mode, 0 .. M/2
     const int o0 = 2 * blockIdx.y, o1 = o0 + 1;
     const bool two = o1 < n_out;
-    const int64_t k = (m < (M + 1) / 2) ? m : m - M;
-    const bool live = (m < M) && (k >= -Ks) && (k <= Ks);
-    const int64_t nk = 2 * Ks + 1, ks = k + Ks;
+    const bool live = k <= Ks;
+    const int64_t nk = Ks + 1;
     const int64_t h = N / 2;
     const bool even = (N % 2) == 0;
     const int64_t hh = even ? h : (N - 1) / 2;
     const double invN = 1.0 / (double)N;
-    const int nb = 2 * BH + 1, nl = 2 * KL + 1;
+    const int nb = 2 * BH + 1, nl = 2 * KL + 1, nlk = KL + 1;
     cplx a0 = make_double2(0.0, 0.0), a1 = a0;
     if (live) {
         for (int i = 0; i < n_in; ++i) {
             const cplx* x = xh + (int64_t)i * N;
-            const cplx* b0 = band + ((int64_t)(o0 * n_in + i) * nb) * nk + ks;
-            const cplx* b1 = band + ((int64_t)((two ? o1 : o0) * n_in + i) * nb) * nk + ks;
+            const cplx* b0 = band + ((int64_t)(o0 * n_in + i) * nb) * nk + k;
+            const cplx* b1 = band + ((int64_t)((two ? o1 : o0) * n_in + i) * nb) * nk + k;
             for (int p = -BH + ps; p <= BH; p += PS) {
                 const cplx v = banded_in_mode(x, N, hh, even, k - p, invN);
                 const cplx c0 = b0[(int64_t)(p + BH) * nk];
@@ -332,16 +334,16 @@ k_banded_apply(const cplx* __restrict__ xh, int n_in, int64_t N, const cplx* __r
                     a1.y = fma(c1.x, v.y, fma(c1.y, v.x, a1.y));
                 }
             }
-            if (k >= -KL && k <= KL) {
-                const cplx* l0 = lowT + ((int64_t)(o0 * n_in + i) * nl) * nl + (k + KL);
-                const cplx* l1 = lowT + ((int64_t)((two ? o1 : o0) * n_in + i) * nl) * nl + (k + KL);
+            if (k <= KL) {
+                const cplx* l0 = lowT + ((int64_t)(o0 * n_in + i) * nl) * nlk + k;
+                const cplx* l1 = lowT + ((int64_t)((two ? o1 : o0) * n_in + i) * nl) * nlk + k;
                 for (int kp = -KL + ps; kp <= KL; kp += PS) {
                     const cplx v = banded_in_mode(x, N, hh, even, kp, invN);
-                    const cplx c0 = l0[(int64_t)(kp + KL) * nl];
+                    const cplx c0 = l0[(int64_t)(kp + KL) * nlk];
                     a0.x = fma(c0.x, v.x, fma(-c0.y, v.y, a0.x));
                     a0.y = fma(c0.x, v.y, fma(c0.y, v.x, a0.y));
                     if (two) {
-                        const cplx c1 = l1[(int64_t)(kp + KL) * nl];
+                        const cplx c1 = l1[(int64_t)(kp + KL) * nlk];
                         a1.x = fma(c1.x, v.x, fma(-c1.y, v.y, a1.x));
                         a1.y = fma(c1.x, v.y, fma(c1.y, v.x, a1.y));
                     }
@@ -351,21 +353,23 @@ k_banded_apply(const cplx* __restrict__ xh, int n_in, int64_t N, const cplx* __r
     }
     red[ps][lane][0] = a0.x; red[ps][lane][1] = a0.y; red[ps][lane][2] = a1.x; red[ps][lane][3] = a1.y;
     __syncthreads();
-    if (ps == 0 && m < M) {
+    if (ps == 0 && k <= M / 2) {
         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
         for (int q = 0; q < PS; ++q) { s0 += red[q][lane][0]; s1 += red[q][lane][1]; s2 += red[q][lane][2]; s3 += red[q][lane][3]; }
-        // (s0 + i s1) + i (s2 + i s3)
-        yh[(int64_t)blockIdx.y * M + m] = make_double2(s0 - s3, s1 + s2);
+        cplx* y = yh + (int64_t)blockIdx.y * M;
+        // mode k: a0 + i a1;  mode -k: conj(a0) + i conj(a1)
+        y[k] = make_double2(s0 - s3, s1 + s2);
+        if (k > 0 && k < M - k) y[M - k] = make_double2(s0 + s3, s2 - s1);
     }
 }
 
 int banded_apply_z(const cplx* xh, int n_in, int64_t N, const cplx* band, const cplx* lowT, int n_out, int BH, int KL,
                    int64_t Ks, cplx* yh, int64_t M, cudaStream_t st) {
-    ARG_CHECK(n_in >= 1 && n_out >= 1 && N >= 2 && M >= 2 * Ks + 1 && BH >= 0 && KL >= 0 && KL <= Ks, "banded_apply_z sizes");
+    ARG_CHECK(n_in >= 1 && n_out >= 1 && N >= 2 && M >= 2 * Ks + 2 && BH >= 0 && KL >= 0 && KL <= Ks, "banded_apply_z sizes");
     constexpr int PS = 8;
-    dim3 grid((unsigned)cdiv(M, 32), (unsigned)((n_out + 1) / 2));
-    KERNEL_TAG("k_banded_apply", 16.0 * ((double)n_out * n_in * ((2.0 * BH + 1) * (2.0 * Ks + 1) + (2.0 * KL + 1) * (2.0 * KL + 1))));
+    dim3 grid((unsigned)cdiv(M / 2 + 1, 32), (unsigned)((n_out + 1) / 2));
+    KERNEL_TAG("k_banded_apply", 16.0 * ((double)n_out * n_in * ((2.0 * BH + 1) * (Ks + 1.0) + (2.0 * KL + 1) * (KL + 1.0))));
     k_banded_apply<PS><<<grid, dim3(32, PS), 0, st>>>(xh, n_in, N, band, lowT, n_out, BH, KL, Ks, yh, M);
     KERNEL_CHECK();
     return IPDE_OK;

@@ -44,6 +44,8 @@ struct EwaldPlan {
     int64_t *og_lin = nullptr, *og_out = nullptr, *og_loc = nullptr;
     unsigned* tile_mask = nullptr;
     int in_lo = 0, in_hi = 0;            // rows of S_w that can be nonzero (active tiles)
+    int in_chi = 0;                      // columns of S_w beyond this one are zero (active tiles)
+    int grid_chi = 0;                    // grid targets only in columns below this one
     int grid_lo = 0, grid_hi = 0;        // rows holding grid targets
     int pts_lo = 0, pts_hi = 0;          // rows touched by the gather windows of the point targets   // 256 bits per tile: which nodes are grid targets (need the local sum)
     int64_t n_pt = 0;
@@ -291,12 +293,15 @@ int ewald_plan_create(int kind, double kappa, double xi, double h, double rc, in
     EW_UP(upload_arr(&p->tile_src, tile_src_host, (size_t)tile_ptr_host[ntiles], cudaMemcpyHostToDevice))
     EW_UP(upload_arr(&p->tile_map, tile_map_host, (size_t)p->ntx * p->nty, cudaMemcpyHostToDevice))
 #undef EW_UP
-    p->in_lo = px; p->in_hi = 0;
+    p->in_lo = px; p->in_hi = 0; p->in_chi = 0;
     for (int t = 0; t < ntiles; ++t) {
         p->in_lo = std::min(p->in_lo, tile_ix_host[t] * EW_TILE);
         p->in_hi = std::max(p->in_hi, std::min(px, (tile_ix_host[t] + 1) * EW_TILE));
+        p->in_chi = std::max(p->in_chi, std::min(py, (tile_iy_host[t] + 1) * EW_TILE));
     }
     if (p->in_hi <= p->in_lo) { p->in_lo = 0; p->in_hi = px; }
+    if (p->in_chi <= 0) p->in_chi = py;
+    p->grid_chi = py;
     p->grid_lo = 0; p->grid_hi = px; p->pts_lo = 0; p->pts_hi = px;
     const size_t nreal = (size_t)px * py, nspec = (size_t)px * (py / 2 + 1);
     CUDA_TRY(cudaMalloc(&p->Sw, sizeof(double) * nreal));
@@ -341,10 +346,14 @@ int ewald_set_grid_targets(EwaldPlan* p, int64_t n, const int64_t* lin_dev, cons
     if (n > 0) {
         std::vector<int64_t> h((size_t)n);
         CUDA_TRY(cudaMemcpy(h.data(), lin_dev, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost));
-        int64_t lo = h[0], hi = h[0];
-        for (int64_t i = 1; i < n; ++i) { lo = std::min(lo, h[i]); hi = std::max(hi, h[i]); }
+        int64_t lo = h[0], hi = h[0], chi = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            lo = std::min(lo, h[i]); hi = std::max(hi, h[i]);
+            chi = std::max(chi, h[i] % p->py);
+        }
         p->grid_lo = (int)(lo / p->py);
         p->grid_hi = (int)(hi / p->py) + 1;
+        p->grid_chi = (int)chi + 1;
     }
     cudaFree(p->tile_mask);
     p->tile_mask = nullptr;
@@ -400,8 +409,8 @@ int ewald_apply(EwaldPlan* p, const double* q, double* grid_out, double* point_o
     // zero padding: only rows [in_lo, in_hi) of S_w are nonzero, only the target rows of the result are needed
     const int out_lo = want_grid ? p->grid_lo : p->pts_lo, out_hi = want_grid ? p->grid_hi : p->pts_hi;
     const int win1[4] = {p->in_lo, p->in_hi, out_lo, out_hi};
-    int rc = fft_r2c_rows(G->row, p->Sw + (size_t)p->in_lo * G->ny, p->spec + (size_t)p->in_lo * G->pitch, p->in_hi - p->in_lo,
-                          G->ny, G->pitch, st);
+    int rc = fft_r2c_rows_nz(G->row, p->Sw + (size_t)p->in_lo * G->ny, p->spec + (size_t)p->in_lo * G->pitch,
+                             p->in_hi - p->in_lo, G->ny, G->pitch, p->in_chi, st);
     if (rc) return rc;
     ColMult MU, MH;
     MU.kind = 3; MU.k2c = 0.0; MU.table = p->multU; MU.fmul = 1; MU.ny = 0; MU.col_offset = 0; MU.deriv = 0;
@@ -410,8 +419,8 @@ int ewald_apply(EwaldPlan* p, const double* q, double* grid_out, double* point_o
     // p->spec when a second field follows); second field: symbol + inverse columns from that copy
     rc = grid_cols_symbol(G, p->spec, p->specw, (want_grid && want_pts) ? p->spec : nullptr, 1, want_grid ? MU : MH, st, win1);
     if (rc) return rc;
-    rc = fft_c2r_rows(G->row, p->specw + (size_t)out_lo * G->pitch, p->R + (size_t)out_lo * G->ny, out_hi - out_lo, G->pitch,
-                      G->ny, c2r_scale, st);
+    rc = fft_c2r_rows_nz(G->row, p->specw + (size_t)out_lo * G->pitch, p->R + (size_t)out_lo * G->ny, out_hi - out_lo, G->pitch,
+                         G->ny, c2r_scale, G->row->d.n + 1, st, want_grid ? p->grid_chi : 0);
     if (rc) return rc;
     if (want_grid) {
         const int gb = (int)std::min<int64_t>(cdiv(p->n_og, 256), (int64_t)ipde_num_sms() * 8);

@@ -1073,7 +1073,8 @@ template <int N, int SIGN>
 __global__ void __launch_bounds__(RegGeom<N>::NT, RegGeom<N>::MINB)
 k_fft_rows_reg_sub(const cplx* __restrict__ tw, const cplx* in, cplx* out, int64_t nsub, int R, int64_t in_pitch, int64_t in_sub,
                    int in_es, int64_t out_pitch, int64_t out_sub, int out_es, double scale, const double* __restrict__ mul,
-                   int64_t mul_pitch) {
+                   int64_t mul_pitch, int64_t in_nz) {
+    // in_nz: input elements with (strided) index >= in_nz are zero and are not read
     using G = RegGeom<N>;
     using K = RegCfg<N>;
     extern __shared__ cplx smem[];
@@ -1095,8 +1096,10 @@ k_fft_rows_reg_sub(const cplx* __restrict__ tw, const cplx* in, cplx* out, int64
         }
     } else {
 #pragma unroll
-        for (int s = 0; s < G::EPT; ++s)
-            v[s] = live ? src[(int64_t)reg_elem<N, K::R0>(jt, s) * in_es] : make_double2(0.0, 0.0);
+        for (int s = 0; s < G::EPT; ++s) {
+            const int64_t a = (int64_t)reg_elem<N, K::R0>(jt, s) * in_es;
+            v[s] = (live && a + r * in_sub < in_nz) ? src[a] : make_double2(0.0, 0.0);
+        }
     }
     reg_fft<N, SIGN, false>(v, line, jt, tw);
     if (live) {
@@ -1109,7 +1112,7 @@ k_fft_rows_reg_sub(const cplx* __restrict__ tw, const cplx* in, cplx* out, int64
 template <int N>
 static int launch_rows_reg_sub(FftPlan* ph, const cplx* in, cplx* out, int64_t nsub, int R, int64_t in_pitch, int64_t in_sub, int in_es,
                                int64_t out_pitch, int64_t out_sub, int out_es, int sign, double scale, const double* mul,
-                               int64_t mul_pitch, cudaStream_t st) {
+                               int64_t mul_pitch, int64_t in_nz, cudaStream_t st) {
     using G = RegGeom<N>;
     const unsigned g = (unsigned)cdiv(nsub, (int64_t)G::L);
     int rc;
@@ -1117,12 +1120,12 @@ static int launch_rows_reg_sub(FftPlan* ph, const cplx* in, cplx* out, int64_t n
         rc = set_smem(k_fft_rows_reg_sub<N, -1>, G::SMEM);
         if (rc) return rc;
         k_fft_rows_reg_sub<N, -1><<<g, G::NT, G::SMEM, st>>>(ph->d.tw, in, out, nsub, R, in_pitch, in_sub, in_es, out_pitch,
-                                                             out_sub, out_es, scale, mul, mul_pitch);
+                                                             out_sub, out_es, scale, mul, mul_pitch, in_nz);
     } else {
         rc = set_smem(k_fft_rows_reg_sub<N, +1>, G::SMEM);
         if (rc) return rc;
         k_fft_rows_reg_sub<N, +1><<<g, G::NT, G::SMEM, st>>>(ph->d.tw, in, out, nsub, R, in_pitch, in_sub, in_es, out_pitch,
-                                                             out_sub, out_es, scale, mul, mul_pitch);
+                                                             out_sub, out_es, scale, mul, mul_pitch, in_nz);
     }
     KERNEL_CHECK();
     return IPDE_OK;
@@ -1135,7 +1138,8 @@ template <int N>
 __global__ void __launch_bounds__(RegGeom<N>::NT, RegGeom<N>::MINB)
 k_c2r_rows_long(const cplx* __restrict__ tw, const cplx* __restrict__ twn, const cplx* __restrict__ half_tw,
                 const cplx* __restrict__ in, cplx* out, int64_t nsub, int64_t in_pitch, int64_t out_pitch, double scale,
-                int nz) {
+                int nz, int64_t out_nz) {
+    // out_nz: only the first out_nz complex pairs of an output row are needed; the others are not written
     // nz: only the first nz entries of an input row can be nonzero (zero-padded spectra: the NUFFT fine grid); the
     // others are not read
     using G = RegGeom<N>;
@@ -1170,18 +1174,21 @@ k_c2r_rows_long(const cplx* __restrict__ tw, const cplx* __restrict__ twn, const
     if (live) {
         cplx* dst = out + row * out_pitch + r;
 #pragma unroll
-        for (int s = 0; s < G::EPT; ++s) dst[(int64_t)reg_elem<N, G::RLAST>(jt, s) * 2] = cscale(v[s], scale);
+        for (int s = 0; s < G::EPT; ++s) {
+            const int64_t a = (int64_t)reg_elem<N, G::RLAST>(jt, s) * 2;
+            if (a + r < out_nz) dst[a] = cscale(v[s], scale);
+        }
     }
 }
 template <int N>
 static int launch_c2r_long(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
-                           double scale, int nz, cudaStream_t st) {
+                           double scale, int nz, int64_t out_nz, cudaStream_t st) {
     using G = RegGeom<N>;
     int rc = set_smem(k_c2r_rows_long<N>, G::SMEM);
     if (rc) return rc;
     const unsigned g = (unsigned)cdiv(2 * batch, (int64_t)G::L);
     k_c2r_rows_long<N><<<g, G::NT, G::SMEM, st>>>(p->half->d.tw, p->d.tw, p->half_tw_dev, in, reinterpret_cast<cplx*>(out),
-                                                  2 * batch, in_pitch, out_pitch / 2, scale, nz);
+                                                  2 * batch, in_pitch, out_pitch / 2, scale, nz, out_nz);
     KERNEL_CHECK();
     return IPDE_OK;
 }
@@ -1204,10 +1211,10 @@ static int ensure_split(FftPlan* p, int R) {
 static int ensure_half(FftPlan* p) { return ensure_split(p, 2); }
 static int rows_reg_sub(FftPlan* p, const cplx* in, cplx* out, int64_t nsub, int64_t in_pitch, int64_t in_sub, int in_es,
                         int64_t out_pitch, int64_t out_sub, int out_es, int sign, double scale, cudaStream_t st,
-                        const double* mul = nullptr, int64_t mul_pitch = 0) {
+                        const double* mul = nullptr, int64_t mul_pitch = 0, int64_t in_nz = (int64_t)1 << 60) {
     const int R = p->splitR;
     const int m = p->d.n / R;
-#define CALL_SUB(N_) return launch_rows_reg_sub<N_>(p->half, in, out, nsub, R, in_pitch, in_sub, in_es, out_pitch, out_sub, out_es, sign, scale, mul, mul_pitch, st)
+#define CALL_SUB(N_) return launch_rows_reg_sub<N_>(p->half, in, out, nsub, R, in_pitch, in_sub, in_es, out_pitch, out_sub, out_es, sign, scale, mul, mul_pitch, in_nz, st)
     REG_DISPATCH(m, CALL_SUB);
 #undef CALL_SUB
 }
@@ -1371,6 +1378,11 @@ __global__ void k_c2r_tangle(int n, const cplx* __restrict__ half_tw, const cplx
 
 int fft_r2c_rows(FftPlan* p, const double* in, cplx* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
                  cudaStream_t st) {
+    return fft_r2c_rows_nz(p, in, out, batch, in_pitch, out_pitch, 2 * (int64_t)p->d.n, st);
+}
+
+int fft_r2c_rows_nz(FftPlan* p, const double* in, cplx* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
+                    int64_t in_nz, cudaStream_t st) {
     if (batch <= 0) return IPDE_OK;
     const int n = p->d.n;
     if (!p->fast && !p->any && n <= IPDE_FFT_GENERIC_MAX) return fft_r2c_rows_generic(p, in, out, batch, in_pitch, out_pitch, st);
@@ -1378,9 +1390,11 @@ int fft_r2c_rows(FftPlan* p, const double* in, cplx* out, int64_t batch, int64_t
         int rc = ensure_half(p);
         if (rc) return rc;
         const int m = n / 2;
-        KERNEL_TAG("k_r2c_rows_long", (16.0 * n + 16.0 * (n + 1)) * (double)batch);
-        // packed row z[j] = (x[2j], x[2j+1]); sub-line r = z[2i + r]: element stride 2, offset r
-        rc = rows_reg_sub(p, reinterpret_cast<const cplx*>(in), out, 2 * batch, in_pitch / 2, 1, 2, out_pitch, m, 1, -1, 1.0, st);
+        KERNEL_TAG("k_r2c_rows_long", (8.0 * std::min<int64_t>(2 * (int64_t)n, in_nz) + 16.0 * (n + 1)) * (double)batch);
+        // packed row z[j] = (x[2j], x[2j+1]); sub-line r = z[2i + r]: element stride 2, offset r; reals beyond in_nz
+        // are zero (zero-padded rows of the evaluator box) and are not read
+        rc = rows_reg_sub(p, reinterpret_cast<const cplx*>(in), out, 2 * batch, in_pitch / 2, 1, 2, out_pitch, m, 1, -1, 1.0, st,
+                          nullptr, 0, (in_nz + 1) / 2);
         if (rc) return rc;
         const int blocks = (int)std::min<int64_t>(cdiv(batch * (m / 2 + 1), 256), (int64_t)ipde_num_sms() * 16);
         KERNEL_TAG("k_r2c_untangle_split", 32.0 * n * (double)batch);
@@ -1421,11 +1435,12 @@ int fft_r2c_rows(FftPlan* p, const double* in, cplx* out, int64_t batch, int64_t
 
 int fft_c2r_rows(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
                  double scale, cudaStream_t st) {
-    return fft_c2r_rows_nz(p, in, out, batch, in_pitch, out_pitch, scale, p->d.n + 1, st);
+    return fft_c2r_rows_nz(p, in, out, batch, in_pitch, out_pitch, scale, p->d.n + 1, st, 2 * (int64_t)p->d.n);
 }
 
 int fft_c2r_rows_nz(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
-                    double scale, int nz, cudaStream_t st) {
+                    double scale, int nz, cudaStream_t st, int64_t out_nz) {
+    if (out_nz <= 0) out_nz = 2 * (int64_t)p->d.n;
     if (batch <= 0) return IPDE_OK;
     const int n = p->d.n;
     if (!p->fast && !p->any && n <= IPDE_FFT_GENERIC_MAX) return fft_c2r_rows_generic(p, in, out, batch, in_pitch, out_pitch, scale, st);
@@ -1433,9 +1448,9 @@ int fft_c2r_rows_nz(FftPlan* p, const cplx* in, double* out, int64_t batch, int6
         int rc = ensure_half(p);
         if (rc) return rc;
         const int m = n / 2;
-        KERNEL_TAG("k_c2r_rows_long", (16.0 * n + 16.0 * std::min(n + 1, nz)) * (double)batch);
-        if (m == 4096) return launch_c2r_long<4096>(p, in, out, batch, in_pitch, out_pitch, scale, nz, st);
-        return launch_c2r_long<8192>(p, in, out, batch, in_pitch, out_pitch, scale, nz, st);
+        KERNEL_TAG("k_c2r_rows_long", (8.0 * std::min<int64_t>(2 * (int64_t)n, out_nz) + 16.0 * std::min(n + 1, nz)) * (double)batch);
+        if (m == 4096) return launch_c2r_long<4096>(p, in, out, batch, in_pitch, out_pitch, scale, nz, (out_nz + 1) / 2, st);
+        return launch_c2r_long<8192>(p, in, out, batch, in_pitch, out_pitch, scale, nz, (out_nz + 1) / 2, st);
     }
     if (n > IPDE_FFT_SMEM_MAX || !p->fast) {
         int rc = ensure_work(p, (size_t)3 * n * batch);

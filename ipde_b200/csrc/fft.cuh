@@ -74,8 +74,12 @@ int fft_r2c_rows(FftPlan* p, const double* in, cplx* out, int64_t batch, int64_t
 int fft_c2r_rows(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
                  double scale, cudaStream_t st);
 // the same when only the first nz entries of every input row can be nonzero (zero-padded spectra)
+// (and only the first out_nz reals of every output row are needed: 0 = all)
 int fft_c2r_rows_nz(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
-                    double scale, int nz, cudaStream_t st);
+                    double scale, int nz, cudaStream_t st, int64_t out_nz = 0);
+// real rows whose entries beyond in_nz are zero (zero-padded rows)
+int fft_r2c_rows_nz(FftPlan* p, const double* in, cplx* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
+                    int64_t in_nz, cudaStream_t st);
 
 // out = FFT( m * IFFT(in) ) / n  row-wise, m real (rows x n).  The annular variable-coefficient multiply
 // (reference ipde/utilities.py:123-124 `ffourier_multiply`).

@@ -58,8 +58,9 @@ class DeviceStructuredOperator(object):
     def __init__(self, op):
         self.op = op
         self.N, self.M, self.n_in, self.n_out = op.N, op.M, op.n_in, op.n_out
-        self.band = to_dev(op.band)
-        self.lowT = to_dev(np.ascontiguousarray(op.low.transpose(0, 1, 3, 2)))
+        # real-to-real operator: output modes k >= 0 only (the kernel mirrors the rest)
+        self.band = to_dev(np.ascontiguousarray(op.band[:, :, :, op.Ks:]))
+        self.lowT = to_dev(np.ascontiguousarray(op.low.transpose(0, 1, 3, 2)[:, :, :, op.KL:]))
         self.npair = (op.n_out + 1)//2
         self._zin = empty((op.n_in, op.N), torch.complex128)
         self._xh = empty((op.n_in, op.N), torch.complex128)
@@ -119,8 +120,8 @@ class DeviceCurveOperator(object):
     """
     def __init__(self, op):
         self.op = op
-        self.band = to_dev(op.band)
-        self.lowT = to_dev(np.ascontiguousarray(op.low.transpose(0, 1, 3, 2)))
+        self.band = to_dev(np.ascontiguousarray(op.band[:, :, :, op.Ks:]))
+        self.lowT = to_dev(np.ascontiguousarray(op.low.transpose(0, 1, 3, 2)[:, :, :, op.KL:]))
         self.npair = (op.n_out + 1)//2
         self._zin = empty((op.n_in, op.M), torch.complex128)
         self._xh = empty((op.n_in, op.M), torch.complex128)
