@@ -27,6 +27,7 @@ extern "C" {
 #define IPDE_KIND_POISSON 0
 #define IPDE_KIND_MODHELM 1
 #define IPDE_KIND_STOKES 2
+#define IPDE_KIND_LAPLACIAN 3   /* ipde_grid_scalar_multiply only: the symbol -(kx^2 + ky^2) itself (ebdyc.laplacian) */
 
 const char* ipde_last_error(void);
 int ipde_version(void);

@@ -487,6 +487,8 @@ __global__ void k_scalar_multiply(cplx* __restrict__ spec, int nx, int ny, int64
         if (kind == IPDE_KIND_POISSON) {
             const double lap = -(kx * kx + ky * ky);
             m = (i == 0 && j == 0) ? 0.0 : 1.0 / lap;
+        } else if (kind == IPDE_KIND_LAPLACIAN) {
+            m = -(kx * kx + ky * ky);          // ebdyc.laplacian: fch * self.lap (ipde/ebdy_collection.py:771-774)
         } else {
             m = 1.0 / (k2const + kx * kx + ky * ky);
         }

@@ -5,6 +5,7 @@
 #define IPDE_KIND_POISSON 0
 #define IPDE_KIND_MODHELM 1
 #define IPDE_KIND_STOKES 2
+#define IPDE_KIND_LAPLACIAN 3
 
 // Half-spectrum layout of a real (nx, ny) grid function: complex (nx, ny/2+1), row pitch ny/2+1.
 // When the column transform is split (n2 > 1) the rows of a spectrum are in four-step order:

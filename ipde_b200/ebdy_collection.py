@@ -253,6 +253,25 @@ class EmbeddedBoundaryCollection(object):
         _ = self.interpolate_radial_to_grid1(f.get_radial_value_list(), f['grid'])
 
     ############################################################################
+    # calculus on EmbeddedFunctions (ipde/ebdy_collection.py:708-792), on the device: ipde_b200/calculus.py
+    def _calculus(self):
+        if getattr(self, '_calc', None) is None or self._calc.D is not self.device:
+            from .calculus import DeviceCalculus
+            self._calc = DeviceCalculus(self)
+        return self._calc
+
+    def gradient(self, ff, derivative_type='spectral'):
+        """(fx, fy) EmbeddedFunctions; 'spectral' (cutoff + Fourier on the grid) or 'fourth' (centred differences)"""
+        from .device import to_dev
+        gx, gy = self._calculus().gradient_device(to_dev(np.asarray(ff, dtype=float).reshape(-1)), derivative_type)
+        return (EmbeddedFunction(self, linear_data=gx.cpu().numpy()), EmbeddedFunction(self, linear_data=gy.cpu().numpy()))
+
+    def laplacian(self, ff, derivative_type='spectral'):
+        from .device import to_dev
+        lap = self._calculus().laplacian_device(to_dev(np.asarray(ff, dtype=float).reshape(-1)), derivative_type)
+        return EmbeddedFunction(self, linear_data=lap.cpu().numpy())
+
+    ############################################################################
     def ready_bump(self, bump, bump_loc=None, bump_width=None):
         if bump_width is None:
             bump_width = self[0].radial_width

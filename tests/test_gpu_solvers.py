@@ -148,6 +148,12 @@ def test_stokes_single_boundary(solver_type):
         assert linf < TOL and l2 < TOL, (solver_type, linf, l2)
     assert abs(solver.iteration_counts[0] - O.iteration_counts[0]) <= 2
     assert u.shape == fu.shape and u[0].shape == (8, 200)
+    # a20: boundary getters of the vector solver (multi_boundary/vector.py:53-56)
+    bt = solver.get_boundary_tractions([u[0]], [v[0]], [p[0]])
+    tx, ty = solver.helpers[0].get_boundary_traction_uvp(u[0], v[0], p[0])
+    assert bt.shape == (400,) and np.array_equal(bt, np.concatenate([tx, ty]))
+    bvals = solver.get_boundary_values([u[0]])
+    assert bvals.shape == (200,)
 
 
 def test_stokes_converges_to_manufactured_solution():
@@ -634,3 +640,30 @@ def test_registration_on_device_matches_host(monkeypatch):
         assert np.array_equal(ea.grid_ia_xind, eb.grid_ia_xind) and np.array_equal(ea.grid_ia_yind, eb.grid_ia_yind)
         assert np.abs(ea.grid_ia_r - eb.grid_ia_r).max() < 1e-13
         assert np.abs(np.angle(np.exp(1j*(ea.grid_ia_t - eb.grid_ia_t)))).max() < 1e-13
+
+
+@pytest.mark.parametrize('derivative_type', ['spectral', 'fourth'])
+def test_embedded_function_calculus(derivative_type):
+    """ebdyc.gradient / ebdyc.laplacian on the device (ipde_b200/calculus.py) against the NumPy
+    restatement of ipde/ebdy_collection.py:708-792 on identical inputs, and against the analytic derivatives"""
+    from oracle import calculus as OC
+    ebdyc = three_bodies(nb=120, M=10)
+    kk = 2*np.pi/3
+    fn = lambda x, y: np.exp(np.sin(kk*x))*np.cos(kk*y)
+    ff = EmbeddedFunction_(ebdyc, fn)
+    gx, gy = ebdyc.gradient(ff, derivative_type)
+    lap = ebdyc.laplacian(ff, derivative_type)
+    ox, oy = OC.gradient(ebdyc, ff, derivative_type)
+    ol = OC.laplacian(ebdyc, ff, derivative_type)
+    for got, ref in ((gx, ox), (gy, oy), (lap, ol)):
+        assert np.abs(np.asarray(got) - ref).max() < 1e-11*max(1.0, np.abs(ref).max())
+    # analytic check on the radial blocks (spectral accuracy there in both modes)
+    n0 = ebdyc.grid_phys.N
+    ax = EmbeddedFunction_(ebdyc, lambda x, y: kk*np.cos(kk*x)*fn(x, y))
+    assert np.abs(np.asarray(gx)[n0:] - np.asarray(ax)[n0:]).max() < 1e-7
+    assert isinstance(ff.gradient()[0], type(ff))
+
+
+def EmbeddedFunction_(ebdyc, fn):
+    from ipde_b200.embedded_function import EmbeddedFunction
+    return EmbeddedFunction(ebdyc, function=fn)
