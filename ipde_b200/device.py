@@ -443,19 +443,23 @@ class FreeSpaceEvaluator(object):
         self.params = P
         sx = np.ascontiguousarray(sx, dtype=float); sy = np.ascontiguousarray(sy, dtype=float)
         self.nsrc = sx.size
+        # extents and the largest distance from the centre over sources and targets; the grid targets (1e8 of them at
+        # 16384^2) are handled as index tensors on the device
         xs, ys = [sx], [sy]
-        if grid_nodes is not None:
-            gix, giy = np.asarray(grid_nodes[0], dtype=np.int64), np.asarray(grid_nodes[1], dtype=np.int64)
-            xs.append(grid_x0 + h*gix)
-            ys.append(grid_y0 + h*giy)
         if points is not None:
             ptx = np.ascontiguousarray(points[0], dtype=float); pty = np.ascontiguousarray(points[1], dtype=float)
             xs.append(ptx); ys.append(pty)
-        # largest source-target distance, bounded by the bounding-box diagonal and by twice the enclosing radius
         lox, hix = min(a.min() for a in xs), max(a.max() for a in xs)
         loy, hiy = min(a.min() for a in ys), max(a.max() for a in ys)
+        if grid_nodes is not None:
+            gix = to_dev(np.asarray(grid_nodes[0]), torch.int64)
+            giy = to_dev(np.asarray(grid_nodes[1]), torch.int64)
+            lox, hix = min(lox, grid_x0 + h*int(gix.min())), max(hix, grid_x0 + h*int(gix.max()))
+            loy, hiy = min(loy, grid_y0 + h*int(giy.min())), max(hiy, grid_y0 + h*int(giy.max()))
         cx, cy = 0.5*(lox + hix), 0.5*(loy + hiy)
         r2max = max(((a - cx)**2 + (b - cy)**2).max() for a, b in zip(xs, ys))
+        if grid_nodes is not None:
+            r2max = max(r2max, float(((grid_x0 + h*gix - cx)**2 + (grid_y0 + h*giy - cy)**2).max()))
         D = min(np.hypot(hix - lox, hiy - loy), 2.0*np.sqrt(r2max))
         ax, ay = np.array([lox, hix]), np.array([loy, hiy])
         self.L = D + 2.0*np.sqrt(2.0)*P.m*h + 2.0*h
@@ -484,12 +488,13 @@ class FreeSpaceEvaluator(object):
         self.n_points = 0
         if grid_nodes is not None:
             bix, biy = gix - self.ilo_x, giy - self.ilo_y          # node indices inside the FFT box
-            lin = bix*self.py + biy
-            t = tmap[bix//E.TILE, biy//E.TILE].astype(np.int64)
-            loc = np.where(t >= 0, t*(E.TILE*E.TILE) + (bix % E.TILE)*E.TILE + (biy % E.TILE), -1)
-            pos = np.ascontiguousarray(grid_out_pos, dtype=np.int64)
-            self.n_grid = int(lin.size)
-            d_lin, d_loc, d_pos = to_dev(lin), to_dev(loc), to_dev(pos)     # keep alive across the call
+            d_lin = bix*self.py + biy
+            t = to_dev(tmap_c, torch.int64)[bix//E.TILE, biy//E.TILE]
+            d_loc = torch.where(t >= 0, t*(E.TILE*E.TILE) + (bix % E.TILE)*E.TILE + (biy % E.TILE),
+                                torch.full_like(t, -1))
+            d_pos = to_dev(np.asarray(grid_out_pos), torch.int64)
+            self.n_grid = int(d_lin.numel())
+            del gix, giy, bix, biy, t
             L_.ipde_ewald_set_grid_targets(hnd, self.n_grid, ptr(d_lin), ptr(d_loc), ptr(d_pos))
         if points is not None:
             self.n_points = int(ptx.size)

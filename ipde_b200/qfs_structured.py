@@ -212,7 +212,21 @@ class StructuredOperator(object):
     def __init__(self, N, M, n_in, n_out, KL, BH, Ks, low, band):
         self.N, self.M, self.n_in, self.n_out = N, M, n_in, n_out
         self.KL, self.BH, self.Ks = KL, BH, Ks
-        self.low, self.band = low, band
+        self.low_t, self.band_t = low, band          # torch tensors where they were built (the device, if any)
+        self._np = None
+
+    def _host(self):
+        if self._np is None:
+            self._np = (self.low_t.cpu().numpy(), self.band_t.cpu().numpy())
+        return self._np
+
+    @property
+    def low(self):
+        return self._host()[0]
+
+    @property
+    def band(self):
+        return self._host()[1]
 
     def in_modes(self, x):
         """x (n_in, N) real -> (n_in, N+1 or N) complex coefficients of modes -N/2..N/2 (Nyquist split)"""
@@ -291,17 +305,20 @@ def _solve_windows(Eb, Cb_list, J, Ks, h_in, col_block, Bw, scale_r, scale_c, pi
     ncol = 2*h_in + 1
     Bx = Bw + col_block
     outs = [torch.zeros((nc, nc, 2*Bx + 1, ncol), dtype=torch.complex128, device=dev) for _ in Cb_list]
+    blocks = []
     a = -h_in
     while a <= h_in:
         b = min(h_in + 1, a + col_block)
-        lo, hi = max(-Ks, a - Bw), min(Ks, b - 1 + Bw)
+        blocks.append((a, b, max(-Ks, a - Bw), min(Ks, b - 1 + Bw)))
+        a = b
+
+    def assemble(a, b, lo, hi):
         rows = torch.arange(lo, hi + 1, device=dev)
         cols = torch.arange(a, b, device=dev)
         nr, ncb = rows.numel(), cols.numel()
-        E = _dense_window(Eb, J, rows, rows)
         sr = scale_r(rows).repeat(nc)
         sc_ = scale_c(rows).repeat(nc)
-        Es = E*sr[:, None]*sc_[None, :]
+        Es = _dense_window(Eb, J, rows, rows)*sr[:, None]*sc_[None, :]
         rhs = []
         for Cb in Cb_list:
             if Cb is None:
@@ -313,11 +330,10 @@ def _solve_windows(Eb, Cb_list, J, Ks, h_in, col_block, Bw, scale_r, scale_c, pi
             else:
                 C = _dense_window(Cb, J, rows, cols)
             rhs.append(C*sr[:, None])
-        R = torch.cat(rhs, dim=1)
-        if pinv_low and lo <= 0 <= hi:
-            Y = _solve_deflated(Es, R)
-        else:
-            Y = torch.linalg.solve(Es, R)
+        return Es, torch.cat(rhs, dim=1), sc_, rows, cols
+
+    def scatter(Y, sc_, rows, cols, a, b, lo, hi):
+        nr, ncb = rows.numel(), cols.numel()
         Y = Y*sc_[:, None]
         w = nc*ncb
         pidx = rows[:, None] - cols[None, :] + Bx                       # (nr, ncb), in [0, 2Bx]
@@ -327,8 +343,27 @@ def _solve_windows(Eb, Cb_list, J, Ks, h_in, col_block, Bw, scale_r, scale_c, pi
             for o in range(nc):
                 for i in range(nc):
                     out[o, i][pidx, cidx] = Yl[o, :, i, :]
-        del E, Es, R, Y
-        a = b
+
+    # windows of equal shape are solved as one batched LU (most of them: every interior block); the window(s) holding
+    # mode 0 of a system with a field-free direction go through the deflated solve one at a time
+    groups = {}
+    for blk in blocks:
+        a, b, lo, hi = blk
+        if pinv_low and lo <= 0 <= hi:
+            Es, R, sc_, rows, cols = assemble(*blk)
+            scatter(_solve_deflated(Es, R), sc_, rows, cols, *blk)
+            continue
+        groups.setdefault((hi - lo, b - a), []).append(blk)
+    for (_, _), blks in groups.items():
+        nr = nc*(blks[0][3] - blks[0][2] + 1)
+        per = max(1, int(2.0e9//(16*nr*nr)))                            # <= 2 GB of window matrices per batch
+        for g0 in range(0, len(blks), per):
+            part = blks[g0:g0 + per]
+            items = [assemble(*blk) for blk in part]
+            Y = torch.linalg.solve(torch.stack([it[0] for it in items]), torch.stack([it[1] for it in items]))
+            for yb, it, blk in zip(Y, items, part):
+                scatter(yb, it[2], it[3], it[4], *blk)
+            del items, Y
     return Bx, outs
 
 
@@ -412,7 +447,29 @@ class CurveOperator(object):
     def __init__(self, N, M, n_in, n_out, KL, BH, Ks, low, band):
         self.N, self.M, self.n_in, self.n_out = N, M, n_in, n_out
         self.KL, self.BH, self.Ks = KL, BH, Ks
-        self.low, self.band = low, band
+        self.low_t, self.band_t = low, band
+        self.band_half_t = None                      # (n_out, n_in, 2BH+1, Ks+1): output modes k >= 0 only
+        self._np = None
+
+    def _host(self):
+        if self._np is None:
+            if self.band_t is None:
+                # full band from the stored half: B[p, -k] = conj B[-p, k]
+                half = self.band_half_t.cpu().numpy()
+                neg = np.conj(half[:, :, ::-1, :0:-1])
+                band = np.concatenate([neg, half], axis=3)
+            else:
+                band = self.band_t.cpu().numpy()
+            self._np = (self.low_t.cpu().numpy(), band)
+        return self._np
+
+    @property
+    def low(self):
+        return self._host()[0]
+
+    @property
+    def band(self):
+        return self._host()[1]
 
     def apply(self, q):
         """NumPy statement of the device apply; q (n_in, M) charges -> (n_out, N) field values"""
@@ -467,10 +524,13 @@ def source_to_curves(qfs, curves, pressure=False, tol=2e-15, KLc=(32, 64, 128, 2
     lows, bands = [], []
     for c in curves:
         lo_, ba_ = _fill(columns(c), Bx, Ks, Ks_src, KL, BH)
-        lows.append(lo_.cpu().numpy())
-        bands.append(ba_.cpu().numpy())
-    low, band = np.concatenate(lows, axis=0), np.concatenate(bands, axis=0)
-    return CurveOperator(N, M, nc, low.shape[0], KL, BH, Ks, low, band)
+        lows.append(lo_)
+        bands.append(ba_[:, :, :, Ks:].clone())                         # output modes k >= 0 (what the device reads)
+    low = torch.cat(lows, dim=0)
+    band_half = torch.cat(bands, dim=0)
+    op = CurveOperator(N, M, nc, low.shape[0], KL, BH, Ks, low, None)
+    op.band_half_t = band_half
+    return op
 
 
 class _Source(object):
@@ -609,7 +669,7 @@ class StructuredQFS(object):
         parts = [_fill(X, Bx, Ks, h_in, KL, BH) for X in Xs]
         low = torch.cat([p[0] for p in parts], dim=1)
         band = torch.cat([p[1] for p in parts], dim=1)
-        return StructuredOperator(self.N, self.M, nc*len(Xs), nc, KL, BH, Ks, low.cpu().numpy(), band.cpu().numpy())
+        return StructuredOperator(self.N, self.M, nc*len(Xs), nc, KL, BH, Ks, low, band)
 
     # -- NumPy statements (oracle side / setup-time use)
     def __call__(self, tau_list):

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 from ..._lib import lib
 from ...annular import ApproximateAnnularGeometry, RealAnnularGeometry
-from ...device import (to_dev, empty, ptr, stream, gemv, layer_apply_scalar)
+from ...device import (to_dev, empty, ptr, stream, gemv, layer_apply_scalar, require_cuda)
 
 
 class DeviceQFS(object):
@@ -58,9 +58,11 @@ class DeviceStructuredOperator(object):
     def __init__(self, op):
         self.op = op
         self.N, self.M, self.n_in, self.n_out = op.N, op.M, op.n_in, op.n_out
-        # real-to-real operator: output modes k >= 0 only (the kernel mirrors the rest)
-        self.band = to_dev(np.ascontiguousarray(op.band[:, :, :, op.Ks:]))
-        self.lowT = to_dev(np.ascontiguousarray(op.low.transpose(0, 1, 3, 2)[:, :, :, op.KL:]))
+        # real-to-real operator: output modes k >= 0 only (the kernel mirrors the rest); the arrays stay where the
+        # setup built them (the device)
+        dev = require_cuda()
+        self.band = op.band_t[:, :, :, op.Ks:].to(dev).contiguous()
+        self.lowT = op.low_t.transpose(2, 3)[:, :, :, op.KL:].to(dev).contiguous()
         self.npair = (op.n_out + 1)//2
         self._zin = empty((op.n_in, op.N), torch.complex128)
         self._xh = empty((op.n_in, op.N), torch.complex128)
@@ -120,8 +122,9 @@ class DeviceCurveOperator(object):
     """
     def __init__(self, op):
         self.op = op
-        self.band = to_dev(np.ascontiguousarray(op.band[:, :, :, op.Ks:]))
-        self.lowT = to_dev(np.ascontiguousarray(op.low.transpose(0, 1, 3, 2)[:, :, :, op.KL:]))
+        dev = require_cuda()
+        self.band = op.band_half_t.to(dev).contiguous()
+        self.lowT = op.low_t.transpose(2, 3)[:, :, :, op.KL:].to(dev).contiguous()
         self.npair = (op.n_out + 1)//2
         self._zin = empty((op.n_in, op.M), torch.complex128)
         self._xh = empty((op.n_in, op.M), torch.complex128)
