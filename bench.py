@@ -161,7 +161,7 @@ def cpu_sample_text(sample_n, info, N):
 
 def run_reference(args, rank, world):
     if rank != 0:
-        return
+        return None
     N = GRID[args.config]
     steps = max(1, min(args.steps, 3))
     warm = min(args.warmup, 1)
@@ -177,7 +177,7 @@ def run_reference(args, rank, world):
                              'kind': 'port', 'sample': cpu_sample_text(args.cpu_sample_n, info, N)},
             'e2e': {'value': rate, 'unit': 'grid-point-solves/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line))
+    return line
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -307,7 +307,28 @@ def run_stokes(args, N, barrier):
     return out
 
 
+class QuietStdout(object):
+    """file descriptor 1 -> stderr while libraries may chat (MAGMA / cuSOLVER banners); the JSON line is printed after"""
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def main():
+    with QuietStdout():
+        line = _main()
+    if line is not None:
+        print(json.dumps(line))
+
+
+def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=30)
@@ -327,8 +348,7 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.impl == 'reference':
-        run_reference(args, rank, world)
-        return
+        return run_reference(args, rank, world)
 
     import ctypes
     import torch
@@ -338,6 +358,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        # the ranks share the host cores (staging copies, NumPy setup): no oversubscription
+        torch.set_num_threads(max(1, (os.cpu_count() or world)//world))
     from ipde_b200._lib import lib
     from ipde_b200.device import to_dev, StageTimer, stream
     from ipde_b200.embedded_function import EmbeddedFunction
@@ -487,9 +509,9 @@ def main():
                                     'cores': info['threaded']['cores'], 'kind': 'port',
                                     'sample': cpu_sample_text(args.cpu_sample_n, info, N),
                                     'single_thread_numpy_fft': info['single_thread_numpy_fft']}
-        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    return line if rank == 0 else None
 
 
 if __name__ == '__main__':

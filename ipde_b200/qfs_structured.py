@@ -266,6 +266,19 @@ class StructuredOperator(object):
         return (np.fft.ifft(buf, axis=1)*M).real
 
 
+def _batched_solve(A, B):
+    """batched LU solve; on the GPU through cuSOLVER (MAGMA's batched path prints a size warning to stdout for
+    windows of this size, which would end up in front of bench.py's JSON line)"""
+    if A.is_cuda:
+        prev = torch.backends.cuda.preferred_linalg_library()
+        torch.backends.cuda.preferred_linalg_library('cusolver')
+        try:
+            return torch.linalg.solve(A, B)
+        finally:
+            torch.backends.cuda.preferred_linalg_library(prev)
+    return torch.linalg.solve(A, B)
+
+
 def _solve_deflated(Es, R, null_tol=1e-9):
     """
     Solve Es Y = R when Es may have ONE null direction (Stokes: a uniform normal force on a closed curve generates no
@@ -360,7 +373,7 @@ def _solve_windows(Eb, Cb_list, J, Ks, h_in, col_block, Bw, scale_r, scale_c, pi
         for g0 in range(0, len(blks), per):
             part = blks[g0:g0 + per]
             items = [assemble(*blk) for blk in part]
-            Y = torch.linalg.solve(torch.stack([it[0] for it in items]), torch.stack([it[1] for it in items]))
+            Y = _batched_solve(torch.stack([it[0] for it in items]), torch.stack([it[1] for it in items]))
             for yb, it, blk in zip(Y, items, part):
                 scatter(yb, it[2], it[3], it[4], *blk)
             del items, Y
