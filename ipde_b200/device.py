@@ -48,6 +48,46 @@ def hptr(a):
     return a.ctypes.data
 
 
+class HostStaging(object):
+    """
+    Host <-> device transfer of the flat EmbeddedFunction vectors for the public entry points.  EmbeddedFunctions
+    created by this package live in page-locked memory (embedded_function._allocate) and are copied straight from / to
+    the user's array; any other host array goes through a lazily allocated pinned staging buffer.
+    """
+
+    def __init__(self):
+        self._buf = {}
+
+    def _stage(self, key, n):
+        b = self._buf.get(key)
+        if b is None or b.numel() != n:
+            b = self._buf[key] = torch.empty(n, dtype=F64).pin_memory()
+        return b
+
+    def upload(self, key, src, dst):
+        t = torch.from_numpy(np.ascontiguousarray(src, dtype=float).reshape(-1))
+        if not t.is_pinned():
+            hb = self._stage(('in', key), t.numel())
+            hb.copy_(t)
+            t = hb
+        dst.copy_(t, non_blocking=True)
+
+    def download(self, pairs):
+        """pairs: [(device vector, host ndarray)]; one synchronisation for all of them"""
+        late = []
+        for key, (src, out) in enumerate(pairs):
+            t = torch.from_numpy(np.asarray(out).reshape(-1))
+            if t.is_pinned():
+                t.copy_(src, non_blocking=True)
+            else:
+                hb = self._stage(('out', key), t.numel())
+                hb.copy_(src, non_blocking=True)
+                late.append((t, hb))
+        torch.cuda.current_stream().synchronize()
+        for t, hb in late:
+            t.copy_(hb)
+
+
 def stream():
     return torch.cuda.current_stream().cuda_stream
 

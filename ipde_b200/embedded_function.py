@@ -15,6 +15,25 @@ import weakref
 import numpy as np
 
 
+PINNED_MIN_BYTES = 1 << 20
+
+
+def _allocate(cls, n, dtype):
+    """
+    Storage of a fresh EmbeddedFunction.  With a GPU present, vectors of a megabyte or more are page-locked (torch's
+    caching host allocator; the tensor stays alive as the array's base), so that the solvers' host entry points
+    (`solver(f)`, multi_boundary/scalar.py, vector.py) copy straight from / to the caller's array instead of through a
+    staging buffer.
+    """
+    dtype = np.dtype(dtype)
+    if n*dtype.itemsize >= PINNED_MIN_BYTES and dtype in (np.dtype(float), np.dtype(complex)):
+        import torch
+        if torch.cuda.is_available():
+            tdt = torch.float64 if dtype == np.dtype(float) else torch.complex128
+            return torch.empty(n, dtype=tdt, pin_memory=True).numpy().view(cls)
+    return np.ndarray.__new__(cls, n, dtype)
+
+
 def _sizes(ebdyc):
     gn = ebdyc.grid_phys.N
     rn = int(np.sum([int(np.prod(e.radial_shape)) for e in ebdyc]))
@@ -26,7 +45,7 @@ class EmbeddedFunction(np.ndarray):
                 radial_value_list=None, linear_data=None, zero=False):
         gn, rn = _sizes(ebdyc)
         if array is None:
-            array = np.ndarray.__new__(cls, gn + rn, dtype)
+            array = _allocate(cls, gn + rn, dtype)
         out = np.asarray(array).view(cls)
         out.ebdyc = weakref.ref(ebdyc)
         out._generate()

@@ -16,7 +16,7 @@ device->host copy of the result everything runs in libipde_b200.so:
 import numpy as np
 import torch
 from ..._lib import lib
-from ...device import to_dev, empty, ptr, stream, layer_apply_scalar
+from ...device import to_dev, empty, ptr, stream, layer_apply_scalar, HostStaging
 from ...embedded_function import EmbeddedFunction, BoundaryFunction
 from ...geometry import BoundaryCollection
 
@@ -241,26 +241,22 @@ class ScalarSolver(object):
         return res
 
     def _staging(self):
-        """persistent pinned host buffers + device input buffer for the public (host array) entry point"""
+        """host staging (device.HostStaging) + device input buffer for the public (host array) entry point"""
         if getattr(self, '_stage', None) is None:
-            n = self.ebdyc.dof
-            self._stage = (torch.empty(n, dtype=torch.float64).pin_memory(),
-                           torch.empty(n, dtype=torch.float64).pin_memory(), empty((n,)))
+            self._stage = (HostStaging(), empty((self.ebdyc.dof,)))
         return self._stage
 
     def __call__(self, f, out=None, **kwargs):
         """
         f must be of type EmbeddedFunction; returns a fresh EmbeddedFunction (as the reference does).
         Extension: `out=` an EmbeddedFunction of the same collection to receive the result (a time-stepping caller
-        avoids the page faults of a fresh 8*dof-byte host array per call).
+        avoids the page faults of a fresh 8*dof-byte host array per call).  EmbeddedFunctions are page-locked, so the
+        copies go straight from / to the caller's arrays.
         """
-        h_in, h_out, d_in = self._staging()
-        h_in.copy_(torch.from_numpy(np.ascontiguousarray(f, dtype=float).reshape(-1)))
-        d_in.copy_(h_in, non_blocking=True)
+        host, d_in = self._staging()
+        host.upload(0, f, d_in)
         res = self.solve_device(d_in, **kwargs)
-        h_out.copy_(res, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
         if out is None:
             out = EmbeddedFunction(self.ebdyc)
-        torch.from_numpy(np.asarray(out).reshape(-1)).copy_(h_out)
+        host.download([(res, out)])
         return out

@@ -17,7 +17,7 @@ GMRES.  On the device:
 import numpy as np
 import torch
 from ..._lib import lib
-from ...device import to_dev, empty, ptr, stream, layer_apply_stokes
+from ...device import to_dev, empty, ptr, stream, layer_apply_stokes, HostStaging
 from ...embedded_function import EmbeddedFunction, BoundaryFunction
 from ...geometry import BoundaryCollection
 
@@ -228,11 +228,10 @@ class VectorSolver(object):
         return res
 
     def _staging(self):
-        """persistent pinned host buffers + device input buffers for the public (host array) entry point"""
+        """host staging (device.HostStaging) + device input buffers for the public (host array) entry point"""
         if getattr(self, '_stage', None) is None:
             n = self.ebdyc.dof
-            pin = lambda: torch.empty(n, dtype=torch.float64).pin_memory()
-            self._stage = ([pin(), pin()], [pin(), pin(), pin()], [empty((n,)), empty((n,))])
+            self._stage = (HostStaging(), [empty((n,)), empty((n,))])
         return self._stage
 
     def __call__(self, fu, fv, out=None, **kwargs):
@@ -240,16 +239,11 @@ class VectorSolver(object):
         fu, fv: EmbeddedFunctions -> (u, v, p) fresh EmbeddedFunctions, as ipde/solvers/multi_boundary/vector.py:57-112.
         Extension: `out=(u, v, p)` EmbeddedFunctions of the same collection to receive the result (time stepping).
         """
-        h_in, h_out, d_in = self._staging()
-        for src, hb, db in zip((fu, fv), h_in, d_in):
-            hb.copy_(torch.from_numpy(np.ascontiguousarray(src, dtype=float).reshape(-1)))
-            db.copy_(hb, non_blocking=True)
+        host, d_in = self._staging()
+        for key, (src, db) in enumerate(zip((fu, fv), d_in)):
+            host.upload(key, src, db)
         res = self.solve_device(d_in[0], d_in[1], **kwargs)
-        for r, hb in zip(res, h_out):
-            hb.copy_(r, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
         if out is None:
             out = tuple(EmbeddedFunction(self.ebdyc) for _ in range(3))
-        for o, hb in zip(out, h_out):
-            torch.from_numpy(np.asarray(o).reshape(-1)).copy_(hb)
+        host.download(list(zip(res, out)))
         return tuple(out)

@@ -41,7 +41,7 @@ print('gmres its', solver.iteration_counts)
 # inhomogeneous solve only: compare with the analytic solution after a Dirichlet correction would need the
 # homogeneous step; here: stage timing + self-consistency (linearity) check
 solver.timer = StageTimer()
-d_in = solver._staging()[2]
+d_in = solver._staging()[1]
 for _ in range(3):
     solver.timer.events = []
     res = solver.solve_device(d_in, tol=1e-12, restart=40, maxiter=5)

@@ -667,3 +667,37 @@ def test_embedded_function_calculus(derivative_type):
 def EmbeddedFunction_(ebdyc, fn):
     from ipde_b200.embedded_function import EmbeddedFunction
     return EmbeddedFunction(ebdyc, function=fn)
+
+
+def test_bench_geometry_2048_against_fast_oracle(monkeypatch):
+    """BASELINE configs[2]/[4] geometry (bench.py) at 2048^2, n_b = 6144 + 1536 + 1536 + 768, M = 20 -- well beyond the
+    all-pairs oracle: the device solve (structured QFS, curve operators, spectral-Ewald evaluators, interface points
+    on the coarse split) against the O(N^2 log N) CPU statement oracle/fast.py (pinned to the direct oracle at 1e-14
+    in tests/test_oracle.py), plus size-independent properties: determinism, linearity, and independence of the
+    interface-point evaluator's spacing."""
+    import os
+    from problems import four_bodies_box
+    from oracle.fast import FastScalarSolver
+    from ipde_b200.solvers.multi_boundary.modified_helmholtz import ModifiedHelmholtzSolver
+    from ipde_b200.solvers.multi_boundary.scalar import ScalarSolver
+    k = 5.0
+    ebdyc = four_bodies_box(2048, M=20)
+    f, ua, _ = manufactured(ebdyc, k, kk=20*np.pi/7)
+    gm = dict(tol=1e-13, restart=50, maxiter=5)
+    monkeypatch.setattr(ScalarSolver, 'POINT_EVAL_COARSENING', 4)
+    solver = ModifiedHelmholtzSolver(ebdyc, k)
+    assert solver.evaluation == 'ewald' and solver.evaluator_p is not None
+    assert all(getattr(h.interface_qfs_g, 'structured', False) for h in solver.helpers[:3])
+    ue = solver(f, **gm)
+    pairs = [(h.interface_qfs_g, h.interface_qfs_r) for h in solver.helpers]
+    uo = FastScalarSolver(ebdyc, 'modified_helmholtz', k, pairs, workers=os.cpu_count())(f, **gm)
+    linf, l2 = rel_errors(ue, uo)
+    print('2048^2 four bodies vs fast oracle: linf %.2e l2 %.2e' % (linf, l2))
+    assert linf < TOL and l2 < TOL, (linf, l2)
+    assert np.array_equal(np.asarray(solver(f, **gm)), np.asarray(ue))
+    assert rel_errors(solver(2.5*f, **gm), 2.5*np.asarray(ue))[0] < 1e-10
+    monkeypatch.setattr(ScalarSolver, 'POINT_EVAL_COARSENING', 1)
+    fine = ModifiedHelmholtzSolver(ebdyc, k, helpers=solver.helpers)
+    assert fine.evaluator_p is None
+    linf, l2 = rel_errors(fine(f, **gm), ue)
+    assert linf < TOL and l2 < TOL, (linf, l2)

@@ -204,3 +204,31 @@ def test_registration_torch_path_matches_numpy_path(monkeypatch):
         assert np.array_equal(ea.grid_ia_xind, eb.grid_ia_xind) and np.array_equal(ea.grid_ia_yind, eb.grid_ia_yind)
         assert np.abs(ea.grid_ia_r - eb.grid_ia_r).max() < 1e-13
         assert np.abs(np.angle(np.exp(1j*(ea.grid_ia_t - eb.grid_ia_t)))).max() < 1e-13
+
+
+def test_registration_against_brute_force_closest_point():
+    """near.py (the restatement of near_finder): for a sample of annulus grid points |r| equals the brute-force
+    distance to a 64x upsampled polygon of the curve, the sign of r matches a winding-number inside test, and t is the
+    parameter of the closest point"""
+    ebdyc = three_bodies(nb=80, M=8)
+    rng = np.random.default_rng(3)
+    for e in ebdyc:
+        bdy = e.bdy
+        fine = fourier_resample(bdy.c, 64*bdy.N)
+        tf = 2*np.pi*np.arange(fine.size)/fine.size
+        sel = rng.choice(e.grid_ia_xind.size, size=min(150, e.grid_ia_xind.size), replace=False)
+        z = ebdyc.grid.xv[e.grid_ia_xind[sel]] + 1j*ebdyc.grid.yv[e.grid_ia_yind[sel]]
+        d = np.abs(z[:, None] - fine[None, :])
+        j = d.argmin(axis=1)
+        hmax = np.abs(np.diff(fine)).max()
+        ra = np.abs(e.grid_ia_r[sel])
+        # the nearest polygon vertex is at most s = hmax/2 along the curve from the foot point:
+        # d^2 <= r^2 + s^2 (1 + kappa r) + O(s^3)
+        bend = 1 + np.abs(bdy.curvature).max()*ra
+        bound = np.minimum(0.5*hmax, bend*hmax**2/(8*np.maximum(ra, 1e-300))) + 1e-12
+        assert np.all(d.min(axis=1) - ra >= -1e-12) and np.all(d.min(axis=1) - ra <= 1.05*bound)
+        assert np.abs(np.angle(np.exp(1j*(e.grid_ia_t[sel] - tf[j])))).max() < 1.5*(tf[1] - tf[0])
+        # winding number: inside <-> r < 0 for a counter-clockwise curve
+        ang = np.angle((np.roll(fine, -1)[None, :] - z[:, None])/(fine[None, :] - z[:, None])).sum(axis=1)/(2*np.pi)
+        inside = np.abs(ang) > 0.5
+        assert np.array_equal(inside, e.grid_ia_r[sel] < 0)
