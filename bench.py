@@ -213,49 +213,75 @@ def parse_profile(text):
 
 
 def run_slab(args, world, rank, barrier):
-    """periodic grid solve of ONE grid slab-decomposed over all ranks (strong scaling of the FFT core) and its error
-    against the same solve done by one GPU alone"""
+    """periodic grid solve of ONE grid slab-decomposed over all ranks (strong scaling of the FFT core), with the
+    transposes fused into the stores of the transform kernels over peer memory (SlabGridSolverP2P) and, as the
+    comparison, with pack + NCCL all-to-all + unpack (SlabGridSolver); error of both against one GPU's own solve"""
     import torch
     import torch.distributed as dist
-    from ipde_b200.distributed import SlabGridSolver
+    from ipde_b200.distributed import SlabGridSolver, SlabGridSolverP2P
     from ipde_b200.device import GridPlan, ptr, stream
     from ipde_b200._lib import lib
     ns = args.slab_grid
     h = 7.0/ns
-    S = SlabGridSolver(ns, ns, h, h, 1, HELMHOLTZ_K, chunks=args.slab_chunks)
-    rows = S.L.rows
+    rows = ns//world
     # the same global forcing on every rank (seeded), each rank keeps its slab
     gen = torch.Generator(device='cuda')
     gen.manual_seed(1234)
     full = torch.randn((ns, ns), dtype=torch.float64, device='cuda', generator=gen)
     fl = full[rank*rows:(rank + 1)*rows].contiguous()
-    out = torch.empty_like(fl)
-    for _ in range(3):
-        S.solve(fl, out=out)
-    barrier()
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record()
-    for _ in range(args.slab_steps):
-        S.solve(fl, out=out)
-    s1.record()
-    barrier()
-    tt = torch.tensor([s0.elapsed_time(s1)/args.slab_steps], dtype=torch.float64, device='cuda')
     # single-GPU solve of the whole grid on this rank, compared on the rank's own rows
     g = GridPlan(ns, ns, h, h)
     uch, work, uc = g.new_spec(), g.new_spec(), g.new_real()
     lib().ipde_grid_solve_scalar(g.h, 1, HELMHOLTZ_K, ptr(full), 0, ptr(uch), ptr(work), ptr(uc), stream())
-    ref = uc[rank*rows:(rank + 1)*rows]
-    err = torch.stack([(out - ref).abs().max(), ref.abs().max()])
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+    ref = uc[rank*rows:(rank + 1)*rows].clone()
     del full, uch, work, uc, g
-    return {'what': 'periodic modified-Helmholtz grid solve (r2c rows, all-to-all, column FFT + symbol + inverse, '
-                    'all-to-all, c2r rows) of ONE %d^2 grid slab-decomposed over all ranks; strong scaling of the FFT core' % ns,
-            'grid': [ns, ns], 'n_gpus': world, 'chunks': S.K, 'ms_per_solve': float(tt[0]),
-            'grid_point_solves_per_s': ns*ns/(float(tt[0])*1e-3),
+    torch.cuda.empty_cache()
+
+    def run(S):
+        out = torch.empty_like(fl)
+        for _ in range(3):
+            S.solve(fl, out=out)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.slab_steps):
+            S.solve(fl, out=out)
+        s1.record()
+        barrier()
+        tt = torch.tensor([s0.elapsed_time(s1)/args.slab_steps], dtype=torch.float64, device='cuda')
+        err = torch.stack([(out - ref).abs().max(), ref.abs().max()])
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        return float(tt[0]), float(err[0]), float(err[0]/err[1])
+
+    res = {'what': 'periodic modified-Helmholtz grid solve (r2c rows, transpose, column FFT + symbol + inverse, transpose, '
+                   'c2r rows) of ONE %d^2 grid slab-decomposed over all ranks; strong scaling of the FFT core' % ns,
+           'grid': [ns, ns], 'n_gpus': world}
+    try:
+        S = SlabGridSolverP2P(ns, ns, h, h, 1, HELMHOLTZ_K)
+        ms, e_abs, e_rel = run(S)
+        res.update({'exchange': 'fused into the kernels: r2c rows and the last column pass store straight into the peers\' '
+                                'slabs (CUDA IPC mappings over NVLink); two 4-byte all-reduces per solve as fences',
+                    'ms_per_solve': ms, 'grid_point_solves_per_s': ns*ns/(ms*1e-3),
+                    'p2p_store_bytes_per_rank_per_solve': int(S.p2p_bytes_per_rank),
+                    'max_abs_error_vs_single_gpu_solve': e_abs, 'relative': e_rel})
+        S.close()
+        del S
+    except Exception as exc:
+        res['p2p_error'] = '%s: %s' % (type(exc).__name__, exc)
+    torch.cuda.empty_cache()
+    S = SlabGridSolver(ns, ns, h, h, 1, HELMHOLTZ_K, chunks=args.slab_chunks)
+    ms, e_abs, e_rel = run(S)
+    nccl = {'exchange': 'pack + NCCL all_to_all_single + unpack', 'chunks': S.K, 'ms_per_solve': ms,
+            'grid_point_solves_per_s': ns*ns/(ms*1e-3),
             'alltoall_bytes_per_rank_per_solve': int(S.alltoall_bytes_per_rank),
-            'max_abs_error_vs_single_gpu_solve': float(err[0]), 'relative': float(err[0]/err[1])}
+            'max_abs_error_vs_single_gpu_solve': e_abs, 'relative': e_rel}
+    if 'ms_per_solve' in res:
+        res['nccl_all_to_all'] = nccl
+    else:
+        res.update(nccl)
+    return res
 
 
 def run_stokes(args, N, barrier):

@@ -95,6 +95,25 @@ int ipde_slab_unpack_chunk(const double* in, int64_t rows, int64_t P, int R, int
  * half spectrum; plan = ipde_grid_plan_create(nx, 2*(Pc-1), xh, yh) */
 int ipde_grid_cols_symbol_slab(void* plan, double* spec_in, double* spec_out, double* spec_copy, int copy_mode, int kind,
                                double k, int ny_global, double yh, int col_offset, void* stream);
+/* ---- the same slab solve with the two transposes done by the STORES of the transform kernels, straight into the
+ *      peers' buffers over NVLink (CUDA IPC mappings) -- no pack, no all-to-all, no unpack
+ *      (ipde_b200/distributed.py, SlabGridSolverP2P).
+ * Device buffers that other processes of the box can map: allocate + export a 64-byte handle / map a peer's handle */
+int ipde_ipc_alloc(int64_t bytes, void** dev_ptr, void* handle64);
+int ipde_ipc_open(const void* handle64, void** dev_ptr);
+int ipde_ipc_close(void* dev_ptr);
+int ipde_ipc_free(void* dev_ptr);
+/* r2c of the `rows` local rows (global rows row0 ...) of ny = 2 (P - 1) reals; entry (row, k) is stored into the column
+ * slab (nx, Pc) of rank k / Pc: peer_cols[q] = base of rank q's column slab (R pointers, host array).
+ * scratch: (rows, P) complex, local */
+int ipde_slab_r2c_rows_scatter(void* row_plan, const double* in, double* scratch, int64_t rows, int64_t in_pitch, int64_t P,
+                               int R, int64_t Pc, int64_t row0, void** peer_cols, void* stream);
+/* column FFT + symbol + inverse column FFT on this rank's column slab (nx, Pc) (overwritten; spec_work: same size), the
+ * last pass storing entry (row i, column col_offset + c) into the row slab (rows, P) of rank i / rows:
+ * peer_rows[q] = base of rank q's row slab.  plan = ipde_grid_plan_create(nx, 2*(Pc-1), xh, yh) */
+int ipde_slab_cols_symbol_scatter(void* plan, double* spec_in, double* spec_work, int kind, double k, int ny_global,
+                                  double yh, int col_offset, int R, int64_t rows, int64_t P, void** peer_rows,
+                                  void* stream);
 /* 4th-order centred differences, zero in the 2-cell border: ipde/derivatives.py:3-23 */
 int ipde_grid_fd4(void* plan, const double* f, double* fx, double* fy, void* stream);
 /* periodic cubic interpolation to points: fast_interp.interp2d(k=3) at ipde/ebdy_collection.py:594-603 */

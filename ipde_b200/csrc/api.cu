@@ -10,6 +10,7 @@
 #include "radial.cuh"
 #include "vector.cuh"
 #include <cstdarg>
+#include <cstring>
 #include <algorithm>
 #include <mutex>
 
@@ -206,6 +207,67 @@ int ipde_slab_pack_chunk(const double* in, int64_t rows, int64_t P, int R, int64
 int ipde_slab_unpack_chunk(const double* in, int64_t rows, int64_t P, int R, int64_t Pc, int64_t koff, int64_t Pk, double* out,
                            void* stream) {
     return grid_slab_unpack(CP(in), rows, P, R, Pc, koff, Pk, MP(out), ST(stream));
+}
+// device buffers shared between the processes of one box (CUDA IPC)
+int ipde_ipc_alloc(int64_t bytes, void** dev_ptr, void* handle64) {
+    ARG_CHECK(bytes > 0 && dev_ptr && handle64, "ipc alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, (size_t)bytes));
+    CUDA_TRY(cudaMemset(p, 0, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        ipde_set_error("cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+        return IPDE_ERR_CUDA;
+    }
+    memcpy(handle64, &h, 64);
+    *dev_ptr = p;
+    return IPDE_OK;
+}
+int ipde_ipc_open(const void* handle64, void** dev_ptr) {
+    ARG_CHECK(handle64 && dev_ptr, "ipc open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return IPDE_OK;
+}
+int ipde_ipc_close(void* dev_ptr) {
+    if (dev_ptr) CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+    return IPDE_OK;
+}
+int ipde_ipc_free(void* dev_ptr) {
+    if (dev_ptr) CUDA_TRY(cudaFree(dev_ptr));
+    return IPDE_OK;
+}
+static int fill_scatter(SlabScatter& S, int R, void** peers) {
+    ARG_CHECK(R >= 1 && R <= IPDE_SLAB_MAX_RANKS && peers, "slab scatter: 1..8 ranks");
+    S = slab_scatter_none();
+    S.R = R;
+    for (int q = 0; q < R; ++q) {
+        ARG_CHECK(peers[q], "slab scatter: null peer buffer");
+        S.base[q] = (cplx*)peers[q];
+    }
+    return IPDE_OK;
+}
+int ipde_slab_r2c_rows_scatter(void* row_plan, const double* in, double* scratch, int64_t rows, int64_t in_pitch, int64_t P,
+                               int R, int64_t Pc, int64_t row0, void** peer_cols, void* stream) {
+    SlabScatter S;
+    int rc = fill_scatter(S, R, peer_cols);
+    if (rc) return rc;
+    S.rows = (int)rows; S.Pc = Pc; S.P = P; S.row0 = row0; S.col0 = 0;
+    return fft_r2c_rows_scatter((FftPlan*)row_plan, in, MP(scratch), rows, in_pitch, P, S, ST(stream));
+}
+int ipde_slab_cols_symbol_scatter(void* plan, double* spec_in, double* spec_work, int kind, double k, int ny_global,
+                                  double yh, int col_offset, int R, int64_t rows, int64_t P, void** peer_rows,
+                                  void* stream) {
+    SlabScatter S;
+    int rc = fill_scatter(S, R, peer_rows);
+    if (rc) return rc;
+    GridPlan* g = (GridPlan*)plan;
+    S.rows = (int)rows; S.Pc = g->pitch; S.P = P; S.row0 = 0; S.col0 = col_offset;
+    return grid_cols_symbol_slab_scatter(g, MP(spec_in), MP(spec_work), kind, k, ny_global, yh, col_offset, S, ST(stream));
 }
 int ipde_grid_cols_symbol_slab(void* plan, double* spec_in, double* spec_out, double* spec_copy, int copy_mode, int kind,
                                double k, int ny_global, double yh, int col_offset, void* stream) {

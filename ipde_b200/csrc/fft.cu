@@ -5,6 +5,8 @@
 #include "fft_short.cuh"
 #include "fft_reg.cuh"
 #include <algorithm>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 // ------------------------------------------------------------------------------------------
 // plans
@@ -317,7 +319,7 @@ template <int RA, int RB, int SIGN>
 __global__ void __launch_bounds__(128, 4)
 k_fft_cols_short(const cplx* __restrict__ tw, const cplx* in, cplx* out, int64_t elem_stride, int64_t n_inner,
                  int64_t outer_stride, double scale, int tw_mode, const cplx* __restrict__ tw_big, RowWindow W,
-                 int tiles_per_outer, int ntiles_total) {
+                 int tiles_per_outer, int ntiles_total, const SlabScatter sc) {
     using K = ShortCfg<RA, RB>;
     constexpr int E = K::EPT;
     __shared__ cplx sm[K::NBUF][K::TILE];
@@ -362,7 +364,11 @@ k_fft_cols_short(const cplx* __restrict__ tw, const cplx* in, cplx* out, int64_t
                     const cplx w = tw_big[S.o * e];
                     r = (SIGN < 0) ? cmul(r, w) : cmulc(r, w);
                 }
-                out[S.base + (int64_t)e * elem_stride] = cscale(r, scale);
+                if (sc.R) {                               // backward slab transpose on the stores
+                    if (sc.col0 + S.col < sc.P) *slab_bwd_addr(sc, row, S.col) = cscale(r, scale);
+                } else {
+                    out[S.base + (int64_t)e * elem_stride] = cscale(r, scale);
+                }
             }
         }
         if (K::PREFETCH) {
@@ -550,7 +556,7 @@ bool fft_short_enabled() { return g_fft_short; }
 template <int RA, int RB>
 static int launch_cols_short(FftPlan* p, const cplx* in, cplx* out, int64_t elem_stride, int64_t n_inner, int64_t n_outer,
                              int64_t outer_stride, int sign, double scale, int tw_mode, const cplx* tw_big, RowWindow W,
-                             cudaStream_t st) {
+                             cudaStream_t st, const SlabScatter& sc) {
     using K = ShortCfg<RA, RB>;
     const int64_t tiles = cdiv(n_inner, (int64_t)K::C);
     const int64_t total = tiles * n_outer;
@@ -559,10 +565,10 @@ static int launch_cols_short(FftPlan* p, const cplx* in, cplx* out, int64_t elem
     const unsigned g = (unsigned)std::min<int64_t>(total, (int64_t)ipde_num_sms() * per_sm);
     if (sign < 0)
         k_fft_cols_short<RA, RB, -1><<<g, 128, 0, st>>>(p->d.tw, in, out, elem_stride, n_inner, outer_stride, scale, tw_mode,
-                                                        tw_big, W, (int)tiles, (int)total);
+                                                        tw_big, W, (int)tiles, (int)total, sc);
     else
         k_fft_cols_short<RA, RB, +1><<<g, 128, 0, st>>>(p->d.tw, in, out, elem_stride, n_inner, outer_stride, scale, tw_mode,
-                                                        tw_big, W, (int)tiles, (int)total);
+                                                        tw_big, W, (int)tiles, (int)total, sc);
     KERNEL_CHECK();
     return IPDE_OK;
 }
@@ -748,10 +754,21 @@ int fft_cols(FftPlan* p, const cplx* in, cplx* out, int64_t elem_stride, int64_t
 
 int fft_cols_windowed(FftPlan* p, const cplx* in, cplx* out, int64_t elem_stride, int64_t n_inner, int64_t n_outer,
                       int64_t outer_stride, int sign, double scale, int tw_mode, const cplx* tw_big, RowWindow W,
-                      cudaStream_t st) {
+                      cudaStream_t st, const SlabScatter* sc) {
     if (n_inner <= 0 || n_outer <= 0) return IPDE_OK;
     const int n = p->d.n;
     ARG_CHECK(p->fast && n <= IPDE_FFT_SMEM_MAX, "windowed column transform needs a tile-engine length");
+    if (sc && sc->R) {
+        // slab transpose on the stores: only the register-resident short pass implements it
+        if (!(g_fft_short && p->pow2 && fft_short_size_plain(n) && W.row_e != 0)) {
+            ipde_set_error("fft_cols: scattered stores need a short power-of-two four-step pass (n = %d)", n);
+            return IPDE_ERR_UNSUPPORTED;
+        }
+        KERNEL_TAG("k_fft_cols", 32.0 * (double)n * (double)n_inner * (double)n_outer);
+#define CALL_SHORT(RA_, RB_) return launch_cols_short<RA_, RB_>(p, in, out, elem_stride, n_inner, n_outer, outer_stride, sign, scale, tw_mode, tw_big, W, st, *sc)
+        SHORT_DISPATCH_PLAIN(n, CALL_SHORT);
+#undef CALL_SHORT
+    }
     int C = pow2_floor(IPDE_FFT_SMEM_MAX / n);
     if (C > 16) C = 16;
     while (C > 1 && C / 2 >= n_inner) C /= 2;
@@ -780,7 +797,7 @@ int fft_cols_windowed(FftPlan* p, const cplx* in, cplx* out, int64_t elem_stride
         if (done) return IPDE_OK;
     }
     if (g_fft_short && p->pow2 && fft_short_size_plain(n)) {
-#define CALL_SHORT(RA_, RB_) return launch_cols_short<RA_, RB_>(p, in, out, elem_stride, n_inner, n_outer, outer_stride, sign, scale, tw_mode, tw_big, W, st)
+#define CALL_SHORT(RA_, RB_) return launch_cols_short<RA_, RB_>(p, in, out, elem_stride, n_inner, n_outer, outer_stride, sign, scale, tw_mode, tw_big, W, st, slab_scatter_none())
         SHORT_DISPATCH_PLAIN(n, CALL_SHORT);
 #undef CALL_SHORT
     }
@@ -874,7 +891,7 @@ k_c2r_rows(FftPlanDev P, const cplx* __restrict__ half_tw, const cplx* __restric
 template <int N>
 __global__ void __launch_bounds__(RegGeom<N>::NT, RegGeom<N>::MINB)
 k_r2c_rows_reg(const cplx* __restrict__ tw, const cplx* __restrict__ half_tw, const double* __restrict__ in,
-               cplx* __restrict__ out, int64_t batch, int64_t in_pitch, int64_t out_pitch) {
+               cplx* __restrict__ out, int64_t batch, int64_t in_pitch, int64_t out_pitch, const SlabScatter sc) {
     using G = RegGeom<N>;
     using K = RegCfg<N>;
     extern __shared__ cplx smem[];
@@ -901,8 +918,13 @@ k_r2c_rows_reg(const cplx* __restrict__ tw, const cplx* __restrict__ half_tw, co
             const cplx zc = cconj(line[reg_pad<G::SH>(k == 0 ? 0 : N - k)]);
             const cplx E = cscale(cadd(zk, zc), 0.5);
             const cplx O = cmulni(cscale(csub(zk, zc), 0.5));
-            dst[k] = cadd(E, cmul(half_tw[k], O));
-            if (k == 0) dst[N] = cadd(E, cmul(half_tw[N], O));
+            if (sc.R) {                                   // forward slab transpose on the stores
+                *slab_fwd_addr(sc, row, k) = cadd(E, cmul(half_tw[k], O));
+                if (k == 0) *slab_fwd_addr(sc, row, N) = cadd(E, cmul(half_tw[N], O));
+            } else {
+                dst[k] = cadd(E, cmul(half_tw[k], O));
+                if (k == 0) dst[N] = cadd(E, cmul(half_tw[N], O));
+            }
         }
     }
 }
@@ -910,7 +932,8 @@ k_r2c_rows_reg(const cplx* __restrict__ tw, const cplx* __restrict__ half_tw, co
 template <int N>
 __global__ void __launch_bounds__(RegGeom<N>::NT, RegGeom<N>::MINB)
 k_c2r_rows_reg(const cplx* __restrict__ tw, const cplx* __restrict__ half_tw, const cplx* __restrict__ in,
-               double* __restrict__ out, int64_t batch, int64_t in_pitch, int64_t out_pitch, double scale) {
+               double* __restrict__ out, int64_t batch, int64_t in_pitch, int64_t out_pitch, double scale,
+               const uint32_t* __restrict__ mask, int64_t mask_pitch) {
     using G = RegGeom<N>;
     using K = RegCfg<N>;
     extern __shared__ cplx smem[];
@@ -937,30 +960,39 @@ k_c2r_rows_reg(const cplx* __restrict__ tw, const cplx* __restrict__ half_tw, co
     reg_fft<N, +1, false>(v, line, jt, tw);
     if (live) {
         cplx* dst = reinterpret_cast<cplx*>(out + row * out_pitch);
+        if (mask) {                                    // bit per block of 64 reals = 32 packed samples
+            const uint32_t* mrow = mask + row * mask_pitch;
 #pragma unroll
-        for (int s = 0; s < G::EPT; ++s) dst[reg_elem<N, G::RLAST>(jt, s)] = cscale(v[s], scale);
+            for (int s = 0; s < G::EPT; ++s) {
+                const int e = reg_elem<N, G::RLAST>(jt, s);
+                if ((mrow[e >> 10] >> ((e >> 5) & 31)) & 1u) dst[e] = cscale(v[s], scale);
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < G::EPT; ++s) dst[reg_elem<N, G::RLAST>(jt, s)] = cscale(v[s], scale);
+        }
     }
 }
 
 template <int N>
 static int launch_r2c_reg(FftPlan* p, const double* in, cplx* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
-                          cudaStream_t st) {
+                          cudaStream_t st, const SlabScatter& sc = slab_scatter_none()) {
     using G = RegGeom<N>;
     int rc = set_smem(k_r2c_rows_reg<N>, G::SMEM);
     if (rc) return rc;
     k_r2c_rows_reg<N><<<(unsigned)cdiv(batch, (int64_t)G::L), G::NT, G::SMEM, st>>>(p->d.tw, p->half_tw_dev, in, out, batch,
-                                                                                   in_pitch, out_pitch);
+                                                                                   in_pitch, out_pitch, sc);
     KERNEL_CHECK();
     return IPDE_OK;
 }
 template <int N>
 static int launch_c2r_reg(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
-                          double scale, cudaStream_t st) {
+                          double scale, const uint32_t* mask, int64_t mask_pitch, cudaStream_t st) {
     using G = RegGeom<N>;
     int rc = set_smem(k_c2r_rows_reg<N>, G::SMEM);
     if (rc) return rc;
     k_c2r_rows_reg<N><<<(unsigned)cdiv(batch, (int64_t)G::L), G::NT, G::SMEM, st>>>(p->d.tw, p->half_tw_dev, in, out, batch,
-                                                                                   in_pitch, out_pitch, scale);
+                                                                                   in_pitch, out_pitch, scale, mask, mask_pitch);
     KERNEL_CHECK();
     return IPDE_OK;
 }
@@ -1132,64 +1164,100 @@ static int launch_rows_reg_sub(FftPlan* ph, const cplx* in, cplx* out, int64_t n
 }
 
 // c2r of rows of 2n reals, n = 2m: the tangle step (half spectrum X[0..n] -> packed spectrum Z) and the radix-2
-// split (A = Z[k] + Z[k+m], B = (Z[k] - Z[k+m]) conj(w^k)) are applied on the loads of the m-point inverse transform;
-// sub-line r = 0 / 1 of a row produces the even / odd packed samples, stored with element stride 2.
+// split (A = Z[k] + Z[k+m], B = (Z[k] - Z[k+m]) conj(w^k)) are applied on the loads of the m-point inverse transform.
+// A row is owned by a CLUSTER OF TWO CTAs: rank 0 transforms A (even packed samples), rank 1 transforms B (odd ones).
+//   loads    rank c tangles and splits the half k in [c m/2, (c+1) m/2) of the row: it keeps its own kind and puts the
+//            other kind into the peer's shared memory (DSMEM) -- every spectrum entry is read from global memory once;
+//   stores   the outputs are exchanged through DSMEM again so that rank c writes the contiguous half
+//            [c n, (c+1) n) reals of the row: 32 contiguous bytes per thread (the first version stored 16-byte pieces
+//            with a stride of 32 from two CTAs: half-written sectors, 1.67 TB/s);
+//   mask     optional bit per (row, block of 64 reals): blocks whose bit is clear are not stored, rows without any
+//            bit are skipped altogether (the NUFFT fine grid is only read around the interface points).
 template <int N>
-__global__ void __launch_bounds__(RegGeom<N>::NT, RegGeom<N>::MINB)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RegGeom<N>::NT, RegGeom<N>::MINB)
 k_c2r_rows_long(const cplx* __restrict__ tw, const cplx* __restrict__ twn, const cplx* __restrict__ half_tw,
-                const cplx* __restrict__ in, cplx* out, int64_t nsub, int64_t in_pitch, int64_t out_pitch, double scale,
-                int nz, int64_t out_nz) {
+                const cplx* __restrict__ in, double* __restrict__ out, int64_t in_pitch, int64_t out_pitch, double scale,
+                int nz, int64_t out_nz, const uint32_t* __restrict__ mask, int64_t mask_pitch) {
     // out_nz: only the first out_nz complex pairs of an output row are needed; the others are not written
     // nz: only the first nz entries of an input row can be nonzero (zero-padded spectra: the NUFFT fine grid); the
     // others are not read
     using G = RegGeom<N>;
     using K = RegCfg<N>;
+    static_assert(G::L == 1 && G::EPT == 16 && K::R0 == 16, "pair kernel: one line per CTA, radix-16 first stage");
+    constexpr int RL = G::RLAST;
+    constexpr int m = N, n = 2 * N, H = N / 2, Q = N / 16;
     extern __shared__ cplx smem[];
-    constexpr int m = N, n = 2 * N;
-    const int tid = threadIdx.x;
-    const int l = tid >> G::LOGT, jt = tid & (G::T - 1);
-    cplx* line = smem + l * G::LINE;
-    const int64_t sub = (int64_t)blockIdx.x * G::L + l;
-    const bool live = sub < nsub;
-    const int64_t row = (live ? sub : 0) >> 1;
-    const int r = (int)(sub & 1);
+    cg::cluster_group cluster = cg::this_cluster();
+    const int c = (int)cluster.block_rank();
+    const int jt = threadIdx.x;
+    const int64_t row = blockIdx.x >> 1;
+    const uint32_t* mrow = mask ? mask + row * mask_pitch : nullptr;
+    if (mrow) {
+        uint32_t any = 0;
+#pragma unroll
+        for (int w = 0; w < N / 512; ++w) any |= mrow[w];
+        if (!any) return;                              // both CTAs of the pair take the same decision
+    }
+    cplx* line = smem;
+    cplx* peer = cluster.map_shared_rank(line, c ^ 1);
+    cluster.sync();                                    // the peer CTA is running: its shared memory may be written
     const cplx* src = in + row * in_pitch;
+    cplx keep[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int k = jt + (8 * c + q) * Q;
+        // Z[kk] = E + i O,  E = (X[kk] + conj X[n-kk])/2,  O = (X[kk] - conj X[n-kk])/2 * conj(half_tw[kk])
+        const cplx zero = make_double2(0.0, 0.0);
+        const cplx x0 = (k < nz) ? src[k] : zero, c0 = (n - k < nz) ? cconj(src[n - k]) : zero;
+        const cplx x1 = (k + m < nz) ? src[k + m] : zero, c1 = (m - k < nz) ? cconj(src[m - k]) : zero;
+        const cplx z0 = cadd(cscale(cadd(x0, c0), 0.5), cmuli(cmulc(cscale(csub(x0, c0), 0.5), half_tw[k])));
+        const cplx z1 = cadd(cscale(cadd(x1, c1), 0.5), cmuli(cmulc(cscale(csub(x1, c1), 0.5), half_tw[k + m])));
+        const cplx A = cadd(z0, z1), B = cmulc(csub(z0, z1), twn[k]);
+        keep[q] = c ? B : A;
+        peer[jt + q * Q] = c ? A : B;
+    }
+    cluster.sync();
     cplx v[G::EPT];
 #pragma unroll
-    for (int s = 0; s < G::EPT; ++s) {
-        const int k = reg_elem<N, K::R0>(jt, s);
-        if (live) {
-            // Z[kk] = E + i O,  E = (X[kk] + conj X[n-kk])/2,  O = (X[kk] - conj X[n-kk])/2 * conj(half_tw[kk])
-            const cplx zero = make_double2(0.0, 0.0);
-            const cplx x0 = (k < nz) ? src[k] : zero, c0 = (n - k < nz) ? cconj(src[n - k]) : zero;
-            const cplx x1 = (k + m < nz) ? src[k + m] : zero, c1 = (m - k < nz) ? cconj(src[m - k]) : zero;
-            const cplx z0 = cadd(cscale(cadd(x0, c0), 0.5), cmuli(cmulc(cscale(csub(x0, c0), 0.5), half_tw[k])));
-            const cplx z1 = cadd(cscale(cadd(x1, c1), 0.5), cmuli(cmulc(cscale(csub(x1, c1), 0.5), half_tw[k + m])));
-            v[s] = (r == 0) ? cadd(z0, z1) : cmulc(csub(z0, z1), twn[k]);
-        } else {
-            v[s] = make_double2(0.0, 0.0);
-        }
+    for (int q = 0; q < 8; ++q) {
+        const cplx o = line[jt + q * Q];
+        v[q] = c ? o : keep[q];
+        v[8 + q] = c ? keep[q] : o;
     }
-    reg_fft<N, +1, false>(v, line, jt, tw);
-    if (live) {
-        cplx* dst = out + row * out_pitch + r;
+    reg_fft<N, +1, true>(v, line, jt, tw);
+    // y_c[e] = z[2e + c] (packed sample = two reals).  Plane c of the owner of e's half <- y_c
+    cluster.sync();
 #pragma unroll
-        for (int s = 0; s < G::EPT; ++s) {
-            const int64_t a = (int64_t)reg_elem<N, G::RLAST>(jt, s) * 2;
-            if (a + r < out_nz) dst[a] = cscale(v[s], scale);
-        }
+    for (int s = 0; s < G::EPT; ++s) {
+        const int e = reg_elem<N, RL>(jt, s);
+        const bool upper = (s % RL) >= RL / 2;         // e >= H, known at compile time
+        cplx* dst = ((int)upper == c) ? line : peer;
+        dst[c * H + (e - (upper ? H : 0))] = cscale(v[s], scale);
+    }
+    cluster.sync();
+    double* orow = out + row * out_pitch;
+#pragma unroll
+    for (int q = 0; q < H / G::NT; ++q) {
+        const int e1 = jt + q * G::NT;
+        const int e = c * H + e1;                      // packed samples 2e, 2e+1 = reals [4e, 4e+4)
+        if (mrow && !((mrow[e >> 9] >> ((e >> 4) & 31)) & 1u)) continue;
+        if (2 * (int64_t)e < out_nz) *reinterpret_cast<cplx*>(orow + 4 * (int64_t)e) = line[e1];
+        if (2 * (int64_t)e + 1 < out_nz) *reinterpret_cast<cplx*>(orow + 4 * (int64_t)e + 2) = line[H + e1];
     }
 }
 template <int N>
 static int launch_c2r_long(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
-                           double scale, int nz, int64_t out_nz, cudaStream_t st) {
+                           double scale, int nz, int64_t out_nz, const uint32_t* mask, int64_t mask_pitch, cudaStream_t st) {
     using G = RegGeom<N>;
     int rc = set_smem(k_c2r_rows_long<N>, G::SMEM);
     if (rc) return rc;
-    const unsigned g = (unsigned)cdiv(2 * batch, (int64_t)G::L);
-    k_c2r_rows_long<N><<<g, G::NT, G::SMEM, st>>>(p->half->d.tw, p->d.tw, p->half_tw_dev, in, reinterpret_cast<cplx*>(out),
-                                                  2 * batch, in_pitch, out_pitch / 2, scale, nz, out_nz);
-    KERNEL_CHECK();
+    for (int64_t r0 = 0; r0 < batch; r0 += (1 << 29)) {
+        const int64_t nb = std::min<int64_t>(batch - r0, 1 << 29);
+        k_c2r_rows_long<N><<<(unsigned)(2 * nb), G::NT, G::SMEM, st>>>(p->half->d.tw, p->d.tw, p->half_tw_dev, in + r0 * in_pitch,
+                                                                      out + r0 * out_pitch, in_pitch, out_pitch, scale, nz, out_nz,
+                                                                      mask ? mask + r0 * mask_pitch : nullptr, mask_pitch);
+        KERNEL_CHECK();
+    }
     return IPDE_OK;
 }
 
@@ -1311,7 +1379,7 @@ static int fft_mul_fft_rows_split(FftPlan* p, int R, const cplx* in, cplx* out, 
 // r2c of rows of 2n reals (n = 2m complex): E_0 | E_1 sit in the first 2m slots of the output row; every thread
 // owns the closed orbit {k, m-k, m+k, n-k} and rewrites it in place with the half spectrum X[0..n].
 __global__ void k_r2c_untangle_split(int m, const cplx* __restrict__ twn, const cplx* __restrict__ half_tw, cplx* __restrict__ out,
-                                     int64_t batch, int64_t out_pitch) {
+                                     int64_t batch, int64_t out_pitch, const SlabScatter sc) {
     const int n = 2 * m;
     const int per = m / 2 + 1;                                    // k = 0 .. m/2
     const int64_t total = batch * per;
@@ -1333,7 +1401,19 @@ __global__ void k_r2c_untangle_split(int m, const cplx* __restrict__ twn, const 
             const cplx O = cmulni(cscale(csub(za, zc), 0.5));
             return cadd(E, cmul(half_tw[kk], O));
         };
-        if (k == 0) {
+        if (sc.R) {
+            // forward slab transpose on the stores (the sub-transforms stay in the local scratch rows)
+            if (k == 0) {
+                *slab_fwd_addr(sc, row, 0) = X(Zk, Zk, 0);
+                *slab_fwd_addr(sc, row, n) = X(Zk, Zk, n);
+                *slab_fwd_addr(sc, row, m) = X(Zkm, Zkm, m);
+            } else {
+                *slab_fwd_addr(sc, row, k) = X(Zk, Znk, k);
+                *slab_fwd_addr(sc, row, n - k) = X(Znk, Zk, n - k);
+                *slab_fwd_addr(sc, row, m - k) = X(Zmk, Zkm, m - k);
+                *slab_fwd_addr(sc, row, m + k) = X(Zkm, Zmk, m + k);
+            }
+        } else if (k == 0) {
             // Z[0] = Zk, Z[m] = Zkm; X[0] pairs Z[0] with itself, X[n] likewise, X[m] pairs Z[m] with Z[m]
             o[0] = X(Zk, Zk, 0);
             o[n] = X(Zk, Zk, n);
@@ -1398,7 +1478,7 @@ int fft_r2c_rows_nz(FftPlan* p, const double* in, cplx* out, int64_t batch, int6
         if (rc) return rc;
         const int blocks = (int)std::min<int64_t>(cdiv(batch * (m / 2 + 1), 256), (int64_t)ipde_num_sms() * 16);
         KERNEL_TAG("k_r2c_untangle_split", 32.0 * n * (double)batch);
-        k_r2c_untangle_split<<<blocks, 256, 0, st>>>(m, p->d.tw, p->half_tw_dev, out, batch, out_pitch);
+        k_r2c_untangle_split<<<blocks, 256, 0, st>>>(m, p->d.tw, p->half_tw_dev, out, batch, out_pitch, slab_scatter_none());
         KERNEL_CHECK();
         return IPDE_OK;
     }
@@ -1433,13 +1513,42 @@ int fft_r2c_rows_nz(FftPlan* p, const double* in, cplx* out, int64_t batch, int6
     return IPDE_OK;
 }
 
+int fft_r2c_rows_scatter(FftPlan* p, const double* in, cplx* scratch, int64_t batch, int64_t in_pitch, int64_t scratch_pitch,
+                         const SlabScatter& sc, cudaStream_t st) {
+    if (batch <= 0) return IPDE_OK;
+    const int n = p->d.n;
+    ARG_CHECK(sc.R >= 1 && sc.R <= IPDE_SLAB_MAX_RANKS && sc.Pc * sc.R >= n + 1, "r2c scatter: bad slab description");
+    if (g_fft_reg && p->fast && fft_split_size(n)) {
+        int rc = ensure_half(p);
+        if (rc) return rc;
+        const int m = n / 2;
+        KERNEL_TAG("k_r2c_rows_long", (16.0 * n + 16.0 * n) * (double)batch);
+        rc = rows_reg_sub(p, reinterpret_cast<const cplx*>(in), scratch, 2 * batch, in_pitch / 2, 1, 2, scratch_pitch, m, 1, -1, 1.0,
+                          st, nullptr, 0, n);
+        if (rc) return rc;
+        const int blocks = (int)std::min<int64_t>(cdiv(batch * (m / 2 + 1), 256), (int64_t)ipde_num_sms() * 16);
+        KERNEL_TAG("k_r2c_untangle_split", 32.0 * n * (double)batch);
+        k_r2c_untangle_split<<<blocks, 256, 0, st>>>(m, p->d.tw, p->half_tw_dev, scratch, batch, scratch_pitch, sc);
+        KERNEL_CHECK();
+        return IPDE_OK;
+    }
+    if (g_fft_reg && p->fast && fft_reg_size(n) && n <= IPDE_FFT_SMEM_MAX) {
+        KERNEL_TAG("k_r2c_rows", (16.0 * n + 16.0 * (n + 1)) * (double)batch);
+#define CALL_REG(N_) return launch_r2c_reg<N_>(p, in, scratch, batch, in_pitch, scratch_pitch, st, sc)
+        REG_DISPATCH(n, CALL_REG);
+#undef CALL_REG
+    }
+    ipde_set_error("r2c scatter: rows of %d reals have no register-resident kernel", 2 * n);
+    return IPDE_ERR_UNSUPPORTED;
+}
+
 int fft_c2r_rows(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
                  double scale, cudaStream_t st) {
     return fft_c2r_rows_nz(p, in, out, batch, in_pitch, out_pitch, scale, p->d.n + 1, st, 2 * (int64_t)p->d.n);
 }
 
 int fft_c2r_rows_nz(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
-                    double scale, int nz, cudaStream_t st, int64_t out_nz) {
+                    double scale, int nz, cudaStream_t st, int64_t out_nz, const uint32_t* mask, int64_t mask_pitch) {
     if (out_nz <= 0) out_nz = 2 * (int64_t)p->d.n;
     if (batch <= 0) return IPDE_OK;
     const int n = p->d.n;
@@ -1448,9 +1557,10 @@ int fft_c2r_rows_nz(FftPlan* p, const cplx* in, double* out, int64_t batch, int6
         int rc = ensure_half(p);
         if (rc) return rc;
         const int m = n / 2;
-        KERNEL_TAG("k_c2r_rows_long", (8.0 * std::min<int64_t>(2 * (int64_t)n, out_nz) + 16.0 * std::min(n + 1, nz)) * (double)batch);
-        if (m == 4096) return launch_c2r_long<4096>(p, in, out, batch, in_pitch, out_pitch, scale, nz, (out_nz + 1) / 2, st);
-        return launch_c2r_long<8192>(p, in, out, batch, in_pitch, out_pitch, scale, nz, (out_nz + 1) / 2, st);
+        // masked stores: the written bytes depend on the mask and are not counted
+        KERNEL_TAG("k_c2r_rows_long", ((mask ? 0.0 : 8.0 * std::min<int64_t>(2 * (int64_t)n, out_nz)) + 16.0 * std::min(n + 1, nz)) * (double)batch);
+        if (m == 4096) return launch_c2r_long<4096>(p, in, out, batch, in_pitch, out_pitch, scale, nz, (out_nz + 1) / 2, mask, mask_pitch, st);
+        return launch_c2r_long<8192>(p, in, out, batch, in_pitch, out_pitch, scale, nz, (out_nz + 1) / 2, mask, mask_pitch, st);
     }
     if (n > IPDE_FFT_SMEM_MAX || !p->fast) {
         int rc = ensure_work(p, (size_t)3 * n * batch);
@@ -1463,7 +1573,8 @@ int fft_c2r_rows_nz(FftPlan* p, const cplx* in, double* out, int64_t batch, int6
     }
     KERNEL_TAG("k_c2r_rows", (16.0 * n + 16.0 * (n + 1)) * (double)batch);
     if (g_fft_reg && fft_reg_size(n)) {
-#define CALL_REG(N_) return launch_c2r_reg<N_>(p, in, out, batch, in_pitch, out_pitch, scale, st)
+        if (n < 1024) mask = nullptr;                  // rows shorter than one mask word
+#define CALL_REG(N_) return launch_c2r_reg<N_>(p, in, out, batch, in_pitch, out_pitch, scale, mask, mask_pitch, st)
         REG_DISPATCH(n, CALL_REG);
 #undef CALL_REG
     }

@@ -64,9 +64,35 @@ struct RowWindow {
     int in_lo, in_hi, out_lo, out_hi;
 };
 static inline RowWindow row_window_all() { RowWindow w = {0, 0, 0, 1, 0, 1}; return w; }
+
+// Slab-decomposed grids (ipde_b200/distributed.py, SlabGridSolverP2P): the transposes between row slabs and column
+// slabs are done by the STORES of the transform kernels, straight into the peers' buffers over NVLink (CUDA IPC
+// mappings), instead of pack + all-to-all + unpack.
+//   forward   rank p owns rows [row0, row0 + rows_local): entry (local row l, column k) of the row spectra goes to
+//             the column slab (nx, Pc) of rank q = k / Pc, position [(row0 + l) * Pc + k - q Pc]
+//   backward  rank p owns columns [col0, col0 + Pc): entry (global row i, local column c) of the column pass goes to
+//             the row slab (rows, P) of rank q = i / rows, position [(i - q rows) * P + col0 + c]   (col0 + c < P)
+#define IPDE_SLAB_MAX_RANKS 8
+struct SlabScatter {
+    int R;                 // 0: plain store
+    int rows;              // rows per rank
+    int64_t Pc, P;         // columns per rank, valid columns (ny/2 + 1)
+    int64_t row0, col0;    // first global row (forward) / first global column (backward) of this rank
+    cplx* base[IPDE_SLAB_MAX_RANKS];
+};
+static inline SlabScatter slab_scatter_none() { SlabScatter s = {}; return s; }
+__device__ __forceinline__ cplx* slab_fwd_addr(const SlabScatter& S, int64_t l, int k) {
+    const int q = (int)(k / S.Pc);
+    return S.base[q] + (S.row0 + l) * S.Pc + (k - q * S.Pc);
+}
+__device__ __forceinline__ cplx* slab_bwd_addr(const SlabScatter& S, int row, int c) {
+    const int q = row / S.rows;
+    return S.base[q] + (int64_t)(row - q * S.rows) * S.P + S.col0 + c;
+}
+
 int fft_cols_windowed(FftPlan* p, const cplx* in, cplx* out, int64_t elem_stride, int64_t n_inner, int64_t n_outer,
                       int64_t outer_stride, int sign, double scale, int tw_mode, const cplx* tw_big, RowWindow W,
-                      cudaStream_t st);
+                      cudaStream_t st, const SlabScatter* sc = nullptr);
 
 // Real <-> half-complex rows (length nr = 2*p->d.n reals <-> nr/2+1 complex), plan is for nr/2.
 int fft_r2c_rows(FftPlan* p, const double* in, cplx* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
@@ -75,8 +101,15 @@ int fft_c2r_rows(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t
                  double scale, cudaStream_t st);
 // the same when only the first nz entries of every input row can be nonzero (zero-padded spectra)
 // (and only the first out_nz reals of every output row are needed: 0 = all)
+// mask (optional): bit b of word mask[row * mask_pitch + (b >> 5)] set <=> the reals [64 b, 64 b + 64) of that output
+// row are needed; the other blocks may be left unwritten (honoured by the long-row and register kernels)
 int fft_c2r_rows_nz(FftPlan* p, const cplx* in, double* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
-                    double scale, int nz, cudaStream_t st, int64_t out_nz = 0);
+                    double scale, int nz, cudaStream_t st, int64_t out_nz = 0, const uint32_t* mask = nullptr,
+                    int64_t mask_pitch = 0);
+// r2c of the local rows of a slab with the forward transpose on the stores (SlabScatter); `scratch` (batch, scratch_pitch)
+// holds the sub-transforms of long rows.  IPDE_ERR_UNSUPPORTED for row lengths without a register kernel.
+int fft_r2c_rows_scatter(FftPlan* p, const double* in, cplx* scratch, int64_t batch, int64_t in_pitch, int64_t scratch_pitch,
+                         const SlabScatter& sc, cudaStream_t st);
 // real rows whose entries beyond in_nz are zero (zero-padded rows)
 int fft_r2c_rows_nz(FftPlan* p, const double* in, cplx* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
                     int64_t in_nz, cudaStream_t st);

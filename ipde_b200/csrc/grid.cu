@@ -330,7 +330,7 @@ static inline bool grid_fused_ok(const GridPlan* g) {
 // the inverse row transforms.  spec_copy (may be null) receives the 2-D spectrum, before (copy_mode 1) or after
 // (2) the multiplication.  spec_in is overwritten when the column transform is split.
 int grid_cols_symbol(GridPlan* g, cplx* spec_in, cplx* spec_out, cplx* spec_copy, int copy_mode, const ColMult& M0,
-                     cudaStream_t st, const int* win) {
+                     cudaStream_t st, const int* win, const SlabScatter* sc) {
     const int64_t P = g->pitch;
     // win = {in_lo, in_hi, out_lo, out_hi}: rows of spec_in outside [in_lo, in_hi) are zero (not read), rows of
     // spec_out outside [out_lo, out_hi) are not needed (not written)
@@ -341,6 +341,10 @@ int grid_cols_symbol(GridPlan* g, cplx* spec_in, cplx* spec_out, cplx* spec_copy
     if (M.ny <= 0) { M.ny = g->ny; M.yh = g->yh; M.col_offset = 0; }
     if (!spec_copy) copy_mode = 0;
     if (g->n2 == 1) {
+        if (sc && sc->R) {
+            ipde_set_error("grid_cols_symbol: scattered stores need a four-step column split (nx = %d)", g->nx);
+            return IPDE_ERR_UNSUPPORTED;
+        }
         M.fmul = 1;
         RowWindow W = {0, 1, in_lo, in_hi, out_lo, out_hi};
         return cols_mult(g->colA, spec_in, spec_out, spec_copy, P, P, 1, 0, 1, copy_mode, M, W, st);
@@ -353,7 +357,7 @@ int grid_cols_symbol(GridPlan* g, cplx* spec_in, cplx* spec_out, cplx* spec_copy
     rc = cols_mult(g->colB, spec_in, spec_out, spec_copy, P, P, g->n1, (int64_t)g->n2 * P, 1, copy_mode, M, row_window_all(), st);
     if (rc) return rc;
     RowWindow Wb = {1, g->n2, 0, g->nx, out_lo, out_hi};
-    return fft_cols_windowed(g->colA, spec_out, spec_out, (int64_t)g->n2 * P, P, g->n2, P, +1, 1.0, 2, g->tw_big, Wb, st);
+    return fft_cols_windowed(g->colA, spec_out, spec_out, (int64_t)g->n2 * P, P, g->n2, P, +1, 1.0, 2, g->tw_big, Wb, st, sc);
 }
 
 // 2-D spectrum (as left by grid_cols_symbol's copy) -> symbol -> inverse column FFT -> spec_out
@@ -724,6 +728,16 @@ int grid_slab_unpack(const cplx* in, int64_t rows, int64_t P, int R, int64_t Pc,
     k_slab_unpack<<<grid_blocks(total, 256), 256, 0, st>>>(in, rows, P, R, Pc, koff, Pk, out);
     KERNEL_CHECK();
     return IPDE_OK;
+}
+int grid_cols_symbol_slab_scatter(GridPlan* g, cplx* spec_in, cplx* spec_work, int kind, double k, int ny_global, double yh,
+                                  int col_offset, const SlabScatter& sc, cudaStream_t st) {
+    ARG_CHECK(grid_fused_ok(g), "column length of the slab plan is not supported by the fused column pass");
+    ARG_CHECK(sc.R >= 1 && sc.R <= IPDE_SLAB_MAX_RANKS && sc.rows * sc.R == g->nx && sc.Pc == g->pitch,
+              "slab scatter: rows * ranks must equal nx and Pc the pitch of the column plan");
+    ColMult M;
+    M.kind = kind; M.k2c = k * k; M.table = nullptr; M.fmul = 1; M.deriv = 0;
+    M.ny = ny_global; M.yh = yh; M.col_offset = col_offset;
+    return grid_cols_symbol(g, spec_in, spec_work, nullptr, 0, M, st, nullptr, &sc);
 }
 int grid_cols_symbol_slab(GridPlan* g, cplx* spec_in, cplx* spec_out, cplx* spec_copy, int copy_mode, int kind, double k,
                           int ny_global, double yh, int col_offset, cudaStream_t st) {

@@ -54,7 +54,10 @@ struct ColMult {
 };
 // win (optional): {in_lo, in_hi, out_lo, out_hi} row windows of zero-padded data, see RowWindow in fft.cuh
 int grid_cols_symbol(GridPlan* g, cplx* spec_in, cplx* spec_out, cplx* spec_copy, int copy_mode, const ColMult& M,
-                     cudaStream_t st, const int* win = nullptr);
+                     cudaStream_t st, const int* win = nullptr, const SlabScatter* sc = nullptr);
+// the same on the column slab of one rank, the last pass storing straight into the row slabs of all ranks
+int grid_cols_symbol_slab_scatter(GridPlan* g, cplx* spec_in, cplx* spec_work, int kind, double k, int ny_global, double yh,
+                                  int col_offset, const SlabScatter& sc, cudaStream_t st);
 // win (optional): {out_lo, out_hi}
 int grid_cols_symbol_inverse(GridPlan* g, const cplx* spec2d, cplx* spec_out, const ColMult& M, cudaStream_t st,
                              const int* win = nullptr);

@@ -37,7 +37,7 @@ int nufft2_plan_create(int nx, int ny, double xh, double yh, int fx, int fy, int
 void nufft2_plan_destroy(Nufft2Plan* p) {
     if (!p) return;
     grid_plan_destroy(p->fine);
-    cudaFree(p->px); cudaFree(p->py); cudaFree(p->fine_spec); cudaFree(p->fine_real);
+    cudaFree(p->px); cudaFree(p->py); cudaFree(p->fine_spec); cudaFree(p->fine_real); cudaFree(p->mask);
     delete p;
 }
 
@@ -141,9 +141,12 @@ __global__ void k_nufft_interp3(const double* __restrict__ fine, int fx, int fy,
                 int jj = (j0 + b) % fy; if (jj < 0) jj += fy;
                 const double g = k * fine[(int64_t)ii * fy + jj];
                 av += g;
-                // d/dx: z = (l - x s)/half, dz/dx = -s/half; d phi/dz = -beta z / sqrt(1 - z^2) phi
-                adx += g * (beta * zx / rx) * (sx / half);
-                ady += g * (beta * zy / ry) * (sy / half);
+                // d/dx: z = (l - x s)/half, dz/dx = -s/half; d phi/dz = -beta z / sqrt(1 - z^2) phi.  The derivative of
+                // the kernel is singular at the edge of its support (phi ~ e^{-beta} there): for a target within ~1e-10
+                // of a fine-grid node the edge node has r -> 0 and the factor 1/r amplifies round-off to 1e-11; below
+                // r = 0.02 the term is at most 3e-14 of the gradient scale and is dropped
+                if (rx > 0.02) adx += g * (beta * zx / rx) * (sx / half);
+                if (ry > 0.02) ady += g * (beta * zy / ry) * (sy / half);
             }
         }
         for (int o = 16; o > 0; o >>= 1) {
@@ -155,13 +158,43 @@ __global__ void k_nufft_interp3(const double* __restrict__ fine, int fx, int fy,
     }
 }
 
-// inverse transform of the zero-padded fine spectrum: column passes over the nonzero columns only, full row pass
-static int nufft2_inverse(Nufft2Plan* p, cudaStream_t st) {
+// the fine grid is only read on the w x w stencils of the targets: one bit per (fine row, block of 64 reals)
+__global__ void k_nufft_mark(int fx, int fy, const double* __restrict__ x, const double* __restrict__ y, int64_t npts, int w,
+                             uint32_t* __restrict__ mask, int words) {
+    const double half = 0.5 * w;
+    const int64_t total = npts * w;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = t / w;
+        const int a = (int)(t - p * w);
+        const double X = x[p] * ((double)fx / TWO_PI), Y = y[p] * ((double)fy / TWO_PI);
+        const int i0 = (int)ceil(X - half), j0 = (int)ceil(Y - half);
+        int ii = (i0 + a) % fx; if (ii < 0) ii += fx;
+        int ja = j0 % fy; if (ja < 0) ja += fy;
+        int jb = (j0 + w - 1) % fy; if (jb < 0) jb += fy;
+        uint32_t* mrow = mask + (int64_t)ii * words;
+        atomicOr(&mrow[ja >> 11], 1u << ((ja >> 6) & 31));
+        atomicOr(&mrow[jb >> 11], 1u << ((jb >> 6) & 31));      // w <= 32: the stencil touches at most two blocks
+    }
+}
+
+// inverse transform of the zero-padded fine spectrum: column passes over the nonzero columns only; the row pass
+// stores only the blocks of the fine grid that the targets' stencils read
+static int nufft2_inverse(Nufft2Plan* p, const double* x, const double* y, int64_t npts, cudaStream_t st) {
     GridPlan* f = p->fine;
     int rc = grid_cols_inverse_n(f, p->fine_spec, p->fine_spec, p->ny / 2 + 1, st);
     if (rc) return rc;
+    const uint32_t* mask = nullptr;
+    const int words = f->ny / 2048;
+    if (npts > 0 && f->ny % 2048 == 0 && p->w <= 32) {
+        if (!p->mask) CUDA_TRY(cudaMalloc(&p->mask, sizeof(uint32_t) * (size_t)f->nx * words));
+        CUDA_TRY(cudaMemsetAsync(p->mask, 0, sizeof(uint32_t) * (size_t)f->nx * words, st));
+        const int mb = (int)std::min<int64_t>(cdiv(npts * p->w, 256), (int64_t)ipde_num_sms() * 16);
+        k_nufft_mark<<<mb, 256, 0, st>>>(f->nx, f->ny, x, y, npts, p->w, p->mask, words);
+        KERNEL_CHECK();
+        mask = p->mask;
+    }
     return fft_c2r_rows_nz(f->row, p->fine_spec, p->fine_real, f->nx, f->pitch, f->ny,
-                           1.0 / ((double)f->nx * (double)f->ny) * 2.0, p->ny / 2 + 1, st);
+                           1.0 / ((double)f->nx * (double)f->ny) * 2.0, p->ny / 2 + 1, st, 0, mask, words);
 }
 
 int nufft2_apply3(Nufft2Plan* p, const cplx* spec, int cn1, int cn2, const double* x, const double* y, int64_t npts,
@@ -173,7 +206,7 @@ int nufft2_apply3(Nufft2Plan* p, const cplx* spec, int cn1, int cn2, const doubl
     k_nufft_pad<<<blocks, 256, 0, st>>>(spec, p->nx, p->ny, p->ny / 2 + 1, cn1, cn2, p->fine_spec, p->fx, p->fy, f->pitch,
                                         f->n1, f->n2, p->px, p->py, p->xh, p->yh, 0, 0, scale);
     KERNEL_CHECK();
-    int rc = nufft2_inverse(p, st);
+    int rc = nufft2_inverse(p, x, y, npts, st);
     if (rc) return rc;
     if (npts > 0) {
         const int b2 = (int)std::min<int64_t>(cdiv(npts * 32, 256), (int64_t)ipde_num_sms() * 16);
@@ -193,7 +226,7 @@ int nufft2_apply(Nufft2Plan* p, const cplx* spec, int cn1, int cn2, int dxp, int
     k_nufft_pad<<<blocks, 256, 0, st>>>(spec, p->nx, p->ny, p->ny / 2 + 1, cn1, cn2, p->fine_spec, p->fx, p->fy, f->pitch,
                                         f->n1, f->n2, p->px, p->py, p->xh, p->yh, dxp, dyp, scale);
     KERNEL_CHECK();
-    int rc = nufft2_inverse(p, st);
+    int rc = nufft2_inverse(p, x, y, npts, st);
     if (rc) return rc;
     if (npts > 0) {
         const int b2 = (int)std::min<int64_t>(cdiv(npts * 32, 256), (int64_t)ipde_num_sms() * 16);

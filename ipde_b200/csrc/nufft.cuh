@@ -9,6 +9,7 @@ struct Nufft2Plan {
     double* py = nullptr;       // ... per coarse y frequency index 0..ny/2
     cplx* fine_spec = nullptr;
     double* fine_real = nullptr;
+    uint32_t* mask = nullptr;   // bit per (fine row, block of 64 reals) read by the current targets
 };
 
 int nufft2_plan_create(int nx, int ny, double xh, double yh, int fx, int fy, int w, double beta, const double* px_host,

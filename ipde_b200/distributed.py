@@ -227,3 +227,112 @@ class SlabGridSolver(object):
         L_.ipde_fft_c2r_rows(self.row_plan, ptr(back), ptr(out), Ls.rows, Ls.P, self.ny,
                              2.0/(float(self.nx)*float(self.ny)), st)
         return out
+
+
+class SlabGridSolverP2P(object):
+    """
+    The slab solve with both transposes FUSED INTO THE TRANSFORM KERNELS: no pack, no all-to-all, no unpack.
+
+        r2c rows, every spectrum entry stored into the column slab of the rank that owns its column
+                                                        k_r2c_rows_reg / k_r2c_untangle_split, NVLink stores
+        tiny all-reduce (every rank's stores have landed)
+        column FFT + symbol + inverse column FFT, the last pass storing every entry into the row slab of the rank
+        that owns its row                               k_fft_cols_short, k_cols_mult_short, NVLink stores
+        tiny all-reduce
+        c2r rows                                        k_c2r_rows_*
+
+    The buffers that peers write into are allocated by the library (cudaMalloc), exported as CUDA IPC handles and mapped
+    by every other rank of the box (`ipde_ipc_*`); the handles travel once, at construction, through
+    `all_gather_object`.  The data path has no collective: the exchange is carried by the stores of the kernels that
+    produce the data and overlaps their arithmetic.  One rank: the same kernels store into the rank's own buffers.
+    Up to 8 ranks (one box); nx a power of two >= 1024 and ny/2 a register-kernel length (256 ... 8192, 16384).
+    """
+    MAX_RANKS = 8
+
+    def __init__(self, nx, ny, xh, yh, kind, k, group=None):
+        import ctypes
+        from ._lib import lib
+        from .device import require_cuda, empty, C128
+        require_cuda()
+        self.group = group
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if world > self.MAX_RANKS:
+            raise Exception('SlabGridSolverP2P: at most %d ranks' % self.MAX_RANKS)
+        self.L = Ls = SlabLayout(nx, ny, world, rank)
+        L_ = lib()
+        # the column plan is a grid plan of width 2 (Pc - 1): round Pc - 1 up to a supported length (zero columns)
+        Ls.Pc = L_.ipde_fft_next_size(max(2, Ls.Pc - 1)) + 1
+        Ls.col0 = rank*Ls.Pc
+        self.nx, self.ny, self.xh, self.yh, self.kind, self.k = nx, ny, float(xh), float(yh), int(kind), float(k)
+        self.row_plan = ctypes.c_void_p()
+        L_.ipde_fft_plan_create(ny//2, ctypes.byref(self.row_plan))
+        self.col_plan = ctypes.c_void_p()
+        L_.ipde_grid_plan_create(nx, 2*(Ls.Pc - 1), float(xh), float(yh), ctypes.byref(self.col_plan))
+        self.scratch = empty((Ls.rows, Ls.P), C128)
+        self.work = empty((nx, Ls.Pc), C128)
+        # shared buffers: my column slab (nx, Pc) and my row slab of the way back (rows, P)
+        self._own, handles = [], []
+        for nbytes in (16*nx*Ls.Pc, 16*Ls.rows*Ls.P):
+            dp, h = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+            L_.ipde_ipc_alloc(nbytes, ctypes.byref(dp), h)
+            self._own.append(dp)
+            handles.append(h.raw)
+        self._mapped = []
+        tables = [[None]*world, [None]*world]
+        if world > 1:
+            gathered = [None]*world
+            dist.all_gather_object(gathered, handles, group=group)
+        for q in range(world):
+            for which in range(2):
+                if q == rank:
+                    tables[which][q] = self._own[which].value
+                else:
+                    dp = ctypes.c_void_p()
+                    L_.ipde_ipc_open(gathered[q][which], ctypes.byref(dp))
+                    self._mapped.append(dp)
+                    tables[which][q] = dp.value
+        self.peer_cols = (ctypes.c_void_p*world)(*tables[0])
+        self.peer_rows = (ctypes.c_void_p*world)(*tables[1])
+        self._flag = torch.zeros(1, device='cuda')
+        self.p2p_bytes_per_rank = 2*16*Ls.rows*Ls.P*(world - 1)//world
+        self._fence()
+
+    def close(self):
+        from ._lib import lib
+        L_ = lib()
+        if getattr(self, '_own', None) is None:
+            return
+        torch.cuda.synchronize()
+        if self.L.R > 1:
+            dist.barrier(group=self.group)        # nobody unmaps or frees while a peer may still store
+        for dp in self._mapped:
+            L_.ipde_ipc_close(dp)
+        if self.L.R > 1:
+            dist.barrier(group=self.group)
+        for dp in self._own:
+            L_.ipde_ipc_free(dp)
+        self._own, self._mapped = None, []
+        L_.ipde_fft_plan_destroy(self.row_plan)
+        L_.ipde_grid_plan_destroy(self.col_plan)
+
+    def _fence(self):
+        """stream-ordered: returns (on the stream) once the kernels enqueued so far on EVERY rank have completed"""
+        if self.L.R > 1:
+            dist.all_reduce(self._flag, group=self.group)
+
+    def solve(self, f_local, out=None):
+        from ._lib import lib
+        from .device import ptr, stream, empty
+        L_, Ls, st = lib(), self.L, stream()
+        if out is None:
+            out = empty((Ls.rows, self.ny))
+        L_.ipde_slab_r2c_rows_scatter(self.row_plan, ptr(f_local), ptr(self.scratch), Ls.rows, self.ny, Ls.P, Ls.R, Ls.Pc,
+                                      Ls.row0, self.peer_cols, st)
+        self._fence()
+        L_.ipde_slab_cols_symbol_scatter(self.col_plan, self._own[0], ptr(self.work), self.kind, self.k, self.ny, self.yh,
+                                         Ls.col0, Ls.R, Ls.rows, Ls.P, self.peer_rows, st)
+        self._fence()
+        L_.ipde_fft_c2r_rows(self.row_plan, self._own[1], ptr(out), Ls.rows, Ls.P, self.ny,
+                             2.0/(float(self.nx)*float(self.ny)), st)
+        return out

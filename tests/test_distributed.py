@@ -71,6 +71,71 @@ def test_slab_pack_unpack_roundtrip():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('shape', [(1024, 1024), (2048, 8192), (1024, 16384), (1024, 32768)])
+def test_slab_p2p_solver_single_gpu(shape):
+    """SlabGridSolverP2P on one rank: the transposing stores of the row and column kernels land in the rank's own IPC
+    buffers (register r2c kernel, long-row untangle kernel, short four-step column pass)"""
+    from ipde_b200.distributed import SlabGridSolverP2P
+    import ipde_b200.device as D
+    nx, ny = shape
+    rng = np.random.default_rng(5)
+    f = rng.standard_normal((nx, ny))
+    xh, yh = 2.4/nx, 3.0/ny
+    S = SlabGridSolverP2P(nx, ny, xh, yh, 1, 2.0)
+    u = S.solve(D.to_dev(f)).cpu().numpy()
+    S.close()
+    ref = _reference(f, xh, yh, 2.0)
+    assert np.abs(u - ref).max()/np.abs(ref).max() < 1e-13
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('R,shape', [(2, (1024, 1024)), (4, (2048, 4096)), (8, (1024, 16384)), (8, (2048, 32768))])
+def test_slab_p2p_virtual_ranks(R, shape):
+    """the index arithmetic of the fused transposes for R ranks, all of them played by one GPU: R column slabs and R row
+    slabs in one process, the C entry points called rank after rank in the order of SlabGridSolverP2P.solve"""
+    import ctypes
+    from ipde_b200._lib import lib
+    import ipde_b200.device as D
+    nx, ny = shape
+    if nx % R:
+        pytest.skip('nx not divisible')
+    rng = np.random.default_rng(R)
+    f = rng.standard_normal((nx, ny))
+    xh, yh = 2.4/nx, 3.0/ny
+    L_ = lib()
+    layouts = [SlabLayout(nx, ny, R, r) for r in range(R)]
+    Pc = L_.ipde_fft_next_size(max(2, layouts[0].Pc - 1)) + 1
+    rows, P = layouts[0].rows, layouts[0].P
+    if nx < 1024 or nx & (nx - 1):
+        pytest.skip('column length without a four-step split')
+    row_plan, col_plan = ctypes.c_void_p(), ctypes.c_void_p()
+    L_.ipde_fft_plan_create(ny//2, ctypes.byref(row_plan))
+    L_.ipde_grid_plan_create(nx, 2*(Pc - 1), xh, yh, ctypes.byref(col_plan))
+    cols = [torch.zeros((nx, Pc), dtype=torch.complex128, device='cuda') for _ in range(R)]
+    back = [torch.zeros((rows, P), dtype=torch.complex128, device='cuda') for _ in range(R)]
+    peer_cols = (ctypes.c_void_p*R)(*[D.ptr(c) for c in cols])
+    peer_rows = (ctypes.c_void_p*R)(*[D.ptr(b) for b in back])
+    scratch, work = D.empty((rows, P), torch.complex128), D.empty((nx, Pc), torch.complex128)
+    st = D.stream()
+    for r in range(R):
+        fl = D.to_dev(f[r*rows:(r + 1)*rows])
+        L_.ipde_slab_r2c_rows_scatter(row_plan, D.ptr(fl), D.ptr(scratch), rows, ny, P, R, Pc, r*rows, peer_cols, st)
+    spec = np.fft.rfft(f, axis=1)
+    for r in range(R):
+        a, b = r*Pc, min(P, (r + 1)*Pc)
+        assert np.abs(cols[r].cpu().numpy()[:, :b - a] - spec[:, a:b]).max() < 1e-12*np.abs(spec).max()
+    for r in range(R):
+        L_.ipde_slab_cols_symbol_scatter(col_plan, D.ptr(cols[r]), D.ptr(work), 1, 2.0, ny, yh, r*Pc, R, rows, P, peer_rows, st)
+    ref = _reference(f, xh, yh, 2.0)
+    for r in range(R):
+        out = D.empty((rows, ny))
+        L_.ipde_fft_c2r_rows(row_plan, D.ptr(back[r]), D.ptr(out), rows, P, ny, 2.0/(nx*ny), st)
+        assert np.abs(out.cpu().numpy() - ref[r*rows:(r + 1)*rows]).max()/np.abs(ref).max() < 1e-13
+    L_.ipde_fft_plan_destroy(row_plan)
+    L_.ipde_grid_plan_destroy(col_plan)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize('n', [256, 4096])
 def test_slab_grid_solver_single_gpu(n):
     """device kernels of the slab path (world 1: pack/unpack, column-slab symbol pass) against NumPy"""

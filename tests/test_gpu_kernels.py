@@ -92,8 +92,10 @@ def test_grid_solve_scalar(D, kind, k, shape):
     assert rel(g.spec_to_numpy_full(uch), ref_h) < 1e-12
 
 
-@pytest.mark.parametrize('shape', [(48, 40), (2048, 32)])
+@pytest.mark.parametrize('shape', [(48, 40), (2048, 32), (32, 1024), (40, 8192), (24, 16384)])
 def test_nufft2_against_direct_sum(D, shape):
+    # row lengths 2048 ... 32768 of the fine grid: the row pass stores only the 64-real blocks under the targets'
+    # stencils (register kernel and the cluster-pair long-row kernel)
     from oracle.solvers import nudft2d_type2
     nx, ny = shape
     xh, yh = 2.4/nx, 3.0/ny
@@ -111,9 +113,14 @@ def test_nufft2_against_direct_sum(D, shape):
     ky = np.fft.fftfreq(ny, yh/(2*np.pi))
     ref = nudft2d_type2(np.stack([fh, 1j*kx*fh, 1j*ky*fh]), x, y).real
     scale = [np.abs(f).max(), np.abs(kx).max()*np.abs(f).max(), np.abs(ky).max()*np.abs(f).max()]
+    tol = 2e-13 if max(shape) <= 2048 else 2e-12      # round-off of 10^5 ... 4 10^5 full-band random modes per point
     for i, (dx, dy) in enumerate([(0, 0), (1, 0), (0, 1)]):
         v = nu(spec, dx, dy).cpu().numpy()
-        assert np.abs(v - ref[i]).max()/scale[i] < 2e-13, (dx, dy)
+        assert np.abs(v - ref[i]).max()/scale[i] < tol, (dx, dy)
+    # value and gradient from ONE fine grid (gradient by differentiating the interpolation kernel); target 1 sits
+    # 1e-12 from a fine-grid node, where the kernel derivative is singular at the edge of the stencil
+    for i, v in enumerate(nu.apply3(spec)):
+        assert np.abs(v.cpu().numpy() - ref[i]).max()/scale[i] < (tol if i == 0 else 5*tol), i
 
 
 @pytest.mark.parametrize('M,n', [(8, 40), (16, 300), (20, 1000)])
