@@ -201,6 +201,11 @@ int ipde_eval_k1(const double* x, double* out, int64_t n, void* stream);
 int ipde_layer_apply_scalar(int kind, double k, const double* sx, const double* sy, const double* q,
                             int64_t nsrc, const double* tx, const double* ty, int64_t ntrg, double* out,
                             int accumulate, void* stream);
+/* normal derivative of the same sums at targets with unit normals (tnx, tny): the boundary operator of the homogeneous
+ * Neumann correction, examples/multi_modified_helmholtz_neumann.py:117-135 (`s_only` / `s_singular` blocks) */
+int ipde_layer_apply_scalar_dn(int kind, double k, const double* sx, const double* sy, const double* q,
+                               int64_t nsrc, const double* tx, const double* ty, const double* tnx, const double* tny,
+                               int64_t ntrg, double* out, int accumulate, void* stream);
 /* setup (QFS): dense out[i*ns + j] = K(t_i, s_j) w_j; layer 0 single, 1 double (normal derivative at the source) */
 int ipde_kernel_matrix(int kind, double k, int layer, const double* tx, const double* ty, int64_t nt, const double* sx,
                        const double* sy, const double* snx, const double* sny, const double* w, int64_t ns, double* out,

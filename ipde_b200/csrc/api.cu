@@ -431,6 +431,11 @@ int ipde_layer_apply_scalar(int kind, double k, const double* sx, const double* 
                             const double* tx, const double* ty, int64_t ntrg, double* out, int accumulate, void* stream) {
     return layer_apply_scalar(kind, k, sx, sy, q, nsrc, tx, ty, ntrg, out, accumulate, ST(stream));
 }
+int ipde_layer_apply_scalar_dn(int kind, double k, const double* sx, const double* sy, const double* q, int64_t nsrc,
+                               const double* tx, const double* ty, const double* tnx, const double* tny, int64_t ntrg,
+                               double* out, int accumulate, void* stream) {
+    return layer_apply_scalar_dn(kind, k, sx, sy, q, nsrc, tx, ty, tnx, tny, ntrg, out, accumulate, ST(stream));
+}
 int ipde_kernel_matrix(int kind, double k, int layer, const double* tx, const double* ty, int64_t nt, const double* sx,
                        const double* sy, const double* snx, const double* sny, const double* w, int64_t ns, double* out,
                        void* stream) {

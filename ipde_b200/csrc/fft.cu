@@ -315,7 +315,7 @@ k_fft_cols_pipe(FftPlanDev P, const cplx* in, cplx* out, int64_t elem_stride, in
 // Short power-of-two strided lines (N = RA*RB in {16, 32, 64}) held in registers, see fft_short.cuh.
 // Same contract as k_fft_cols (four-step twiddles, row windows, in == out allowed: tiles are disjoint and a tile is
 // read completely before it is written).
-template <int RA, int RB, int SIGN>
+template <int RA, int RB, int SIGN, bool SCATTER>
 __global__ void __launch_bounds__(128, 4)
 k_fft_cols_short(const cplx* __restrict__ tw, const cplx* in, cplx* out, int64_t elem_stride, int64_t n_inner,
                  int64_t outer_stride, double scale, int tw_mode, const cplx* __restrict__ tw_big, RowWindow W,
@@ -364,7 +364,7 @@ k_fft_cols_short(const cplx* __restrict__ tw, const cplx* in, cplx* out, int64_t
                     const cplx w = tw_big[S.o * e];
                     r = (SIGN < 0) ? cmul(r, w) : cmulc(r, w);
                 }
-                if (sc.R) {                               // backward slab transpose on the stores
+                if (SCATTER) {                            // backward slab transpose on the stores
                     if (sc.col0 + S.col < sc.P) *slab_bwd_addr(sc, row, S.col) = cscale(r, scale);
                 } else {
                     out[S.base + (int64_t)e * elem_stride] = cscale(r, scale);
@@ -563,12 +563,16 @@ static int launch_cols_short(FftPlan* p, const cplx* in, cplx* out, int64_t elem
     ARG_CHECK(total < (int64_t)1 << 30, "short column transform: too many tiles");
     const int64_t per_sm = 4;
     const unsigned g = (unsigned)std::min<int64_t>(total, (int64_t)ipde_num_sms() * per_sm);
-    if (sign < 0)
-        k_fft_cols_short<RA, RB, -1><<<g, 128, 0, st>>>(p->d.tw, in, out, elem_stride, n_inner, outer_stride, scale, tw_mode,
-                                                        tw_big, W, (int)tiles, (int)total, sc);
+    if (sc.R) {
+        ARG_CHECK(sign > 0, "short column transform: scattered stores are built for the inverse pass");
+        k_fft_cols_short<RA, RB, +1, true><<<g, 128, 0, st>>>(p->d.tw, in, out, elem_stride, n_inner, outer_stride, scale,
+                                                              tw_mode, tw_big, W, (int)tiles, (int)total, sc);
+    } else if (sign < 0)
+        k_fft_cols_short<RA, RB, -1, false><<<g, 128, 0, st>>>(p->d.tw, in, out, elem_stride, n_inner, outer_stride, scale,
+                                                               tw_mode, tw_big, W, (int)tiles, (int)total, sc);
     else
-        k_fft_cols_short<RA, RB, +1><<<g, 128, 0, st>>>(p->d.tw, in, out, elem_stride, n_inner, outer_stride, scale, tw_mode,
-                                                        tw_big, W, (int)tiles, (int)total, sc);
+        k_fft_cols_short<RA, RB, +1, false><<<g, 128, 0, st>>>(p->d.tw, in, out, elem_stride, n_inner, outer_stride, scale,
+                                                               tw_mode, tw_big, W, (int)tiles, (int)total, sc);
     KERNEL_CHECK();
     return IPDE_OK;
 }

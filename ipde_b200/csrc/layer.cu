@@ -118,6 +118,46 @@ __global__ void k_layer_scalar(const double* __restrict__ sx, const double* __re
     }
 }
 
+// normal derivative at the targets of the same sums: d/dn_t sum_s G(t - s) q_s, (tnx, tny) the target normals
+//   Laplace: -(d.n)/(2 pi r^2);  modified Helmholtz: -k K1(k r) (d.n)/(2 pi r),  d = t - s
+template <int KIND>
+__global__ void k_layer_scalar_dn(const double* __restrict__ sx, const double* __restrict__ sy, const double* __restrict__ q,
+                                  int64_t nsrc, const double* __restrict__ tx, const double* __restrict__ ty,
+                                  const double* __restrict__ tnx, const double* __restrict__ tny, int64_t ntrg, double kk,
+                                  int64_t chunk_len, double* __restrict__ partial) {
+    __shared__ double shx[LAYER_TILE], shy[LAYER_TILE], shq[LAYER_TILE];
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t s0 = blockIdx.y * chunk_len;
+    const int64_t s1 = min(nsrc, s0 + chunk_len);
+    const bool live = t < ntrg;
+    const double x = live ? tx[t] : 0.0, y = live ? ty[t] : 0.0;
+    const double nx = live ? tnx[t] : 0.0, ny = live ? tny[t] : 0.0;
+    double acc = 0.0;
+    for (int64_t base = s0; base < s1; base += LAYER_TILE) {
+        const int cnt = (int)min((int64_t)LAYER_TILE, s1 - base);
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+            shx[i] = sx[base + i]; shy[i] = sy[base + i]; shq[i] = q[base + i];
+        }
+        __syncthreads();
+        if (live) {
+#pragma unroll 4
+            for (int i = 0; i < cnt; ++i) {
+                const double dx = x - shx[i], dy = y - shy[i];
+                const double r2 = dx * dx + dy * dy;
+                const double dn = dx * nx + dy * ny;
+                if (KIND == 0) {
+                    acc -= dn / r2 * shq[i];
+                } else {
+                    const double r = sqrt(r2);
+                    acc -= kk * bessel_k1(kk * r, kk * kk * r2) * dn / r * shq[i];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (live) partial[(int64_t)blockIdx.y * ntrg + t] = acc * 0.15915494309189533577;   // 1/(2 pi)
+}
+
 // Stokes: forces (fx, fy) already weighted; outputs u, v, p
 __global__ void k_layer_stokes(const double* __restrict__ sx, const double* __restrict__ sy, const double* __restrict__ fx,
                                const double* __restrict__ fy, int64_t nsrc, const double* __restrict__ tx,
@@ -208,6 +248,32 @@ int layer_apply_scalar(int kind, double k, const double* sx, const double* sy, c
         k_layer_scalar<0><<<grid, LAYER_THREADS, 0, st>>>(sx, sy, q, nsrc, tx, ty, ntrg, k, chunk_len, partial);
     else
         k_layer_scalar<1><<<grid, LAYER_THREADS, 0, st>>>(sx, sy, q, nsrc, tx, ty, ntrg, k, chunk_len, partial);
+    KERNEL_CHECK();
+    k_layer_reduce<<<(int)std::max<int64_t>(1, std::min<int64_t>(cdiv(ntrg, 256), 2048)), 256, 0, st>>>(partial, nchunks, ntrg, out, accumulate);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+
+int layer_apply_scalar_dn(int kind, double k, const double* sx, const double* sy, const double* q, int64_t nsrc,
+                          const double* tx, const double* ty, const double* tnx, const double* tny, int64_t ntrg, double* out,
+                          int accumulate, cudaStream_t st) {
+    if (ntrg <= 0) return IPDE_OK;
+    if (nsrc <= 0) {
+        if (!accumulate) CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * ntrg, st));
+        return IPDE_OK;
+    }
+    if (kind == 1) ARG_CHECK(g_k0_ready, "K0 table not set (call ipde_set_k0_table)");
+    int nchunks; int64_t chunk_len;
+    choose_chunks(nsrc, ntrg, &nchunks, &chunk_len);
+    PartialScratch scratch(st);
+    int rc = scratch.get((size_t)nchunks * ntrg);
+    if (rc) return rc;
+    double* partial = scratch.ptr;
+    dim3 grid((unsigned)cdiv(ntrg, LAYER_THREADS), (unsigned)nchunks);
+    if (kind == 0)
+        k_layer_scalar_dn<0><<<grid, LAYER_THREADS, 0, st>>>(sx, sy, q, nsrc, tx, ty, tnx, tny, ntrg, k, chunk_len, partial);
+    else
+        k_layer_scalar_dn<1><<<grid, LAYER_THREADS, 0, st>>>(sx, sy, q, nsrc, tx, ty, tnx, tny, ntrg, k, chunk_len, partial);
     KERNEL_CHECK();
     k_layer_reduce<<<(int)std::max<int64_t>(1, std::min<int64_t>(cdiv(ntrg, 256), 2048)), 256, 0, st>>>(partial, nchunks, ntrg, out, accumulate);
     KERNEL_CHECK();

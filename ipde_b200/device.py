@@ -364,6 +364,18 @@ def layer_apply_scalar(kind, k, sx, sy, q, tx, ty, out=None, accumulate=False):
     return out
 
 
+def layer_apply_scalar_dn(kind, k, sx, sy, q, tx, ty, tnx, tny, out=None, accumulate=False):
+    """normal derivative at targets with unit normals (tnx, tny) of the sums of layer_apply_scalar"""
+    if kind == 1:
+        ensure_k0_table()
+    nt = int(tx.numel())
+    if out is None:
+        out = empty((nt,))
+    lib().ipde_layer_apply_scalar_dn(kind, float(k), ptr(sx), ptr(sy), ptr(q), int(sx.numel()), ptr(tx), ptr(ty),
+                                     ptr(tnx), ptr(tny), nt, ptr(out), 1 if accumulate else 0, stream())
+    return out
+
+
 def layer_apply_stokes(sx, sy, fx, fy, tx, ty, out=None, accumulate=False):
     nt = int(tx.numel())
     if out is None:

@@ -283,15 +283,28 @@ class SlabGridSolverP2P(object):
         if world > 1:
             gathered = [None]*world
             dist.all_gather_object(gathered, handles, group=group)
-        for q in range(world):
-            for which in range(2):
-                if q == rank:
-                    tables[which][q] = self._own[which].value
-                else:
-                    dp = ctypes.c_void_p()
-                    L_.ipde_ipc_open(gathered[q][which], ctypes.byref(dp))
-                    self._mapped.append(dp)
-                    tables[which][q] = dp.value
+        failure = None
+        try:
+            for q in range(world):
+                for which in range(2):
+                    if q == rank:
+                        tables[which][q] = self._own[which].value
+                    else:
+                        dp = ctypes.c_void_p()
+                        L_.ipde_ipc_open(gathered[q][which], ctypes.byref(dp))
+                        self._mapped.append(dp)
+                        tables[which][q] = dp.value
+        except Exception as exc:
+            failure = exc
+        if world > 1:
+            # every rank takes the same decision: a rank that cannot map a peer must not leave the others waiting
+            ok = torch.tensor([0 if failure is not None else 1], device='cuda')
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok) == 0:
+                self.close()
+                raise Exception('SlabGridSolverP2P: peer mapping failed on some rank (%s)' % (failure,))
+        elif failure is not None:
+            raise failure
         self.peer_cols = (ctypes.c_void_p*world)(*tables[0])
         self.peer_rows = (ctypes.c_void_p*world)(*tables[1])
         self._flag = torch.zeros(1, device='cuda')
@@ -315,6 +328,10 @@ class SlabGridSolverP2P(object):
         self._own, self._mapped = None, []
         L_.ipde_fft_plan_destroy(self.row_plan)
         L_.ipde_grid_plan_destroy(self.col_plan)
+
+    def __del__(self):
+        # buffers that peers may still have mapped are released by close() (collective); never from the collector
+        pass
 
     def _fence(self):
         """stream-ordered: returns (on the stream) once the kernels enqueued so far on EVERY rank have completed"""

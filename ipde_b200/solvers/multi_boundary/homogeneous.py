@@ -24,7 +24,7 @@ Both routes compute the unique solution of the homogeneous Dirichlet problem; th
 import numpy as np
 import scipy.sparse.linalg
 
-from ...device import to_dev, empty, layer_apply_scalar, FreeSpaceEvaluator
+from ...device import to_dev, empty, layer_apply_scalar, layer_apply_scalar_dn, FreeSpaceEvaluator
 from ...embedded_function import EmbeddedFunction
 from ...qfs import Laplace_QFS, Modified_Helmholtz_QFS
 from ..internals.scalar import DeviceQFS, device_qfs
@@ -44,10 +44,7 @@ class DirichletCorrection(object):
         self.kind, self.k = solver.kernel_kind, float(solver.k)
         self.qfs, self.dqfs = [], []
         for ebdy in e:
-            if self.kind == 0:
-                q = Laplace_QFS(ebdy.bdy, ebdy.interior, True, False, tol=tol, b2c=False)
-            else:
-                q = Modified_Helmholtz_QFS(ebdy.bdy, ebdy.interior, True, False, self.k, tol=tol, b2c=False)
+            q = self._build_qfs(ebdy, tol)
             self.qfs.append(q)
             self.dqfs.append(device_qfs(q))
         self.nb = [ebdy.bdy.N for ebdy in e]
@@ -75,6 +72,12 @@ class DirichletCorrection(object):
         else:
             self.d_tx, self.d_ty = to_dev(pts.x), to_dev(pts.y)
         self.iterations = 0
+
+    def _build_qfs(self, ebdy, tol):
+        """boundary values -> sources (u2s) only"""
+        if self.kind == 0:
+            return Laplace_QFS(ebdy.bdy, ebdy.interior, True, False, tol=tol, b2c=False)
+        return Modified_Helmholtz_QFS(ebdy.bdy, ebdy.interior, True, False, self.k, tol=tol, b2c=False)
 
     # ---- boundary data -> weighted source strengths of every boundary (one flat device vector)
     def _sources(self, tau_blocks, out):
@@ -119,6 +122,10 @@ class DirichletCorrection(object):
         bv = self.solver.get_boundary_values(ue)
         g = np.asarray(bc, dtype=float).ravel() - np.asarray(bv, dtype=float).ravel()
         tau = self.densities(g, **kwargs)
+        return self._add_field(ue, tau)
+
+    def _add_field(self, ue, tau):
+        """ue + field of the sources of the boundary densities tau on all physical grid points and radial points"""
         t = to_dev(tau)
         q = self._sources([t[self.boff[i]:self.boff[i + 1]] for i in range(len(self.dqfs))],
                           empty((int(self.soff[-1]),)))
@@ -128,3 +135,76 @@ class DirichletCorrection(object):
         else:
             layer_apply_scalar(self.kind, self.k, self.d_sx, self.d_sy, q, self.d_tx, self.d_ty, out=u, accumulate=True)
         return EmbeddedFunction(self.ebdyc, linear_data=u.cpu().numpy())
+
+
+class NeumannCorrection(DirichletCorrection):
+    """
+    Homogeneous correction for NEUMANN data (examples/multi_modified_helmholtz_neumann.py:97-163): after
+    `ue = solver(f)`, find the homogeneous solution whose normal derivative on every boundary is
+    bc_n - d/dn ue, and add it on all grid and radial points.
+
+    The reference solves the second-kind equation (S' -+ I/2) tau = g for a single-layer density with pybie2d's Kress
+    self-quadrature (its `s_singular` / `s_only` blocks, :117-131), then tau -> QFS sources -> Layer_Apply (:141-158).
+    Here the same density is the unknown, but the operator is applied THROUGH the sources:
+
+        sigma_j = QFS_j(tau_j)                        density -> effective sources (single-layer QFS, as :146)
+        (A tau)_i = d/dn_i sum_j S(bdy_i <- src_j) sigma_j     k_layer_scalar_dn, every pair (i, j), i = j included
+
+    Since the sources of QFS_j carry the single-layer potential of tau_j on the physical side, A is the reference's
+    second-kind operator (GMRES: a few tens of iterations) without a singular quadrature; and because the correction
+    that is finally added IS the field of these sources -- an exact solution of the homogeneous equation whose normal
+    derivative is collocated at the boundary nodes -- its accuracy is that of the source representation, not of the
+    quadrature.  Modified Helmholtz only (the pure Neumann Poisson problem is singular; the reference has no such
+    example).  Normals: `bdy.normal_x/y`, the convention of `solver.get_boundary_normal_derivatives`.
+    """
+
+    def __init__(self, solver, tol=1e-12, evaluation='auto'):
+        if solver.kernel_kind == 0:
+            raise Exception('NeumannCorrection: modified Helmholtz only (the pure Neumann Poisson problem is singular)')
+        DirichletCorrection.__init__(self, solver, tol=tol, evaluation=evaluation)
+        self.d_bnx = [to_dev(ebdy.bdy.normal_x) for ebdy in self.ebdyc]
+        self.d_bny = [to_dev(ebdy.bdy.normal_y) for ebdy in self.ebdyc]
+
+    def _build_qfs(self, ebdy, tol):
+        """single-layer density -> sources (examples/multi_modified_helmholtz_neumann.py:146)"""
+        return Modified_Helmholtz_QFS(ebdy.bdy, ebdy.interior, True, False, self.k, tol=tol, u2s=False)
+
+    def _sources(self, tau_blocks, out):
+        for i, dq in enumerate(self.dqfs):
+            s = dq(tau_blocks[i])
+            out[self.soff[i]:self.soff[i + 1]] = s*dq.sw
+        return out
+
+    def _apply(self, tau_host):
+        n = len(self.dqfs)
+        t = to_dev(np.ascontiguousarray(tau_host, dtype=float))
+        blocks = [t[self.boff[i]:self.boff[i + 1]] for i in range(n)]
+        q = self._sources(blocks, empty((int(self.soff[-1]),)))
+        res = empty((int(self.boff[-1]),))
+        for i in range(n):
+            layer_apply_scalar_dn(self.kind, self.k, self.d_sx, self.d_sy, q, self.d_bx[i], self.d_by[i], self.d_bnx[i],
+                                  self.d_bny[i], out=res[self.boff[i]:self.boff[i + 1]])
+        return res.cpu().numpy()
+
+    def densities(self, g, tol=1e-13, restart=80, maxiter=10):
+        g = np.asarray(g, dtype=float).ravel()
+        count = [0]
+        def cb(_):
+            count[0] += 1
+        A = scipy.sparse.linalg.LinearOperator((g.size, g.size), matvec=self._apply, dtype=float)
+        tau, info = scipy.sparse.linalg.gmres(A, g, rtol=tol, atol=0.0, restart=restart, maxiter=maxiter, callback=cb,
+                                              callback_type='pr_norm')
+        self.iterations = count[0]
+        if info != 0:
+            raise Exception('NeumannCorrection: GMRES on the boundary system did not converge (info = %d)' % info)
+        return tau
+
+    def boundary_normal_derivative_of_sources(self, tau):
+        """d/dn of the correction on every boundary (the quantity GMRES matched to the data)"""
+        return self._apply(np.asarray(tau, dtype=float).ravel())
+
+    def __call__(self, ue, bc_n, **kwargs):
+        bn = self.solver.get_boundary_normal_derivatives(ue)
+        g = np.asarray(bc_n, dtype=float).ravel() - np.asarray(bn, dtype=float).ravel()
+        self.tau = self.densities(g, **kwargs)
+        return self._add_field(ue, self.tau)

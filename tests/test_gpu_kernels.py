@@ -123,6 +123,34 @@ def test_nufft2_against_direct_sum(D, shape):
         assert np.abs(v.cpu().numpy() - ref[i]).max()/scale[i] < (tol if i == 0 else 5*tol), i
 
 
+@pytest.mark.parametrize('kind,k', [(0, 0.0), (1, 3.7)])
+def test_layer_apply_scalar_normal_derivative(D, kind, k):
+    """k_layer_scalar_dn: d/dn_t of the point-source sums against NumPy/SciPy (K1), near and far pairs"""
+    rng = np.random.default_rng(11)
+    ns, nt = 700, 333
+    sx, sy = rng.uniform(-1, 1, ns), rng.uniform(-1, 1, ns)
+    tx, ty = rng.uniform(-1.2, 1.2, nt), rng.uniform(-1.2, 1.2, nt)
+    tx[:5], ty[:5] = sx[:5] + 1e-3, sy[:5] - 2e-3          # close pairs (small-argument branch of K1)
+    tx[5:8], ty[5:8] = sx[5:8] + 3.0, sy[5:8] + 2.0         # large arguments (Chebyshev tail)
+    th = rng.uniform(0, 2*np.pi, nt)
+    nx, ny = np.cos(th), np.sin(th)
+    q = rng.standard_normal(ns)
+    dx, dy = tx[:, None] - sx[None, :], ty[:, None] - sy[None, :]
+    r = np.hypot(dx, dy)
+    dn = dx*nx[:, None] + dy*ny[:, None]
+    if kind == 0:
+        ref = (-dn/r**2/(2*np.pi)).dot(q)
+    else:
+        ref = (-k*scipy.special.k1(k*r)*dn/r/(2*np.pi)).dot(q)
+    out = D.layer_apply_scalar_dn(kind, k, D.to_dev(sx), D.to_dev(sy), D.to_dev(q), D.to_dev(tx), D.to_dev(ty),
+                                  D.to_dev(nx), D.to_dev(ny)).cpu().numpy()
+    assert np.abs(out - ref).max() < 1e-13*np.abs(ref).max()
+    acc = D.to_dev(np.ones(nt))
+    D.layer_apply_scalar_dn(kind, k, D.to_dev(sx), D.to_dev(sy), D.to_dev(q), D.to_dev(tx), D.to_dev(ty), D.to_dev(nx),
+                            D.to_dev(ny), out=acc, accumulate=True)
+    assert np.abs(acc.cpu().numpy() - 1.0 - ref).max() < 1e-13*np.abs(ref).max()
+
+
 @pytest.mark.parametrize('M,n', [(8, 40), (16, 300), (20, 1000)])
 def test_radial_to_points(D, M, n):
     from oracle.solvers import interpolate_radial_to_points

@@ -399,6 +399,50 @@ def test_dirichlet_correction_poisson():
     assert np.abs(us[0] - us[1]).max() < 1e-10
 
 
+def _normal_data(ebdyc, kk):
+    """d/dn of the manufactured solution exp(sin(kk x)) sin(kk y) with the boundary normals"""
+    out = []
+    for e in ebdyc:
+        b = e.bdy
+        ux = kk*np.cos(kk*b.x)*np.exp(np.sin(kk*b.x))*np.sin(kk*b.y)
+        uy = kk*np.exp(np.sin(kk*b.x))*np.cos(kk*b.y)
+        out.append(ux*b.normal_x + uy*b.normal_y)
+    return np.concatenate(out)
+
+
+@pytest.mark.parametrize('bodies', [1, 3])
+def test_neumann_correction(bodies):
+    """SURVEY 8(f).1, Neumann data (examples/multi_modified_helmholtz_neumann.py:97-163): inhomogeneous solve + the
+    homogeneous correction whose normal derivative matches bc_n - d/dn ue reproduces the analytic solution; the
+    normal-derivative getter of the solver uses the boundary normals; both evaluation back-ends agree"""
+    from ipde_b200.solvers.multi_boundary.modified_helmholtz import ModifiedHelmholtzSolver
+    from ipde_b200.solvers.multi_boundary.homogeneous import NeumannCorrection
+    if bodies == 1:
+        ebdyc, k, kk = single_star(nb=400, M=12, ng=480), 2.0, np.pi/3
+    else:
+        ebdyc, k, kk = three_bodies(nb=200, M=12), 5.0, 10*np.pi/7
+    f, ua, sol = manufactured(ebdyc, k, kk=kk)
+    solver = ModifiedHelmholtzSolver(ebdyc, k)
+    bcn = _normal_data(ebdyc, kk)
+    # convention of the getter: d/dn with bdy.normal_x/y (as the reference's bcs2v - bvs, :78,:134-137)
+    dn_exact = np.asarray(solver.get_boundary_normal_derivatives(ua))
+    assert np.abs(dn_exact - bcn).max() < 1e-6*np.abs(bcn).max()
+    ue = solver(f, tol=1e-13, restart=60, maxiter=5)
+    us = []
+    for ev in ('direct', 'ewald'):
+        corr = NeumannCorrection(solver, evaluation=ev)
+        u = corr(ue, bcn)
+        assert 1 <= corr.iterations <= 80, corr.iterations
+        err = np.abs(np.asarray(u) - np.asarray(ua)).max()
+        print('neumann', bodies, ev, 'iterations', corr.iterations, 'err %.2e' % err)
+        assert err < 5e-7, (ev, err)
+        # the correction's own normal derivative is the data GMRES was given
+        g = bcn - np.asarray(solver.get_boundary_normal_derivatives(ue))
+        assert np.abs(corr.boundary_normal_derivative_of_sources(corr.tau) - g).max() < 1e-10*max(1.0, np.abs(g).max())
+        us.append(np.asarray(u))
+    assert np.abs(us[0] - us[1]).max() < 1e-10
+
+
 def test_traction_computation():
     """examples/test_traction_computation.py:97-147 (the traction check of BASELINE configs[3]): the traction of an
     analytic Stokes field on the interface / boundary from (i) the grid stress through the spectral interface
