@@ -188,6 +188,11 @@ int ipde_radial_traction(const double* Ur, const double* Ut, const double* dUr, 
 int ipde_vector_jumps(const double* rtx, const double* rty, const double* txx, const double* txy, const double* tyy,
                       const double* bu, const double* bv, const double* inx, const double* iny, int n, double sign,
                       double* tau, void* stream);
+/* pr (M, n) += mean_j [ -(txx_j + tyy_j)/2 + pb_j - sum_i est_i pr[i, j] ]: removes the pressure jump across the
+ * interface between the grid side (grid solve + grid-side sources pb) and the annulus side, whose additive constants
+ * the stokeslet representations of ipde/solvers/internals/vector.py:104-162 leave free */
+int ipde_pressure_continuity(const double* txx, const double* tyy, const double* pb, const double* est, double* pr, int M,
+                             int n, void* stream);
 /* d/dt of `rows` real rows of length n (plan from ipde_fft_plan_create(n)); work_cplx: rows*n complex.
  * EmbeddedBoundary._radial_grid_t_derivative, ipde/embedded_boundary.py:473-474 */
 int ipde_theta_derivative(void* fft_plan, const double* f, double* work_cplx, double* out, int rows, void* stream);

@@ -383,6 +383,10 @@ int ipde_vector_jumps(const double* rtx, const double* rty, const double* txx, c
                       double* tau, void* stream) {
     return vec_jumps(rtx, rty, txx, txy, tyy, bu, bv, inx, iny, n, sign, tau, ST(stream));
 }
+int ipde_pressure_continuity(const double* txx, const double* tyy, const double* pb, const double* est, double* pr, int M,
+                             int n, void* stream) {
+    return vec_pressure_continuity(txx, tyy, pb, est, pr, M, n, ST(stream));
+}
 int ipde_theta_derivative(void* fft_plan, const double* f, double* work_cplx, double* out, int rows, void* stream) {
     return vec_theta_derivative((FftPlan*)fft_plan, f, work_cplx, out, rows, ST(stream));
 }

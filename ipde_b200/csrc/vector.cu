@@ -101,6 +101,43 @@ int vec_jumps(const double* rtx, const double* rty, const double* txx, const dou
     return IPDE_OK;
 }
 
+// Pressure continuity across the interface.  A set of stokeslets determines the pressure it generates only up to what
+// the velocity fixes (grad p = lap u): the grid side (grid solve + grid-side sources) and the annulus side (annular
+// solve, whose constant pressure mode is free, + annulus-side sources) each carry their own additive constant, while
+// the pressure of the solution is continuous across the interface.  One CTA:
+//     shift = mean_j [ -(txx_j + tyy_j)/2 + pb_j - sum_i est_i pr[i, j] ],     pr += shift
+// (-(txx + tyy)/2 = grid-solve pressure at interface node j, the grid velocity being divergence free; pb = pressure of
+// all grid-side sources there; est = radial interpolation weights to the interface.)
+__global__ void k_pressure_continuity(const double* __restrict__ txx, const double* __restrict__ tyy, const double* __restrict__ pb,
+                                      const double* __restrict__ est, double* __restrict__ pr, int M, int n) {
+    __shared__ double red[32];
+    __shared__ double shift;
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        double a = -0.5 * (txx[j] + tyy[j]) + pb[j];
+        for (int i = 0; i < M; ++i) a -= est[i] * pr[(int64_t)i * n + j];
+        acc += a;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) shift = v / (double)n;
+    }
+    __syncthreads();
+    const double c = shift;
+    const int64_t count = (int64_t)M * n;
+    for (int64_t i = threadIdx.x; i < count; i += blockDim.x) pr[i] += c;
+}
+int vec_pressure_continuity(const double* txx, const double* tyy, const double* pb, const double* est, double* pr, int M, int n,
+                            cudaStream_t st) {
+    k_pressure_continuity<<<1, 1024, 0, st>>>(txx, tyy, pb, est, pr, M, n);
+    KERNEL_CHECK();
+    return IPDE_OK;
+}
+
 // d/dt of real (M, n) rows: ifft(i k fft(f)).real with all n modes (embedded_boundary.py:473-474)
 __global__ void k_real_to_cplx_rows(const double* __restrict__ in, cplx* __restrict__ out, int64_t total) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)

@@ -9,3 +9,5 @@ int vec_radial_traction(const double* Ur, const double* Ut, const double* dUr, c
 int vec_jumps(const double* rtx, const double* rty, const double* txx, const double* txy, const double* tyy, const double* bu,
               const double* bv, const double* inx, const double* iny, int n, double sign, double* tau, cudaStream_t st);
 int vec_theta_derivative(FftPlan* p, const double* f, double* work_cplx, double* out, int rows, cudaStream_t st);
+int vec_pressure_continuity(const double* txx, const double* tyy, const double* pb, const double* est, double* pr, int M, int n,
+                            cudaStream_t st);

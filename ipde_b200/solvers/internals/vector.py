@@ -80,7 +80,7 @@ class VectorHelper(object):
         self.curve_w = self.curve_r = None
         if getattr(self.interface_qfs_g, 'structured', False) and getattr(self.interface_qfs_r, 'structured', False):
             from ...qfs_structured import source_to_curves
-            self.curve_w = DeviceCurveOperator(source_to_curves(self.interface_qfs_g, [e.interface.c]))
+            self.curve_w = DeviceCurveOperator(source_to_curves(self.interface_qfs_g, [e.interface.c], pressure=True))
             levels = [e.radial_x[i] + 1j*e.radial_y[i] for i in range(M)]
             self.curve_r = DeviceCurveOperator(source_to_curves(self.interface_qfs_r, levels, pressure=True))
 
@@ -156,6 +156,7 @@ class VectorHelper(object):
         self.sigma_g = v2f(self.d_qfs_g(self._tau))
         self.sigma_r = v2f(self.d_qfs_r(self._tau))
         self.ur, self.vr, self.pr = ur, vr, pr
+        self._btxx, self._btyy = btxx, btyy
         return self.sigma_g
 
     def _weighted(self, sigma, w):
@@ -165,24 +166,38 @@ class VectorHelper(object):
         lib().ipde_vec_mul(ptr(sigma[1]), ptr(w), ptr(q[1]), m, stream())
         return q
 
+    def _own_interface_field(self):
+        """(u, v, p) of this boundary's grid-side sources on its own interface"""
+        g = self.d_qfs_g
+        n = self.ebdy.bdy.N
+        if self.curve_w is not None:
+            w = empty((3, n))
+            self.curve_w(self.sigma_g.reshape(-1), [w[0], w[1], w[2]])
+            return w
+        q = self._weighted(self.sigma_g, g.sw)
+        if getattr(self, 'evaluation', 'direct') == 'ewald' and self.evaluator_w is not None:
+            return self.evaluator_w(q[0], q[1])
+        return layer_apply_stokes(g.sx, g.sy, q[0], q[1], self.d_ix, self.d_iy)
+
+    def _pressure_continuity(self, pb):
+        """shift the radial pressure so that it continues the grid-side pressure across the interface (the two sides'
+        stokeslet representations each leave their additive constant free; csrc/vector.cu:k_pressure_continuity)"""
+        e = self.ebdy
+        lib().ipde_pressure_continuity(ptr(self._btxx), ptr(self._btyy), ptr(pb), ptr(self.d_iv_est), ptr(self.pr), e.M,
+                                       e.bdy.N, stream())
+
     def correct(self, ub, vb, pb, single_ebdy, own_field=None):
+        """ub, vb, pb: field of ALL grid-side sources on this boundary's interface (multi-boundary collections; a
+        single boundary computes its own)"""
         g, r = self.d_qfs_g, self.d_qfs_r
         n = self.ebdy.bdy.N
         ewald = getattr(self, 'evaluation', 'direct') == 'ewald'
         if single_ebdy:
             sigma_r_tot = self.sigma_r
+            w = self._own_interface_field()
+            pb = w[2] if w.shape[0] > 2 else None
         else:
-            if own_field is not None:
-                w = own_field                  # caller-provided field of our own grid-side sources on our interface
-            elif self.curve_w is not None:
-                w = empty((2, n))
-                self.curve_w(self.sigma_g.reshape(-1), [w[0], w[1]])
-            else:
-                q = self._weighted(self.sigma_g, g.sw)
-                if ewald and self.evaluator_w is not None:
-                    w = self.evaluator_w(q[0], q[1])
-                else:
-                    w = layer_apply_stokes(g.sx, g.sy, q[0], q[1], self.d_ix, self.d_iy)
+            w = own_field if own_field is not None else self._own_interface_field()
             Ub = empty((2*n,))
             lib().ipde_vec_axpby(1.0, ptr(ub), -1.0, ptr(w[0]), ptr(Ub[:n]), n, stream())
             lib().ipde_vec_axpby(1.0, ptr(vb), -1.0, ptr(w[1]), ptr(Ub[n:]), n, stream())
@@ -196,14 +211,16 @@ class VectorHelper(object):
             for i in range(self.ebdy.M):
                 rows += [self.ur[i], self.vr[i], self.pr[i]]
             self.curve_r(sigma_r_tot.reshape(-1), rows, accumulate=True)
-            return self.ur, self.vr, self.pr
-        q = self._weighted(sigma_r_tot, r.sw)
-        nt = int(self.d_rx.numel())
-        if ewald:
-            # accumulated straight into the radial blocks
-            self.evaluator_r(q[0], q[1], point_out=(self.ur.view(-1), self.vr.view(-1), self.pr.view(-1)))
         else:
-            rslp = layer_apply_stokes(r.sx, r.sy, q[0], q[1], self.d_rx, self.d_ry)
-            for dst, k in ((self.ur, 0), (self.vr, 1), (self.pr, 2)):
-                lib().ipde_vec_axpby(1.0, ptr(dst), 1.0, ptr(rslp[k]), ptr(dst), nt, stream())
+            q = self._weighted(sigma_r_tot, r.sw)
+            nt = int(self.d_rx.numel())
+            if ewald:
+                # accumulated straight into the radial blocks
+                self.evaluator_r(q[0], q[1], point_out=(self.ur.view(-1), self.vr.view(-1), self.pr.view(-1)))
+            else:
+                rslp = layer_apply_stokes(r.sx, r.sy, q[0], q[1], self.d_rx, self.d_ry)
+                for dst, k in ((self.ur, 0), (self.vr, 1), (self.pr, 2)):
+                    lib().ipde_vec_axpby(1.0, ptr(dst), 1.0, ptr(rslp[k]), ptr(dst), nt, stream())
+        if pb is not None:
+            self._pressure_continuity(pb.contiguous())
         return self.ur, self.vr, self.pr

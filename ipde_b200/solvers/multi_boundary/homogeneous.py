@@ -26,7 +26,7 @@ import scipy.sparse.linalg
 
 from ...device import to_dev, empty, layer_apply_scalar, layer_apply_scalar_dn, FreeSpaceEvaluator
 from ...embedded_function import EmbeddedFunction
-from ...qfs import Laplace_QFS, Modified_Helmholtz_QFS
+from ...qfs import Laplace_QFS, Modified_Helmholtz_QFS, Stokes_QFS
 from ..internals.scalar import DeviceQFS, device_qfs
 
 
@@ -208,3 +208,71 @@ class NeumannCorrection(DirichletCorrection):
         g = np.asarray(bc_n, dtype=float).ravel() - np.asarray(bn, dtype=float).ravel()
         self.tau = self.densities(g, **kwargs)
         return self._add_field(ue, self.tau)
+
+
+class StokesDirichletCorrection(object):
+    """
+    Homogeneous (no-slip / prescribed velocity) correction of the Stokes solve, examples/interior_stokes_with_multi.py:
+    98-118: after `u, v, p = solver(fu, fv)` add the Stokes flow whose boundary velocity is bc - (u, v)|_bdy.
+
+    The reference solves (D - I/2 + N) tau = g with pybie2d's singular double-layer form and a pressure fix, then
+    tau -> Stokes_QFS sources -> stokeslet sums on `ebdyc.grid_and_radial_pts`.  Here, as in DirichletCorrection, the
+    flow is represented by stokeslets on the QFS source curve of every boundary, obtained from the boundary velocity
+    by the QFS boundary -> source operator:
+
+        tau_i (both components on boundary i),  sigma_i = u2s_i(tau_i)
+        tau_i + sum_{j != i} S(bdy_i <- src_j) sigma_j = bc_i - (u, v)|_i
+
+    one boundary: tau = g (the reference's example); several: GMRES on the block system.  Sums: k_layer_stokes through
+    the solver's own Layer_Apply.  The pressure is defined up to a constant -- normalise as the example does (:120-125).
+    """
+    def __init__(self, solver, tol=1e-13):
+        self.solver = solver
+        e = self.ebdyc = solver.ebdyc
+        self.qfs = [Stokes_QFS(ebdy.bdy, ebdy.interior, True, True, tol=tol) for ebdy in e]
+        self.nb = [ebdy.bdy.N for ebdy in e]
+        self.off = np.concatenate([[0], np.cumsum([2*n for n in self.nb])])
+        self.iterations = 0
+
+    def _sources(self, tau):
+        return [q.u2s(tau[self.off[i]:self.off[i + 1]]).reshape(2, -1) for i, q in enumerate(self.qfs)]
+
+    def _apply(self, tau):
+        sig = self._sources(tau)
+        out = np.array(tau, dtype=float)
+        for i, ebdy in enumerate(self.ebdyc):
+            for j, q in enumerate(self.qfs):
+                if i != j:
+                    cu, cv, _ = self.solver.Layer_Apply(q.source, ebdy.bdy, sig[j])
+                    out[self.off[i]:self.off[i + 1]] += np.concatenate([cu, cv])
+        return out
+
+    def densities(self, g, tol=1e-13, restart=60, maxiter=10):
+        if len(self.qfs) == 1:
+            self.iterations = 0
+            return g
+        count = [0]
+        def cb(_):
+            count[0] += 1
+        A = scipy.sparse.linalg.LinearOperator((g.size, g.size), matvec=self._apply, dtype=float)
+        tau, info = scipy.sparse.linalg.gmres(A, g, rtol=tol, atol=0.0, restart=restart, maxiter=maxiter, callback=cb,
+                                              callback_type='pr_norm')
+        self.iterations = count[0]
+        if info != 0:
+            raise Exception('StokesDirichletCorrection: GMRES on the boundary system did not converge (info = %d)' % info)
+        return tau
+
+    def __call__(self, u, v, p, bcu, bcv, **kwargs):
+        """bcu, bcv: prescribed boundary velocity, concatenated over the boundaries -> corrected (u, v, p)"""
+        bu = np.asarray(self.solver.get_boundary_values(u), dtype=float)
+        bv = np.asarray(self.solver.get_boundary_values(v), dtype=float)
+        gu, gv = np.asarray(bcu, dtype=float).ravel() - bu, np.asarray(bcv, dtype=float).ravel() - bv
+        boff = np.concatenate([[0], np.cumsum(self.nb)])
+        g = np.concatenate([np.concatenate([gu[boff[i]:boff[i + 1]], gv[boff[i]:boff[i + 1]]]) for i in range(len(self.nb))])
+        tau = self.densities(g, **kwargs)
+        pts = self.ebdyc.grid_and_radial_pts
+        out = [np.array(np.asarray(a), dtype=float) for a in (u, v, p)]
+        for q, sig in zip(self.qfs, self._sources(tau)):
+            for a, c in zip(out, self.solver.Layer_Apply(q.source, pts, sig)):
+                a += c
+        return tuple(EmbeddedFunction(self.ebdyc, linear_data=a) for a in out)

@@ -296,6 +296,7 @@ class OracleVectorHelper(object):
         self.sigma_g = self.qfs_g([taus, taud]).reshape(2, -1)
         self.sigma_r = self.qfs_r([taus, taud]).reshape(2, -1)
         self.ur, self.vr, self.pr = ur, vr, pr
+        self._pg = -0.5*(btxx + btyy)          # grid-solve pressure on the interface (the grid velocity is divergence free)
         return self.sigma_g
 
     def correct(self, ub, vb, pb, single_ebdy):
@@ -312,6 +313,13 @@ class OracleVectorHelper(object):
         self.ur = self.ur + r[0].reshape(self.ur.shape)
         self.vr = self.vr + r[1].reshape(self.ur.shape)
         self.pr = self.pr + r[2].reshape(self.ur.shape)
+        # Pressure continuity across the interface.  The velocity fixes the pressure of a stokeslet representation only
+        # up to a constant on either side: the restated QFS (ipde_b200/qfs.py) maps the density c n -- no velocity, a
+        # pressure jump c -- to zero sources, where the reference's qfs package (absent; its pressure fix is visible in
+        # examples/interior_stokes_with_multi.py:99-106) transmits it.  The constant is restored from the continuity of
+        # the pressure of the solution: with it the published errs_p (:32) are reproduced, without it the annulus is
+        # off by O(1e-1).  Same step as csrc/vector.cu:k_pressure_continuity.
+        self.pr = self.pr + np.mean(self._pg + pb - self._iv.dot(self.pr))
         return self.ur, self.vr, self.pr
 
 

@@ -142,10 +142,12 @@ def test_stokes_single_boundary(solver_type):
     O = vector_oracle_for(solver, solver_type)
     uo, vo, po = O(fu, fv, tol=1e-13, restart=60, maxiter=4)
     scale = max(np.abs(uo).max(), np.abs(vo).max())
-    for got, ref, s in ((u, uo, scale), (v, vo, scale), (p, po, np.abs(po).max())):
+    # pressure: the annulus constant comes from the continuity step (interface means of interpolated stresses, each
+    # good to ~1e-12 of the stress scale): 3e-11 relative L2 (measured 1.0e-11), L-inf 1e-11
+    for got, ref, s, tol2 in ((u, uo, scale, TOL), (v, vo, scale, TOL), (p, po, np.abs(po).max(), 3*TOL)):
         linf = np.abs(np.asarray(got) - ref).max()/s
         l2 = np.linalg.norm(np.asarray(got) - ref)/np.linalg.norm(ref)
-        assert linf < TOL and l2 < TOL, (solver_type, linf, l2)
+        assert linf < TOL and l2 < tol2, (solver_type, linf, l2)
     assert abs(solver.iteration_counts[0] - O.iteration_counts[0]) <= 2
     assert u.shape == fu.shape and u[0].shape == (8, 200)
     # a20: boundary getters of the vector solver (multi_boundary/vector.py:53-56)
@@ -199,6 +201,9 @@ def test_stokes_three_boundaries():
     for b in range(len(ebdyc.ebdys)):
         blk = dp[n0 + sum(ebdyc.radial_dof_list[:b]):n0 + sum(ebdyc.radial_dof_list[:b + 1])]
         assert np.abs(blk - blk.mean()).max()/ps < TOL, b
+        # since the pressure-continuity step (k_pressure_continuity; the same in the oracle) the constant of every
+        # annulus is determined as well
+        assert abs(blk.mean())/ps < 1e-10, (b, blk.mean())
 
 
 @pytest.mark.parametrize('backend', ['direct', 'ewald'])
@@ -297,6 +302,7 @@ def test_stokes_ewald_backend(problem):
         blk = dp[n0 + sum(ebdyc.radial_dof_list[:b]):n0 + sum(ebdyc.radial_dof_list[:b + 1])]
         # measured (scripts/stokes_parity_probe.py): 5e-14 single, 1.9e-11 worst annulus of the three-body case
         assert np.abs(blk - blk.mean()).max()/ps < 5e-11, (problem, b)
+        assert abs(blk.mean())/ps < 1e-10, (problem, b, blk.mean())
         if problem == 'single':
             assert np.abs(blk).max()/ps < TOL
 
@@ -441,6 +447,64 @@ def test_neumann_correction(bodies):
         assert np.abs(corr.boundary_normal_derivative_of_sources(corr.tau) - g).max() < 1e-10*max(1.0, np.abs(g).max())
         us.append(np.asarray(u))
     assert np.abs(us[0] - us[1]).max() < 1e-10
+
+
+def test_neumann_correction_matches_oracle():
+    """device Neumann correction against its all-pairs NumPy statement (oracle/homogeneous.py) on identical inputs"""
+    from ipde_b200.solvers.multi_boundary.modified_helmholtz import ModifiedHelmholtzSolver
+    from ipde_b200.solvers.multi_boundary.homogeneous import NeumannCorrection
+    from oracle.homogeneous import OracleNeumannCorrection
+    ebdyc = three_bodies(nb=100, M=8)
+    f, ua, sol = manufactured(ebdyc, 5.0, kk=10*np.pi/7)
+    solver = ModifiedHelmholtzSolver(ebdyc, 5.0)
+    ue = solver(f, tol=1e-13, restart=60, maxiter=5)
+    bcn = _normal_data(ebdyc, 10*np.pi/7)
+    corr = NeumannCorrection(solver, evaluation='direct')
+    O = OracleNeumannCorrection(ebdyc, 5.0, corr.qfs)
+    uo = O(ue, bcn)
+    u = corr(ue, bcn)
+    linf, l2 = rel_errors(u, uo)
+    assert linf < 1e-10 and l2 < 1e-10, (linf, l2)
+    assert abs(corr.iterations - O.iterations) <= 3
+
+
+def test_stokes_dirichlet_correction():
+    """SURVEY 8(f).1, Stokes (examples/interior_stokes_with_multi.py:98-125): solve + homogeneous velocity correction +
+    pressure normalisation against the analytic (u, v, p), at the published resolution nb = 300 (errs_U 6.65e-07,
+    errs_p 6.57e-05, :31-32)"""
+    from problems import stokes_manufactured
+    from ipde_b200.geometry import GSB, Grid, star, arc_length_parameterize
+    from ipde_b200.embedded_boundary import EmbeddedBoundary
+    from ipde_b200.ebdy_collection import EmbeddedBoundaryCollection
+    from ipde_b200.embedded_function import EmbeddedFunction
+    from ipde_b200.slepian import SlepianMollifier
+    from ipde_b200.solvers.multi_boundary.stokes import StokesSolver
+    from ipde_b200.solvers.multi_boundary.homogeneous import StokesDirichletCorrection
+    nb = 300
+    M = 12
+    bdy = GSB(c=star(nb, a=0.1, f=5))
+    bdy = GSB(*arc_length_parameterize(bdy.x, bdy.y))
+    Lb = np.pi/2
+    grid = Grid([-Lb, Lb], nb//2, [-Lb, Lb], nb//2)
+    MOL = SlepianMollifier(int(1.5*M))
+    ebdy = EmbeddedBoundary(bdy, True, M, grid.xh*0.75, heaviside=MOL.step)
+    ebdyc = EmbeddedBoundaryCollection([ebdy])
+    ebdyc.register_grid(grid)
+    ebdyc.ready_bump(MOL.bump, (Lb - ebdy.radial_width, Lb - ebdy.radial_width), ebdy.radial_width)
+    fu, fv, ua, va, pa, (u_f, v_f, p_f) = stokes_manufactured(ebdyc)
+    solver = StokesSolver(ebdyc)
+    u, v, p = solver(fu, fv, tol=1e-14, restart=50, maxiter=4)
+    corr = StokesDirichletCorrection(solver)
+    u, v, p = corr(u, v, p, u_f(bdy.x, bdy.y), v_f(bdy.x, bdy.y))
+    area = EmbeddedFunction(ebdyc, function=lambda x, y: np.ones_like(x)).integrate()
+    pn = np.asarray(p) - p.integrate()/area
+    pan = np.asarray(pa) - pa.integrate()/area
+    eU = max(np.abs(np.asarray(u) - np.asarray(ua)).max(), np.abs(np.asarray(v) - np.asarray(va)).max())
+    eP = np.abs(pn - pan).max()
+    print('stokes correction nb=300: U %.2e (published 6.65e-07), p %.2e (published 6.57e-05)' % (eU, eP))
+    assert eU < 3*6.65e-07 and eP < 3*6.57e-05, (eU, eP)
+    # the corrected velocity takes the boundary values
+    assert np.abs(np.asarray(solver.get_boundary_values(u)) - u_f(bdy.x, bdy.y)).max() < 1e-8
 
 
 def test_traction_computation():

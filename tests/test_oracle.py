@@ -122,6 +122,35 @@ def test_oracle_dirichlet_correction_reproduces_manufactured_solution():
     assert err < 1e-6, err          # 2.2e-7 at this resolution (n_b = 300, M = 8)
 
 
+def test_oracle_neumann_correction_reproduces_manufactured_solution():
+    """the same with Neumann data (examples/multi_modified_helmholtz_neumann.py:97-163): oracle inhomogeneous solve +
+    the correction whose normal derivative matches bc_n - d/dn ue lands on the analytic solution"""
+    from problems import single_star, manufactured
+    from oracle.solvers import OracleScalarSolver
+    from oracle.homogeneous import OracleNeumannCorrection
+    from ipde_b200.qfs import Modified_Helmholtz_QFS
+    from ipde_b200.embedded_function import EmbeddedFunction
+    k, kk = 2.0, np.pi/3
+    ebdyc = single_star(nb=300, M=8)
+    f, ua, sol = manufactured(ebdyc, k, kk=kk)
+    ebdy = ebdyc[0]
+    pair = (Modified_Helmholtz_QFS(ebdy.interface, True, True, True, k, tol=1e-12, u2s=False, device_build=False),
+            Modified_Helmholtz_QFS(ebdy.interface, False, True, True, k, tol=1e-12, device_build=False))
+    O = OracleScalarSolver(ebdyc, 'modified_helmholtz', k, 'spectral', [pair])
+    uo = EmbeddedFunction(ebdyc, linear_data=np.asarray(O(f, tol=1e-13, restart=60, maxiter=5)))
+    b = ebdy.bdy
+    ux = kk*np.cos(kk*b.x)*np.exp(np.sin(kk*b.x))*np.sin(kk*b.y)
+    uy = kk*np.exp(np.sin(kk*b.x))*np.cos(kk*b.y)
+    bcn = ux*b.normal_x + uy*b.normal_y
+    qb = Modified_Helmholtz_QFS(b, True, True, False, k, tol=1e-12, u2s=False, device_build=False)
+    corr = OracleNeumannCorrection(ebdyc, k, [qb])
+    u = corr(uo, bcn)
+    err = np.abs(u - np.asarray(ua)).max()
+    assert np.abs(np.asarray(uo) - np.asarray(ua)).max() > 0.1      # the correction matters
+    assert 1 <= corr.iterations <= 40
+    assert err < 2e-6, err
+
+
 @pytest.mark.parametrize('kind,kappa,N', [(0, 0.0, 96), (1, 2.0, 96), (1, 20.0, 64)])
 def test_numpy_spectral_ewald_matches_direct_sum(kind, kappa, N):
     """host tables and mathematics of the free-space evaluator (ipde_b200/ewald.py) on the CPU: truncated kernel,
