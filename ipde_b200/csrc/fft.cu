@@ -1430,6 +1430,109 @@ __global__ void k_r2c_untangle_split(int m, const cplx* __restrict__ twn, const 
         }
     }
 }
+// r2c of rows of 2n reals (n = 2m complex), one CLUSTER OF TWO CTAs per row -- the forward counterpart of
+// k_c2r_rows_long, replacing the strided sub-transforms + in-place untangle pass:
+//   loads    rank c reads the contiguous half [c m, (c+1) m) of the packed row z[j] = (x[2j], x[2j+1]) and deals it out:
+//            z[2i + r] goes to slot i of rank r's shared memory (DSMEM) -- every sector is read once, by one CTA;
+//   FFT      rank r transforms its sub-line E_r = FFT_m(z[2i + r]) in registers;
+//   stores   both E_r are left in shared memory; rank c combines (Z[k] = E_0 + w^k E_1, Z[k+m] = E_0 - w^k E_1) and
+//            untangles the orbits {k, m-k, m+k, n-k} with k in [c m/4, (c+1) m/4) (+ m/4 itself and the three real
+//            entries 0, m, n), reading the peer's E over DSMEM, and writes four contiguous runs of the half spectrum.
+// Optional forward slab transpose on the stores (SlabScatter).
+template <int N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RegGeom<N>::NT, RegGeom<N>::MINB)
+k_r2c_rows_pair(const cplx* __restrict__ tw, const cplx* __restrict__ twn, const cplx* __restrict__ half_tw,
+                const cplx* __restrict__ in, cplx* __restrict__ out, int64_t in_pitch, int64_t out_pitch, int64_t in_nz,
+                const SlabScatter sc) {
+    // in: packed rows (in_pitch in complex units); in_nz: packed entries j >= in_nz are zero and are not read
+    using G = RegGeom<N>;
+    using K = RegCfg<N>;
+    static_assert(G::L == 1 && G::EPT == 16, "pair kernel: one line per CTA");
+    constexpr int RL = G::RLAST;
+    constexpr int m = N, n = 2 * N;
+    extern __shared__ cplx smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int c = (int)cluster.block_rank();
+    const int jt = threadIdx.x;
+    const int64_t row = blockIdx.x >> 1;
+    cplx* line = smem;
+    cplx* peer = cluster.map_shared_rank(line, c ^ 1);
+    cluster.sync();                                    // the peer CTA is running: its shared memory may be written
+    const cplx* src = in + row * in_pitch;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int j = c * m + jt + q * G::NT;          // packed index, contiguous across the CTA
+        const cplx z = (j < in_nz) ? src[j] : make_double2(0.0, 0.0);
+        cplx* dst = ((j & 1) == c) ? line : peer;
+        dst[j >> 1] = z;
+    }
+    cluster.sync();
+    cplx v[G::EPT];
+#pragma unroll
+    for (int s = 0; s < G::EPT; ++s) v[s] = line[reg_elem<N, K::R0>(jt, s)];
+    reg_fft<N, -1, true>(v, line, jt, tw);
+    __syncthreads();                                   // the last exchange has been read
+#pragma unroll
+    for (int s = 0; s < G::EPT; ++s) line[reg_elem<N, RL>(jt, s)] = v[s];
+    cluster.sync();
+    const cplx* E0 = c ? peer : line;
+    const cplx* E1 = c ? line : peer;
+    cplx* o = out + row * out_pitch;
+    auto X = [&](cplx za, cplx zb, int kk) {           // half-spectrum entry kk from Z[kk], Z[n - kk]
+        const cplx zc = cconj(zb);
+        const cplx E = cscale(cadd(za, zc), 0.5);
+        const cplx O = cmulni(cscale(csub(za, zc), 0.5));
+        return cadd(E, cmul(half_tw[kk], O));
+    };
+    auto put = [&](int kk, cplx val) {
+        if (sc.R) *slab_fwd_addr(sc, row, kk) = val; else o[kk] = val;
+    };
+    // orbits k in [c m/4, (c+1) m/4); rank 1 also takes k = m/2 (the orbit {m/2, 3m/2})
+    for (int t = jt; t < m / 4 + c; t += G::NT) {
+        const int k = c * (m / 4) + t;
+        const int km = (k == 0) ? 0 : m - k;
+        const cplx e0k = E0[k], e1k = E1[k], e0m = E0[km], e1m = E1[km];
+        const cplx tk = cmul(twn[k], e1k);
+        const cplx wm = (k == 0) ? make_double2(1.0, 0.0) : make_double2(-twn[k].x, twn[k].y);     // w_n^{m-k}
+        const cplx tm = cmul(wm, e1m);
+        const cplx Zk = cadd(e0k, tk), Zkm = csub(e0k, tk);       // Z[k], Z[k + m]
+        const cplx Zmk = cadd(e0m, tm), Znk = csub(e0m, tm);      // Z[m - k], Z[n - k]   (k = 0: Z[0], Z[m])
+        if (k == 0) {
+            put(0, X(Zk, Zk, 0));
+            put(n, X(Zk, Zk, n));
+            put(m, X(Zkm, Zkm, m));
+        } else {
+            put(k, X(Zk, Znk, k));
+            put(n - k, X(Znk, Zk, n - k));
+            put(m - k, X(Zmk, Zkm, m - k));
+            put(m + k, X(Zkm, Zmk, m + k));                      // 2k == m: the same two entries, the same values
+        }
+    }
+    cluster.sync();                                    // the peer may still be reading this CTA's shared memory
+}
+template <int N>
+static int launch_r2c_pair(FftPlan* p, const double* in, cplx* out, int64_t batch, int64_t in_pitch, int64_t out_pitch,
+                           int64_t in_nz, const SlabScatter& sc, cudaStream_t st) {
+    using G = RegGeom<N>;
+    int rc = set_smem(k_r2c_rows_pair<N>, G::SMEM);
+    if (rc) return rc;
+    for (int64_t r0 = 0; r0 < batch; r0 += (1 << 29)) {
+        const int64_t nb = std::min<int64_t>(batch - r0, 1 << 29);
+        SlabScatter s2 = sc;
+        s2.row0 += r0;
+        k_r2c_rows_pair<N><<<(unsigned)(2 * nb), G::NT, G::SMEM, st>>>(p->half->d.tw, p->d.tw, p->half_tw_dev,
+                                                                      reinterpret_cast<const cplx*>(in) + r0 * (in_pitch / 2),
+                                                                      out + r0 * out_pitch, in_pitch / 2, out_pitch, in_nz, s2);
+        KERNEL_CHECK();
+    }
+    return IPDE_OK;
+}
+// Measured (scripts/bench_rows.py, 16384^2 solve): the fused pair kernel is 5-14 % SLOWER than sub-transforms + untangle
+// pass (r2c of 16384 rows x 16384 reals 2.26 vs 1.98 ms; 5.8 vs 5.2 ms inside the solve) -- the 8192-point CTA is bound by
+// its own latency (one CTA per SM), and the two extra trips through shared memory cost more than the saved pass.  Kept
+// as an option (IPDE_FFT_PAIR=1); the default is the two-kernel path.
+static const bool g_fft_pair = []() { const char* e = getenv("IPDE_FFT_PAIR"); return e && e[0] == '1'; }();
+
 // Global-memory versions of the pack / unpack steps for long rows
 __global__ void k_r2c_untangle(int n, const cplx* __restrict__ half_tw, const cplx* __restrict__ z, cplx* __restrict__ out,
                                int64_t batch, int64_t z_pitch, int64_t out_pitch) {
@@ -1475,6 +1578,10 @@ int fft_r2c_rows_nz(FftPlan* p, const double* in, cplx* out, int64_t batch, int6
         if (rc) return rc;
         const int m = n / 2;
         KERNEL_TAG("k_r2c_rows_long", (8.0 * std::min<int64_t>(2 * (int64_t)n, in_nz) + 16.0 * (n + 1)) * (double)batch);
+        if (g_fft_pair && in_pitch % 2 == 0) {
+            if (m == 4096) return launch_r2c_pair<4096>(p, in, out, batch, in_pitch, out_pitch, (in_nz + 1) / 2, slab_scatter_none(), st);
+            return launch_r2c_pair<8192>(p, in, out, batch, in_pitch, out_pitch, (in_nz + 1) / 2, slab_scatter_none(), st);
+        }
         // packed row z[j] = (x[2j], x[2j+1]); sub-line r = z[2i + r]: element stride 2, offset r; reals beyond in_nz
         // are zero (zero-padded rows of the evaluator box) and are not read
         rc = rows_reg_sub(p, reinterpret_cast<const cplx*>(in), out, 2 * batch, in_pitch / 2, 1, 2, out_pitch, m, 1, -1, 1.0, st,
@@ -1527,6 +1634,10 @@ int fft_r2c_rows_scatter(FftPlan* p, const double* in, cplx* scratch, int64_t ba
         if (rc) return rc;
         const int m = n / 2;
         KERNEL_TAG("k_r2c_rows_long", (16.0 * n + 16.0 * n) * (double)batch);
+        if (g_fft_pair && in_pitch % 2 == 0) {
+            if (m == 4096) return launch_r2c_pair<4096>(p, in, scratch, batch, in_pitch, scratch_pitch, n, sc, st);
+            return launch_r2c_pair<8192>(p, in, scratch, batch, in_pitch, scratch_pitch, n, sc, st);
+        }
         rc = rows_reg_sub(p, reinterpret_cast<const cplx*>(in), scratch, 2 * batch, in_pitch / 2, 1, 2, scratch_pitch, m, 1, -1, 1.0,
                           st, nullptr, 0, n);
         if (rc) return rc;
