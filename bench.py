@@ -21,8 +21,10 @@ grid-point-solves/s.
           not installable)
   N > 1   `value`: every rank solves its own forcing on its own copy of the problem -- independent solves are the
           unit of this path that shards without a data-path collective ("scaling": "weak"; replicas, not one problem).
-          `slab_grid_solve`: ONE 16384^2 periodic grid solve slab-decomposed over all ranks (NCCL all-to-all
-          transposes; strong scaling of the FFT core) with its error against the single-GPU solve.
+          `slab_grid_solve`: ONE 16384^2 periodic grid solve slab-decomposed over all ranks (strong scaling of the
+          FFT core): the transposes fused into the stores of the transform kernels over CUDA-IPC peer mappings
+          (SlabGridSolverP2P), with pack + NCCL all-to-all + unpack as the comparison, and the error of both against
+          the single-GPU solve.
 """
 import argparse
 import json
@@ -523,7 +525,7 @@ def _main():
                         'h2d_bytes_per_step': int(f_host.nbytes), 'd2h_bytes_per_step': int(np.asarray(ue).nbytes),
                         'ms_per_step': e2e_ms, 'steps': e2e_steps,
                         'api': 'ModifiedHelmholtzSolver.__call__(EmbeddedFunction, out=EmbeddedFunction) -> EmbeddedFunction: '
-                               'host arrays in and out through pinned staging buffers, result array reused across steps'},
+                               'page-locked EmbeddedFunctions copied straight to / from the device (no staging copy), result array reused across steps'},
                 'roofline': roofline}
         if slab is not None:
             line['slab_grid_solve'] = slab

@@ -2,9 +2,11 @@
 Homogeneous (boundary-condition) correction -- the step every caller of the reference performs right after the
 inhomogeneous solve:
 
-    examples/interior_modified_helmholtz.py:73-86       single boundary, Dirichlet
-    examples/multi_modified_helmholtz.py:113-177        boundary collection, Dirichlet
-    examples/poisson_for_paper.py:88-105                Poisson, Dirichlet
+    examples/interior_modified_helmholtz.py:73-86       single boundary, Dirichlet        DirichletCorrection
+    examples/multi_modified_helmholtz.py:113-177        boundary collection, Dirichlet    DirichletCorrection
+    examples/poisson_for_paper.py:88-105                Poisson, Dirichlet                DirichletCorrection
+    examples/multi_modified_helmholtz_neumann.py:97-163 boundary collection, Neumann      NeumannCorrection
+    examples/interior_stokes_with_multi.py:98-125       Stokes, prescribed velocity       StokesDirichletCorrection
 
 The reference solves a dense second-kind integral equation for a double-layer density on all boundaries (pybie2d
 self-quadratures + numpy.linalg.solve), turns it into effective sources with QFS and sums them onto
