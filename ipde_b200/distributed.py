@@ -229,6 +229,59 @@ class SlabGridSolver(object):
         return out
 
 
+def p2p_columns_per_rank(P, world, next_size=lambda n: n):
+    """columns per rank of SlabGridSolverP2P: ceil(P / world), with Pc - 1 rounded up to a supported FFT length (the
+    column plan is a grid plan of width 2 (Pc - 1)); world * Pc >= P always"""
+    Pc = max(3, -(-P//world))
+    return next_size(max(2, Pc - 1)) + 1
+
+
+def p2p_forward_address(row0, l, k, Pc):
+    """entry (local row l, column k) of the row spectra of the rank owning rows row0... -> (destination rank, offset in
+    its column slab (nx, Pc)); csrc/fft.cuh:slab_fwd_addr"""
+    q = k//Pc
+    return q, (row0 + l)*Pc + (k - q*Pc)
+
+
+def p2p_backward_address(i, c, rows, P, col0):
+    """entry (global row i, local column c) of the rank owning columns col0... -> (destination rank, offset in its row
+    slab (rows, P)); only columns col0 + c < P are stored; csrc/fft.cuh:slab_bwd_addr"""
+    q = i//rows
+    return q, (i - q*rows)*P + col0 + c
+
+
+def slab_p2p_solve_virtual(nx, ny, world, f, symbol, next_size=lambda n: n):
+    """NumPy statement of SlabGridSolverP2P with all ranks played by one process: the two transposes are the scattered
+    stores of the address functions above, nothing else moves data.  Returns the full (nx, ny) result."""
+    P = ny//2 + 1
+    rows = nx//world
+    Pc = p2p_columns_per_rank(P, world, next_size)
+    cols = [np.zeros(nx*Pc, dtype=complex) for _ in range(world)]
+    back = [np.zeros(rows*P, dtype=complex) for _ in range(world)]
+    kk = np.arange(P)
+    for r in range(world):
+        spec = np.fft.rfft(f[r*rows:(r + 1)*rows], axis=1)
+        for l in range(rows):
+            q, off = p2p_forward_address(r*rows, l, kk, Pc)
+            for dest in range(world):
+                m = q == dest
+                cols[dest][off[m]] = spec[l, m]
+    ii = np.arange(nx)
+    for r in range(world):
+        slab = cols[r].reshape(nx, Pc)
+        j = r*Pc + np.arange(Pc)
+        valid = j < P
+        mult = np.zeros((nx, Pc))
+        mult[:, valid] = symbol(ii[:, None], j[valid][None, :])
+        res = np.fft.ifft(np.fft.fft(slab, axis=0)*mult, axis=0)
+        for c in np.flatnonzero(valid):
+            q, off = p2p_backward_address(ii, c, rows, P, r*Pc)
+            for dest in range(world):
+                m = q == dest
+                back[dest][off[m]] = res[m, c]
+    return np.concatenate([np.fft.irfft(b.reshape(rows, P), n=ny, axis=1) for b in back], axis=0)
+
+
 class SlabGridSolverP2P(object):
     """
     The slab solve with both transposes FUSED INTO THE TRANSFORM KERNELS: no pack, no all-to-all, no unpack.
@@ -262,7 +315,7 @@ class SlabGridSolverP2P(object):
         self.L = Ls = SlabLayout(nx, ny, world, rank)
         L_ = lib()
         # the column plan is a grid plan of width 2 (Pc - 1): round Pc - 1 up to a supported length (zero columns)
-        Ls.Pc = L_.ipde_fft_next_size(max(2, Ls.Pc - 1)) + 1
+        Ls.Pc = p2p_columns_per_rank(Ls.P, world, L_.ipde_fft_next_size)
         Ls.col0 = rank*Ls.Pc
         self.nx, self.ny, self.xh, self.yh, self.kind, self.k = nx, ny, float(xh), float(yh), int(kind), float(k)
         self.row_plan = ctypes.c_void_p()

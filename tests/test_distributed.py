@@ -6,7 +6,7 @@ import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
-from ipde_b200.distributed import SlabLayout, slab_grid_solve_numpy
+from ipde_b200.distributed import SlabLayout, slab_grid_solve_numpy, slab_p2p_solve_virtual, p2p_columns_per_rank
 
 
 def _reference(f, xh, yh, k):
@@ -68,6 +68,25 @@ def test_slab_pack_unpack_roundtrip():
             for c in range(K):
                 Lc.unpack_chunk(Lc.pack_chunk(s, c*Pk, Pk), c*Pk, Pk, back)
             assert np.array_equal(back, s)
+
+
+@pytest.mark.parametrize('world,nx,ny', [(2, 16, 12), (4, 32, 50), (8, 64, 30), (3, 24, 16), (8, 8, 64)])
+def test_slab_p2p_addresses_numpy(world, nx, ny):
+    """host statement of the fused transposes (the address functions the CUDA stores implement, csrc/fft.cuh) for all
+    ranks in one process: every spectrum entry lands exactly once, the result is the unsharded solve"""
+    rng = np.random.default_rng(world*nx + ny)
+    f = rng.standard_normal((nx, ny))
+    xh, yh, k = 2.4/nx, 3.1/ny, 2.0
+    def symbol(i, j):
+        kx = np.fft.fftfreq(nx, xh/(2*np.pi))[i]
+        ky = 2*np.pi*j/(ny*yh)
+        return 1.0/(k*k + kx*kx + ky*ky)
+    round8 = lambda n: -(-n//8)*8          # any rounding of the column width must leave the result unchanged
+    for nxt in (lambda n: n, round8):
+        assert world*p2p_columns_per_rank(ny//2 + 1, world, nxt) >= ny//2 + 1
+        u = slab_p2p_solve_virtual(nx, ny, world, f, symbol, nxt)
+        ref = _reference(f, xh, yh, k)
+        assert np.abs(u - ref).max()/np.abs(ref).max() < 1e-13
 
 
 @pytest.mark.gpu

@@ -151,6 +151,48 @@ def test_oracle_neumann_correction_reproduces_manufactured_solution():
     assert err < 2e-6, err
 
 
+def test_oracle_stokes_reproduces_published_errors():
+    """examples/interior_stokes_with_multi.py at its published resolution nb = 300 (errs_U 6.65e-07, errs_p 6.57e-05,
+    :31-32) on the CPU: oracle Stokes solve + the homogeneous velocity correction (:98-118) + pressure normalisation
+    (:120-125).  The pressure figure needs the continuity step of OracleVectorHelper.correct: without it the annulus
+    is off by 7.5e-02."""
+    from problems import stokes_manufactured
+    from ipde_b200.geometry import GSB, Grid, star, arc_length_parameterize
+    from ipde_b200.embedded_boundary import EmbeddedBoundary
+    from ipde_b200.ebdy_collection import EmbeddedBoundaryCollection
+    from ipde_b200.embedded_function import EmbeddedFunction
+    from ipde_b200.slepian import SlepianMollifier
+    from ipde_b200.qfs import Stokes_QFS
+    from oracle.solvers import OracleVectorSolver, layer_apply_stokes
+    nb, M = 300, 12
+    bdy = GSB(c=star(nb, a=0.1, f=5))
+    bdy = GSB(*arc_length_parameterize(bdy.x, bdy.y))
+    Lb = np.pi/2
+    grid = Grid([-Lb, Lb], nb//2, [-Lb, Lb], nb//2)
+    MOL = SlepianMollifier(int(1.5*M))
+    ebdy = EmbeddedBoundary(bdy, True, M, grid.xh*0.75, heaviside=MOL.step)
+    ebdyc = EmbeddedBoundaryCollection([ebdy])
+    ebdyc.register_grid(grid)
+    ebdyc.ready_bump(MOL.bump, (Lb - ebdy.radial_width, Lb - ebdy.radial_width), ebdy.radial_width)
+    fu, fv, ua, va, pa, (u_f, v_f, p_f) = stokes_manufactured(ebdyc)
+    pair = (Stokes_QFS(ebdy.interface, True, True, True, tol=1e-13, u2s=False, device_build=False),
+            Stokes_QFS(ebdy.interface, False, True, True, tol=1e-13, device_build=False))
+    O = OracleVectorSolver(ebdyc, 'spectral', [pair])
+    E = lambda a: EmbeddedFunction(ebdyc, linear_data=np.asarray(a))
+    u, v, p = [E(a) for a in O(fu, fv, tol=1e-14, restart=50, maxiter=4)]
+    h = O.helpers[0]
+    qb = Stokes_QFS(bdy, True, True, True, tol=1e-13, device_build=False)
+    g = np.concatenate([u_f(bdy.x, bdy.y) - h._bv.dot(u[0]), v_f(bdy.x, bdy.y) - h._bv.dot(v[0])])
+    sig = qb.u2s(g).reshape(2, -1)*qb.source.weights
+    pts = ebdyc.grid_and_radial_pts
+    cu, cv, cp = layer_apply_stokes(qb.source.x, qb.source.y, sig[0], sig[1], pts.x, pts.y)
+    area = EmbeddedFunction(ebdyc, function=lambda x, y: np.ones_like(x)).integrate()
+    pt = E(np.asarray(p) + cp)
+    eP = np.abs((np.asarray(pt) - pt.integrate()/area) - (np.asarray(pa) - pa.integrate()/area)).max()
+    eU = max(np.abs(np.asarray(u) + cu - np.asarray(ua)).max(), np.abs(np.asarray(v) + cv - np.asarray(va)).max())
+    assert eU < 1.5*6.65e-07 and eP < 1.5*6.57e-05, (eU, eP)          # measured 6.61e-07 / 6.48e-05
+
+
 @pytest.mark.parametrize('kind,kappa,N', [(0, 0.0, 96), (1, 2.0, 96), (1, 20.0, 64)])
 def test_numpy_spectral_ewald_matches_direct_sum(kind, kappa, N):
     """host tables and mathematics of the free-space evaluator (ipde_b200/ewald.py) on the CPU: truncated kernel,
