@@ -291,8 +291,9 @@ def test_stokes_ewald_backend(problem):
     # Pressure.  With several boundaries `correct()` sends the others' velocity on the interface through u2s
     # (ipde/solvers/internals/vector.py:134-162, where the reference itself notes the missing pressure correction):
     # a uniform normal force on the source curve changes no velocity but shifts the pressure of that annulus by a
-    # constant, so this constant is fixed by round-off alone.  Compare the pressure where it is determined (grid
-    # points outside the annuli) strictly, and every annulus up to its additive constant.
+    # constant, so this constant used to be fixed by round-off alone; the pressure-continuity step (device and oracle)
+    # now determines it.  Compare the pressure on the grid points outside the annuli strictly, every annulus up to
+    # its additive constant at the same level, and the constant itself to 1e-10.
     dp = np.asarray(p) - po
     ps = np.abs(po).max()
     pna = ebdyc.phys_inds[ebdyc.phys_not_in_annulus]
