@@ -26,7 +26,7 @@ for nr in [int(a) for a in sys.argv[1:]] or [4096, 8192, 16384, 32768]:
     out = torch.empty_like(f)
     st = D.stream(); L = lib()
     t_f = timeit(lambda: L.ipde_fft_r2c_rows(p.h, D.ptr(f), D.ptr(spec), batch, nr, pitch, st), reps)
-    t_i = timeit(lambda: L.ipde_fft_c2r_rows(p.h, D.ptr(spec), D.ptr(out), batch, pitch, nr, 1.0/nr, st), reps)
+    t_i = timeit(lambda: L.ipde_fft_c2r_rows(p.h, D.ptr(spec), D.ptr(out), batch, pitch, nr, 2.0/nr, st), reps)
     err = float((out - f).abs().max())
     b = batch*(nr*8 + pitch*16)
     line = 'rows nr=%6d batch %6d: r2c %.3f ms %5.0f GB/s | c2r %.3f ms %5.0f GB/s | roundtrip err %.1e' % (
