@@ -17,10 +17,94 @@ are executed by the CUDA library (ipde_b200/device.py).
 """
 import numpy as np
 from .geometry import PointSet, LazyPointSet, Grid
-from .near import points_inside_curve
+from .near import points_inside_curve, CurveTaylor, compute_local_coordinates
 from .embedded_boundary import EmbeddedBoundary, LoadEmbeddedBoundary
 from .embedded_function import EmbeddedFunction, BoundaryFunction
 from .utilities import affine_transformation
+
+
+class EmbeddedPointPartition(object):
+    """
+    Unstructured points (x, y) sorted by where an EmbeddedFunction is to be read there
+    (API mirror of ipde/ebdy_collection.py:37-229):
+
+        zone 1   not in any annulus and not flagged exterior   -> trigonometric interpolation of the smoothed grid part
+        zone 2   inside the annulus of boundary i (zone2l[i])  -> Chebyshev x Fourier interpolation of radial block i,
+                 with the coordinates (zone2r, zone2_transfr, zone2t)
+        zone 3   within a radial width of boundary i on its non-physical side (zone3l[i])  -> nan
+
+    As in the reference, only points within one radial width of a boundary get coordinates; a point far from every
+    boundary is taken to be physical (zone 1).  Coordinates: closest node of the 2x upsampled curve from a k-d tree
+    as the guess, then the Newton iteration of near.py on the Taylor tables of the trigonometric interpolant --
+    the machinery grid registration uses (replaces near_finder.points_near_curve_coarse + compute_local_coordinates,
+    :109-121).  dzl / gil (danger-zone and guess-index lists, :59-66) are honoured when given.
+    """
+    def __init__(self, ebdyc, x, y, fix_r=False, dzl=None, gil=None):
+        from scipy.spatial import cKDTree
+        self.grid = ebdyc.grid
+        self.x_check, self.y_check, self.fix_r = x, y, fix_r
+        self.dzl, self.gil = dzl, gil
+        self.sh = np.shape(x)
+        self.x = np.asarray(x, dtype=float).ravel()
+        self.y = np.asarray(y, dtype=float).ravel()
+        self.size = n = self.x.size
+        z = self.x + 1j*self.y
+        zone1 = np.ones(n, dtype=bool)
+        zone1_or_2 = np.ones(n, dtype=bool)
+        self.zone2l, self.zone2r, self.zone2_transfr, self.zone2t = [], [], [], []
+        self.zone3l, self.zone3r, self.zone3t = [], [], []
+        self.full_t = np.full(n, np.nan)
+        self.full_r = np.full(n, np.nan)
+        for ind, ebdy in enumerate(ebdyc):
+            ct = CurveTaylor(ebdy.bdy.c)
+            if dzl is not None and gil is not None and dzl[ind] is not None and gil[ind] is not None:
+                near = np.asarray(dzl[ind], dtype=np.int64)
+                guess = 2*np.asarray(gil[ind], dtype=np.int64)          # boundary node -> node of the 2x curve
+            else:
+                nodes = ct.tab[0]
+                tree = cKDTree(np.column_stack([nodes.real, nodes.imag]))
+                # a point within `width` of the curve is within sqrt(width^2 + (1 + kappa width) (hmax/2)^2) of a node
+                hmax = np.abs(np.diff(np.append(nodes, nodes[0]))).max()
+                dist, guess = tree.query(np.column_stack([self.x, self.y]), workers=-1)
+                near = np.flatnonzero(dist <= np.hypot(ebdy.radial_width, 0.75*hmax))
+                guess = guess[near]
+            if near.size == 0:
+                e = np.zeros(0)
+                ei = np.zeros(0, dtype=np.int64)
+                self.zone2l.append(ei); self.zone2r.append(e); self.zone2_transfr.append(e); self.zone2t.append(e)
+                self.zone3l.append(ei); self.zone3r.append(e); self.zone3t.append(e)
+                continue
+            t, r = compute_local_coordinates(ct, z[near], guess, tol=getattr(ebdy, 'coordinate_tolerance', 1e-14))
+            if fix_r:
+                ebdy.fix_r(r)
+            self.full_t[near], self.full_r[near] = t, r
+            inside, phys_beyond, exterior = ebdy.check_if_r_in_annulus(r)
+            zone1[near] &= phys_beyond
+            zone1_or_2[near] &= ~exterior
+            self.zone2l.append(near[inside])
+            self.zone2r.append(r[inside])
+            self.zone2_transfr.append(ebdy.nufft_transform_r(r[inside]))
+            self.zone2t.append(t[inside])
+            self.zone3l.append(near[exterior])
+            self.zone3r.append(r[exterior])
+            self.zone3t.append(t[exterior])
+        self.zone1, self.zone1_or_2 = zone1, zone1_or_2
+        self.zone1_N = int(zone1.sum())
+        self.zone2_Ns = [len(a) for a in self.zone2l]
+        self.zone3_Ns = [len(a) for a in self.zone3l]
+        self.zone2_N, self.zone3_N = int(np.sum(self.zone2_Ns)), int(np.sum(self.zone3_Ns))
+        g = self.grid
+        self.x_transf = affine_transformation(self.x[zone1], g.x_bounds[0], g.x_bounds[1], 0.0, 2*np.pi)
+        self.y_transf = affine_transformation(self.y[zone1], g.y_bounds[0], g.y_bounds[1], 0.0, 2*np.pi)
+
+    def is_it_i(self, x, y, fix_r):
+        return x is self.x_check and y is self.y_check and fix_r == self.fix_r
+
+    def reshape(self, out):
+        return out.reshape(self.sh)
+
+    def get_Ns(self):
+        return self.zone1_N, self.zone2_N, self.zone3_N
 
 
 def LoadEmbeddedBoundaryCollection(d):
@@ -251,6 +335,47 @@ class EmbeddedBoundaryCollection(object):
         return [ebdy.interpolate_radial_to_grid1(fr, f) for ebdy, fr in zip(self.ebdys, fr_list)]
     def update_radial_to_grid1(self, f):
         _ = self.interpolate_radial_to_grid1(f.get_radial_value_list(), f['grid'])
+
+    ############################################################################
+    # EmbeddedFunction -> unstructured points (ipde/ebdy_collection.py:651-707)
+    def get_interpolation_key(self, x, y, fix_r=False, dzl=None, gil=None):
+        for key, part in enumerate(getattr(self, 'registered_partitions', [])):
+            if part.is_it_i(x, y, fix_r):
+                return key
+        return self.register_points(x, y, fix_r, dzl, gil)
+
+    def register_points(self, x, y, fix_r=False, dzl=None, gil=None):
+        if not hasattr(self, 'registered_partitions'):
+            self.registered_partitions = []
+        self.registered_partitions.append(EmbeddedPointPartition(self, x, y, fix_r, dzl, gil))
+        return len(self.registered_partitions) - 1
+
+    def interpolate_to_points(self, ff, x, y, fix_r=False, dzl=None, gil=None):
+        """
+        Values of the EmbeddedFunction ff at the points (x, y): type-2 NUFFT of the smoothed grid part in zone 1 (the
+        reference's finufft.nufft2d2 call, :687-694), Chebyshev x Fourier interpolation of the radial blocks in the
+        annuli (:695-702), nan on the flagged exterior points (:704-706).  Device kernels: scatter + cutoff, the grid
+        FFT, k_nufft_pad / k_nufft_interp, k_radial_interp.
+        """
+        from .device import to_dev, ptr, stream, Nufft2
+        from ._lib import lib
+        p = self.registered_partitions[self.get_interpolation_key(x, y, fix_r, dzl, gil)]
+        out = np.empty(p.size)
+        if p.zone1_N > 0:
+            D = self.device
+            f_dev = to_dev(np.ascontiguousarray(np.asarray(ff, dtype=float).reshape(-1)))
+            lib().ipde_grid_scatter_cutoff(D.grid.h, ptr(f_dev), ptr(D.phys_lin), ptr(D.step_compact), D.n_phys,
+                                           ptr(D.fc), stream())
+            spec = D.grid.fft2(D.fc)
+            if getattr(p, '_nufft', None) is None or p._nufft.grid is not D.grid:
+                p._nufft = Nufft2(D.grid, p.x_transf, p.y_transf)
+            out[p.zone1] = p._nufft(spec).cpu().numpy()
+        for ind, ebdy in enumerate(self.ebdys):
+            if p.zone2_Ns[ind] > 0:
+                out[p.zone2l[ind]] = ebdy.interpolate_radial_to_points(ff[ind], p.zone2_transfr[ind], p.zone2t[ind])
+        for z3 in p.zone3l:
+            out[z3] = np.nan
+        return out
 
     ############################################################################
     # calculus on EmbeddedFunctions (ipde/ebdy_collection.py:708-792), on the device: ipde_b200/calculus.py

@@ -232,3 +232,51 @@ def test_registration_against_brute_force_closest_point():
         ang = np.angle((np.roll(fine, -1)[None, :] - z[:, None])/(fine[None, :] - z[:, None])).sum(axis=1)/(2*np.pi)
         inside = np.abs(ang) > 0.5
         assert np.array_equal(inside, e.grid_ia_r[sel] < 0)
+
+
+def test_point_partition_against_brute_force():
+    """EmbeddedPointPartition (ipde/ebdy_collection.py:37-229): zones of random points against a brute-force
+    classification (distance to a 64x upsampled polygon + winding number), coordinates against the closest vertex"""
+    from ipde_b200.ebdy_collection import EmbeddedPointPartition
+    ebdyc = three_bodies(nb=80, M=8)
+    g = ebdyc.grid
+    rng = np.random.default_rng(5)
+    n = 3000
+    x = rng.uniform(g.x_bounds[0], g.x_bounds[1], n)
+    y = rng.uniform(g.y_bounds[0], g.y_bounds[1], n)
+    p = EmbeddedPointPartition(ebdyc, x, y)
+    assert p.zone1_N + p.zone2_N + p.zone3_N >= n          # a point may be near two boundaries
+    z = x + 1j*y
+    in_any = np.zeros(n, dtype=bool)
+    flagged = np.zeros(n, dtype=bool)
+    for ind, e in enumerate(ebdyc):
+        fine = fourier_resample(e.bdy.c, 64*e.bdy.N)
+        d = np.abs(z[:, None] - fine[None, :]).min(axis=1)
+        ang = np.angle((np.roll(fine, -1)[None, :] - z[:, None])/(fine[None, :] - z[:, None])).sum(axis=1)/(2*np.pi)
+        inside_curve = np.abs(ang) > 0.5
+        physical_side = inside_curve if e.interior else ~inside_curve
+        w = e.radial_width
+        margin = 1e-3*w                                     # polygon resolution
+        sure_annulus = physical_side & (d < w - margin)
+        sure_exterior = ~physical_side & (d < w - margin) & (d > margin)
+        sure_far = d > w + margin
+        z2 = np.zeros(n, dtype=bool); z2[p.zone2l[ind]] = True
+        z3 = np.zeros(n, dtype=bool); z3[p.zone3l[ind]] = True
+        assert np.all(z2[sure_annulus]) and not np.any(z2[sure_exterior | sure_far])
+        # zone 3: every located point on the non-physical side (the search radius is a little more than the width)
+        assert np.all(z3[sure_exterior]) and not np.any(z3 & physical_side & (d > margin)) and not np.any(z3[d > 2*w])
+        # coordinates: |r| is the distance to the curve, t the parameter of the closest point
+        near = p.zone2l[ind]
+        ra = np.abs(p.zone2r[ind])
+        hmax = np.abs(np.diff(fine)).max()
+        bound = np.minimum(0.5*hmax, (1 + np.abs(e.bdy.curvature).max()*ra)*hmax**2/(8*np.maximum(ra, 1e-300))) + 1e-12
+        assert np.all(d[near] - ra >= -1e-12) and np.all(d[near] - ra <= 1.05*bound)
+        tf = 2*np.pi*np.arange(fine.size)/fine.size
+        j = np.abs(z[near, None] - fine[None, :]).argmin(axis=1)
+        assert np.abs(np.angle(np.exp(1j*(p.zone2t[ind] - tf[j])))).max() < 3*(tf[1] - tf[0])
+        assert np.all((p.zone2_transfr[ind] >= 0) & (p.zone2_transfr[ind] <= np.pi))
+        in_any |= z2
+        flagged |= z2 | z3
+    assert np.array_equal(p.zone1, ~flagged) or np.all(p.zone1[~flagged])
+    assert not np.any(p.zone1 & in_any)
+    assert p.x_transf.size == p.zone1_N and p.x_transf.min() >= 0 and p.x_transf.max() <= 2*np.pi

@@ -244,3 +244,38 @@ def test_fast_oracle_matches_direct_oracle():
     uo = OracleScalarSolver(ebdyc, 'modified_helmholtz', k, 'spectral', pairs)(f, **gm)
     uf = FastScalarSolver(ebdyc, 'modified_helmholtz', k, pairs, workers=2)(f, **gm)
     assert np.abs(uf - uo).max() < 1e-12*np.abs(uo).max()
+
+
+def test_interpolate_to_points_numpy_statement():
+    """ebdyc.register_points + the reference's interpolation formulas (ipde/ebdy_collection.py:666-707) in NumPy: NUDFT
+    of the smoothed grid part in zone 1, Chebyshev x Fourier interpolation in the annuli -- pins the partition, the
+    affine maps and the accuracy the device path (tests/test_gpu_solvers.py::test_interpolate_to_points) is held to"""
+    from problems import three_bodies
+    from ipde_b200.embedded_function import EmbeddedFunction
+    from ipde_b200.geometry import fourier_resample
+    from oracle.solvers import nudft2d_type2, interpolate_radial_to_points
+    ebdyc = three_bodies(nb=200, M=12)
+    kk = 4*np.pi/7
+    sol = lambda x, y: np.exp(np.sin(kk*x))*np.sin(kk*y)
+    ff = EmbeddedFunction(ebdyc, function=sol)
+    g = ebdyc.grid
+    rng = np.random.default_rng(9)
+    n = 1500
+    x = rng.uniform(g.x_bounds[0], g.x_bounds[1], n)
+    y = rng.uniform(g.y_bounds[0], g.y_bounds[1], n)
+    p = ebdyc.registered_partitions[ebdyc.register_points(x, y)]
+    out = np.full(n, np.nan)
+    out[p.zone1] = nudft2d_type2(np.fft.fft2(ff.get_smoothed_grid_value())[None], p.x_transf, p.y_transf)[0].real
+    for ind in range(len(ebdyc)):
+        out[p.zone2l[ind]] = interpolate_radial_to_points(ff[ind], p.zone2_transfr[ind], p.zone2t[ind])
+    ex = sol(x, y)
+    z = x + 1j*y
+    phys = np.ones(n, dtype=bool)
+    for e in ebdyc:
+        fine = fourier_resample(e.bdy.c, 8*e.bdy.N)
+        ang = np.angle((np.roll(fine, -1)[None, :] - z[:, None])/(fine[None, :] - z[:, None])).sum(axis=1)/(2*np.pi)
+        phys &= (np.abs(ang) > 0.5) if e.interior else (np.abs(ang) <= 0.5)
+    z1, z2 = p.zone1 & phys, np.concatenate(p.zone2l)
+    assert z1.sum() > 300 and z2.size > 100
+    assert np.abs(out[z1] - ex[z1]).max() < 2e-8           # roll-off of the cutoff on the 480^2 grid: 4e-09
+    assert np.abs(out[z2] - ex[z2]).max() < 1e-12
