@@ -184,25 +184,33 @@ def run_reference(args, rank, world):
 
 # ---------------------------------------------------------------------------------------------------------------------
 def ncu_traffic(kernel):
-    """dram read+write bytes per launch of `kernel` from the committed ncu --set full summary (profiles/), or None"""
+    """(dram read+write bytes per captured launch, description) of `kernel` from the committed ncu --set full summary
+    (profiles/), or (None, None).  The capture holds some of the kernel's launches of one solve; when its records carry
+    their own algorithmic bytes the description states them, so that traffic is compared with the bytes of the SAME
+    launches (the roofline's algorithmic_bytes_per_launch is the mean over all launches of the step)."""
     for rnd in ('r02', 'r01'):
         path = os.path.join(ROOT, 'profiles', '%s_ncu_%s.json' % (rnd, kernel))
         try:
             recs = json.load(open(path))
         except Exception:
             continue
-        tot = []
+        tot, alg = [], []
         for r in recs:
             try:
                 def val(key):
                     v, u = r[key].split()[:2]
                     return float(v)*{'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[u]
                 tot.append(val('dram__bytes_read.sum') + val('dram__bytes_write.sum'))
+                if 'algorithmic_bytes' in r:
+                    alg.append(float(r['algorithmic_bytes']))
             except Exception:
                 pass
         if tot:
-            return float(np.mean(tot))
-    return None
+            note = '%d launch(es) captured by ncu --set full (profiles/%s_ncu_%s.json)' % (len(tot), rnd, kernel)
+            if len(alg) == len(tot):
+                note += '; algorithmic bytes of the captured launches: %.4g per launch' % float(np.mean(alg))
+            return float(np.mean(tot)), note
+    return None, None
 
 
 def parse_profile(text):
@@ -497,7 +505,8 @@ def _main():
         achieved = dom['bytes']/(dom['ms']*1e-3)/1e9
         alg = sum(ALG_BYTES.values())
         roofline = {'bound': 'hbm', 'kernel': dom['kernel'], 'achieved': achieved, 'peak': peak,
-                    'peak_source': peak_kind, 'unit': 'GB/s', 'frac': achieved/peak, 'traffic': ncu_traffic(dom['kernel']),
+                    'peak_source': peak_kind, 'unit': 'GB/s', 'frac': achieved/peak, 'traffic': ncu_traffic(dom['kernel'])[0],
+                    'traffic_of': ncu_traffic(dom['kernel'])[1],
                     'algorithmic_bytes_per_launch': dom['bytes']/dom['launches'],
                     'ms_per_launch': dom['ms']/dom['launches'], 'launches_per_step': dom['launches']/prof_steps,
                     'share_of_step': dom['ms']/prof_ms,
