@@ -280,3 +280,74 @@ def test_point_partition_against_brute_force():
     assert np.array_equal(p.zone1, ~flagged) or np.all(p.zone1[~flagged])
     assert not np.any(p.zone1 & in_any)
     assert p.x_transf.size == p.zone1_N and p.x_transf.min() >= 0 and p.x_transf.max() <= 2*np.pi
+
+
+@pytest.mark.parametrize('kind', ['laplace', 'modified_helmholtz'])
+@pytest.mark.parametrize('interior', [True, False])
+def test_qfs_against_layer_potential_quadrature(kind, interior):
+    """QFS (the restatement of the absent `qfs` package) independently of Green's formula: for arbitrary smooth
+    densities the effective sources reproduce the single + double layer potential of the boundary at test points well
+    away from it, where the periodic trapezoid rule on a 4x upsampled curve is spectrally accurate"""
+    import scipy.special as ss
+    k = 2.5
+    bdy = GSB(c=star(240, a=0.12, f=4))
+    t = bdy.t
+    sigma = np.exp(np.cos(t))*np.sin(2*t) + 0.3
+    mu = np.cos(3*t + 0.4) - 0.5*np.sin(t)
+    if kind == 'laplace':
+        q = Q.Laplace_QFS(bdy, interior, True, True, tol=1e-13)
+    else:
+        q = Q.Modified_Helmholtz_QFS(bdy, interior, True, True, k, tol=1e-13)
+    src = q([sigma, mu])
+    tt = np.linspace(0, 2*np.pi, 41, endpoint=False)
+    z = (0.45 if interior else 1.9)*np.exp(1j*tt)*(1 + 0.1*np.cos(2*tt))
+    val = Q.layer_apply_matrix_free(q.kernel, q.source, z.real, z.imag, src)
+    # quadrature of the layer potentials on the upsampled curve
+    up = 4
+    fine = GSB(c=fourier_resample(bdy.c, up*bdy.N))
+    sf, mf = fourier_resample(sigma, up*bdy.N).real, fourier_resample(mu, up*bdy.N).real
+    dx, dy = z.real[:, None] - fine.x[None, :], z.imag[:, None] - fine.y[None, :]
+    r = np.hypot(dx, dy)
+    dn = dx*fine.normal_x[None, :] + dy*fine.normal_y[None, :]          # (x - y) . n_y
+    if kind == 'laplace':
+        S = -np.log(r)/(2*np.pi)
+        Dk = dn/(2*np.pi*r*r)
+    else:
+        S = ss.k0(k*r)/(2*np.pi)
+        Dk = k*ss.k1(k*r)*dn/r/(2*np.pi)
+    ref = (S*(sf*fine.weights)[None, :]).sum(axis=1) + (Dk*(mf*fine.weights)[None, :]).sum(axis=1)
+    assert np.abs(val - ref).max() < 2e-12*max(1.0, np.abs(ref).max()), np.abs(val - ref).max()
+
+
+@pytest.mark.parametrize('interior', [True, False])
+def test_stokes_qfs_against_layer_potential_quadrature(interior):
+    """the same for the Stokes QFS: stokeslet + stresslet layer potentials of arbitrary smooth vector densities (with
+    a net normal component: its single layer carries no velocity and is the direction the density -> source map drops)
+    against the trapezoid rule on the upsampled curve, velocity at far test points"""
+    bdy = GSB(c=star(240, a=0.12, f=4))
+    t = bdy.t
+    sig = np.concatenate([np.exp(np.cos(t))*np.sin(2*t) + 0.3 + 0.7*bdy.normal_x, np.cos(t - 0.2) + 0.7*bdy.normal_y])
+    mu = np.concatenate([np.cos(3*t + 0.4), 0.5*np.sin(2*t) + 0.1])
+    # the double-layer density must carry no net flux: the velocity jumps across the curve by mu, so outside the flux is
+    # int mu.n ds, which stokeslets inside the body cannot produce (in the solver mu is the jump of two divergence-free
+    # fields and has none)
+    n = bdy.N
+    flux = np.sum((mu[:n]*bdy.normal_x + mu[n:]*bdy.normal_y)*bdy.weights)/np.sum(bdy.weights)
+    mu = mu - flux*np.concatenate([bdy.normal_x, bdy.normal_y])
+    q = Q.Stokes_QFS(bdy, interior, True, True, tol=1e-13)
+    src = q([sig, mu]).reshape(2, -1)
+    tt = np.linspace(0, 2*np.pi, 41, endpoint=False)
+    z = (0.45 if interior else 1.9)*np.exp(1j*tt)*(1 + 0.1*np.cos(2*tt))
+    K = q.kernel
+    w2 = np.tile(q.source.weights, 2)
+    val = K.slp(z.real, z.imag, q.source.x, q.source.y).dot(src.ravel()*w2)
+    up = 4
+    n = bdy.N
+    fine = GSB(c=fourier_resample(bdy.c, up*n))
+    rs = lambda a: fourier_resample(a, up*n).real
+    sf = np.concatenate([rs(sig[:n]), rs(sig[n:])])
+    mf = np.concatenate([rs(mu[:n]), rs(mu[n:])])
+    wf = np.tile(fine.weights, 2)
+    ref = K.slp(z.real, z.imag, fine.x, fine.y).dot(sf*wf) + \
+        K.dlp(z.real, z.imag, fine.x, fine.y, fine.normal_x, fine.normal_y).dot(mf*wf)
+    assert np.abs(val - ref).max() < 5e-12*max(1.0, np.abs(ref).max()), np.abs(val - ref).max()
