@@ -279,3 +279,39 @@ def test_interpolate_to_points_numpy_statement():
     assert z1.sum() > 300 and z2.size > 100
     assert np.abs(out[z1] - ex[z1]).max() < 2e-8           # roll-off of the cutoff on the 480^2 grid: 4e-09
     assert np.abs(out[z2] - ex[z2]).max() < 1e-12
+
+
+def test_cubic_interpolation_statement_properties():
+    """oracle statement of fast_interp.interp2d(k=3, periodic) (absent package; ipde/ebdy_collection.py:594-603): the
+    centred four-node Lagrange stencil is the only placement that (i) returns nodal values at the nodes, (ii) is exact
+    for tensor cubics wherever the stencil does not wrap, (iii) is symmetric about the cell (mirrored data gives mirrored
+    values) and (iv) converges at fourth order on a periodic function"""
+    from oracle.solvers import lagrange_interp2d_periodic
+    rng = np.random.default_rng(4)
+    N = 40
+    h = 2.0/N
+    xv = -1.0 + h*np.arange(N)
+    f = rng.standard_normal((N, N))
+    ii, jj = rng.integers(0, N, 50), rng.integers(0, N, 50)
+    v = lagrange_interp2d_periodic(f, -1.0, -1.0, h, h, xv[ii], xv[jj], 3)
+    assert np.abs(v - f[ii, jj]).max() < 1e-13
+    poly = lambda x, y: (1 + x - 0.5*x**2 + 2*x**3)*(2 - y + y**2 - 0.3*y**3)
+    P = poly(xv[:, None], xv[None, :])
+    px, py = rng.uniform(-0.8, 0.7, 200), rng.uniform(-0.8, 0.7, 200)
+    assert np.abs(lagrange_interp2d_periodic(P, -1.0, -1.0, h, h, px, py, 3) - poly(px, py)).max() < 1e-12
+    # mirror symmetry: x -> -x about a cell centre maps the stencil onto itself
+    px2 = rng.uniform(-0.5, 0.5, 100)
+    a = lagrange_interp2d_periodic(f, -1.0, -1.0, h, h, px2, py[:100], 3)
+    fm = f[::-1]                                  # node i <-> node N-1-i : x -> -x - h + ... (grid reflected)
+    xm = (xv[0] + xv[-1]) - px2
+    b = lagrange_interp2d_periodic(fm, -1.0, -1.0, h, h, xm, py[:100], 3)
+    assert np.abs(a - b).max() < 1e-12
+    errs = []
+    for n in (32, 64, 128):
+        hh = 2.0/n
+        g = -1.0 + hh*np.arange(n)
+        F = np.exp(np.sin(np.pi*g))[:, None]*np.cos(np.pi*g)[None, :]
+        q = lagrange_interp2d_periodic(F, -1.0, -1.0, hh, hh, px, py, 3)
+        errs.append(np.abs(q - np.exp(np.sin(np.pi*px))*np.cos(np.pi*py)).max())
+    rate = np.log2(errs[0]/errs[1]), np.log2(errs[1]/errs[2])
+    assert 3.7 < rate[0] < 4.4 and 3.7 < rate[1] < 4.4, (errs, rate)
